@@ -1,0 +1,560 @@
+// Hardware probe for the sm_100a primitives the implicit-GEMM conv kernels rely on.
+// Not part of the product: it pins down (on a real B200) the descriptor semantics that are not
+// testable in the CPU container:
+//   * canonical K-major SWIZZLE_32B/64B/128B operands (bf16), N = 80 / 160 tiles
+//   * A-operand start addresses shifted by an arbitrary number of rows inside a swizzled tile
+//   * MN-major operands with overlapping atoms (the wgrad "tap folding" trick)
+//   * non-swizzled "planar" K-major layout with SBO = 128 B
+//   * accumulator column placement in TMEM
+//   * TMA 5-D tiled loads with negative / out-of-range coordinates and swizzle
+// Usage: probe_tcgen05 all | probe_tcgen05 <test-name>
+// Every test runs in its own process (a faulting descriptor kills the CUDA context).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../vnet_tensorflow_b200/csrc/sm100_ptx.cuh"
+
+using namespace sm100;
+
+#define CK(x)                                                                              \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess) {                                                               \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);      \
+      exit(2);                                                                             \
+    }                                                                                      \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// host bf16 helpers
+// ---------------------------------------------------------------------------------------------
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  uint32_t r = u + 0x7FFF + ((u >> 16) & 1);
+  return static_cast<uint16_t>(r >> 16);
+}
+static float bf2f(uint16_t h) {
+  uint32_t u = static_cast<uint32_t>(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static uint32_t rng_state = 12345u;
+static uint32_t rnd() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return rng_state >> 8;
+}
+// small integers / quarter steps -> every product and partial sum is exact in fp32
+static float rnd_val() { return static_cast<float>(static_cast<int>(rnd() % 9) - 4) * 0.5f; }
+
+static uint32_t swz(uint32_t off, int mode) {
+  switch (mode) {
+    case 128: return off ^ (((off >> 7) & 7u) << 4);
+    case 64: return off ^ (((off >> 7) & 3u) << 4);
+    case 32: return off ^ (((off >> 7) & 1u) << 4);
+    default: return off;
+  }
+}
+static uint32_t layout_code(int mode) {
+  return mode == 128 ? SWZ_128B : mode == 64 ? SWZ_64B : mode == 32 ? SWZ_32B : SWZ_NONE;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device: MMA script interpreter
+// ---------------------------------------------------------------------------------------------
+struct MmaOp {
+  uint64_t adesc;  // start address relative to the 1024-aligned smem base
+  uint64_t bdesc;
+  uint32_t idesc;
+  uint32_t dcol;
+  uint32_t accum;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(128, 1)
+    mma_probe(const uint4* __restrict__ img, uint32_t img_bytes, const MmaOp* __restrict__ ops,
+              int nops, float* __restrict__ dout, int ncols, int* __restrict__ status) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  for (uint32_t i = tid; i < img_bytes / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = img[i];
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  if (tid == 32) {
+    mbar_init(smem_u32(&mbar), 1);
+    fence_mbar_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    for (int i = 0; i < nops; ++i) {
+      MmaOp op = ops[i];
+      uint64_t ad = op.adesc + static_cast<uint64_t>(base >> 4);
+      uint64_t bd = op.bdesc + static_cast<uint64_t>(base >> 4);
+      mma_f16_ss(tmem + op.dcol, ad, bd, op.idesc, op.accum);
+    }
+    mma_commit(smem_u32(&mbar));
+  }
+  __syncwarp();
+  bool ok = mbar_wait_bounded(smem_u32(&mbar), 0, 1u << 22);
+  if (!ok && tid == 0) status[0] = 1;
+  tc_fence_after_sync();
+  if (ok) {
+    for (int c = 0; c < ncols; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c, r);
+      tmem_ld_wait();
+      for (int j = 0; j < 16; ++j)
+        if (c + j < ncols) dout[(warp * 32 + lane) * ncols + c + j] = __uint_as_float(r[j]);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device: TMA probe (one 5-D tiled load, dump the shared-memory image)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+    tma_probe(const __grid_constant__ CUtensorMap tmap, int c0, int c1, int c2, int c3, int c4,
+              uint32_t bytes, uint8_t* __restrict__ out, int* __restrict__ status) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t mbar;
+  const int tid = threadIdx.x;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  for (uint32_t i = tid; i < bytes; i += 128) sm[i] = 0xCD;
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(smem_u32(&mbar), 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(smem_u32(&mbar), bytes);
+    tma_load_5d(base, &tmap, smem_u32(&mbar), c0, c1, c2, c3, c4);
+  }
+  bool ok = mbar_wait_bounded(smem_u32(&mbar), 0, 1u << 22);
+  if (!ok && tid == 0) status[0] = 1;
+  __syncthreads();
+  for (uint32_t i = tid; i < bytes; i += 128) out[i] = sm[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: test harness
+// ---------------------------------------------------------------------------------------------
+struct Mat {  // logical bf16 matrix, row-major [rows][cols]
+  int rows, cols;
+  std::vector<float> v;
+  Mat(int r, int c) : rows(r), cols(c), v(static_cast<size_t>(r) * c) {
+    for (auto& x : v) x = rnd_val();
+  }
+  float at(int r, int c) const { return v[static_cast<size_t>(r) * cols + c]; }
+};
+
+// place matrix X as rows of `cols` bf16 (row pitch = cols*2 bytes) at region `off`, swizzled
+static void put_rows(std::vector<uint8_t>& img, uint32_t off, const Mat& X, int mode) {
+  const uint32_t rb = X.cols * 2;
+  for (int r = 0; r < X.rows; ++r)
+    for (int c = 0; c < X.cols; ++c) {
+      uint32_t o = swz(off + r * rb + c * 2, mode);
+      uint16_t h = f2bf(X.at(r, c));
+      if (o + 2 > img.size()) img.resize(o + 2, 0);
+      memcpy(&img[o], &h, 2);
+    }
+}
+// planar non-swizzled layout: [cols/8 planes][rows][8 elements = 16 B]
+static void put_planar(std::vector<uint8_t>& img, uint32_t off, const Mat& X, uint32_t plane_stride) {
+  for (int r = 0; r < X.rows; ++r)
+    for (int c = 0; c < X.cols; ++c) {
+      uint32_t o = off + (c / 8) * plane_stride + r * 16 + (c % 8) * 2;
+      uint16_t h = f2bf(X.at(r, c));
+      if (o + 2 > img.size()) img.resize(o + 2, 0);
+      memcpy(&img[o], &h, 2);
+    }
+}
+
+static int run_mma(const std::vector<uint8_t>& img_in, const std::vector<MmaOp>& ops, int ncols,
+                   const std::vector<float>& expect /*[128][ncols]*/, const char* name) {
+  std::vector<uint8_t> img = img_in;
+  img.resize((img.size() + 1023) / 1024 * 1024 + 4096, 0);
+  uint4* dimg;
+  MmaOp* dops;
+  float* dout;
+  int* dstat;
+  CK(cudaMalloc(&dimg, img.size()));
+  CK(cudaMalloc(&dops, ops.size() * sizeof(MmaOp)));
+  CK(cudaMalloc(&dout, 128 * ncols * sizeof(float)));
+  CK(cudaMalloc(&dstat, sizeof(int)));
+  CK(cudaMemcpy(dimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dops, ops.data(), ops.size() * sizeof(MmaOp), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0xFF, 128 * ncols * sizeof(float)));
+  CK(cudaMemset(dstat, 0, sizeof(int)));
+  size_t smem = img.size() + 1024;
+  CK(cudaFuncSetAttribute(mma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mma_probe<<<1, 128, smem>>>(dimg, (uint32_t)img.size(), dops, (int)ops.size(), dout, ncols, dstat);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("RESULT %-28s FAULT (%s)\n", name, cudaGetErrorString(e));
+    return 1;
+  }
+  int stat = 0;
+  std::vector<float> out(128 * ncols);
+  CK(cudaMemcpy(&stat, dstat, sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out.data(), dout, out.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  if (stat) {
+    printf("RESULT %-28s TIMEOUT (mbarrier never completed)\n", name);
+    return 1;
+  }
+  int bad = 0;
+  double maxd = 0;
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < ncols; ++n) {
+      float a = out[m * ncols + n], b = expect[m * ncols + n];
+      double d = fabs((double)a - (double)b);
+      if (!(d <= 1e-3)) {
+        if (bad < 6) printf("   mismatch %s [m=%d n=%d] got %g want %g\n", name, m, n, a, b);
+        ++bad;
+      }
+      if (d > maxd) maxd = d;
+    }
+  printf("RESULT %-28s %s  mismatches=%d/%d maxdiff=%g\n", name, bad ? "FAIL" : "PASS", bad,
+         128 * ncols, maxd);
+  return bad ? 1 : 0;
+}
+
+// D[m][n] = sum_k A(m,k) * B(n,k) with bf16-rounded inputs
+template <class FA, class FB>
+static std::vector<float> gemm_ref(int N, int K, int ncols, int dcol, FA a, FB b,
+                                   std::vector<float>* into = nullptr) {
+  std::vector<float> d = into ? *into : std::vector<float>(128 * ncols, 0.f);
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < N; ++n) {
+      float s = 0;
+      for (int k = 0; k < K; ++k) s += bf2f(f2bf(a(m, k))) * bf2f(f2bf(b(n, k)));
+      d[m * ncols + dcol + n] = s;
+    }
+  return d;
+}
+
+// ---- individual tests -----------------------------------------------------------------------
+static int test_k_sw(int mode, int N) {  // canonical K-major, row bytes == swizzle span
+  const int K = mode / 2;
+  Mat A(128, K), B(N, K);
+  std::vector<uint8_t> img;
+  const uint32_t offB = 128 * mode;
+  put_rows(img, 0, A, mode);
+  put_rows(img, offB, B, mode);
+  std::vector<MmaOp> ops;
+  for (int j = 0; j < K / 16; ++j)
+    ops.push_back({make_smem_desc(32 * j, 16, 8 * mode, layout_code(mode)),
+                   make_smem_desc(offB + 32 * j, 16, 8 * mode, layout_code(mode)),
+                   make_instr_desc(128, N, FMT_BF16), 0, (uint32_t)(j > 0), 0});
+  auto ex = gemm_ref(N, K, N, 0, [&](int m, int k) { return A.at(m, k); },
+                     [&](int n, int k) { return B.at(n, k); });
+  char nm[64];
+  snprintf(nm, sizeof nm, "k_sw%d_n%d", mode, N);
+  return run_mma(img, ops, N, ex, nm);
+}
+
+static int test_shift(int mode, int s, int use_base_offset) {  // A start shifted by s rows
+  const int K = mode / 2, N = 16, R = 160;
+  Mat A(R, K), B(N, K);
+  std::vector<uint8_t> img;
+  const uint32_t offB = ((R * mode + 1023) / 1024) * 1024;
+  put_rows(img, 0, A, mode);
+  put_rows(img, offB, B, mode);
+  std::vector<MmaOp> ops;
+  const uint32_t start = s * mode;
+  const uint32_t bo = use_base_offset ? ((start >> 7) & 7u) : 0u;
+  for (int j = 0; j < K / 16; ++j)
+    ops.push_back({make_smem_desc(start + 32 * j, 16, 8 * mode, layout_code(mode), bo),
+                   make_smem_desc(offB + 32 * j, 16, 8 * mode, layout_code(mode)),
+                   make_instr_desc(128, N, FMT_BF16), 0, (uint32_t)(j > 0), 0});
+  auto ex = gemm_ref(N, K, N, 0, [&](int m, int k) { return A.at(m + s, k); },
+                     [&](int n, int k) { return B.at(n, k); });
+  char nm[64];
+  snprintf(nm, sizeof nm, "shift_sw%d_s%d_bo%d", mode, s, use_base_offset);
+  return run_mma(img, ops, N, ex, nm);
+}
+
+static int test_planar(int s) {  // non-swizzled K-major, rows at 16 B pitch (SBO = 128)
+  const int K = 16, N = 80, R = 160;
+  Mat A(R, K), B(N, K);
+  std::vector<uint8_t> img;
+  const uint32_t psA = R * 16, offB = 2 * psA, psB = N * 16;
+  put_planar(img, 0, A, psA);
+  put_planar(img, offB, B, psB);
+  std::vector<MmaOp> ops;
+  ops.push_back({make_smem_desc(s * 16, psA, 128, SWZ_NONE), make_smem_desc(offB, psB, 128, SWZ_NONE),
+                 make_instr_desc(128, N, FMT_BF16), 0, 0, 0});
+  auto ex = gemm_ref(N, K, N, 0, [&](int m, int k) { return A.at(m + s, k); },
+                     [&](int n, int k) { return B.at(n, k); });
+  char nm[64];
+  snprintf(nm, sizeof nm, "planar_none_s%d", s);
+  return run_mma(img, ops, N, ex, nm);
+}
+
+static int test_mn_canon() {  // canonical MN-major: A SW128 (2 MN atoms x 2 K atoms), B SW32
+  const int K = 16, N = 16;
+  Mat At(128, K), Bt(N, K);  // logical A[m][k], B[n][k]
+  std::vector<uint8_t> img;
+  // A: atom(mn_i, k_j) at (mn_i + 2*k_j)*1024; inside: row = k%8 (128 B pitch), col = (m%64)*2
+  for (int m = 0; m < 128; ++m)
+    for (int k = 0; k < K; ++k) {
+      uint32_t o = swz(((m / 64) + 2 * (k / 8)) * 1024 + (k % 8) * 128 + (m % 64) * 2, 128);
+      uint16_t h = f2bf(At.at(m, k));
+      if (o + 2 > img.size()) img.resize(o + 2, 0);
+      memcpy(&img[o], &h, 2);
+    }
+  const uint32_t offB = 4096;
+  // B: SW32 MN-major, one MN atom (16 n), K rows at 32 B pitch, 8-row groups at 256 B
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      uint32_t o = swz(offB + k * 32 + n * 2, 32);
+      uint16_t h = f2bf(Bt.at(n, k));
+      if (o + 2 > img.size()) img.resize(o + 2, 0);
+      memcpy(&img[o], &h, 2);
+    }
+  std::vector<MmaOp> ops;
+  ops.push_back({make_smem_desc(0, 1024, 2048, SWZ_128B), make_smem_desc(offB, 32, 256, SWZ_32B),
+                 make_instr_desc(128, N, FMT_BF16, 1, 1), 0, 0, 0});
+  auto ex = gemm_ref(N, K, N, 0, [&](int m, int k) { return At.at(m, k); },
+                     [&](int n, int k) { return Bt.at(n, k); });
+  return run_mma(img, ops, N, ex, "mn_canon_sw128A_sw32B");
+}
+
+// wgrad-style folding: X image [voxel rows][16 ch] (32 B rows, SW32). A^T atoms j = 0..7 are the
+// same rows shifted by j voxels (LBO = 32 B). B = dY image [rows][16 co], `nb` atoms at LBO = lineB.
+static int test_mn_fold(int nb, int k0) {
+  const int K = 16, C = 16, R = 192;
+  const int lineRows = 32;
+  Mat X(R, C), Y(R, C);
+  std::vector<uint8_t> img;
+  const uint32_t offY = ((R * 32 + 1023) / 1024) * 1024;
+  put_rows(img, 0, X, 32);
+  put_rows(img, offY, Y, 32);
+  const int N = 16 * nb;
+  std::vector<MmaOp> ops;
+  ops.push_back({make_smem_desc(k0 * 32, 32, 256, SWZ_32B),
+                 make_smem_desc(offY + k0 * 32, lineRows * 32, 256, SWZ_32B),
+                 make_instr_desc(128, N, FMT_BF16, 1, 1), 0, 0, 0});
+  // D[(j,ci)][(l,co)] = sum_k X[k0+k+j][ci] * Y[k0+k+l*lineRows][co]
+  auto ex = gemm_ref(N, K, N, 0,
+                     [&](int m, int k) { return X.at(k0 + k + m / 16, m % 16); },
+                     [&](int n, int k) { return Y.at(k0 + k + (n / 16) * lineRows, n % 16); });
+  char nm[64];
+  snprintf(nm, sizeof nm, "mn_fold_nb%d_k%d", nb, k0);
+  return run_mma(img, ops, N, ex, nm);
+}
+
+static int test_dcol(int stride) {  // several N=80 accumulators at column stride `stride`
+  const int mode = 32, K = 16, N = 80;
+  Mat A(128, K), B0(N, K), B1(N, K), B2(N, K);
+  std::vector<uint8_t> img;
+  put_rows(img, 0, A, mode);
+  put_rows(img, 4096, B0, mode);
+  put_rows(img, 8192, B1, mode);
+  put_rows(img, 12288, B2, mode);
+  std::vector<MmaOp> ops;
+  const Mat* Bs[3] = {&B0, &B1, &B2};
+  const int ncols = 2 * stride + N;
+  std::vector<float> ex(128 * ncols, 0.f);
+  for (int t = 0; t < 3; ++t) {
+    ops.push_back({make_smem_desc(0, 16, 256, SWZ_32B), make_smem_desc(4096 * (t + 1), 16, 256, SWZ_32B),
+                   make_instr_desc(128, N, FMT_BF16), (uint32_t)(t * stride), 0, 0});
+    const Mat* Bp = Bs[t];
+    ex = gemm_ref(N, K, ncols, t * stride, [&](int m, int k) { return A.at(m, k); },
+                  [&](int n, int k) { return Bp->at(n, k); }, &ex);
+  }
+  // columns between accumulators are unspecified: only compare the written ranges
+  std::vector<float> exm = ex;
+  char nm[64];
+  snprintf(nm, sizeof nm, "dcol_stride%d", stride);
+  // run, then mask unspecified columns by copying device values: do it by widening tolerance:
+  // simplest: zero-initialised gaps are not guaranteed, so fill gaps via a 4th MMA-free check below
+  if (stride != N) {
+    // fill the gaps with accumulate=0 MMAs of a zero B so the expectation (0) is well defined
+    Mat Z(16, K);
+    for (auto& x : Z.v) x = 0.f;
+    put_rows(img, 16384, Z, mode);
+    for (int t = 0; t < 2; ++t)
+      for (int c = t * stride + N; c < (t + 1) * stride; c += 16)
+        ops.push_back({make_smem_desc(0, 16, 256, SWZ_32B), make_smem_desc(16384, 16, 256, SWZ_32B),
+                       make_instr_desc(128, 16, FMT_BF16), (uint32_t)c, 0, 0});
+  }
+  return run_mma(img, ops, ncols, exm, nm);
+}
+
+// ---- TMA -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn) {
+    printf("cuTensorMapEncodeTiled not found\n");
+    exit(2);
+  }
+  return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// tensor [N][D][H][W][C] bf16; box (bc, bw, bh, bd, 1) at coords (c0, w0, h0, d0, 0)
+static int test_tma(const char* name, int D, int H, int W, int C, int bc, int bw, int bh, int bd,
+                    int c0, int w0, int h0, int d0, int mode) {
+  const size_t n = (size_t)D * H * W * C;
+  std::vector<uint16_t> t(n);
+  for (size_t i = 0; i < n; ++i) t[i] = static_cast<uint16_t>(0x1000 + (i * 7919u) % 0x6000);
+  uint16_t* dt;
+  CK(cudaMalloc(&dt, n * 2));
+  CK(cudaMemcpy(dt, t.data(), n * 2, cudaMemcpyHostToDevice));
+  CUtensorMap tm;
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, 1};
+  cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                        (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = mode == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : mode == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : mode == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                       : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = get_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, dt, gdim, gstr, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    printf("RESULT %-28s ENCODE_FAIL (%d)\n", name, (int)r);
+    return 1;
+  }
+  const uint32_t bytes = (uint32_t)bc * bw * bh * bd * 2;
+  uint8_t* dout;
+  int* dstat;
+  CK(cudaMalloc(&dout, bytes));
+  CK(cudaMalloc(&dstat, 4));
+  CK(cudaMemset(dstat, 0, 4));
+  size_t smem = bytes + 2048;
+  CK(cudaFuncSetAttribute(tma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tma_probe<<<1, 128, smem>>>(tm, c0, w0, h0, d0, 0, bytes, dout, dstat);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("RESULT %-28s FAULT (%s)\n", name, cudaGetErrorString(e));
+    return 1;
+  }
+  int stat;
+  CK(cudaMemcpy(&stat, dstat, 4, cudaMemcpyDeviceToHost));
+  if (stat) {
+    printf("RESULT %-28s TIMEOUT\n", name);
+    return 1;
+  }
+  std::vector<uint8_t> out(bytes), ex(bytes, 0);
+  CK(cudaMemcpy(out.data(), dout, bytes, cudaMemcpyDeviceToHost));
+  for (int d = 0; d < bd; ++d)
+    for (int h = 0; h < bh; ++h)
+      for (int w = 0; w < bw; ++w)
+        for (int c = 0; c < bc; ++c) {
+          int gd = d0 + d, gh = h0 + h, gw = w0 + w, gc = c0 + c;
+          uint16_t v = 0;
+          if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W && gc >= 0 && gc < C)
+            v = t[(((size_t)gd * H + gh) * W + gw) * C + gc];
+          uint32_t o = swz(((((uint32_t)d * bh + h) * bw + w) * bc + c) * 2, mode);
+          memcpy(&ex[o], &v, 2);
+        }
+  int bad = 0;
+  for (uint32_t i = 0; i < bytes; ++i)
+    if (out[i] != ex[i]) {
+      if (bad < 6) printf("   mismatch %s byte %u got %02x want %02x\n", name, i, out[i], ex[i]);
+      ++bad;
+    }
+  printf("RESULT %-28s %s  mismatching bytes=%d/%u\n", name, bad ? "FAIL" : "PASS", bad, bytes);
+  return bad ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct TestEntry {
+  const char* name;
+  int (*fn)();
+};
+static const TestEntry kTests[] = {
+    {"k_sw128_n80", [] { return test_k_sw(128, 80); }},
+    {"k_sw64_n160", [] { return test_k_sw(64, 160); }},
+    {"k_sw32_n80", [] { return test_k_sw(32, 80); }},
+    {"k_sw32_n16", [] { return test_k_sw(32, 16); }},
+    {"k_sw128_n256", [] { return test_k_sw(128, 256); }},
+    {"shift_sw128_s1_bo0", [] { return test_shift(128, 1, 0); }},
+    {"shift_sw128_s1_bo1", [] { return test_shift(128, 1, 1); }},
+    {"shift_sw128_s3_bo0", [] { return test_shift(128, 3, 0); }},
+    {"shift_sw128_s3_bo1", [] { return test_shift(128, 3, 1); }},
+    {"shift_sw128_s8_bo0", [] { return test_shift(128, 8, 0); }},
+    {"shift_sw128_s13_bo0", [] { return test_shift(128, 13, 0); }},
+    {"shift_sw64_s1_bo0", [] { return test_shift(64, 1, 0); }},
+    {"shift_sw64_s3_bo0", [] { return test_shift(64, 3, 0); }},
+    {"shift_sw64_s3_bo1", [] { return test_shift(64, 3, 1); }},
+    {"shift_sw32_s1_bo0", [] { return test_shift(32, 1, 0); }},
+    {"shift_sw32_s2_bo0", [] { return test_shift(32, 2, 0); }},
+    {"shift_sw32_s3_bo0", [] { return test_shift(32, 3, 0); }},
+    {"shift_sw32_s4_bo0", [] { return test_shift(32, 4, 0); }},
+    {"shift_sw32_s5_bo1", [] { return test_shift(32, 5, 1); }},
+    {"planar_none_s0", [] { return test_planar(0); }},
+    {"planar_none_s3", [] { return test_planar(3); }},
+    {"mn_canon", [] { return test_mn_canon(); }},
+    {"mn_fold_nb1_k0", [] { return test_mn_fold(1, 0); }},
+    {"mn_fold_nb1_k16", [] { return test_mn_fold(1, 16); }},
+    {"mn_fold_nb5_k0", [] { return test_mn_fold(5, 0); }},
+    {"mn_fold_nb5_k8", [] { return test_mn_fold(5, 8); }},
+    {"dcol_stride80", [] { return test_dcol(80); }},
+    {"dcol_stride96", [] { return test_dcol(96); }},
+    {"tma_sw32_oob", [] { return test_tma("tma_sw32_oob", 3, 5, 12, 16, 16, 8, 3, 2, 0, -2, -1, 1, 32); }},
+    {"tma_sw32_hi", [] { return test_tma("tma_sw32_hi", 3, 5, 12, 16, 16, 8, 3, 2, 0, 8, 3, 2, 32); }},
+    {"tma_sw64", [] { return test_tma("tma_sw64", 2, 4, 10, 32, 32, 8, 2, 2, 0, -1, 0, 0, 64); }},
+    {"tma_sw128", [] { return test_tma("tma_sw128", 2, 3, 10, 64, 64, 8, 2, 1, 0, 3, 2, 1, 128); }},
+    {"tma_sw128_c128", [] { return test_tma("tma_sw128_c128", 2, 3, 10, 128, 64, 8, 2, 1, 64, -1, 0, 0, 128); }},
+    {"tma_none_16B", [] { return test_tma("tma_none_16B", 3, 5, 12, 16, 8, 8, 3, 2, 8, -2, -1, 1, 0); }},
+    {"tma_sw32_128rows", [] { return test_tma("tma_sw32_128rows", 2, 6, 128, 16, 16, 128, 3, 1, 0, 0, -2, 1, 32); }},
+};
+
+int main(int argc, char** argv) {
+  if (argc < 2) {
+    printf("usage: %s all|<test>\n", argv[0]);
+    return 2;
+  }
+  std::string which = argv[1];
+  if (which == "all") {
+    int fails = 0;
+    for (const auto& t : kTests) {
+      std::string cmd = std::string("timeout 120 ") + argv[0] + " " + t.name;
+      fflush(stdout);
+      int rc = system(cmd.c_str());
+      if (rc != 0) ++fails;
+    }
+    printf("PROBE SUMMARY: %d of %zu tests did not pass\n", fails, sizeof(kTests) / sizeof(kTests[0]));
+    return 0;
+  }
+  for (const auto& t : kTests)
+    if (which == t.name) {
+      int rc = t.fn();
+      fflush(stdout);
+      return rc;
+    }
+  printf("unknown test %s\n", which.c_str());
+  return 2;
+}
