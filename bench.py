@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the V-Net training hot path (BASELINE.json metric: patches/sec, 128^3, 1ch -> 2cls).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+One "step" = one optimiser step (forward + weighted Dice + backward + Adam [+ gradient all-reduce])
+over one batch of synthetic patches.  N>1 is launched by torchrun (one rank per GPU, NCCL); whole
+patches are sharded over ranks (weak scaling: per-GPU batch fixed).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TRAIN_GFLOP_PER_PATCH_128 = 3371.7   # BASELINE.md §2 (fprop + dgrad + wgrad, 128^3, M=1, K=2)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--patch", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=2, help="patches per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("VNB_BENCH_PRECISION", "bf16x3"),
+                    choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def train_gflop_per_patch(patch: int) -> float:
+    return TRAIN_GFLOP_PER_PATCH_128 * (patch / 128.0) ** 3
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p["bf16_tflops_sustained"], "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference leg (oracle port of the reference's TF1 graph; TensorFlow itself cannot run here)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step_seconds(sample_patch: int, repeats: int, warmup: int):
+    import torch
+    from oracle import ref_vnet as R
+    from vnet_tensorflow_b200.synthetic import synth_batch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = R.VNetSpec(num_classes=2, in_channels=1)
+    state = R.TrainState(params=R.init_params(spec, 42))
+    times = []
+    for i in range(warmup + repeats):
+        img, lab = synth_batch(i, 1, sample_patch, 1, 2)
+        t0 = time.perf_counter()
+        R.train_step(state, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, cores
+
+
+def cpu_baseline(patch: int):
+    """Bounded sample: one 64^3 (or 32^3) training step of the same network on all host cores, scaled
+    to `patch`^3 units by the voxel ratio (the conv stack's work is linear in voxels)."""
+    sample = 64 if patch >= 64 else patch
+    times, cores = cpu_reference_step_seconds(sample, 1, 1)
+    t = float(np.median(times))
+    scale = (sample / patch) ** 3
+    return {"value": scale / t, "unit": "patches/sec", "cores": cores, "kind": "port",
+            "sample": "1 optimiser step on one %d^3 patch (fwd+Dice+bwd+Adam, torch-CPU oracle, %d threads), %.2f s, "
+                      "scaled by (%d/%d)^3 voxels" % (sample, cores, t, sample, patch)}
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    sample = 64 if args.patch >= 64 else args.patch
+    steps = max(1, min(args.steps, 8))        # bounded: each step is a ~seconds-long CPU training step
+    warm = max(1, min(args.warmup, 2))
+    times, cores = cpu_reference_step_seconds(sample, steps, warm)
+    t = float(np.mean(times))
+    scale = (sample / args.patch) ** 3
+    value = scale / t
+    line = {
+        "impl": "reference", "metric": "patches/sec (128^3, 1ch->2cls) training step", "value": value,
+        "unit": "patches/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t / scale, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "V-Net 3D train step, %d^3 patch, 1 modality, 2 classes, weighted_sorensen, Adam" % args.patch,
+                   "patch": args.patch, "batch_per_gpu": args.batch, "timed_steps": steps, "timed_warmup": warm},
+        "cpu_baseline": {"value": value, "unit": "patches/sec", "cores": cores, "kind": "port",
+                         "sample": "%d timed optimiser steps on one %d^3 patch each (TF1-semantics CPU restatement on "
+                                   "PyTorch/oneDNN, %d threads), scaled by voxel count to %d^3" % (steps, sample, cores, args.patch)},
+        "e2e": {"value": value, "unit": "patches/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+def run_b200(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from vnet_tensorflow_b200.init import initialize
+    from vnet_tensorflow_b200.engine import VNetEngine
+    from vnet_tensorflow_b200.synthetic import synth_batch
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    P, B = args.patch, args.batch
+    eng = VNetEngine(num_classes=2, in_channels=1, patch_shape=(P, P, P), max_batch=B, precision=args.precision,
+                     loss="weighted_sorensen", loss_weights=(0.1, 1.0), optimizer="Adam", learning_rate=1e-2,
+                     decay_factor=0.99, decay_steps=100.0, device=local_rank)
+    initialize(eng, 42)
+    if world > 1:
+        uid = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(rank, world, uid[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        eng.sync()
+
+    # synthetic batches in pinned host memory (one per step so the e2e leg really moves new data)
+    nb = min(args.steps + args.warmup, 4)
+    pinned = []
+    for i in range(nb):
+        img, lab = synth_batch(i, B, P, 1, 2, rank=rank)
+        ti = torch.from_numpy(img).pin_memory()
+        tl = torch.from_numpy(lab).pin_memory()
+        pinned.append((ti, tl, ti.numpy(), tl.numpy()))
+    dropout = 0.01  # configs/*.json Networks.Dropout
+
+    # ---- leg 1: device-resident inputs ("value") ------------------------------------------------
+    eng.upload_batch(pinned[0][2], pinned[0][3])
+    for i in range(args.warmup):
+        eng.train_step_resident(B, dropout, seed=i)
+    barrier()
+    l0 = eng.gpu_launches()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.event_record(0)
+    for i in range(args.steps):
+        eng.train_step_resident(B, dropout, seed=100 + i)
+    eng.event_record(1)
+    barrier()
+    ms_dev = eng.event_elapsed_ms()
+    clocks = sampler.stop()
+    launches = eng.gpu_launches() - l0
+
+    # ---- leg 2: end to end through the public API with host buffers ("e2e") ---------------------
+    for i in range(min(args.warmup, 2)):
+        eng.train_step(pinned[i % nb][2], pinned[i % nb][3], dropout, seed=i)
+    barrier()
+    t0 = time.perf_counter()
+    eng.event_record(0)
+    loss = None
+    for i in range(args.steps):
+        loss = eng.train_step(pinned[i % nb][2], pinned[i % nb][3], dropout, seed=200 + i, want_loss=True)
+    eng.event_record(1)
+    barrier()
+    ms_e2e = max(eng.event_elapsed_ms(), 0.0)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(ms_e2e, wall_e2e)  # host-side copies/readbacks are part of the end-to-end time
+
+    # ---- dominant-kernel roofline: CUDA events around every 5^3 convolution launch ---------------
+    eng.profile_enable(True)
+    prof_steps = min(args.steps, 3)
+    for i in range(prof_steps):
+        eng.train_step_resident(B, dropout, seed=300 + i)
+    conv_ms, conv_n, conv_fl = eng.profile_read(0)
+    wg_ms, wg_n, wg_fl = eng.profile_read(1)
+    eng.profile_enable(False)
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = measured_peaks()
+        patches = B * world * args.steps
+        value = patches / (ms_dev / 1e3)
+        e2e_val = patches / (ms_e2e / 1e3)
+        img_bytes = B * P ** 3 * 4
+        lab_bytes = B * P ** 3 * 4
+        conv_tflops = (conv_fl + wg_fl) / ((conv_ms + wg_ms) * 1e-3) / 1e12 if conv_ms + wg_ms > 0 else 0.0
+        step_tflops = value * train_gflop_per_patch(P) / 1e3 / world
+        line = {
+            "metric": "patches/sec (128^3, 1ch->2cls) training step", "value": value, "unit": "patches/sec",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (fp32-grade split, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "V-Net 3D train step (fwd + weighted Dice + bwd + Adam%s), %d^3 patch, 1 modality, 2 classes, "
+                                   "batch %d per GPU (BASELINE configs[1])" % (" + ring all-reduce" if world > 1 else "", P, B),
+                       "patch": P, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "precision": args.precision, "dropout": dropout,
+                       "l2": "per-step working set (activations %.1f GB) >> 126 MB L2, no explicit flush" % (0.7 * 3 * B * (P / 128) ** 3)},
+            "e2e": {"value": e2e_val, "unit": "patches/sec", "h2d_bytes_per_step": img_bytes + lab_bytes,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                         "frac": conv_tflops / peaks["tflops"], "traffic": None,
+                         "kernel": "5x5x5 convolution kernels (fprop+dgrad+wgrad), %d launches over %d profiled steps, "
+                                   "CUDA events on the engine stream" % (conv_n + wg_n, prof_steps),
+                         "fprop_dgrad_tflops": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
+                         "wgrad_tflops": wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else 0.0,
+                         "conv_share_of_step": (conv_ms + wg_ms) / prof_steps / (ms_dev / args.steps),
+                         "whole_step_tflops_per_gpu": step_tflops, "peak_source": peaks["source"] + " (cuBLAS bf16 sustained)"},
+            "final_loss": loss,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(P)
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+/* vnet_b200.h -- C ABI of libvnet_b200.so, the B200-native V-Net engine.
+ *
+ * The reference (jackyko1991/vnet-tensorflow) has no FFI seam: its hot path is whatever
+ * `sess.run(...)` executes inside TensorFlow.  This ABI is the seam a maintainer binds instead
+ * (ctypes stub: INTEGRATION.md).  Each entry point names the reference interface it replaces
+ * (paths relative to the reference tree):
+ *
+ *   vnb_create            networks.VNet(...).GetNetwork + build_model_graph     networks.py:209-305, model.py:297-630
+ *   vnb_set/get_param     tf.train.Saver restore/save by variable name          model.py:689-699,758-764
+ *   vnb_forward           sess.run(['predicted_label/prediction:0','softmax:0']) model.py:914-917
+ *   vnb_loss              sess.run([summary_op, loss_op]) test step             model.py:784-789
+ *   vnb_train_step        sess.run([train_op, summary_op, loss_op])             model.py:743-748
+ *   vnb_forward_backward  the gradient half of optimizer.minimize               model.py:660
+ *   vnb_apply_gradients   the apply half of optimizer.minimize (+ lr decay)     model.py:641-660
+ *   vnb_comm_*            (absent in the reference: single device)              SURVEY.md 2.1
+ *
+ * Conventions
+ *   - All tensors cross the boundary as caller-owned, C-contiguous host buffers in the reference's
+ *     layouts: images float32 [N,X,Y,Z,M], labels int32 [N,X,Y,Z] (class indices), logits/softmax
+ *     float32 [N,X,Y,Z,K], argmax int64 [N,X,Y,Z]; conv filters [kd,kh,kw,Cin,Cout], transposed-conv
+ *     filters [kd,kh,kw,Cout,Cin] (layers2.py:60,66,92).
+ *   - The library owns all device memory behind the opaque handle (allocated once for max_batch).
+ *   - Every call returns VNB_OK (0) or a negative vnb_status; nothing throws across the boundary;
+ *     the message is available from vnb_last_error() (thread local).
+ *   - One handle <-> one GPU <-> one host thread.  Data parallelism = one process per GPU.
+ *   - There is no CPU fallback: vnb_create fails with VNB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef VNET_B200_H
+#define VNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vnb_handle vnb_handle;
+
+typedef enum vnb_status {
+  VNB_OK = 0,
+  VNB_ERR_INVALID_ARG = -1,
+  VNB_ERR_SHAPE = -2,
+  VNB_ERR_CUDA = -3,
+  VNB_ERR_NCCL = -4,
+  VNB_ERR_OOM = -5,
+  VNB_ERR_UNSUPPORTED = -6,
+  VNB_ERR_INTERNAL = -7
+} vnb_status;
+
+/* TrainingSetting.Precision (new optional config key) */
+enum { VNB_PREC_FP32 = 0, /* fp32 FMA on CUDA cores, exact-precision parity mode            */
+       VNB_PREC_BF16X3 = 1, /* tcgen05 bf16 split (hi/lo) x3, fp32 accumulate: fp32-grade      */
+       VNB_PREC_BF16 = 2 }; /* tcgen05 bf16, fp32 accumulate                                    */
+
+/* TrainingSetting.Loss.Name (model.py:495-560), same order as the reference's if-chain */
+enum { VNB_LOSS_XENT = 0, VNB_LOSS_WEIGHTED_XENT, VNB_LOSS_SORENSEN, VNB_LOSS_WEIGHTED_SORENSEN,
+       VNB_LOSS_JACCARD, VNB_LOSS_WEIGHTED_JACCARD, VNB_LOSS_MIXED_SORENSEN,
+       VNB_LOSS_MIXED_WEIGHTED_SORENSEN, VNB_LOSS_MIXED_JACCARD, VNB_LOSS_MIXED_WEIGHTED_JACCARD };
+
+/* TrainingSetting.Optimizer.Name (model.py:649-658) */
+enum { VNB_OPT_ADAM = 0, VNB_OPT_SGD = 1 };
+
+/* which per-variable buffer vnb_set_slot / vnb_get_slot address */
+enum { VNB_SLOT_VALUE = 0, VNB_SLOT_GRAD = 1, VNB_SLOT_ADAM_M = 2, VNB_SLOT_ADAM_V = 3 };
+
+typedef struct vnb_config {
+  int32_t in_channels;          /* len(Data.ImageFilenames)            model.py:189 */
+  int32_t num_classes;          /* len(SegmentationClasses)            model.py:190 */
+  int32_t num_channels;         /* Networks.NumChannel                 model.py:212 */
+  int32_t num_levels;           /* Networks.NumLevels                  model.py:213 */
+  int32_t num_convolutions[8];  /* Networks.NumConvolutions            model.py:214 */
+  int32_t bottom_convolutions;  /* Networks.BottomConvolutions         model.py:215 */
+  int32_t patch_shape[3];       /* PatchShape [X,Y,Z]                  model.py:198 */
+  int32_t max_batch;            /* max(BatchSize, Evaluation BatchSize) model.py:197,234 */
+  int32_t precision;            /* VNB_PREC_*                                          */
+  int32_t loss;                 /* VNB_LOSS_*                          model.py:222 */
+  float loss_weights[8];        /* Loss.Weights                        model.py:223 */
+  float loss_alpha;             /* Loss.Alpha                          model.py:224 */
+  int32_t optimizer;            /* VNB_OPT_*                           model.py:217 */
+  float learning_rate;          /* Optimizer.InitialLearningRate       model.py:218 */
+  float decay_factor;           /* Optimizer.Decay.Factor              model.py:219 */
+  float decay_steps;            /* Optimizer.Decay.Steps               model.py:220 */
+} vnb_config;
+
+const char* vnb_last_error(void);
+const char* vnb_version(void);
+
+int vnb_create(const vnb_config* cfg, int device, vnb_handle** out);
+int vnb_destroy(vnb_handle* h);
+
+/* variable inventory, TF names in creation order (vnet/encoder/level_1/conv_1/weights, ...) */
+int vnb_num_params(vnb_handle* h, int* count);
+int vnb_param_info(vnb_handle* h, int index, const char** tf_name, int* ndim, int64_t dims[5], int* trainable);
+int vnb_set_param(vnb_handle* h, const char* tf_name, const void* host, size_t bytes);
+int vnb_get_param(vnb_handle* h, const char* tf_name, void* host, size_t bytes);
+int vnb_set_slot(vnb_handle* h, const char* tf_name, int slot, const void* host, size_t bytes);
+int vnb_get_slot(vnb_handle* h, const char* tf_name, int slot, void* host, size_t bytes);
+int vnb_get_step(vnb_handle* h, int64_t* global_step);
+int vnb_set_step(vnb_handle* h, int64_t global_step);
+
+/* inference: any of logits / softmax / argmax may be NULL */
+int vnb_forward(vnb_handle* h, const float* images, int n, float* logits, float* softmax, int64_t* argmax);
+/* loss without update; dice_terms (optional) receives [n][K][4] = (I, L, R, xent-sum) per sample/class */
+int vnb_loss(vnb_handle* h, const float* images, const int32_t* labels, int n, float* loss_out, double* dice_terms);
+/* one optimiser step; loss_out may be NULL (then the call does not synchronise) */
+int vnb_train_step(vnb_handle* h, const float* images, const int32_t* labels, int n, float dropout_rate,
+                   uint64_t seed, float* loss_out);
+/* gradients only (left in the VNB_SLOT_GRAD buffers), then the apply half */
+int vnb_forward_backward(vnb_handle* h, const float* images, const int32_t* labels, int n, float dropout_rate,
+                         uint64_t seed, int update_moving_stats, float* loss_out);
+int vnb_apply_gradients(vnb_handle* h);
+
+/* data parallel: one process per GPU; rank 0 creates the id and shares it out of band */
+int vnb_comm_unique_id(void* id_out_128_bytes);
+int vnb_comm_init(vnb_handle* h, int rank, int world, const void* unique_id_128_bytes);
+int vnb_comm_world(vnb_handle* h, int* rank, int* world);
+
+/* device-resident stepping (benchmark 'value' leg): upload once, then step on the resident batch */
+int vnb_upload_batch(vnb_handle* h, const float* images, const int32_t* labels, int n);
+int vnb_train_step_resident(vnb_handle* h, int n, float dropout_rate, uint64_t seed);
+/* CUDA-event timing on the handle's compute stream: record event 0 / 1, then read the elapsed ms */
+int vnb_event_record(vnb_handle* h, int which);
+int vnb_event_elapsed_ms(vnb_handle* h, float* ms);
+/* per-kernel-class profiling with CUDA events around every convolution launch (5x5x5 fprop/dgrad/wgrad):
+ * enable, run steps, then read (sum of device ms, launches, algorithmic FLOPs) for class 0 fprop+dgrad, 1 wgrad */
+int vnb_profile_enable(vnb_handle* h, int on);
+int vnb_profile_read(vnb_handle* h, int kernel_class, double* ms, int64_t* launches, double* flops);
+
+int vnb_sync(vnb_handle* h);
+/* number of kernels this handle has launched so far */
+int vnb_gpu_launches(vnb_handle* h, int64_t* count);
+
+/* test / debug hooks ------------------------------------------------------------------------- */
+/* copy an intermediate tensor of the last run: kind 0 activation, 1 its gradient (dL/dz for conv
+ * units after a backward pass), 2 pre-batch-norm conv output; scope = TF scope of the unit */
+int vnb_read_tensor(vnb_handle* h, const char* scope, int kind, float* host, size_t bytes, int n);
+/* standalone 5x5x5 convolution ops on host buffers (NDHWC / [125][Cin][Cout]); precision as VNB_PREC_* */
+int vnb_op_conv5_fprop(int device, int precision, const float* x, const float* w, const float* bias,
+                       const float* residual, float* y, int n, int d, int h, int w_, int cin, int cout);
+int vnb_op_conv5_dgrad(int device, int precision, const float* dy, const float* w, float* dx, int n, int d,
+                       int h, int w_, int cin, int cout);
+int vnb_op_conv5_wgrad(int device, int precision, const float* x, const float* dy, float* dw, int n, int d,
+                       int h, int w_, int cin, int cout);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VNET_B200_H */

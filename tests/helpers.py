@@ -1,0 +1,58 @@
+"""Shared helpers of the test-suite (golden fixtures, engine construction, comparison metrics)."""
+import importlib.util
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLDEN, "make_golden.py"))
+make_golden = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(make_golden)
+CASES = make_golden.CASES
+perturbed_params = make_golden.perturbed_params
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def engine_for(spec, P, N, loss, weights, library, precision="fp32", **kw):
+    from vnet_tensorflow_b200.engine import VNetEngine
+    return VNetEngine(num_classes=spec.num_classes, in_channels=spec.in_channels, patch_shape=(P, P, P), max_batch=N,
+                      num_channels=spec.num_channels, num_levels=spec.num_levels,
+                      num_convolutions=spec.num_convolutions, bottom_convolutions=spec.bottom_convolutions,
+                      precision=precision, loss=loss, loss_weights=weights, library=library, **kw)
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b|  (the 'relative fp32' tolerance of BASELINE.json is on the tensor scale)."""
+    b = np.asarray(b, np.float64)
+    return float(np.abs(np.asarray(a, np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def analytically_zero(name, spec):
+    """Variables whose gradient is exactly 0 in the reference graph, where TF/torch autodiff only
+    produces rounding noise: conv biases, and every gamma/beta of a batch norm whose
+    output is discarded or re-normalised (the dead BN, and betas of all but the last BN of a chain)."""
+    if name.endswith("/biases"):
+        return True
+    if "/decoder/" not in name or "batch_normalization" not in name:
+        return False
+    level = int(name.split("/decoder/level_")[1].split("/")[0]) - 1
+    n = spec.num_convolutions[level]
+    conv = name.split("/")[3]
+    if not conv.startswith("conv_"):
+        return False
+    i = int(conv.split("_")[1]) - 1
+    bn = name.split("/")[4]
+    k = 0 if bn == "batch_normalization" else int(bn.rsplit("_", 1)[1])
+    is_beta = name.endswith("/beta")
+    if n == 1:                       # CH_T: only beta of BN2 is live
+        return is_beta and k < 2
+    if i == 0:
+        return False                 # plain BN
+    if i == n - 1:                   # CH_Q: beta of BN0 is re-normalised away
+        return is_beta and k == 0
+    return k == 0                    # CH_D: BN0 entirely dead

@@ -1,0 +1,67 @@
+"""The product library's boundary (no GPU needed): libvnet_b200.so loads, exports every symbol that
+include/vnet_b200.h declares, and fails loudly -- never falls back -- when no B200 is present."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from vnet_tensorflow_b200 import _ffi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def product_lib():
+    if not os.path.exists(_ffi.DEFAULT_LIB):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _ffi.Library(_ffi.DEFAULT_LIB)
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "vnet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vnb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_ffi_and_shared_object_agree(product_lib):
+    declared = _header_symbols()
+    assert declared == sorted(_ffi.EXPORTED_SYMBOLS)
+    nm = subprocess.run(["nm", "-D", "--defined-only", product_lib.path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (vnb_[a-z0-9_]+)", nm))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    assert "sm_100a" in product_lib.version()
+
+
+def test_sass_is_blackwell_native(product_lib):
+    """The shipped .so carries sm_100a SASS (and, once the tensor-core path is in, UTC*MMA / UTMALDG)."""
+    out = subprocess.run(["cuobjdump", "-lelf", product_lib.path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_create_fails_loudly_without_gpu(product_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible; the no-GPU failure path is exercised in the CPU container")
+    cfg = _ffi.VnbConfig()
+    cfg.in_channels, cfg.num_classes, cfg.num_channels, cfg.num_levels = 1, 2, 16, 1
+    cfg.num_convolutions[0] = 1
+    cfg.bottom_convolutions = 1
+    for i in range(3):
+        cfg.patch_shape[i] = 8
+    cfg.max_batch = 1
+    h = C.c_void_p()
+    rc = product_lib.vnb_create(C.byref(cfg), 0, C.byref(h))
+    assert rc == -3  # VNB_ERR_CUDA
+    assert b"no CPU fallback" in product_lib.vnb_last_error()
+    assert not h.value
+    from vnet_tensorflow_b200.engine import VNetEngine
+    with pytest.raises(_ffi.VnbError):
+        VNetEngine(num_classes=2, patch_shape=(16, 16, 16), library=product_lib)
+
+
+def test_missing_library_is_an_error(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        _ffi.Library(str(tmp_path / "libvnet_b200.so"))

@@ -1,0 +1,152 @@
+"""Kernel + engine logic on the CPU: the product's .cu sources are compiled with tests/emul/cuda_emul.h
+(fiber-per-thread CUDA emulation) and the resulting engine is compared with the oracle.  These tests
+exercise exactly the code that runs on the GPU in VNB_PREC_FP32 mode (index arithmetic, reductions,
+BN chains, backward ordering, optimiser), without a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_vnet as R
+from tests.helpers import analytically_zero, engine_for, perturbed_params, rel_err
+from vnet_tensorflow_b200 import _ffi
+from vnet_tensorflow_b200.synthetic import synth_batch
+
+SPEC_A = R.VNetSpec(num_classes=2, in_channels=1, num_channels=4, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=2)
+SPEC_B = R.VNetSpec(num_classes=3, in_channels=2, num_channels=4, num_levels=2, num_convolutions=(3, 1), bottom_convolutions=1)
+SPEC_C = R.VNetSpec(num_classes=4, in_channels=1, num_channels=8, num_levels=1, num_convolutions=(4,), bottom_convolutions=1)
+
+
+def _grad_check(eng, grads_o, spec, tol):
+    g = eng.get_grads()
+    scale = max(float(np.abs(v.numpy()).max()) for v in grads_o.values())
+    for k, v in g.items():
+        ref = grads_o[k].numpy()
+        if analytically_zero(k, spec):
+            assert np.abs(v).max() <= 1e-6 * scale + 1e-12, k
+            assert np.abs(ref).max() <= 1e-4 * scale, k  # the oracle only has rounding noise here
+            continue
+        assert np.abs(v - ref).max() <= tol * max(np.abs(ref).max(), 1e-3 * scale), k
+
+
+@pytest.mark.parametrize("spec,N,loss,weights", [
+    (SPEC_A, 2, "weighted_sorensen", (0.1, 1.0)),
+    (SPEC_B, 1, "mixed_weighted_jaccard", (0.1, 0.5, 1.0)),
+    (SPEC_C, 2, "jaccard", ()),
+    (SPEC_A, 1, "xent", ()),
+    (SPEC_B, 2, "weighted_xent", (0.2, 0.3, 1.0)),
+    (SPEC_A, 2, "mixed_sorensen", ()),
+    (SPEC_A, 2, "sorensen", ()),
+])
+def test_forward_loss_backward_match_oracle(emul_lib, spec, N, loss, weights):
+    P = 8
+    params = perturbed_params(spec)
+    img, lab = synth_batch(0, N, P, spec.in_channels, spec.num_classes)
+    eng = engine_for(spec, P, N, loss, weights, emul_lib)
+    assert list(eng.variables()) == [n for n, _, _ in R.param_specs(spec)]
+    eng.set_params(params)
+    loss_o, logits_o, grads_o, upd = R.loss_and_grads(params, img, lab, spec, loss, weights)
+    logits, softmax, argmax = eng.forward(img)
+    assert rel_err(logits, logits_o.numpy()) < 2e-5
+    assert rel_err(softmax, torch.softmax(logits_o, -1).numpy()) < 2e-5
+    assert int((argmax != R.predict(logits_o).numpy()).sum()) == 0
+    l, terms = eng.loss(img, lab, want_terms=True)
+    assert abs(l - float(loss_o)) < 2e-6
+    kind = "jaccard" if "jaccard" in loss else "sorensen"
+    assert rel_err(terms[..., :3], R.dice_terms(logits_o, torch.from_numpy(lab), kind).numpy()) < 1e-5
+    l2 = eng.forward_backward(img, lab, update_moving_stats=True)
+    assert abs(l2 - float(loss_o)) < 2e-6
+    _grad_check(eng, grads_o, spec, 2e-4)
+    for k, u in upd.items():  # UPDATE_OPS (model.py:665-666)
+        assert np.abs(eng.get_param(k) - u.numpy()).max() < 1e-4 * max(1.0, float(u.abs().max())), k
+    eng.close()
+
+
+def test_inference_does_not_touch_moving_statistics(emul_lib):
+    eng = engine_for(SPEC_A, 8, 1, "sorensen", (), emul_lib)
+    eng.set_params(perturbed_params(SPEC_A))
+    img, lab = synth_batch(0, 1, 8, 1, 2)
+    before = eng.get_param("vnet/output_layer/batch_normalization/moving_mean")
+    eng.forward(img)
+    eng.loss(img, lab)
+    assert np.array_equal(before, eng.get_param("vnet/output_layer/batch_normalization/moving_mean"))
+    eng.close()
+
+
+@pytest.mark.parametrize("optimizer", ["Adam", "SGD"])
+def test_training_trajectory_matches_oracle(emul_lib, optimizer):
+    """Three optimiser steps (model.py:641-666): lr decay, TF-form Adam, moving stats, global_step."""
+    spec, P, N = SPEC_A, 8, 2
+    params = perturbed_params(spec)
+    state = R.TrainState(params={k: v.copy() for k, v in params.items()})
+    eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 1.0), emul_lib, optimizer=optimizer,
+                     learning_rate=1e-2, decay_factor=0.5, decay_steps=2.0)
+    eng.set_params(params)
+    for step in range(3):
+        img, lab = synth_batch(step, N, P, 1, 2)
+        lo, _, _ = R.train_step(state, img, lab, spec, "weighted_sorensen", (0.1, 1.0), lr0=1e-2, decay_steps=2.0,
+                                decay_factor=0.5, optimizer=optimizer)
+        le = eng.train_step(img, lab)
+        assert abs(le - lo) < 5e-5, (step, le, lo)
+    assert eng.global_step == 3
+    for k in eng.variables():
+        if analytically_zero(k, spec):
+            continue  # Adam turns rounding noise into +-lr walks on these
+        a, b = eng.get_param(k), state.params[k]
+        assert np.abs(a - b).max() <= 5e-3 * max(np.abs(b).max(), 1e-2), k
+    eng.close()
+
+
+def test_dropout_mask_is_reproducible_and_matches_oracle_with_injected_mask(emul_lib):
+    spec, P, N, rate, seed = SPEC_A, 8, 1, 0.3, 1234
+    params = perturbed_params(spec)
+    img, lab = synth_batch(0, N, P, 1, 2)
+    eng = engine_for(spec, P, N, "sorensen", (), emul_lib)
+    eng.set_params(params)
+    l1 = eng.forward_backward(img, lab, dropout_rate=rate, seed=seed)
+    g1 = eng.get_grads()
+    l2 = eng.forward_backward(img, lab, dropout_rate=rate, seed=seed)
+    assert l1 == l2
+    assert all(np.array_equal(g1[k], v) for k, v in eng.get_grads().items())
+    l3 = eng.forward_backward(img, lab, dropout_rate=rate, seed=seed + 1)
+    assert l3 != l1
+    # recover the keep-masks from the activations (a == 0 exactly where dropped) and replay in the oracle
+    eng.forward_backward(img, lab, dropout_rate=rate, seed=seed)
+    masks = {}
+    dims = {1: (8, 8, 8), 2: (4, 4, 4)}
+    for name, c, sp in [("vnet/encoder/level_1/conv_1", 4, dims[1]), ("vnet/encoder/level_2/conv_1", 8, dims[2]),
+                        ("vnet/encoder/level_2/conv_2", 8, dims[2]), ("vnet/bottom_level/conv_1", 16, (2, 2, 2)),
+                        ("vnet/bottom_level/conv_2", 16, (2, 2, 2)), ("vnet/decoder/level_2/conv_1", 8, dims[2]),
+                        ("vnet/decoder/level_2/conv_2", 8, dims[2]), ("vnet/decoder/level_1/conv_1", 4, dims[1])]:
+        a = eng.read_tensor(name, 0, N, c, sp)
+        masks[name] = torch.from_numpy((a != 0).astype(np.float32))
+        keep = float(masks[name].mean())
+        assert 0.45 < keep < 0.95
+    lo, _, go, _ = R.loss_and_grads(params, img, lab, spec, "sorensen", (), dropout_rate=rate, masks=masks)
+    assert abs(float(lo) - l1) < 5e-6
+    _grad_check(eng, go, spec, 5e-4)
+    eng.close()
+
+
+def test_abi_error_behaviour(emul_lib):
+    """Errors come back as negative status + message, never as exceptions across the C boundary."""
+    import ctypes as C
+    cfg = _ffi.VnbConfig()
+    h = C.c_void_p()
+    rc = emul_lib.vnb_create(C.byref(cfg), 0, C.byref(h))  # all-zero config
+    assert rc == -1 and b"BottomConvolutions" in emul_lib.vnb_last_error()
+    with pytest.raises(AssertionError):
+        engine_for(SPEC_A, 8, 1, "weighted_sorensen", (1.0,), emul_lib)  # model.py:71 length assert
+    with pytest.raises(SystemExit):
+        engine_for(SPEC_A, 8, 1, "not_a_loss", (), emul_lib)             # model.py:559-560
+    with pytest.raises(_ffi.VnbError):
+        engine_for(SPEC_A, 10, 1, "sorensen", (), emul_lib)              # 10 is not divisible by 2^NumLevels
+    eng = engine_for(SPEC_A, 8, 1, "sorensen", (), emul_lib)
+    with pytest.raises(ValueError):
+        eng.forward(np.zeros((2, 8, 8, 8, 1), np.float32))               # batch > max_batch
+    with pytest.raises(KeyError):
+        eng.get_param("vnet/nope")
+    rc = emul_lib.vnb_get_param(eng._h, b"vnet/nope", None, 0)
+    assert rc == -1
+    rc = emul_lib.vnb_forward(None, None, 1, None, None, None)
+    assert rc == -1 and b"handle" in emul_lib.vnb_last_error()
+    eng.close()

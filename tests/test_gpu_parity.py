@@ -1,0 +1,209 @@
+"""Parity tests proper (run on the B200 with -m gpu): the CUDA engine, called through the C ABI,
+against the CPU oracle on the same seeded inputs and against the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): logits within 1e-3 relative fp32 (relative to the logit scale),
+bit-exact argmax label volumes, Dice terms/loss to fp32 rounding.  The fp32 and bf16x3 precisions are
+held to that bar; bf16 is the documented reduced-precision fast mode (looser bound, measured)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_vnet as R
+from tests.helpers import CASES, analytically_zero, engine_for, load_golden, perturbed_params, rel_err
+from vnet_tensorflow_b200.synthetic import synth_batch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = {"fp32": 2e-4, "bf16x3": 1e-3, "bf16": 8e-2}
+GRAD_TOL = {"fp32": 2e-3, "bf16x3": 5e-3, "bf16": 0.25}
+
+
+def _check_grads(eng, grads_ref, spec, tol):
+    g = eng.get_grads()
+    scale = max(float(np.abs(v).max()) for v in grads_ref.values())
+    worst = 0.0
+    for k, v in g.items():
+        ref = grads_ref[k]
+        if analytically_zero(k, spec):
+            assert np.abs(v).max() <= 1e-5 * scale + 1e-12, k
+            continue
+        err = np.abs(v - ref).max() / max(np.abs(ref).max(), 1e-3 * scale)
+        worst = max(worst, err)
+        assert err <= tol, (k, err)
+    return worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name", ["tiny_m1_k2", "tiny_m2_k3", "default_m1_k2_p32"])
+def test_golden_fixtures(gpu_lib, name, precision):
+    kw, P, N, loss, weights = CASES[name]
+    spec = R.VNetSpec(**kw)
+    gold = load_golden(name)
+    img, lab = synth_batch(0, N, P, spec.in_channels, spec.num_classes)
+    eng = engine_for(spec, P, N, loss, weights, gpu_lib, precision=precision)
+    eng.set_params(perturbed_params(spec))
+    logits, _, argmax = eng.forward(img)
+    assert rel_err(logits, gold["logits"]) < LOGIT_TOL[precision]
+    margin = np.sort(gold["logits"], -1)
+    margin = margin[..., -1] - margin[..., -2]
+    flips = (argmax != gold["argmax"])
+    if precision == "bf16":
+        assert flips.mean() < 0.02
+    else:  # bit-exact label volume wherever the class margin exceeds the numerical error bound
+        safe = margin > 2 * LOGIT_TOL[precision] * np.abs(gold["logits"]).max()
+        assert int((flips & safe).sum()) == 0
+        assert int(flips.sum()) <= 2
+    l, terms = eng.loss(img, lab, want_terms=True)
+    assert abs(l - float(gold["loss"])) < (5e-3 if precision == "bf16" else 5e-5)
+    if precision != "bf16":
+        assert rel_err(terms[..., :3], gold["dice_terms"]) < 2e-4
+    eng.forward_backward(img, lab)
+    g = eng.get_grads()
+    scale = max(float(v) for k, v in gold.items() if k.startswith("gnorm/"))
+    for k, v in g.items():
+        if analytically_zero(k, spec):
+            continue
+        gn = float(np.sqrt((v.astype(np.float64) ** 2).sum()))
+        ref = float(gold["gnorm/" + k])
+        assert abs(gn - ref) <= GRAD_TOL[precision] * max(ref, 1e-3 * scale), (k, gn, ref)
+        stride = max(1, v.size // 64)
+        assert np.abs(v.reshape(-1)[::stride][:64] - gold["gsample/" + k]).max() <= GRAD_TOL[precision] * max(
+            np.abs(gold["gsample/" + k]).max(), 1e-3 * scale), k
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_config1_64cube_forward_dice_matches_oracle(gpu_lib, precision):
+    """BASELINE config #1: single 64^3, 1-modality, 2-class patch, batch 1, forward + weighted Dice."""
+    spec = R.VNetSpec(num_classes=2, in_channels=1)
+    params = R.init_params(spec, 42)
+    img, lab = synth_batch(0, 1, 64, 1, 2)
+    eng = engine_for(spec, 64, 1, "weighted_sorensen", (0.1, 1.0), gpu_lib, precision=precision)
+    eng.set_params(params)
+    logits, softmax, argmax = eng.forward(img)
+    p = R.to_torch(params)
+    with torch.no_grad():
+        lo, _ = R.forward(p, torch.from_numpy(img), spec)
+        loss_o = R.loss_from_logits(lo, torch.from_numpy(lab), "weighted_sorensen", (0.1, 1.0))
+    ref = lo.numpy()
+    err = rel_err(logits, ref)
+    assert err < LOGIT_TOL[precision], err
+    ref_arg = R.predict(lo).numpy()
+    margin = np.abs(ref[..., 1] - ref[..., 0])
+    flips = argmax != ref_arg
+    assert int((flips & (margin > 2 * LOGIT_TOL[precision] * np.abs(ref).max())).sum()) == 0
+    assert flips.mean() < 1e-4
+    # hard Dice from the label volumes (integer TP/FP/FN) is exact when the labels are
+    if not flips.any():
+        tp = int(((argmax == 1) & (lab == 1)).sum())
+        tp_o = int(((ref_arg == 1) & (lab == 1)).sum())
+        assert tp == tp_o
+    assert abs(eng.loss(img, lab) - float(loss_o)) < 5e-5
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_gradients_match_oracle_default_net(gpu_lib, precision):
+    spec = R.VNetSpec(num_classes=2, in_channels=1)
+    params = perturbed_params(spec)
+    img, lab = synth_batch(5, 2, 32, 1, 2)
+    eng = engine_for(spec, 32, 2, "weighted_sorensen", (0.1, 1.0), gpu_lib, precision=precision)
+    eng.set_params(params)
+    l = eng.forward_backward(img, lab, update_moving_stats=True)
+    lo, _, go, upd = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
+    assert abs(l - float(lo)) < 5e-5
+    _check_grads(eng, {k: v.numpy() for k, v in go.items()}, spec, GRAD_TOL[precision])
+    for k, u in upd.items():
+        assert np.abs(eng.get_param(k) - u.numpy()).max() < 1e-3 * max(1.0, float(u.abs().max())), k
+    eng.close()
+
+
+def test_multimodal_four_class_net_matches_oracle(gpu_lib):
+    """BASELINE config #3 shape (4 modalities, 4 classes) at a size the oracle finishes in seconds."""
+    spec = R.VNetSpec(num_classes=4, in_channels=4)
+    params = perturbed_params(spec)
+    img, lab = synth_batch(2, 1, 32, 4, 4)
+    eng = engine_for(spec, 32, 1, "weighted_sorensen", (0.01, 0.1, 0.5, 1.0), gpu_lib, precision="fp32")
+    eng.set_params(params)
+    l = eng.forward_backward(img, lab)
+    lo, lg, go, _ = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.01, 0.1, 0.5, 1.0))
+    assert abs(l - float(lo)) < 5e-5
+    logits, _, _ = eng.forward(img)
+    assert rel_err(logits, lg.numpy()) < 2e-4
+    _check_grads(eng, {k: v.numpy() for k, v in go.items()}, spec, 2e-3)
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_three_training_steps_follow_the_oracle(gpu_lib, precision):
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=16, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=2)
+    params = perturbed_params(spec)
+    state = R.TrainState(params={k: v.copy() for k, v in params.items()})
+    eng = engine_for(spec, 16, 2, "weighted_sorensen", (0.1, 1.0), gpu_lib, precision=precision, learning_rate=1e-3)
+    eng.set_params(params)
+    for step in range(3):
+        img, lab = synth_batch(step, 2, 16, 1, 2)
+        lo, _, _ = R.train_step(state, img, lab, spec, "weighted_sorensen", (0.1, 1.0), lr0=1e-3)
+        le = eng.train_step(img, lab)
+        assert abs(le - lo) < 2e-3, (step, le, lo)
+    assert eng.global_step == 3
+    eng.close()
+
+
+@pytest.mark.parametrize("cin,cout,dims", [(16, 16, (8, 8, 16)), (32, 16, (4, 8, 32)), (64, 32, (8, 8, 8)),
+                                           (4, 16, (6, 5, 9)), (128, 128, (4, 4, 4))])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_conv5_ops_match_torch(gpu_lib, cin, cout, dims, precision):
+    """Per-op hooks: 5^3 SAME convolution forward, input gradient and filter gradient."""
+    import ctypes as C
+    if precision != "fp32" and (cin % 16 or cout % 16):
+        pytest.skip("tensor-core path needs channel multiples of 16; such layers run the fp32 kernel")
+    rng = np.random.default_rng(7)
+    n = 2
+    x = rng.normal(0, 1, (n,) + dims + (cin,)).astype(np.float32)
+    w = rng.normal(0, 0.05, (5, 5, 5, cin, cout)).astype(np.float32)
+    b = rng.normal(0, 1, (cout,)).astype(np.float32)
+    r = rng.normal(0, 1, (n,) + dims + (cout,)).astype(np.float32)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    wt = torch.from_numpy(w).requires_grad_(True)
+    y_ref = R.conv_same(xt, wt, torch.from_numpy(b)) + torch.from_numpy(r)
+    dy = rng.normal(0, 1, y_ref.shape).astype(np.float32)
+    y_ref.backward(torch.from_numpy(dy))
+    prec = {"fp32": 0, "bf16x3": 1}[precision]
+    tol = 1e-5 if precision == "fp32" else 3e-5
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    y = np.empty_like(dy)
+    gpu_lib.check(gpu_lib.vnb_op_conv5_fprop(0, prec, ptr(x), ptr(w), ptr(b), ptr(r), ptr(y), n, *dims, cin, cout))
+    assert rel_err(y, y_ref.detach().numpy()) < tol
+    dx = np.empty_like(x)
+    gpu_lib.check(gpu_lib.vnb_op_conv5_dgrad(0, prec, ptr(dy), ptr(w), ptr(dx), n, *dims, cin, cout))
+    assert rel_err(dx, xt.grad.numpy()) < tol
+    dw = np.empty_like(w)
+    gpu_lib.check(gpu_lib.vnb_op_conv5_wgrad(0, prec, ptr(x), ptr(dy), ptr(dw), n, *dims, cin, cout))
+    assert rel_err(dw, wt.grad.numpy()) < 5 * tol
+
+
+def test_full_size_properties_128cube(gpu_lib):
+    """BASELINE config #2 size (128^3, batch 2): size-independent properties instead of the oracle --
+    determinism of the forward, bias invariance of the logits, Dice of a perfect prediction,
+    and a loss that decreases over optimiser steps."""
+    spec = R.VNetSpec(num_classes=2, in_channels=1)
+    params = R.init_params(spec, 42)
+    img, lab = synth_batch(0, 2, 128, 1, 2)
+    eng = engine_for(spec, 128, 2, "weighted_sorensen", (0.1, 1.0), gpu_lib, precision="bf16x3", learning_rate=1e-3)
+    eng.set_params(params)
+    a, _, am = eng.forward(img, want_softmax=False)
+    b, _, _ = eng.forward(img, want_softmax=False, want_argmax=False)
+    assert np.array_equal(a, b)
+    rng = np.random.default_rng(0)
+    for k, (shape, _) in eng.variables().items():
+        if k.endswith("/biases"):
+            eng.set_param(k, rng.normal(0, 2, shape).astype(np.float32))
+    c, _, _ = eng.forward(img, want_softmax=False, want_argmax=False)
+    assert rel_err(c, a) < 1e-3
+    l0, terms = eng.loss(img, lab, want_terms=True)
+    assert np.allclose(terms[..., 2].sum(1), 128 ** 3)  # one-hot mass = voxel count per sample
+    assert np.allclose(terms[..., 1].sum(1), 128 ** 3, rtol=1e-4)  # softmax mass
+    losses = [eng.train_step(img, lab) for _ in range(4)]
+    assert losses[-1] < losses[0]
+    eng.close()

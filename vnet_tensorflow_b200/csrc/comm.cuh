@@ -1,0 +1,183 @@
+// Data-parallel gradient exchange (new functionality: the reference is single-device).
+//
+// One process per GPU.  The flat gradient buffer is cut into buckets along unit boundaries; as soon
+// as the backward pass has produced a bucket (Engine grad hook) it is all-reduced on a side stream
+// while the remaining backward kernels keep running on the compute stream; the optimiser step waits
+// on the side stream and folds the 1/world mean into its own pass.
+//
+// Two schedules over the same NCCL communicator (NVLink 5 / NVSwitch transport):
+//   ring (default) : hand-rolled reduce-scatter + all-gather built from ncclSend/ncclRecv pairs to
+//                    the ring neighbours, with our own fp32 accumulate kernel between hops
+//   nccl           : ncclAllReduce (lets NCCL pick NVLS / tree), for comparison (VNB_ALLREDUCE=nccl)
+// NCCL is resolved with dlopen so that the library binds to whatever libnccl.so.2 the process
+// already carries (PyTorch ships its own) instead of pinning a second copy.
+#pragma once
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace vnb {
+
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+
+  static NcclApi& get() {
+    static NcclApi api = load();
+    return api;
+  }
+  static NcclApi load() {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) throw std::runtime_error(std::string("NCCL: cannot dlopen libnccl.so.2: ") + dlerror());
+    auto sym = [&](const char* n) {
+      void* p = dlsym(h, n);
+      if (!p) throw std::runtime_error(std::string("NCCL: missing symbol ") + n);
+      return p;
+    };
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+    a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
+    a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+    return a;
+  }
+};
+
+#define VNB_NCCL_OK(expr)                                                                      \
+  do {                                                                                         \
+    ncclResult_t r__ = (expr);                                                                 \
+    if (r__ != ncclSuccess)                                                                    \
+      throw std::runtime_error(std::string("NCCL error: ") + NcclApi::get().GetErrorString(r__) + \
+                               " at " + __FILE__ + ":" + std::to_string(__LINE__));            \
+  } while (0)
+
+__global__ void accumulate_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] += src[i];
+}
+
+class Comm {
+ public:
+  static void unique_id(void* out128) {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    VNB_NCCL_OK(NcclApi::get().GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+  }
+
+  Comm(int rank, int world, const void* uid, Engine& e) : rank_(rank), world_(world) {
+    ncclUniqueId id;
+    memcpy(&id, uid, sizeof(id));
+    VNB_NCCL_OK(NcclApi::get().CommInitRank(&comm_, world, id, rank));
+    VNB_CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    const char* mode = getenv("VNB_ALLREDUCE");
+    use_ring_ = !(mode && std::string(mode) == "nccl");
+    const auto& buckets = e.buckets();
+    size_t max_chunk = 0;
+    for (const auto& b : buckets) max_chunk = std::max(max_chunk, chunk_elems(b.hi - b.lo));
+    events_.resize(buckets.size());
+    for (auto& ev : events_) VNB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    VNB_CUDA_OK(cudaEventCreateWithFlags(&done_, cudaEventDisableTiming));
+    if (world_ > 1) VNB_CUDA_OK(cudaMalloc(&scratch_, std::max<size_t>(max_chunk, 4) * sizeof(float)));
+    e.set_grad_hook([this, &e](int bucket) { this->on_bucket_ready(e, bucket); });
+  }
+  ~Comm() {
+    if (scratch_) cudaFree(scratch_);
+    for (auto ev : events_) cudaEventDestroy(ev);
+    cudaEventDestroy(done_);
+    cudaStreamDestroy(stream_);
+    if (comm_) NcclApi::get().CommDestroy(comm_);
+  }
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+
+  void begin_step(Engine&) { pending_ = 0; }
+
+  // called from Engine::backward (host side, in stream order) when bucket `bi` is complete
+  void on_bucket_ready(Engine& e, int bi) {
+    if (world_ == 1) return;
+    const Engine::Bucket& b = e.buckets()[bi];
+    VNB_CUDA_OK(cudaEventRecord(events_[bi], e.stream()));
+    VNB_CUDA_OK(cudaStreamWaitEvent(stream_, events_[bi], 0));
+    float* g = e.grad_buffer() + b.lo;
+    const size_t n = b.hi - b.lo;
+    if (use_ring_)
+      ring_allreduce(g, n);
+    else
+      VNB_NCCL_OK(NcclApi::get().AllReduce(g, g, n, ncclFloat, ncclSum, comm_, stream_));
+    ++pending_;
+  }
+
+  // compute stream waits for all bucket all-reduces before the optimiser reads the gradients
+  void finish_allreduce(Engine& e) {
+    if (world_ == 1) return;
+    VNB_CUDA_OK(cudaEventRecord(done_, stream_));
+    VNB_CUDA_OK(cudaStreamWaitEvent(e.stream(), done_, 0));
+  }
+
+ private:
+  size_t chunk_elems(size_t n) const { return (((n + world_ - 1) / world_) + 3) & ~size_t(3); }
+
+  // reduce-scatter then all-gather around the ring rank -> rank+1; W-1 hops each
+  void ring_allreduce(float* g, size_t n) {
+    NcclApi& api = NcclApi::get();
+    const int W = world_, next = (rank_ + 1) % W, prev = (rank_ + W - 1) % W;
+    const size_t chunk = chunk_elems(n);
+    auto range = [&](int c, size_t& off, size_t& len) {
+      off = std::min(n, static_cast<size_t>(c) * chunk);
+      len = std::min(n - off, chunk);
+    };
+    for (int s = 0; s < W - 1; ++s) {
+      size_t so, sl, ro, rl;
+      range(((rank_ - s) % W + W) % W, so, sl);
+      range(((rank_ - s - 1) % W + W) % W, ro, rl);
+      VNB_NCCL_OK(api.GroupStart());
+      if (sl) VNB_NCCL_OK(api.Send(g + so, sl, ncclFloat, next, comm_, stream_));
+      if (rl) VNB_NCCL_OK(api.Recv(scratch_, rl, ncclFloat, prev, comm_, stream_));
+      VNB_NCCL_OK(api.GroupEnd());
+      if (rl) {
+        const int blocks = static_cast<int>(std::min<size_t>((rl + 1023) / 1024, 296));
+        accumulate_kernel<<<blocks, 256, 0, stream_>>>(g + ro, scratch_, static_cast<long long>(rl));
+      }
+    }
+    for (int s = 0; s < W - 1; ++s) {
+      size_t so, sl, ro, rl;
+      range(((rank_ + 1 - s) % W + W) % W, so, sl);
+      range(((rank_ - s) % W + W) % W, ro, rl);
+      VNB_NCCL_OK(api.GroupStart());
+      if (sl) VNB_NCCL_OK(api.Send(g + so, sl, ncclFloat, next, comm_, stream_));
+      if (rl) VNB_NCCL_OK(api.Recv(g + ro, rl, ncclFloat, prev, comm_, stream_));
+      VNB_NCCL_OK(api.GroupEnd());
+    }
+  }
+
+  int rank_, world_;
+  ncclComm_t comm_ = nullptr;
+  cudaStream_t stream_ = nullptr;
+  bool use_ring_ = true;
+  float* scratch_ = nullptr;
+  std::vector<cudaEvent_t> events_;
+  cudaEvent_t done_ = nullptr;
+  int pending_ = 0;
+};
+
+}  // namespace vnb

@@ -1,0 +1,361 @@
+// fp32 CUDA-core convolution kernels ("exact" precision mode and the on-device anchor that the
+// tcgen05 implicit-GEMM kernels are validated against at sizes the CPU oracle cannot reach).
+//
+// Reference ops restated (paths relative to /root/reference):
+//   layers2.convolution 5x5x5 stride 1 SAME   layers2.py:59-63  <- networks.py:264,316,333,346,356
+//   layers2.down_convolution 2x2x2 stride 2   layers2.py:78-84  <- networks.py:278
+//   layers2.up_convolution (conv3d_transpose) layers2.py:65-74,88-94 <- networks.py:292
+//   1x1x1 output convolution                  networks.py:302
+// plus their input-gradient (dgrad) and filter-gradient (wgrad) forms (TF autodiff of model.py:660).
+//
+// Layout: activations NDHWC fp32; 5^3 filters [125][Cin][Cout] (= TF [kd,kh,kw,Cin,Cout]);
+// 2^3 filters [8][Cfine][Ccoarse] (TF down: [2,2,2,Cin,Cout], TF up: [2,2,2,Cout,Cin] -- both have
+// the fine-resolution channel first, so one set of kernels serves both directions).
+#pragma once
+#include "vnb_cuda.h"
+
+namespace vnb {
+
+struct Dims {  // spatial extents of one sample
+  int D, H, W;
+};
+
+// -------------------------------------------------------------------------------------------------
+// 5x5x5 stride-1 SAME convolution, forward form.  Input = channel concat of (in1, in2)
+// (tf.concat at networks.py:325 is never materialised).  Output channels [0,Co1) go to out1 and
+// [Co1, Co1+Co2) to out2 (used by dgrad of the concat convolution); each output may accumulate.
+// dgrad is this kernel run on dz with flipped+transposed weights (see flip_transpose_w5_kernel).
+// -------------------------------------------------------------------------------------------------
+constexpr int kC5_TD = 4, kC5_TH = 4, kC5_TW = 16;         // output tile, one voxel per thread
+constexpr int kC5_CK = 8;                                   // input channels per smem chunk
+constexpr int kC5_CO = 16;                                  // output channels per thread
+constexpr int kC5_HV = (kC5_TD + 4) * (kC5_TH + 4) * (kC5_TW + 4);  // halo voxels = 1280
+constexpr int kC5_XS = kC5_HV + 1;                          // padded channel stride (bank conflicts)
+constexpr size_t kC5_SMEM = (static_cast<size_t>(kC5_CK) * kC5_XS + 125 * kC5_CK * kC5_CO) * sizeof(float);
+
+struct Conv5Args {
+  const float* in1;
+  const float* in2;   // may be nullptr
+  int C1, C2;         // channels of in1 / in2
+  const float* w;     // [125][C1+C2][Cout]
+  const float* bias;  // [Cout] or nullptr
+  const float* res;   // residual [V][Cout] added in the epilogue, or nullptr
+  float* out1;
+  float* out2;        // may be nullptr
+  int Co1, Co2;       // Cout = Co1 + Co2
+  int acc1, acc2;     // accumulate into existing contents
+  Dims dims;
+  int N;
+};
+
+__global__ void __launch_bounds__(256) conv5_ref_kernel(Conv5Args p) {
+  VNB_DYN_SMEM(float, smem);
+  float* xs = smem;                       // [CK][XS]
+  float* ws = smem + kC5_CK * kC5_XS;     // [125][CK][CO]
+  const int D = p.dims.D, H = p.dims.H, W = p.dims.W;
+  const int tw_n = (W + kC5_TW - 1) / kC5_TW, th_n = (H + kC5_TH - 1) / kC5_TH;
+  int tile = blockIdx.x;
+  const int tw0 = (tile % tw_n) * kC5_TW;
+  tile /= tw_n;
+  const int th0 = (tile % th_n) * kC5_TH;
+  const int td0 = (tile / th_n) * kC5_TD;
+  const int co0 = blockIdx.y * kC5_CO;
+  const int n = blockIdx.z;
+  const int t = threadIdx.x;
+  const int lw = t % kC5_TW, lh = (t / kC5_TW) % kC5_TH, ld = t / (kC5_TW * kC5_TH);
+  const int Cin = p.C1 + p.C2, Cout = p.Co1 + p.Co2;
+  const long long sample = static_cast<long long>(D) * H * W;
+
+  float acc[kC5_CO];
+#pragma unroll
+  for (int j = 0; j < kC5_CO; ++j) acc[j] = 0.f;
+
+  for (int cb = 0; cb < Cin; cb += kC5_CK) {
+    __syncthreads();
+    // halo tile: xs[ci][hv], zero outside the volume (SAME padding) and beyond Cin
+    for (int i = t; i < kC5_HV * kC5_CK; i += 256) {
+      const int ci = i % kC5_CK, hv = i / kC5_CK;
+      const int hw = hv % (kC5_TW + 4), hh = (hv / (kC5_TW + 4)) % (kC5_TH + 4), hd = hv / ((kC5_TW + 4) * (kC5_TH + 4));
+      const int gd = td0 + hd - 2, gh = th0 + hh - 2, gw = tw0 + hw - 2, cg = cb + ci;
+      float val = 0.f;
+      if (cg < Cin && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
+        const long long vox = n * sample + (static_cast<long long>(gd) * H + gh) * W + gw;
+        val = cg < p.C1 ? p.in1[vox * p.C1 + cg] : p.in2[vox * p.C2 + (cg - p.C1)];
+      }
+      xs[ci * kC5_XS + hv] = val;
+    }
+    for (int i = t; i < 125 * kC5_CK * kC5_CO; i += 256) {
+      const int co = i % kC5_CO, ci = (i / kC5_CO) % kC5_CK, tap = i / (kC5_CO * kC5_CK);
+      const int cg = cb + ci;
+      ws[i] = (cg < Cin && co0 + co < Cout) ? p.w[(static_cast<long long>(tap) * Cin + cg) * Cout + co0 + co] : 0.f;
+    }
+    __syncthreads();
+    for (int kd = 0; kd < 5; ++kd)
+      for (int kh = 0; kh < 5; ++kh)
+        for (int kw = 0; kw < 5; ++kw) {
+          const int tap = (kd * 5 + kh) * 5 + kw;
+          const int hv = ((ld + kd) * (kC5_TH + 4) + (lh + kh)) * (kC5_TW + 4) + lw + kw;
+#pragma unroll
+          for (int ci = 0; ci < kC5_CK; ++ci) {
+            const float x = xs[ci * kC5_XS + hv];
+            const float* wr = ws + (tap * kC5_CK + ci) * kC5_CO;
+#pragma unroll
+            for (int j = 0; j < kC5_CO; ++j) acc[j] += x * wr[j];
+          }
+        }
+  }
+  const int gd = td0 + ld, gh = th0 + lh, gw = tw0 + lw;
+  if (gd >= D || gh >= H || gw >= W) return;
+  const long long vox = n * sample + (static_cast<long long>(gd) * H + gh) * W + gw;
+#pragma unroll
+  for (int j = 0; j < kC5_CO; ++j) {
+    const int co = co0 + j;
+    if (co >= Cout) break;
+    float y = acc[j];
+    if (p.bias) y += p.bias[co];
+    if (p.res) y += p.res[vox * Cout + co];
+    if (co < p.Co1) {
+      float* o = p.out1 + vox * p.Co1 + co;
+      *o = p.acc1 ? *o + y : y;
+    } else {
+      float* o = p.out2 + vox * p.Co2 + (co - p.Co1);
+      *o = p.acc2 ? *o + y : y;
+    }
+  }
+}
+
+// wd[tap'][co][ci] = w[124 - tap'][ci][co]: dgrad(dz) = conv5(dz, wd) (flipped taps, swapped channels)
+__global__ void flip_transpose_w5_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cin, int Cout) {
+  const long long total = 125LL * Cin * Cout;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const int co = static_cast<int>((i / Cin) % Cout);
+    const int tap = static_cast<int>(i / (static_cast<long long>(Cin) * Cout));
+    wd[i] = w[(static_cast<long long>(124 - tap) * Cin + ci) * Cout + co];
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// 5x5x5 filter gradient: dw[tap][ci][co] += sum_v x[v + off(tap)][ci] * dz[v][co]
+// grid: (voxel splits, (Cin/16 blocks) * (Cout/16 blocks)); thread = one (ci, co) pair with all
+// 125 taps in registers; block partial sums are added to dw with fp32 atomics (dw pre-zeroed).
+// -------------------------------------------------------------------------------------------------
+constexpr int kW5_TD = 2, kW5_TH = 4, kW5_TW = 16;
+constexpr int kW5_HV = (kW5_TD + 4) * (kW5_TH + 4) * (kW5_TW + 4);  // 960
+constexpr int kW5_TV = kW5_TD * kW5_TH * kW5_TW;                    // 128
+constexpr size_t kW5_SMEM = (static_cast<size_t>(kW5_HV) * 16 + kW5_TV * 16) * sizeof(float);
+
+struct Wgrad5Args {
+  const float* in1;
+  const float* in2;
+  int C1, C2;
+  const float* dz;  // [V][Cout]
+  int Cout;
+  float* dw;        // [125][C1+C2][Cout], pre-zeroed
+  Dims dims;
+  int N;
+  int tiles_per_block;
+};
+
+__global__ void __launch_bounds__(256) conv5_wgrad_ref_kernel(Wgrad5Args p) {
+  VNB_DYN_SMEM(float, smem);
+  float* xs = smem;                 // [HV][16 ci]
+  float* ds = smem + kW5_HV * 16;   // [TV][16 co]
+  const int D = p.dims.D, H = p.dims.H, W = p.dims.W;
+  const int Cin = p.C1 + p.C2, Cout = p.Cout;
+  const int co_blocks = (Cout + 15) / 16;
+  const int ci0 = (blockIdx.y / co_blocks) * 16, co0 = (blockIdx.y % co_blocks) * 16;
+  const int t = threadIdx.x, ci = t / 16, co = t % 16;
+  const int tw_n = (W + kW5_TW - 1) / kW5_TW, th_n = (H + kW5_TH - 1) / kW5_TH, td_n = (D + kW5_TD - 1) / kW5_TD;
+  const long long tiles_per_sample = static_cast<long long>(tw_n) * th_n * td_n;
+  const long long ntiles = tiles_per_sample * p.N;
+  const long long sample = static_cast<long long>(D) * H * W;
+  float acc[125];
+#pragma unroll
+  for (int k = 0; k < 125; ++k) acc[k] = 0.f;
+
+  const long long first = static_cast<long long>(blockIdx.x) * p.tiles_per_block;
+  for (long long tile = first; tile < first + p.tiles_per_block && tile < ntiles; ++tile) {
+    const int n = static_cast<int>(tile / tiles_per_sample);
+    long long r = tile % tiles_per_sample;
+    const int tw0 = static_cast<int>(r % tw_n) * kW5_TW;
+    r /= tw_n;
+    const int th0 = static_cast<int>(r % th_n) * kW5_TH;
+    const int td0 = static_cast<int>(r / th_n) * kW5_TD;
+    __syncthreads();
+    for (int i = t; i < kW5_HV * 16; i += 256) {
+      const int c = i % 16, hv = i / 16;
+      const int hw = hv % (kW5_TW + 4), hh = (hv / (kW5_TW + 4)) % (kW5_TH + 4), hd = hv / ((kW5_TW + 4) * (kW5_TH + 4));
+      const int gd = td0 + hd - 2, gh = th0 + hh - 2, gw = tw0 + hw - 2, cg = ci0 + c;
+      float val = 0.f;
+      if (cg < Cin && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
+        const long long vox = n * sample + (static_cast<long long>(gd) * H + gh) * W + gw;
+        val = cg < p.C1 ? p.in1[vox * p.C1 + cg] : p.in2[vox * p.C2 + (cg - p.C1)];
+      }
+      xs[i] = val;
+    }
+    for (int i = t; i < kW5_TV * 16; i += 256) {
+      const int c = i % 16, tv = i / 16;
+      const int lw = tv % kW5_TW, lh = (tv / kW5_TW) % kW5_TH, ld = tv / (kW5_TW * kW5_TH);
+      const int gd = td0 + ld, gh = th0 + lh, gw = tw0 + lw;
+      float val = 0.f;
+      if (co0 + c < Cout && gd < D && gh < H && gw < W) {
+        const long long vox = n * sample + (static_cast<long long>(gd) * H + gh) * W + gw;
+        val = p.dz[vox * Cout + co0 + c];
+      }
+      ds[i] = val;
+    }
+    __syncthreads();
+    for (int tv = 0; tv < kW5_TV; ++tv) {
+      const float g = ds[tv * 16 + co];
+      const int lw = tv % kW5_TW, lh = (tv / kW5_TW) % kW5_TH, ld = tv / (kW5_TW * kW5_TH);
+      const float* xb = xs + ((ld * (kW5_TH + 4) + lh) * (kW5_TW + 4) + lw) * 16 + ci;
+#pragma unroll
+      for (int kd = 0; kd < 5; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 5; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 5; ++kw)
+            acc[(kd * 5 + kh) * 5 + kw] += xb[((kd * (kW5_TH + 4) + kh) * (kW5_TW + 4) + kw) * 16] * g;
+    }
+  }
+  if (ci0 + ci < Cin && co0 + co < Cout) {
+#pragma unroll
+    for (int k = 0; k < 125; ++k)
+      atomicAdd(p.dw + (static_cast<long long>(k) * Cin + ci0 + ci) * Cout + co0 + co, acc[k]);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// 2x2x2 stride-2 kernels.  `fine` is [N][2Dc][2Hc][2Wc][CF], `coarse` is [N][Dc][Hc][Wc][CC],
+// w is [8][CF][CC] with tap = (a*2 + b)*2 + d (a,b,d = offsets along D,H,W).
+//   gather : coarse[o][cc] (+)= sum_{tap,cf} fine[2o+tap][cf] * w[tap][cf][cc] (+ bias[cc])   down fprop, up dgrad
+//   scatter: fine[2i+tap][cf] (+)= sum_cc coarse[i][cc] * w[tap][cf][cc] (+ bias[cf])         up fprop, down dgrad
+//   wgrad  : dw[tap][cf][cc] += sum_{n,i} fine[2i+tap][cf] * coarse[i][cc]
+// -------------------------------------------------------------------------------------------------
+struct K2Args {
+  const float* fine_in;
+  const float* coarse_in;
+  float* fine_out;
+  float* coarse_out;
+  const float* w;
+  float* dw;
+  const float* bias;
+  int CF, CC;
+  Dims cd;  // coarse dims
+  int N;
+  int accumulate;
+};
+
+__global__ void k2_gather_kernel(K2Args p) {
+  const long long total = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W * p.CC;
+  const int Hf = 2 * p.cd.H, Wf = 2 * p.cd.W, Df = 2 * p.cd.D;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cc = static_cast<int>(i % p.CC);
+    long long o = i / p.CC;
+    const int ow = static_cast<int>(o % p.cd.W);
+    o /= p.cd.W;
+    const int oh = static_cast<int>(o % p.cd.H);
+    o /= p.cd.H;
+    const int od = static_cast<int>(o % p.cd.D);
+    const int n = static_cast<int>(o / p.cd.D);
+    float s = p.bias ? p.bias[cc] : 0.f;
+    for (int tap = 0; tap < 8; ++tap) {
+      const int fd = 2 * od + (tap >> 2), fh = 2 * oh + ((tap >> 1) & 1), fw = 2 * ow + (tap & 1);
+      const float* f = p.fine_in + (((static_cast<long long>(n) * Df + fd) * Hf + fh) * Wf + fw) * p.CF;
+      const float* wr = p.w + static_cast<long long>(tap) * p.CF * p.CC + cc;
+      for (int cf = 0; cf < p.CF; ++cf) s += f[cf] * wr[static_cast<long long>(cf) * p.CC];
+    }
+    p.coarse_out[i] = p.accumulate ? p.coarse_out[i] + s : s;
+  }
+}
+
+__global__ void k2_scatter_kernel(K2Args p) {
+  const int Hf = 2 * p.cd.H, Wf = 2 * p.cd.W, Df = 2 * p.cd.D;
+  const long long total = static_cast<long long>(p.N) * Df * Hf * Wf * p.CF;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cf = static_cast<int>(i % p.CF);
+    long long o = i / p.CF;
+    const int fw = static_cast<int>(o % Wf);
+    o /= Wf;
+    const int fh = static_cast<int>(o % Hf);
+    o /= Hf;
+    const int fd = static_cast<int>(o % Df);
+    const int n = static_cast<int>(o / Df);
+    const int tap = ((fd & 1) << 2) | ((fh & 1) << 1) | (fw & 1);
+    const float* c = p.coarse_in + (((static_cast<long long>(n) * p.cd.D + (fd >> 1)) * p.cd.H + (fh >> 1)) * p.cd.W + (fw >> 1)) * p.CC;
+    const float* wr = p.w + (static_cast<long long>(tap) * p.CF + cf) * p.CC;
+    float s = p.bias ? p.bias[cf] : 0.f;
+    for (int cc = 0; cc < p.CC; ++cc) s += c[cc] * wr[cc];
+    p.fine_out[i] = p.accumulate ? p.fine_out[i] + s : s;
+  }
+}
+
+// grid: (ceil(8*CF*CC / 256), voxel splits); fp32 atomics into pre-zeroed dw
+__global__ void k2_wgrad_kernel(K2Args p, int voxels_per_split) {
+  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (e >= 8LL * p.CF * p.CC) return;
+  const int cc = static_cast<int>(e % p.CC);
+  const int cf = static_cast<int>((e / p.CC) % p.CF);
+  const int tap = static_cast<int>(e / (static_cast<long long>(p.CC) * p.CF));
+  const int Hf = 2 * p.cd.H, Wf = 2 * p.cd.W, Df = 2 * p.cd.D;
+  const long long V = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
+  const long long v0 = static_cast<long long>(blockIdx.y) * voxels_per_split;
+  float s = 0.f;
+  for (long long v = v0; v < v0 + voxels_per_split && v < V; ++v) {
+    long long o = v;
+    const int ow = static_cast<int>(o % p.cd.W);
+    o /= p.cd.W;
+    const int oh = static_cast<int>(o % p.cd.H);
+    o /= p.cd.H;
+    const int od = static_cast<int>(o % p.cd.D);
+    const int n = static_cast<int>(o / p.cd.D);
+    const int fd = 2 * od + (tap >> 2), fh = 2 * oh + ((tap >> 1) & 1), fw = 2 * ow + (tap & 1);
+    s += p.fine_in[(((static_cast<long long>(n) * Df + fd) * Hf + fh) * Wf + fw) * p.CF + cf] * p.coarse_in[v * p.CC + cc];
+  }
+  atomicAdd(p.dw + e, s);
+}
+
+// -------------------------------------------------------------------------------------------------
+// 1x1x1 convolution (output layer, networks.py:302): w [Cin][K]
+// -------------------------------------------------------------------------------------------------
+__global__ void conv1_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                   const float* __restrict__ bias, float* __restrict__ z, long long V, int Cin, int K) {
+  const long long total = V * K;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const long long v = i / K;
+    float s = bias ? bias[k] : 0.f;
+    for (int c = 0; c < Cin; ++c) s += x[v * Cin + c] * w[c * K + k];
+    z[i] = s;
+  }
+}
+__global__ void conv1_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                   float* __restrict__ dx, long long V, int Cin, int K, int accumulate) {
+  const long long total = V * Cin;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cin);
+    const long long v = i / Cin;
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += dz[v * K + k] * w[c * K + k];
+    dx[i] = accumulate ? dx[i] + s : s;
+  }
+}
+// dw[c][k] += sum_v x[v][c] * dz[v][k]; thread = (c,k) pair, block-strided over voxel chunks
+__global__ void conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ dw,
+                                   long long V, int Cin, int K, int voxels_per_block) {
+  const int t = threadIdx.x;
+  if (t >= Cin * K) return;
+  const int c = t / K, k = t % K;
+  const long long v0 = static_cast<long long>(blockIdx.x) * voxels_per_block;
+  double s = 0.0;
+  for (long long v = v0; v < v0 + voxels_per_block && v < V; ++v) s += static_cast<double>(x[v * Cin + c]) * dz[v * K + k];
+  atomicAdd(dw + t, static_cast<float>(s));
+}
+
+}  // namespace vnb

@@ -1,0 +1,1003 @@
+// V-Net engine: builds the reference graph (networks.VNet.GetNetwork, networks.py:246-305) as a static
+// list of "conv units" over device buffers and runs forward / loss / backward / optimiser steps
+// (the sess.run([train_op, loss_op]) of model.py:743-748 and the inference run of model.py:914-917).
+//
+// A conv unit = { convolution (5^3 | 2^3 down | 2^3 up | 1^3 | tiled input) + bias (+ residual) }
+//               -> batch-norm chain (bn_chain.h) -> optional PReLU -> optional dropout.
+// Parameters live in one flat fp32 buffer in TF variable-creation order (same names as the reference
+// checkpoint) so that the optimiser and the data-parallel all-reduce are single passes.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "bn_chain.h"
+#include "conv_ref.cuh"
+#include "kernels.cuh"
+#include "vnb_cuda.h"
+#ifndef VNB_EMULATE
+#include "conv_tc.cuh"
+#endif
+
+namespace vnb {
+
+#define VNB_CUDA_OK(expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " +  \
+                               __FILE__ + ":" + std::to_string(__LINE__));                        \
+  } while (0)
+
+enum Precision : int { PREC_FP32 = 0, PREC_BF16X3 = 1, PREC_BF16 = 2 };
+enum LossName : int {
+  LOSS_XENT = 0, LOSS_WEIGHTED_XENT, LOSS_SORENSEN, LOSS_WEIGHTED_SORENSEN, LOSS_JACCARD,
+  LOSS_WEIGHTED_JACCARD, LOSS_MIXED_SORENSEN, LOSS_MIXED_WEIGHTED_SORENSEN, LOSS_MIXED_JACCARD,
+  LOSS_MIXED_WEIGHTED_JACCARD
+};
+enum OptName : int { OPT_ADAM = 0, OPT_SGD = 1 };
+
+struct EngineConfig {
+  int in_channels = 1, num_classes = 2, num_channels = 16, num_levels = 4;
+  int num_convolutions[8] = {1, 2, 3, 3, 0, 0, 0, 0};
+  int bottom_convolutions = 3;
+  int patch[3] = {64, 64, 64};
+  int max_batch = 1;
+  int precision = PREC_FP32;
+  int loss = LOSS_WEIGHTED_SORENSEN;
+  float loss_weights[kMaxClasses] = {1, 1, 1, 1, 1, 1, 1, 1};
+  float loss_alpha = 1.0f;
+  int optimizer = OPT_ADAM;
+  float lr0 = 1e-2f, decay_factor = 0.99f, decay_steps = 100.f;
+};
+
+enum UnitKind : int { U_INPUT_TILE = 0, U_CONV5, U_DOWN, U_UP, U_CONV1 };
+
+struct ParamEntry {
+  std::string name;
+  int ndim = 0;
+  long long dims[5] = {0, 0, 0, 0, 0};
+  size_t offset = 0, count = 0;
+  bool trainable = true;  // false: moving statistics (state buffer)
+};
+
+struct Act {        // one activation tensor and its gradient
+  int C = 0;
+  Dims dims{0, 0, 0};
+  float* a = nullptr;
+  float* d = nullptr;
+  uint16_t* a_hi = nullptr;  // bf16 copies for the tensor-core path
+  uint16_t* a_lo = nullptr;
+  uint16_t* d_hi = nullptr;
+  uint16_t* d_lo = nullptr;
+  bool needs_grad = true;
+};
+
+struct Unit {
+  std::string scope;
+  int kind = U_CONV5;
+  int in1 = -1, in2 = -1, res = -1, out = -1;
+  int Cin1 = 0, Cin2 = 0, Cout = 0;
+  int chain = CH_S;
+  bool has_act = false, has_dropout = false;
+  // parameter offsets (floats) into the flat buffers; -1 = absent
+  long long w_off = -1, b_off = -1, alpha_off = -1;
+  long long gamma_off[3] = {-1, -1, -1}, beta_off[3] = {-1, -1, -1};
+  long long mm_off[3] = {-1, -1, -1}, mv_off[3] = {-1, -1, -1};
+  size_t w_count = 0;
+  size_t p_lo = 0;                    // first trainable-parameter offset of this unit
+  // buffers
+  float* z = nullptr;                 // pre-BN tensor [V][Cout]
+  double *mean = nullptr, *var = nullptr;
+  float *scale = nullptr, *shift = nullptr, *P = nullptr, *Q = nullptr, *S = nullptr;
+  // backward plan
+  bool res_accumulate = false, in1_accumulate = false, in2_accumulate = false, need_dgrad = true;
+#ifndef VNB_EMULATE
+  TcConvPlan tc;                      // tensor-core plan (precision != fp32)
+#endif
+};
+
+class Engine {
+ public:
+  explicit Engine(const EngineConfig& cfg) : cfg_(cfg) {
+    validate();
+    VNB_CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    build_graph();
+    allocate();
+    init_default_params();
+  }
+  ~Engine() {
+    for (void* p : allocs_) cudaFree(p);
+    cudaStreamDestroy(stream_);
+  }
+
+  struct Bucket {  // contiguous slice of the flat gradient buffer, complete once unit `unit_lo` has run backward
+    int unit_lo, unit_hi;
+    size_t lo, hi;
+  };
+  const std::vector<Bucket>& buckets() const { return buckets_; }
+  void set_grad_hook(std::function<void(int)> hook) { grad_hook_ = std::move(hook); }
+
+  const std::vector<ParamEntry>& params() const { return entries_; }
+  const EngineConfig& config() const { return cfg_; }
+  size_t num_trainable() const { return n_train_; }
+  cudaStream_t stream() const { return stream_; }
+  float* grad_buffer() { return grads_; }
+  long long global_step() const { return global_step_; }
+  void set_global_step(long long s) { global_step_ = s; }
+  void set_grad_scale(float s) { grad_scale_ = s; }
+
+  const ParamEntry& find(const std::string& name) const {
+    auto it = index_.find(name);
+    if (it == index_.end()) throw std::invalid_argument("unknown variable: " + name);
+    return entries_[it->second];
+  }
+  // kind: 0 value, 1 gradient, 2 Adam m, 3 Adam v
+  float* buffer_for(const ParamEntry& e, int kind) {
+    if (!e.trainable) {
+      if (kind != 0) throw std::invalid_argument("moving statistics have no gradient / slots: " + e.name);
+      return state_ + e.offset;
+    }
+    float* base = kind == 0 ? params_ : kind == 1 ? grads_ : kind == 2 ? adam_m_ : adam_v_;
+    return base + e.offset;
+  }
+  void set_param(const std::string& name, const float* host, size_t bytes, int kind = 0) {
+    const ParamEntry& e = find(name);
+    if (bytes != e.count * sizeof(float)) throw std::invalid_argument("size mismatch for " + name);
+    VNB_CUDA_OK(cudaMemcpyAsync(buffer_for(e, kind), host, bytes, cudaMemcpyHostToDevice, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+    weights_dirty_ = true;
+  }
+  void get_param(const std::string& name, float* host, size_t bytes, int kind = 0) {
+    const ParamEntry& e = find(name);
+    if (bytes != e.count * sizeof(float)) throw std::invalid_argument("size mismatch for " + name);
+    VNB_CUDA_OK(cudaMemcpyAsync(host, buffer_for(e, kind), bytes, cudaMemcpyDeviceToHost, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+  }
+
+  // ---- public steps ---------------------------------------------------------------------------
+  // inference run (model.py:914-917): dropout 0, batch statistics, no moving-average update
+  void forward_host(const float* images, int N, float* logits, float* softmax, long long* argmax) {
+    check_batch(N);
+    upload_images(images, N);
+    forward(N, 0.f, 0, false);
+    const long long V = voxels(N);
+    const int K = cfg_.num_classes;
+    if (softmax || argmax) {
+      LossCfg lc = loss_cfg();
+      dim3 grid(loss_blocks(), N);
+      VNB_LAUNCH(softmax_loss_fwd_kernel, grid, 256, 0, stream_, acts_[head_act_].a, (const int32_t*)nullptr,
+                 V / N, lc, softmax ? softmax_dev_ : (float*)nullptr, argmax ? argmax_dev_ : (long long*)nullptr,
+                 (double*)nullptr);
+    }
+    if (logits) VNB_CUDA_OK(cudaMemcpyAsync(logits, acts_[head_act_].a, V * K * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    if (softmax) VNB_CUDA_OK(cudaMemcpyAsync(softmax, softmax_dev_, V * K * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    if (argmax) VNB_CUDA_OK(cudaMemcpyAsync(argmax, argmax_dev_, V * sizeof(long long), cudaMemcpyDeviceToHost, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+  }
+
+  // loss only (the in-loop test step of model.py:784-789): returns loss, optional dice terms [N][K][4]
+  float loss_host(const float* images, const int32_t* labels, int N, double* terms) {
+    check_batch(N);
+    upload_images(images, N);
+    upload_labels(labels, N);
+    forward(N, 0.f, 0, false);
+    loss_forward(N);
+    float loss;
+    VNB_CUDA_OK(cudaMemcpyAsync(&loss, loss_dev_, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    if (terms)
+      VNB_CUDA_OK(cudaMemcpyAsync(terms, terms_dev_, sizeof(double) * N * cfg_.num_classes * 4, cudaMemcpyDeviceToHost, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+    return loss;
+  }
+
+  // forward + loss + backward; gradients left in the flat gradient buffer (no optimiser step)
+  void forward_backward_device(int N, float dropout, uint64_t seed, bool update_moving) {
+    forward(N, dropout, seed, update_moving);
+    loss_forward(N);
+    backward(N, dropout, seed);
+  }
+  void upload_batch(const float* images, const int32_t* labels, int N) {
+    check_batch(N);
+    upload_images(images, N);
+    upload_labels(labels, N);
+  }
+  // optimiser over the flat buffers; `world` folds the data-parallel mean into the update
+  void optimizer_step(int world) {
+    const float lr = cfg_.lr0 * std::pow(cfg_.decay_factor, static_cast<float>(global_step_) / cfg_.decay_steps);
+    const long long t = global_step_ + 1;
+    const float gscale = grad_scale_ / static_cast<float>(world);
+    const int blocks = grid_for(n_train_, 256);
+    if (cfg_.optimizer == OPT_ADAM) {
+      const double b1 = 0.9, b2 = 0.999;
+      const float lr_t = static_cast<float>(lr * std::sqrt(1.0 - std::pow(b2, (double)t)) / (1.0 - std::pow(b1, (double)t)));
+      VNB_LAUNCH(adam_step_kernel, blocks, 256, 0, stream_, params_, (const float*)grads_, adam_m_, adam_v_,
+                 (long long)n_train_, lr_t, 0.9f, 0.999f, 1e-8f, gscale);
+    } else {
+      VNB_LAUNCH(sgd_step_kernel, blocks, 256, 0, stream_, params_, (const float*)grads_, (long long)n_train_, lr, gscale);
+    }
+    global_step_ = t;
+    weights_dirty_ = true;
+  }
+  float read_loss() {
+    float loss;
+    VNB_CUDA_OK(cudaMemcpyAsync(&loss, loss_dev_, sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+    return loss;
+  }
+  // single-process training step (model.py:743-748)
+  float train_step_host(const float* images, const int32_t* labels, int N, float dropout, uint64_t seed, bool want_loss) {
+    upload_batch(images, labels, N);
+    forward_backward_device(N, dropout, seed, true);
+    optimizer_step(1);
+    return want_loss ? read_loss() : 0.f;
+  }
+  void sync() { VNB_CUDA_OK(cudaStreamSynchronize(stream_)); }
+
+  // debug access for tests: copy an activation (kind 0), its gradient (1) or the unit's pre-BN z (2)
+  void read_tensor(const std::string& scope, int kind, float* host, size_t bytes, int N) {
+    for (const Unit& u : units_)
+      if (u.scope == scope) {
+        const Act& a = acts_[u.out];
+        const size_t n = static_cast<size_t>(voxels_of(a.dims, N)) * a.C * sizeof(float);
+        if (bytes != n) throw std::invalid_argument("read_tensor size mismatch for " + scope);
+        const float* src = kind == 0 ? a.a : kind == 1 ? a.d : u.z;
+        VNB_CUDA_OK(cudaMemcpyAsync(host, src, n, cudaMemcpyDeviceToHost, stream_));
+        VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+        return;
+      }
+    throw std::invalid_argument("unknown scope: " + scope);
+  }
+  long long gpu_launches() const { return launches_; }
+
+  // ---- device timing ----------------------------------------------------------------------------
+  void event_record(int which) {
+#ifndef VNB_EMULATE
+    if (!timer_ev_[0]) {
+      VNB_CUDA_OK(cudaEventCreate(&timer_ev_[0]));
+      VNB_CUDA_OK(cudaEventCreate(&timer_ev_[1]));
+    }
+    VNB_CUDA_OK(cudaEventRecord(timer_ev_[which & 1], stream_));
+#else
+    (void)which;
+#endif
+  }
+  float event_elapsed_ms() {
+    float ms = 0.f;
+#ifndef VNB_EMULATE
+    VNB_CUDA_OK(cudaEventSynchronize(timer_ev_[1]));
+    VNB_CUDA_OK(cudaEventElapsedTime(&ms, timer_ev_[0], timer_ev_[1]));
+#endif
+    return ms;
+  }
+  void profile_enable(bool on) {
+    profiling_ = on;
+    prof_used_ = 0;
+  }
+  void profile_read(int cls, double* ms, long long* launches, double* flops) {
+    double t = 0, f = 0;
+    long long n = 0;
+#ifndef VNB_EMULATE
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+    for (size_t i = 0; i < prof_used_; ++i) {
+      if (prof_[i].cls != cls) continue;
+      float e = 0.f;
+      VNB_CUDA_OK(cudaEventElapsedTime(&e, prof_[i].a, prof_[i].b));
+      t += e;
+      f += prof_[i].flops;
+      ++n;
+    }
+#endif
+    *ms = t;
+    *launches = n;
+    *flops = f;
+  }
+  struct ProfScope {  // brackets one kernel launch with events when profiling is on
+    Engine& e;
+    long long idx = -1;
+    ProfScope(Engine& eng, int cls, double flops) : e(eng) {
+#ifndef VNB_EMULATE
+      if (!e.profiling_) return;
+      if (e.prof_used_ == e.prof_.size()) {
+        ProfRec r;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        e.prof_.push_back(r);
+      }
+      idx = static_cast<long long>(e.prof_used_++);
+      e.prof_[idx].cls = cls;
+      e.prof_[idx].flops = flops;
+      cudaEventRecord(e.prof_[idx].a, e.stream_);
+#else
+      (void)cls;
+      (void)flops;
+#endif
+    }
+    ~ProfScope() {
+#ifndef VNB_EMULATE
+      if (idx >= 0) cudaEventRecord(e.prof_[idx].b, e.stream_);
+#endif
+    }
+  };
+
+ private:
+  // ---- graph construction ---------------------------------------------------------------------
+  void validate() {
+    const EngineConfig& c = cfg_;
+    if (c.num_levels < 1 || c.num_levels > 8) throw std::invalid_argument("num_levels out of range");
+    if (c.num_classes < 1 || c.num_classes > kMaxClasses) throw std::invalid_argument("num_classes out of range (1..8)");
+    if (c.in_channels < 1 || c.max_batch < 1) throw std::invalid_argument("bad in_channels / max_batch");
+    for (int i = 0; i < 3; ++i)
+      if (c.patch[i] <= 0 || c.patch[i] % (1 << c.num_levels))
+        throw std::invalid_argument("PatchShape must be divisible by 2^NumLevels (odd skip sizes unsupported, SURVEY H7)");
+    if (c.num_channels * (1 << c.num_levels) > 256 && (c.num_channels * (1 << c.num_levels)) % 256)
+      throw std::invalid_argument("unsupported channel width");
+  }
+  long long voxels_of(const Dims& d, int N) const { return static_cast<long long>(N) * d.D * d.H * d.W; }
+  long long voxels(int N) const { return voxels_of(acts_[head_act_].dims, N); }
+
+  int add_act(int C, Dims dims, bool needs_grad = true) {
+    Act a;
+    a.C = C;
+    a.dims = dims;
+    a.needs_grad = needs_grad;
+    acts_.push_back(a);
+    return static_cast<int>(acts_.size()) - 1;
+  }
+  long long add_param(const std::string& name, std::initializer_list<long long> dims, bool trainable) {
+    ParamEntry e;
+    e.name = name;
+    e.ndim = static_cast<int>(dims.size());
+    size_t cnt = 1;
+    int i = 0;
+    for (long long d : dims) {
+      e.dims[i++] = d;
+      cnt *= static_cast<size_t>(d);
+    }
+    e.count = cnt;
+    e.trainable = trainable;
+    size_t& cursor = trainable ? n_train_ : n_state_;
+    e.offset = cursor;
+    cursor += (cnt + 3) & ~size_t(3);  // keep every tensor 16-byte aligned
+    index_[name] = entries_.size();
+    entries_.push_back(e);
+    return static_cast<long long>(e.offset);
+  }
+  void add_bn(Unit& u, int k, int C) {
+    const std::string base = u.scope + "/batch_normalization" + (k == 0 ? "" : "_" + std::to_string(k));
+    u.gamma_off[k] = add_param(base + "/gamma", {C}, true);
+    u.beta_off[k] = add_param(base + "/beta", {C}, true);
+    u.mm_off[k] = add_param(base + "/moving_mean", {C}, false);
+    u.mv_off[k] = add_param(base + "/moving_variance", {C}, false);
+  }
+  // registers parameters in TF creation order: weights, biases, BNs, alpha
+  int add_unit(int kind, const std::string& scope, int in1, int in2, int res, int Cout, Dims out_dims,
+               int chain, bool act, bool dropout) {
+    Unit u;
+    u.scope = scope;
+    u.kind = kind;
+    u.in1 = in1;
+    u.in2 = in2;
+    u.res = res;
+    u.Cin1 = acts_[in1].C;
+    u.Cin2 = in2 >= 0 ? acts_[in2].C : 0;
+    u.Cout = Cout;
+    u.chain = chain;
+    u.has_act = act;
+    u.has_dropout = dropout;
+    u.p_lo = n_train_;
+    const long long Cin = u.Cin1 + u.Cin2;
+    if (kind == U_CONV5) {
+      u.w_off = add_param(scope + "/weights", {5, 5, 5, Cin, Cout}, true);
+      u.w_count = 125ull * Cin * Cout;
+    } else if (kind == U_DOWN) {
+      u.w_off = add_param(scope + "/weights", {2, 2, 2, Cin, Cout}, true);
+      u.w_count = 8ull * Cin * Cout;
+    } else if (kind == U_UP) {  // layers2.py:92: [2,2,2,Cout,Cin]
+      u.w_off = add_param(scope + "/weights", {2, 2, 2, Cout, Cin}, true);
+      u.w_count = 8ull * Cin * Cout;
+    } else if (kind == U_CONV1) {
+      u.w_off = add_param(scope + "/weights", {1, 1, 1, Cin, Cout}, true);
+      u.w_count = static_cast<size_t>(Cin) * Cout;
+    }
+    if (kind != U_INPUT_TILE) u.b_off = add_param(scope + "/biases", {Cout}, true);
+    for (int k = 0; k < chain_num_bn(chain); ++k) add_bn(u, k, Cout);
+    if (act) u.alpha_off = add_param(scope + "/alpha", {Cout}, true);
+    u.out = add_act(Cout, out_dims);
+    units_.push_back(u);
+    return u.out;
+  }
+
+  void build_graph() {
+    const EngineConfig& c = cfg_;
+    Dims full{c.patch[0], c.patch[1], c.patch[2]};
+    const int C0 = c.num_channels;
+    image_act_ = add_act(c.in_channels, full, false);
+    int x;
+    if (c.in_channels == 1)  // networks.py:254-259
+      x = add_unit(U_INPUT_TILE, "vnet/input_layer", image_act_, -1, -1, C0, full, CH_S, false, false);
+    else                      // networks.py:260-266
+      x = add_unit(U_CONV5, "vnet/input_layer", image_act_, -1, -1, C0, full, CH_S, true, false);
+    std::vector<int> features;
+    Dims d = full;
+    for (int l = 0; l < c.num_levels; ++l) {  // networks.py:270-280
+      const int ch = C0 << l;
+      const std::string scope = "vnet/encoder/level_" + std::to_string(l + 1);
+      const int block_in = x, n = c.num_convolutions[l];
+      for (int i = 0; i < n; ++i)
+        x = add_unit(U_CONV5, scope + "/conv_" + std::to_string(i + 1), x, -1, i == n - 1 ? block_in : -1, ch, d, CH_S, true, true);
+      features.push_back(x);
+      Dims half{d.D / 2, d.H / 2, d.W / 2};
+      x = add_unit(U_DOWN, scope + "/down_convolution", x, -1, -1, 2 * ch, half, CH_S, true, false);
+      d = half;
+    }
+    {  // networks.py:282-283
+      const int ch = C0 << c.num_levels, block_in = x, n = c.bottom_convolutions;
+      for (int i = 0; i < n; ++i)
+        x = add_unit(U_CONV5, "vnet/bottom_level/conv_" + std::to_string(i + 1), x, -1, i == n - 1 ? block_in : -1, ch, d, CH_S, true, true);
+    }
+    for (int l = c.num_levels - 1; l >= 0; --l) {  // networks.py:285-296
+      const int ch = C0 << l;
+      const std::string scope = "vnet/decoder/level_" + std::to_string(l + 1);
+      const int f = features[l];
+      Dims up = acts_[f].dims;
+      x = add_unit(U_UP, scope + "/up_convolution", x, -1, -1, ch, up, CH_S, true, false);
+      const int n = c.num_convolutions[l];
+      if (n == 1) {  // networks.py:328-340
+        x = add_unit(U_CONV5, scope + "/conv_1", x, f, -1, ch, up, CH_T, true, true);
+      } else {       // networks.py:342-363
+        x = add_unit(U_CONV5, scope + "/conv_1", x, f, -1, ch, up, CH_S, true, true);
+        for (int i = 1; i < n; ++i)
+          x = add_unit(U_CONV5, scope + "/conv_" + std::to_string(i + 1), x, -1, -1, ch, up, i == n - 1 ? CH_Q : CH_D, true, true);
+      }
+      d = up;
+    }
+    head_act_ = add_unit(U_CONV1, "vnet/output_layer", x, -1, -1, c.num_classes, full, CH_S, false, false);  // networks.py:298-303
+
+    // gradient buckets for the data-parallel exchange: ~1/8 of the parameters each, cut at unit
+    // boundaries, listed in the order the backward pass completes them (last unit first)
+    {
+      const size_t target = std::max<size_t>(n_train_ / 8, 1u << 18);
+      int hi_unit = static_cast<int>(units_.size());
+      size_t hi_off = n_train_;
+      for (int ui = static_cast<int>(units_.size()) - 1; ui >= 0; --ui) {
+        if (hi_off - units_[ui].p_lo >= target || ui == 0) {
+          if (hi_off > units_[ui].p_lo) buckets_.push_back(Bucket{ui, hi_unit, units_[ui].p_lo, hi_off});
+          hi_unit = ui;
+          hi_off = units_[ui].p_lo;
+        }
+      }
+    }
+    // backward plan: walk units in reverse, first writer of each gradient buffer overwrites
+    std::vector<bool> written(acts_.size(), false);
+    written[head_act_] = true;  // dL/dlogits written by the loss kernel
+    for (int ui = static_cast<int>(units_.size()) - 1; ui >= 0; --ui) {
+      Unit& u = units_[ui];
+      if (u.res >= 0) {
+        u.res_accumulate = written[u.res];
+        written[u.res] = true;
+      }
+      u.need_dgrad = (u.kind != U_INPUT_TILE) && acts_[u.in1].needs_grad;
+      if (u.need_dgrad) {
+        u.in1_accumulate = written[u.in1];
+        written[u.in1] = true;
+        if (u.in2 >= 0) {
+          u.in2_accumulate = written[u.in2];
+          written[u.in2] = true;
+        }
+      }
+    }
+  }
+
+  template <class T>
+  T* dev_alloc(size_t count) {
+    void* p = nullptr;
+    VNB_CUDA_OK(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    allocs_.push_back(p);
+    return static_cast<T*>(p);
+  }
+
+  void allocate() {
+    const int NB = cfg_.max_batch;
+    params_ = dev_alloc<float>(n_train_);
+    grads_ = dev_alloc<float>(n_train_);
+    adam_m_ = dev_alloc<float>(n_train_);
+    adam_v_ = dev_alloc<float>(n_train_);
+    state_ = dev_alloc<float>(n_state_);
+    VNB_CUDA_OK(cudaMemset(grads_, 0, n_train_ * sizeof(float)));
+    VNB_CUDA_OK(cudaMemset(adam_m_, 0, n_train_ * sizeof(float)));
+    VNB_CUDA_OK(cudaMemset(adam_v_, 0, n_train_ * sizeof(float)));
+    const bool tc = cfg_.precision != PREC_FP32;
+    const bool lo = cfg_.precision == PREC_BF16X3;
+    size_t max_w5 = 0;
+    int maxC = 1;
+    for (Act& a : acts_) {
+      const size_t n = static_cast<size_t>(voxels_of(a.dims, NB)) * a.C;
+      a.a = dev_alloc<float>(n);
+      if (a.needs_grad) a.d = dev_alloc<float>(n);
+      if (tc) {
+        a.a_hi = dev_alloc<uint16_t>(n);
+        if (lo) a.a_lo = dev_alloc<uint16_t>(n);
+        if (a.needs_grad) {
+          a.d_hi = dev_alloc<uint16_t>(n);
+          if (lo) a.d_lo = dev_alloc<uint16_t>(n);
+        }
+      }
+      maxC = std::max(maxC, a.C);
+    }
+    for (Unit& u : units_) {
+      const Act& o = acts_[u.out];
+      const size_t n = static_cast<size_t>(voxels_of(o.dims, NB)) * o.C;
+      u.z = (u.kind == U_INPUT_TILE) ? acts_[u.in1].a : dev_alloc<float>(n);
+      u.mean = dev_alloc<double>(u.Cout);
+      u.var = dev_alloc<double>(u.Cout);
+      u.scale = dev_alloc<float>(u.Cout);
+      u.shift = dev_alloc<float>(u.Cout);
+      u.P = dev_alloc<float>(u.Cout);
+      u.Q = dev_alloc<float>(u.Cout);
+      u.S = dev_alloc<float>(u.Cout);
+      if (u.kind == U_CONV5) max_w5 = std::max(max_w5, u.w_count);
+    }
+    partial_ = dev_alloc<double>(static_cast<size_t>(kMaxRedBlocks) * 3 * std::max(maxC, 4 * kMaxClasses) + 64);
+    wflip_ = dev_alloc<float>(max_w5);
+    labels_dev_ = dev_alloc<int32_t>(voxels(NB));
+    softmax_dev_ = dev_alloc<float>(voxels(NB) * cfg_.num_classes);
+    argmax_dev_ = dev_alloc<long long>(voxels(NB));
+    loss_partial_ = dev_alloc<double>(static_cast<size_t>(NB) * kLossBlocks * kMaxClasses * 4);
+    terms_dev_ = dev_alloc<double>(static_cast<size_t>(NB) * kMaxClasses * 4);
+    coef_dev_ = dev_alloc<float>(static_cast<size_t>(NB) * kMaxClasses * 3);
+    loss_dev_ = dev_alloc<float>(4);
+#ifndef VNB_EMULATE
+    if (tc) tc_setup();
+#endif
+  }
+
+  void init_default_params() {  // biases 0, gamma 1, beta 0, moving mean 0 / variance 1, alpha 0.1; weights 0
+    std::vector<float> p(n_train_, 0.f), s(n_state_, 0.f);
+    for (const ParamEntry& e : entries_) {
+      const std::string& nm = e.name;
+      auto ends = [&](const char* suf) { const size_t l = strlen(suf); return nm.size() >= l && nm.compare(nm.size() - l, l, suf) == 0; };
+      float v = 0.f;
+      if (ends("/gamma") || ends("/moving_variance")) v = 1.f;
+      if (ends("/alpha")) v = 0.1f;
+      float* dst = (e.trainable ? p.data() : s.data()) + e.offset;
+      for (size_t i = 0; i < e.count; ++i) dst[i] = v;
+    }
+    VNB_CUDA_OK(cudaMemcpy(params_, p.data(), n_train_ * sizeof(float), cudaMemcpyHostToDevice));
+    VNB_CUDA_OK(cudaMemcpy(state_, s.data(), n_state_ * sizeof(float), cudaMemcpyHostToDevice));
+  }
+
+  // ---- helpers --------------------------------------------------------------------------------
+  static int grid_for(long long n, int block, int cap = kMaxRedBlocks * 2) {
+    long long b = (n + block - 1) / block;
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(b, cap)));
+  }
+  void check_batch(int N) const {
+    if (N < 1 || N > cfg_.max_batch) throw std::invalid_argument("batch size outside [1, max_batch]");
+  }
+  void upload_images(const float* images, int N) {
+    const Act& a = acts_[image_act_];
+    VNB_CUDA_OK(cudaMemcpyAsync(a.a, images, voxels_of(a.dims, N) * a.C * sizeof(float), cudaMemcpyHostToDevice, stream_));
+  }
+  void upload_labels(const int32_t* labels, int N) {
+    VNB_CUDA_OK(cudaMemcpyAsync(labels_dev_, labels, voxels(N) * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+  }
+  BnParams bn_params(const Unit& u) {
+    BnParams bp;
+    for (int k = 0; k < 3; ++k) {
+      const bool on = k < chain_num_bn(u.chain);
+      bp.gamma[k] = on ? params_ + u.gamma_off[k] : nullptr;
+      bp.beta[k] = on ? params_ + u.beta_off[k] : nullptr;
+      bp.moving_mean[k] = on ? state_ + u.mm_off[k] : nullptr;
+      bp.moving_var[k] = on ? state_ + u.mv_off[k] : nullptr;
+    }
+    return bp;
+  }
+  static RedGeom red_geom(int C, int c0, long long V) {
+    RedGeom g;
+    g.C = C;
+    g.c0 = c0;
+    g.CW = std::min(C - c0, 256);
+    g.V = V;
+    return g;
+  }
+  static int red_threads(const RedGeom& g) { return (kRedThreads / g.CW) * g.CW; }
+  static int red_blocks(const RedGeom& g) {
+    const long long per_block = static_cast<long long>(red_threads(g) / g.CW) * 16;  // >= 16 voxels per thread group
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((g.V + per_block - 1) / per_block, kMaxRedBlocks)));
+  }
+  LossCfg loss_cfg() const {
+    LossCfg lc;
+    lc.K = cfg_.num_classes;
+    const int l = cfg_.loss;
+    lc.jaccard = (l == LOSS_JACCARD || l == LOSS_WEIGHTED_JACCARD || l == LOSS_MIXED_JACCARD || l == LOSS_MIXED_WEIGHTED_JACCARD);
+    lc.use_dice = !(l == LOSS_XENT || l == LOSS_WEIGHTED_XENT);
+    lc.weighted_dice = (l == LOSS_WEIGHTED_SORENSEN || l == LOSS_WEIGHTED_JACCARD || l == LOSS_MIXED_WEIGHTED_SORENSEN || l == LOSS_MIXED_WEIGHTED_JACCARD);
+    lc.use_xent = (l == LOSS_XENT || l == LOSS_WEIGHTED_XENT || l >= LOSS_MIXED_SORENSEN);
+    lc.weighted_xent = (l == LOSS_WEIGHTED_XENT || l == LOSS_MIXED_WEIGHTED_SORENSEN || l == LOSS_MIXED_WEIGHTED_JACCARD);
+    lc.xent_alpha = (l >= LOSS_MIXED_SORENSEN) ? cfg_.loss_alpha : 1.0f;
+    lc.smooth = 1e-5f;
+    for (int i = 0; i < kMaxClasses; ++i) lc.w[i] = cfg_.loss_weights[i];
+    return lc;
+  }
+  static constexpr int kLossBlocks = 296;
+  int loss_blocks() const {
+    const long long Vn = voxels(1);
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((Vn + 2047) / 2048, kLossBlocks)));
+  }
+
+  // ---- forward --------------------------------------------------------------------------------
+  void run_conv_fprop(Unit& u, int N) {
+    const Act& x1 = acts_[u.in1];
+    const Act& o = acts_[u.out];
+    const float* bias = params_ + u.b_off;
+    if (u.kind == U_CONV5) {
+#ifndef VNB_EMULATE
+      if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid) {
+        tc_run_fprop(u, N);
+        return;
+      }
+#endif
+      Conv5Args p;
+      p.in1 = x1.a;
+      p.in2 = u.in2 >= 0 ? acts_[u.in2].a : nullptr;
+      p.C1 = u.Cin1;
+      p.C2 = u.Cin2;
+      p.w = params_ + u.w_off;
+      p.bias = bias;
+      p.res = u.res >= 0 ? acts_[u.res].a : nullptr;
+      p.out1 = u.z;
+      p.out2 = nullptr;
+      p.Co1 = u.Cout;
+      p.Co2 = 0;
+      p.acc1 = p.acc2 = 0;
+      p.dims = o.dims;
+      p.N = N;
+      ProfScope ps(*this, 0, conv5_flops(u, N));
+      launch_conv5(p);
+    } else if (u.kind == U_DOWN || u.kind == U_UP) {
+      K2Args p{};
+      p.w = params_ + u.w_off;
+      p.bias = bias;
+      p.N = N;
+      p.accumulate = 0;
+      if (u.kind == U_DOWN) {
+        p.fine_in = x1.a;
+        p.coarse_out = u.z;
+        p.CF = u.Cin1;
+        p.CC = u.Cout;
+        p.cd = o.dims;
+        const long long total = voxels_of(o.dims, N) * u.Cout;
+        VNB_LAUNCH(k2_gather_kernel, grid_for(total, 256), 256, 0, stream_, p);
+      } else {
+        p.coarse_in = x1.a;
+        p.fine_out = u.z;
+        p.CF = u.Cout;
+        p.CC = u.Cin1;
+        p.cd = x1.dims;
+        const long long total = voxels_of(o.dims, N) * u.Cout;
+        VNB_LAUNCH(k2_scatter_kernel, grid_for(total, 256), 256, 0, stream_, p);
+      }
+      ++launches_;
+    } else if (u.kind == U_CONV1) {
+      const long long V = voxels_of(o.dims, N);
+      VNB_LAUNCH(conv1_fprop_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, (const float*)x1.a,
+                 (const float*)(params_ + u.w_off), bias, u.z, V, u.Cin1, u.Cout);
+      ++launches_;
+    }
+  }
+  void launch_conv5(const Conv5Args& p) {
+    const Dims& d = p.dims;
+    const int tiles = ((d.W + kC5_TW - 1) / kC5_TW) * ((d.H + kC5_TH - 1) / kC5_TH) * ((d.D + kC5_TD - 1) / kC5_TD);
+    dim3 grid(tiles, (p.Co1 + p.Co2 + kC5_CO - 1) / kC5_CO, p.N);
+    launch_conv5_attr_once();
+    VNB_LAUNCH(conv5_ref_kernel, grid, 256, kC5_SMEM, stream_, p);
+    ++launches_;
+  }
+
+  void forward(int N, float dropout, uint64_t seed, bool update_moving) {
+#ifndef VNB_EMULATE
+    if (cfg_.precision != PREC_FP32) tc_prepare_weights();
+#endif
+    for (size_t ui = 0; ui < units_.size(); ++ui) {
+      Unit& u = units_[ui];
+      const Act& o = acts_[u.out];
+      const long long V = voxels_of(o.dims, N);
+      int nblk, nq_stride = 2;
+      if (u.kind == U_INPUT_TILE) {
+        nblk = grid_for(V, 256, kMaxRedBlocks);
+        VNB_LAUNCH(image_stats_kernel, nblk, 256, 0, stream_, (const float*)u.z, V, partial_);
+      } else {
+        run_conv_fprop(u, N);
+        RedGeom g = red_geom(u.Cout, 0, V);
+        nblk = red_blocks(g);
+        for (int c0 = 0; c0 < u.Cout; c0 += 256) {
+          g = red_geom(u.Cout, c0, V);
+          VNB_LAUNCH(bn_stats_kernel, nblk, red_threads(g), 0, stream_, (const float*)u.z, g, partial_);
+          ++launches_;
+        }
+      }
+      VNB_LAUNCH(bn_finalize_fwd_kernel, (u.Cout + 127) / 128, 128, 0, stream_, (const double*)partial_, nblk, nq_stride,
+                 u.Cout, static_cast<double>(V), u.chain, bn_params(u), u.kind == U_INPUT_TILE ? 1 : 0,
+                 update_moving ? 1 : 0, u.mean, u.var, u.scale, u.shift);
+      ApplyArgs ap;
+      ap.z = u.z;
+      ap.a = acts_[u.out].a;
+      ap.a_hi = acts_[u.out].a_hi;
+      ap.a_lo = acts_[u.out].a_lo;
+      ap.scale = u.scale;
+      ap.shift = u.shift;
+      ap.alpha = u.has_act ? params_ + u.alpha_off : nullptr;
+      ap.total = V * u.Cout;
+      ap.C = u.Cout;
+      ap.tiled_input = u.kind == U_INPUT_TILE ? 1 : 0;
+      ap.drop_rate = u.has_dropout ? dropout : 0.f;
+      ap.seed = seed;
+      ap.unit = static_cast<uint32_t>(ui);
+      VNB_LAUNCH(bn_apply_kernel, grid_for(ap.total, 256), 256, 0, stream_, ap);
+      launches_ += 3;
+    }
+  }
+
+  void loss_forward(int N) {
+    const LossCfg lc = loss_cfg();
+    const long long Vn = voxels(1);
+    const int nblk = loss_blocks();
+    dim3 grid(nblk, N);
+    VNB_LAUNCH(softmax_loss_fwd_kernel, grid, 256, 0, stream_, (const float*)acts_[head_act_].a,
+               (const int32_t*)labels_dev_, Vn, lc, (float*)nullptr, (long long*)nullptr, loss_partial_);
+    VNB_LAUNCH(loss_finalize_kernel, 1, 64, 0, stream_, (const double*)loss_partial_, N, nblk, Vn, lc, terms_dev_, coef_dev_, loss_dev_);
+    launches_ += 2;
+  }
+
+  // ---- backward -------------------------------------------------------------------------------
+  void backward(int N, float dropout, uint64_t seed) {
+    const LossCfg lc = loss_cfg();
+    const long long Vn = voxels(1);
+    dim3 lgrid(loss_blocks(), N);
+    VNB_LAUNCH(softmax_loss_bwd_kernel, lgrid, 256, 0, stream_, (const float*)acts_[head_act_].a,
+               (const int32_t*)labels_dev_, Vn, lc, (const float*)coef_dev_, 1.0f, acts_[head_act_].d);
+    ++launches_;
+    for (int ui = static_cast<int>(units_.size()) - 1; ui >= 0; --ui) {
+      Unit& u = units_[ui];
+      Act& o = acts_[u.out];
+      const long long V = voxels_of(o.dims, N);
+      BwdArgs b;
+      b.z = u.z;
+      b.d = o.d;
+      b.d_hi = (u.kind == U_CONV5) ? o.d_hi : nullptr;
+      b.d_lo = (u.kind == U_CONV5) ? o.d_lo : nullptr;
+      b.res_grad = u.res >= 0 ? acts_[u.res].d : nullptr;
+      b.res_accumulate = u.res_accumulate ? 1 : 0;
+      b.scale = u.scale;
+      b.shift = u.shift;
+      b.alpha = u.has_act ? params_ + u.alpha_off : nullptr;
+      b.mean = u.mean;
+      b.P = u.P;
+      b.Q = u.Q;
+      b.S = u.S;
+      b.C = u.Cout;
+      b.tiled_input = u.kind == U_INPUT_TILE ? 1 : 0;
+      b.drop_rate = u.has_dropout ? dropout : 0.f;
+      b.seed = seed;
+      b.unit = static_cast<uint32_t>(ui);
+      RedGeom g = red_geom(u.Cout, 0, V);
+      const int nblk = red_blocks(g);
+      for (int c0 = 0; c0 < u.Cout; c0 += 256) {
+        g = red_geom(u.Cout, c0, V);
+        VNB_LAUNCH(bn_bwd_reduce_kernel, nblk, red_threads(g), 0, stream_, b, g, partial_);
+        ++launches_;
+      }
+      BnGradPtrs gp;
+      for (int k = 0; k < 3; ++k) {
+        const bool on = k < chain_num_bn(u.chain);
+        gp.dgamma[k] = on ? grads_ + u.gamma_off[k] : nullptr;
+        gp.dbeta[k] = on ? grads_ + u.beta_off[k] : nullptr;
+      }
+      gp.dalpha = u.has_act ? grads_ + u.alpha_off : nullptr;
+      VNB_LAUNCH(bn_finalize_bwd_kernel, (u.Cout + 127) / 128, 128, 0, stream_, (const double*)partial_, nblk, u.Cout,
+                 static_cast<double>(V), u.chain, bn_params(u), (const double*)u.var, gp, u.P, u.Q, u.S);
+      ++launches_;
+      if (u.kind == U_INPUT_TILE) {  // image needs no gradient
+        notify_bucket(ui);
+        continue;
+      }
+      VNB_LAUNCH(bn_bwd_apply_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, b, V * u.Cout);
+      ++launches_;
+      run_conv_backward(u, N);
+      notify_bucket(ui);
+    }
+  }
+  void notify_bucket(int ui) {
+    if (!grad_hook_) return;
+    for (size_t b = 0; b < buckets_.size(); ++b)
+      if (buckets_[b].unit_lo == ui) grad_hook_(static_cast<int>(b));
+  }
+
+  void run_conv_backward(Unit& u, int N) {
+    const Act& x1 = acts_[u.in1];
+    const Act& o = acts_[u.out];
+    float* dw = grads_ + u.w_off;
+    const float* dz = o.d;
+    VNB_CUDA_OK(cudaMemsetAsync(dw, 0, u.w_count * sizeof(float), stream_));
+    VNB_CUDA_OK(cudaMemsetAsync(grads_ + u.b_off, 0, u.Cout * sizeof(float), stream_));
+    if (u.kind == U_CONV5) {
+      const int Cin = u.Cin1 + u.Cin2;
+#ifndef VNB_EMULATE
+      const bool tc = cfg_.precision != PREC_FP32;
+      if (tc && u.need_dgrad && u.tc.dgrad.valid) {
+        tc_run_dgrad(u, N);
+      } else
+#endif
+      if (u.need_dgrad) {
+        VNB_LAUNCH(flip_transpose_w5_kernel, grid_for(static_cast<long long>(u.w_count), 256), 256, 0, stream_,
+                   (const float*)(params_ + u.w_off), wflip_, Cin, u.Cout);
+        ++launches_;
+        Conv5Args p;
+        p.in1 = dz;
+        p.in2 = nullptr;
+        p.C1 = u.Cout;
+        p.C2 = 0;
+        p.w = wflip_;
+        p.bias = nullptr;
+        p.res = nullptr;
+        p.out1 = x1.d;
+        p.Co1 = u.Cin1;
+        p.acc1 = u.in1_accumulate ? 1 : 0;
+        p.out2 = u.in2 >= 0 ? acts_[u.in2].d : nullptr;
+        p.Co2 = u.Cin2;
+        p.acc2 = u.in2_accumulate ? 1 : 0;
+        p.dims = o.dims;
+        p.N = N;
+        ProfScope ps(*this, 0, conv5_flops(u, N));
+        launch_conv5(p);
+      }
+#ifndef VNB_EMULATE
+      if (tc && u.tc.wgrad.valid) {
+        tc_run_wgrad(u, N);
+        return;
+      }
+#endif
+      Wgrad5Args w;
+      w.in1 = x1.a;
+      w.in2 = u.in2 >= 0 ? acts_[u.in2].a : nullptr;
+      w.C1 = u.Cin1;
+      w.C2 = u.Cin2;
+      w.dz = dz;
+      w.Cout = u.Cout;
+      w.dw = dw;
+      w.dims = o.dims;
+      w.N = N;
+      const Dims& d = o.dims;
+      const long long ntiles = static_cast<long long>((d.W + kW5_TW - 1) / kW5_TW) * ((d.H + kW5_TH - 1) / kW5_TH) *
+                               ((d.D + kW5_TD - 1) / kW5_TD) * N;
+      const int pairs = ((Cin + 15) / 16) * ((u.Cout + 15) / 16);
+      long long splits = std::max<long long>(1, std::min<long long>(ntiles, (2 * 1184 + pairs - 1) / pairs));
+      w.tiles_per_block = static_cast<int>((ntiles + splits - 1) / splits);
+      splits = (ntiles + w.tiles_per_block - 1) / w.tiles_per_block;
+      dim3 grid(static_cast<unsigned>(splits), pairs);
+      launch_conv5_attr_once();
+      {
+        ProfScope ps(*this, 1, conv5_flops(u, N));
+        VNB_LAUNCH(conv5_wgrad_ref_kernel, grid, 256, kW5_SMEM, stream_, w);
+      }
+      ++launches_;
+    } else if (u.kind == U_DOWN || u.kind == U_UP) {
+      K2Args p{};
+      p.w = params_ + u.w_off;
+      p.dw = dw;
+      p.N = N;
+      if (u.kind == U_DOWN) {  // z coarse, x fine
+        p.CF = u.Cin1;
+        p.CC = u.Cout;
+        p.cd = o.dims;
+        p.coarse_in = dz;
+        p.fine_in = x1.a;
+        if (u.need_dgrad) {
+          p.fine_out = x1.d;
+          p.accumulate = u.in1_accumulate ? 1 : 0;
+          const long long total = voxels_of(x1.dims, N) * u.Cin1;
+          VNB_LAUNCH(k2_scatter_kernel, grid_for(total, 256), 256, 0, stream_, p);
+          ++launches_;
+        }
+      } else {  // z fine, x coarse
+        p.CF = u.Cout;
+        p.CC = u.Cin1;
+        p.cd = x1.dims;
+        p.fine_in = dz;
+        if (u.need_dgrad) {
+          p.coarse_out = x1.d;
+          p.accumulate = u.in1_accumulate ? 1 : 0;
+          const long long total = voxels_of(x1.dims, N) * u.Cin1;
+          VNB_LAUNCH(k2_gather_kernel, grid_for(total, 256), 256, 0, stream_, p);
+          ++launches_;
+        }
+        p.coarse_in = x1.a;
+      }
+      p.bias = nullptr;
+      const long long Vc = voxels_of(p.cd, N);
+      const long long outs = 8LL * p.CF * p.CC;
+      const int oblocks = static_cast<int>((outs + 255) / 256);
+      long long splits = std::max<long long>(1, std::min<long long>(Vc, (2 * 1184 + oblocks - 1) / oblocks));
+      const int vps = static_cast<int>((Vc + splits - 1) / splits);
+      splits = (Vc + vps - 1) / vps;
+      dim3 grid(oblocks, static_cast<unsigned>(splits));
+      VNB_LAUNCH(k2_wgrad_kernel, grid, 256, 0, stream_, p, vps);
+      ++launches_;
+    } else if (u.kind == U_CONV1) {
+      const long long V = voxels_of(o.dims, N);
+      if (u.need_dgrad) {
+        VNB_LAUNCH(conv1_dgrad_kernel, grid_for(V * u.Cin1, 256), 256, 0, stream_, dz, (const float*)(params_ + u.w_off),
+                   x1.d, V, u.Cin1, u.Cout, u.in1_accumulate ? 1 : 0);
+        ++launches_;
+      }
+      const int vpb = 2048;
+      const int blocks = static_cast<int>((V + vpb - 1) / vpb);
+      const int threads = ((u.Cin1 * u.Cout + 31) / 32) * 32;
+      VNB_LAUNCH(conv1_wgrad_kernel, blocks, threads, 0, stream_, (const float*)x1.a, dz, dw, V, u.Cin1, u.Cout, vpb);
+      ++launches_;
+    }
+  }
+  double conv5_flops(const Unit& u, int N) const {  // 2*MAC of one 5^3 pass (fprop = dgrad = wgrad)
+    return 2.0 * 125.0 * (u.Cin1 + u.Cin2) * u.Cout * static_cast<double>(voxels_of(acts_[u.out].dims, N));
+  }
+  void launch_conv5_attr_once() {
+#ifndef VNB_EMULATE
+    static bool attr_set = false;
+    if (!attr_set) {
+      VNB_CUDA_OK(cudaFuncSetAttribute(conv5_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5_SMEM));
+      VNB_CUDA_OK(cudaFuncSetAttribute(conv5_wgrad_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kW5_SMEM));
+      attr_set = true;
+    }
+#endif
+  }
+
+#ifndef VNB_EMULATE
+  // tensor-core path (conv_tc.cuh)
+  void tc_setup();
+  void tc_prepare_weights();
+  void tc_run_fprop(Unit& u, int N);
+  void tc_run_dgrad(Unit& u, int N);
+  void tc_run_wgrad(Unit& u, int N);
+#endif
+
+  EngineConfig cfg_;
+  cudaStream_t stream_ = 0;
+  std::vector<ParamEntry> entries_;
+  std::map<std::string, size_t> index_;
+  std::vector<Act> acts_;
+  std::vector<Unit> units_;
+  std::vector<void*> allocs_;
+  std::vector<Bucket> buckets_;
+  std::function<void(int)> grad_hook_;
+  size_t n_train_ = 0, n_state_ = 0;
+  int image_act_ = -1, head_act_ = -1;
+  float *params_ = nullptr, *grads_ = nullptr, *adam_m_ = nullptr, *adam_v_ = nullptr, *state_ = nullptr;
+  double* partial_ = nullptr;
+  float* wflip_ = nullptr;
+  int32_t* labels_dev_ = nullptr;
+  float* softmax_dev_ = nullptr;
+  long long* argmax_dev_ = nullptr;
+  double *loss_partial_ = nullptr, *terms_dev_ = nullptr;
+  float *coef_dev_ = nullptr, *loss_dev_ = nullptr;
+  long long global_step_ = 0;
+  float grad_scale_ = 1.0f;
+  bool weights_dirty_ = true;
+  long long launches_ = 0;
+  bool profiling_ = false;
+  struct ProfRec {
+    cudaEvent_t a{}, b{};
+    int cls = 0;
+    double flops = 0;
+  };
+  std::vector<ProfRec> prof_;
+  size_t prof_used_ = 0;
+  cudaEvent_t timer_ev_[2] = {};
+};
+
+}  // namespace vnb

@@ -1,0 +1,532 @@
+// HBM-bound kernels of the V-Net hot path: per-channel batch-norm statistics, the fused
+// BN-chain + PReLU + dropout apply pass, their backward passes, softmax + Dice/Jaccard/x-ent
+// reductions (forward, argmax, backward), and the multi-tensor Adam/SGD step.
+//
+// Reference semantics restated (paths relative to /root/reference):
+//   tf.layers.batch_normalization(training=True)     networks.py:259..361  -> bn_stats / bn_finalize / bn_apply
+//   prelu                                           layers2.py:97-99      -> bn_apply (fused)
+//   tf.nn.dropout(rate)                             networks.py:321..363  -> bn_apply (fused, counter RNG)
+//   softmax / one_hot / dice_coe / x-ent / argmax   model.py:26-92,447,477,495-568 -> softmax_loss_*
+//   exponential_decay + Adam/SGD                    model.py:641-660      -> optimizer_step
+//
+// Layout: activations are NDHWC fp32, i.e. a [V][C] matrix per tensor with V = N*D*H*W voxels and
+// channels fastest.  All per-channel reductions are two-stage and deterministic: each block writes a
+// partial in double precision, a single-block finalize kernel sums the partials in index order.
+#pragma once
+#include "bn_chain.h"
+#include "vnb_cuda.h"
+
+namespace vnb {
+
+constexpr int kRedThreads = 256;   // upper bound; actual block = (256 / CW) * CW threads
+constexpr int kMaxRedBlocks = 1184; // 8 blocks per SM on 148 SMs
+constexpr float kBnEps = 1e-3f;     // networks.py:259 epsilon=0.001
+constexpr float kBnMomentum = 0.99f;
+
+// ---------------------------------------------------------------------------------------------
+// counter-based dropout RNG: keep-mask is a pure function of (seed, unit, element index), so the
+// backward pass regenerates it instead of storing it.  tf.nn.dropout keeps where u >= rate.
+// ---------------------------------------------------------------------------------------------
+VNB_HD uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+VNB_HD float dropout_uniform(uint64_t seed, uint32_t unit, uint64_t idx) {
+  uint64_t h = mix64(seed ^ mix64((static_cast<uint64_t>(unit) << 40) ^ idx));
+  return static_cast<float>(h >> 40) * (1.0f / 16777216.0f);  // 24-bit mantissa, [0,1)
+}
+
+// ---------------------------------------------------------------------------------------------
+// block-level per-channel combine. Thread t owns channel (t % CW); acc[] are its private sums.
+// partial layout: [block][NQ][C] doubles.
+// ---------------------------------------------------------------------------------------------
+template <int NQ>
+__device__ __forceinline__ void block_channel_combine(const double (&acc)[NQ], int CW, int C, int c0,
+                                                      double* __restrict__ partial) {
+  __shared__ double red[NQ][kRedThreads];
+  const int t = threadIdx.x, nt = blockDim.x;
+  for (int q = 0; q < NQ; ++q) red[q][t] = acc[q];
+  __syncthreads();
+  if (t < CW) {
+    for (int q = 0; q < NQ; ++q) {
+      double s = 0.0;
+      for (int g = t; g < nt; g += CW) s += red[q][g];
+      partial[(static_cast<size_t>(blockIdx.x) * NQ + q) * C + c0 + t] = s;
+    }
+  }
+}
+
+struct RedGeom {  // how a [V][C] tensor (or a channel window of it) is spread over a reduction grid
+  int C, c0, CW;  // total channels, window start, window width (CW <= 256, blockDim % CW == 0)
+  long long V;
+};
+
+// element loop used by every per-channel reduction: thread t -> channel c0 + t % CW,
+// voxels (blockIdx*G + t / CW) + k * gridDim*G, G = blockDim / CW voxel groups per block
+#define VNB_CHANNEL_LOOP(geom, v, c)                                              \
+  const int c = (geom).c0 + static_cast<int>(threadIdx.x) % (geom).CW;            \
+  const long long vstep_ = static_cast<long long>(gridDim.x) * (blockDim.x / (geom).CW); \
+  for (long long v = static_cast<long long>(blockIdx.x) * (blockDim.x / (geom).CW) + threadIdx.x / (geom).CW; \
+       v < (geom).V; v += vstep_)
+
+// ---------------------------------------------------------------------------------------------
+// BN forward statistics: partial[blk][2][C] = (sum z, sum z^2)
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_stats_kernel(const float* __restrict__ z, RedGeom g, double* __restrict__ partial) {
+  double acc[2] = {0.0, 0.0};
+  float s = 0.f, s2 = 0.f;
+  int cnt = 0;
+  VNB_CHANNEL_LOOP(g, v, c) {
+    const float x = z[v * g.C + c];
+    s += x;
+    s2 += x * x;
+    if (++cnt == 64) {  // flush fp32 running sums into double every 64 elements
+      acc[0] += s;
+      acc[1] += s2;
+      s = s2 = 0.f;
+      cnt = 0;
+    }
+  }
+  acc[0] += s;
+  acc[1] += s2;
+  block_channel_combine<2>(acc, g.CW, g.C, g.c0, partial);
+}
+
+// input layer, in_channels == 1 (networks.py:254-259): statistics of the single-channel image
+__global__ void image_stats_kernel(const float* __restrict__ img, long long V, double* __restrict__ partial) {
+  double acc[2] = {0.0, 0.0};
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const double x = img[v];
+    acc[0] += x;
+    acc[1] += x * x;
+  }
+  __shared__ double red[2][kRedThreads];
+  red[0][threadIdx.x] = acc[0];
+  red[1][threadIdx.x] = acc[1];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, b = 0;
+    for (unsigned i = 0; i < blockDim.x; ++i) {
+      a += red[0][i];
+      b += red[1][i];
+    }
+    partial[blockIdx.x * 2 + 0] = a;
+    partial[blockIdx.x * 2 + 1] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BN forward finalize: partial sums -> mu, sigma^2 -> chain closed form -> scale/shift; optional
+// moving-average update (only train_op runs UPDATE_OPS, model.py:665-666).
+// One thread per channel. `single_channel_stats`: all channels share partial column 0 (tiled input).
+// ---------------------------------------------------------------------------------------------
+struct BnParams {       // device pointers into the flat parameter / state buffers
+  const float* gamma[3];
+  const float* beta[3];
+  float* moving_mean[3];
+  float* moving_var[3];
+};
+
+__global__ void bn_finalize_fwd_kernel(const double* __restrict__ partial, int nblk, int nq_stride, int C,
+                                       double count, int chain, BnParams bp, int single_channel_stats,
+                                       int update_moving, double* __restrict__ mean_out,
+                                       double* __restrict__ var_out, float* __restrict__ scale_out,
+                                       float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int pc = single_channel_stats ? 0 : c;
+  const int PC = single_channel_stats ? 1 : C;
+  double s = 0.0, s2 = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += partial[(static_cast<size_t>(b) * nq_stride + 0) * PC + pc];
+    s2 += partial[(static_cast<size_t>(b) * nq_stride + 1) * PC + pc];
+  }
+  const double mu = s / count;
+  double var = s2 / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  double gam[3] = {1, 1, 1}, bet[3] = {0, 0, 0};
+  const int nbn = chain_num_bn(chain);
+  for (int k = 0; k < nbn; ++k) {
+    gam[k] = bp.gamma[k][c];
+    bet[k] = bp.beta[k][c];
+  }
+  const ChainOut o = chain_eval(chain, var, gam, bet, static_cast<double>(kBnEps));
+  mean_out[c] = mu;
+  var_out[c] = var;
+  const double A = o.A.v, B = bet[o.beta_idx];
+  scale_out[c] = static_cast<float>(A);
+  shift_out[c] = static_cast<float>(B - A * mu);
+  if (update_moving) {
+    for (int k = 0; k < nbn; ++k) {
+      const float bm = static_cast<float>((o.mean_is_mu[k] ? mu : 0.0) + o.bn_mean[k]);
+      const float bv = static_cast<float>(o.bn_var[k]);
+      // assign_moving_average: var -= (var - value) * (1 - momentum)
+      bp.moving_mean[k][c] -= (bp.moving_mean[k][c] - bm) * (1.0f - kBnMomentum);
+      bp.moving_var[k][c] -= (bp.moving_var[k][c] - bv) * (1.0f - kBnMomentum);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused apply: a = dropout(prelu(scale*z + shift)); optional bf16 hi (+lo) copies for the
+// tensor-core convolution path (a ~= hi + lo, lo = bf16(a - hi)).
+// ---------------------------------------------------------------------------------------------
+struct ApplyArgs {
+  const float* z;        // [V][C] pre-BN tensor; for the tiled input layer: [V][1] image
+  float* a;              // [V][C] output activation (fp32)
+  uint16_t* a_hi;        // optional bf16 copies (nullptr = skip)
+  uint16_t* a_lo;
+  const float* scale;    // [C]
+  const float* shift;    // [C]
+  const float* alpha;    // [C] or nullptr (no activation: input layer M==1, output layer)
+  long long total;       // V*C
+  int C;
+  int tiled_input;       // z has one channel, broadcast over C (tf.tile, networks.py:258)
+  float drop_rate;       // 0 = identity
+  uint64_t seed;
+  uint32_t unit;
+};
+
+__global__ void bn_apply_kernel(ApplyArgs p) {
+  const float keep_scale = p.drop_rate > 0.f ? 1.0f / (1.0f - p.drop_rate) : 1.0f;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % p.C);
+    const float zin = p.tiled_input ? p.z[i / p.C] : p.z[i];
+    float y = p.scale[c] * zin + p.shift[c];
+    if (p.alpha) y = y > 0.f ? y : p.alpha[c] * y;  // max(0,y) + alpha*min(0,y)
+    if (p.drop_rate > 0.f) y = dropout_uniform(p.seed, p.unit, static_cast<uint64_t>(i)) >= p.drop_rate ? y * keep_scale : 0.f;
+    p.a[i] = y;
+    if (p.a_hi) {
+      const uint16_t hi = f32_to_bf16(y);
+      p.a_hi[i] = hi;
+      if (p.a_lo) p.a_lo[i] = f32_to_bf16(y - bf16_to_f32(hi));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward of the fused apply + BN chain.
+//   d    = dL/da (after the consumers accumulated into it)
+//   g    = dL/dyhat = dropout_bwd(d) * prelu'(yhat)          yhat = scale*z + shift
+//   R0 = sum g, R1 = sum g*(z - mu), Ralpha = sum dropout_bwd(d) * min(yhat, 0)
+// ---------------------------------------------------------------------------------------------
+struct BwdArgs {
+  const float* z;       // [V][C] (or [V][1] for the tiled input layer)
+  float* d;             // [V][C] in: dL/da ; out (apply kernel): dL/dz, in place
+  uint16_t* d_hi;       // optional bf16 copies of dL/dz for the tensor-core dgrad/wgrad
+  uint16_t* d_lo;
+  float* res_grad;      // optional: residual branch gradient target (block input's dL/da)
+  int res_accumulate;   // 0: write, 1: add
+  const float* scale;
+  const float* shift;
+  const float* alpha;   // or nullptr
+  const double* mean;   // [C]
+  const float* P;       // [C] coefficients from bn_finalize_bwd (apply kernel only)
+  const float* Q;
+  const float* S;
+  int C;
+  int tiled_input;
+  float drop_rate;
+  uint64_t seed;
+  uint32_t unit;
+};
+
+__device__ __forceinline__ float bwd_g(const BwdArgs& p, long long i, int c, float zin, float& yhat, float& dd) {
+  yhat = p.scale[c] * zin + p.shift[c];
+  dd = p.d[i];
+  if (p.drop_rate > 0.f)
+    dd = dropout_uniform(p.seed, p.unit, static_cast<uint64_t>(i)) >= p.drop_rate ? dd / (1.0f - p.drop_rate) : 0.f;
+  if (!p.alpha) return dd;
+  // TF gradients of maximum(0,y)/minimum(0,y): 1 for y>0, alpha for y<0, 0 at the tie
+  return yhat > 0.f ? dd : (yhat < 0.f ? dd * p.alpha[c] : 0.f);
+}
+
+__global__ void bn_bwd_reduce_kernel(BwdArgs p, RedGeom g, double* __restrict__ partial) {
+  double acc[3] = {0.0, 0.0, 0.0};
+  VNB_CHANNEL_LOOP(g, v, c) {
+    const long long i = v * g.C + c;
+    const float zin = p.tiled_input ? p.z[v] : p.z[i];
+    float yhat, dd;
+    const float gg = bwd_g(p, i, c, zin, yhat, dd);
+    acc[0] += gg;
+    acc[1] += static_cast<double>(gg) * (static_cast<double>(zin) - p.mean[c]);
+    if (p.alpha && yhat < 0.f) acc[2] += static_cast<double>(dd) * yhat;
+  }
+  block_channel_combine<3>(acc, g.CW, g.C, g.c0, partial);
+}
+
+struct BnGradPtrs {  // where the parameter gradients go (flat gradient buffer), nullptr = none
+  float* dgamma[3];
+  float* dbeta[3];
+  float* dalpha;
+};
+
+__global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int nblk, int C, double count,
+                                       int chain, BnParams bp, const double* __restrict__ var,
+                                       BnGradPtrs gp, float* __restrict__ P, float* __restrict__ Q,
+                                       float* __restrict__ S) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double R0 = 0, R1 = 0, Ra = 0;
+  for (int b = 0; b < nblk; ++b) {
+    R0 += partial[(static_cast<size_t>(b) * 3 + 0) * C + c];
+    R1 += partial[(static_cast<size_t>(b) * 3 + 1) * C + c];
+    Ra += partial[(static_cast<size_t>(b) * 3 + 2) * C + c];
+  }
+  double gam[3] = {1, 1, 1}, bet[3] = {0, 0, 0};
+  const int nbn = chain_num_bn(chain);
+  for (int k = 0; k < nbn; ++k) {
+    gam[k] = bp.gamma[k][c];
+    bet[k] = bp.beta[k][c];
+  }
+  const ChainOut o = chain_eval(chain, var[c], gam, bet, static_cast<double>(kBnEps));
+  P[c] = static_cast<float>(o.A.v);
+  Q[c] = static_cast<float>(-o.A.v * R0 / count);
+  S[c] = static_cast<float>(2.0 * o.A.d[0] * R1 / count);
+  for (int k = 0; k < nbn; ++k) {
+    if (gp.dgamma[k]) gp.dgamma[k][c] = static_cast<float>(R1 * o.A.d[1 + k]);
+    if (gp.dbeta[k]) gp.dbeta[k][c] = (k == o.beta_idx) ? static_cast<float>(R0) : 0.f;
+  }
+  if (gp.dalpha) gp.dalpha[c] = static_cast<float>(Ra);
+}
+
+// dL/dz = P*g + Q + S*(z - mu), in place over d; optional residual-branch gradient and bf16 copies
+__global__ void bn_bwd_apply_kernel(BwdArgs p, long long total) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % p.C);
+    const float zin = p.z[i];
+    float yhat, dd;
+    const float gg = bwd_g(p, i, c, zin, yhat, dd);
+    const float dz = p.P[c] * gg + p.Q[c] + p.S[c] * (zin - static_cast<float>(p.mean[c]));
+    p.d[i] = dz;
+    if (p.res_grad) p.res_grad[i] = p.res_accumulate ? p.res_grad[i] + dz : dz;
+    if (p.d_hi) {
+      const uint16_t hi = f32_to_bf16(dz);
+      p.d_hi[i] = hi;
+      if (p.d_lo) p.d_lo[i] = f32_to_bf16(dz - bf16_to_f32(hi));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// softmax + loss reductions (model.py:447,477,26-92,495-560) and argmax (model.py:568)
+// partial layout: [n][blk][K][4] = (I, L, R, X) with X = sum_v cw[t_v] * (-log p_{t_v}) [t==c slot]
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxClasses = 8;
+
+struct LossCfg {
+  int K;
+  int jaccard;            // 0 sorensen, 1 jaccard
+  int weighted_dice;      // use class weights in the dice term
+  int use_dice;           // dice term present
+  int use_xent;           // cross-entropy term present
+  int weighted_xent;      // class-weighted cross entropy
+  float xent_alpha;       // multiplier of the x-ent term (Loss.Alpha for mixed_*, 1 for pure)
+  float smooth;           // 1e-5
+  float w[kMaxClasses];   // Loss.Weights
+};
+
+__global__ void softmax_loss_fwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
+                                        long long Vn /*voxels per sample*/, LossCfg cfg,
+                                        float* __restrict__ softmax_out, long long* __restrict__ argmax_out,
+                                        double* __restrict__ partial) {
+  const int K = cfg.K, n = blockIdx.y;
+  double acc[kMaxClasses][4];
+  for (int c = 0; c < K; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < Vn;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long gv = static_cast<long long>(n) * Vn + v;
+    float x[kMaxClasses];
+    float mx = -3.4e38f;
+    int am = 0;
+    for (int c = 0; c < K; ++c) {
+      x[c] = logits[gv * K + c];
+      if (x[c] > mx) {  // strict > : lowest index wins ties (tf.argmax)
+        mx = x[c];
+        am = c;
+      }
+    }
+    float se = 0.f;
+    for (int c = 0; c < K; ++c) {
+      x[c] = expf(x[c] - mx);
+      se += x[c];
+    }
+    const float inv = 1.0f / se;
+    const int t = labels ? labels[gv] : -1;
+    for (int c = 0; c < K; ++c) {
+      const float pc = x[c] * inv;
+      if (softmax_out) softmax_out[gv * K + c] = pc;
+      const float tc = (t == c) ? 1.f : 0.f;
+      acc[c][0] += pc * tc;
+      acc[c][1] += cfg.jaccard ? pc * pc : pc;
+      acc[c][2] += tc;  // t*t == t
+      if (t == c) acc[c][3] += -static_cast<double>(logf(pc > 1e-38f ? pc : 1e-38f));
+    }
+    if (argmax_out) argmax_out[gv] = am;
+  }
+  if (!partial) return;
+  __shared__ double red[kRedThreads];
+  for (int c = 0; c < K; ++c)
+    for (int q = 0; q < 4; ++q) {
+      red[threadIdx.x] = acc[c][q];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (unsigned i = 0; i < blockDim.x; ++i) s += red[i];
+        partial[((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * K + c) * 4 + q] = s;
+      }
+      __syncthreads();
+    }
+}
+
+// single block: sums partials, evaluates the configured loss and d(loss)/d(I,L,X) per (n,c)
+// terms_out [N][K][4]; coef_out [N][K][3] = (dLoss/dI, dLoss/dL, dLoss/dX-per-voxel-weight)
+__global__ void loss_finalize_kernel(const double* __restrict__ partial, int N, int nblk, long long Vn,
+                                     LossCfg cfg, double* __restrict__ terms_out, float* __restrict__ coef_out,
+                                     float* __restrict__ loss_out) {
+  const int K = cfg.K;
+  const int pairs = N * K;
+  for (int pr = threadIdx.x; pr < pairs; pr += blockDim.x) {
+    const int n = pr / K, c = pr % K;
+    for (int q = 0; q < 4; ++q) {
+      double s = 0.0;
+      for (int b = 0; b < nblk; ++b) s += partial[((static_cast<size_t>(n) * nblk + b) * K + c) * 4 + q];
+      terms_out[(static_cast<size_t>(n) * K + c) * 4 + q] = s;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double loss = 0.0;
+  const double s = cfg.smooth;
+  for (int i = 0; i < pairs * 3; ++i) coef_out[i] = 0.f;
+  if (cfg.use_dice) {
+    double dice = 0.0;
+    if (cfg.weighted_dice) {  // model.py:70-75
+      for (int n = 0; n < N; ++n) {
+        double num = 0.0, den = 0.0;
+        for (int c = 0; c < K; ++c) {
+          const double* t = terms_out + (static_cast<size_t>(n) * K + c) * 4;
+          num += 2.0 * cfg.w[c] * t[0] + s;
+          den += cfg.w[c] * (t[1] + t[2]) + s;
+        }
+        dice += num / den / N;
+        for (int c = 0; c < K; ++c) {
+          float* co = coef_out + (static_cast<size_t>(n) * K + c) * 3;
+          co[0] = static_cast<float>(-(2.0 * cfg.w[c] / den) / N);          // d(1-dice)/dI
+          co[1] = static_cast<float>((num * cfg.w[c] / (den * den)) / N);   // d(1-dice)/dL
+        }
+      }
+    } else {  // model.py:82-83
+      for (int n = 0; n < N; ++n)
+        for (int c = 0; c < K; ++c) {
+          const double* t = terms_out + (static_cast<size_t>(n) * K + c) * 4;
+          const double num = 2.0 * t[0] + s, den = t[1] + t[2] + s;
+          dice += num / den / pairs;
+          float* co = coef_out + (static_cast<size_t>(n) * K + c) * 3;
+          co[0] = static_cast<float>(-(2.0 / den) / pairs);
+          co[1] = static_cast<float>((num / (den * den)) / pairs);
+        }
+    }
+    loss += 1.0 - dice;
+  }
+  if (cfg.use_xent) {  // reduce_mean over all N*V voxels (model.py:91,496)
+    double xs = 0.0;
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < K; ++c) {
+        const double wc = cfg.weighted_xent ? cfg.w[c] : 1.0;
+        xs += wc * terms_out[(static_cast<size_t>(n) * K + c) * 4 + 3];
+        coef_out[(static_cast<size_t>(n) * K + c) * 3 + 2] =
+            static_cast<float>(cfg.xent_alpha * wc / (static_cast<double>(N) * Vn));
+      }
+    loss += cfg.xent_alpha * xs / (static_cast<double>(N) * Vn);
+  }
+  loss_out[0] = static_cast<float>(loss);
+}
+
+// dL/dlogits, written to `dlogits` (the output layer's activation-gradient buffer)
+__global__ void softmax_loss_bwd_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
+                                        long long Vn, LossCfg cfg, const float* __restrict__ coef,
+                                        float grad_scale, float* __restrict__ dlogits) {
+  const int K = cfg.K, n = blockIdx.y;
+  float cI[kMaxClasses], cL[kMaxClasses], cX[kMaxClasses];
+  for (int c = 0; c < K; ++c) {
+    cI[c] = coef[(static_cast<size_t>(n) * K + c) * 3 + 0];
+    cL[c] = coef[(static_cast<size_t>(n) * K + c) * 3 + 1];
+    cX[c] = coef[(static_cast<size_t>(n) * K + c) * 3 + 2];
+  }
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < Vn;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long gv = static_cast<long long>(n) * Vn + v;
+    float p[kMaxClasses];
+    float mx = -3.4e38f;
+    for (int c = 0; c < K; ++c) {
+      p[c] = logits[gv * K + c];
+      mx = p[c] > mx ? p[c] : mx;
+    }
+    float se = 0.f;
+    for (int c = 0; c < K; ++c) {
+      p[c] = expf(p[c] - mx);
+      se += p[c];
+    }
+    const float inv = 1.0f / se;
+    const int t = labels[gv];
+    float dp[kMaxClasses];
+    float dot = 0.f;
+    for (int c = 0; c < K; ++c) {
+      p[c] *= inv;
+      dp[c] = (t == c ? cI[c] : 0.f) + cL[c] * (cfg.jaccard ? 2.f * p[c] : 1.f);
+      dot += p[c] * dp[c];
+    }
+    const bool valid = t >= 0 && t < K;
+    for (int c = 0; c < K; ++c) {
+      float gl = p[c] * (dp[c] - dot);
+      if (valid) gl += cX[t] * (p[c] - (t == c ? 1.f : 0.f));
+      dlogits[gv * K + c] = gl * grad_scale;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimiser over the flat parameter buffer (model.py:649-660).  Adam in TF's epsilon-hat form:
+//   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  m += (g-m)(1-b1);  v += (g^2-v)(1-b2);
+//   p -= lr_t * m / (sqrt(v) + eps)
+// `gscale` folds the data-parallel gradient average (1/world) into the same pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
+                                 float gscale) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+    const float vi = v[i] + (gi * gi - v[i]) * (1.0f - b2);
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+__global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, float lr,
+                                float gscale) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    p[i] -= lr * g[i] * gscale;
+}
+
+// fp32 -> bf16 hi/lo split of an arbitrary buffer (used for the network input and packed weights)
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long n, uint16_t* __restrict__ hi,
+                                  uint16_t* __restrict__ lo) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float f = x[i];
+    const uint16_t h = f32_to_bf16(f);
+    hi[i] = h;
+    if (lo) lo[i] = f32_to_bf16(f - bf16_to_f32(h));
+  }
+}
+
+}  // namespace vnb

@@ -1,0 +1,521 @@
+// C ABI of libvnet_b200.so (see include/vnet_b200.h).  Thin, exception-free shell over vnb::Engine.
+#include "../../include/vnet_b200.h"
+
+#include <memory>
+#include <new>
+
+#include "engine.cuh"
+#ifndef VNB_EMULATE
+#include "comm.cuh"
+#include "conv_tc_impl.cuh"
+#endif
+
+struct vnb_handle {
+  std::unique_ptr<vnb::Engine> engine;
+  int device = 0;
+#ifndef VNB_EMULATE
+  std::unique_ptr<vnb::Comm> comm;
+#endif
+};
+
+namespace {
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return VNB_OK;
+  } catch (const std::invalid_argument& e) {
+    return fail(VNB_ERR_INVALID_ARG, e.what());
+  } catch (const std::bad_alloc& e) {
+    return fail(VNB_ERR_OOM, e.what());
+  } catch (const std::exception& e) {
+    const std::string m = e.what();
+    if (m.find("out of memory") != std::string::npos) return fail(VNB_ERR_OOM, m);
+    if (m.find("NCCL") != std::string::npos) return fail(VNB_ERR_NCCL, m);
+    if (m.find("CUDA") != std::string::npos) return fail(VNB_ERR_CUDA, m);
+    return fail(VNB_ERR_INTERNAL, m);
+  } catch (...) {
+    return fail(VNB_ERR_INTERNAL, "unknown exception");
+  }
+}
+void need(const void* p, const char* what) {
+  if (!p) throw std::invalid_argument(std::string(what) + " must not be NULL");
+}
+void select_device(vnb_handle* h) {
+#ifndef VNB_EMULATE
+  VNB_CUDA_OK(cudaSetDevice(h->device));
+#else
+  (void)h;
+#endif
+}
+}  // namespace
+
+extern "C" {
+
+const char* vnb_last_error(void) { return g_last_error.c_str(); }
+const char* vnb_version(void) {
+#ifdef VNB_EMULATE
+  return "vnet_b200 0.1 (CPU emulation build: tests only)";
+#else
+  return "vnet_b200 0.1 (sm_100a)";
+#endif
+}
+
+int vnb_create(const vnb_config* c, int device, vnb_handle** out) {
+  return guarded([&] {
+    need(c, "cfg");
+    need(out, "out");
+    *out = nullptr;
+#ifndef VNB_EMULATE
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+      throw std::runtime_error("CUDA: no CUDA device visible -- libvnet_b200 has no CPU fallback");
+    if (device < 0 || device >= count) throw std::invalid_argument("device index out of range");
+    cudaDeviceProp prop;
+    VNB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      throw std::runtime_error("CUDA: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                               ", this library is built for sm_100a (B200) only");
+    VNB_CUDA_OK(cudaSetDevice(device));
+#endif
+    vnb::EngineConfig e;
+    e.in_channels = c->in_channels;
+    e.num_classes = c->num_classes;
+    e.num_channels = c->num_channels;
+    e.num_levels = c->num_levels;
+    for (int i = 0; i < 8; ++i) e.num_convolutions[i] = c->num_convolutions[i];
+    e.bottom_convolutions = c->bottom_convolutions;
+    for (int i = 0; i < 3; ++i) e.patch[i] = c->patch_shape[i];
+    e.max_batch = c->max_batch;
+    e.precision = c->precision;
+    e.loss = c->loss;
+    for (int i = 0; i < 8; ++i) e.loss_weights[i] = c->loss_weights[i];
+    e.loss_alpha = c->loss_alpha;
+    e.optimizer = c->optimizer;
+    e.lr0 = c->learning_rate;
+    e.decay_factor = c->decay_factor;
+    e.decay_steps = c->decay_steps;
+    if (e.precision < 0 || e.precision > 2) throw std::invalid_argument("precision must be VNB_PREC_*");
+    if (e.loss < 0 || e.loss > VNB_LOSS_MIXED_WEIGHTED_JACCARD) throw std::invalid_argument("loss must be VNB_LOSS_*");
+    if (e.optimizer < 0 || e.optimizer > VNB_OPT_SGD) throw std::invalid_argument("optimizer must be VNB_OPT_*");
+    for (int l = 0; l < e.num_levels && l < 8; ++l)
+      if (e.num_convolutions[l] < 1) throw std::invalid_argument("NumConvolutions entries must be >= 1");
+    if (e.bottom_convolutions < 1) throw std::invalid_argument("BottomConvolutions must be >= 1");
+#ifdef VNB_EMULATE
+    if (e.precision != VNB_PREC_FP32) throw std::invalid_argument("emulation build supports VNB_PREC_FP32 only");
+#endif
+    std::unique_ptr<vnb_handle> h(new vnb_handle);
+    h->device = device;
+    h->engine.reset(new vnb::Engine(e));
+    *out = h.release();
+  });
+}
+
+int vnb_destroy(vnb_handle* h) {
+  return guarded([&] {
+    if (!h) return;
+    select_device(h);
+#ifndef VNB_EMULATE
+    h->comm.reset();
+#endif
+    delete h;
+  });
+}
+
+int vnb_num_params(vnb_handle* h, int* count) {
+  return guarded([&] {
+    need(h, "handle");
+    need(count, "count");
+    *count = static_cast<int>(h->engine->params().size());
+  });
+}
+
+int vnb_param_info(vnb_handle* h, int index, const char** tf_name, int* ndim, int64_t dims[5], int* trainable) {
+  return guarded([&] {
+    need(h, "handle");
+    const auto& ps = h->engine->params();
+    if (index < 0 || index >= static_cast<int>(ps.size())) throw std::invalid_argument("parameter index out of range");
+    const vnb::ParamEntry& e = ps[index];
+    if (tf_name) *tf_name = e.name.c_str();
+    if (ndim) *ndim = e.ndim;
+    if (dims)
+      for (int i = 0; i < 5; ++i) dims[i] = e.dims[i];
+    if (trainable) *trainable = e.trainable ? 1 : 0;
+  });
+}
+
+int vnb_set_slot(vnb_handle* h, const char* name, int slot, const void* host, size_t bytes) {
+  return guarded([&] {
+    need(h, "handle");
+    need(name, "tf_name");
+    need(host, "host");
+    if (slot < 0 || slot > 3) throw std::invalid_argument("slot must be VNB_SLOT_*");
+    select_device(h);
+    h->engine->set_param(name, static_cast<const float*>(host), bytes, slot);
+  });
+}
+int vnb_get_slot(vnb_handle* h, const char* name, int slot, void* host, size_t bytes) {
+  return guarded([&] {
+    need(h, "handle");
+    need(name, "tf_name");
+    need(host, "host");
+    if (slot < 0 || slot > 3) throw std::invalid_argument("slot must be VNB_SLOT_*");
+    select_device(h);
+    h->engine->get_param(name, static_cast<float*>(host), bytes, slot);
+  });
+}
+int vnb_set_param(vnb_handle* h, const char* name, const void* host, size_t bytes) {
+  return vnb_set_slot(h, name, VNB_SLOT_VALUE, host, bytes);
+}
+int vnb_get_param(vnb_handle* h, const char* name, void* host, size_t bytes) {
+  return vnb_get_slot(h, name, VNB_SLOT_VALUE, host, bytes);
+}
+int vnb_get_step(vnb_handle* h, int64_t* s) {
+  return guarded([&] {
+    need(h, "handle");
+    need(s, "global_step");
+    *s = h->engine->global_step();
+  });
+}
+int vnb_set_step(vnb_handle* h, int64_t s) {
+  return guarded([&] {
+    need(h, "handle");
+    if (s < 0) throw std::invalid_argument("global_step must be >= 0");
+    h->engine->set_global_step(s);
+  });
+}
+
+int vnb_forward(vnb_handle* h, const float* images, int n, float* logits, float* softmax, int64_t* argmax) {
+  return guarded([&] {
+    need(h, "handle");
+    need(images, "images");
+    select_device(h);
+    h->engine->forward_host(images, n, logits, softmax, reinterpret_cast<long long*>(argmax));
+  });
+}
+
+int vnb_loss(vnb_handle* h, const float* images, const int32_t* labels, int n, float* loss_out, double* terms) {
+  return guarded([&] {
+    need(h, "handle");
+    need(images, "images");
+    need(labels, "labels");
+    select_device(h);
+    const float l = h->engine->loss_host(images, labels, n, terms);
+    if (loss_out) *loss_out = l;
+  });
+}
+
+int vnb_forward_backward(vnb_handle* h, const float* images, const int32_t* labels, int n, float dropout,
+                         uint64_t seed, int update_moving, float* loss_out) {
+  return guarded([&] {
+    need(h, "handle");
+    need(images, "images");
+    need(labels, "labels");
+    if (!(dropout >= 0.f && dropout < 1.f)) throw std::invalid_argument("dropout_rate must be in [0,1)");
+    select_device(h);
+    h->engine->upload_batch(images, labels, n);
+#ifndef VNB_EMULATE
+    if (h->comm) h->comm->begin_step(*h->engine);
+#endif
+    h->engine->forward_backward_device(n, dropout, seed, update_moving != 0);
+    if (loss_out) *loss_out = h->engine->read_loss();
+  });
+}
+
+int vnb_apply_gradients(vnb_handle* h) {
+  return guarded([&] {
+    need(h, "handle");
+    select_device(h);
+    int world = 1;
+#ifndef VNB_EMULATE
+    if (h->comm) {
+      h->comm->finish_allreduce(*h->engine);
+      world = h->comm->world();
+    }
+#endif
+    h->engine->optimizer_step(world);
+  });
+}
+
+int vnb_train_step(vnb_handle* h, const float* images, const int32_t* labels, int n, float dropout, uint64_t seed,
+                   float* loss_out) {
+  int rc = vnb_forward_backward(h, images, labels, n, dropout, seed, 1, nullptr);
+  if (rc != VNB_OK) return rc;
+  rc = vnb_apply_gradients(h);
+  if (rc != VNB_OK) return rc;
+  if (loss_out) return guarded([&] { *loss_out = h->engine->read_loss(); });
+  return VNB_OK;
+}
+
+int vnb_comm_unique_id(void* id_out) {
+  return guarded([&] {
+    need(id_out, "id_out");
+#ifndef VNB_EMULATE
+    vnb::Comm::unique_id(id_out);
+#else
+    throw std::invalid_argument("emulation build has no communicator");
+#endif
+  });
+}
+int vnb_comm_init(vnb_handle* h, int rank, int world, const void* uid) {
+  return guarded([&] {
+    need(h, "handle");
+    need(uid, "unique_id");
+    if (world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad rank/world");
+#ifndef VNB_EMULATE
+    select_device(h);
+    h->comm.reset(new vnb::Comm(rank, world, uid, *h->engine));
+#else
+    throw std::invalid_argument("emulation build has no communicator");
+#endif
+  });
+}
+int vnb_comm_world(vnb_handle* h, int* rank, int* world) {
+  return guarded([&] {
+    need(h, "handle");
+    int r = 0, w = 1;
+#ifndef VNB_EMULATE
+    if (h->comm) {
+      r = h->comm->rank();
+      w = h->comm->world();
+    }
+#endif
+    if (rank) *rank = r;
+    if (world) *world = w;
+  });
+}
+
+int vnb_upload_batch(vnb_handle* h, const float* images, const int32_t* labels, int n) {
+  return guarded([&] {
+    need(h, "handle");
+    need(images, "images");
+    need(labels, "labels");
+    select_device(h);
+    h->engine->upload_batch(images, labels, n);
+    h->engine->sync();
+  });
+}
+int vnb_train_step_resident(vnb_handle* h, int n, float dropout, uint64_t seed) {
+  return guarded([&] {
+    need(h, "handle");
+    if (n < 1 || n > h->engine->config().max_batch) throw std::invalid_argument("batch size outside [1, max_batch]");
+    select_device(h);
+    int world = 1;
+#ifndef VNB_EMULATE
+    if (h->comm) h->comm->begin_step(*h->engine);
+#endif
+    h->engine->forward_backward_device(n, dropout, seed, true);
+#ifndef VNB_EMULATE
+    if (h->comm) {
+      h->comm->finish_allreduce(*h->engine);
+      world = h->comm->world();
+    }
+#endif
+    h->engine->optimizer_step(world);
+  });
+}
+int vnb_event_record(vnb_handle* h, int which) {
+  return guarded([&] {
+    need(h, "handle");
+    select_device(h);
+    h->engine->event_record(which);
+  });
+}
+int vnb_event_elapsed_ms(vnb_handle* h, float* ms) {
+  return guarded([&] {
+    need(h, "handle");
+    need(ms, "ms");
+    select_device(h);
+    *ms = h->engine->event_elapsed_ms();
+  });
+}
+int vnb_profile_enable(vnb_handle* h, int on) {
+  return guarded([&] {
+    need(h, "handle");
+    h->engine->profile_enable(on != 0);
+  });
+}
+int vnb_profile_read(vnb_handle* h, int cls, double* ms, int64_t* launches, double* flops) {
+  return guarded([&] {
+    need(h, "handle");
+    need(ms, "ms");
+    need(launches, "launches");
+    need(flops, "flops");
+    select_device(h);
+    long long n = 0;
+    h->engine->profile_read(cls, ms, &n, flops);
+    *launches = n;
+  });
+}
+
+int vnb_sync(vnb_handle* h) {
+  return guarded([&] {
+    need(h, "handle");
+    select_device(h);
+    h->engine->sync();
+  });
+}
+int vnb_gpu_launches(vnb_handle* h, int64_t* count) {
+  return guarded([&] {
+    need(h, "handle");
+    need(count, "count");
+    *count = h->engine->gpu_launches();
+  });
+}
+int vnb_read_tensor(vnb_handle* h, const char* scope, int kind, float* host, size_t bytes, int n) {
+  return guarded([&] {
+    need(h, "handle");
+    need(scope, "scope");
+    need(host, "host");
+    select_device(h);
+    h->engine->read_tensor(scope, kind, host, bytes, n);
+  });
+}
+
+}  // extern "C"
+
+// ---- standalone convolution ops (test hooks) ------------------------------------------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  explicit DevBuf(size_t bytes) {
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) throw std::runtime_error("CUDA: out of memory in op hook");
+  }
+  ~DevBuf() { cudaFree(p); }
+  template <class T>
+  T* as() { return static_cast<T*>(p); }
+};
+void op_device(int device) {
+#ifndef VNB_EMULATE
+  VNB_CUDA_OK(cudaSetDevice(device));
+#else
+  (void)device;
+#endif
+}
+void op_conv5(int precision, const float* x, const float* w, const float* bias, const float* res, float* y, int n,
+              vnb::Dims dims, int cin, int cout, bool dgrad_form) {
+  using namespace vnb;
+  const size_t V = static_cast<size_t>(n) * dims.D * dims.H * dims.W;
+  const int ci = dgrad_form ? cout : cin, co = dgrad_form ? cin : cout;  // channels seen by the kernel
+  DevBuf dx(V * ci * 4), dw(125ull * cin * cout * 4), dwf(125ull * cin * cout * 4), dy(V * co * 4), db(co * 4), dr(V * co * 4);
+  VNB_CUDA_OK(cudaMemcpy(dx.p, x, V * ci * 4, cudaMemcpyHostToDevice));
+  VNB_CUDA_OK(cudaMemcpy(dw.p, w, 125ull * cin * cout * 4, cudaMemcpyHostToDevice));
+  if (bias) VNB_CUDA_OK(cudaMemcpy(db.p, bias, co * 4, cudaMemcpyHostToDevice));
+  if (res) VNB_CUDA_OK(cudaMemcpy(dr.p, res, V * co * 4, cudaMemcpyHostToDevice));
+#ifndef VNB_EMULATE
+  if (precision != VNB_PREC_FP32) {
+    tc_op_conv5(precision, dx.as<float>(), dw.as<float>(), bias ? db.as<float>() : nullptr, res ? dr.as<float>() : nullptr,
+                dy.as<float>(), n, dims, cin, cout, dgrad_form);
+    VNB_CUDA_OK(cudaDeviceSynchronize());
+    VNB_CUDA_OK(cudaMemcpy(y, dy.p, V * co * 4, cudaMemcpyDeviceToHost));
+    return;
+  }
+  VNB_CUDA_OK(cudaFuncSetAttribute(conv5_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5_SMEM));
+#else
+  (void)precision;
+#endif
+  const float* wk = dw.as<float>();
+  if (dgrad_form) {
+    VNB_LAUNCH(flip_transpose_w5_kernel, 1024, 256, 0, 0, (const float*)dw.as<float>(), dwf.as<float>(), cin, cout);
+    wk = dwf.as<float>();
+  }
+  Conv5Args p;
+  p.in1 = dx.as<float>();
+  p.in2 = nullptr;
+  p.C1 = ci;
+  p.C2 = 0;
+  p.w = wk;
+  p.bias = bias ? db.as<float>() : nullptr;
+  p.res = res ? dr.as<float>() : nullptr;
+  p.out1 = dy.as<float>();
+  p.out2 = nullptr;
+  p.Co1 = co;
+  p.Co2 = 0;
+  p.acc1 = p.acc2 = 0;
+  p.dims = dims;
+  p.N = n;
+  const int tiles = ((dims.W + kC5_TW - 1) / kC5_TW) * ((dims.H + kC5_TH - 1) / kC5_TH) * ((dims.D + kC5_TD - 1) / kC5_TD);
+  dim3 grid(tiles, (co + kC5_CO - 1) / kC5_CO, n);
+  VNB_LAUNCH(conv5_ref_kernel, grid, 256, kC5_SMEM, 0, p);
+  VNB_CUDA_OK(cudaDeviceSynchronize());
+  VNB_CUDA_OK(cudaGetLastError());
+  VNB_CUDA_OK(cudaMemcpy(y, dy.p, V * co * 4, cudaMemcpyDeviceToHost));
+}
+}  // namespace
+
+extern "C" {
+
+int vnb_op_conv5_fprop(int device, int precision, const float* x, const float* w, const float* bias,
+                       const float* residual, float* y, int n, int d, int h, int w_, int cin, int cout) {
+  return guarded([&] {
+    need(x, "x");
+    need(w, "w");
+    need(y, "y");
+    op_device(device);
+    op_conv5(precision, x, w, bias, residual, y, n, vnb::Dims{d, h, w_}, cin, cout, false);
+  });
+}
+int vnb_op_conv5_dgrad(int device, int precision, const float* dy, const float* w, float* dx, int n, int d, int h,
+                       int w_, int cin, int cout) {
+  return guarded([&] {
+    need(dy, "dy");
+    need(w, "w");
+    need(dx, "dx");
+    op_device(device);
+    op_conv5(precision, dy, w, nullptr, nullptr, dx, n, vnb::Dims{d, h, w_}, cin, cout, true);
+  });
+}
+int vnb_op_conv5_wgrad(int device, int precision, const float* x, const float* dy, float* dw, int n, int d, int h,
+                       int w_, int cin, int cout) {
+  return guarded([&] {
+    using namespace vnb;
+    need(x, "x");
+    need(dy, "dy");
+    need(dw, "dw");
+    op_device(device);
+    const Dims dims{d, h, w_};
+    const size_t V = static_cast<size_t>(n) * d * h * w_;
+    DevBuf bx(V * cin * 4), bdy(V * cout * 4), bdw(125ull * cin * cout * 4);
+    VNB_CUDA_OK(cudaMemcpy(bx.p, x, V * cin * 4, cudaMemcpyHostToDevice));
+    VNB_CUDA_OK(cudaMemcpy(bdy.p, dy, V * cout * 4, cudaMemcpyHostToDevice));
+    VNB_CUDA_OK(cudaMemset(bdw.p, 0, 125ull * cin * cout * 4));
+#ifndef VNB_EMULATE
+    if (precision != VNB_PREC_FP32) {
+      tc_op_wgrad5(precision, bx.as<float>(), bdy.as<float>(), bdw.as<float>(), n, dims, cin, cout);
+      VNB_CUDA_OK(cudaDeviceSynchronize());
+      VNB_CUDA_OK(cudaMemcpy(dw, bdw.p, 125ull * cin * cout * 4, cudaMemcpyDeviceToHost));
+      return;
+    }
+    VNB_CUDA_OK(cudaFuncSetAttribute(conv5_wgrad_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kW5_SMEM));
+#else
+    (void)precision;
+#endif
+    Wgrad5Args a;
+    a.in1 = bx.as<float>();
+    a.in2 = nullptr;
+    a.C1 = cin;
+    a.C2 = 0;
+    a.dz = bdy.as<float>();
+    a.Cout = cout;
+    a.dw = bdw.as<float>();
+    a.dims = dims;
+    a.N = n;
+    const long long ntiles = static_cast<long long>((w_ + kW5_TW - 1) / kW5_TW) * ((h + kW5_TH - 1) / kW5_TH) * ((d + kW5_TD - 1) / kW5_TD) * n;
+    const int pairs = ((cin + 15) / 16) * ((cout + 15) / 16);
+    a.tiles_per_block = static_cast<int>(std::max<long long>(1, ntiles / 64));
+    const long long splits = (ntiles + a.tiles_per_block - 1) / a.tiles_per_block;
+    dim3 grid(static_cast<unsigned>(splits), pairs);
+    VNB_LAUNCH(conv5_wgrad_ref_kernel, grid, 256, kW5_SMEM, 0, a);
+    VNB_CUDA_OK(cudaDeviceSynchronize());
+    VNB_CUDA_OK(cudaGetLastError());
+    VNB_CUDA_OK(cudaMemcpy(dw, bdw.p, 125ull * cin * cout * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+"""Python host object over one libvnet_b200 handle (one handle <-> one GPU <-> one host thread).
+
+`VNetEngine` owns the opaque C handle and exposes the steps the reference performs with
+`sess.run(...)`: inference (model.py:914-917), loss-only test step (model.py:784-789) and the
+training step (model.py:743-748).  All arrays cross as C-contiguous NumPy buffers in the reference's
+layouts (NDHWC images, int32 label indices).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _ffi
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class VNetEngine:
+    def __init__(self, *, num_classes: int, in_channels: int = 1, patch_shape: Sequence[int] = (64, 64, 64),
+                 max_batch: int = 1, num_channels: int = 16, num_levels: int = 4,
+                 num_convolutions: Sequence[int] = (1, 2, 3, 3), bottom_convolutions: int = 3,
+                 precision: str = "fp32", loss: str = "weighted_sorensen", loss_weights: Sequence[float] = (),
+                 loss_alpha: float = 1.0, optimizer: str = "Adam", learning_rate: float = 1e-2,
+                 decay_factor: float = 0.99, decay_steps: float = 100.0, device: int = 0,
+                 library: Optional[_ffi.Library] = None):
+        self.lib = library or _ffi.default_library()
+        if precision not in _ffi.PRECISIONS:
+            raise ValueError("Precision must be one of %s" % sorted(_ffi.PRECISIONS))
+        if loss not in _ffi.LOSSES:
+            raise SystemExit("Invalid loss function")  # model.py:559-560
+        if optimizer not in _ffi.OPTIMIZERS:
+            raise SystemExit("Invalid optimizer")  # model.py:657-658
+        if len(num_convolutions) != num_levels:
+            raise AssertionError("num_levels == len(num_convolutions)")  # networks.py:228
+        if len(patch_shape) != 3:
+            raise ValueError("only 3-D PatchShape is accelerated (the 2-D branches are out of scope)")
+        cfg = _ffi.VnbConfig()
+        cfg.in_channels, cfg.num_classes = in_channels, num_classes
+        cfg.num_channels, cfg.num_levels = num_channels, num_levels
+        for i, n in enumerate(num_convolutions):
+            cfg.num_convolutions[i] = int(n)
+        cfg.bottom_convolutions = bottom_convolutions
+        for i in range(3):
+            cfg.patch_shape[i] = int(patch_shape[i])
+        cfg.max_batch = max_batch
+        cfg.precision = _ffi.PRECISIONS[precision]
+        cfg.loss = _ffi.LOSSES[loss]
+        w = list(loss_weights) if len(loss_weights) else [1.0] * num_classes
+        if "weighted" in loss and len(w) != num_classes:
+            raise AssertionError("Length of DICE weight is {}, should be {}".format(len(w), num_classes))  # model.py:71
+        for i in range(8):
+            cfg.loss_weights[i] = float(w[i]) if i < len(w) else 1.0
+        cfg.loss_alpha = loss_alpha
+        cfg.optimizer = _ffi.OPTIMIZERS[optimizer]
+        cfg.learning_rate, cfg.decay_factor, cfg.decay_steps = learning_rate, decay_factor, decay_steps
+        self.cfg = cfg
+        self.num_classes, self.in_channels = num_classes, in_channels
+        self.patch_shape = tuple(int(p) for p in patch_shape)
+        self.max_batch = max_batch
+        self.precision = precision
+        self._h = C.c_void_p()
+        self.lib.check(self.lib.vnb_create(C.byref(cfg), device, C.byref(self._h)))
+        self._specs = self._read_specs()
+
+    # ---- lifetime -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.vnb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- variables ----------------------------------------------------------------------------
+    def _read_specs(self):
+        n = C.c_int()
+        self.lib.check(self.lib.vnb_num_params(self._h, C.byref(n)))
+        specs = OrderedDict()
+        for i in range(n.value):
+            name, ndim, tr = C.c_char_p(), C.c_int(), C.c_int()
+            dims = (C.c_int64 * 5)()
+            self.lib.check(self.lib.vnb_param_info(self._h, i, C.byref(name), C.byref(ndim), dims, C.byref(tr)))
+            specs[name.value.decode()] = (tuple(int(dims[k]) for k in range(ndim.value)), bool(tr.value))
+        return specs
+
+    def variables(self) -> "OrderedDict[str, Tuple[Tuple[int, ...], bool]]":
+        """TF variable name -> (shape, trainable), in creation order."""
+        return self._specs
+
+    def set_param(self, name: str, value: np.ndarray, slot: int = _ffi.SLOT_VALUE):
+        shape, _ = self._specs[name]
+        a = np.ascontiguousarray(value, dtype=np.float32)
+        if tuple(a.shape) != shape:
+            raise ValueError("%s: expected shape %s, got %s" % (name, shape, a.shape))
+        self.lib.check(self.lib.vnb_set_slot(self._h, name.encode(), slot, _ptr(a), a.nbytes))
+
+    def get_param(self, name: str, slot: int = _ffi.SLOT_VALUE) -> np.ndarray:
+        shape, _ = self._specs[name]
+        a = np.empty(shape, np.float32)
+        self.lib.check(self.lib.vnb_get_slot(self._h, name.encode(), slot, _ptr(a), a.nbytes))
+        return a
+
+    def set_params(self, params: Dict[str, np.ndarray]):
+        for k, v in params.items():
+            self.set_param(k, v)
+
+    def get_params(self, names: Optional[Iterable[str]] = None) -> "OrderedDict[str, np.ndarray]":
+        return OrderedDict((k, self.get_param(k)) for k in (names or self._specs))
+
+    def get_grads(self) -> "OrderedDict[str, np.ndarray]":
+        return OrderedDict((k, self.get_param(k, _ffi.SLOT_GRAD)) for k, (_, tr) in self._specs.items() if tr)
+
+    @property
+    def global_step(self) -> int:
+        s = C.c_int64()
+        self.lib.check(self.lib.vnb_get_step(self._h, C.byref(s)))
+        return s.value
+
+    @global_step.setter
+    def global_step(self, v: int):
+        self.lib.check(self.lib.vnb_set_step(self._h, int(v)))
+
+    # ---- steps --------------------------------------------------------------------------------
+    def _check_images(self, images: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(images, dtype=np.float32)
+        want = self.patch_shape + (self.in_channels,)
+        if a.ndim != 5 or tuple(a.shape[1:]) != want:
+            raise ValueError("images must be [N,%d,%d,%d,%d] float32, got %s" % (want + (a.shape,)))
+        if not 1 <= a.shape[0] <= self.max_batch:
+            raise ValueError("batch %d outside [1, %d]" % (a.shape[0], self.max_batch))
+        return a
+
+    def _check_labels(self, labels: np.ndarray, n: int) -> np.ndarray:
+        l = np.ascontiguousarray(labels, dtype=np.int32)
+        if l.ndim == 5 and l.shape[-1] == 1:  # model.py:741 feeds [...,np.newaxis]
+            l = np.ascontiguousarray(l[..., 0])
+        if tuple(l.shape) != (n,) + self.patch_shape:
+            raise ValueError("labels must be [N,X,Y,Z] int32 class indices, got %s" % (l.shape,))
+        return l
+
+    def forward(self, images, want_logits=True, want_softmax=True, want_argmax=True):
+        """sess.run(['predicted_label/prediction:0','softmax:0']) of model.py:914-917 (+ logits)."""
+        a = self._check_images(images)
+        n = a.shape[0]
+        shp = (n,) + self.patch_shape
+        logits = np.empty(shp + (self.num_classes,), np.float32) if want_logits else None
+        softmax = np.empty(shp + (self.num_classes,), np.float32) if want_softmax else None
+        argmax = np.empty(shp, np.int64) if want_argmax else None
+        self.lib.check(self.lib.vnb_forward(self._h, _ptr(a), n, _ptr(logits), _ptr(softmax), _ptr(argmax)))
+        return logits, softmax, argmax
+
+    def loss(self, images, labels, want_terms=False):
+        a = self._check_images(images)
+        l = self._check_labels(labels, a.shape[0])
+        out = C.c_float()
+        terms = np.empty((a.shape[0], self.num_classes, 4), np.float64) if want_terms else None
+        self.lib.check(self.lib.vnb_loss(self._h, _ptr(a), _ptr(l), a.shape[0], C.byref(out), _ptr(terms)))
+        return (out.value, terms) if want_terms else out.value
+
+    def train_step(self, images, labels, dropout_rate=0.0, seed=0, want_loss=True):
+        a = self._check_images(images)
+        l = self._check_labels(labels, a.shape[0])
+        out = C.c_float()
+        self.lib.check(self.lib.vnb_train_step(self._h, _ptr(a), _ptr(l), a.shape[0], float(dropout_rate),
+                                               int(seed), C.byref(out) if want_loss else None))
+        return out.value if want_loss else None
+
+    def forward_backward(self, images, labels, dropout_rate=0.0, seed=0, update_moving_stats=False, want_loss=True):
+        a = self._check_images(images)
+        l = self._check_labels(labels, a.shape[0])
+        out = C.c_float()
+        self.lib.check(self.lib.vnb_forward_backward(self._h, _ptr(a), _ptr(l), a.shape[0], float(dropout_rate),
+                                                     int(seed), int(bool(update_moving_stats)),
+                                                     C.byref(out) if want_loss else None))
+        return out.value if want_loss else None
+
+    def apply_gradients(self):
+        self.lib.check(self.lib.vnb_apply_gradients(self._h))
+
+    def upload_batch(self, images, labels):
+        a = self._check_images(images)
+        l = self._check_labels(labels, a.shape[0])
+        self.lib.check(self.lib.vnb_upload_batch(self._h, _ptr(a), _ptr(l), a.shape[0]))
+        return a.shape[0]
+
+    def train_step_resident(self, n, dropout_rate=0.0, seed=0):
+        self.lib.check(self.lib.vnb_train_step_resident(self._h, int(n), float(dropout_rate), int(seed)))
+
+    def event_record(self, which: int):
+        self.lib.check(self.lib.vnb_event_record(self._h, which))
+
+    def event_elapsed_ms(self) -> float:
+        ms = C.c_float()
+        self.lib.check(self.lib.vnb_event_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on: bool):
+        self.lib.check(self.lib.vnb_profile_enable(self._h, int(on)))
+
+    def profile_read(self, kernel_class: int):
+        ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+        self.lib.check(self.lib.vnb_profile_read(self._h, kernel_class, C.byref(ms), C.byref(n), C.byref(fl)))
+        return ms.value, n.value, fl.value
+
+    def sync(self):
+        self.lib.check(self.lib.vnb_sync(self._h))
+
+    def gpu_launches(self) -> int:
+        c = C.c_int64()
+        self.lib.check(self.lib.vnb_gpu_launches(self._h, C.byref(c)))
+        return c.value
+
+    def read_tensor(self, scope: str, kind: int, n: int, channels: int, spatial: Sequence[int]) -> np.ndarray:
+        a = np.empty((n,) + tuple(spatial) + (channels,), np.float32)
+        self.lib.check(self.lib.vnb_read_tensor(self._h, scope.encode(), kind, _ptr(a), a.nbytes, n))
+        return a
+
+    # ---- data parallel ------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self.lib.check(self.lib.vnb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self.lib.check(self.lib.vnb_comm_init(self._h, rank, world, buf))
