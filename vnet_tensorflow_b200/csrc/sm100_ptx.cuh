@@ -5,9 +5,15 @@
 // Bit layouts follow the PTX ISA "tcgen05 matrix descriptor" / "instruction descriptor" tables.
 #pragma once
 #include <cstdint>
+#ifdef VNB_EMULATE
+#include "emul_sm100.h"  // tests/emul: CPU model of the async units, same function names
+#else
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace sm100 {
+
+typedef CUtensorMap TmaDesc;
 
 // ----------------------------------------------------------------------------------------------
 // address helpers
@@ -166,6 +172,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
       : "memory");
 }
 
+}  // namespace sm100
+#endif  // VNB_EMULATE
+
+namespace sm100 {
 // ----------------------------------------------------------------------------------------------
 // descriptors
 // ----------------------------------------------------------------------------------------------
