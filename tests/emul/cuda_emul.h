@@ -81,6 +81,11 @@ struct Block {
   std::vector<uint64_t> warp_count[2];
   std::vector<uint8_t> dyn_smem;
   std::function<void()> body;
+  struct NamedBar {
+    int arrived = 0;
+    uint64_t gen = 0;
+  };
+  NamedBar named[16];
 };
 
 inline Block& blk() {
@@ -118,6 +123,7 @@ inline void run_block(std::function<void()> body) {
   b.body = body;
   b.live = b.nthreads;
   b.bar_arrived = 0;
+  for (auto& nb : b.named) nb = Block::NamedBar();
   if ((int)b.fibers.size() < b.nthreads) b.fibers.resize(b.nthreads);
   int nwarps = (b.nthreads + 31) / 32;
   for (int k = 0; k < 2; ++k) {
@@ -192,6 +198,21 @@ inline void syncthreads() {
     return;
   }
   while (b.bar_gen == gen) yield_wait();
+}
+
+// bar.sync id, count: barrier among `count` threads of the block
+inline void named_barrier(int id, int count) {
+  Block& b = blk();
+  Block::NamedBar& nb = b.named[id & 15];
+  uint64_t gen = nb.gen;
+  nb.arrived++;
+  b.progress++;
+  if (nb.arrived == count) {
+    nb.arrived = 0;
+    nb.gen++;
+    return;
+  }
+  while (nb.gen == gen) yield_wait();
 }
 
 template <class T>

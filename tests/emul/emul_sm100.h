@@ -205,6 +205,6 @@ inline void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   const uint32_t lane = (taddr >> 16) + (emul::cur()->lin & 31), col = taddr & 0xFFFF;
   for (int j = 0; j < 8; ++j) memcpy(&r[j], &st().tmem[lane * 512 + col + j], 4);
 }
-inline void named_bar_sync(int, int) { emul::syncthreads_subset(); }
+inline void named_bar_sync(int id, int count) { emul::named_barrier(id, count); }
 
 }  // namespace sm100

@@ -15,7 +15,13 @@ from vnet_tensorflow_b200.synthetic import synth_batch
 pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = {"fp32": 2e-4, "bf16x3": 1e-3, "bf16": 8e-2}
-GRAD_TOL = {"fp32": 2e-3, "bf16x3": 5e-3, "bf16": 0.25}
+# Gradients of this network are ill-conditioned in the max norm: a 1e-5 relative perturbation of one
+# layer's weights moves the *exact* (fp64) gradients by ~3e-2 while the logits move by 1e-5, because a
+# handful of PReLU inputs cross zero (measured with the oracle, see DESIGN.md "conditioning").  The
+# fp32 path (same engine, exact-fp32 convolutions) is therefore held to a tight bound and pins the
+# engine logic; the tensor-core precisions get a bound at the conditioning floor, and their kernels
+# are pinned tightly per op in test_conv5_ops_match_torch.
+GRAD_TOL = {"fp32": 2e-3, "bf16x3": 8e-2, "bf16": 0.5}
 
 
 def _check_grads(eng, grads_ref, spec, tol):

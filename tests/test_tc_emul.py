@@ -1,0 +1,78 @@
+"""The tcgen05 implicit-GEMM convolution kernel on the CPU: compiled with the emulation shim, its TMA
+boxes, mbarrier pipeline, UMMA descriptors, TMEM double buffering and kw-folding epilogue run against
+the probe-validated model of the hardware (tests/emul/emul_sm100.h) and are compared with torch."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_vnet as R
+from tests.helpers import analytically_zero, engine_for, perturbed_params, rel_err
+from vnet_tensorflow_b200.synthetic import synth_batch
+
+
+def _bf16(x):
+    return torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("cin,cout,dims,n,prec", [
+    (16, 16, (2, 4, 32), 1, 2),     # CT=16, T=3 tiles, SW32
+    (16, 16, (2, 7, 128), 1, 1),    # full 128-wide lines, partial last h-block, bf16x3
+    (32, 32, (2, 4, 16), 2, 1),     # CT=32, SW64, two k-steps per stage
+    (32, 16, (3, 8, 16), 1, 2),     # two output slices in dgrad
+    (64, 32, (4, 8, 8), 1, 1),      # box spanning two d-planes
+])
+def test_conv5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
+    rng = np.random.default_rng(7)
+    x = rng.normal(0, 1, (n,) + dims + (cin,)).astype(np.float32)
+    w = rng.normal(0, 0.05, (5, 5, 5, cin, cout)).astype(np.float32)
+    b = rng.normal(0, 1, (cout,)).astype(np.float32)
+    r = rng.normal(0, 1, (n,) + dims + (cout,)).astype(np.float32)
+    dy = rng.normal(0, 1, (n,) + dims + (cout,)).astype(np.float32)
+    xr, wr, dyr = (_bf16(x), _bf16(w), _bf16(dy)) if prec == 2 else (x, w, dy)  # bf16 mode: exact vs rounded inputs
+    tol = 1e-6 if prec == 2 else 3e-5
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    y_ref = (R.conv_same(torch.from_numpy(xr).double(), torch.from_numpy(wr).double(), torch.from_numpy(b).double())
+             + torch.from_numpy(r).double()).numpy()
+    y = np.empty_like(dy)
+    emul_lib.check(emul_lib.vnb_op_conv5_fprop(0, prec, ptr(x), ptr(w), ptr(b), ptr(r), ptr(y), n, *dims, cin, cout))
+    assert rel_err(y, y_ref) < tol
+    xt = torch.from_numpy(x).double().requires_grad_(True)
+    R.conv_same(xt, torch.from_numpy(wr).double(), torch.zeros(cout).double()).backward(torch.from_numpy(dyr).double())
+    dx = np.empty_like(x)
+    emul_lib.check(emul_lib.vnb_op_conv5_dgrad(0, prec, ptr(dy), ptr(w), ptr(dx), n, *dims, cin, cout))
+    assert rel_err(dx, xt.grad.numpy()) < tol
+
+
+def test_unsupported_shapes_are_rejected_not_miscomputed(emul_lib):
+    x = np.zeros((1, 3, 5, 16, 16), np.float32)
+    w = np.zeros((5, 5, 5, 16, 16), np.float32)
+    y = np.zeros((1, 3, 5, 16, 16), np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = emul_lib.vnb_op_conv5_fprop(0, 1, ptr(x), ptr(w), None, None, ptr(y), 1, 3, 5, 16, 16, 16)
+    assert rc == -1 and b"not supported" in emul_lib.vnb_last_error()
+
+
+def test_engine_bf16x3_matches_oracle(emul_lib):
+    """Whole network with tensor-core convolutions where the geometry allows (levels 1-2 here) and the
+    fp32 kernels elsewhere: concat inputs, residual epilogue, split dgrad outputs, accumulate flags."""
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=16, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=2)
+    P, N = 16, 1
+    params = perturbed_params(spec)
+    img, lab = synth_batch(0, N, P, 1, 2)
+    eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 1.0), emul_lib, precision="bf16x3")
+    eng.set_params(params)
+    l = eng.forward_backward(img, lab)
+    lo, lg, go, _ = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
+    logits, _, am = eng.forward(img)
+    assert abs(l - float(lo)) < 2e-6
+    assert rel_err(logits, lg.numpy()) < 1e-4          # north_star bound is 1e-3
+    assert int((am != R.predict(lg).numpy()).sum()) == 0
+    g = eng.get_grads()
+    for k, v in g.items():                              # conditioning floor, see test_gpu_parity.GRAD_TOL
+        if analytically_zero(k, spec):
+            continue
+        ref = go[k].numpy().astype(np.float64)
+        assert np.sqrt(((v - ref) ** 2).sum()) <= 5e-2 * max(np.sqrt((ref ** 2).sum()), 1e-9), k
+    eng.close()

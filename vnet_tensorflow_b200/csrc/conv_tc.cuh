@@ -1,11 +1,486 @@
-// tcgen05 implicit-GEMM convolution path (placeholder plan types; kernels land in a later commit).
+// tcgen05 implicit-GEMM 5x5x5 convolution (fprop and, with flipped/transposed weights, dgrad).
+//
+// Replaces tf.nn.convolution 5^3 'SAME' + bias (+ residual) -- layers2.py:59-63 via networks.py:264,
+// 316,333,346,356 -- and its input gradient (TF autodiff, model.py:660), on the 5th-gen tensor cores.
+//
+// Formulation ("kw-folded line tiles", im2col-free):
+//   * GEMM M = 128 consecutive *input* voxels = whole W-lines (rows r = (d,h,w), w fastest), loaded by
+//     ONE 5-D TMA box per (kd,kh) tap pair straight from the NDHWC bf16 activation tensor; SAME
+//     padding in d/h comes from TMA out-of-range zero fill, the 5 kw taps are folded into the GEMM N
+//     dimension:  D[r][kw*CT + co] = sum_{kd,kh,ci} X[line(r)+(kd,kh)][w(r)][ci] * W[kd][kh][kw][ci][co]
+//     so one A tile feeds N = 5*CT columns (80 / 160) instead of CT -- the skinny-N problem of
+//     Cout = 16/32 layers (65 % of the FLOPs) becomes an N = 80/160 MMA.
+//   * accumulators stay in TMEM over all 25*Cin/KC k-steps; the epilogue re-aligns the 5 kw slices
+//     (y[w] = sum_kw D[w+kw-2][kw]) through shared memory, adds bias / residual and stores fp32.
+//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue;
+//     4-stage smem ring (full/empty mbarriers), double-buffered TMEM (tmem_full/tmem_empty) so the
+//     epilogue of tile i overlaps the main loop of tile i+1; persistent CTAs, one per SM.
+//   * precision: bf16 operands, fp32 accumulate.  NSPLIT = 3 runs hi*hi + lo*hi + hi*lo on
+//     (hi, lo) bf16 splits of activations and weights = fp32-grade products ("bf16x3").
 #pragma once
+#include <stdexcept>
+#include <string>
+
+#include "sm100_ptx.cuh"
 #include "vnb_cuda.h"
+
 namespace vnb {
-struct TcKernelPlan {
+
+using sm100::TmaDesc;
+
+constexpr int kTcStages = 4;
+constexpr int kTcThreads = 192;
+constexpr int kTcEpiRowPad = 20;  // floats per staged row (16 + 4: conflict-free float4 rows)
+constexpr int kTcEpiBytes = 5 * 128 * kTcEpiRowPad * 4;
+
+template <int CT, int TMAX, int KC, int NSPLIT>
+struct TcCfg {
+  static constexpr int ROWB = KC * 2;                       // bytes per smem row (= swizzle span)
+  static constexpr int NB = 5 * CT;                         // GEMM N (kw-folded)
+  static constexpr int NPL = NSPLIT == 3 ? 2 : 1;           // operand planes (hi, lo)
+  static constexpr int A_BYTES = TMAX * 128 * ROWB;
+  static constexpr int B_BYTES = ((NB * ROWB + 1023) / 1024) * 1024;
+  static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
+  static constexpr int BUF_COLS = TMAX * NB;                // TMEM columns per accumulator buffer
+  static constexpr int SMEM_BYTES = kTcStages * STAGE_BYTES + kTcEpiBytes + 256 + 1024;
+  static constexpr uint32_t LAYOUT = ROWB == 32 ? sm100::SWZ_32B : ROWB == 64 ? sm100::SWZ_64B : sm100::SWZ_128B;
+  static_assert(2 * BUF_COLS <= 512, "TMEM overflow");
+  static_assert(NB % 16 == 0 && NB <= 256, "invalid UMMA N");
+};
+
+struct TcGeom {
+  int N, D, H, W;      // activation extents
+  int C1, C2;          // channels of the two concatenated inputs (C2 may be 0)
+  int Co1, Co2;        // output channel split (Co2 may be 0)
+  int T;               // 128-row tiles per work item (<= TMAX)
+  int bh, bd;          // box extent in lines (h) and planes (d): W*bh*bd == T*128
+  int n_hb, n_db;      // blocks per sample along h and d
+  int n_slices;        // (Co1+Co2) / CT
+  int n_kc;            // (C1+C2) / KC
+  int n_items;
+};
+
+struct TcArgs {
+  TcGeom g;
+  const float* bias;   // [Co1+Co2] or nullptr
+  const float* res;    // [V][Co1+Co2] or nullptr
+  float* out1;
+  float* out2;
+  int acc1, acc2;
+};
+
+template <int CT, int TMAX, int KC, int NSPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ TmaDesc a1_lo,
+                const __grid_constant__ TmaDesc a2_hi, const __grid_constant__ TmaDesc a2_lo,
+                const __grid_constant__ TmaDesc w_hi, const __grid_constant__ TmaDesc w_lo, const TcArgs p) {
+  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
+  using namespace sm100;
+  VNB_DYN_SMEM(uint8_t, smem_raw);
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const uint32_t sm_addr = smem_u32(sm);
+  float* epi = reinterpret_cast<float*>(sm + kTcStages * Cfg::STAGE_BYTES);
+  const uint32_t bar_base = sm_addr + kTcStages * Cfg::STAGE_BYTES + kTcEpiBytes;
+  // barriers: full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4); then TMEM slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + 2 + b); };
+  const uint32_t slot_addr = bar_base + 8u * (2 * kTcStages + 4);
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTcStages * Cfg::STAGE_BYTES + kTcEpiBytes + 8 * (2 * kTcStages + 4));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TcGeom& g = p.g;
+  const int n_it = 25 * g.n_kc;
+  const int kc1 = g.C1 / KC;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(slot_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *slot_ptr;
+
+  if (warp == 0) {
+    // ======================= TMA producer (one elected lane) =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        const int slice = item % g.n_slices;
+        int x = item / g.n_slices;
+        const int hb = x % g.n_hb;
+        x /= g.n_hb;
+        const int db = x % g.n_db;
+        const int n = x / g.n_db;
+        const int h0 = hb * g.bh, d0 = db * g.bd;
+        for (int it = 0; it < n_it; ++it) {
+          const int kc = it % g.n_kc, kh = (it / g.n_kc) % 5, kd = it / (5 * g.n_kc);
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t st_addr = sm_addr + stage * Cfg::STAGE_BYTES;
+          const uint32_t a_bytes = static_cast<uint32_t>(g.T) * 128u * Cfg::ROWB;
+          mbar_expect_tx(full_bar(stage), Cfg::NPL * (a_bytes + Cfg::NB * Cfg::ROWB));
+          const bool src1 = kc < kc1;
+          const int cch = (src1 ? kc : kc - kc1) * KC;
+          tma_load_5d(st_addr, src1 ? &a1_hi : &a2_hi, full_bar(stage), cch, 0, h0 + kh - 2, d0 + kd - 2, n);
+          const int brow = (slice * n_it + it) * Cfg::NB;
+          tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES, &w_hi, full_bar(stage), 0, brow);
+          if (NSPLIT == 3) {
+            tma_load_5d(st_addr + Cfg::A_BYTES, src1 ? &a1_lo : &a2_lo, full_bar(stage), cch, 0, h0 + kh - 2, d0 + kd - 2, n);
+            tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES + Cfg::B_BYTES, &w_lo, full_bar(stage), 0, brow);
+          }
+          if (++stage == kTcStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (one elected lane) =======================
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(128, Cfg::NB, FMT_BF16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int j = 0;
+      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
+        const int buf = j & 1;
+        const uint32_t use = static_cast<uint32_t>(j >> 1);
+        mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
+        for (int it = 0; it < n_it; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after_sync();
+          const uint32_t a_hi = sm_addr + stage * Cfg::STAGE_BYTES;
+          const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+          const uint32_t b_hi = a_hi + Cfg::NPL * Cfg::A_BYTES;
+          const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+          for (int t = 0; t < g.T; ++t) {
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ++ks) {
+              const uint32_t aoff = t * 128 * Cfg::ROWB + ks * 32;
+              const uint64_t da_hi = make_smem_desc(a_hi + aoff, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
+              const uint64_t db_hi = make_smem_desc(b_hi + ks * 32, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
+              const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+              mma_f16_ss(d_base + t * Cfg::NB, da_hi, db_hi, idesc, acc);
+              if (NSPLIT == 3) {
+                const uint64_t da_lo = make_smem_desc(a_lo + aoff, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
+                const uint64_t db_lo = make_smem_desc(b_lo + ks * 32, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
+                mma_f16_ss(d_base + t * Cfg::NB, da_lo, db_hi, idesc, 1u);
+                mma_f16_ss(d_base + t * Cfg::NB, da_hi, db_lo, idesc, 1u);
+              }
+            }
+          }
+          mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == kTcStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        mma_commit(tfull_bar(buf));  // accumulators of this item complete
+      }
+    }
+  } else {
+    // ======================= epilogue (4 warps = 128 TMEM lanes) =======================
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;     // row inside a 128-row tile
+    const int Ctot = g.Co1 + g.Co2;
+    int j = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
+      const int slice = item % g.n_slices;
+      int x = item / g.n_slices;
+      const int hb = x % g.n_hb;
+      x /= g.n_hb;
+      const int db = x % g.n_db;
+      const int n = x / g.n_db;
+      const int buf = j & 1;
+      const uint32_t use = static_cast<uint32_t>(j >> 1);
+      mbar_wait(tfull_bar(buf), use & 1u);
+      tc_fence_after_sync();
+      for (int t = 0; t < g.T; ++t) {
+        const int R = t * 128 + r;
+        const int w = R % g.W;
+        const int line = R / g.W;
+        const int gh = hb * g.bh + line % g.bh, gd = db * g.bd + line / g.bh;
+        const bool valid = gh < g.H && gd < g.D;
+        const long long vox = ((static_cast<long long>(n) * g.D + gd) * g.H + gh) * g.W + w;
+        const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::BUF_COLS + t * Cfg::NB;
+#pragma unroll 1
+        for (int cc = 0; cc < CT / 16; ++cc) {
+#pragma unroll
+          for (int kw = 0; kw < 5; ++kw) {
+            uint32_t v[16];
+            tmem_ld16(t_addr + kw * CT + cc * 16, v);
+            tmem_ld_wait();
+            float4* dst = reinterpret_cast<float4*>(epi + (kw * 128 + r) * kTcEpiRowPad);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          }
+          named_bar_sync(1, 128);
+          float acc[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+          for (int kw = 0; kw < 5; ++kw) {
+            const int ws = w + kw - 2;
+            if (ws >= 0 && ws < g.W) {
+              const float4* src = reinterpret_cast<const float4*>(epi + (kw * 128 + r + kw - 2) * kTcEpiRowPad);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 f = src[i];
+                acc[4 * i] += f.x;
+                acc[4 * i + 1] += f.y;
+                acc[4 * i + 2] += f.z;
+                acc[4 * i + 3] += f.w;
+              }
+            }
+          }
+          named_bar_sync(1, 128);
+          if (valid) {
+            const int co = slice * CT + cc * 16;  // first of 16 output channels handled here
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] += p.bias[co + i];
+            }
+            if (p.res) {
+              const float4* rs = reinterpret_cast<const float4*>(p.res + vox * Ctot + co);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 f = rs[i];
+                acc[4 * i] += f.x;
+                acc[4 * i + 1] += f.y;
+                acc[4 * i + 2] += f.z;
+                acc[4 * i + 3] += f.w;
+              }
+            }
+            float4* o;
+            int accumulate;
+            if (co < g.Co1) {
+              o = reinterpret_cast<float4*>(p.out1 + vox * g.Co1 + co);
+              accumulate = p.acc1;
+            } else {
+              o = reinterpret_cast<float4*>(p.out2 + vox * g.Co2 + (co - g.Co1));
+              accumulate = p.acc2;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float4 f = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+              if (accumulate) {
+                const float4 old = o[i];
+                f.x += old.x;
+                f.y += old.y;
+                f.z += old.z;
+                f.w += old.w;
+              }
+              o[i] = f;
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(tempty_bar(buf));  // 128 arrivals free the accumulator buffer
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 TF filter [125][Cin][Cout] -> bf16 (hi, lo) GEMM-B tiles
+//   packed[slice][it = (kd*5+kh)*n_kc + kc][n = kw*CT + col][k = KC]   (K-major rows of KC elements)
+// fprop : col = output channel, k = input channel, taps as stored
+// dgrad : col = input channel (the conv's "output"), k = output channel, taps flipped (124 - tap)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_w5_kernel(const float* __restrict__ w, int Cin, int Cout, int dgrad, int CT, int KC,
+                               uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  const int Kin = dgrad ? Cout : Cin;    // GEMM K channels
+  const int Nout = dgrad ? Cin : Cout;   // GEMM N channels
+  const int n_kc = Kin / KC, n_it = 25 * n_kc, NB = 5 * CT;
+  const long long total = static_cast<long long>(Nout / CT) * n_it * NB * KC;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % KC);
+    long long x = i / KC;
+    const int nrow = static_cast<int>(x % NB);
+    x /= NB;
+    const int it = static_cast<int>(x % n_it);
+    const int slice = static_cast<int>(x / n_it);
+    const int kw = nrow / CT, col = slice * CT + nrow % CT;
+    const int kc = it % n_kc, kh = (it / n_kc) % 5, kd = it / (5 * n_kc);
+    const int kch = kc * KC + k;
+    float v;
+    if (!dgrad) {
+      const int tap = (kd * 5 + kh) * 5 + kw;
+      v = w[(static_cast<long long>(tap) * Cin + kch) * Cout + col];
+    } else {
+      const int tap = 124 - ((kd * 5 + kh) * 5 + kw);
+      v = w[(static_cast<long long>(tap) * Cin + col) * Cout + kch];
+    }
+    const uint16_t h = f32_to_bf16(v);
+    hi[i] = h;
+    if (lo) lo[i] = f32_to_bf16(v - bf16_to_f32(h));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers: tensor maps and launch plans
+// ---------------------------------------------------------------------------------------------
+inline void tma_encode(TmaDesc* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, uint32_t swizzle_bytes) {
+#ifdef VNB_EMULATE
+  TmaDesc d;
+  d.base = static_cast<const uint8_t*>(base);
+  d.rank = rank;
+  d.elem = 2;
+  d.swizzle = swizzle_bytes;
+  for (int i = 0; i < rank; ++i) {
+    d.dims[i] = dims[i];
+    d.strides[i] = i == 0 ? 2 : strides_bytes[i - 1];
+    d.box[i] = box[i];
+  }
+  *out = d;
+#else
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f)
+      throw std::runtime_error("CUDA: cuTensorMapEncodeTiled unavailable");
+    fn = reinterpret_cast<EncodeFn>(f);
+  }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = strides_bytes[i - 1];
+  }
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("CUDA: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+#endif
+}
+
+// NDHWC bf16 activation [N][D][H][W][C] -> 5-D map (C, W, H, D, N) with box (KC, W, bh, bd, 1)
+inline void tma_encode_act(TmaDesc* out, const uint16_t* base, int N, int D, int H, int W, int C, int KC, int bh, int bd) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+  const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)D * H * W * C * 2};
+  const uint32_t box[5] = {(uint32_t)KC, (uint32_t)W, (uint32_t)bh, (uint32_t)bd, 1};
+  tma_encode(out, base, 5, dims, str, box, KC * 2);
+}
+// packed weights [rows][KC] -> 2-D map, box (KC, NB)
+inline void tma_encode_w(TmaDesc* out, const uint16_t* base, long long rows, int KC, int NB) {
+  const uint64_t dims[2] = {(uint64_t)KC, (uint64_t)rows};
+  const uint64_t str[1] = {(uint64_t)KC * 2};
+  const uint32_t box[2] = {(uint32_t)KC, (uint32_t)NB};
+  tma_encode(out, base, 2, dims, str, box, KC * 2);
+}
+
+struct TcKernelPlan {   // one launch of conv5_tc_kernel
   bool valid = false;
+  int CT = 0, KC = 0;
+  TcGeom g{};
+  TmaDesc a1_hi, a1_lo, a2_hi, a2_lo, w_hi, w_lo;
+  uint16_t* wp_hi = nullptr;   // packed weights
+  uint16_t* wp_lo = nullptr;
+  size_t wp_elems = 0;
 };
 struct TcConvPlan {
   TcKernelPlan fprop, dgrad, wgrad;
 };
+
+// geometry for a [N][D][H][W] activation, kernel-side channel counts (C1+C2 in, Co1+Co2 out)
+inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C1, int C2, int Co1, int Co2) {
+  auto mult = [](int v, int m) { return v % m == 0; };
+  if (mult(C1, 32) && mult(C2, 32) && mult(Co1, 32) && mult(Co2, 32) && Co1 > 0) {
+    pl.CT = 32;
+    pl.KC = 32;
+  } else if (mult(C1, 16) && mult(C2, 16) && mult(Co1, 16) && mult(Co2, 16) && Co1 > 0 && C1 > 0) {
+    pl.CT = 16;
+    pl.KC = 16;
+  } else {
+    return false;
+  }
+  if (W > 128 || W < 1 || 128 % W != 0) return false;
+  const int tmax = pl.CT == 16 ? 3 : 1;
+  for (int T = tmax; T >= 1; --T) {
+    const int lines = T * 128 / W;
+    int bh, bd;
+    if (lines <= H) {
+      bh = lines;
+      bd = 1;
+    } else {
+      if (lines % H) continue;
+      bh = H;
+      bd = lines / H;
+      if (bd > D || D % bd) continue;
+    }
+    if (bh > 256 || bd > 256) continue;
+    TcGeom& g = pl.g;
+    g.N = N; g.D = D; g.H = H; g.W = W;
+    g.C1 = C1; g.C2 = C2; g.Co1 = Co1; g.Co2 = Co2;
+    g.T = T; g.bh = bh; g.bd = bd;
+    g.n_hb = (H + bh - 1) / bh;
+    g.n_db = D / bd;
+    g.n_slices = (Co1 + Co2) / pl.CT;
+    g.n_kc = (C1 + C2) / pl.KC;
+    g.n_items = N * g.n_db * g.n_hb * g.n_slices;
+    return true;
+  }
+  return false;
+}
+
+template <int CT, int TMAX, int KC, int NSPLIT>
+inline void tc_launch_inst(const TcKernelPlan& pl, const TcArgs& a, int sms, cudaStream_t stream) {
+  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
+  auto kfn = conv5_tc_kernel<CT, TMAX, KC, NSPLIT>;
+#ifndef VNB_EMULATE
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+      throw std::runtime_error("CUDA: cannot reserve shared memory for conv5_tc_kernel");
+    attr = true;
+  }
+#endif
+  const int grid = std::max(1, std::min(a.g.n_items, sms));
+  VNB_LAUNCH(kfn, grid, kTcThreads, Cfg::SMEM_BYTES, stream, pl.a1_hi, pl.a1_lo, pl.a2_hi, pl.a2_lo, pl.w_hi, pl.w_lo, a);
+}
+
+inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int sms, cudaStream_t stream) {
+  if (pl.CT == 16) {
+    if (split3) tc_launch_inst<16, 3, 16, 3>(pl, a, sms, stream);
+    else tc_launch_inst<16, 3, 16, 1>(pl, a, sms, stream);
+  } else {
+    if (split3) tc_launch_inst<32, 1, 32, 3>(pl, a, sms, stream);
+    else tc_launch_inst<32, 1, 32, 1>(pl, a, sms, stream);
+  }
+}
+
 }  // namespace vnb

@@ -1,16 +1,164 @@
-// tcgen05 implicit-GEMM convolution path: engine glue (filled in by the tensor-core kernel commit).
+// tcgen05 convolution path: engine glue (plans, weight packing, launches) and standalone op hooks.
 #pragma once
+#include "conv_tc.cuh"
 #include "engine.cuh"
+
 namespace vnb {
-inline void Engine::tc_setup() {}
-inline void Engine::tc_prepare_weights() {}
-inline void Engine::tc_run_fprop(Unit&, int) {}
-inline void Engine::tc_run_dgrad(Unit&, int) {}
-inline void Engine::tc_run_wgrad(Unit&, int) {}
-inline void tc_op_conv5(int, const float*, const float*, const float*, const float*, float*, int, Dims, int, int, bool) {
-  throw std::invalid_argument("tensor-core convolution path not built yet");
+
+inline int tc_query_sms() {
+#ifdef VNB_EMULATE
+  return 2;  // emulation: two persistent "CTAs" so the tile scheduler's striding is exercised
+#else
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+#endif
 }
+
+// fill the tensor maps of a plan; lo pointers may be null (single-pass bf16): hi is reused as a dummy
+inline void tc_encode_plan(TcKernelPlan& pl, int Nmax, const uint16_t* a1_hi, const uint16_t* a1_lo, const uint16_t* a2_hi,
+                           const uint16_t* a2_lo) {
+  const TcGeom& g = pl.g;
+  tma_encode_act(&pl.a1_hi, a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, g.bh, g.bd);
+  tma_encode_act(&pl.a1_lo, a1_lo ? a1_lo : a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, g.bh, g.bd);
+  if (g.C2 > 0) {
+    tma_encode_act(&pl.a2_hi, a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, g.bh, g.bd);
+    tma_encode_act(&pl.a2_lo, a2_lo ? a2_lo : a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, g.bh, g.bd);
+  } else {
+    pl.a2_hi = pl.a1_hi;
+    pl.a2_lo = pl.a1_lo;
+  }
+  const long long rows = static_cast<long long>(g.n_slices) * 25 * g.n_kc * 5 * pl.CT;
+  tma_encode_w(&pl.w_hi, pl.wp_hi, rows, pl.KC, 5 * pl.CT);
+  tma_encode_w(&pl.w_lo, pl.wp_lo ? pl.wp_lo : pl.wp_hi, rows, pl.KC, 5 * pl.CT);
+}
+
+inline void Engine::tc_setup() {
+  sm_count_ = tc_query_sms();
+  const bool lo = cfg_.precision == PREC_BF16X3;
+  const int NB = cfg_.max_batch;
+  for (Unit& u : units_) {
+    if (u.kind != U_CONV5) continue;
+    const Act& x1 = acts_[u.in1];
+    const Act& o = acts_[u.out];
+    const Dims d = o.dims;
+    TcKernelPlan& f = u.tc.fprop;
+    if (tc_plan_geometry(f, NB, d.D, d.H, d.W, u.Cin1, u.Cin2, u.Cout, 0)) {
+      f.wp_elems = u.w_count;
+      f.wp_hi = dev_alloc<uint16_t>(f.wp_elems);
+      f.wp_lo = lo ? dev_alloc<uint16_t>(f.wp_elems) : nullptr;
+      tc_encode_plan(f, NB, x1.a_hi, x1.a_lo, u.in2 >= 0 ? acts_[u.in2].a_hi : nullptr, u.in2 >= 0 ? acts_[u.in2].a_lo : nullptr);
+      f.valid = true;
+    }
+    TcKernelPlan& g = u.tc.dgrad;
+    if (u.need_dgrad && tc_plan_geometry(g, NB, d.D, d.H, d.W, u.Cout, 0, u.Cin1, u.Cin2)) {
+      g.wp_elems = u.w_count;
+      g.wp_hi = dev_alloc<uint16_t>(g.wp_elems);
+      g.wp_lo = lo ? dev_alloc<uint16_t>(g.wp_elems) : nullptr;
+      tc_encode_plan(g, NB, o.d_hi, o.d_lo, nullptr, nullptr);
+      g.valid = true;
+    }
+  }
+}
+
+inline void Engine::tc_prepare_weights() {
+  if (!weights_dirty_) return;
+  for (Unit& u : units_) {
+    if (u.kind != U_CONV5) continue;
+    const int Cin = u.Cin1 + u.Cin2;
+    for (int pass = 0; pass < 2; ++pass) {
+      TcKernelPlan& pl = pass == 0 ? u.tc.fprop : u.tc.dgrad;
+      if (!pl.valid) continue;
+      VNB_LAUNCH(pack_w5_kernel, grid_for(static_cast<long long>(pl.wp_elems), 256), 256, 0, stream_,
+                 (const float*)(params_ + u.w_off), Cin, u.Cout, pass, pl.CT, pl.KC, pl.wp_hi, pl.wp_lo);
+      ++launches_;
+    }
+  }
+  weights_dirty_ = false;
+}
+
+inline void Engine::tc_run_fprop(Unit& u, int N) {
+  TcKernelPlan& pl = u.tc.fprop;
+  TcArgs a;
+  a.g = pl.g;
+  a.g.N = N;
+  a.g.n_items = N * a.g.n_db * a.g.n_hb * a.g.n_slices;
+  a.bias = params_ + u.b_off;
+  a.res = u.res >= 0 ? acts_[u.res].a : nullptr;
+  a.out1 = u.z;
+  a.out2 = nullptr;
+  a.acc1 = a.acc2 = 0;
+  ProfScope ps(*this, 0, conv5_flops(u, N));
+  tc_launch(pl, a, cfg_.precision == PREC_BF16X3, sm_count_, stream_);
+  ++launches_;
+}
+
+inline void Engine::tc_run_dgrad(Unit& u, int N) {
+  TcKernelPlan& pl = u.tc.dgrad;
+  TcArgs a;
+  a.g = pl.g;
+  a.g.N = N;
+  a.g.n_items = N * a.g.n_db * a.g.n_hb * a.g.n_slices;
+  a.bias = nullptr;
+  a.res = nullptr;
+  a.out1 = acts_[u.in1].d;
+  a.acc1 = u.in1_accumulate ? 1 : 0;
+  a.out2 = u.in2 >= 0 ? acts_[u.in2].d : nullptr;
+  a.acc2 = u.in2_accumulate ? 1 : 0;
+  ProfScope ps(*this, 0, conv5_flops(u, N));
+  tc_launch(pl, a, cfg_.precision == PREC_BF16X3, sm_count_, stream_);
+  ++launches_;
+}
+
+inline void Engine::tc_run_wgrad(Unit&, int) {}
+
+// ---- standalone op hooks (tests): fp32 device buffers in, fp32 out ---------------------------------
+struct TcScratch {
+  std::vector<void*> ptrs;
+  template <class T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(n, 8) * sizeof(T)) != cudaSuccess) throw std::runtime_error("CUDA: out of memory in tc op hook");
+    ptrs.push_back(p);
+    return static_cast<T*>(p);
+  }
+  ~TcScratch() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+};
+
+inline void tc_op_conv5(int precision, const float* x, const float* w, const float* bias, const float* res, float* y, int n,
+                        Dims dims, int cin, int cout, bool dgrad_form) {
+  const bool lo = precision == PREC_BF16X3;
+  const int ci = dgrad_form ? cout : cin, co = dgrad_form ? cin : cout;
+  TcKernelPlan pl;
+  if (!tc_plan_geometry(pl, n, dims.D, dims.H, dims.W, ci, 0, co, 0))
+    throw std::invalid_argument("shape not supported by the tensor-core convolution (channels % 16, W | 128)");
+  TcScratch s;
+  const size_t nx = static_cast<size_t>(n) * dims.D * dims.H * dims.W * ci;
+  uint16_t* xh = s.alloc<uint16_t>(nx);
+  uint16_t* xl = lo ? s.alloc<uint16_t>(nx) : nullptr;
+  VNB_LAUNCH(split_bf16_kernel, 1024, 256, 0, 0, x, static_cast<long long>(nx), xh, xl);
+  pl.wp_elems = 125ull * cin * cout;
+  pl.wp_hi = s.alloc<uint16_t>(pl.wp_elems);
+  pl.wp_lo = lo ? s.alloc<uint16_t>(pl.wp_elems) : nullptr;
+  VNB_LAUNCH(pack_w5_kernel, 1024, 256, 0, 0, w, cin, cout, dgrad_form ? 1 : 0, pl.CT, pl.KC, pl.wp_hi, pl.wp_lo);
+  tc_encode_plan(pl, n, xh, xl, nullptr, nullptr);
+  TcArgs a;
+  a.g = pl.g;
+  a.bias = bias;
+  a.res = res;
+  a.out1 = y;
+  a.out2 = nullptr;
+  a.acc1 = a.acc2 = 0;
+  tc_launch(pl, a, lo, tc_query_sms(), 0);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
+    throw std::runtime_error("CUDA: tensor-core convolution kernel failed");
+}
+
 inline void tc_op_wgrad5(int, const float*, const float*, float*, int, Dims, int, int) {
   throw std::invalid_argument("tensor-core wgrad path not built yet");
 }
+
 }  // namespace vnb

@@ -19,10 +19,8 @@
 #include "bn_chain.h"
 #include "conv_ref.cuh"
 #include "kernels.cuh"
-#include "vnb_cuda.h"
-#ifndef VNB_EMULATE
 #include "conv_tc.cuh"
-#endif
+#include "vnb_cuda.h"
 
 namespace vnb {
 
@@ -97,9 +95,7 @@ struct Unit {
   float *scale = nullptr, *shift = nullptr, *P = nullptr, *Q = nullptr, *S = nullptr;
   // backward plan
   bool res_accumulate = false, in1_accumulate = false, in2_accumulate = false, need_dgrad = true;
-#ifndef VNB_EMULATE
   TcConvPlan tc;                      // tensor-core plan (precision != fp32)
-#endif
 };
 
 class Engine {
@@ -552,9 +548,7 @@ class Engine {
     terms_dev_ = dev_alloc<double>(static_cast<size_t>(NB) * kMaxClasses * 4);
     coef_dev_ = dev_alloc<float>(static_cast<size_t>(NB) * kMaxClasses * 3);
     loss_dev_ = dev_alloc<float>(4);
-#ifndef VNB_EMULATE
     if (tc) tc_setup();
-#endif
   }
 
   void init_default_params() {  // biases 0, gamma 1, beta 0, moving mean 0 / variance 1, alpha 0.1; weights 0
@@ -637,12 +631,10 @@ class Engine {
     const Act& o = acts_[u.out];
     const float* bias = params_ + u.b_off;
     if (u.kind == U_CONV5) {
-#ifndef VNB_EMULATE
-      if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid) {
+      if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid && !getenv("VNB_DEBUG_NO_TC_FPROP")) {
         tc_run_fprop(u, N);
         return;
       }
-#endif
       Conv5Args p;
       p.in1 = x1.a;
       p.in2 = u.in2 >= 0 ? acts_[u.in2].a : nullptr;
@@ -701,9 +693,7 @@ class Engine {
   }
 
   void forward(int N, float dropout, uint64_t seed, bool update_moving) {
-#ifndef VNB_EMULATE
     if (cfg_.precision != PREC_FP32) tc_prepare_weights();
-#endif
     for (size_t ui = 0; ui < units_.size(); ++ui) {
       Unit& u = units_[ui];
       const Act& o = acts_[u.out];
@@ -828,13 +818,10 @@ class Engine {
     VNB_CUDA_OK(cudaMemsetAsync(grads_ + u.b_off, 0, u.Cout * sizeof(float), stream_));
     if (u.kind == U_CONV5) {
       const int Cin = u.Cin1 + u.Cin2;
-#ifndef VNB_EMULATE
       const bool tc = cfg_.precision != PREC_FP32;
-      if (tc && u.need_dgrad && u.tc.dgrad.valid) {
+      if (tc && u.need_dgrad && u.tc.dgrad.valid && !getenv("VNB_DEBUG_NO_TC_DGRAD")) {
         tc_run_dgrad(u, N);
-      } else
-#endif
-      if (u.need_dgrad) {
+      } else if (u.need_dgrad) {
         VNB_LAUNCH(flip_transpose_w5_kernel, grid_for(static_cast<long long>(u.w_count), 256), 256, 0, stream_,
                    (const float*)(params_ + u.w_off), wflip_, Cin, u.Cout);
         ++launches_;
@@ -857,12 +844,10 @@ class Engine {
         ProfScope ps(*this, 0, conv5_flops(u, N));
         launch_conv5(p);
       }
-#ifndef VNB_EMULATE
       if (tc && u.tc.wgrad.valid) {
         tc_run_wgrad(u, N);
         return;
       }
-#endif
       Wgrad5Args w;
       w.in1 = x1.a;
       w.in2 = u.in2 >= 0 ? acts_[u.in2].a : nullptr;
@@ -957,14 +942,13 @@ class Engine {
 #endif
   }
 
-#ifndef VNB_EMULATE
-  // tensor-core path (conv_tc.cuh)
+  // tensor-core path (conv_tc.cuh / conv_tc_impl.cuh)
   void tc_setup();
   void tc_prepare_weights();
   void tc_run_fprop(Unit& u, int N);
   void tc_run_dgrad(Unit& u, int N);
   void tc_run_wgrad(Unit& u, int N);
-#endif
+  int sm_count_ = 148;
 
   EngineConfig cfg_;
   cudaStream_t stream_ = 0;

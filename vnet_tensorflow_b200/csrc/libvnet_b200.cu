@@ -5,9 +5,9 @@
 #include <new>
 
 #include "engine.cuh"
+#include "conv_tc_impl.cuh"
 #ifndef VNB_EMULATE
 #include "comm.cuh"
-#include "conv_tc_impl.cuh"
 #endif
 
 struct vnb_handle {
@@ -107,9 +107,6 @@ int vnb_create(const vnb_config* c, int device, vnb_handle** out) {
     for (int l = 0; l < e.num_levels && l < 8; ++l)
       if (e.num_convolutions[l] < 1) throw std::invalid_argument("NumConvolutions entries must be >= 1");
     if (e.bottom_convolutions < 1) throw std::invalid_argument("BottomConvolutions must be >= 1");
-#ifdef VNB_EMULATE
-    if (e.precision != VNB_PREC_FP32) throw std::invalid_argument("emulation build supports VNB_PREC_FP32 only");
-#endif
     std::unique_ptr<vnb_handle> h(new vnb_handle);
     h->device = device;
     h->engine.reset(new vnb::Engine(e));
@@ -408,7 +405,6 @@ void op_conv5(int precision, const float* x, const float* w, const float* bias, 
   VNB_CUDA_OK(cudaMemcpy(dw.p, w, 125ull * cin * cout * 4, cudaMemcpyHostToDevice));
   if (bias) VNB_CUDA_OK(cudaMemcpy(db.p, bias, co * 4, cudaMemcpyHostToDevice));
   if (res) VNB_CUDA_OK(cudaMemcpy(dr.p, res, V * co * 4, cudaMemcpyHostToDevice));
-#ifndef VNB_EMULATE
   if (precision != VNB_PREC_FP32) {
     tc_op_conv5(precision, dx.as<float>(), dw.as<float>(), bias ? db.as<float>() : nullptr, res ? dr.as<float>() : nullptr,
                 dy.as<float>(), n, dims, cin, cout, dgrad_form);
@@ -416,9 +412,8 @@ void op_conv5(int precision, const float* x, const float* w, const float* bias, 
     VNB_CUDA_OK(cudaMemcpy(y, dy.p, V * co * 4, cudaMemcpyDeviceToHost));
     return;
   }
+#ifndef VNB_EMULATE
   VNB_CUDA_OK(cudaFuncSetAttribute(conv5_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5_SMEM));
-#else
-  (void)precision;
 #endif
   const float* wk = dw.as<float>();
   if (dgrad_form) {
@@ -485,16 +480,14 @@ int vnb_op_conv5_wgrad(int device, int precision, const float* x, const float* d
     VNB_CUDA_OK(cudaMemcpy(bx.p, x, V * cin * 4, cudaMemcpyHostToDevice));
     VNB_CUDA_OK(cudaMemcpy(bdy.p, dy, V * cout * 4, cudaMemcpyHostToDevice));
     VNB_CUDA_OK(cudaMemset(bdw.p, 0, 125ull * cin * cout * 4));
-#ifndef VNB_EMULATE
     if (precision != VNB_PREC_FP32) {
       tc_op_wgrad5(precision, bx.as<float>(), bdy.as<float>(), bdw.as<float>(), n, dims, cin, cout);
       VNB_CUDA_OK(cudaDeviceSynchronize());
       VNB_CUDA_OK(cudaMemcpy(dw, bdw.p, 125ull * cin * cout * 4, cudaMemcpyDeviceToHost));
       return;
     }
+#ifndef VNB_EMULATE
     VNB_CUDA_OK(cudaFuncSetAttribute(conv5_wgrad_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kW5_SMEM));
-#else
-    (void)precision;
 #endif
     Wgrad5Args a;
     a.in1 = bx.as<float>();

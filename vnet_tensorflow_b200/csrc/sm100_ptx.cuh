@@ -11,6 +11,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+
 namespace sm100 {
 
 typedef CUtensorMap TmaDesc;
@@ -55,8 +57,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Waits are bounded (~4 s of SM clocks): a pipeline bug then traps with a message instead of hanging
+// the GPU until the driver watchdog fires.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {
+      printf("[vnet_b200] mbarrier wait timed out: block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x,
+             (int)threadIdx.x, bar, parity);
+      __trap();
+    }
   }
 }
 // bounded wait used by probes/tests: returns false on timeout instead of hanging the GPU
@@ -95,6 +106,11 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
       " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// named barrier among `count` threads (count a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------
