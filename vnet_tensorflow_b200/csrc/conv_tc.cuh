@@ -412,9 +412,6 @@ struct TcKernelPlan {   // one launch of conv5_tc_kernel
   uint16_t* wp_lo = nullptr;
   size_t wp_elems = 0;
 };
-struct TcConvPlan {
-  TcKernelPlan fprop, dgrad, wgrad;
-};
 
 // geometry for a [N][D][H][W] activation, kernel-side channel counts (C1+C2 in, Co1+Co2 out)
 inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C1, int C2, int Co1, int Co2) {

@@ -38,6 +38,7 @@ inline void Engine::tc_setup() {
   sm_count_ = tc_query_sms();
   const bool lo = cfg_.precision == PREC_BF16X3;
   const int NB = cfg_.max_batch;
+  size_t wg_partial_floats = 0;
   for (Unit& u : units_) {
     if (u.kind != U_CONV5) continue;
     const Act& x1 = acts_[u.in1];
@@ -59,7 +60,15 @@ inline void Engine::tc_setup() {
       tc_encode_plan(g, NB, o.d_hi, o.d_lo, nullptr, nullptr);
       g.valid = true;
     }
+    WgPlan& wg = u.tc.wgrad;
+    if (wg_plan_geometry(wg, NB, d.D, d.H, d.W, u.Cin1, u.Cin2, u.Cout, lo, sm_count_)) {
+      wg_encode_plan(wg, NB, x1.a_hi, x1.a_lo, u.in2 >= 0 ? acts_[u.in2].a_hi : nullptr,
+                     u.in2 >= 0 ? acts_[u.in2].a_lo : nullptr, o.d_hi, o.d_lo);
+      wg.valid = true;
+      wg_partial_floats = std::max(wg_partial_floats, wg.partial_floats);
+    }
   }
+  if (wg_partial_floats) wg_partial_ = dev_alloc<float>(wg_partial_floats);
 }
 
 inline void Engine::tc_prepare_weights() {
@@ -111,7 +120,11 @@ inline void Engine::tc_run_dgrad(Unit& u, int N) {
   ++launches_;
 }
 
-inline void Engine::tc_run_wgrad(Unit&, int) {}
+inline void Engine::tc_run_wgrad(Unit& u, int N) {
+  ProfScope ps(*this, 1, conv5_flops(u, N));
+  wg_launch(u.tc.wgrad, N, cfg_.precision == PREC_BF16X3, wg_partial_, grads_ + u.w_off, stream_);
+  launches_ += 2;
+}
 
 // ---- standalone op hooks (tests): fp32 device buffers in, fp32 out ---------------------------------
 struct TcScratch {
@@ -157,8 +170,24 @@ inline void tc_op_conv5(int precision, const float* x, const float* w, const flo
     throw std::runtime_error("CUDA: tensor-core convolution kernel failed");
 }
 
-inline void tc_op_wgrad5(int, const float*, const float*, float*, int, Dims, int, int) {
-  throw std::invalid_argument("tensor-core wgrad path not built yet");
+inline void tc_op_wgrad5(int precision, const float* x, const float* dy, float* dw, int n, Dims dims, int cin, int cout) {
+  const bool lo = precision == PREC_BF16X3;
+  WgPlan pl;
+  if (!wg_plan_geometry(pl, n, dims.D, dims.H, dims.W, cin, 0, cout, lo, tc_query_sms()))
+    throw std::invalid_argument("shape not supported by the tensor-core wgrad (channels % 16, W in {8..128})");
+  TcScratch s;
+  const size_t V = static_cast<size_t>(n) * dims.D * dims.H * dims.W;
+  uint16_t* xh = s.alloc<uint16_t>(V * cin);
+  uint16_t* xl = lo ? s.alloc<uint16_t>(V * cin) : nullptr;
+  uint16_t* zh = s.alloc<uint16_t>(V * cout);
+  uint16_t* zl = lo ? s.alloc<uint16_t>(V * cout) : nullptr;
+  VNB_LAUNCH(split_bf16_kernel, 1024, 256, 0, 0, x, static_cast<long long>(V * cin), xh, xl);
+  VNB_LAUNCH(split_bf16_kernel, 1024, 256, 0, 0, dy, static_cast<long long>(V * cout), zh, zl);
+  float* partial = s.alloc<float>(pl.partial_floats);
+  wg_encode_plan(pl, n, xh, xl, nullptr, nullptr, zh, zl);
+  wg_launch(pl, n, lo, partial, dw, 0);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
+    throw std::runtime_error("CUDA: tensor-core wgrad kernel failed");
 }
 
 }  // namespace vnb

@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "conv_tc.cuh"
 #include "vnb_cuda.h"
+#include "wgrad_tc.cuh"
 
 namespace vnb {
 
@@ -844,7 +845,7 @@ class Engine {
         ProfScope ps(*this, 0, conv5_flops(u, N));
         launch_conv5(p);
       }
-      if (tc && u.tc.wgrad.valid) {
+      if (tc && u.tc.wgrad.valid && !getenv("VNB_DEBUG_NO_TC_WGRAD")) {
         tc_run_wgrad(u, N);
         return;
       }
@@ -949,6 +950,7 @@ class Engine {
   void tc_run_dgrad(Unit& u, int N);
   void tc_run_wgrad(Unit& u, int N);
   int sm_count_ = 148;
+  float* wg_partial_ = nullptr;
 
   EngineConfig cfg_;
   cudaStream_t stream_ = 0;

@@ -1,0 +1,323 @@
+// tcgen05 filter-gradient kernel for the 5x5x5 convolutions (TF autodiff of layers2.py:59-63 under
+// optimizer.minimize, model.py:660):   dW[kd][kh][kw][ci][co] = sum_v X[v + (kd,kh,kw) - 2][ci] * dZ[v][co]
+//
+// GEMM with K = voxels along w.  Both operands are read straight from NDHWC bf16 tiles ([voxel rows]
+// [16 channels] = 32-byte rows, SWIZZLE_32B) as MN-major UMMA operands, and two tap axes are folded
+// into the MMA by *overlapping atoms* (descriptor semantics pinned on hardware by
+// tools/probe_tcgen05.cu, test mn_fold_*):
+//   A^T: M = 8 atoms x 16 ci, atom j = the X line shifted by j voxels (LBO = one 32-byte row) -> kw = j
+//   B  : N = 5 atoms x 16 co, atom l = the dZ line l lines further down (LBO = line pitch)     -> kh = 4 - l
+//   D_kd[(j,ci)][(l,co)] += sum_w X[dx][hx][w + j - 2][ci] * dZ[dx - kd + 2][hx - 2 + l][w][co]
+// so one M=128 x N=80 x K=16 MMA advances 25 taps at once (5 of the 8 kw atoms are useful), and the five
+// kd planes use five accumulators = 400 of the 512 TMEM columns, resident for the CTA's lifetime.
+// A CTA owns one (16-ci chunk, 16-co chunk) pair and a strided share of the voxel slabs (split-K);
+// partial filter gradients go to a scratch buffer and are summed in fixed order (deterministic).
+//
+// warp0 = TMA producer, warp1 = MMA issuer, warps 2-5 = final TMEM read-out.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace vnb {
+
+constexpr int kWgThreads = 192;
+
+struct WgGeom {
+  int N, D, H, W;
+  int C1, C2, Cout;
+  int HT;            // X lines per work item
+  int n_hb;          // ceil(H / HT)
+  int n_ci, n_co;    // 16-channel chunks
+  int splits;        // CTAs per (ci,co) pair
+  int z_stages;
+  int xt_bytes, zt_bytes;  // per-plane tile sizes (1024-aligned)
+  int npl;           // 1 (bf16) or 2 (hi/lo)
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ TmaDesc x1_lo,
+                 const __grid_constant__ TmaDesc x2_hi, const __grid_constant__ TmaDesc x2_lo,
+                 const __grid_constant__ TmaDesc z_hi, const __grid_constant__ TmaDesc z_lo, const WgGeom g,
+                 float* __restrict__ partial /* [split][pair][125][16][16] */) {
+  using namespace sm100;
+  constexpr int NPL = NSPLIT == 3 ? 2 : 1;
+  VNB_DYN_SMEM(uint8_t, smem_raw);
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const uint32_t sm_addr = smem_u32(sm);
+  const uint32_t x_ring = sm_addr;                                  // 2 x NPL x xt_bytes
+  const uint32_t z_ring = x_ring + 2u * NPL * g.xt_bytes;           // z_stages x NPL x zt_bytes
+  const uint32_t bar_off = 2u * NPL * g.xt_bytes + static_cast<uint32_t>(g.z_stages) * NPL * g.zt_bytes;
+  const uint32_t bar_base = sm_addr + bar_off;
+  auto xfull = [&](int s) { return bar_base + 8u * s; };            // [2]
+  auto xempty = [&](int s) { return bar_base + 8u * (2 + s); };     // [2]
+  auto zfull = [&](int s) { return bar_base + 8u * (4 + s); };      // [8]
+  auto zempty = [&](int s) { return bar_base + 8u * (12 + s); };    // [8]
+  const uint32_t done_bar = bar_base + 8u * 20;
+  const uint32_t slot_addr = bar_base + 8u * 21;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + bar_off + 8 * 21);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pair = blockIdx.x / g.splits, split = blockIdx.x % g.splits;
+  const int ci_chunk = pair / g.n_co, co_chunk = pair % g.n_co;
+  const int n_items = g.N * g.D * g.n_hb;
+  const int lpm = g.W == 8 ? 2 : 1;                // X lines covered by one K = 16 step
+  const int ksteps = g.W * lpm / 16;               // MMA k-steps per group of `lpm` lines
+  const uint32_t x_pitch = static_cast<uint32_t>(g.W + 8) * 32u;   // bytes between X lines in smem
+  const uint32_t z_pitch = static_cast<uint32_t>(g.W) * 32u;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(xfull(s), 1);
+      mbar_init(xempty(s), 1);
+    }
+    for (int s = 0; s < 8; ++s) {
+      mbar_init(zfull(s), 1);
+      mbar_init(zempty(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(slot_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const bool src1 = ci_chunk * 16 < g.C1;
+      const int xc = src1 ? ci_chunk * 16 : ci_chunk * 16 - g.C1;
+      const TmaDesc* xh = src1 ? &x1_hi : &x2_hi;
+      const TmaDesc* xl = src1 ? &x1_lo : &x2_lo;
+      int xs = 0, zs = 0;
+      uint32_t xph = 0, zph = 0;
+      const uint32_t x_tx = static_cast<uint32_t>(g.HT) * (g.W + 8) * 32u * NPL;
+      const uint32_t z_tx = static_cast<uint32_t>(g.HT + 4) * g.W * 32u * NPL;
+      for (int item = split; item < n_items; item += g.splits) {
+        const int hb = item % g.n_hb;
+        const int dx = (item / g.n_hb) % g.D;
+        const int n = item / (g.n_hb * g.D);
+        const int h0 = hb * g.HT;
+        mbar_wait(xempty(xs), xph ^ 1u);
+        mbar_expect_tx(xfull(xs), x_tx);
+        tma_load_5d(x_ring + (xs * NPL) * g.xt_bytes, xh, xfull(xs), xc, -2, h0, dx, n);
+        if (NSPLIT == 3) tma_load_5d(x_ring + (xs * NPL + 1) * g.xt_bytes, xl, xfull(xs), xc, -2, h0, dx, n);
+        if (++xs == 2) {
+          xs = 0;
+          xph ^= 1u;
+        }
+        for (int kd = 0; kd < 5; ++kd) {
+          const int dz = dx - kd + 2;
+          mbar_wait(zempty(zs), zph ^ 1u);
+          mbar_expect_tx(zfull(zs), z_tx);
+          tma_load_5d(z_ring + (zs * NPL) * g.zt_bytes, &z_hi, zfull(zs), co_chunk * 16, 0, h0 - 2, dz, n);
+          if (NSPLIT == 3) tma_load_5d(z_ring + (zs * NPL + 1) * g.zt_bytes, &z_lo, zfull(zs), co_chunk * 16, 0, h0 - 2, dz, n);
+          if (++zs == g.z_stages) {
+            zs = 0;
+            zph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(128, 80, FMT_BF16, 1, 1);
+      const uint32_t sbo_a = lpm == 2 ? x_pitch : 256u;   // K rows 8..15: next line (W = 8) or next 8 voxels
+      const uint32_t sbo_b = 256u;                         // dZ lines are contiguous, so both cases are +256 B
+      int xs = 0, zs = 0;
+      uint32_t xph = 0, zph = 0;
+      bool first = true;
+      for (int item = split; item < n_items; item += g.splits) {
+        mbar_wait(xfull(xs), xph);
+        tc_fence_after_sync();
+        const uint32_t xa_hi = x_ring + (xs * NPL) * g.xt_bytes;
+        const uint32_t xa_lo = xa_hi + g.xt_bytes;
+        for (int kd = 0; kd < 5; ++kd) {
+          mbar_wait(zfull(zs), zph);
+          tc_fence_after_sync();
+          const uint32_t za_hi = z_ring + (zs * NPL) * g.zt_bytes;
+          const uint32_t za_lo = za_hi + g.zt_bytes;
+          const uint32_t d_addr = tmem + kd * 80;
+          for (int t = 0; t < g.HT; t += lpm) {
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t koff = lpm == 2 ? 0u : static_cast<uint32_t>(ks) * 16u * 32u;
+              const uint32_t aoff = static_cast<uint32_t>(t) * x_pitch + koff;
+              const uint32_t boff = static_cast<uint32_t>(t) * z_pitch + koff;
+              const uint64_t da = make_smem_desc(xa_hi + aoff, 32, sbo_a, SWZ_32B);
+              const uint64_t db = make_smem_desc(za_hi + boff, z_pitch, sbo_b, SWZ_32B);
+              const uint32_t acc = (first && t == 0 && ks == 0) ? 0u : 1u;
+              mma_f16_ss(d_addr, da, db, idesc, acc);
+              if (NSPLIT == 3) {
+                const uint64_t da_lo = make_smem_desc(xa_lo + aoff, 32, sbo_a, SWZ_32B);
+                const uint64_t db_lo = make_smem_desc(za_lo + boff, z_pitch, sbo_b, SWZ_32B);
+                mma_f16_ss(d_addr, da_lo, db, idesc, 1u);
+                mma_f16_ss(d_addr, da, db_lo, idesc, 1u);
+              }
+            }
+          }
+          mma_commit(zempty(zs));
+          if (++zs == g.z_stages) {
+            zs = 0;
+            zph ^= 1u;
+          }
+        }
+        first = false;
+        mma_commit(xempty(xs));
+        if (++xs == 2) {
+          xs = 0;
+          xph ^= 1u;
+        }
+      }
+      mma_commit(done_bar);
+    }
+  } else {
+    // read-out: thread = accumulator row m = (kw slot j, ci); columns n = (l, co); kh = 4 - l
+    const int q = warp & 3, m = q * 32 + lane;
+    const int j = m / 16, ci = m % 16;
+    mbar_wait(done_bar, 0);
+    tc_fence_after_sync();
+    const bool has_work = split < n_items;
+    float* out = partial + (static_cast<size_t>(split) * (g.n_ci * g.n_co) + pair) * (125 * 256);
+    for (int kd = 0; kd < 5; ++kd)
+      for (int l = 0; l < 5; ++l) {
+        uint32_t v[16];
+        if (has_work) {
+          tmem_ld16(tmem + (static_cast<uint32_t>(q * 32) << 16) + kd * 80 + l * 16, v);
+          tmem_ld_wait();
+        } else {
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
+        if (j < 5) {
+          const int tap = (kd * 5 + (4 - l)) * 5 + j;
+          float4* o = reinterpret_cast<float4*>(out + (tap * 16 + ci) * 16);
+          for (int i = 0; i < 4; ++i)
+            o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                               __uint_as_float(v[4 * i + 3]));
+        }
+      }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// dw[tap][ci][co] = sum_split partial[split][pair(ci/16, co/16)][tap][ci%16][co%16]   (fixed order)
+__global__ void wgrad5_reduce_kernel(const float* __restrict__ partial, int splits, int n_ci, int n_co, int Cin, int Cout,
+                                     float* __restrict__ dw) {
+  const long long total = 125LL * Cin * Cout;
+  const int pairs = n_ci * n_co;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % Cout);
+    const int ci = static_cast<int>((i / Cout) % Cin);
+    const int tap = static_cast<int>(i / (static_cast<long long>(Cout) * Cin));
+    const int pair = (ci / 16) * n_co + co / 16;
+    const size_t off = (static_cast<size_t>(pair) * 125 + tap) * 256 + (ci % 16) * 16 + co % 16;
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += partial[static_cast<size_t>(sp) * pairs * (125 * 256) + off];
+    dw[i] = s;
+  }
+}
+
+struct WgPlan {
+  bool valid = false;
+  WgGeom g{};
+  TmaDesc x1_hi, x1_lo, x2_hi, x2_lo, z_hi, z_lo;
+  size_t smem = 0;
+  size_t partial_floats = 0;
+};
+
+inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int C2, int Cout, bool split3, int sms) {
+  if (C1 % 16 || C2 % 16 || Cout % 16 || C1 <= 0) return false;
+  if (!(W == 8 || W == 16 || W == 32 || W == 64 || W == 128)) return false;
+  WgGeom& g = pl.g;
+  g.N = N; g.D = D; g.H = H; g.W = W;
+  g.C1 = C1; g.C2 = C2; g.Cout = Cout;
+  g.npl = split3 ? 2 : 1;
+  int ht = std::max(2, 512 / W);
+  if (split3) ht = std::max(2, ht / 2);
+  ht = std::min(ht, H);
+  if (W == 8 && (ht % 2)) return false;
+  if (ht + 4 > 256 || W + 8 > 256) return false;
+  g.HT = ht;
+  g.n_hb = (H + ht - 1) / ht;
+  g.n_ci = (C1 + C2) / 16;
+  g.n_co = Cout / 16;
+  const int pairs = g.n_ci * g.n_co;
+  const int items = N * D * g.n_hb;
+  g.splits = std::max(1, std::min(items, (sms + pairs - 1) / pairs));
+  g.xt_bytes = ((ht * (W + 8) * 32 + 1023) / 1024) * 1024;
+  g.zt_bytes = (((ht + 4) * W * 32 + 1023) / 1024) * 1024;
+  const int budget = 200 * 1024 - 2 * g.npl * g.xt_bytes - 1024;
+  g.z_stages = std::min(8, budget / (g.npl * g.zt_bytes));
+  if (g.z_stages < 2) return false;
+  pl.smem = 2 * g.npl * g.xt_bytes + static_cast<size_t>(g.z_stages) * g.npl * g.zt_bytes + 256 + 1024;
+  pl.partial_floats = static_cast<size_t>(g.splits) * pairs * 125 * 256;
+  return true;
+}
+
+struct TcConvPlan {
+  TcKernelPlan fprop, dgrad;
+  WgPlan wgrad;
+};
+
+// x tensors: box (16, W+8, HT, 1, 1); dz tensor: box (16, W, HT+4, 1, 1); all SWIZZLE_32B
+inline void wg_encode_act(TmaDesc* out, const uint16_t* base, int N, int D, int H, int W, int C, int bw, int bh) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
+  const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)D * H * W * C * 2};
+  const uint32_t box[5] = {16, (uint32_t)bw, (uint32_t)bh, 1, 1};
+  tma_encode(out, base, 5, dims, str, box, 32);
+}
+
+inline void wg_encode_plan(WgPlan& pl, int Nmax, const uint16_t* x1_hi, const uint16_t* x1_lo, const uint16_t* x2_hi,
+                           const uint16_t* x2_lo, const uint16_t* z_hi, const uint16_t* z_lo) {
+  const WgGeom& g = pl.g;
+  wg_encode_act(&pl.x1_hi, x1_hi, Nmax, g.D, g.H, g.W, g.C1, g.W + 8, g.HT);
+  wg_encode_act(&pl.x1_lo, x1_lo ? x1_lo : x1_hi, Nmax, g.D, g.H, g.W, g.C1, g.W + 8, g.HT);
+  if (g.C2 > 0) {
+    wg_encode_act(&pl.x2_hi, x2_hi, Nmax, g.D, g.H, g.W, g.C2, g.W + 8, g.HT);
+    wg_encode_act(&pl.x2_lo, x2_lo ? x2_lo : x2_hi, Nmax, g.D, g.H, g.W, g.C2, g.W + 8, g.HT);
+  } else {
+    pl.x2_hi = pl.x1_hi;
+    pl.x2_lo = pl.x1_lo;
+  }
+  wg_encode_act(&pl.z_hi, z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.W, g.HT + 4);
+  wg_encode_act(&pl.z_lo, z_lo ? z_lo : z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.W, g.HT + 4);
+}
+
+inline void wg_launch(const WgPlan& pl, int N, bool split3, float* partial, float* dw, cudaStream_t stream) {
+  WgGeom g = pl.g;
+  g.N = N;
+  const int items = N * g.D * g.n_hb;
+  (void)items;
+  const int pairs = g.n_ci * g.n_co;
+  const int grid = pairs * g.splits;
+  if (split3) {
+    auto kfn = wgrad5_tc_kernel<3>;
+#ifndef VNB_EMULATE
+    static bool attr3 = false;
+    if (!attr3 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      throw std::runtime_error("CUDA: cannot reserve shared memory for wgrad5_tc_kernel");
+    attr3 = true;
+#endif
+    VNB_LAUNCH(kfn, grid, kWgThreads, pl.smem, stream, pl.x1_hi, pl.x1_lo, pl.x2_hi, pl.x2_lo, pl.z_hi, pl.z_lo, g, partial);
+  } else {
+    auto kfn = wgrad5_tc_kernel<1>;
+#ifndef VNB_EMULATE
+    static bool attr1 = false;
+    if (!attr1 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      throw std::runtime_error("CUDA: cannot reserve shared memory for wgrad5_tc_kernel");
+    attr1 = true;
+#endif
+    VNB_LAUNCH(kfn, grid, kWgThreads, pl.smem, stream, pl.x1_hi, pl.x1_lo, pl.x2_hi, pl.x2_lo, pl.z_hi, pl.z_lo, g, partial);
+  }
+  const long long total = 125LL * (g.C1 + g.C2) * g.Cout;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 2368));
+  VNB_LAUNCH(wgrad5_reduce_kernel, blocks, 256, 0, stream, (const float*)partial, g.splits, g.n_ci, g.n_co, g.C1 + g.C2, g.Cout, dw);
+}
+
+}  // namespace vnb
