@@ -150,3 +150,21 @@ def test_abi_error_behaviour(emul_lib):
     rc = emul_lib.vnb_forward(None, None, 1, None, None, None)
     assert rc == -1 and b"handle" in emul_lib.vnb_last_error()
     eng.close()
+
+
+def test_sixteen_channel_net_tight_gradients(emul_lib):
+    """16-channel network in fp32 mode: exercises the vectorised BN passes and the tiled 2x2x2 kernels
+    (which need channel multiples of 16) against tight oracle bounds."""
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=16, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=1)
+    P, N = 8, 2
+    params = perturbed_params(spec)
+    img, lab = synth_batch(1, N, P, 1, 2)
+    eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 1.0), emul_lib)
+    eng.set_params(params)
+    l = eng.forward_backward(img, lab, update_moving_stats=True)
+    lo, lg, go, upd = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
+    logits, _, _ = eng.forward(img)
+    assert abs(l - float(lo)) < 2e-6
+    assert rel_err(logits, lg.numpy()) < 2e-5
+    _grad_check(eng, go, spec, 5e-4)
+    eng.close()

@@ -18,6 +18,7 @@
 
 #include "bn_chain.h"
 #include "conv_ref.cuh"
+#include "k2_tiled.cuh"
 #include "kernels.cuh"
 #include "conv_tc.cuh"
 #include "vnb_cuda.h"
@@ -593,6 +594,11 @@ class Engine {
     }
     return bp;
   }
+  static bool v4_ok(int C, long long total) { return C % 4 == 0 && C >= 4 && 256 % (C / 4) == 0 && total < (1LL << 31); }
+  static int v4_blocks(long long total4, int C) {  // grid stride must keep (i % C4) fixed per thread: any multiple of 256 threads does
+    (void)C;
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((total4 + 256 * 8 - 1) / (256 * 8), kMaxRedBlocks)));
+  }
   static RedGeom red_geom(int C, int c0, long long V) {
     RedGeom g;
     g.C = C;
@@ -665,18 +671,15 @@ class Engine {
         p.CF = u.Cin1;
         p.CC = u.Cout;
         p.cd = o.dims;
-        const long long total = voxels_of(o.dims, N) * u.Cout;
-        VNB_LAUNCH(k2_gather_kernel, grid_for(total, 256), 256, 0, stream_, p);
+        launch_k2_gather(p);
       } else {
         p.coarse_in = x1.a;
         p.fine_out = u.z;
         p.CF = u.Cout;
         p.CC = u.Cin1;
         p.cd = x1.dims;
-        const long long total = voxels_of(o.dims, N) * u.Cout;
-        VNB_LAUNCH(k2_scatter_kernel, grid_for(total, 256), 256, 0, stream_, p);
+        launch_k2_scatter(p);
       }
-      ++launches_;
     } else if (u.kind == U_CONV1) {
       const long long V = voxels_of(o.dims, N);
       VNB_LAUNCH(conv1_fprop_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, (const float*)x1.a,
@@ -705,15 +708,22 @@ class Engine {
         VNB_LAUNCH(image_stats_kernel, nblk, 256, 0, stream_, (const float*)u.z, V, partial_);
       } else {
         run_conv_fprop(u, N);
-        RedGeom g = red_geom(u.Cout, 0, V);
-        nblk = red_blocks(g);
-        for (int c0 = 0; c0 < u.Cout; c0 += 256) {
-          g = red_geom(u.Cout, c0, V);
-          VNB_LAUNCH(bn_stats_kernel, nblk, red_threads(g), 0, stream_, (const float*)u.z, g, partial_);
+        if (v4_ok(u.Cout, V * u.Cout)) {
+          const unsigned total4 = static_cast<unsigned>(V * u.Cout / 4);
+          nblk = v4_blocks(total4, u.Cout);
+          VNB_LAUNCH(bn_stats_v4_kernel, nblk, 256, 0, stream_, (const float*)u.z, u.Cout, total4, partial_);
           ++launches_;
+        } else {
+          RedGeom g = red_geom(u.Cout, 0, V);
+          nblk = red_blocks(g);
+          for (int c0 = 0; c0 < u.Cout; c0 += 256) {
+            g = red_geom(u.Cout, c0, V);
+            VNB_LAUNCH(bn_stats_kernel, nblk, red_threads(g), 0, stream_, (const float*)u.z, g, partial_);
+            ++launches_;
+          }
         }
       }
-      VNB_LAUNCH(bn_finalize_fwd_kernel, (u.Cout + 127) / 128, 128, 0, stream_, (const double*)partial_, nblk, nq_stride,
+      VNB_LAUNCH(bn_finalize_fwd_kernel, u.Cout, 128, 0, stream_, (const double*)partial_, nblk, nq_stride,
                  u.Cout, static_cast<double>(V), u.chain, bn_params(u), u.kind == U_INPUT_TILE ? 1 : 0,
                  update_moving ? 1 : 0, u.mean, u.var, u.scale, u.shift);
       ApplyArgs ap;
@@ -730,7 +740,10 @@ class Engine {
       ap.drop_rate = u.has_dropout ? dropout : 0.f;
       ap.seed = seed;
       ap.unit = static_cast<uint32_t>(ui);
-      VNB_LAUNCH(bn_apply_kernel, grid_for(ap.total, 256), 256, 0, stream_, ap);
+      if (v4_ok(u.Cout, ap.total))
+        VNB_LAUNCH(bn_apply_v4_kernel, grid_for(ap.total / 4, 256), 256, 0, stream_, ap);
+      else
+        VNB_LAUNCH(bn_apply_kernel, grid_for(ap.total, 256), 256, 0, stream_, ap);
       launches_ += 3;
     }
   }
@@ -777,12 +790,21 @@ class Engine {
       b.drop_rate = u.has_dropout ? dropout : 0.f;
       b.seed = seed;
       b.unit = static_cast<uint32_t>(ui);
-      RedGeom g = red_geom(u.Cout, 0, V);
-      const int nblk = red_blocks(g);
-      for (int c0 = 0; c0 < u.Cout; c0 += 256) {
-        g = red_geom(u.Cout, c0, V);
-        VNB_LAUNCH(bn_bwd_reduce_kernel, nblk, red_threads(g), 0, stream_, b, g, partial_);
+      const bool v4 = v4_ok(u.Cout, V * u.Cout);
+      int nblk;
+      if (v4) {
+        const unsigned total4 = static_cast<unsigned>(V * u.Cout / 4);
+        nblk = v4_blocks(total4, u.Cout);
+        VNB_LAUNCH(bn_bwd_reduce_v4_kernel, nblk, 256, 0, stream_, b, total4, partial_);
         ++launches_;
+      } else {
+        RedGeom g = red_geom(u.Cout, 0, V);
+        nblk = red_blocks(g);
+        for (int c0 = 0; c0 < u.Cout; c0 += 256) {
+          g = red_geom(u.Cout, c0, V);
+          VNB_LAUNCH(bn_bwd_reduce_kernel, nblk, red_threads(g), 0, stream_, b, g, partial_);
+          ++launches_;
+        }
       }
       BnGradPtrs gp;
       for (int k = 0; k < 3; ++k) {
@@ -791,14 +813,17 @@ class Engine {
         gp.dbeta[k] = on ? grads_ + u.beta_off[k] : nullptr;
       }
       gp.dalpha = u.has_act ? grads_ + u.alpha_off : nullptr;
-      VNB_LAUNCH(bn_finalize_bwd_kernel, (u.Cout + 127) / 128, 128, 0, stream_, (const double*)partial_, nblk, u.Cout,
+      VNB_LAUNCH(bn_finalize_bwd_kernel, u.Cout, 128, 0, stream_, (const double*)partial_, nblk, u.Cout,
                  static_cast<double>(V), u.chain, bn_params(u), (const double*)u.var, gp, u.P, u.Q, u.S);
       ++launches_;
       if (u.kind == U_INPUT_TILE) {  // image needs no gradient
         notify_bucket(ui);
         continue;
       }
-      VNB_LAUNCH(bn_bwd_apply_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, b, V * u.Cout);
+      if (v4)
+        VNB_LAUNCH(bn_bwd_apply_v4_kernel, grid_for(V * u.Cout / 4, 256), 256, 0, stream_, b, V * u.Cout);
+      else
+        VNB_LAUNCH(bn_bwd_apply_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, b, V * u.Cout);
       ++launches_;
       run_conv_backward(u, N);
       notify_bucket(ui);
@@ -887,9 +912,7 @@ class Engine {
         if (u.need_dgrad) {
           p.fine_out = x1.d;
           p.accumulate = u.in1_accumulate ? 1 : 0;
-          const long long total = voxels_of(x1.dims, N) * u.Cin1;
-          VNB_LAUNCH(k2_scatter_kernel, grid_for(total, 256), 256, 0, stream_, p);
-          ++launches_;
+          launch_k2_scatter(p);
         }
       } else {  // z fine, x coarse
         p.CF = u.Cout;
@@ -899,22 +922,12 @@ class Engine {
         if (u.need_dgrad) {
           p.coarse_out = x1.d;
           p.accumulate = u.in1_accumulate ? 1 : 0;
-          const long long total = voxels_of(x1.dims, N) * u.Cin1;
-          VNB_LAUNCH(k2_gather_kernel, grid_for(total, 256), 256, 0, stream_, p);
-          ++launches_;
+          launch_k2_gather(p);
         }
         p.coarse_in = x1.a;
       }
       p.bias = nullptr;
-      const long long Vc = voxels_of(p.cd, N);
-      const long long outs = 8LL * p.CF * p.CC;
-      const int oblocks = static_cast<int>((outs + 255) / 256);
-      long long splits = std::max<long long>(1, std::min<long long>(Vc, (2 * 1184 + oblocks - 1) / oblocks));
-      const int vps = static_cast<int>((Vc + splits - 1) / splits);
-      splits = (Vc + vps - 1) / vps;
-      dim3 grid(oblocks, static_cast<unsigned>(splits));
-      VNB_LAUNCH(k2_wgrad_kernel, grid, 256, 0, stream_, p, vps);
-      ++launches_;
+      launch_k2_wgrad(p);
     } else if (u.kind == U_CONV1) {
       const long long V = voxels_of(o.dims, N);
       if (u.need_dgrad) {
@@ -928,6 +941,47 @@ class Engine {
       VNB_LAUNCH(conv1_wgrad_kernel, blocks, threads, 0, stream_, (const float*)x1.a, dz, dw, V, u.Cin1, u.Cout, vpb);
       ++launches_;
     }
+  }
+  static bool k2_tiled_ok(const K2Args& p) { return p.CF % 16 == 0 && p.CC % 16 == 0; }
+  void launch_k2_gather(const K2Args& p) {
+    const long long M = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
+    if (k2_tiled_ok(p)) {
+      dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (p.CC + kK2_BN - 1) / kK2_BN);
+      VNB_LAUNCH(k2_gather_tiled_kernel, grid, 256, 0, stream_, p, M);
+    } else {
+      VNB_LAUNCH(k2_gather_kernel, grid_for(M * p.CC, 256), 256, 0, stream_, p);
+    }
+    ++launches_;
+  }
+  void launch_k2_scatter(const K2Args& p) {
+    const long long M = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
+    if (k2_tiled_ok(p)) {
+      dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (8 * p.CF + kK2_BN - 1) / kK2_BN);
+      VNB_LAUNCH(k2_scatter_tiled_kernel, grid, 256, 0, stream_, p, M);
+    } else {
+      VNB_LAUNCH(k2_scatter_kernel, grid_for(M * 8 * p.CF, 256), 256, 0, stream_, p);
+    }
+    ++launches_;
+  }
+  void launch_k2_wgrad(const K2Args& p) {
+    const long long M = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
+    if (k2_tiled_ok(p)) {
+      const int gx = (8 * p.CF + kK2_BM - 1) / kK2_BM, gy = (p.CC + kK2_BN - 1) / kK2_BN;
+      long long splits = std::max<long long>(1, std::min<long long>((M + 255) / 256, (4 * 148 + gx * gy - 1) / (gx * gy)));
+      long long mps = ((M + splits - 1) / splits + kK2_BK - 1) / kK2_BK * kK2_BK;
+      splits = (M + mps - 1) / mps;
+      dim3 grid(gx, gy, static_cast<unsigned>(splits));
+      VNB_LAUNCH(k2_wgrad_tiled_kernel, grid, 256, 0, stream_, p, M, mps);
+    } else {
+      const long long outs = 8LL * p.CF * p.CC;
+      const int oblocks = static_cast<int>((outs + 255) / 256);
+      long long splits = std::max<long long>(1, std::min<long long>(M, (2 * 1184 + oblocks - 1) / oblocks));
+      const int vps = static_cast<int>((M + splits - 1) / splits);
+      splits = (M + vps - 1) / vps;
+      dim3 grid(oblocks, static_cast<unsigned>(splits));
+      VNB_LAUNCH(k2_wgrad_kernel, grid, 256, 0, stream_, p, vps);
+    }
+    ++launches_;
   }
   double conv5_flops(const Unit& u, int N) const {  // 2*MAC of one 5^3 pass (fprop = dgrad = wgrad)
     return 2.0 * 125.0 * (u.Cin1 + u.Cin2) * u.Cout * static_cast<double>(voxels_of(acts_[u.out].dims, N));

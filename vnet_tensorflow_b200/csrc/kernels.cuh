@@ -135,14 +135,23 @@ __global__ void bn_finalize_fwd_kernel(const double* __restrict__ partial, int n
                                        int update_moving, double* __restrict__ mean_out,
                                        double* __restrict__ var_out, float* __restrict__ scale_out,
                                        float* __restrict__ shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int c = blockIdx.x;  // one block per channel; threads sum the per-block partials in a fixed order
   const int pc = single_channel_stats ? 0 : c;
   const int PC = single_channel_stats ? 1 : C;
+  __shared__ double fin_red[2][128];
+  double ps = 0.0, ps2 = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    ps += partial[(static_cast<size_t>(b) * nq_stride + 0) * PC + pc];
+    ps2 += partial[(static_cast<size_t>(b) * nq_stride + 1) * PC + pc];
+  }
+  fin_red[0][threadIdx.x] = ps;
+  fin_red[1][threadIdx.x] = ps2;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   double s = 0.0, s2 = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += partial[(static_cast<size_t>(b) * nq_stride + 0) * PC + pc];
-    s2 += partial[(static_cast<size_t>(b) * nq_stride + 1) * PC + pc];
+  for (unsigned i = 0; i < blockDim.x; ++i) {
+    s += fin_red[0][i];
+    s2 += fin_red[1][i];
   }
   const double mu = s / count;
   double var = s2 / count - mu * mu;
@@ -269,13 +278,24 @@ __global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int n
                                        int chain, BnParams bp, const double* __restrict__ var,
                                        BnGradPtrs gp, float* __restrict__ P, float* __restrict__ Q,
                                        float* __restrict__ S) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int c = blockIdx.x;  // one block per channel
+  __shared__ double fin_red[3][128];
+  double p0 = 0, p1 = 0, p2 = 0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    p0 += partial[(static_cast<size_t>(b) * 3 + 0) * C + c];
+    p1 += partial[(static_cast<size_t>(b) * 3 + 1) * C + c];
+    p2 += partial[(static_cast<size_t>(b) * 3 + 2) * C + c];
+  }
+  fin_red[0][threadIdx.x] = p0;
+  fin_red[1][threadIdx.x] = p1;
+  fin_red[2][threadIdx.x] = p2;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   double R0 = 0, R1 = 0, Ra = 0;
-  for (int b = 0; b < nblk; ++b) {
-    R0 += partial[(static_cast<size_t>(b) * 3 + 0) * C + c];
-    R1 += partial[(static_cast<size_t>(b) * 3 + 1) * C + c];
-    Ra += partial[(static_cast<size_t>(b) * 3 + 2) * C + c];
+  for (unsigned i = 0; i < blockDim.x; ++i) {
+    R0 += fin_red[0][i];
+    R1 += fin_red[1][i];
+    Ra += fin_red[2][i];
   }
   double gam[3] = {1, 1, 1}, bet[3] = {0, 0, 0};
   const int nbn = chain_num_bn(chain);
@@ -527,6 +547,181 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long n, uint
     hi[i] = h;
     if (lo) lo[i] = f32_to_bf16(f - bf16_to_f32(h));
   }
+}
+
+}  // namespace vnb
+
+// =================================================================================================
+// Vectorised (4 channels per thread, 128-bit accesses) variants of the hot per-element passes.
+// Preconditions (checked by the engine, which falls back to the scalar kernels otherwise):
+//   C % 4 == 0, (C/4) divides 256, total elements < 2^31.
+// =================================================================================================
+namespace vnb {
+
+VNB_HD uint32_t pack_bf16x2(float a, float b) {
+  return static_cast<uint32_t>(f32_to_bf16(a)) | (static_cast<uint32_t>(f32_to_bf16(b)) << 16);
+}
+
+__device__ __forceinline__ void store_hi_lo4(uint16_t* hi, uint16_t* lo, unsigned i4, const float (&y)[4]) {
+  uint16_t h[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = f32_to_bf16(y[k]);
+  reinterpret_cast<uint2*>(hi)[i4] = make_uint2(h[0] | (static_cast<uint32_t>(h[1]) << 16), h[2] | (static_cast<uint32_t>(h[3]) << 16));
+  if (lo)
+    reinterpret_cast<uint2*>(lo)[i4] = make_uint2(pack_bf16x2(y[0] - bf16_to_f32(h[0]), y[1] - bf16_to_f32(h[1])),
+                                                  pack_bf16x2(y[2] - bf16_to_f32(h[2]), y[3] - bf16_to_f32(h[3])));
+}
+
+__global__ void __launch_bounds__(256) bn_apply_v4_kernel(ApplyArgs p) {
+  const unsigned total4 = static_cast<unsigned>(p.total / 4), C4 = static_cast<unsigned>(p.C / 4);
+  const float keep_scale = p.drop_rate > 0.f ? 1.0f / (1.0f - p.drop_rate) : 1.0f;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const unsigned c = (i % C4) * 4;
+    float z[4];
+    if (p.tiled_input) {
+      const float v = p.z[i / C4];
+      z[0] = z[1] = z[2] = z[3] = v;
+    } else {
+      const float4 f = reinterpret_cast<const float4*>(p.z)[i];
+      z[0] = f.x; z[1] = f.y; z[2] = f.z; z[3] = f.w;
+    }
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(p.shift + c);
+    float y[4] = {sc.x * z[0] + sh.x, sc.y * z[1] + sh.y, sc.z * z[2] + sh.z, sc.w * z[3] + sh.w};
+    if (p.alpha) {
+      const float4 al = *reinterpret_cast<const float4*>(p.alpha + c);
+      y[0] = y[0] > 0.f ? y[0] : al.x * y[0];
+      y[1] = y[1] > 0.f ? y[1] : al.y * y[1];
+      y[2] = y[2] > 0.f ? y[2] : al.z * y[2];
+      y[3] = y[3] > 0.f ? y[3] : al.w * y[3];
+    }
+    if (p.drop_rate > 0.f) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        y[k] = dropout_uniform(p.seed, p.unit, static_cast<uint64_t>(i) * 4 + k) >= p.drop_rate ? y[k] * keep_scale : 0.f;
+    }
+    reinterpret_cast<float4*>(p.a)[i] = make_float4(y[0], y[1], y[2], y[3]);
+    if (p.a_hi) store_hi_lo4(p.a_hi, p.a_lo, i, y);
+  }
+}
+
+// g for 4 consecutive channels (same semantics as bwd_g)
+__device__ __forceinline__ void bwd_g4(const BwdArgs& p, unsigned i, unsigned c, const float (&z)[4], float (&g)[4],
+                                       float (&yhat)[4], float (&dd)[4]) {
+  const float4 sc = *reinterpret_cast<const float4*>(p.scale + c);
+  const float4 sh = *reinterpret_cast<const float4*>(p.shift + c);
+  const float4 d4 = reinterpret_cast<const float4*>(p.d)[i];
+  yhat[0] = sc.x * z[0] + sh.x; yhat[1] = sc.y * z[1] + sh.y; yhat[2] = sc.z * z[2] + sh.z; yhat[3] = sc.w * z[3] + sh.w;
+  dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
+  if (p.drop_rate > 0.f) {
+    const float inv = 1.0f / (1.0f - p.drop_rate);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      dd[k] = dropout_uniform(p.seed, p.unit, static_cast<uint64_t>(i) * 4 + k) >= p.drop_rate ? dd[k] * inv : 0.f;
+  }
+  if (p.alpha) {
+    const float4 al = *reinterpret_cast<const float4*>(p.alpha + c);
+    const float a[4] = {al.x, al.y, al.z, al.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = yhat[k] > 0.f ? dd[k] : (yhat[k] < 0.f ? dd[k] * a[k] : 0.f);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) g[k] = dd[k];
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_v4_kernel(BwdArgs p, long long total) {
+  const unsigned total4 = static_cast<unsigned>(total / 4), C4 = static_cast<unsigned>(p.C / 4);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
+    const unsigned c = (i % C4) * 4;
+    const float4 zf = reinterpret_cast<const float4*>(p.z)[i];
+    const float z[4] = {zf.x, zf.y, zf.z, zf.w};
+    float g[4], yhat[4], dd[4];
+    bwd_g4(p, i, c, z, g, yhat, dd);
+    const float4 P = *reinterpret_cast<const float4*>(p.P + c);
+    const float4 Q = *reinterpret_cast<const float4*>(p.Q + c);
+    const float4 S = *reinterpret_cast<const float4*>(p.S + c);
+    float dz[4];
+    dz[0] = P.x * g[0] + Q.x + S.x * (z[0] - static_cast<float>(p.mean[c]));
+    dz[1] = P.y * g[1] + Q.y + S.y * (z[1] - static_cast<float>(p.mean[c + 1]));
+    dz[2] = P.z * g[2] + Q.z + S.z * (z[2] - static_cast<float>(p.mean[c + 2]));
+    dz[3] = P.w * g[3] + Q.w + S.w * (z[3] - static_cast<float>(p.mean[c + 3]));
+    reinterpret_cast<float4*>(p.d)[i] = make_float4(dz[0], dz[1], dz[2], dz[3]);
+    if (p.res_grad) {
+      float4* r = reinterpret_cast<float4*>(p.res_grad) + i;
+      float4 o = make_float4(dz[0], dz[1], dz[2], dz[3]);
+      if (p.res_accumulate) {
+        const float4 old = *r;
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *r = o;
+    }
+    if (p.d_hi) store_hi_lo4(p.d_hi, p.d_lo, i, dz);
+  }
+}
+
+// per-channel reductions, 4 channels per thread. blockDim = 256, C4 = C/4 divides 256.
+// partial layout identical to the scalar kernels: [block][NQ][C] doubles.
+template <int NQ>
+__device__ __forceinline__ void block_channel_combine_v4(const float (&acc)[NQ][4], unsigned C4, int C,
+                                                         double* __restrict__ partial) {
+  __shared__ float red[NQ * 4][256];
+  const unsigned t = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[q * 4 + k][t] = acc[q][k];
+  __syncthreads();
+  if (t < C4) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        double s = 0.0;
+        for (unsigned g = t; g < 256; g += C4) s += red[q * 4 + k][g];
+        partial[(static_cast<size_t>(blockIdx.x) * NQ + q) * C + t * 4 + k] = s;
+      }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_v4_kernel(const float* __restrict__ z, int C, unsigned total4,
+                                                          double* __restrict__ partial) {
+  const unsigned C4 = static_cast<unsigned>(C / 4);
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  // thread t keeps channel quad t % C4 because the stride gridDim*256 is a multiple of C4
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total4; i += gridDim.x * 256u) {
+    const float4 f = reinterpret_cast<const float4*>(z)[i];
+    acc[0][0] += f.x; acc[0][1] += f.y; acc[0][2] += f.z; acc[0][3] += f.w;
+    acc[1][0] += f.x * f.x; acc[1][1] += f.y * f.y; acc[1][2] += f.z * f.z; acc[1][3] += f.w * f.w;
+  }
+  block_channel_combine_v4<2>(acc, C4, C, partial);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_v4_kernel(BwdArgs p, unsigned total4, double* __restrict__ partial) {
+  const unsigned C4 = static_cast<unsigned>(p.C / 4);
+  const unsigned c = (threadIdx.x % C4) * 4;
+  const float mu[4] = {static_cast<float>(p.mean[c]), static_cast<float>(p.mean[c + 1]), static_cast<float>(p.mean[c + 2]),
+                       static_cast<float>(p.mean[c + 3])};
+  float acc[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total4; i += gridDim.x * 256u) {
+    float z[4];
+    if (p.tiled_input) {
+      const float v = p.z[i / C4];
+      z[0] = z[1] = z[2] = z[3] = v;
+    } else {
+      const float4 zf = reinterpret_cast<const float4*>(p.z)[i];
+      z[0] = zf.x; z[1] = zf.y; z[2] = zf.z; z[3] = zf.w;
+    }
+    float g[4], yhat[4], dd[4];
+    bwd_g4(p, i, c, z, g, yhat, dd);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc[0][k] += g[k];
+      acc[1][k] += g[k] * (z[k] - mu[k]);
+      if (p.alpha && yhat[k] < 0.f) acc[2][k] += dd[k] * yhat[k];
+    }
+  }
+  block_channel_combine_v4<3>(acc, C4, p.C, partial);
 }
 
 }  // namespace vnb
