@@ -21,7 +21,7 @@ LOGIT_TOL = {"fp32": 2e-4, "bf16x3": 1e-3, "bf16": 8e-2}
 # fp32 path (same engine, exact-fp32 convolutions) is therefore held to a tight bound and pins the
 # engine logic; the tensor-core precisions get a bound at the conditioning floor, and their kernels
 # are pinned tightly per op in test_conv5_ops_match_torch.
-GRAD_TOL = {"fp32": 2e-3, "bf16x3": 8e-2, "bf16": 0.5}
+GRAD_TOL = {"fp32": 5e-3, "bf16x3": 8e-2, "bf16": 0.5}
 
 
 def _check_grads(eng, grads_ref, spec, tol, l2=False):

@@ -1,0 +1,258 @@
+"""Drop-in for the reference orchestrator `model.image2label` (model.py:169-1243): same constructor
+(`image2label(sess, config)`, `sess` ignored), same `train()` / `evaluate()` entry points, same config
+keys, checkpoint naming and stdout lines -- with the TF1 graph replaced by the B200 engine.
+
+Mapped reference code:
+  read_config            model.py:185-245   -> vnet_tensorflow_b200.config (tolerant)
+  build_model_graph      model.py:297-630   -> VNetEngine construction + variable initialisation
+  dataset_iterator       model.py:267-295   -> NiftiDataset3D.NiftiDataset(...).get_dataset() + shuffle(3) + batch
+  train                  model.py:632-815   -> epoch / step loop, LogInterval checkpoints, TestStep test loss
+  evaluate_single_3D     model.py:817-977   -> sliding windows, softmax accumulation, argmax, optional LCC / volume threshold
+  evaluate               model.py:1131-1243 -> per-case loop, NIfTI outputs
+TensorBoard image/metric summaries (model.py:314-334,449-463,570-626) are out of scope; scalars go to
+`LogDir/{train,test}/scalars.jsonl`.
+"""
+from __future__ import annotations
+
+import datetime
+import json
+import math
+import os
+import random
+import shutil
+import sys
+from typing import List
+
+import numpy as np
+
+from . import checkpoint, config as config_mod, nifti
+from .engine import VNetEngine
+from .init import initialize
+from .pipeline import NiftiDataset3D
+
+
+def _now():
+    return datetime.datetime.now()
+
+
+class image2label(object):
+    def __init__(self, sess, config, device: int = 0, library=None):
+        self.sess = sess  # kept for signature compatibility (model.py:170); unused
+        self.config = config
+        self.device = device
+        self.library = library
+        self.engine = None
+        self.epoches = 999999999999999999
+
+    # ---- configuration ------------------------------------------------------------------------
+    def read_config(self):
+        print("{}: Reading configuration file...".format(_now()))
+        self.cfg = config_mod.from_dict(self.config) if isinstance(self.config, dict) else self.config
+        for k, v in vars(self.cfg).items():
+            setattr(self, k, v)
+        self.dimension = len(self.cfg.patch_shape)
+        if self.dimension != 3:
+            sys.exit("Only the 3-D V-Net path is accelerated (PatchShape must have 3 entries)")
+        print("{}: Reading configuration file complete".format(_now()))
+
+    def _transforms(self, yaml_path, phase):
+        """model.py:341-402: instantiate NiftiDataset3D transforms by name from the pipeline YAML."""
+        if not yaml_path or not os.path.exists(yaml_path):
+            return []
+        import yaml
+        with open(yaml_path) as f:
+            spec = yaml.safe_load(f)
+        out = []
+        for t in (spec.get("preprocess", {}).get(phase, {}) or {}).get("3D", []) or []:
+            cls = getattr(NiftiDataset3D, t["name"], None)
+            if cls is None:
+                print("{}: transform {} is not available in this port, skipped".format(_now(), t["name"]))
+                continue
+            out.append(cls(**(t.get("variables") or {})))
+        return out
+
+    def dataset_iterator(self, data_dir, transforms, train=True):
+        """model.py:267-295: dataset -> shuffle(buffer 3) -> batch(drop_remainder)."""
+        usable = (not self.cfg.synthetic) and os.path.isdir(data_dir) and self._has_nifti(data_dir)
+        if usable:
+            ds = NiftiDataset3D.NiftiDataset(data_dir=data_dir, image_filenames=self.image_filenames,
+                                             label_filename=self.label_filename, transforms=transforms, train=train,
+                                             labels=self.label_classes).get_dataset()
+        else:
+            print("{}: no readable NIfTI data in {} -- using synthetic patches".format(_now(), data_dir))
+            ds = NiftiDataset3D.SyntheticDataset(self.patch_shape, self.input_channel_num, self.output_channel_num,
+                                                 size=4 * self.batch_size, seed=0 if train else 10 ** 6).get_dataset()
+
+        def batches():
+            buf: List = []
+            it = iter(ds)
+            pending = []
+            while True:
+                while len(buf) < 3:  # tf.data shuffle(buffer_size=3)
+                    try:
+                        buf.append(next(it))
+                    except StopIteration:
+                        break
+                if not buf:
+                    break
+                pending.append(buf.pop(random.randrange(len(buf))))
+                if len(pending) == self.batch_size:
+                    yield np.stack([p[0] for p in pending], 0), np.stack([p[1] for p in pending], 0)
+                    pending = []
+        return batches
+
+    def _has_nifti(self, data_dir):
+        for case in sorted(os.listdir(data_dir)):
+            p = os.path.join(data_dir, case, self.image_filenames[0])
+            if os.path.exists(p):
+                try:
+                    nifti.read(p)
+                    return True
+                except Exception:
+                    return False
+        return False
+
+    def build_model_graph(self, max_batch=None):
+        print("{}: Start to build model graph...".format(_now()))
+        self.engine = VNetEngine(
+            num_classes=self.output_channel_num, in_channels=self.input_channel_num, patch_shape=self.patch_shape,
+            max_batch=max_batch or max(self.batch_size, self.evaluate_batch), num_channels=self.num_channel,
+            num_levels=self.num_levels, num_convolutions=self.num_convolutions, bottom_convolutions=self.bottom_convolutions,
+            precision=self.precision, loss=self.loss_name, loss_weights=self.loss_weights, loss_alpha=self.loss_alpha,
+            optimizer=self.optimizer_name, learning_rate=self.initial_learning_rate, decay_factor=self.decay_factor,
+            decay_steps=self.decay_steps, device=self.device, library=self.library)
+        initialize(self.engine)  # tf.initializers.global_variables(), model.py:673
+        print("{}: Build graph complete".format(_now()))
+
+    # ---- training -----------------------------------------------------------------------------
+    def _log(self, which, step, **scalars):
+        d = os.path.join(self.log_dir, which)
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "scalars.jsonl"), "a") as f:
+            f.write(json.dumps(dict(step=step, **scalars)) + "\n")
+
+    def train(self):
+        print("{}: VNet Tensorflow training start...".format(_now()))
+        self.read_config()
+        self.build_model_graph()
+        train_batches = self.dataset_iterator(self.train_data_dir, self._transforms(self.training_pipeline, "train"), True)
+        test_batches = self.dataset_iterator(self.test_data_dir, self._transforms(self.training_pipeline, "test"), True) if self.testing else None
+        start_epoch = 0
+        print("{}: Start training...".format(_now()))
+        if not self.restore_training:  # model.py:679-688: wipe log / checkpoint dirs
+            for d in (self.log_dir, self.ckpt_dir):
+                if os.path.exists(d):
+                    shutil.rmtree(d)
+                os.makedirs(d)
+        else:
+            latest = checkpoint.latest(self.ckpt_dir)
+            if latest is not None:
+                print("{}: Last checkpoint found at {}, loading...".format(_now(), self.ckpt_dir))
+                _, start_epoch = checkpoint.restore(self.engine, latest)
+            print("{}: Last checkpoint epoch: {}".format(_now(), start_epoch))
+            print("{}: Last checkpoint global step: {}".format(_now(), self.engine.global_step))
+        test_iter = iter(test_batches()) if test_batches else None
+        for epoch in range(start_epoch, self.epoches):
+            print("{}: Epoch {} starts...".format(_now(), epoch + 1))
+            loss_sum, count = 0.0, 0
+            for image, label in train_batches():
+                if self.engine.global_step > self.max_itr:
+                    sys.exit("{}: Reach maximum iteration steps, training abort.".format(_now()))
+                loss = self.engine.train_step(image, label, self.dropout_rate, seed=self.engine.global_step)
+                print('{}: Segmentation training loss: {}'.format(_now(), str(loss)))
+                loss_sum += loss
+                count += 1
+                step = self.engine.global_step
+                self._log("train", step, total_loss=loss)
+                if step % self.log_interval == 0:
+                    print("{}: Saving checkpoint of step {} at {}...".format(_now(), step, self.ckpt_dir))
+                    checkpoint.save(self.engine, self.ckpt_dir, step, epoch)
+                if self.testing and step % self.test_step == 0:
+                    try:
+                        timg, tlab = next(test_iter)
+                    except StopIteration:
+                        test_iter = iter(test_batches())
+                        timg, tlab = next(test_iter)
+                    tloss = self.engine.loss(timg, tlab)  # dropout 0, batch statistics, no update (model.py:784-789)
+                    print('{}: Segmentation testing loss: {}'.format(_now(), str(tloss)))
+                    self._log("test", step, total_loss=tloss)
+            print("{}: Training of epoch {} complete, epoch loss: {}".format(_now(), epoch + 1, loss_sum / max(count, 1)))
+            print("{}: Saving checkpoint of epoch {} at {}...".format(_now(), epoch + 1, self.ckpt_dir))
+            checkpoint.save(self.engine, self.ckpt_dir, self.engine.global_step, epoch + 1)
+            print("{}: Saving checkpoint succeed".format(_now()))
+
+    # ---- evaluation ---------------------------------------------------------------------------
+    def evaluate_single_3D(self, images_np: np.ndarray):
+        """model.py:866-937 on an [X,Y,Z,M] array: returns (label int64 [X,Y,Z], softmax sums list, weight)."""
+        P, S = self.patch_shape, self.evaluate_stride
+        dims = images_np.shape[:3]
+        pads = [(0, max(p - d, 0)) for d, p in zip(dims, P)] + [(0, 0)]
+        if any(p[1] for p in pads):
+            images_np = np.pad(images_np, pads)
+        vol = images_np.shape[:3]
+        num = [int(math.ceil((vol[a] - P[a]) / float(S[a]))) + 1 for a in range(3)]
+        windows = []
+        for i in range(num[0]):
+            for j in range(num[1]):
+                for k in range(num[2]):
+                    st = []
+                    for a, idx in enumerate((i, j, k)):
+                        s = idx * S[a]
+                        if s + P[a] > vol[a]:  # last patch clamped (model.py:879-892)
+                            s = vol[a] - P[a]
+                        st.append(s)
+                    windows.append(tuple(st))
+        softmax_np = np.zeros(vol + (self.output_channel_num,), np.float32)
+        weight_np = np.zeros(vol, np.float32)
+        B = self.evaluate_batch
+        for b0 in range(0, len(windows), B):
+            group = windows[b0:b0 + B]
+            batch = np.stack([images_np[s[0]:s[0] + P[0], s[1]:s[1] + P[1], s[2]:s[2] + P[2], :] for s in group], 0)
+            _, softmax, _ = self.engine.forward(batch, want_logits=False, want_argmax=False)
+            for j, s in enumerate(group):
+                sl = (slice(s[0], s[0] + P[0]), slice(s[1], s[1] + P[1]), slice(s[2], s[2] + P[2]))
+                softmax_np[sl] += softmax[j]
+                weight_np[sl] += 1.0
+        label_np = np.argmax(softmax_np, axis=-1)  # model.py:934 (un-normalised sums)
+        crop = tuple(slice(0, d) for d in dims)
+        return label_np[crop], softmax_np[crop], weight_np[crop]
+
+    def evaluate(self):
+        self.read_config()
+        self.build_model_graph(max_batch=self.evaluate_batch)
+        checkpoint.restore(self.engine, self.checkpoint_path)  # model.py:1138-1139
+        transforms = self._transforms(self.evaluate_pipeline, "evaluate")
+        print("{}: Start evaluation...".format(_now()))
+        for case in sorted(os.listdir(self.evaluate_data_dir)):
+            case_dir = os.path.join(self.evaluate_data_dir, case)
+            if not os.path.isdir(case_dir):
+                continue
+            print("{}: Evaluating {}...".format(_now(), case))
+            images = [nifti.read(os.path.join(case_dir, ch)) for ch in self.evaluate_image_filenames]
+            sample = {'image': images, 'label': nifti.Image(np.zeros(images[0].GetSize(), np.int32), images[0].spacing, images[0].origin)}
+            for t in transforms:
+                sample = t(sample)
+            arr = np.stack([np.asarray(im.array, np.float32) for im in sample['image']], -1)
+            label_np, softmax_np, weight_np = self.evaluate_single_3D(arr)
+            out = np.zeros(label_np.shape, np.int32)
+            for idx, value in enumerate(self.label_classes):  # class index -> label value
+                out[label_np == idx] = value
+            if self.evaluate_lcc or self.evaluate_volume_threshold > 0:  # model.py:1217-1223
+                from scipy import ndimage
+                comp, n = ndimage.label(out > 0)
+                if n > 0:
+                    sizes = ndimage.sum(out > 0, comp, range(1, n + 1))
+                    keep = np.zeros(n + 1, bool)
+                    if self.evaluate_lcc:
+                        keep[1 + int(np.argmax(sizes))] = True
+                    else:
+                        keep[1:] = sizes >= self.evaluate_volume_threshold
+                    out[~keep[comp]] = 0
+            ref = sample['image'][0]
+            nifti.write(os.path.join(case_dir, self.evaluate_label_filename), nifti.Image(out, ref.spacing, ref.origin))
+            if self.evaluate_probability_output:  # model.py:935-937,1234-1243
+                prob = softmax_np / np.maximum(weight_np[..., None], 1.0)
+                for c, value in enumerate(self.label_classes):
+                    name = self.evaluate_probability_filename.replace(".nii", "_%s.nii" % value, 1)
+                    nifti.write(os.path.join(case_dir, name), nifti.Image(prob[..., c].astype(np.float32), ref.spacing, ref.origin))
+        print("{}: Evaluation complete".format(_now()))
