@@ -125,8 +125,8 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     sample = 64 if args.patch >= 64 else args.patch
-    steps = max(1, min(args.steps, 8))        # bounded: each step is a ~seconds-long CPU training step
-    warm = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 3))        # bounded: one CPU training step on a 64^3 patch takes ~30 s
+    warm = 1
     times, cores = cpu_reference_step_seconds(sample, steps, warm)
     t = float(np.mean(times))
     scale = (sample / args.patch) ** 3

@@ -76,3 +76,24 @@ def test_engine_bf16x3_matches_oracle(emul_lib):
         ref = go[k].numpy().astype(np.float64)
         assert np.sqrt(((v - ref) ** 2).sum()) <= 5e-2 * max(np.sqrt((ref ** 2).sum()), 1e-9), k
     eng.close()
+
+
+@pytest.mark.parametrize("cin,cout,dims,n,prec", [
+    (16, 16, (3, 6, 16), 1, 2),     # one (ci,co) pair, split-K over slabs
+    (16, 16, (2, 5, 32), 2, 1),     # odd H (partial last slab), bf16x3
+    (32, 16, (2, 4, 64), 1, 2),     # two ci chunks
+    (16, 32, (3, 8, 8), 1, 1),      # W = 8: one K step spans two lines
+    (16, 16, (2, 3, 128), 1, 2),    # full-width lines
+])
+def test_wgrad5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
+    """MN-major overlapping-atom tap folding (kw on M, kh on N, kd on five TMEM accumulators)."""
+    rng = np.random.default_rng(3)
+    x = rng.normal(0, 1, (n,) + dims + (cin,)).astype(np.float32)
+    dy = rng.normal(0, 1, (n,) + dims + (cout,)).astype(np.float32)
+    xr, dyr = (_bf16(x), _bf16(dy)) if prec == 2 else (x, dy)
+    wt = torch.zeros(5, 5, 5, cin, cout, dtype=torch.float64, requires_grad=True)
+    R.conv_same(torch.from_numpy(xr).double(), wt, torch.zeros(cout).double()).backward(torch.from_numpy(dyr).double())
+    dw = np.empty((5, 5, 5, cin, cout), np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    emul_lib.check(emul_lib.vnb_op_conv5_wgrad(0, prec, ptr(x), ptr(dy), ptr(dw), n, *dims, cin, cout))
+    assert rel_err(dw, wt.grad.numpy()) < (1e-6 if prec == 2 else 3e-5)

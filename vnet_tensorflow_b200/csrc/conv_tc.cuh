@@ -18,6 +18,7 @@
 //   * precision: bf16 operands, fp32 accumulate.  NSPLIT = 3 runs hi*hi + lo*hi + hi*lo on
 //     (hi, lo) bf16 splits of activations and weights = fp32-grade products ("bf16x3").
 #pragma once
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -58,6 +59,10 @@ struct TcGeom {
   int n_slices;        // (Co1+Co2) / CT
   int n_kc;            // (C1+C2) / KC
   int n_items;
+  // resident-lines mode (bd == 1): one A load per (kd, k-chunk) holds bh+4 lines and serves all five kh taps
+  int resident;
+  int a_stage_bytes;   // per operand plane, 1024-aligned
+  int n_a, n_b;        // ring depths
 };
 
 struct TcArgs {
@@ -69,134 +74,17 @@ struct TcArgs {
   int acc1, acc2;
 };
 
+// epilogue shared by both pipeline modes: TMEM -> registers -> shift-sum over the 5 kw slices -> bias /
+// residual -> fp32 store.  Runs on warps 2..5 (128 threads = 128 TMEM lanes).
 template <int CT, int TMAX, int KC, int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1)
-conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ TmaDesc a1_lo,
-                const __grid_constant__ TmaDesc a2_hi, const __grid_constant__ TmaDesc a2_lo,
-                const __grid_constant__ TmaDesc w_hi, const __grid_constant__ TmaDesc w_lo, const TcArgs p) {
+__device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi, uint32_t tmem, uint32_t tfull0, uint32_t tempty0) {
   using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
   using namespace sm100;
-  VNB_DYN_SMEM(uint8_t, smem_raw);
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  const uint32_t sm_addr = smem_u32(sm);
-  float* epi = reinterpret_cast<float*>(sm + kTcStages * Cfg::STAGE_BYTES);
-  const uint32_t bar_base = sm_addr + kTcStages * Cfg::STAGE_BYTES + kTcEpiBytes;
-  // barriers: full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4); then TMEM slot
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + 2 + b); };
-  const uint32_t slot_addr = bar_base + 8u * (2 * kTcStages + 4);
-  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTcStages * Cfg::STAGE_BYTES + kTcEpiBytes + 8 * (2 * kTcStages + 4));
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const TcGeom& g = p.g;
-  const int n_it = 25 * g.n_kc;
-  const int kc1 = g.C1 / KC;
-
-  if (tid == 0) {
-    for (int s = 0; s < kTcStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(slot_addr, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = *slot_ptr;
-
-  if (warp == 0) {
-    // ======================= TMA producer (one elected lane) =======================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-        const int slice = item % g.n_slices;
-        int x = item / g.n_slices;
-        const int hb = x % g.n_hb;
-        x /= g.n_hb;
-        const int db = x % g.n_db;
-        const int n = x / g.n_db;
-        const int h0 = hb * g.bh, d0 = db * g.bd;
-        for (int it = 0; it < n_it; ++it) {
-          const int kc = it % g.n_kc, kh = (it / g.n_kc) % 5, kd = it / (5 * g.n_kc);
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t st_addr = sm_addr + stage * Cfg::STAGE_BYTES;
-          const uint32_t a_bytes = static_cast<uint32_t>(g.T) * 128u * Cfg::ROWB;
-          mbar_expect_tx(full_bar(stage), Cfg::NPL * (a_bytes + Cfg::NB * Cfg::ROWB));
-          const bool src1 = kc < kc1;
-          const int cch = (src1 ? kc : kc - kc1) * KC;
-          tma_load_5d(st_addr, src1 ? &a1_hi : &a2_hi, full_bar(stage), cch, 0, h0 + kh - 2, d0 + kd - 2, n);
-          const int brow = (slice * n_it + it) * Cfg::NB;
-          tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES, &w_hi, full_bar(stage), 0, brow);
-          if (NSPLIT == 3) {
-            tma_load_5d(st_addr + Cfg::A_BYTES, src1 ? &a1_lo : &a2_lo, full_bar(stage), cch, 0, h0 + kh - 2, d0 + kd - 2, n);
-            tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES + Cfg::B_BYTES, &w_lo, full_bar(stage), 0, brow);
-          }
-          if (++stage == kTcStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ======================= MMA issuer (one elected lane) =======================
-    if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(128, Cfg::NB, FMT_BF16);
-      int stage = 0;
-      uint32_t phase = 0;
-      int j = 0;
-      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
-        const int buf = j & 1;
-        const uint32_t use = static_cast<uint32_t>(j >> 1);
-        mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
-        tc_fence_after_sync();
-        const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
-        for (int it = 0; it < n_it; ++it) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after_sync();
-          const uint32_t a_hi = sm_addr + stage * Cfg::STAGE_BYTES;
-          const uint32_t a_lo = a_hi + Cfg::A_BYTES;
-          const uint32_t b_hi = a_hi + Cfg::NPL * Cfg::A_BYTES;
-          const uint32_t b_lo = b_hi + Cfg::B_BYTES;
-          for (int t = 0; t < g.T; ++t) {
-#pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks) {
-              const uint32_t aoff = t * 128 * Cfg::ROWB + ks * 32;
-              const uint64_t da_hi = make_smem_desc(a_hi + aoff, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
-              const uint64_t db_hi = make_smem_desc(b_hi + ks * 32, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
-              const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-              mma_f16_ss(d_base + t * Cfg::NB, da_hi, db_hi, idesc, acc);
-              if (NSPLIT == 3) {
-                const uint64_t da_lo = make_smem_desc(a_lo + aoff, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
-                const uint64_t db_lo = make_smem_desc(b_lo + ks * 32, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
-                mma_f16_ss(d_base + t * Cfg::NB, da_lo, db_hi, idesc, 1u);
-                mma_f16_ss(d_base + t * Cfg::NB, da_hi, db_lo, idesc, 1u);
-              }
-            }
-          }
-          mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
-          if (++stage == kTcStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-        mma_commit(tfull_bar(buf));  // accumulators of this item complete
-      }
-    }
-  } else {
-    // ======================= epilogue (4 warps = 128 TMEM lanes) =======================
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  auto tfull_bar = [&](int b) { return tfull0 + 8u * b; };
+  auto tempty_bar = [&](int b) { return tempty0 + 8u * b; };
+  {
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;     // row inside a 128-row tile
     const int Ctot = g.Co1 + g.Co2;
@@ -297,6 +185,297 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
       tc_fence_before_sync();
       mbar_arrive(tempty_bar(buf));  // 128 arrivals free the accumulator buffer
     }
+  }
+}
+
+// Resident-lines pipeline (plans with bd == 1): ring A holds, per (kd, k-chunk), the bh+4 input lines that
+// all five kh taps of the item read (the kh shift is a start-address offset of kh*W rows inside the swizzled
+// tile); ring B streams the packed weights per (kd, kh, k-chunk).  Cuts the activation traffic L2->SMEM
+// from 25 to 5*(bh+4)/bh line loads per output line.
+template <int CT, int TMAX, int KC, int NSPLIT>
+__device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const TmaDesc& a1_lo, const TmaDesc& a2_hi,
+                                                  const TmaDesc& a2_lo, const TmaDesc& w_hi, const TmaDesc& w_lo,
+                                                  const TcArgs& p, uint8_t* sm, uint32_t sm_addr) {
+  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
+  using namespace sm100;
+  const TcGeom& g = p.g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_ring = sm_addr;
+  const uint32_t b_ring = a_ring + static_cast<uint32_t>(g.n_a) * Cfg::NPL * g.a_stage_bytes;
+  const uint32_t epi_off = static_cast<uint32_t>(g.n_a) * Cfg::NPL * g.a_stage_bytes + static_cast<uint32_t>(g.n_b) * Cfg::NPL * Cfg::B_BYTES;
+  float* epi = reinterpret_cast<float*>(sm + epi_off);
+  const uint32_t bar_base = sm_addr + epi_off + kTcEpiBytes;
+  auto afull = [&](int s) { return bar_base + 8u * s; };          // [4]
+  auto aempty = [&](int s) { return bar_base + 8u * (4 + s); };   // [4]
+  auto bfull = [&](int s) { return bar_base + 8u * (8 + s); };    // [4]
+  auto bempty = [&](int s) { return bar_base + 8u * (12 + s); };  // [4]
+  const uint32_t tfull0 = bar_base + 8u * 16, tempty0 = bar_base + 8u * 18;
+  const uint32_t slot_addr = bar_base + 8u * 20;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + epi_off + kTcEpiBytes + 8 * 20);
+  const int kc1 = g.C1 / KC;
+  const int n_it = 25 * g.n_kc;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(afull(s), 1);
+      mbar_init(aempty(s), 1);
+      mbar_init(bfull(s), 1);
+      mbar_init(bempty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull0 + 8u * b, 1);
+      mbar_init(tempty0 + 8u * b, 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(slot_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *slot_ptr;
+  const uint32_t a_rows = static_cast<uint32_t>(g.T * 128 + 4 * g.W);   // rows held per A stage
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        const int slice = item % g.n_slices;
+        int x = item / g.n_slices;
+        const int hb = x % g.n_hb;
+        x /= g.n_hb;
+        const int db = x % g.n_db;
+        const int n = x / g.n_db;
+        const int h0 = hb * g.bh, d0 = db;
+        for (int kd = 0; kd < 5; ++kd)
+          for (int kc = 0; kc < g.n_kc; ++kc) {
+            mbar_wait(aempty(as), aph ^ 1u);
+            mbar_expect_tx(afull(as), Cfg::NPL * a_rows * Cfg::ROWB);
+            const bool src1 = kc < kc1;
+            const int cch = (src1 ? kc : kc - kc1) * KC;
+            const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
+            tma_load_5d(a_addr, src1 ? &a1_hi : &a2_hi, afull(as), cch, 0, h0 - 2, d0 + kd - 2, n);
+            if (NSPLIT == 3) tma_load_5d(a_addr + g.a_stage_bytes, src1 ? &a1_lo : &a2_lo, afull(as), cch, 0, h0 - 2, d0 + kd - 2, n);
+            if (++as == g.n_a) {
+              as = 0;
+              aph ^= 1u;
+            }
+            for (int kh = 0; kh < 5; ++kh) {
+              const int it = (kd * 5 + kh) * g.n_kc + kc;
+              mbar_wait(bempty(bs), bph ^ 1u);
+              mbar_expect_tx(bfull(bs), Cfg::NPL * Cfg::NB * Cfg::ROWB);
+              const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
+              const int brow = (slice * n_it + it) * Cfg::NB;
+              tma_load_2d(b_addr, &w_hi, bfull(bs), 0, brow);
+              if (NSPLIT == 3) tma_load_2d(b_addr + Cfg::B_BYTES, &w_lo, bfull(bs), 0, brow);
+              if (++bs == g.n_b) {
+                bs = 0;
+                bph ^= 1u;
+              }
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(128, Cfg::NB, FMT_BF16);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int j = 0;
+      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
+        const int buf = j & 1;
+        const uint32_t use = static_cast<uint32_t>(j >> 1);
+        mbar_wait(tempty0 + 8u * buf, (use & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
+        bool first = true;
+        for (int kd = 0; kd < 5; ++kd)
+          for (int kc = 0; kc < g.n_kc; ++kc) {
+            mbar_wait(afull(as), aph);
+            tc_fence_after_sync();
+            const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
+            const uint64_t da_hi0 = make_smem_desc(a_addr, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
+            const uint64_t da_lo0 = da_hi0 + (static_cast<uint32_t>(g.a_stage_bytes) >> 4);
+            for (int kh = 0; kh < 5; ++kh) {
+              mbar_wait(bfull(bs), bph);
+              tc_fence_after_sync();
+              const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
+              const uint64_t db_hi0 = make_smem_desc(b_addr, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
+              const uint64_t db_lo0 = db_hi0 + (Cfg::B_BYTES >> 4);
+              for (int t = 0; t < g.T; ++t) {
+#pragma unroll
+                for (int ks = 0; ks < KC / 16; ++ks) {
+                  const uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t * 128 + kh * g.W) * Cfg::ROWB + ks * 32) >> 4);
+                  const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
+                  const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                  const uint32_t d_addr = d_base + t * Cfg::NB;
+                  mma_f16_ss(d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
+                  if (NSPLIT == 3) {
+                    mma_f16_ss(d_addr, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
+                    mma_f16_ss(d_addr, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
+                  }
+                }
+              }
+              first = false;
+              mma_commit(bempty(bs));
+              if (++bs == g.n_b) {
+                bs = 0;
+                bph ^= 1u;
+              }
+            }
+            mma_commit(aempty(as));
+            if (++as == g.n_a) {
+              as = 0;
+              aph ^= 1u;
+            }
+          }
+        mma_commit(tfull0 + 8u * buf);
+      }
+    }
+  } else {
+    conv5_tc_epilogue<CT, TMAX, KC, NSPLIT>(p, epi, tmem, tfull0, tempty0);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+template <int CT, int TMAX, int KC, int NSPLIT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ TmaDesc a1_lo,
+                const __grid_constant__ TmaDesc a2_hi, const __grid_constant__ TmaDesc a2_lo,
+                const __grid_constant__ TmaDesc w_hi, const __grid_constant__ TmaDesc w_lo, const TcArgs p) {
+  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
+  using namespace sm100;
+  VNB_DYN_SMEM(uint8_t, smem_raw);
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const uint32_t sm_addr = smem_u32(sm);
+  float* epi = reinterpret_cast<float*>(sm + kTcStages * Cfg::STAGE_BYTES);
+  const uint32_t bar_base = sm_addr + kTcStages * Cfg::STAGE_BYTES + kTcEpiBytes;
+  // barriers: full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4); then TMEM slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + 2 + b); };
+  const uint32_t slot_addr = bar_base + 8u * (2 * kTcStages + 4);
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTcStages * Cfg::STAGE_BYTES + kTcEpiBytes + 8 * (2 * kTcStages + 4));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TcGeom& g = p.g;
+  const int n_it = 25 * g.n_kc;
+  const int kc1 = g.C1 / KC;
+  if (g.resident) {
+    conv5_tc_resident<CT, TMAX, KC, NSPLIT>(a1_hi, a1_lo, a2_hi, a2_lo, w_hi, w_lo, p, sm, sm_addr);
+    return;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(slot_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *slot_ptr;
+
+  if (warp == 0) {
+    // ======================= TMA producer (one elected lane) =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+        const int slice = item % g.n_slices;
+        int x = item / g.n_slices;
+        const int hb = x % g.n_hb;
+        x /= g.n_hb;
+        const int db = x % g.n_db;
+        const int n = x / g.n_db;
+        const int h0 = hb * g.bh, d0 = db * g.bd;
+        for (int it = 0; it < n_it; ++it) {
+          const int kc = it % g.n_kc, kh = (it / g.n_kc) % 5, kd = it / (5 * g.n_kc);
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t st_addr = sm_addr + stage * Cfg::STAGE_BYTES;
+          const uint32_t a_bytes = static_cast<uint32_t>(g.T) * 128u * Cfg::ROWB;
+          mbar_expect_tx(full_bar(stage), Cfg::NPL * (a_bytes + Cfg::NB * Cfg::ROWB));
+          const bool src1 = kc < kc1;
+          const int cch = (src1 ? kc : kc - kc1) * KC;
+          tma_load_5d(st_addr, src1 ? &a1_hi : &a2_hi, full_bar(stage), cch, 0, h0 + kh - 2, d0 + kd - 2, n);
+          const int brow = (slice * n_it + it) * Cfg::NB;
+          tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES, &w_hi, full_bar(stage), 0, brow);
+          if (NSPLIT == 3) {
+            tma_load_5d(st_addr + Cfg::A_BYTES, src1 ? &a1_lo : &a2_lo, full_bar(stage), cch, 0, h0 + kh - 2, d0 + kd - 2, n);
+            tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES + Cfg::B_BYTES, &w_lo, full_bar(stage), 0, brow);
+          }
+          if (++stage == kTcStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (one elected lane) =======================
+    if (lane == 0) {
+      const uint32_t idesc = make_instr_desc(128, Cfg::NB, FMT_BF16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int j = 0;
+      for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
+        const int buf = j & 1;
+        const uint32_t use = static_cast<uint32_t>(j >> 1);
+        mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
+        for (int it = 0; it < n_it; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after_sync();
+          // descriptors differ between MMAs only in the start-address field (bits 0-13, units of 16 B):
+          // build one base per operand per stage and advance it with a single 64-bit add
+          const uint32_t a_hi = sm_addr + stage * Cfg::STAGE_BYTES;
+          const uint64_t da_hi0 = make_smem_desc(a_hi, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
+          const uint64_t da_lo0 = da_hi0 + (Cfg::A_BYTES >> 4);
+          const uint64_t db_hi0 = da_hi0 + ((Cfg::NPL * Cfg::A_BYTES) >> 4);
+          const uint64_t db_lo0 = db_hi0 + (Cfg::B_BYTES >> 4);
+          for (int t = 0; t < g.T; ++t) {
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ++ks) {
+              const uint64_t aoff = static_cast<uint64_t>((t * 128 * Cfg::ROWB + ks * 32) >> 4);
+              const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
+              const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+              const uint32_t d_addr = d_base + t * Cfg::NB;
+              mma_f16_ss(d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
+              if (NSPLIT == 3) {
+                mma_f16_ss(d_addr, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
+                mma_f16_ss(d_addr, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
+              }
+            }
+          }
+          mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == kTcStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        mma_commit(tfull_bar(buf));  // accumulators of this item complete
+      }
+    }
+  } else {
+    conv5_tc_epilogue<CT, TMAX, KC, NSPLIT>(p, epi, tmem, tfull_bar(0), tempty_bar(0));
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -411,10 +590,11 @@ struct TcKernelPlan {   // one launch of conv5_tc_kernel
   uint16_t* wp_hi = nullptr;   // packed weights
   uint16_t* wp_lo = nullptr;
   size_t wp_elems = 0;
+  size_t smem = 0;             // dynamic shared memory of the launch
 };
 
 // geometry for a [N][D][H][W] activation, kernel-side channel counts (C1+C2 in, Co1+Co2 out)
-inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C1, int C2, int Co1, int Co2) {
+inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C1, int C2, int Co1, int Co2, bool split3) {
   auto mult = [](int v, int m) { return v % m == 0; };
   if (mult(C1, 32) && mult(C2, 32) && mult(Co1, 32) && mult(Co2, 32) && Co1 > 0) {
     pl.CT = 32;
@@ -449,6 +629,29 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
     g.n_slices = (Co1 + Co2) / pl.CT;
     g.n_kc = (C1 + C2) / pl.KC;
     g.n_items = N * g.n_db * g.n_hb * g.n_slices;
+    // shared-memory plan: resident-lines pipeline when the box is a single d-plane and the rings fit
+    const int npl = split3 ? 2 : 1;
+    const int rowb = pl.KC * 2;
+    const int b_bytes = ((5 * pl.CT * rowb + 1023) / 1024) * 1024;
+    const int tmax_rows = tmax * 128;
+    g.resident = 0;
+    g.a_stage_bytes = 0;
+    g.n_a = g.n_b = 0;
+    pl.smem = static_cast<size_t>(kTcStages) * npl * (tmax_rows * rowb + b_bytes) + kTcEpiBytes + 256 + 1024;
+    if (bd == 1 && !getenv("VNB_TC_NO_RESIDENT")) {
+      const int a_stage = (((T * 128 + 4 * W) * rowb + 1023) / 1024) * 1024;
+      for (int nb = 4; nb >= 2; --nb) {
+        const size_t need = 2ull * npl * a_stage + static_cast<size_t>(nb) * npl * b_bytes + kTcEpiBytes + 256 + 1024;
+        if (need <= 227 * 1024) {
+          g.resident = 1;
+          g.a_stage_bytes = a_stage;
+          g.n_a = 2;
+          g.n_b = nb;
+          pl.smem = need;
+          break;
+        }
+      }
+    }
     return true;
   }
   return false;
@@ -461,13 +664,14 @@ inline void tc_launch_inst(const TcKernelPlan& pl, const TcArgs& a, int sms, cud
 #ifndef VNB_EMULATE
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       throw std::runtime_error("CUDA: cannot reserve shared memory for conv5_tc_kernel");
     attr = true;
   }
 #endif
+  static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "streaming pipeline exceeds shared memory");
   const int grid = std::max(1, std::min(a.g.n_items, sms));
-  VNB_LAUNCH(kfn, grid, kTcThreads, Cfg::SMEM_BYTES, stream, pl.a1_hi, pl.a1_lo, pl.a2_hi, pl.a2_lo, pl.w_hi, pl.w_lo, a);
+  VNB_LAUNCH(kfn, grid, kTcThreads, pl.smem, stream, pl.a1_hi, pl.a1_lo, pl.a2_hi, pl.a2_lo, pl.w_hi, pl.w_lo, a);
 }
 
 inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int sms, cudaStream_t stream) {

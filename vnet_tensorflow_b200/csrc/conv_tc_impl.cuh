@@ -20,11 +20,12 @@ inline int tc_query_sms() {
 inline void tc_encode_plan(TcKernelPlan& pl, int Nmax, const uint16_t* a1_hi, const uint16_t* a1_lo, const uint16_t* a2_hi,
                            const uint16_t* a2_lo) {
   const TcGeom& g = pl.g;
-  tma_encode_act(&pl.a1_hi, a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, g.bh, g.bd);
-  tma_encode_act(&pl.a1_lo, a1_lo ? a1_lo : a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, g.bh, g.bd);
+  const int lines = g.resident ? g.bh + 4 : g.bh;   // resident mode: the box carries the 2+2 halo lines
+  tma_encode_act(&pl.a1_hi, a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, lines, g.bd);
+  tma_encode_act(&pl.a1_lo, a1_lo ? a1_lo : a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, lines, g.bd);
   if (g.C2 > 0) {
-    tma_encode_act(&pl.a2_hi, a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, g.bh, g.bd);
-    tma_encode_act(&pl.a2_lo, a2_lo ? a2_lo : a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, g.bh, g.bd);
+    tma_encode_act(&pl.a2_hi, a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, lines, g.bd);
+    tma_encode_act(&pl.a2_lo, a2_lo ? a2_lo : a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, lines, g.bd);
   } else {
     pl.a2_hi = pl.a1_hi;
     pl.a2_lo = pl.a1_lo;
@@ -45,7 +46,7 @@ inline void Engine::tc_setup() {
     const Act& o = acts_[u.out];
     const Dims d = o.dims;
     TcKernelPlan& f = u.tc.fprop;
-    if (tc_plan_geometry(f, NB, d.D, d.H, d.W, u.Cin1, u.Cin2, u.Cout, 0)) {
+    if (tc_plan_geometry(f, NB, d.D, d.H, d.W, u.Cin1, u.Cin2, u.Cout, 0, lo)) {
       f.wp_elems = u.w_count;
       f.wp_hi = dev_alloc<uint16_t>(f.wp_elems);
       f.wp_lo = lo ? dev_alloc<uint16_t>(f.wp_elems) : nullptr;
@@ -53,7 +54,7 @@ inline void Engine::tc_setup() {
       f.valid = true;
     }
     TcKernelPlan& g = u.tc.dgrad;
-    if (u.need_dgrad && tc_plan_geometry(g, NB, d.D, d.H, d.W, u.Cout, 0, u.Cin1, u.Cin2)) {
+    if (u.need_dgrad && tc_plan_geometry(g, NB, d.D, d.H, d.W, u.Cout, 0, u.Cin1, u.Cin2, lo)) {
       g.wp_elems = u.w_count;
       g.wp_hi = dev_alloc<uint16_t>(g.wp_elems);
       g.wp_lo = lo ? dev_alloc<uint16_t>(g.wp_elems) : nullptr;
@@ -146,7 +147,7 @@ inline void tc_op_conv5(int precision, const float* x, const float* w, const flo
   const bool lo = precision == PREC_BF16X3;
   const int ci = dgrad_form ? cout : cin, co = dgrad_form ? cin : cout;
   TcKernelPlan pl;
-  if (!tc_plan_geometry(pl, n, dims.D, dims.H, dims.W, ci, 0, co, 0))
+  if (!tc_plan_geometry(pl, n, dims.D, dims.H, dims.W, ci, 0, co, 0, lo))
     throw std::invalid_argument("shape not supported by the tensor-core convolution (channels % 16, W | 128)");
   TcScratch s;
   const size_t nx = static_cast<size_t>(n) * dims.D * dims.H * dims.W * ci;

@@ -135,28 +135,29 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
         mbar_wait(xfull(xs), xph);
         tc_fence_after_sync();
         const uint32_t xa_hi = x_ring + (xs * NPL) * g.xt_bytes;
-        const uint32_t xa_lo = xa_hi + g.xt_bytes;
         for (int kd = 0; kd < 5; ++kd) {
           mbar_wait(zfull(zs), zph);
           tc_fence_after_sync();
           const uint32_t za_hi = z_ring + (zs * NPL) * g.zt_bytes;
-          const uint32_t za_lo = za_hi + g.zt_bytes;
           const uint32_t d_addr = tmem + kd * 80;
+          // only the start-address field changes between MMAs: one base descriptor per operand, 64-bit adds after
+          const uint64_t da0 = make_smem_desc(xa_hi, 32, sbo_a, SWZ_32B);
+          const uint64_t da0_lo = da0 + (static_cast<uint32_t>(g.xt_bytes) >> 4);
+          const uint64_t db0 = make_smem_desc(za_hi, z_pitch, sbo_b, SWZ_32B);
+          const uint64_t db0_lo = db0 + (static_cast<uint32_t>(g.zt_bytes) >> 4);
+          uint32_t acc = first ? 0u : 1u;
           for (int t = 0; t < g.HT; t += lpm) {
+            uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t) * x_pitch) >> 4);
+            uint64_t boff = static_cast<uint64_t>((static_cast<uint32_t>(t) * z_pitch) >> 4);
             for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t koff = lpm == 2 ? 0u : static_cast<uint32_t>(ks) * 16u * 32u;
-              const uint32_t aoff = static_cast<uint32_t>(t) * x_pitch + koff;
-              const uint32_t boff = static_cast<uint32_t>(t) * z_pitch + koff;
-              const uint64_t da = make_smem_desc(xa_hi + aoff, 32, sbo_a, SWZ_32B);
-              const uint64_t db = make_smem_desc(za_hi + boff, z_pitch, sbo_b, SWZ_32B);
-              const uint32_t acc = (first && t == 0 && ks == 0) ? 0u : 1u;
-              mma_f16_ss(d_addr, da, db, idesc, acc);
+              mma_f16_ss(d_addr, da0 + aoff, db0 + boff, idesc, acc);
               if (NSPLIT == 3) {
-                const uint64_t da_lo = make_smem_desc(xa_lo + aoff, 32, sbo_a, SWZ_32B);
-                const uint64_t db_lo = make_smem_desc(za_lo + boff, z_pitch, sbo_b, SWZ_32B);
-                mma_f16_ss(d_addr, da_lo, db, idesc, 1u);
-                mma_f16_ss(d_addr, da, db_lo, idesc, 1u);
+                mma_f16_ss(d_addr, da0_lo + aoff, db0 + boff, idesc, 1u);
+                mma_f16_ss(d_addr, da0 + aoff, db0_lo + boff, idesc, 1u);
               }
+              acc = 1u;
+              aoff += 32;  // next 16 voxels: 16 rows x 32 B = 512 B (only taken when lpm == 1)
+              boff += 32;
             }
           }
           mma_commit(zempty(zs));
