@@ -59,7 +59,7 @@ enum { VNB_LOSS_XENT = 0, VNB_LOSS_WEIGHTED_XENT, VNB_LOSS_SORENSEN, VNB_LOSS_WE
        VNB_LOSS_MIXED_WEIGHTED_SORENSEN, VNB_LOSS_MIXED_JACCARD, VNB_LOSS_MIXED_WEIGHTED_JACCARD };
 
 /* TrainingSetting.Optimizer.Name (model.py:649-658) */
-enum { VNB_OPT_ADAM = 0, VNB_OPT_SGD = 1 };
+enum { VNB_OPT_ADAM = 0, VNB_OPT_SGD = 1, VNB_OPT_MOMENTUM = 2, VNB_OPT_NESTEROV = 3 };
 
 /* which per-variable buffer vnb_set_slot / vnb_get_slot address */
 enum { VNB_SLOT_VALUE = 0, VNB_SLOT_GRAD = 1, VNB_SLOT_ADAM_M = 2, VNB_SLOT_ADAM_V = 3 };
@@ -81,6 +81,7 @@ typedef struct vnb_config {
   float learning_rate;          /* Optimizer.InitialLearningRate       model.py:218 */
   float decay_factor;           /* Optimizer.Decay.Factor              model.py:219 */
   float decay_steps;            /* Optimizer.Decay.Steps               model.py:220 */
+  float momentum;               /* Optimizer.Momentum (Momentum / NesterovMomentum) model.py:653-656 */
 } vnb_config;
 
 const char* vnb_last_error(void);

@@ -482,7 +482,7 @@ class TrainState:
 
 def train_step(state: TrainState, images, labels, spec: VNetSpec, loss_name="weighted_sorensen",
                weights=(), alpha=1.0, lr0=1e-2, decay_steps=100, decay_factor=0.99,
-               optimizer="Adam", dtype=torch.float32):
+               optimizer="Adam", dtype=torch.float32, momentum=0.9):
     """sess.run(train_op) of model.py:743-748 with dropout 0: fwd + bwd + optimiser + BN UPDATE_OPS."""
     loss, logits, grads, updates = loss_and_grads(state.params, images, labels, spec, loss_name,
                                                   weights, alpha, 0.0, None, dtype)
@@ -498,6 +498,11 @@ def train_step(state: TrainState, images, labels, spec: VNetSpec, loss_name="wei
             state.v[k] = v.to(torch.float32).numpy()
         elif optimizer == "SGD":
             p = p - lr * g
+        elif optimizer in ("Momentum", "NesterovMomentum"):  # tf.train.MomentumOptimizer (model.py:653-656)
+            a = torch.from_numpy(state.m.get(k, np.zeros_like(state.params[k]))).to(dtype)
+            a = momentum * a + g
+            p = p - (lr * (g + momentum * a) if optimizer == "NesterovMomentum" else lr * a)
+            state.m[k] = a.to(torch.float32).numpy()
         else:
             raise SystemExit("Invalid optimizer")
         state.params[k] = p.to(torch.float32).numpy()

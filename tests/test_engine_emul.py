@@ -72,7 +72,7 @@ def test_inference_does_not_touch_moving_statistics(emul_lib):
     eng.close()
 
 
-@pytest.mark.parametrize("optimizer", ["Adam", "SGD"])
+@pytest.mark.parametrize("optimizer", ["Adam", "SGD", "Momentum", "NesterovMomentum"])
 def test_training_trajectory_matches_oracle(emul_lib, optimizer):
     """Three optimiser steps (model.py:641-666): lr decay, TF-form Adam, moving stats, global_step."""
     spec, P, N = SPEC_A, 8, 2

@@ -17,7 +17,7 @@ LOSSES = {
     "weighted_jaccard": 5, "mixed_sorensen": 6, "mixed_weighted_sorensen": 7, "mixed_jaccard": 8,
     "mixed_weighted_jaccard": 9,
 }
-OPTIMIZERS = {"Adam": 0, "SGD": 1}
+OPTIMIZERS = {"Adam": 0, "SGD": 1, "Momentum": 2, "NesterovMomentum": 3}
 SLOT_VALUE, SLOT_GRAD, SLOT_ADAM_M, SLOT_ADAM_V = 0, 1, 2, 3
 
 
@@ -28,7 +28,7 @@ class VnbConfig(C.Structure):
         ("patch_shape", C.c_int32 * 3), ("max_batch", C.c_int32), ("precision", C.c_int32),
         ("loss", C.c_int32), ("loss_weights", C.c_float * 8), ("loss_alpha", C.c_float),
         ("optimizer", C.c_int32), ("learning_rate", C.c_float), ("decay_factor", C.c_float),
-        ("decay_steps", C.c_float),
+        ("decay_steps", C.c_float), ("momentum", C.c_float),
     ]
 
 

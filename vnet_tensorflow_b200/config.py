@@ -53,6 +53,7 @@ class Config:
     initial_learning_rate: float = 1e-2
     decay_factor: float = 0.99
     decay_steps: float = 100
+    momentum: float = 0.9
     spacing: Sequence[float] = (1.0, 1.0, 1.0)
     drop_ratio: float = 0.01
     min_pixel: int = 30
@@ -115,6 +116,7 @@ def from_dict(cfg: dict) -> Config:
     dec = opt.get("Decay", {})
     c.decay_factor = float(_get(dec, "Factor", default=0.99))
     c.decay_steps = float(_get(dec, "Steps", default=100))
+    c.momentum = float(_get(opt, "Momentum", default=0.9))  # the reference reads self.momentum, never set (R6)
     c.spacing = tuple(_get(t, "Spacing", default=c.spacing))
     c.drop_ratio = float(_get(t, "DropRatio", default=0.01))
     c.min_pixel = int(_get(t, "MinPixel", default=30))

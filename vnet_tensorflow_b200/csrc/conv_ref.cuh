@@ -346,16 +346,28 @@ __global__ void conv1_dgrad_kernel(const float* __restrict__ dz, const float* __
     dx[i] = accumulate ? dx[i] + s : s;
   }
 }
-// dw[c][k] += sum_v x[v][c] * dz[v][k]; thread = (c,k) pair, block-strided over voxel chunks
-__global__ void conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ dw,
-                                   long long V, int Cin, int K, int voxels_per_block) {
-  const int t = threadIdx.x;
-  if (t >= Cin * K) return;
-  const int c = t / K, k = t % K;
+// dw[c][k] += sum_v x[v][c] * dz[v][k].  256 threads = (Cin*K pairs) x (256 / pairs voxel lanes);
+// lanes stride over the block's voxel chunk, partial sums are combined through shared memory.
+__global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                          float* __restrict__ dw, long long V, int Cin, int K,
+                                                          int voxels_per_block) {
+  __shared__ float red[256];
+  const int pairs = Cin * K;
+  const int lanes = 256 / pairs;  // pairs <= 256 (checked by the engine)
+  const int t = threadIdx.x, pr = t % pairs, ln = t / pairs;
+  const int c = pr / K, k = pr % K;
   const long long v0 = static_cast<long long>(blockIdx.x) * voxels_per_block;
-  double s = 0.0;
-  for (long long v = v0; v < v0 + voxels_per_block && v < V; ++v) s += static_cast<double>(x[v * Cin + c]) * dz[v * K + k];
-  atomicAdd(dw + t, static_cast<float>(s));
+  const long long v1 = v0 + voxels_per_block < V ? v0 + voxels_per_block : V;
+  float s = 0.f;
+  if (ln < lanes)
+    for (long long v = v0 + ln; v < v1; v += lanes) s += x[v * Cin + c] * dz[v * K + k];
+  red[t] = ln < lanes ? s : 0.f;
+  __syncthreads();
+  if (t < pairs) {
+    float tot = 0.f;
+    for (int l = 0; l < lanes; ++l) tot += red[l * pairs + t];
+    atomicAdd(dw + t, tot);
+  }
 }
 
 }  // namespace vnb

@@ -30,7 +30,7 @@ namespace vnb {
 using sm100::TmaDesc;
 
 constexpr int kTcStages = 4;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 192;             // 2 control warps + 4 epilogue warps (one epilogue group)
 constexpr int kTcEpiRowPad = 20;  // floats per staged row (16 + 4: conflict-free float4 rows)
 constexpr int kTcEpiBytes = 5 * 128 * kTcEpiRowPad * 4;
 
@@ -43,7 +43,12 @@ struct TcCfg {
   static constexpr int B_BYTES = ((NB * ROWB + 1023) / 1024) * 1024;
   static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
   static constexpr int BUF_COLS = TMAX * NB;                // TMEM columns per accumulator buffer
-  static constexpr int SMEM_BYTES = kTcStages * STAGE_BYTES + kTcEpiBytes + 256 + 1024;
+  // single-pass bf16 is epilogue-bound on the Cout = 16 layers: it gets one epilogue group (4 warps, own
+  // staging buffer) per TMEM accumulator buffer; the 3-pass mode is MMA-bound and keeps one group
+  static constexpr int EG = NSPLIT == 3 ? 1 : 2;
+  static constexpr int THREADS = 64 + 128 * EG;
+  static constexpr int EPI_BYTES = EG * kTcEpiBytes;
+  static constexpr int SMEM_BYTES = kTcStages * STAGE_BYTES + EPI_BYTES + 256 + 1024;
   static constexpr uint32_t LAYOUT = ROWB == 32 ? sm100::SWZ_32B : ROWB == 64 ? sm100::SWZ_64B : sm100::SWZ_128B;
   static_assert(2 * BUF_COLS <= 512, "TMEM overflow");
   static_assert(NB % 16 == 0 && NB <= 256, "invalid UMMA N");
@@ -77,11 +82,14 @@ struct TcArgs {
 // epilogue shared by both pipeline modes: TMEM -> registers -> shift-sum over the 5 kw slices -> bias /
 // residual -> fp32 store.  Runs on warps 2..5 (128 threads = 128 TMEM lanes).
 template <int CT, int TMAX, int KC, int NSPLIT>
-__device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi, uint32_t tmem, uint32_t tfull0, uint32_t tempty0) {
+__device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_base, uint32_t tmem, uint32_t tfull0, uint32_t tempty0) {
   using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
   using namespace sm100;
   const TcGeom& g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int eg = (warp - 2) >> 2;                       // epilogue group of this warp
+  float* epi = epi_base + eg * (kTcEpiBytes / 4);
+  const int bar_id = 1 + eg;
   auto tfull_bar = [&](int b) { return tfull0 + 8u * b; };
   auto tempty_bar = [&](int b) { return tempty0 + 8u * b; };
   {
@@ -90,6 +98,7 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi, u
     const int Ctot = g.Co1 + g.Co2;
     int j = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
+      if (Cfg::EG == 2 && (j & 1) != eg) continue;      // with two groups, group == accumulator buffer
       const int slice = item % g.n_slices;
       int x = item / g.n_slices;
       const int hb = x % g.n_hb;
@@ -110,23 +119,28 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi, u
         const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::BUF_COLS + t * Cfg::NB;
 #pragma unroll 1
         for (int cc = 0; cc < CT / 16; ++cc) {
-#pragma unroll
-          for (int kw = 0; kw < 5; ++kw) {
-            uint32_t v[16];
-            tmem_ld16(t_addr + kw * CT + cc * 16, v);
-            tmem_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(epi + (kw * 128 + r) * kTcEpiRowPad);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                   __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-          }
-          named_bar_sync(1, 128);
           float acc[16];
+          {  // all five kw slices in flight, one wait; the centre slice (kw = 2) never leaves registers
+            uint32_t v[5][16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            for (int kw = 0; kw < 5; ++kw) tmem_ld16(t_addr + kw * CT + cc * 16, v[kw]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int kw = 0; kw < 5; ++kw) {
+              if (kw == 2) continue;
+              float4* dst = reinterpret_cast<float4*>(epi + (kw * 128 + r) * kTcEpiRowPad);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                dst[i] = make_float4(__uint_as_float(v[kw][4 * i]), __uint_as_float(v[kw][4 * i + 1]),
+                                     __uint_as_float(v[kw][4 * i + 2]), __uint_as_float(v[kw][4 * i + 3]));
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[2][i]);
+          }
+          named_bar_sync(bar_id, 128);
 #pragma unroll
           for (int kw = 0; kw < 5; ++kw) {
+            if (kw == 2) continue;
             const int ws = w + kw - 2;
             if (ws >= 0 && ws < g.W) {
               const float4* src = reinterpret_cast<const float4*>(epi + (kw * 128 + r + kw - 2) * kTcEpiRowPad);
@@ -140,7 +154,7 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi, u
               }
             }
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(bar_id, 128);
           if (valid) {
             const int co = slice * CT + cc * 16;  // first of 16 output channels handled here
             if (p.bias) {
@@ -204,14 +218,14 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
   const uint32_t b_ring = a_ring + static_cast<uint32_t>(g.n_a) * Cfg::NPL * g.a_stage_bytes;
   const uint32_t epi_off = static_cast<uint32_t>(g.n_a) * Cfg::NPL * g.a_stage_bytes + static_cast<uint32_t>(g.n_b) * Cfg::NPL * Cfg::B_BYTES;
   float* epi = reinterpret_cast<float*>(sm + epi_off);
-  const uint32_t bar_base = sm_addr + epi_off + kTcEpiBytes;
+  const uint32_t bar_base = sm_addr + epi_off + Cfg::EPI_BYTES;
   auto afull = [&](int s) { return bar_base + 8u * s; };          // [4]
   auto aempty = [&](int s) { return bar_base + 8u * (4 + s); };   // [4]
   auto bfull = [&](int s) { return bar_base + 8u * (8 + s); };    // [4]
   auto bempty = [&](int s) { return bar_base + 8u * (12 + s); };  // [4]
   const uint32_t tfull0 = bar_base + 8u * 16, tempty0 = bar_base + 8u * 18;
   const uint32_t slot_addr = bar_base + 8u * 20;
-  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + epi_off + kTcEpiBytes + 8 * 20);
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + epi_off + Cfg::EPI_BYTES + 8 * 20);
   const int kc1 = g.C1 / KC;
   const int n_it = 25 * g.n_kc;
 
@@ -344,7 +358,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
 }
 
 template <int CT, int TMAX, int KC, int NSPLIT>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(64 + 128 * (NSPLIT == 3 ? 1 : 2), 1)
 conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ TmaDesc a1_lo,
                 const __grid_constant__ TmaDesc a2_hi, const __grid_constant__ TmaDesc a2_lo,
                 const __grid_constant__ TmaDesc w_hi, const __grid_constant__ TmaDesc w_lo, const TcArgs p) {
@@ -355,14 +369,14 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
   uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const uint32_t sm_addr = smem_u32(sm);
   float* epi = reinterpret_cast<float*>(sm + kTcStages * Cfg::STAGE_BYTES);
-  const uint32_t bar_base = sm_addr + kTcStages * Cfg::STAGE_BYTES + kTcEpiBytes;
+  const uint32_t bar_base = sm_addr + kTcStages * Cfg::STAGE_BYTES + Cfg::EPI_BYTES;
   // barriers: full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4); then TMEM slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + 2 + b); };
   const uint32_t slot_addr = bar_base + 8u * (2 * kTcStages + 4);
-  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTcStages * Cfg::STAGE_BYTES + kTcEpiBytes + 8 * (2 * kTcStages + 4));
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTcStages * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + 8 * (2 * kTcStages + 4));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const TcGeom& g = p.g;
@@ -488,34 +502,39 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
 // fprop : col = output channel, k = input channel, taps as stored
 // dgrad : col = input channel (the conv's "output"), k = output channel, taps flipped (124 - tap)
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_w5_kernel(const float* __restrict__ w, int Cin, int Cout, int dgrad, int CT, int KC,
-                               uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
-  const int Kin = dgrad ? Cout : Cin;    // GEMM K channels
-  const int Nout = dgrad ? Cin : Cout;   // GEMM N channels
-  const int n_kc = Kin / KC, n_it = 25 * n_kc, NB = 5 * CT;
-  const long long total = static_cast<long long>(Nout / CT) * n_it * NB * KC;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(i % KC);
-    long long x = i / KC;
-    const int nrow = static_cast<int>(x % NB);
-    x /= NB;
-    const int it = static_cast<int>(x % n_it);
-    const int slice = static_cast<int>(x / n_it);
-    const int kw = nrow / CT, col = slice * CT + nrow % CT;
-    const int kc = it % n_kc, kh = (it / n_kc) % 5, kd = it / (5 * n_kc);
-    const int kch = kc * KC + k;
-    float v;
-    if (!dgrad) {
+// One block per (slice, it): the [5*CT][KC] tile is gathered through shared memory so that both the fp32
+// reads (runs of CT or KC contiguous floats) and the bf16 writes (whole tile contiguous) are coalesced.
+__global__ void __launch_bounds__(256) pack_w5_kernel(const float* __restrict__ w, int Cin, int Cout, int dgrad, int CT, int KC,
+                                                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  __shared__ float tile[160 * 33];         // [nrow][k] with a padded pitch of KC + 1
+  const int Kin = dgrad ? Cout : Cin;      // GEMM K channels
+  const int n_kc = Kin / KC, n_it = 25 * n_kc, NB = 5 * CT, pitch = KC + 1;
+  const int it = blockIdx.x % n_it, slice = blockIdx.x / n_it;
+  const int kc = it % n_kc, kh = (it / n_kc) % 5, kd = it / (5 * n_kc);
+  const int elems = NB * KC;
+  for (int e = threadIdx.x; e < elems; e += blockDim.x) {
+    int nrow, k;
+    if (!dgrad) {  // source rows: fixed (tap, kch), CT contiguous output channels
+      const int cl = e % CT, k_ = (e / CT) % KC, kw = e / (CT * KC);
+      nrow = kw * CT + cl;
+      k = k_;
       const int tap = (kd * 5 + kh) * 5 + kw;
-      v = w[(static_cast<long long>(tap) * Cin + kch) * Cout + col];
-    } else {
+      tile[nrow * pitch + k] = w[(static_cast<long long>(tap) * Cin + kc * KC + k) * Cout + slice * CT + cl];
+    } else {       // source rows: fixed (tap, input channel), KC contiguous output channels
+      k = e % KC;
+      nrow = e / KC;
+      const int kw = nrow / CT, col = slice * CT + nrow % CT;
       const int tap = 124 - ((kd * 5 + kh) * 5 + kw);
-      v = w[(static_cast<long long>(tap) * Cin + col) * Cout + kch];
+      tile[nrow * pitch + k] = w[(static_cast<long long>(tap) * Cin + col) * Cout + kc * KC + k];
     }
+  }
+  __syncthreads();
+  const long long base = static_cast<long long>(blockIdx.x) * elems;
+  for (int e = threadIdx.x; e < elems; e += blockDim.x) {
+    const float v = tile[(e / KC) * pitch + e % KC];
     const uint16_t h = f32_to_bf16(v);
-    hi[i] = h;
-    if (lo) lo[i] = f32_to_bf16(v - bf16_to_f32(h));
+    hi[base + e] = h;
+    if (lo) lo[base + e] = f32_to_bf16(v - bf16_to_f32(h));
   }
 }
 
@@ -637,11 +656,12 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
     g.resident = 0;
     g.a_stage_bytes = 0;
     g.n_a = g.n_b = 0;
-    pl.smem = static_cast<size_t>(kTcStages) * npl * (tmax_rows * rowb + b_bytes) + kTcEpiBytes + 256 + 1024;
+    const size_t epi_bytes = static_cast<size_t>(split3 ? 1 : 2) * kTcEpiBytes;
+    pl.smem = static_cast<size_t>(kTcStages) * npl * (tmax_rows * rowb + b_bytes) + epi_bytes + 256 + 1024;
     if (bd == 1 && !getenv("VNB_TC_NO_RESIDENT")) {
       const int a_stage = (((T * 128 + 4 * W) * rowb + 1023) / 1024) * 1024;
       for (int nb = 4; nb >= 2; --nb) {
-        const size_t need = 2ull * npl * a_stage + static_cast<size_t>(nb) * npl * b_bytes + kTcEpiBytes + 256 + 1024;
+        const size_t need = 2ull * npl * a_stage + static_cast<size_t>(nb) * npl * b_bytes + epi_bytes + 256 + 1024;
         if (need <= 227 * 1024) {
           g.resident = 1;
           g.a_stage_bytes = a_stage;
@@ -671,7 +691,7 @@ inline void tc_launch_inst(const TcKernelPlan& pl, const TcArgs& a, int sms, cud
 #endif
   static_assert(Cfg::SMEM_BYTES <= 227 * 1024, "streaming pipeline exceeds shared memory");
   const int grid = std::max(1, std::min(a.g.n_items, sms));
-  VNB_LAUNCH(kfn, grid, kTcThreads, pl.smem, stream, pl.a1_hi, pl.a1_lo, pl.a2_hi, pl.a2_lo, pl.w_hi, pl.w_lo, a);
+  VNB_LAUNCH(kfn, grid, Cfg::THREADS, pl.smem, stream, pl.a1_hi, pl.a1_lo, pl.a2_hi, pl.a2_lo, pl.w_hi, pl.w_lo, a);
 }
 
 inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int sms, cudaStream_t stream) {

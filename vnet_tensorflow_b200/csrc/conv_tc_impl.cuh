@@ -80,7 +80,7 @@ inline void Engine::tc_prepare_weights() {
     for (int pass = 0; pass < 2; ++pass) {
       TcKernelPlan& pl = pass == 0 ? u.tc.fprop : u.tc.dgrad;
       if (!pl.valid) continue;
-      VNB_LAUNCH(pack_w5_kernel, grid_for(static_cast<long long>(pl.wp_elems), 256), 256, 0, stream_,
+      VNB_LAUNCH(pack_w5_kernel, pl.g.n_slices * 25 * pl.g.n_kc, 256, 0, stream_,
                  (const float*)(params_ + u.w_off), Cin, u.Cout, pass, pl.CT, pl.KC, pl.wp_hi, pl.wp_lo);
       ++launches_;
     }
@@ -157,7 +157,7 @@ inline void tc_op_conv5(int precision, const float* x, const float* w, const flo
   pl.wp_elems = 125ull * cin * cout;
   pl.wp_hi = s.alloc<uint16_t>(pl.wp_elems);
   pl.wp_lo = lo ? s.alloc<uint16_t>(pl.wp_elems) : nullptr;
-  VNB_LAUNCH(pack_w5_kernel, 1024, 256, 0, 0, w, cin, cout, dgrad_form ? 1 : 0, pl.CT, pl.KC, pl.wp_hi, pl.wp_lo);
+  VNB_LAUNCH(pack_w5_kernel, pl.g.n_slices * 25 * pl.g.n_kc, 256, 0, 0, w, cin, cout, dgrad_form ? 1 : 0, pl.CT, pl.KC, pl.wp_hi, pl.wp_lo);
   tc_encode_plan(pl, n, xh, xl, nullptr, nullptr);
   TcArgs a;
   a.g = pl.g;

@@ -40,7 +40,7 @@ enum LossName : int {
   LOSS_WEIGHTED_JACCARD, LOSS_MIXED_SORENSEN, LOSS_MIXED_WEIGHTED_SORENSEN, LOSS_MIXED_JACCARD,
   LOSS_MIXED_WEIGHTED_JACCARD
 };
-enum OptName : int { OPT_ADAM = 0, OPT_SGD = 1 };
+enum OptName : int { OPT_ADAM = 0, OPT_SGD = 1, OPT_MOMENTUM = 2, OPT_NESTEROV = 3 };
 
 struct EngineConfig {
   int in_channels = 1, num_classes = 2, num_channels = 16, num_levels = 4;
@@ -54,6 +54,7 @@ struct EngineConfig {
   float loss_alpha = 1.0f;
   int optimizer = OPT_ADAM;
   float lr0 = 1e-2f, decay_factor = 0.99f, decay_steps = 100.f;
+  float momentum = 0.9f;
 };
 
 enum UnitKind : int { U_INPUT_TILE = 0, U_CONV5, U_DOWN, U_UP, U_CONV1 };
@@ -216,8 +217,11 @@ class Engine {
       const float lr_t = static_cast<float>(lr * std::sqrt(1.0 - std::pow(b2, (double)t)) / (1.0 - std::pow(b1, (double)t)));
       VNB_LAUNCH(adam_step_kernel, blocks, 256, 0, stream_, params_, (const float*)grads_, adam_m_, adam_v_,
                  (long long)n_train_, lr_t, 0.9f, 0.999f, 1e-8f, gscale);
-    } else {
+    } else if (cfg_.optimizer == OPT_SGD) {
       VNB_LAUNCH(sgd_step_kernel, blocks, 256, 0, stream_, params_, (const float*)grads_, (long long)n_train_, lr, gscale);
+    } else {  // Momentum / Nesterov: the accumulator lives in the first Adam slot buffer
+      VNB_LAUNCH(momentum_step_kernel, blocks, 256, 0, stream_, params_, (const float*)grads_, adam_m_, (long long)n_train_, lr,
+                 cfg_.momentum, cfg_.optimizer == OPT_NESTEROV ? 1 : 0, gscale);
     }
     global_step_ = t;
     weights_dirty_ = true;
@@ -935,10 +939,10 @@ class Engine {
                    x1.d, V, u.Cin1, u.Cout, u.in1_accumulate ? 1 : 0);
         ++launches_;
       }
-      const int vpb = 2048;
+      if (u.Cin1 * u.Cout > 256) throw std::runtime_error("output layer wider than 256 (Cin*K) is not supported");
+      const int vpb = 4096;
       const int blocks = static_cast<int>((V + vpb - 1) / vpb);
-      const int threads = ((u.Cin1 * u.Cout + 31) / 32) * 32;
-      VNB_LAUNCH(conv1_wgrad_kernel, blocks, threads, 0, stream_, (const float*)x1.a, dz, dw, V, u.Cin1, u.Cout, vpb);
+      VNB_LAUNCH(conv1_wgrad_kernel, blocks, 256, 0, stream_, (const float*)x1.a, dz, dw, V, u.Cin1, u.Cout, vpb);
       ++launches_;
     }
   }

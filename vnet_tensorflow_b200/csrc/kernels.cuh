@@ -537,6 +537,18 @@ __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__
     p[i] -= lr * g[i] * gscale;
 }
 
+// tf.train.MomentumOptimizer: accum = momentum*accum + g; p -= lr*accum   (use_nesterov: p -= lr*(g + momentum*accum))
+__global__ void momentum_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ accum, long long n,
+                                     float lr, float momentum, int nesterov, float gscale) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float a = momentum * accum[i] + gi;
+    accum[i] = a;
+    p[i] -= nesterov ? lr * (gi + momentum * a) : lr * a;
+  }
+}
+
 // fp32 -> bf16 hi/lo split of an arbitrary buffer (used for the network input and packed weights)
 __global__ void split_bf16_kernel(const float* __restrict__ x, long long n, uint16_t* __restrict__ hi,
                                   uint16_t* __restrict__ lo) {
@@ -575,6 +587,9 @@ __device__ __forceinline__ void store_hi_lo4(uint16_t* hi, uint16_t* lo, unsigne
 __global__ void __launch_bounds__(256) bn_apply_v4_kernel(ApplyArgs p) {
   const unsigned total4 = static_cast<unsigned>(p.total / 4), C4 = static_cast<unsigned>(p.C / 4);
   const float keep_scale = p.drop_rate > 0.f ? 1.0f / (1.0f - p.drop_rate) : 1.0f;
+  const float4* __restrict__ z4 = reinterpret_cast<const float4*>(p.z);
+  float4* __restrict__ a4 = reinterpret_cast<float4*>(p.a);
+#pragma unroll 4
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
     const unsigned c = (i % C4) * 4;
     float z[4];
@@ -582,7 +597,7 @@ __global__ void __launch_bounds__(256) bn_apply_v4_kernel(ApplyArgs p) {
       const float v = p.z[i / C4];
       z[0] = z[1] = z[2] = z[3] = v;
     } else {
-      const float4 f = reinterpret_cast<const float4*>(p.z)[i];
+      const float4 f = z4[i];
       z[0] = f.x; z[1] = f.y; z[2] = f.z; z[3] = f.w;
     }
     const float4 sc = *reinterpret_cast<const float4*>(p.scale + c);
@@ -600,7 +615,7 @@ __global__ void __launch_bounds__(256) bn_apply_v4_kernel(ApplyArgs p) {
       for (int k = 0; k < 4; ++k)
         y[k] = dropout_uniform(p.seed, p.unit, static_cast<uint64_t>(i) * 4 + k) >= p.drop_rate ? y[k] * keep_scale : 0.f;
     }
-    reinterpret_cast<float4*>(p.a)[i] = make_float4(y[0], y[1], y[2], y[3]);
+    a4[i] = make_float4(y[0], y[1], y[2], y[3]);
     if (p.a_hi) store_hi_lo4(p.a_hi, p.a_lo, i, y);
   }
 }
@@ -632,9 +647,11 @@ __device__ __forceinline__ void bwd_g4(const BwdArgs& p, unsigned i, unsigned c,
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_v4_kernel(BwdArgs p, long long total) {
   const unsigned total4 = static_cast<unsigned>(total / 4), C4 = static_cast<unsigned>(p.C / 4);
+  const float4* __restrict__ z4 = reinterpret_cast<const float4*>(p.z);
+#pragma unroll 2
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
     const unsigned c = (i % C4) * 4;
-    const float4 zf = reinterpret_cast<const float4*>(p.z)[i];
+    const float4 zf = z4[i];
     const float z[4] = {zf.x, zf.y, zf.z, zf.w};
     float g[4], yhat[4], dd[4];
     bwd_g4(p, i, c, z, g, yhat, dd);
@@ -689,6 +706,7 @@ __global__ void __launch_bounds__(256) bn_stats_v4_kernel(const float* __restric
   const unsigned C4 = static_cast<unsigned>(C / 4);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   // thread t keeps channel quad t % C4 because the stride gridDim*256 is a multiple of C4
+#pragma unroll 4
   for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total4; i += gridDim.x * 256u) {
     const float4 f = reinterpret_cast<const float4*>(z)[i];
     acc[0][0] += f.x; acc[0][1] += f.y; acc[0][2] += f.z; acc[0][3] += f.w;
@@ -703,6 +721,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v4_kernel(BwdArgs p, unsign
   const float mu[4] = {static_cast<float>(p.mean[c]), static_cast<float>(p.mean[c + 1]), static_cast<float>(p.mean[c + 2]),
                        static_cast<float>(p.mean[c + 3])};
   float acc[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll 2
   for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < total4; i += gridDim.x * 256u) {
     float z[4];
     if (p.tiled_input) {

@@ -101,9 +101,10 @@ int vnb_create(const vnb_config* c, int device, vnb_handle** out) {
     e.lr0 = c->learning_rate;
     e.decay_factor = c->decay_factor;
     e.decay_steps = c->decay_steps;
+    e.momentum = c->momentum;
     if (e.precision < 0 || e.precision > 2) throw std::invalid_argument("precision must be VNB_PREC_*");
     if (e.loss < 0 || e.loss > VNB_LOSS_MIXED_WEIGHTED_JACCARD) throw std::invalid_argument("loss must be VNB_LOSS_*");
-    if (e.optimizer < 0 || e.optimizer > VNB_OPT_SGD) throw std::invalid_argument("optimizer must be VNB_OPT_*");
+    if (e.optimizer < 0 || e.optimizer > VNB_OPT_NESTEROV) throw std::invalid_argument("optimizer must be VNB_OPT_*");
     for (int l = 0; l < e.num_levels && l < 8; ++l)
       if (e.num_convolutions[l] < 1) throw std::invalid_argument("NumConvolutions entries must be >= 1");
     if (e.bottom_convolutions < 1) throw std::invalid_argument("BottomConvolutions must be >= 1");

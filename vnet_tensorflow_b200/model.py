@@ -120,7 +120,7 @@ class image2label(object):
             num_levels=self.num_levels, num_convolutions=self.num_convolutions, bottom_convolutions=self.bottom_convolutions,
             precision=self.precision, loss=self.loss_name, loss_weights=self.loss_weights, loss_alpha=self.loss_alpha,
             optimizer=self.optimizer_name, learning_rate=self.initial_learning_rate, decay_factor=self.decay_factor,
-            decay_steps=self.decay_steps, device=self.device, library=self.library)
+            decay_steps=self.decay_steps, momentum=self.momentum, device=self.device, library=self.library)
         initialize(self.engine)  # tf.initializers.global_variables(), model.py:673
         print("{}: Build graph complete".format(_now()))
 
