@@ -82,6 +82,7 @@ typedef struct vnb_config {
   float decay_factor;           /* Optimizer.Decay.Factor              model.py:219 */
   float decay_steps;            /* Optimizer.Decay.Steps               model.py:220 */
   float momentum;               /* Optimizer.Momentum (Momentum / NesterovMomentum) model.py:653-656 */
+  int32_t graph_flavour;        /* 0 = networks.VNet (main.py path), 1 = VNet.py legacy flavour (train.py:271-279) */
 } vnb_config;
 
 const char* vnb_last_error(void);

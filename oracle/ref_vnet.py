@@ -18,6 +18,7 @@ Reference files restated (paths relative to /root/reference):
   layers2.py:78-94   down_convolution / up_convolution     -> used by VNet.forward
   layers2.py:97-99   prelu                                 -> prelu
   networks.py:209-365 VNet (GetNetwork, convolution_block, convolution_block_2) -> VNet.forward
+  VNet.py:26-155, Layers.py:88-131  legacy graph flavour used by train.py -> forward(spec.flavour='legacy')
   model.py:26-85     dice_coe                              -> dice_coe
   model.py:87-92     weighted softmax xent                 -> weighted_xent
   model.py:447,477,495-560,568  softmax / one_hot / loss zoo / argmax -> loss_from_logits, predict
@@ -51,6 +52,7 @@ class VNetSpec:
     num_levels: int = 4
     num_convolutions: Tuple[int, ...] = (1, 2, 3, 3)
     bottom_convolutions: int = 3
+    flavour: str = "networks"  # "networks" = networks.VNet (live path); "legacy" = VNet.py / Layers.py (train.py)
 
     def __post_init__(self):
         self.num_convolutions = tuple(self.num_convolutions)
@@ -90,12 +92,15 @@ def param_specs(spec: VNetSpec) -> List[Tuple[str, Tuple[int, ...], str]]:
         conv(s, (5, 5, 5, spec.in_channels, C0), C0)
         bn(s, 0, C0)
         alpha(s, C0)
+    legacy = spec.flavour == "legacy"
     for l in range(spec.num_levels):  # networks.py:270-280
         c = C0 * 2 ** l
         for i in range(spec.num_convolutions[l]):
             s = "vnet/encoder/level_%d/conv_%d" % (l + 1, i + 1)
             conv(s, (5, 5, 5, c, c), c)
             bn(s, 0, c)
+            if legacy:  # VNet.py:31-35: two batch norms per convolution
+                bn(s, 1, c)
             alpha(s, c)
         s = "vnet/encoder/level_%d/down_convolution" % (l + 1)
         conv(s, (2, 2, 2, c, 2 * c), 2 * c)
@@ -106,6 +111,8 @@ def param_specs(spec: VNetSpec) -> List[Tuple[str, Tuple[int, ...], str]]:
         s = "vnet/bottom_level/conv_%d" % (i + 1)
         conv(s, (5, 5, 5, c, c), c)
         bn(s, 0, c)
+        if legacy:
+            bn(s, 1, c)
         alpha(s, c)
     for l in reversed(range(spec.num_levels)):  # networks.py:285-296
         c = C0 * 2 ** l
@@ -117,7 +124,18 @@ def param_specs(spec: VNetSpec) -> List[Tuple[str, Tuple[int, ...], str]]:
         n = spec.num_convolutions[l]
         s = "vnet/decoder/level_%d/conv_1" % (l + 1)
         conv(s, (5, 5, 5, 2 * c, c), c)
-        if n == 1:  # networks.py:328-340: three BNs
+        if legacy:  # VNet.py:45-72
+            bn(s, 0, c)
+            if n == 1:
+                bn(s, 1, c)
+            alpha(s, c)
+            for i in range(1, n):
+                s = "vnet/decoder/level_%d/conv_%d" % (l + 1, i + 1)
+                conv(s, (5, 5, 5, c, c), c)
+                bn(s, 0, c)
+                bn(s, 1, c)
+                alpha(s, c)
+        elif n == 1:  # networks.py:328-340: three BNs
             bn(s, 0, c)
             bn(s, 1, c)
             bn(s, 2, c)
@@ -266,7 +284,47 @@ def forward(params: Dict[str, torch.Tensor], images: torch.Tensor, spec: VNetSpe
         x = cx.act(x, s)
     cx.tap(s, x)
 
+    def legacy_block(x, n, scope):  # VNet.py:26-40
+        layer_input = x
+        for i in range(n):
+            sc = "%s/conv_%d" % (scope, i + 1)
+            x = cx.conv(x, sc)
+            x = cx.bn(x, sc, 0)
+            if i == n - 1:
+                x = x + layer_input
+            x = cx.bn(x, sc, 1)
+            x = cx.act(x, sc)
+            x = _dropout(x, dropout_rate, masks, sc)
+            cx.tap(sc, x)
+        return x
+
+    def legacy_block_2(x, f, n, scope):  # VNet.py:43-73 (true residual to the up-convolution output)
+        layer_input = x
+        x = torch.cat((x, f), dim=-1)
+        sc = scope + "/conv_1"
+        x = cx.conv(x, sc)
+        x = cx.bn(x, sc, 0)
+        if n == 1:
+            x = x + layer_input
+            x = cx.bn(x, sc, 1)
+        x = cx.act(x, sc)
+        x = _dropout(x, dropout_rate, masks, sc)
+        cx.tap(sc, x)
+        for i in range(1, n):
+            sc = "%s/conv_%d" % (scope, i + 1)
+            x = cx.conv(x, sc)
+            x = cx.bn(x, sc, 0)
+            if i == n - 1:
+                x = x + layer_input
+            x = cx.bn(x, sc, 1)
+            x = cx.act(x, sc)
+            x = _dropout(x, dropout_rate, masks, sc)
+            cx.tap(sc, x)
+        return x
+
     def convolution_block(x, n, scope):  # networks.py:307-322
+        if spec.flavour == "legacy":
+            return legacy_block(x, n, scope)
         layer_input = x
         for i in range(n):
             sc = "%s/conv_%d" % (scope, i + 1)
@@ -280,6 +338,8 @@ def forward(params: Dict[str, torch.Tensor], images: torch.Tensor, spec: VNetSpe
         return x
 
     def convolution_block_2(x, f, n, scope):  # networks.py:324-365
+        if spec.flavour == "legacy":
+            return legacy_block_2(x, f, n, scope)
         x = torch.cat((x, f), dim=-1)
         sc = scope + "/conv_1"
         if n == 1:

@@ -23,7 +23,8 @@ def engine_for(spec, P, N, loss, weights, library, precision="fp32", **kw):
     return VNetEngine(num_classes=spec.num_classes, in_channels=spec.in_channels, patch_shape=(P, P, P), max_batch=N,
                       num_channels=spec.num_channels, num_levels=spec.num_levels,
                       num_convolutions=spec.num_convolutions, bottom_convolutions=spec.bottom_convolutions,
-                      precision=precision, loss=loss, loss_weights=weights, library=library, **kw)
+                      precision=precision, loss=loss, loss_weights=weights, library=library,
+                      flavour=getattr(spec, "flavour", "networks"), **kw)
 
 
 def rel_err(a, b):
@@ -38,6 +39,18 @@ def analytically_zero(name, spec):
     output is discarded or re-normalised (the dead BN, and betas of all but the last BN of a chain)."""
     if name.endswith("/biases"):
         return True
+    if getattr(spec, "flavour", "networks") == "legacy":
+        # VNet.py: in conv -> BN -> BN (non-last convs) the first BN's beta is re-normalised away
+        if not name.endswith("/batch_normalization/beta") or "/conv_" not in name:
+            return False
+        parts = name.split("/")
+        i = int(parts[-3].split("_")[1]) - 1
+        if parts[1] == "bottom_level":
+            return i < spec.bottom_convolutions - 1
+        n = spec.num_convolutions[int(parts[2].split("_")[1]) - 1]
+        if parts[1] == "encoder":
+            return i < n - 1
+        return 1 <= i < n - 1
     if "/decoder/" not in name or "batch_normalization" not in name:
         return False
     level = int(name.split("/decoder/level_")[1].split("/")[0]) - 1

@@ -168,3 +168,28 @@ def test_sixteen_channel_net_tight_gradients(emul_lib):
     assert rel_err(logits, lg.numpy()) < 2e-5
     _grad_check(eng, go, spec, 5e-4)
     eng.close()
+
+
+@pytest.mark.parametrize("convs,bottom,loss", [((1, 2, 2), 3, "jaccard"), ((2, 1), 1, "weighted_sorensen")])
+def test_legacy_vnet_py_flavour_matches_oracle(emul_lib, convs, bottom, loss):
+    """VNet.py graph (two BNs per conv, true residual added between them) as used by
+    train.py:271-279 (num_levels=3, (1,2,2), bottom 3, prelu)."""
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=4, num_levels=len(convs), num_convolutions=convs,
+                      bottom_convolutions=bottom, flavour="legacy")
+    P, N = (16 if len(convs) == 3 else 8), 2   # keep >= 2^3 voxels at the bottom level (batch-norm conditioning)
+    weights = (0.1, 1.0) if "weighted" in loss else ()
+    params = perturbed_params(spec)
+    img, lab = synth_batch(0, N, P, 1, 2)
+    eng = engine_for(spec, P, N, loss, weights, emul_lib)
+    assert list(eng.variables()) == [n for n, _, _ in R.param_specs(spec)]
+    eng.set_params(params)
+    lo, lg, go, upd = R.loss_and_grads(params, img, lab, spec, loss, weights)
+    logits, _, am = eng.forward(img)
+    assert rel_err(logits, lg.numpy()) < 2e-5
+    assert int((am != R.predict(lg).numpy()).sum()) == 0
+    l = eng.forward_backward(img, lab, update_moving_stats=True)
+    assert abs(l - float(lo)) < 2e-6
+    _grad_check(eng, go, spec, 3e-4)
+    for k, u in upd.items():
+        assert np.abs(eng.get_param(k) - u.numpy()).max() < 1e-4 * max(1.0, float(u.abs().max())), k
+    eng.close()

@@ -97,3 +97,25 @@ def test_wgrad5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     emul_lib.check(emul_lib.vnb_op_conv5_wgrad(0, prec, ptr(x), ptr(dy), ptr(dw), n, *dims, cin, cout))
     assert rel_err(dw, wt.grad.numpy()) < (1e-6 if prec == 2 else 3e-5)
+
+
+def test_multimodal_input_runs_on_tensor_cores_with_padded_channels(emul_lib):
+    """in_channels = 3 (not a multiple of 16): the input convolution and its filter gradient run on the
+    tensor-core kernels over zero-padded bf16 copies of the image (BASELINE config #3 shape)."""
+    spec = R.VNetSpec(num_classes=3, in_channels=3, num_channels=16, num_levels=1, num_convolutions=(1,), bottom_convolutions=1)
+    P, N = 16, 1
+    params = perturbed_params(spec)
+    img, lab = synth_batch(4, N, P, 3, 3)
+    eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 0.5, 1.0), emul_lib, precision="bf16x3")
+    eng.set_params(params)
+    l = eng.forward_backward(img, lab)
+    lo, lg, go, _ = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.1, 0.5, 1.0))
+    logits, _, am = eng.forward(img)
+    assert abs(l - float(lo)) < 5e-6
+    assert rel_err(logits, lg.numpy()) < 1e-4
+    k = "vnet/input_layer/weights"
+    g = eng.get_grads()[k]
+    ref = go[k].numpy()
+    assert g.shape == (5, 5, 5, 3, 16)
+    assert np.sqrt(((g - ref) ** 2).sum()) <= 2e-2 * np.sqrt((ref ** 2).sum())
+    eng.close()

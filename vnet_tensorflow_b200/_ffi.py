@@ -28,7 +28,7 @@ class VnbConfig(C.Structure):
         ("patch_shape", C.c_int32 * 3), ("max_batch", C.c_int32), ("precision", C.c_int32),
         ("loss", C.c_int32), ("loss_weights", C.c_float * 8), ("loss_alpha", C.c_float),
         ("optimizer", C.c_int32), ("learning_rate", C.c_float), ("decay_factor", C.c_float),
-        ("decay_steps", C.c_float), ("momentum", C.c_float),
+        ("decay_steps", C.c_float), ("momentum", C.c_float), ("graph_flavour", C.c_int32),
     ]
 
 

@@ -8,6 +8,7 @@
 //   CH_Q  "x + BN(x)"     li = BN0(z); y = BN1(z + li)                    networks.py:358-361 (last conv)
 //   CH_D  dead BN         li = BN0(z) (unused); y = BN1(z)                networks.py:358,361 (middle convs)
 //   CH_T  triple          u = BN0(z); li = BN1(u); y = BN2(u + li)        networks.py:334-337 (n == 1)
+//   CH_2  double          y = BN1(BN0(z))                                 VNet.py:31-35 (legacy flavour, non-last convs)
 //
 // All intermediate tensors are per-channel affine functions  s*(z - mu) + m  of z, so the whole chain
 // collapses to  y = A*(z - mu) + B  with A = A(sigma^2, gamma_k) and B = beta_last, and each BN's own
@@ -24,7 +25,7 @@
 
 namespace vnb {
 
-enum ChainType : int { CH_S = 0, CH_Q = 1, CH_D = 2, CH_T = 3 };
+enum ChainType : int { CH_S = 0, CH_Q = 1, CH_D = 2, CH_T = 3, CH_2 = 4 };
 
 VNB_HD int chain_num_bn(int type) { return type == CH_S ? 1 : (type == CH_T ? 3 : 2); }
 
@@ -105,6 +106,13 @@ VNB_HD ChainOut chain_eval(int type, double sigma2, const double gamma[3], const
     o.bn_var[1] = vt.v;
     o.mean_is_mu[1] = true;
     o.bn_mean[1] = beta[0];
+  } else if (type == CH_2) {
+    const Dual s0 = g0 * r0;                      // u = s0*(z-mu) + beta0
+    const Dual vu = s0 * s0 * s2;
+    o.A = g1 * s0 * dual_rsqrt_eps(vu, eps);
+    o.beta_idx = 1;
+    o.bn_mean[1] = beta[0];
+    o.bn_var[1] = vu.v;
   } else {  // CH_T
     const Dual s0 = g0 * r0;                      // u = s0*(z-mu) + beta0
     const Dual vu = s0 * s0 * s2;

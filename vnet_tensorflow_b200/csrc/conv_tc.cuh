@@ -505,9 +505,10 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
 // One block per (slice, it): the [5*CT][KC] tile is gathered through shared memory so that both the fp32
 // reads (runs of CT or KC contiguous floats) and the bf16 writes (whole tile contiguous) are coalesced.
 __global__ void __launch_bounds__(256) pack_w5_kernel(const float* __restrict__ w, int Cin, int Cout, int dgrad, int CT, int KC,
-                                                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+                                                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int Cin_gemm) {
+  // Cin_gemm >= Cin: input channels seen by the GEMM (zero rows beyond the real Cin; fprop only)
   __shared__ float tile[160 * 33];         // [nrow][k] with a padded pitch of KC + 1
-  const int Kin = dgrad ? Cout : Cin;      // GEMM K channels
+  const int Kin = dgrad ? Cout : Cin_gemm;  // GEMM K channels
   const int n_kc = Kin / KC, n_it = 25 * n_kc, NB = 5 * CT, pitch = KC + 1;
   const int it = blockIdx.x % n_it, slice = blockIdx.x / n_it;
   const int kc = it % n_kc, kh = (it / n_kc) % 5, kd = it / (5 * n_kc);
@@ -519,7 +520,8 @@ __global__ void __launch_bounds__(256) pack_w5_kernel(const float* __restrict__ 
       nrow = kw * CT + cl;
       k = k_;
       const int tap = (kd * 5 + kh) * 5 + kw;
-      tile[nrow * pitch + k] = w[(static_cast<long long>(tap) * Cin + kc * KC + k) * Cout + slice * CT + cl];
+      const int kch = kc * KC + k;
+      tile[nrow * pitch + k] = kch < Cin ? w[(static_cast<long long>(tap) * Cin + kch) * Cout + slice * CT + cl] : 0.f;
     } else {       // source rows: fixed (tap, input channel), KC contiguous output channels
       k = e % KC;
       nrow = e / KC;
@@ -535,6 +537,57 @@ __global__ void __launch_bounds__(256) pack_w5_kernel(const float* __restrict__ 
     const uint16_t h = f32_to_bf16(v);
     hi[base + e] = h;
     if (lo) lo[base + e] = f32_to_bf16(v - bf16_to_f32(h));
+  }
+}
+
+// all layers' packs in one launch: blockIdx.x is mapped to (job, tile) through a prefix table
+struct PackJob {
+  const float* w;
+  uint16_t* hi;
+  uint16_t* lo;
+  int Cin, Cout, dgrad, CT, KC, Cin_gemm;
+  int first_block;   // prefix sum of tiles
+};
+__device__ __forceinline__ void pack_w5_tile(const PackJob& j, int tile_idx, float* tile);
+
+__global__ void __launch_bounds__(256) pack_w5_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ float tile[160 * 33];
+  int lo = 0, hi = njobs - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {  // last job with first_block <= b
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].first_block <= b) lo = mid; else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  pack_w5_tile(j, b - j.first_block, tile);
+}
+
+__device__ __forceinline__ void pack_w5_tile(const PackJob& j, int tile_idx, float* tile) {
+  const int Kin = j.dgrad ? j.Cout : j.Cin_gemm;
+  const int KC = j.KC, CT = j.CT, Cin = j.Cin, Cout = j.Cout;
+  const int n_kc = Kin / KC, n_it = 25 * n_kc, NB = 5 * CT, pitch = KC + 1;
+  const int it = tile_idx % n_it, slice = tile_idx / n_it;
+  const int kc = it % n_kc, kh = (it / n_kc) % 5, kd = it / (5 * n_kc);
+  const int elems = NB * KC;
+  for (int e = threadIdx.x; e < elems; e += blockDim.x) {
+    if (!j.dgrad) {
+      const int cl = e % CT, k = (e / CT) % KC, kw = e / (CT * KC);
+      const int tap = (kd * 5 + kh) * 5 + kw, kch = kc * KC + k;
+      tile[(kw * CT + cl) * pitch + k] = kch < Cin ? j.w[(static_cast<long long>(tap) * Cin + kch) * Cout + slice * CT + cl] : 0.f;
+    } else {
+      const int k = e % KC, nrow = e / KC;
+      const int kw = nrow / CT, col = slice * CT + nrow % CT;
+      const int tap = 124 - ((kd * 5 + kh) * 5 + kw);
+      tile[nrow * pitch + k] = j.w[(static_cast<long long>(tap) * Cin + col) * Cout + kc * KC + k];
+    }
+  }
+  __syncthreads();
+  const long long base = static_cast<long long>(tile_idx) * elems;
+  for (int e = threadIdx.x; e < elems; e += blockDim.x) {
+    const float v = tile[(e / KC) * pitch + e % KC];
+    const uint16_t h = f32_to_bf16(v);
+    j.hi[base + e] = h;
+    if (j.lo) j.lo[base + e] = f32_to_bf16(v - bf16_to_f32(h));
   }
 }
 

@@ -45,9 +45,12 @@ inline void Engine::tc_setup() {
     const Act& x1 = acts_[u.in1];
     const Act& o = acts_[u.out];
     const Dims d = o.dims;
+    // multi-modal network input (networks.py:260-266): the image's bf16 copies are zero-padded to 16 channels
+    const bool padded_in = (u.in1 == image_act_) && image_cpad_ > 0;
+    const int c1 = padded_in ? image_cpad_ : u.Cin1;
     TcKernelPlan& f = u.tc.fprop;
-    if (tc_plan_geometry(f, NB, d.D, d.H, d.W, u.Cin1, u.Cin2, u.Cout, 0, lo)) {
-      f.wp_elems = u.w_count;
+    if (tc_plan_geometry(f, NB, d.D, d.H, d.W, c1, u.Cin2, u.Cout, 0, lo)) {
+      f.wp_elems = 125ull * (c1 + u.Cin2) * u.Cout;
       f.wp_hi = dev_alloc<uint16_t>(f.wp_elems);
       f.wp_lo = lo ? dev_alloc<uint16_t>(f.wp_elems) : nullptr;
       tc_encode_plan(f, NB, x1.a_hi, x1.a_lo, u.in2 >= 0 ? acts_[u.in2].a_hi : nullptr, u.in2 >= 0 ? acts_[u.in2].a_lo : nullptr);
@@ -62,7 +65,7 @@ inline void Engine::tc_setup() {
       g.valid = true;
     }
     WgPlan& wg = u.tc.wgrad;
-    if (wg_plan_geometry(wg, NB, d.D, d.H, d.W, u.Cin1, u.Cin2, u.Cout, lo, sm_count_)) {
+    if (wg_plan_geometry(wg, NB, d.D, d.H, d.W, c1, u.Cin2, u.Cout, lo, sm_count_)) {
       wg_encode_plan(wg, NB, x1.a_hi, x1.a_lo, u.in2 >= 0 ? acts_[u.in2].a_hi : nullptr,
                      u.in2 >= 0 ? acts_[u.in2].a_lo : nullptr, o.d_hi, o.d_lo);
       wg.valid = true;
@@ -74,16 +77,39 @@ inline void Engine::tc_setup() {
 
 inline void Engine::tc_prepare_weights() {
   if (!weights_dirty_) return;
-  for (Unit& u : units_) {
-    if (u.kind != U_CONV5) continue;
-    const int Cin = u.Cin1 + u.Cin2;
-    for (int pass = 0; pass < 2; ++pass) {
-      TcKernelPlan& pl = pass == 0 ? u.tc.fprop : u.tc.dgrad;
-      if (!pl.valid) continue;
-      VNB_LAUNCH(pack_w5_kernel, pl.g.n_slices * 25 * pl.g.n_kc, 256, 0, stream_,
-                 (const float*)(params_ + u.w_off), Cin, u.Cout, pass, pl.CT, pl.KC, pl.wp_hi, pl.wp_lo);
-      ++launches_;
+  if (!pack_jobs_dev_) {  // one table for every (layer, fprop|dgrad) pack, built once
+    std::vector<PackJob> jobs;
+    int blocks = 0;
+    for (Unit& u : units_) {
+      if (u.kind != U_CONV5) continue;
+      for (int pass = 0; pass < 2; ++pass) {
+        TcKernelPlan& pl = pass == 0 ? u.tc.fprop : u.tc.dgrad;
+        if (!pl.valid) continue;
+        PackJob j;
+        j.w = params_ + u.w_off;
+        j.hi = pl.wp_hi;
+        j.lo = pl.wp_lo;
+        j.Cin = u.Cin1 + u.Cin2;
+        j.Cout = u.Cout;
+        j.dgrad = pass;
+        j.CT = pl.CT;
+        j.KC = pl.KC;
+        j.Cin_gemm = pl.g.C1 + pl.g.C2;
+        j.first_block = blocks;
+        blocks += pl.g.n_slices * 25 * pl.g.n_kc;
+        jobs.push_back(j);
+      }
     }
+    pack_blocks_ = blocks;
+    pack_njobs_ = static_cast<int>(jobs.size());
+    if (pack_njobs_) {
+      pack_jobs_dev_ = dev_alloc<PackJob>(jobs.size());
+      VNB_CUDA_OK(cudaMemcpy(pack_jobs_dev_, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+    }
+  }
+  if (pack_njobs_) {
+    VNB_LAUNCH(pack_w5_multi_kernel, pack_blocks_, 256, 0, stream_, (const PackJob*)pack_jobs_dev_, pack_njobs_);
+    ++launches_;
   }
   weights_dirty_ = false;
 }
@@ -123,7 +149,7 @@ inline void Engine::tc_run_dgrad(Unit& u, int N) {
 
 inline void Engine::tc_run_wgrad(Unit& u, int N) {
   ProfScope ps(*this, 1, conv5_flops(u, N));
-  wg_launch(u.tc.wgrad, N, cfg_.precision == PREC_BF16X3, wg_partial_, grads_ + u.w_off, stream_);
+  wg_launch(u.tc.wgrad, N, cfg_.precision == PREC_BF16X3, wg_partial_, grads_ + u.w_off, stream_, u.Cin1 + u.Cin2);
   launches_ += 2;
 }
 
@@ -157,7 +183,7 @@ inline void tc_op_conv5(int precision, const float* x, const float* w, const flo
   pl.wp_elems = 125ull * cin * cout;
   pl.wp_hi = s.alloc<uint16_t>(pl.wp_elems);
   pl.wp_lo = lo ? s.alloc<uint16_t>(pl.wp_elems) : nullptr;
-  VNB_LAUNCH(pack_w5_kernel, pl.g.n_slices * 25 * pl.g.n_kc, 256, 0, 0, w, cin, cout, dgrad_form ? 1 : 0, pl.CT, pl.KC, pl.wp_hi, pl.wp_lo);
+  VNB_LAUNCH(pack_w5_kernel, pl.g.n_slices * 25 * pl.g.n_kc, 256, 0, 0, w, cin, cout, dgrad_form ? 1 : 0, pl.CT, pl.KC, pl.wp_hi, pl.wp_lo, cin);
   tc_encode_plan(pl, n, xh, xl, nullptr, nullptr);
   TcArgs a;
   a.g = pl.g;

@@ -55,9 +55,10 @@ struct EngineConfig {
   int optimizer = OPT_ADAM;
   float lr0 = 1e-2f, decay_factor = 0.99f, decay_steps = 100.f;
   float momentum = 0.9f;
+  int flavour = 0;  // 0: networks.VNet (live path, model.py:428-438); 1: VNet.py legacy flavour (train.py:271-279)
 };
 
-enum UnitKind : int { U_INPUT_TILE = 0, U_CONV5, U_DOWN, U_UP, U_CONV1 };
+enum UnitKind : int { U_INPUT_TILE = 0, U_CONV5, U_DOWN, U_UP, U_CONV1, U_ADD };
 
 struct ParamEntry {
   std::string name;
@@ -370,8 +371,9 @@ class Engine {
     entries_.push_back(e);
     return static_cast<long long>(e.offset);
   }
-  void add_bn(Unit& u, int k, int C) {
-    const std::string base = u.scope + "/batch_normalization" + (k == 0 ? "" : "_" + std::to_string(k));
+  void add_bn(Unit& u, int k, int C, int name_offset = 0) {
+    const int idx = k + name_offset;
+    const std::string base = u.scope + "/batch_normalization" + (idx == 0 ? "" : "_" + std::to_string(idx));
     u.gamma_off[k] = add_param(base + "/gamma", {C}, true);
     u.beta_off[k] = add_param(base + "/beta", {C}, true);
     u.mm_off[k] = add_param(base + "/moving_mean", {C}, false);
@@ -379,7 +381,7 @@ class Engine {
   }
   // registers parameters in TF creation order: weights, biases, BNs, alpha
   int add_unit(int kind, const std::string& scope, int in1, int in2, int res, int Cout, Dims out_dims,
-               int chain, bool act, bool dropout) {
+               int chain, bool act, bool dropout, int bn_name_offset = 0) {
     Unit u;
     u.scope = scope;
     u.kind = kind;
@@ -407,8 +409,8 @@ class Engine {
       u.w_off = add_param(scope + "/weights", {1, 1, 1, Cin, Cout}, true);
       u.w_count = static_cast<size_t>(Cin) * Cout;
     }
-    if (kind != U_INPUT_TILE) u.b_off = add_param(scope + "/biases", {Cout}, true);
-    for (int k = 0; k < chain_num_bn(chain); ++k) add_bn(u, k, Cout);
+    if (kind != U_INPUT_TILE && kind != U_ADD) u.b_off = add_param(scope + "/biases", {Cout}, true);
+    for (int k = 0; k < chain_num_bn(chain); ++k) add_bn(u, k, Cout, bn_name_offset);
     if (act) u.alpha_off = add_param(scope + "/alpha", {Cout}, true);
     u.out = add_act(Cout, out_dims);
     units_.push_back(u);
@@ -425,14 +427,27 @@ class Engine {
       x = add_unit(U_INPUT_TILE, "vnet/input_layer", image_act_, -1, -1, C0, full, CH_S, false, false);
     else                      // networks.py:260-266
       x = add_unit(U_CONV5, "vnet/input_layer", image_act_, -1, -1, C0, full, CH_S, true, false);
+    const bool legacy = c.flavour == 1;
+    // VNet.py:26-40: conv -> BN -> (+ block input on the last conv) -> BN -> act -> dropout.  The add sits
+    // between the two batch norms, so the last conv becomes two units: conv+BN0, then add+BN1+act+dropout.
+    auto legacy_conv = [&](const std::string& sc, int in1, int in2, int res, int ch, Dims dd) {
+      if (res < 0) return add_unit(U_CONV5, sc, in1, in2, -1, ch, dd, CH_2, true, true);
+      const int u0 = add_unit(U_CONV5, sc, in1, in2, -1, ch, dd, CH_S, false, false);
+      return add_unit(U_ADD, sc, u0, -1, res, ch, dd, CH_S, true, true, 1);
+    };
     std::vector<int> features;
     Dims d = full;
     for (int l = 0; l < c.num_levels; ++l) {  // networks.py:270-280
       const int ch = C0 << l;
       const std::string scope = "vnet/encoder/level_" + std::to_string(l + 1);
       const int block_in = x, n = c.num_convolutions[l];
-      for (int i = 0; i < n; ++i)
-        x = add_unit(U_CONV5, scope + "/conv_" + std::to_string(i + 1), x, -1, i == n - 1 ? block_in : -1, ch, d, CH_S, true, true);
+      for (int i = 0; i < n; ++i) {
+        const std::string sc = scope + "/conv_" + std::to_string(i + 1);
+        if (legacy)
+          x = legacy_conv(sc, x, -1, i == n - 1 ? block_in : -1, ch, d);
+        else
+          x = add_unit(U_CONV5, sc, x, -1, i == n - 1 ? block_in : -1, ch, d, CH_S, true, true);
+      }
       features.push_back(x);
       Dims half{d.D / 2, d.H / 2, d.W / 2};
       x = add_unit(U_DOWN, scope + "/down_convolution", x, -1, -1, 2 * ch, half, CH_S, true, false);
@@ -440,8 +455,13 @@ class Engine {
     }
     {  // networks.py:282-283
       const int ch = C0 << c.num_levels, block_in = x, n = c.bottom_convolutions;
-      for (int i = 0; i < n; ++i)
-        x = add_unit(U_CONV5, "vnet/bottom_level/conv_" + std::to_string(i + 1), x, -1, i == n - 1 ? block_in : -1, ch, d, CH_S, true, true);
+      for (int i = 0; i < n; ++i) {
+        const std::string sc = "vnet/bottom_level/conv_" + std::to_string(i + 1);
+        if (legacy)
+          x = legacy_conv(sc, x, -1, i == n - 1 ? block_in : -1, ch, d);
+        else
+          x = add_unit(U_CONV5, sc, x, -1, i == n - 1 ? block_in : -1, ch, d, CH_S, true, true);
+      }
     }
     for (int l = c.num_levels - 1; l >= 0; --l) {  // networks.py:285-296
       const int ch = C0 << l;
@@ -450,7 +470,16 @@ class Engine {
       Dims up = acts_[f].dims;
       x = add_unit(U_UP, scope + "/up_convolution", x, -1, -1, ch, up, CH_S, true, false);
       const int n = c.num_convolutions[l];
-      if (n == 1) {  // networks.py:328-340
+      if (legacy) {  // VNet.py:43-73: true residual to the up-convolution output
+        const int x_up = x;
+        if (n == 1) {
+          x = legacy_conv(scope + "/conv_1", x_up, f, x_up, ch, up);
+        } else {
+          x = add_unit(U_CONV5, scope + "/conv_1", x_up, f, -1, ch, up, CH_S, true, true);
+          for (int i = 1; i < n; ++i)
+            x = legacy_conv(scope + "/conv_" + std::to_string(i + 1), x, -1, i == n - 1 ? x_up : -1, ch, up);
+        }
+      } else if (n == 1) {  // networks.py:328-340
         x = add_unit(U_CONV5, scope + "/conv_1", x, f, -1, ch, up, CH_T, true, true);
       } else {       // networks.py:342-363
         x = add_unit(U_CONV5, scope + "/conv_1", x, f, -1, ch, up, CH_S, true, true);
@@ -523,8 +552,13 @@ class Engine {
       a.a = dev_alloc<float>(n);
       if (a.needs_grad) a.d = dev_alloc<float>(n);
       if (tc) {
-        a.a_hi = dev_alloc<uint16_t>(n);
-        if (lo) a.a_lo = dev_alloc<uint16_t>(n);
+        size_t nh = n;
+        if (&a == &acts_[image_act_] && a.C > 1 && a.C % 16) {  // padded bf16 copies of a multi-modal input
+          image_cpad_ = (a.C + 15) / 16 * 16;
+          nh = static_cast<size_t>(voxels_of(a.dims, NB)) * image_cpad_;
+        }
+        a.a_hi = dev_alloc<uint16_t>(nh);
+        if (lo) a.a_lo = dev_alloc<uint16_t>(nh);
         if (a.needs_grad) {
           a.d_hi = dev_alloc<uint16_t>(n);
           if (lo) a.d_lo = dev_alloc<uint16_t>(n);
@@ -640,7 +674,7 @@ class Engine {
   void run_conv_fprop(Unit& u, int N) {
     const Act& x1 = acts_[u.in1];
     const Act& o = acts_[u.out];
-    const float* bias = params_ + u.b_off;
+    const float* bias = u.b_off >= 0 ? params_ + u.b_off : nullptr;
     if (u.kind == U_CONV5) {
       if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid && !getenv("VNB_DEBUG_NO_TC_FPROP")) {
         tc_run_fprop(u, N);
@@ -684,6 +718,10 @@ class Engine {
         p.cd = x1.dims;
         launch_k2_scatter(p);
       }
+    } else if (u.kind == U_ADD) {
+      const long long n = voxels_of(o.dims, N) * u.Cout;
+      VNB_LAUNCH(add2_kernel, grid_for(n, 256), 256, 0, stream_, (const float*)x1.a, (const float*)acts_[u.res].a, u.z, n);
+      ++launches_;
     } else if (u.kind == U_CONV1) {
       const long long V = voxels_of(o.dims, N);
       VNB_LAUNCH(conv1_fprop_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, (const float*)x1.a,
@@ -701,7 +739,16 @@ class Engine {
   }
 
   void forward(int N, float dropout, uint64_t seed, bool update_moving) {
-    if (cfg_.precision != PREC_FP32) tc_prepare_weights();
+    if (cfg_.precision != PREC_FP32) {
+      tc_prepare_weights();
+      if (image_cpad_ > 0) {
+        const Act& im = acts_[image_act_];
+        const long long V = voxels_of(im.dims, N);
+        VNB_LAUNCH(split_pad_bf16_kernel, grid_for(V * image_cpad_, 256), 256, 0, stream_, (const float*)im.a, V, im.C,
+                   image_cpad_, im.a_hi, im.a_lo);
+        ++launches_;
+      }
+    }
     for (size_t ui = 0; ui < units_.size(); ++ui) {
       Unit& u = units_[ui];
       const Act& o = acts_[u.out];
@@ -782,6 +829,8 @@ class Engine {
       b.d_lo = (u.kind == U_CONV5) ? o.d_lo : nullptr;
       b.res_grad = u.res >= 0 ? acts_[u.res].d : nullptr;
       b.res_accumulate = u.res_accumulate ? 1 : 0;
+      b.res_grad2 = u.kind == U_ADD ? acts_[u.in1].d : nullptr;
+      b.res_accumulate2 = u.in1_accumulate ? 1 : 0;
       b.scale = u.scale;
       b.shift = u.shift;
       b.alpha = u.has_act ? params_ + u.alpha_off : nullptr;
@@ -829,7 +878,7 @@ class Engine {
       else
         VNB_LAUNCH(bn_bwd_apply_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, b, V * u.Cout);
       ++launches_;
-      run_conv_backward(u, N);
+      if (u.kind != U_ADD) run_conv_backward(u, N);
       notify_bucket(ui);
     }
   }
@@ -1008,6 +1057,9 @@ class Engine {
   void tc_run_dgrad(Unit& u, int N);
   void tc_run_wgrad(Unit& u, int N);
   int sm_count_ = 148;
+  int image_cpad_ = 0;
+  PackJob* pack_jobs_dev_ = nullptr;
+  int pack_blocks_ = 0, pack_njobs_ = 0;
   float* wg_partial_ = nullptr;
 
   EngineConfig cfg_;

@@ -27,15 +27,31 @@ constexpr float kBnMomentum = 0.99f;
 // counter-based dropout RNG: keep-mask is a pure function of (seed, unit, element index), so the
 // backward pass regenerates it instead of storing it.  tf.nn.dropout keeps where u >= rate.
 // ---------------------------------------------------------------------------------------------
-VNB_HD uint64_t mix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
+// One 32-bit hash (lowbias32) yields two 16-bit uniforms, so a float4 of activations costs two hashes.
+// keep(idx) <=> u16 >= round(rate * 65536); the scale uses the quantised rate so E[mask * scale] = 1.
+VNB_HD uint32_t hash32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
 }
-VNB_HD float dropout_uniform(uint64_t seed, uint32_t unit, uint64_t idx) {
-  uint64_t h = mix64(seed ^ mix64((static_cast<uint64_t>(unit) << 40) ^ idx));
-  return static_cast<float>(h >> 40) * (1.0f / 16777216.0f);  // 24-bit mantissa, [0,1)
+VNB_HD uint32_t dropout_key(uint64_t seed, uint32_t unit) {
+  return hash32(static_cast<uint32_t>(seed) ^ hash32(static_cast<uint32_t>(seed >> 32) + 0x9E3779B1u * (unit + 1u)));
+}
+// 32 random bits shared by elements idx with equal idx >> 1
+VNB_HD uint32_t dropout_bits(uint32_t key, uint64_t idx) {
+  const uint64_t pair = idx >> 1;
+  return hash32(static_cast<uint32_t>(pair) * 0x9E3779B1u + static_cast<uint32_t>(pair >> 32) * 0x85EBCA77u + key);
+}
+VNB_HD uint32_t dropout_threshold(float rate) { return static_cast<uint32_t>(rate * 65536.0f + 0.5f); }
+VNB_HD float dropout_keep_scale(float rate) {
+  return rate > 0.f ? 65536.0f / (65536.0f - static_cast<float>(dropout_threshold(rate))) : 1.0f;
+}
+VNB_HD bool dropout_keep(uint32_t key, uint64_t idx, uint32_t thresh) {
+  const uint32_t b = dropout_bits(key, idx);
+  return ((idx & 1u) ? (b >> 16) : (b & 0xFFFFu)) >= thresh;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -200,14 +216,15 @@ struct ApplyArgs {
 };
 
 __global__ void bn_apply_kernel(ApplyArgs p) {
-  const float keep_scale = p.drop_rate > 0.f ? 1.0f / (1.0f - p.drop_rate) : 1.0f;
+  const float keep_scale = dropout_keep_scale(p.drop_rate);
+  const uint32_t dkey = dropout_key(p.seed, p.unit), dthr = dropout_threshold(p.drop_rate);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % p.C);
     const float zin = p.tiled_input ? p.z[i / p.C] : p.z[i];
     float y = p.scale[c] * zin + p.shift[c];
     if (p.alpha) y = y > 0.f ? y : p.alpha[c] * y;  // max(0,y) + alpha*min(0,y)
-    if (p.drop_rate > 0.f) y = dropout_uniform(p.seed, p.unit, static_cast<uint64_t>(i)) >= p.drop_rate ? y * keep_scale : 0.f;
+    if (p.drop_rate > 0.f) y = dropout_keep(dkey, static_cast<uint64_t>(i), dthr) ? y * keep_scale : 0.f;
     p.a[i] = y;
     if (p.a_hi) {
       const uint16_t hi = f32_to_bf16(y);
@@ -230,6 +247,8 @@ struct BwdArgs {
   uint16_t* d_lo;
   float* res_grad;      // optional: residual branch gradient target (block input's dL/da)
   int res_accumulate;   // 0: write, 1: add
+  float* res_grad2;     // optional second target (the summand of an add unit)
+  int res_accumulate2;
   const float* scale;
   const float* shift;
   const float* alpha;   // or nullptr
@@ -248,7 +267,8 @@ __device__ __forceinline__ float bwd_g(const BwdArgs& p, long long i, int c, flo
   yhat = p.scale[c] * zin + p.shift[c];
   dd = p.d[i];
   if (p.drop_rate > 0.f)
-    dd = dropout_uniform(p.seed, p.unit, static_cast<uint64_t>(i)) >= p.drop_rate ? dd / (1.0f - p.drop_rate) : 0.f;
+    dd = dropout_keep(dropout_key(p.seed, p.unit), static_cast<uint64_t>(i), dropout_threshold(p.drop_rate))
+             ? dd * dropout_keep_scale(p.drop_rate) : 0.f;
   if (!p.alpha) return dd;
   // TF gradients of maximum(0,y)/minimum(0,y): 1 for y>0, alpha for y<0, 0 at the tie
   return yhat > 0.f ? dd : (yhat < 0.f ? dd * p.alpha[c] : 0.f);
@@ -325,6 +345,7 @@ __global__ void bn_bwd_apply_kernel(BwdArgs p, long long total) {
     const float dz = p.P[c] * gg + p.Q[c] + p.S[c] * (zin - static_cast<float>(p.mean[c]));
     p.d[i] = dz;
     if (p.res_grad) p.res_grad[i] = p.res_accumulate ? p.res_grad[i] + dz : dz;
+    if (p.res_grad2) p.res_grad2[i] = p.res_accumulate2 ? p.res_grad2[i] + dz : dz;
     if (p.d_hi) {
       const uint16_t hi = f32_to_bf16(dz);
       p.d_hi[i] = hi;
@@ -537,6 +558,21 @@ __global__ void sgd_step_kernel(float* __restrict__ p, const float* __restrict__
     p[i] -= lr * g[i] * gscale;
 }
 
+// [V][C] fp32 -> [V][Cpad] bf16 (hi, lo) with zero padding channels: multi-modal network input for the
+// tensor-core input convolution (which wants channel multiples of 16)
+__global__ void split_pad_bf16_kernel(const float* __restrict__ x, long long V, int C, int Cpad, uint16_t* __restrict__ hi,
+                                      uint16_t* __restrict__ lo) {
+  const long long total = V * Cpad;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cpad);
+    const float f = c < C ? x[(i / Cpad) * C + c] : 0.f;
+    const uint16_t h = f32_to_bf16(f);
+    hi[i] = h;
+    if (lo) lo[i] = f32_to_bf16(f - bf16_to_f32(h));
+  }
+}
+
 // tf.train.MomentumOptimizer: accum = momentum*accum + g; p -= lr*accum   (use_nesterov: p -= lr*(g + momentum*accum))
 __global__ void momentum_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ accum, long long n,
                                      float lr, float momentum, int nesterov, float gscale) {
@@ -586,12 +622,13 @@ __device__ __forceinline__ void store_hi_lo4(uint16_t* hi, uint16_t* lo, unsigne
 
 __global__ void __launch_bounds__(256) bn_apply_v4_kernel(ApplyArgs p) {
   const unsigned total4 = static_cast<unsigned>(p.total / 4), C4 = static_cast<unsigned>(p.C / 4);
-  const float keep_scale = p.drop_rate > 0.f ? 1.0f / (1.0f - p.drop_rate) : 1.0f;
+  const float keep_scale = dropout_keep_scale(p.drop_rate);
+  const uint32_t dkey = dropout_key(p.seed, p.unit), dthr = dropout_threshold(p.drop_rate);
   const float4* __restrict__ z4 = reinterpret_cast<const float4*>(p.z);
   float4* __restrict__ a4 = reinterpret_cast<float4*>(p.a);
 #pragma unroll 4
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
-    const unsigned c = (i % C4) * 4;
+    const unsigned c = (i & (C4 - 1u)) * 4;  // C4 divides 256, hence a power of two
     float z[4];
     if (p.tiled_input) {
       const float v = p.z[i / C4];
@@ -611,9 +648,11 @@ __global__ void __launch_bounds__(256) bn_apply_v4_kernel(ApplyArgs p) {
       y[3] = y[3] > 0.f ? y[3] : al.w * y[3];
     }
     if (p.drop_rate > 0.f) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        y[k] = dropout_uniform(p.seed, p.unit, static_cast<uint64_t>(i) * 4 + k) >= p.drop_rate ? y[k] * keep_scale : 0.f;
+      const uint32_t b0 = dropout_bits(dkey, static_cast<uint64_t>(i) * 4), b1 = dropout_bits(dkey, static_cast<uint64_t>(i) * 4 + 2);
+      y[0] = (b0 & 0xFFFFu) >= dthr ? y[0] * keep_scale : 0.f;
+      y[1] = (b0 >> 16) >= dthr ? y[1] * keep_scale : 0.f;
+      y[2] = (b1 & 0xFFFFu) >= dthr ? y[2] * keep_scale : 0.f;
+      y[3] = (b1 >> 16) >= dthr ? y[3] * keep_scale : 0.f;
     }
     a4[i] = make_float4(y[0], y[1], y[2], y[3]);
     if (p.a_hi) store_hi_lo4(p.a_hi, p.a_lo, i, y);
@@ -629,10 +668,13 @@ __device__ __forceinline__ void bwd_g4(const BwdArgs& p, unsigned i, unsigned c,
   yhat[0] = sc.x * z[0] + sh.x; yhat[1] = sc.y * z[1] + sh.y; yhat[2] = sc.z * z[2] + sh.z; yhat[3] = sc.w * z[3] + sh.w;
   dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
   if (p.drop_rate > 0.f) {
-    const float inv = 1.0f / (1.0f - p.drop_rate);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      dd[k] = dropout_uniform(p.seed, p.unit, static_cast<uint64_t>(i) * 4 + k) >= p.drop_rate ? dd[k] * inv : 0.f;
+    const float inv = dropout_keep_scale(p.drop_rate);
+    const uint32_t dkey = dropout_key(p.seed, p.unit), dthr = dropout_threshold(p.drop_rate);
+    const uint32_t b0 = dropout_bits(dkey, static_cast<uint64_t>(i) * 4), b1 = dropout_bits(dkey, static_cast<uint64_t>(i) * 4 + 2);
+    dd[0] = (b0 & 0xFFFFu) >= dthr ? dd[0] * inv : 0.f;
+    dd[1] = (b0 >> 16) >= dthr ? dd[1] * inv : 0.f;
+    dd[2] = (b1 & 0xFFFFu) >= dthr ? dd[2] * inv : 0.f;
+    dd[3] = (b1 >> 16) >= dthr ? dd[3] * inv : 0.f;
   }
   if (p.alpha) {
     const float4 al = *reinterpret_cast<const float4*>(p.alpha + c);
@@ -650,7 +692,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_v4_kernel(BwdArgs p, long lo
   const float4* __restrict__ z4 = reinterpret_cast<const float4*>(p.z);
 #pragma unroll 2
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += gridDim.x * blockDim.x) {
-    const unsigned c = (i % C4) * 4;
+    const unsigned c = (i & (C4 - 1u)) * 4;
     const float4 zf = z4[i];
     const float z[4] = {zf.x, zf.y, zf.z, zf.w};
     float g[4], yhat[4], dd[4];
@@ -673,8 +715,24 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_v4_kernel(BwdArgs p, long lo
       }
       *r = o;
     }
+    if (p.res_grad2) {
+      float4* r = reinterpret_cast<float4*>(p.res_grad2) + i;
+      float4 o = make_float4(dz[0], dz[1], dz[2], dz[3]);
+      if (p.res_accumulate2) {
+        const float4 old = *r;
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *r = o;
+    }
     if (p.d_hi) store_hi_lo4(p.d_hi, p.d_lo, i, dz);
   }
+}
+
+// z = a + b (the residual add that sits between the two batch norms of the legacy flavour, VNet.py:33-34)
+__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ z, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    z[i] = a[i] + b[i];
 }
 
 // per-channel reductions, 4 channels per thread. blockDim = 256, C4 = C/4 divides 256.

@@ -102,6 +102,8 @@ int vnb_create(const vnb_config* c, int device, vnb_handle** out) {
     e.decay_factor = c->decay_factor;
     e.decay_steps = c->decay_steps;
     e.momentum = c->momentum;
+    e.flavour = c->graph_flavour;
+    if (e.flavour < 0 || e.flavour > 1) throw std::invalid_argument("graph_flavour must be 0 (networks.VNet) or 1 (VNet.py)");
     if (e.precision < 0 || e.precision > 2) throw std::invalid_argument("precision must be VNB_PREC_*");
     if (e.loss < 0 || e.loss > VNB_LOSS_MIXED_WEIGHTED_JACCARD) throw std::invalid_argument("loss must be VNB_LOSS_*");
     if (e.optimizer < 0 || e.optimizer > VNB_OPT_NESTEROV) throw std::invalid_argument("optimizer must be VNB_OPT_*");

@@ -209,6 +209,7 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
 // dw[tap][ci][co] = sum_split partial[split][pair(ci/16, co/16)][tap][ci%16][co%16]   (fixed order)
 __global__ void wgrad5_reduce_kernel(const float* __restrict__ partial, int splits, int n_ci, int n_co, int Cin, int Cout,
                                      float* __restrict__ dw) {
+  // Cin = real input channels of dw; the GEMM may have run on a zero-padded multiple of 16 (n_ci chunks)
   const long long total = 125LL * Cin * Cout;
   const int pairs = n_ci * n_co;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -290,7 +291,7 @@ inline void wg_encode_plan(WgPlan& pl, int Nmax, const uint16_t* x1_hi, const ui
   wg_encode_act(&pl.z_lo, z_lo ? z_lo : z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.W, g.HT + 4);
 }
 
-inline void wg_launch(const WgPlan& pl, int N, bool split3, float* partial, float* dw, cudaStream_t stream) {
+inline void wg_launch(const WgPlan& pl, int N, bool split3, float* partial, float* dw, cudaStream_t stream, int cin_real = 0) {
   WgGeom g = pl.g;
   g.N = N;
   const int items = N * g.D * g.n_hb;
@@ -316,9 +317,10 @@ inline void wg_launch(const WgPlan& pl, int N, bool split3, float* partial, floa
 #endif
     VNB_LAUNCH(kfn, grid, kWgThreads, pl.smem, stream, pl.x1_hi, pl.x1_lo, pl.x2_hi, pl.x2_lo, pl.z_hi, pl.z_lo, g, partial);
   }
-  const long long total = 125LL * (g.C1 + g.C2) * g.Cout;
+  const int cin = cin_real > 0 ? cin_real : g.C1 + g.C2;
+  const long long total = 125LL * cin * g.Cout;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 2368));
-  VNB_LAUNCH(wgrad5_reduce_kernel, blocks, 256, 0, stream, (const float*)partial, g.splits, g.n_ci, g.n_co, g.C1 + g.C2, g.Cout, dw);
+  VNB_LAUNCH(wgrad5_reduce_kernel, blocks, 256, 0, stream, (const float*)partial, g.splits, g.n_ci, g.n_co, cin, g.Cout, dw);
 }
 
 }  // namespace vnb

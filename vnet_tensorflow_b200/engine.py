@@ -26,7 +26,7 @@ class VNetEngine:
                  num_convolutions: Sequence[int] = (1, 2, 3, 3), bottom_convolutions: int = 3,
                  precision: str = "fp32", loss: str = "weighted_sorensen", loss_weights: Sequence[float] = (),
                  loss_alpha: float = 1.0, optimizer: str = "Adam", learning_rate: float = 1e-2,
-                 decay_factor: float = 0.99, decay_steps: float = 100.0, momentum: float = 0.9, device: int = 0,
+                 decay_factor: float = 0.99, decay_steps: float = 100.0, momentum: float = 0.9, flavour: str = "networks", device: int = 0,
                  library: Optional[_ffi.Library] = None):
         self.lib = library or _ffi.default_library()
         if precision not in _ffi.PRECISIONS:
@@ -59,6 +59,9 @@ class VNetEngine:
         cfg.optimizer = _ffi.OPTIMIZERS[optimizer]
         cfg.learning_rate, cfg.decay_factor, cfg.decay_steps = learning_rate, decay_factor, decay_steps
         cfg.momentum = momentum
+        if flavour not in ("networks", "legacy"):
+            raise ValueError("flavour must be 'networks' (networks.VNet) or 'legacy' (VNet.py)")
+        cfg.graph_flavour = 1 if flavour == "legacy" else 0
         self.cfg = cfg
         self.num_classes, self.in_channels = num_classes, in_channels
         self.patch_shape = tuple(int(p) for p in patch_shape)

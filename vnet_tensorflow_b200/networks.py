@@ -45,3 +45,20 @@ class VNet(object):
             raise ValueError("only the 3-D branch of networks.VNet is accelerated: x must be [N,X,Y,Z,M]")
         logits, _, _ = self._ensure(x).forward(x, want_softmax=False, want_argmax=False)
         return logits
+
+
+class LegacyVNet(VNet):
+    """Drop-in for the legacy `VNet.VNet(num_classes, keep_prob, ...).network_fn(x)` (VNet.py:75-155) that only
+    `train.py:271-279` uses: two batch norms per convolution with the residual added between them, and a
+    true residual to the up-convolution output in the decoder."""
+
+    def __init__(self, num_classes, keep_prob=1.0, num_channels=16, num_levels=4, num_convolutions=(1, 2, 3, 3),
+                 bottom_convolutions=3, is_training=True, activation_fn="prelu", precision="bf16x3", device=0):
+        super().__init__(num_classes, 1.0 - keep_prob, num_channels, num_levels, num_convolutions, bottom_convolutions,
+                         is_training, activation_fn, precision, device)
+        self.keep_prob = keep_prob
+
+    def network_fn(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        logits, _, _ = self._ensure(x, flavour="legacy").forward(x, want_softmax=False, want_argmax=False)
+        return logits
