@@ -53,6 +53,40 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "tflops": 1400.0, "source": "fallback"}
 
 
+def roofline_block(precision, peaks, fd_ms, fd_n, fd_fl, wg_ms, wg_n, wg_fl, prof_steps, ms_per_step, step_tflops):
+    """Roofline of the dominant kernel class (largest share of the step).  achieved = algorithmic FLOPs
+    (2*125*Cin*Cout*voxels per launch; the three MMA passes of bf16x3 are NOT counted) / CUDA-event time of the
+    launches on the engine stream; peak = measured cuBLAS bf16 (sustained); traffic = DRAM bytes per launch of
+    that class from the committed ncu --set full capture (profiles/r01_traffic.json), else null."""
+    classes = {
+        "conv5_tc_kernel (5^3 fprop + dgrad)": (fd_ms, fd_n, fd_fl),
+        "wgrad5_tc_kernel (5^3 filter gradient)": (wg_ms, wg_n, wg_fl),
+    }
+    dom = max(classes, key=lambda k: classes[k][0])
+    ms, n, fl = classes[dom]
+    achieved = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f).get(precision, {}).get(dom.split(" ")[0])
+    except Exception:
+        pass
+    return {
+        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["tflops"], "traffic": traffic,
+        "launches_per_step": n / max(prof_steps, 1), "avg_launch_ms": ms / max(n, 1),
+        "share_of_step": ms / max(prof_steps, 1) / ms_per_step,
+        "peak_source": peaks["source"] + " cuBLAS bf16 sustained (MEASURED_PEAKS.json)",
+        "mma_passes": 3 if precision == "bf16x3" else 1,
+        "fprop_dgrad_tflops": fd_fl / (fd_ms * 1e-3) / 1e12 if fd_ms > 0 else 0.0,
+        "wgrad_tflops": wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else 0.0,
+        "all_conv5_tflops": (fd_fl + wg_fl) / ((fd_ms + wg_ms) * 1e-3) / 1e12 if fd_ms + wg_ms > 0 else 0.0,
+        "conv_share_of_step": (fd_ms + wg_ms) / max(prof_steps, 1) / ms_per_step,
+        "whole_step_tflops_per_gpu": step_tflops,
+        "method": "CUDA events around every 5^3 convolution launch on the engine stream, %d profiled steps" % prof_steps,
+    }
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
 
@@ -236,7 +270,6 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         e2e_val = patches / (ms_e2e / 1e3)
         img_bytes = B * P ** 3 * 4
         lab_bytes = B * P ** 3 * 4
-        conv_tflops = (conv_fl + wg_fl) / ((conv_ms + wg_ms) * 1e-3) / 1e12 if conv_ms + wg_ms > 0 else 0.0
         step_tflops = value * train_gflop_per_patch(P) / 1e3 / world
         line = {
             "metric": "patches/sec (128^3, 1ch->2cls) training step", "value": value, "unit": "patches/sec",
@@ -253,14 +286,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": conv_tflops / peaks["tflops"], "traffic": None,
-                         "kernel": "5x5x5 convolution kernels (fprop+dgrad+wgrad), %d launches over %d profiled steps, "
-                                   "CUDA events on the engine stream" % (conv_n + wg_n, prof_steps),
-                         "fprop_dgrad_tflops": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
-                         "wgrad_tflops": wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else 0.0,
-                         "conv_share_of_step": (conv_ms + wg_ms) / prof_steps / (ms_dev / args.steps),
-                         "whole_step_tflops_per_gpu": step_tflops, "peak_source": peaks["source"] + " (cuBLAS bf16 sustained)"},
+            "roofline": roofline_block(args.precision, peaks, conv_ms, conv_n, conv_fl, wg_ms, wg_n, wg_fl, prof_steps,
+                                       ms_dev / args.steps, step_tflops),
             "final_loss": loss,
         }
         if world == 1 and not args.no_cpu_baseline:

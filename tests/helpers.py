@@ -40,17 +40,16 @@ def analytically_zero(name, spec):
     if name.endswith("/biases"):
         return True
     if getattr(spec, "flavour", "networks") == "legacy":
-        # VNet.py: in conv -> BN -> BN (non-last convs) the first BN's beta is re-normalised away
+        # VNet.py: whenever a conv has two batch norms (BN -> [+ residual] -> BN) the first BN's beta only shifts
+        # the second BN's input by a constant and is normalised away; only decoder conv_1 with n > 1 has one BN
         if not name.endswith("/batch_normalization/beta") or "/conv_" not in name:
             return False
         parts = name.split("/")
         i = int(parts[-3].split("_")[1]) - 1
-        if parts[1] == "bottom_level":
-            return i < spec.bottom_convolutions - 1
+        if parts[1] != "decoder":
+            return True
         n = spec.num_convolutions[int(parts[2].split("_")[1]) - 1]
-        if parts[1] == "encoder":
-            return i < n - 1
-        return 1 <= i < n - 1
+        return not (i == 0 and n > 1)
     if "/decoder/" not in name or "batch_normalization" not in name:
         return False
     level = int(name.split("/decoder/level_")[1].split("/")[0]) - 1
