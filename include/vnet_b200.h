@@ -56,7 +56,11 @@ enum { VNB_PREC_FP32 = 0, /* fp32 FMA on CUDA cores, exact-precision parity mode
 /* TrainingSetting.Loss.Name (model.py:495-560), same order as the reference's if-chain */
 enum { VNB_LOSS_XENT = 0, VNB_LOSS_WEIGHTED_XENT, VNB_LOSS_SORENSEN, VNB_LOSS_WEIGHTED_SORENSEN,
        VNB_LOSS_JACCARD, VNB_LOSS_WEIGHTED_JACCARD, VNB_LOSS_MIXED_SORENSEN,
-       VNB_LOSS_MIXED_WEIGHTED_SORENSEN, VNB_LOSS_MIXED_JACCARD, VNB_LOSS_MIXED_WEIGHTED_JACCARD };
+       VNB_LOSS_MIXED_WEIGHTED_SORENSEN, VNB_LOSS_MIXED_JACCARD, VNB_LOSS_MIXED_WEIGHTED_JACCARD,
+       VNB_LOSS_SORENSEN_FG /* legacy train.py:373-377 --loss_function sorensen: Dice of softmax[...,1] vs the label volume */ };
+
+/* legacy --attention_loss_function (train.py:387-399); needs vnb_set_distmap before a loss / training call */
+enum { VNB_ATT_NONE = 0, VNB_ATT_L2 = 1, VNB_ATT_ABS = 2 };
 
 /* TrainingSetting.Optimizer.Name (model.py:649-658) */
 enum { VNB_OPT_ADAM = 0, VNB_OPT_SGD = 1, VNB_OPT_MOMENTUM = 2, VNB_OPT_NESTEROV = 3 };
@@ -83,6 +87,10 @@ typedef struct vnb_config {
   float decay_steps;            /* Optimizer.Decay.Steps               model.py:220 */
   float momentum;               /* Optimizer.Momentum (Momentum / NesterovMomentum) model.py:653-656 */
   int32_t graph_flavour;        /* 0 = networks.VNet (main.py path), 1 = VNet.py legacy flavour (train.py:271-279) */
+  int32_t attention;            /* 1 = --attention: AttentionModule -> (1+softmax)*logits gating -> OutputModule
+                                   (train.py:281-312, attention.py:105-114, OutputModule.py:105-114) */
+  int32_t attention_loss;       /* VNB_ATT_*                           train.py:387-399 */
+  int32_t module_channels;      /* attention.py:41 / OutputModule.py:41 num_channels (0 = 64) */
 } vnb_config;
 
 const char* vnb_last_error(void);
@@ -128,6 +136,14 @@ int vnb_event_elapsed_ms(vnb_handle* h, float* ms);
  * enable, run steps, then read (sum of device ms, launches, algorithmic FLOPs) for class 0 fprop+dgrad, 1 wgrad */
 int vnb_profile_enable(vnb_handle* h, int on);
 int vnb_profile_read(vnb_handle* h, int kernel_class, double* ms, int64_t* launches, double* flops);
+
+/* attention path (vnb_config.attention = 1): the distance map fed as distmap_placeholder (train.py:176-179,
+ * 536) for the next loss / training calls, [n][X][Y][Z] floats in [0,1]; the three loss scalars of the last
+ * loss / training call (total_loss_op, loss_op, att_loss_op; train.py:417,351-382,387-399); and
+ * softmax_attention of the last forward pass (train.py:288), [n][X][Y][Z][K] */
+int vnb_set_distmap(vnb_handle* h, const float* distmap, int n);
+int vnb_read_losses(vnb_handle* h, float out_total_seg_att[3]);
+int vnb_read_softmax_attention(vnb_handle* h, float* host, size_t bytes, int n);
 
 int vnb_sync(vnb_handle* h);
 /* number of kernels this handle has launched so far */

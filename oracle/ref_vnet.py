@@ -585,3 +585,164 @@ def window_starts(dim: int, patch: int, stride: int) -> List[int]:
             s = dim - patch
         starts.append(s)
     return starts
+
+
+# --------------------------------------------------------------------------------------------------
+# Legacy attention path: train.py:269-312, attention.py, OutputModule.py
+# --------------------------------------------------------------------------------------------------
+MODULE_CHANNELS = 64  # attention.py:41 / OutputModule.py:41 num_channels default
+
+
+def module_param_specs(var_scope: str, bn_scope: str, in_ch: int, num_classes: int, nch: int = MODULE_CHANNELS):
+    """Variables of AttentionModule / OutputModule in creation order.  `tf.Variable`s are unnamed, so they are
+    `<name_scope>/<variable_scope>/Variable[_k]` (attention.py:25-31); the tf.layers batch norms live under the
+    variable scope only.  kind in {mod_w, mod_b, gamma, beta, moving_mean, moving_variance}."""
+    out, vi, bi = [], 0, 0
+
+    def var(scope, shape, kind):
+        nonlocal vi
+        out.append(("%s/Variable%s" % (scope, "" if vi == 0 else "_%d" % vi), tuple(shape), kind))
+        vi += 1
+
+    def bn(scope, c):
+        nonlocal bi
+        base = "%s/batch_normalization%s" % (scope, "" if bi == 0 else "_%d" % bi)
+        for k in ("gamma", "beta", "moving_mean", "moving_variance"):
+            out.append((base + "/" + k, (c,), k))
+        bi += 1
+
+    enc_v, enc_b = var_scope + "/encoder", bn_scope + "/encoder"
+    cin = in_ch
+    for _ in range(3):  # attention.py:105-109: three residual blocks
+        var(enc_v, (3, 3, 3, cin, nch), "mod_w"); var(enc_v, (nch,), "mod_b"); bn(enc_b, nch)   # conv1 + BN
+        var(enc_v, (3, 3, 3, nch, nch), "mod_w"); var(enc_v, (nch,), "mod_b"); bn(enc_b, nch)   # conv2 + BN
+        var(enc_v, (1, 1, 1, cin, nch), "mod_w"); var(enc_v, (nch,), "mod_b")                   # shortcut 1x1x1
+        bn(enc_b, nch)                                                                            # BN after the add
+        cin = nch
+    vi, bi = 0, 0
+    var(var_scope + "/output", (1, 1, 1, nch, num_classes), "mod_w"); var(var_scope + "/output", (num_classes,), "mod_b")
+    bn(bn_scope + "/output", num_classes)
+    return out
+
+
+def attention_param_specs(spec: VNetSpec, nch: int = MODULE_CHANNELS):
+    """V-Net (legacy flavour) + AttentionModule + OutputModule variables (train.py:271-310)."""
+    K = spec.num_classes
+    return (param_specs(spec)
+            + module_param_specs("attention/AttentionModule", "AttentionModule", K, K, nch)
+            + module_param_specs("output/output", "output", K, K, nch))
+
+
+def init_attention_params(spec: VNetSpec, seed: int = 42, module_seed: int = 43, nch: int = MODULE_CHANNELS):
+    p = init_params(spec, seed)
+    rng = np.random.Generator(np.random.PCG64(module_seed))
+    for name, shape, kind in attention_param_specs(spec, nch)[len(param_specs(spec)):]:
+        if kind == "mod_w":  # tf.truncated_normal(stddev=0.1): redraw beyond two sigma (attention.py:25-27)
+            w = rng.normal(0.0, 0.1, size=shape)
+            bad = np.abs(w) > 0.2
+            while bad.any():
+                w[bad] = rng.normal(0.0, 0.1, size=int(bad.sum()))
+                bad = np.abs(w) > 0.2
+            p[name] = w.astype(np.float32)
+        elif kind in ("mod_b", "beta", "moving_mean"):
+            p[name] = np.zeros(shape, np.float32)
+        else:  # gamma, moving_variance
+            p[name] = np.ones(shape, np.float32)
+    return p
+
+
+def _bn_inference(x, p, base):
+    """tf.layers.batch_normalization(training=False): the modules are fed train_phase=False even while
+    training (train.py:538-540), so they normalise with their never-updated moving statistics."""
+    return (x - p[base + "/moving_mean"]) * torch.rsqrt(p[base + "/moving_variance"] + BN_EPS) * p[base + "/gamma"] + p[base + "/beta"]
+
+
+def _conv3_valid_padded(x, w, b):
+    """tf.pad 1 voxel then tf.nn.conv3d(..., 'VALID') + b (attention.py:84-90,63-70) == SAME 3^3 convolution."""
+    y = F.conv3d(x.permute(0, 4, 1, 2, 3), w.permute(4, 3, 0, 1, 2), padding=1)
+    return y.permute(0, 2, 3, 4, 1) + b
+
+
+def module_forward(p, x, var_scope: str, bn_scope: str, collect=None):
+    """AttentionModule.GetNetwork / OutputModule.GetNetwork (attention.py:83-114, OutputModule.py:83-114)."""
+    vi, bi = [0], [0]
+
+    def var(scope):
+        n = "%s/Variable%s" % (scope, "" if vi[0] == 0 else "_%d" % vi[0])
+        vi[0] += 1
+        return p[n]
+
+    def bn(scope, t):
+        base = "%s/batch_normalization%s" % (scope, "" if bi[0] == 0 else "_%d" % bi[0])
+        bi[0] += 1
+        return _bn_inference(t, p, base)
+
+    ev, eb = var_scope + "/encoder", bn_scope + "/encoder"
+    for blk in range(3):
+        c1 = torch.relu(bn(eb, _conv3_valid_padded(x, var(ev), var(ev))))          # ConvActivate3d_block (keep_prob 1)
+        c2 = bn(eb, _conv3_valid_padded(c1, var(ev), var(ev)))                     # Conv3d_block
+        up = F.conv3d(x.permute(0, 4, 1, 2, 3), var(ev).permute(4, 3, 0, 1, 2)).permute(0, 2, 3, 4, 1) + var(ev)
+        x = torch.relu(bn(eb, c2 + up))
+        if collect is not None:
+            collect["%s/block_%d" % (bn_scope, blk + 1)] = x
+    vi[0], bi[0] = 0, 0
+    w, b = var(var_scope + "/output"), var(var_scope + "/output")
+    y = F.conv3d(x.permute(0, 4, 1, 2, 3), w.permute(4, 3, 0, 1, 2)).permute(0, 2, 3, 4, 1) + b
+    return bn(bn_scope + "/output", y)
+
+
+def attention_forward(params, images, spec: VNetSpec, collect=None):
+    """train.py:269-312: V-Net (VNet.py flavour, batch statistics) -> attention module -> (1 + softmax) gating ->
+    output module.  Returns dict of the named tensors and the V-Net's moving-statistic updates."""
+    logits_vnet, updates = forward(params, images, spec, collect=collect)
+    logits_att = module_forward(params, logits_vnet, "attention/AttentionModule", "AttentionModule", collect)
+    softmax_att = torch.softmax(logits_att, dim=-1)
+    logits_masked = (1.0 + softmax_att) * logits_vnet                                # train.py:302
+    logits_out = module_forward(params, logits_masked, "output/output", "output", collect)
+    return {"logits_vnet": logits_vnet, "logits_attention": logits_att, "softmax_attention": softmax_att,
+            "logits_masked": logits_masked, "logits_output": logits_out}, updates
+
+
+def attention_total_loss(out, labels, distmap, loss="jaccard", att_loss="l2", weights=(), alpha=1.0):
+    """train.py:351-418: segmentation loss on logits_output + attention loss against the distance map.
+    `loss`: train.py's own names 'sorensen_fg' (= --loss_function sorensen, train.py:373-377: foreground channel
+    against the label volume, mean over the batch), 'jaccard' and 'xent' (train.py:353-357,378-382; these two
+    coincide with model.py's forms), or any other Loss.Name of model.py:495-560 (used for K > 2, where
+    train.py's binary-only forms do not apply)."""
+    lo = out["logits_output"]
+    lab = labels.long()
+    if loss == "sorensen_fg":
+        o = torch.softmax(lo, dim=-1)[..., 1:2]
+        t = (lab == 1).to(lo.dtype).unsqueeze(-1)  # tf.cast(labels) for binary labels
+        inse = (o * t).sum(dim=(1, 2, 3))
+        dice = (2.0 * inse + 1e-5) / (o.sum(dim=(1, 2, 3)) + t.sum(dim=(1, 2, 3)) + 1e-5)
+        seg = 1.0 - dice.mean()
+    else:
+        seg = loss_from_logits(lo, lab, loss, weights, alpha)
+    sa = out["softmax_attention"]
+    d = distmap.to(lo.dtype)
+    if att_loss == "l2":     # train.py:387-393
+        att = torch.mean(torch.square(sa[..., 1] - d) * 100.0)
+    elif att_loss == "abs":  # train.py:394-399
+        att = torch.mean(torch.abs(sa - torch.stack([1.0 - d, d], dim=-1)))
+    elif att_loss in (None, "none"):
+        att = torch.zeros((), dtype=lo.dtype)
+    else:
+        raise SystemExit("Invalid loss function")
+    return att + seg, seg, att
+
+
+def attention_loss_and_grads(params_np, images, labels, distmap, spec, loss="jaccard", att_loss="l2", dtype=torch.float32,
+                             weights=(), alpha=1.0):
+    p = to_torch(params_np, dtype, requires_grad=True)
+    for k in p:  # module moving statistics are constants
+        if k.endswith(("moving_mean", "moving_variance")):
+            p[k].requires_grad_(False)
+    x = torch.from_numpy(np.ascontiguousarray(images)).to(dtype)
+    out, updates = attention_forward(p, x, spec)
+    total, seg, att = attention_total_loss(out, torch.from_numpy(np.ascontiguousarray(labels)),
+                                           torch.from_numpy(np.ascontiguousarray(distmap)), loss, att_loss, weights, alpha)
+    names = [k for k, t in p.items() if t.requires_grad]
+    grads = torch.autograd.grad(total, [p[k] for k in names], allow_unused=True)
+    g = OrderedDict((k, torch.zeros_like(p[k]) if t is None else t) for k, t in zip(names, grads))
+    return total.detach(), seg.detach(), att.detach(), {k: v.detach() for k, v in out.items()}, g, updates

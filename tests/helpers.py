@@ -68,3 +68,24 @@ def analytically_zero(name, spec):
     if i == n - 1:                   # CH_Q: beta of BN0 is re-normalised away
         return is_beta and k == 0
     return k == 0                    # CH_D: BN0 entirely dead
+
+
+def perturbed_attention_params(spec, nch, seed=42, weight_scale=1.0):
+    """V-Net + attention / output module variables with every term exercised: perturbed
+    gamma / beta / alpha / biases, and non-trivial *moving* statistics in the modules (their batch norms run in
+    inference mode, train.py:538-540).  `weight_scale` shrinks the sigma=0.1 truncated-normal module weights so
+    that a 64-channel module stays well conditioned (the reference init grows activations ~4x per conv)."""
+    from oracle import ref_vnet as R
+    p = R.init_attention_params(spec, seed, seed + 1, nch)
+    base = perturbed_params(spec, seed)
+    for k in base:
+        p[k] = base[k]
+    rng = np.random.Generator(np.random.PCG64(seed + 2))
+    for name, shape, kind in R.attention_param_specs(spec, nch)[len(R.param_specs(spec)):]:
+        if kind == "mod_w":
+            p[name] = (p[name] * weight_scale).astype(np.float32)
+        elif kind in ("mod_b", "beta", "moving_mean"):
+            p[name] = rng.normal(0, 0.2, shape).astype(np.float32)
+        elif kind in ("gamma", "moving_variance"):
+            p[name] = rng.uniform(0.6, 1.4, shape).astype(np.float32)
+    return p

@@ -193,3 +193,85 @@ def test_legacy_vnet_py_flavour_matches_oracle(emul_lib, convs, bottom, loss):
     for k, u in upd.items():
         assert np.abs(eng.get_param(k) - u.numpy()).max() < 1e-4 * max(1.0, float(u.abs().max())), k
     eng.close()
+
+
+@pytest.mark.parametrize("flavour,K,loss,att_loss", [
+    ("legacy", 2, "jaccard", "l2"),        # train.py defaults: VNet.py graph, --loss_function jaccard, --attention_loss_function l2
+    ("legacy", 2, "sorensen_fg", "abs"),   # train.py:373-377 + :394-398
+    ("networks", 3, "weighted_sorensen", "l2"),  # BASELINE config #5 shape: 2 modalities, 3 classes, model.py loss
+])
+def test_attention_gating_path_matches_oracle(emul_lib, flavour, K, loss, att_loss):
+    """V-Net -> AttentionModule -> (1 + softmax) gating -> OutputModule, Dice + attention loss
+    (train.py:281-312,351-418; attention.py:83-114; OutputModule.py:83-114)."""
+    from tests.helpers import perturbed_attention_params
+    from vnet_tensorflow_b200.synthetic import synth_patch
+    M = 2 if K == 3 else 1
+    spec = R.VNetSpec(num_classes=K, in_channels=M, num_channels=4, num_levels=2, num_convolutions=(1, 2),
+                      bottom_convolutions=1, flavour=flavour)
+    P, N, nch = 8, 2, 8
+    weights = (0.01, 0.1, 1.0) if "weighted" in loss else ()
+    params = perturbed_attention_params(spec, nch)
+    samples = [synth_patch(1234 + 100000 * i, P, M, K) for i in range(N)]
+    img, lab, dm = (np.stack([s[j] for s in samples], 0) for j in range(3))
+    eng = engine_for(spec, P, N, loss, weights, emul_lib, attention=True, attention_loss=att_loss, module_channels=nch)
+    assert list(eng.variables()) == [n for n, _, _ in R.attention_param_specs(spec, nch)]
+    eng.set_params(params)
+    tot, seg, att, out, go, upd = R.attention_loss_and_grads(params, img, lab, dm, spec, loss, att_loss, weights=weights)
+    logits, softmax, am = eng.forward(img)
+    assert rel_err(logits, out["logits_output"].numpy()) < 3e-5
+    assert int((am != R.predict(out["logits_output"]).numpy()).sum()) == 0
+    assert rel_err(eng.softmax_attention(N), out["softmax_attention"].numpy()) < 3e-5
+    assert rel_err(eng.read_tensor("masked_vnet", 0, N, K, (P, P, P)), out["logits_masked"].numpy()) < 3e-5
+    with pytest.raises(_ffi.VnbError):  # attention loss configured but no distance map fed
+        eng.loss(img, lab)
+    eng.set_distmap(dm)
+    l = eng.forward_backward(img, lab, update_moving_stats=True)
+    t3 = eng.losses()
+    assert abs(l - float(tot)) < 3e-6 * max(1.0, abs(float(tot)))
+    assert abs(t3[1] - float(seg)) < 3e-6 and abs(t3[2] - float(att)) < 3e-6 * max(1.0, abs(float(att)))
+    g = eng.get_grads()
+    assert set(g) == set(go)
+    scale = max(float(np.abs(v.numpy()).max()) for v in go.values())
+    for k, v in g.items():
+        ref = go[k].numpy()
+        if analytically_zero(k, spec):
+            assert np.abs(v).max() <= 1e-6 * scale + 1e-12, k
+            continue
+        assert np.abs(v - ref).max() <= 3e-4 * max(np.abs(ref).max(), 1e-3 * scale), k
+    for k, u in upd.items():  # only the V-Net's batch norms run UPDATE_OPS; the modules' moving statistics stay put
+        assert np.abs(eng.get_param(k) - u.numpy()).max() < 1e-4 * max(1.0, float(u.abs().max())), k
+    for k in params:
+        if k.startswith(("AttentionModule/", "output/")) and k.endswith(("moving_mean", "moving_variance")):
+            assert np.array_equal(eng.get_param(k), params[k]), k
+    eng.close()
+
+
+def test_attention_path_training_steps_follow_oracle(emul_lib):
+    """Adam over the gated network: V-Net, attention and output module variables all move as in the oracle."""
+    from tests.helpers import perturbed_attention_params
+    from vnet_tensorflow_b200.synthetic import synth_patch
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=4, num_levels=1, num_convolutions=(1,),
+                      bottom_convolutions=1, flavour="legacy")
+    P, N, nch = 8, 1, 4
+    params = perturbed_attention_params(spec, nch)
+    im, lb, dm = (a[None] for a in synth_patch(7, P, 1, 2))
+    eng = engine_for(spec, P, N, "jaccard", (), emul_lib, attention=True, attention_loss="l2", module_channels=nch,
+                     learning_rate=1e-3)
+    eng.set_params(params)
+    eng.set_distmap(dm)
+    p = {k: v.copy() for k, v in params.items()}
+    m = {k: torch.zeros(v.shape) for k, v in p.items()}
+    v2 = {k: torch.zeros(v.shape) for k, v in p.items()}
+    for step in range(2):
+        tot, _, _, _, go, upd = R.attention_loss_and_grads(p, im, lb, dm, spec, "jaccard", "l2")
+        le = eng.train_step(im, lb)
+        assert abs(le - float(tot)) < 1e-4 * max(1.0, abs(float(tot))), (step, le, float(tot))
+        lr = R.learning_rate(1e-3, step, 100.0, 0.99)
+        for k, g in go.items():
+            pk, m[k], v2[k] = R.adam_update(torch.from_numpy(p[k]), g, m[k], v2[k], step + 1, lr)
+            p[k] = pk.numpy()
+        for k, u in upd.items():
+            p[k] = u.numpy()
+    for k in ("attention/AttentionModule/encoder/Variable", "output/output/output/Variable_1", "output/encoder/batch_normalization_8/gamma"):
+        assert np.abs(eng.get_param(k) - p[k]).max() < 2e-4, k  # two Adam steps move each weight by ~2e-3
+    eng.close()

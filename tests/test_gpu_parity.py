@@ -249,3 +249,75 @@ def test_full_size_properties_128cube(gpu_lib):
     losses = [eng.train_step(img, lab) for _ in range(4)]
     assert losses[-1] < losses[0]
     eng.close()
+
+
+def _attention_case(spec, P, N, nch, weight_scale):
+    from tests.helpers import perturbed_attention_params
+    from vnet_tensorflow_b200.synthetic import synth_patch
+    params = perturbed_attention_params(spec, nch, weight_scale=weight_scale)
+    samples = [synth_patch(1234 + 100000 * i, P, spec.in_channels, spec.num_classes) for i in range(N)]
+    img, lab, dm = (np.stack([s[j] for s in samples], 0) for j in range(3))
+    return params, img, lab, dm
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("flavour,K,M,loss,att_loss", [("legacy", 2, 1, "jaccard", "l2"),
+                                                       ("legacy", 2, 1, "sorensen_fg", "abs"),
+                                                       ("networks", 3, 2, "weighted_sorensen", "l2")])
+def test_attention_gating_path(gpu_lib, flavour, K, M, loss, att_loss, precision):
+    """SURVEY §8 row a15 (BASELINE config #5): V-Net -> AttentionModule (64 ch) -> (1 + softmax) * logits ->
+    OutputModule (64 ch), Dice + attention loss, against the oracle restatement of train.py:281-312,351-418."""
+    convs = (1, 2, 2) if flavour == "legacy" else (1, 2)
+    spec = R.VNetSpec(num_classes=K, in_channels=M, num_channels=16, num_levels=len(convs), num_convolutions=convs,
+                      bottom_convolutions=2, flavour=flavour)
+    P, N, nch = 32, 2, 64
+    weights = (0.01, 0.1, 1.0) if "weighted" in loss else ()
+    params, img, lab, dm = _attention_case(spec, P, N, nch, weight_scale=0.25)
+    eng = engine_for(spec, P, N, loss, weights, gpu_lib, precision=precision, attention=True, attention_loss=att_loss)
+    assert list(eng.variables()) == [n for n, _, _ in R.attention_param_specs(spec, nch)]
+    eng.set_params(params)
+    tot, seg, att, out, go, upd = R.attention_loss_and_grads(params, img, lab, dm, spec, loss, att_loss, weights=weights)
+    logits, _, am = eng.forward(img)
+    tol = LOGIT_TOL[precision]
+    assert rel_err(logits, out["logits_output"].numpy()) < tol
+    assert rel_err(eng.softmax_attention(N), out["softmax_attention"].numpy()) < tol
+    flips = (am != R.predict(out["logits_output"]).numpy()).mean()
+    assert flips < (0.02 if precision == "bf16" else 1e-4)
+    eng.set_distmap(dm)
+    l = eng.forward_backward(img, lab, update_moving_stats=True)
+    t3 = eng.losses()
+    ltol = 5e-2 if precision == "bf16" else 2e-4
+    assert abs(l - float(tot)) < ltol * max(1.0, abs(float(tot)))
+    assert abs(t3[1] - float(seg)) < ltol and abs(t3[2] - float(att)) < ltol * max(1.0, abs(float(att)))
+    if precision == "bf16":
+        assert all(np.isfinite(v).all() for v in eng.get_grads().values())
+    else:
+        _check_grads(eng, {k: v.numpy() for k, v in go.items()}, spec, max(GRAD_TOL[precision], 3e-2), l2=True)
+    eng.close()
+
+
+def test_attention_path_trains(gpu_lib):
+    """Three Adam steps of the gated network follow the oracle's trajectory (losses, fp32 path)."""
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=16, num_levels=2, num_convolutions=(1, 2),
+                      bottom_convolutions=1, flavour="legacy")
+    P, N, nch = 16, 2, 64
+    params, img, lab, dm = _attention_case(spec, P, N, nch, weight_scale=0.25)
+    eng = engine_for(spec, P, N, "jaccard", (), gpu_lib, precision="fp32", attention=True, attention_loss="l2",
+                     learning_rate=1e-3)
+    eng.set_params(params)
+    eng.set_distmap(dm)
+    p = {k: v.copy() for k, v in params.items()}
+    m = {k: torch.zeros(v.shape) for k, v in p.items()}
+    v2 = {k: torch.zeros(v.shape) for k, v in p.items()}
+    for step in range(3):
+        tot, _, _, _, go, upd = R.attention_loss_and_grads(p, img, lab, dm, spec, "jaccard", "l2")
+        le = eng.train_step(img, lab)
+        assert abs(le - float(tot)) < 2e-3 * max(1.0, abs(float(tot))), (step, le, float(tot))
+        lr = R.learning_rate(1e-3, step, 100.0, 0.99)
+        for k, g in go.items():
+            pk, m[k], v2[k] = R.adam_update(torch.from_numpy(p[k]), g, m[k], v2[k], step + 1, lr)
+            p[k] = pk.numpy()
+        for k, u in upd.items():
+            p[k] = u.numpy()
+    assert eng.global_step == 3
+    eng.close()

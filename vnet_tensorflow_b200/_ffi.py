@@ -16,7 +16,9 @@ LOSSES = {
     "xent": 0, "weighted_xent": 1, "sorensen": 2, "weighted_sorensen": 3, "jaccard": 4,
     "weighted_jaccard": 5, "mixed_sorensen": 6, "mixed_weighted_sorensen": 7, "mixed_jaccard": 8,
     "mixed_weighted_jaccard": 9,
+    "sorensen_fg": 10,  # legacy train.py --loss_function sorensen (foreground channel only)
 }
+ATTENTION_LOSSES = {None: 0, "none": 0, "l2": 1, "abs": 2}
 OPTIMIZERS = {"Adam": 0, "SGD": 1, "Momentum": 2, "NesterovMomentum": 3}
 SLOT_VALUE, SLOT_GRAD, SLOT_ADAM_M, SLOT_ADAM_V = 0, 1, 2, 3
 
@@ -29,6 +31,7 @@ class VnbConfig(C.Structure):
         ("loss", C.c_int32), ("loss_weights", C.c_float * 8), ("loss_alpha", C.c_float),
         ("optimizer", C.c_int32), ("learning_rate", C.c_float), ("decay_factor", C.c_float),
         ("decay_steps", C.c_float), ("momentum", C.c_float), ("graph_flavour", C.c_int32),
+        ("attention", C.c_int32), ("attention_loss", C.c_int32), ("module_channels", C.c_int32),
     ]
 
 
@@ -69,6 +72,9 @@ _PROTOTYPES = {
     "vnb_event_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "vnb_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "vnb_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "vnb_set_distmap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "vnb_read_losses": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "vnb_read_softmax_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "vnb_sync": (C.c_int, [C.c_void_p]),
     "vnb_gpu_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "vnb_read_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]),

@@ -24,20 +24,25 @@ struct Dims {  // spatial extents of one sample
 // 5x5x5 stride-1 SAME convolution, forward form.  Input = channel concat of (in1, in2)
 // (tf.concat at networks.py:325 is never materialised).  Output channels [0,Co1) go to out1 and
 // [Co1, Co1+Co2) to out2 (used by dgrad of the concat convolution); each output may accumulate.
-// dgrad is this kernel run on dz with flipped+transposed weights (see flip_transpose_w5_kernel).
+// dgrad is this kernel run on dz with flipped+transposed weights (see flip_transpose_w_kernel).
 // -------------------------------------------------------------------------------------------------
 constexpr int kC5_TD = 4, kC5_TH = 4, kC5_TW = 16;         // output tile, one voxel per thread
 constexpr int kC5_CK = 8;                                   // input channels per smem chunk
 constexpr int kC5_CO = 16;                                  // output channels per thread
-constexpr int kC5_HV = (kC5_TD + 4) * (kC5_TH + 4) * (kC5_TW + 4);  // halo voxels = 1280
-constexpr int kC5_XS = kC5_HV + 1;                          // padded channel stride (bank conflicts)
-constexpr size_t kC5_SMEM = (static_cast<size_t>(kC5_CK) * kC5_XS + 125 * kC5_CK * kC5_CO) * sizeof(float);
+template <int KS> struct ConvRefGeom {                      // KS = 5 (V-Net, layers2.py:59-63) or 3 (attention.py:63-81)
+  static constexpr int R = KS / 2, TAPS = KS * KS * KS;
+  static constexpr int HH = kC5_TH + KS - 1, HW = kC5_TW + KS - 1;
+  static constexpr int HV = (kC5_TD + KS - 1) * HH * HW;  // halo voxels (1280 for KS = 5)
+  static constexpr int XS = HV + 1;                         // padded channel stride (bank conflicts)
+  static constexpr size_t SMEM = (static_cast<size_t>(kC5_CK) * XS + TAPS * kC5_CK * kC5_CO) * sizeof(float);
+};
+constexpr size_t kC5_SMEM = ConvRefGeom<5>::SMEM;
 
 struct Conv5Args {
   const float* in1;
   const float* in2;   // may be nullptr
   int C1, C2;         // channels of in1 / in2
-  const float* w;     // [125][C1+C2][Cout]
+  const float* w;     // [KS^3][C1+C2][Cout]
   const float* bias;  // [Cout] or nullptr
   const float* res;   // residual [V][Cout] added in the epilogue, or nullptr
   float* out1;
@@ -48,10 +53,12 @@ struct Conv5Args {
   int N;
 };
 
-__global__ void __launch_bounds__(256) conv5_ref_kernel(Conv5Args p) {
+template <int KS>
+__global__ void __launch_bounds__(256) conv_ref_kernel(Conv5Args p) {
+  using G = ConvRefGeom<KS>;
   VNB_DYN_SMEM(float, smem);
   float* xs = smem;                       // [CK][XS]
-  float* ws = smem + kC5_CK * kC5_XS;     // [125][CK][CO]
+  float* ws = smem + kC5_CK * G::XS;      // [TAPS][CK][CO]
   const int D = p.dims.D, H = p.dims.H, W = p.dims.W;
   const int tw_n = (W + kC5_TW - 1) / kC5_TW, th_n = (H + kC5_TH - 1) / kC5_TH;
   int tile = blockIdx.x;
@@ -73,31 +80,31 @@ __global__ void __launch_bounds__(256) conv5_ref_kernel(Conv5Args p) {
   for (int cb = 0; cb < Cin; cb += kC5_CK) {
     __syncthreads();
     // halo tile: xs[ci][hv], zero outside the volume (SAME padding) and beyond Cin
-    for (int i = t; i < kC5_HV * kC5_CK; i += 256) {
+    for (int i = t; i < G::HV * kC5_CK; i += 256) {
       const int ci = i % kC5_CK, hv = i / kC5_CK;
-      const int hw = hv % (kC5_TW + 4), hh = (hv / (kC5_TW + 4)) % (kC5_TH + 4), hd = hv / ((kC5_TW + 4) * (kC5_TH + 4));
-      const int gd = td0 + hd - 2, gh = th0 + hh - 2, gw = tw0 + hw - 2, cg = cb + ci;
+      const int hw = hv % G::HW, hh = (hv / G::HW) % G::HH, hd = hv / (G::HW * G::HH);
+      const int gd = td0 + hd - G::R, gh = th0 + hh - G::R, gw = tw0 + hw - G::R, cg = cb + ci;
       float val = 0.f;
       if (cg < Cin && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
         const long long vox = n * sample + (static_cast<long long>(gd) * H + gh) * W + gw;
         val = cg < p.C1 ? p.in1[vox * p.C1 + cg] : p.in2[vox * p.C2 + (cg - p.C1)];
       }
-      xs[ci * kC5_XS + hv] = val;
+      xs[ci * G::XS + hv] = val;
     }
-    for (int i = t; i < 125 * kC5_CK * kC5_CO; i += 256) {
+    for (int i = t; i < G::TAPS * kC5_CK * kC5_CO; i += 256) {
       const int co = i % kC5_CO, ci = (i / kC5_CO) % kC5_CK, tap = i / (kC5_CO * kC5_CK);
       const int cg = cb + ci;
       ws[i] = (cg < Cin && co0 + co < Cout) ? p.w[(static_cast<long long>(tap) * Cin + cg) * Cout + co0 + co] : 0.f;
     }
     __syncthreads();
-    for (int kd = 0; kd < 5; ++kd)
-      for (int kh = 0; kh < 5; ++kh)
-        for (int kw = 0; kw < 5; ++kw) {
-          const int tap = (kd * 5 + kh) * 5 + kw;
-          const int hv = ((ld + kd) * (kC5_TH + 4) + (lh + kh)) * (kC5_TW + 4) + lw + kw;
+    for (int kd = 0; kd < KS; ++kd)
+      for (int kh = 0; kh < KS; ++kh)
+        for (int kw = 0; kw < KS; ++kw) {
+          const int tap = (kd * KS + kh) * KS + kw;
+          const int hv = ((ld + kd) * G::HH + (lh + kh)) * G::HW + lw + kw;
 #pragma unroll
           for (int ci = 0; ci < kC5_CK; ++ci) {
-            const float x = xs[ci * kC5_XS + hv];
+            const float x = xs[ci * G::XS + hv];
             const float* wr = ws + (tap * kC5_CK + ci) * kC5_CO;
 #pragma unroll
             for (int j = 0; j < kC5_CO; ++j) acc[j] += x * wr[j];
@@ -123,28 +130,34 @@ __global__ void __launch_bounds__(256) conv5_ref_kernel(Conv5Args p) {
     }
   }
 }
+#define conv5_ref_kernel conv_ref_kernel<5>
 
-// wd[tap'][co][ci] = w[124 - tap'][ci][co]: dgrad(dz) = conv5(dz, wd) (flipped taps, swapped channels)
-__global__ void flip_transpose_w5_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cin, int Cout) {
-  const long long total = 125LL * Cin * Cout;
+// wd[tap'][co][ci] = w[TAPS-1 - tap'][ci][co]: dgrad(dz) = conv(dz, wd) (flipped taps, swapped channels)
+__global__ void flip_transpose_w_kernel(const float* __restrict__ w, float* __restrict__ wd, int Cin, int Cout, int taps) {
+  const long long total = static_cast<long long>(taps) * Cin * Cout;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int ci = static_cast<int>(i % Cin);
     const int co = static_cast<int>((i / Cin) % Cout);
     const int tap = static_cast<int>(i / (static_cast<long long>(Cin) * Cout));
-    wd[i] = w[(static_cast<long long>(124 - tap) * Cin + ci) * Cout + co];
+    wd[i] = w[(static_cast<long long>(taps - 1 - tap) * Cin + ci) * Cout + co];
   }
 }
 
 // -------------------------------------------------------------------------------------------------
-// 5x5x5 filter gradient: dw[tap][ci][co] += sum_v x[v + off(tap)][ci] * dz[v][co]
+// KS^3 filter gradient: dw[tap][ci][co] += sum_v x[v + off(tap)][ci] * dz[v][co]
 // grid: (voxel splits, (Cin/16 blocks) * (Cout/16 blocks)); thread = one (ci, co) pair with all
-// 125 taps in registers; block partial sums are added to dw with fp32 atomics (dw pre-zeroed).
+// KS^3 taps in registers; block partial sums are added to dw with fp32 atomics (dw pre-zeroed).
 // -------------------------------------------------------------------------------------------------
 constexpr int kW5_TD = 2, kW5_TH = 4, kW5_TW = 16;
-constexpr int kW5_HV = (kW5_TD + 4) * (kW5_TH + 4) * (kW5_TW + 4);  // 960
 constexpr int kW5_TV = kW5_TD * kW5_TH * kW5_TW;                    // 128
-constexpr size_t kW5_SMEM = (static_cast<size_t>(kW5_HV) * 16 + kW5_TV * 16) * sizeof(float);
+template <int KS> struct WgradRefGeom {
+  static constexpr int R = KS / 2, TAPS = KS * KS * KS;
+  static constexpr int HH = kW5_TH + KS - 1, HW = kW5_TW + KS - 1;
+  static constexpr int HV = (kW5_TD + KS - 1) * HH * HW;          // 960 for KS = 5
+  static constexpr size_t SMEM = (static_cast<size_t>(HV) * 16 + kW5_TV * 16) * sizeof(float);
+};
+constexpr size_t kW5_SMEM = WgradRefGeom<5>::SMEM;
 
 struct Wgrad5Args {
   const float* in1;
@@ -152,16 +165,18 @@ struct Wgrad5Args {
   int C1, C2;
   const float* dz;  // [V][Cout]
   int Cout;
-  float* dw;        // [125][C1+C2][Cout], pre-zeroed
+  float* dw;        // [KS^3][C1+C2][Cout], pre-zeroed
   Dims dims;
   int N;
   int tiles_per_block;
 };
 
-__global__ void __launch_bounds__(256) conv5_wgrad_ref_kernel(Wgrad5Args p) {
+template <int KS>
+__global__ void __launch_bounds__(256) conv_wgrad_ref_kernel(Wgrad5Args p) {
+  using G = WgradRefGeom<KS>;
   VNB_DYN_SMEM(float, smem);
   float* xs = smem;                 // [HV][16 ci]
-  float* ds = smem + kW5_HV * 16;   // [TV][16 co]
+  float* ds = smem + G::HV * 16;    // [TV][16 co]
   const int D = p.dims.D, H = p.dims.H, W = p.dims.W;
   const int Cin = p.C1 + p.C2, Cout = p.Cout;
   const int co_blocks = (Cout + 15) / 16;
@@ -171,9 +186,9 @@ __global__ void __launch_bounds__(256) conv5_wgrad_ref_kernel(Wgrad5Args p) {
   const long long tiles_per_sample = static_cast<long long>(tw_n) * th_n * td_n;
   const long long ntiles = tiles_per_sample * p.N;
   const long long sample = static_cast<long long>(D) * H * W;
-  float acc[125];
+  float acc[G::TAPS];
 #pragma unroll
-  for (int k = 0; k < 125; ++k) acc[k] = 0.f;
+  for (int k = 0; k < G::TAPS; ++k) acc[k] = 0.f;
 
   const long long first = static_cast<long long>(blockIdx.x) * p.tiles_per_block;
   for (long long tile = first; tile < first + p.tiles_per_block && tile < ntiles; ++tile) {
@@ -184,10 +199,10 @@ __global__ void __launch_bounds__(256) conv5_wgrad_ref_kernel(Wgrad5Args p) {
     const int th0 = static_cast<int>(r % th_n) * kW5_TH;
     const int td0 = static_cast<int>(r / th_n) * kW5_TD;
     __syncthreads();
-    for (int i = t; i < kW5_HV * 16; i += 256) {
+    for (int i = t; i < G::HV * 16; i += 256) {
       const int c = i % 16, hv = i / 16;
-      const int hw = hv % (kW5_TW + 4), hh = (hv / (kW5_TW + 4)) % (kW5_TH + 4), hd = hv / ((kW5_TW + 4) * (kW5_TH + 4));
-      const int gd = td0 + hd - 2, gh = th0 + hh - 2, gw = tw0 + hw - 2, cg = ci0 + c;
+      const int hw = hv % G::HW, hh = (hv / G::HW) % G::HH, hd = hv / (G::HW * G::HH);
+      const int gd = td0 + hd - G::R, gh = th0 + hh - G::R, gw = tw0 + hw - G::R, cg = ci0 + c;
       float val = 0.f;
       if (cg < Cin && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
         const long long vox = n * sample + (static_cast<long long>(gd) * H + gh) * W + gw;
@@ -210,22 +225,23 @@ __global__ void __launch_bounds__(256) conv5_wgrad_ref_kernel(Wgrad5Args p) {
     for (int tv = 0; tv < kW5_TV; ++tv) {
       const float g = ds[tv * 16 + co];
       const int lw = tv % kW5_TW, lh = (tv / kW5_TW) % kW5_TH, ld = tv / (kW5_TW * kW5_TH);
-      const float* xb = xs + ((ld * (kW5_TH + 4) + lh) * (kW5_TW + 4) + lw) * 16 + ci;
+      const float* xb = xs + ((ld * G::HH + lh) * G::HW + lw) * 16 + ci;
 #pragma unroll
-      for (int kd = 0; kd < 5; ++kd)
+      for (int kd = 0; kd < KS; ++kd)
 #pragma unroll
-        for (int kh = 0; kh < 5; ++kh)
+        for (int kh = 0; kh < KS; ++kh)
 #pragma unroll
-          for (int kw = 0; kw < 5; ++kw)
-            acc[(kd * 5 + kh) * 5 + kw] += xb[((kd * (kW5_TH + 4) + kh) * (kW5_TW + 4) + kw) * 16] * g;
+          for (int kw = 0; kw < KS; ++kw)
+            acc[(kd * KS + kh) * KS + kw] += xb[((kd * G::HH + kh) * G::HW + kw) * 16] * g;
     }
   }
   if (ci0 + ci < Cin && co0 + co < Cout) {
 #pragma unroll
-    for (int k = 0; k < 125; ++k)
+    for (int k = 0; k < G::TAPS; ++k)
       atomicAdd(p.dw + (static_cast<long long>(k) * Cin + ci0 + ci) * Cout + co0 + co, acc[k]);
   }
 }
+#define conv5_wgrad_ref_kernel conv_wgrad_ref_kernel<5>
 
 // -------------------------------------------------------------------------------------------------
 // 2x2x2 stride-2 kernels.  `fine` is [N][2Dc][2Hc][2Wc][CF], `coarse` is [N][Dc][Hc][Wc][CC],
@@ -368,6 +384,114 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
     for (int l = 0; l < lanes; ++l) tot += red[l * pairs + t];
     atomicAdd(dw + t, tot);
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// General 1x1x1 convolution (shortcut branch and output layer of the attention / output modules,
+// attention.py:98-100,111): a [V][Cin] x [Cin][Cout] matrix product, fp32 FMA.
+//   fprop : out[v][co]  = sum_ci x[v][ci] w[ci][co] + bias[co] + res[v][co]
+//   dgrad : same kernel with `transposed` = 1 (w read as [Cout][Cin]) and `accumulate`
+//   wgrad : dw[ci][co] += sum_v x[v][ci] dz[v][co]   (dw pre-zeroed, fp32 atomics across voxel splits)
+// Block = 64 voxels x 64 outputs; thread = one voxel x 16 consecutive outputs.
+// -------------------------------------------------------------------------------------------------
+struct Conv1Args {
+  const float* x;     // [V][K]   (K = reduction width)
+  const float* w;     // [K][M], or [M][K] when transposed
+  const float* bias;  // [M] or nullptr
+  const float* res;   // [V][M] or nullptr
+  float* out;         // [V][M]
+  long long V;
+  int K, M;
+  int transposed, accumulate;
+};
+
+__global__ void __launch_bounds__(256) conv1g_kernel(Conv1Args p) {
+  __shared__ float xs[64][65];
+  __shared__ float ws[64][64];
+  const int t = threadIdx.x, lv = t % 64, m0 = blockIdx.y * 64 + (t / 64) * 16;
+  const long long v0 = static_cast<long long>(blockIdx.x) * 64, v = v0 + lv;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int kb = 0; kb < p.K; kb += 64) {
+    const int kn = p.K - kb < 64 ? p.K - kb : 64;
+    __syncthreads();
+    for (int i = t; i < 64 * kn; i += 256) {
+      const int k = i % kn, r = i / kn;
+      xs[r][k] = (v0 + r < p.V) ? p.x[(v0 + r) * p.K + kb + k] : 0.f;
+    }
+    for (int i = t; i < 64 * 64; i += 256) {
+      const int m = i % 64, k = i / 64, mg = blockIdx.y * 64 + m;
+      float val = 0.f;
+      if (k < kn && mg < p.M)
+        val = p.transposed ? p.w[static_cast<long long>(mg) * p.K + kb + k] : p.w[static_cast<long long>(kb + k) * p.M + mg];
+      ws[k][m] = val;
+    }
+    __syncthreads();
+    const int mo = (t / 64) * 16;
+    for (int k = 0; k < kn; ++k) {
+      const float xv = xs[lv][k];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] += xv * ws[k][mo + j];
+    }
+  }
+  if (v >= p.V) return;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int m = m0 + j;
+    if (m >= p.M) break;
+    float y = acc[j];
+    if (p.bias) y += p.bias[m];
+    if (p.res) y += p.res[v * p.M + m];
+    float* o = p.out + v * p.M + m;
+    *o = p.accumulate ? *o + y : y;
+  }
+}
+
+// grid (voxel splits, ceil(Cin/64), ceil(Cout/64)); thread (ty, tx) owns a 4x4 block of the 64x64 tile
+__global__ void __launch_bounds__(256) conv1g_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                           float* __restrict__ dw, long long V, int Cin, int Cout,
+                                                           long long voxels_per_block) {
+  __shared__ float xs[32][64];
+  __shared__ float ds[32][64];
+  const int t = threadIdx.x, ty = t / 16, tx = t % 16;
+  const int ci0 = blockIdx.y * 64, co0 = blockIdx.z * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const long long vb = static_cast<long long>(blockIdx.x) * voxels_per_block;
+  const long long ve = vb + voxels_per_block < V ? vb + voxels_per_block : V;
+  for (long long v0 = vb; v0 < ve; v0 += 32) {
+    __syncthreads();
+    for (int i = t; i < 32 * 64; i += 256) {
+      const int c = i % 64, r = i / 64;
+      const bool in = v0 + r < ve;
+      xs[r][c] = (in && ci0 + c < Cin) ? x[(v0 + r) * Cin + ci0 + c] : 0.f;
+      ds[r][c] = (in && co0 + c < Cout) ? dz[(v0 + r) * Cout + co0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      float xa[4], db[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) xa[a] = xs[r][ty * 4 + a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) db[b] = ds[r][tx * 4 + b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] += xa[a] * db[b];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int ci = ci0 + ty * 4 + a, co = co0 + tx * 4 + b;
+      if (ci < Cin && co < Cout) atomicAdd(dw + static_cast<long long>(ci) * Cout + co, acc[a][b]);
+    }
 }
 
 }  // namespace vnb

@@ -38,8 +38,10 @@ enum Precision : int { PREC_FP32 = 0, PREC_BF16X3 = 1, PREC_BF16 = 2 };
 enum LossName : int {
   LOSS_XENT = 0, LOSS_WEIGHTED_XENT, LOSS_SORENSEN, LOSS_WEIGHTED_SORENSEN, LOSS_JACCARD,
   LOSS_WEIGHTED_JACCARD, LOSS_MIXED_SORENSEN, LOSS_MIXED_WEIGHTED_SORENSEN, LOSS_MIXED_JACCARD,
-  LOSS_MIXED_WEIGHTED_JACCARD
+  LOSS_MIXED_WEIGHTED_JACCARD,
+  LOSS_SORENSEN_FG  // legacy train.py:373-377: Dice of softmax[...,1] against the label volume
 };
+enum AttentionLoss : int { ATT_NONE = 0, ATT_L2 = 1, ATT_ABS = 2 };  // train.py:387-399
 enum OptName : int { OPT_ADAM = 0, OPT_SGD = 1, OPT_MOMENTUM = 2, OPT_NESTEROV = 3 };
 
 struct EngineConfig {
@@ -56,9 +58,12 @@ struct EngineConfig {
   float lr0 = 1e-2f, decay_factor = 0.99f, decay_steps = 100.f;
   float momentum = 0.9f;
   int flavour = 0;  // 0: networks.VNet (live path, model.py:428-438); 1: VNet.py legacy flavour (train.py:271-279)
+  int attention = 0;       // 1: AttentionModule -> (1 + softmax) gating -> OutputModule after the V-Net (train.py:281-312)
+  int attention_loss = ATT_NONE;
+  int module_channels = 64;  // attention.py:41 num_channels
 };
 
-enum UnitKind : int { U_INPUT_TILE = 0, U_CONV5, U_DOWN, U_UP, U_CONV1, U_ADD };
+enum UnitKind : int { U_INPUT_TILE = 0, U_CONV5, U_DOWN, U_UP, U_CONV1, U_ADD, U_CONV3, U_GATE };
 
 struct ParamEntry {
   std::string name;
@@ -87,6 +92,8 @@ struct Unit {
   int Cin1 = 0, Cin2 = 0, Cout = 0;
   int chain = CH_S;
   bool has_act = false, has_dropout = false;
+  bool relu = false;          // activation is ReLU (no alpha parameter): attention.py:51-52
+  bool bn_inference = false;  // BN normalises with its moving statistics (train_phase=False, train.py:538-540)
   // parameter offsets (floats) into the flat buffers; -1 = absent
   long long w_off = -1, b_off = -1, alpha_off = -1;
   long long gamma_off[3] = {-1, -1, -1}, beta_off[3] = {-1, -1, -1};
@@ -241,6 +248,23 @@ class Engine {
     return want_loss ? read_loss() : 0.f;
   }
   void sync() { VNB_CUDA_OK(cudaStreamSynchronize(stream_)); }
+  // distance map of the attention loss (train.py:176-179 distmap_placeholder), [N][D][H][W] in [0,1]
+  void set_distmap(const float* distmap, int N) {
+    if (!cfg_.attention) throw std::invalid_argument("set_distmap: the attention path is not enabled");
+    check_batch(N);
+    VNB_CUDA_OK(cudaMemcpyAsync(distmap_dev_, distmap, voxels(N) * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    distmap_valid_ = true;
+  }
+  void read_losses(float out[3]) {  // total, segmentation, attention (train.py:417)
+    VNB_CUDA_OK(cudaMemcpyAsync(out, loss_dev_, 3 * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+  }
+  // softmax_attention of the last forward pass (train.py:288), [N][D][H][W][K]
+  void read_softmax_attention(float* host, int N) {
+    if (!cfg_.attention) throw std::invalid_argument("the attention path is not enabled");
+    VNB_CUDA_OK(cudaMemcpyAsync(host, gate_soft_, voxels(N) * cfg_.num_classes * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+  }
 
   // debug access for tests: copy an activation (kind 0), its gradient (1) or the unit's pre-BN z (2)
   void read_tensor(const std::string& scope, int kind, float* host, size_t bytes, int N) {
@@ -380,8 +404,11 @@ class Engine {
     u.mv_off[k] = add_param(base + "/moving_variance", {C}, false);
   }
   // registers parameters in TF creation order: weights, biases, BNs, alpha
+  struct UnitNames {  // explicit variable names (tf.Variable auto-names of the attention / output modules)
+    std::string w, b, bn;
+  };
   int add_unit(int kind, const std::string& scope, int in1, int in2, int res, int Cout, Dims out_dims,
-               int chain, bool act, bool dropout, int bn_name_offset = 0) {
+               int chain, bool act, bool dropout, int bn_name_offset = 0, const UnitNames* names = nullptr) {
     Unit u;
     u.scope = scope;
     u.kind = kind;
@@ -396,6 +423,28 @@ class Engine {
     u.has_dropout = dropout;
     u.p_lo = n_train_;
     const long long Cin = u.Cin1 + u.Cin2;
+    if (names) {  // module unit: ReLU, inference-mode BN, weights / biases are anonymous tf.Variables
+      u.relu = act;
+      u.bn_inference = true;
+      const long long ks = kind == U_CONV3 ? 3 : 1;
+      u.w_off = add_param(names->w, {ks, ks, ks, Cin, Cout}, true);
+      u.w_count = static_cast<size_t>(ks * ks * ks * Cin * Cout);
+      u.b_off = add_param(names->b, {Cout}, true);
+      for (const char* leaf : {"/gamma", "/beta"}) {
+        const long long off = add_param(names->bn + leaf, {Cout}, true);
+        (leaf[1] == 'g' ? u.gamma_off[0] : u.beta_off[0]) = off;
+      }
+      u.mm_off[0] = add_param(names->bn + "/moving_mean", {Cout}, false);
+      u.mv_off[0] = add_param(names->bn + "/moving_variance", {Cout}, false);
+      u.out = add_act(Cout, out_dims);
+      units_.push_back(u);
+      return u.out;
+    }
+    if (kind == U_GATE) {  // no parameters, no batch norm
+      u.out = add_act(Cout, out_dims);
+      units_.push_back(u);
+      return u.out;
+    }
     if (kind == U_CONV5) {
       u.w_off = add_param(scope + "/weights", {5, 5, 5, Cin, Cout}, true);
       u.w_count = 125ull * Cin * Cout;
@@ -489,6 +538,14 @@ class Engine {
       d = up;
     }
     head_act_ = add_unit(U_CONV1, "vnet/output_layer", x, -1, -1, c.num_classes, full, CH_S, false, false);  // networks.py:298-303
+    if (c.attention) {  // train.py:281-312
+      vnet_logits_act_ = head_act_;
+      const int att = add_module("attention/AttentionModule", "AttentionModule", head_act_, full);  // attention.py:105-114
+      att_logits_act_ = att;
+      gate_unit_ = static_cast<int>(units_.size());
+      const int masked = add_unit(U_GATE, "masked_vnet", att, head_act_, -1, c.num_classes, full, CH_S, false, false);
+      head_act_ = add_module("output/output", "output", masked, full);                               // OutputModule.py:105-114
+    }
 
     // gradient buckets for the data-parallel exchange: ~1/8 of the parameters each, cut at unit
     // boundaries, listed in the order the backward pass completes them (last unit first)
@@ -523,6 +580,35 @@ class Engine {
         }
       }
     }
+  }
+
+  // AttentionModule / OutputModule (attention.py:83-114, OutputModule.py:83-114): three residual blocks of
+  // {3^3 conv + BN + ReLU, 3^3 conv + BN, 1^3 shortcut conv, add, BN, ReLU} and a 1^3 conv + BN to K classes.
+  // `vs` prefixes the anonymous tf.Variables (name scope + variable scope), `bs` the tf.layers BN variables.
+  int add_module(const std::string& vs, const std::string& bs, int x, Dims dims) {
+    const int nch = cfg_.module_channels;
+    int vi = 0, bi = 0;
+    auto names = [&](const std::string& sub) {
+      UnitNames n;
+      auto var = [&]() { return vs + "/" + sub + "/Variable" + (vi == 0 ? std::string() : "_" + std::to_string(vi)); };
+      n.w = var();
+      ++vi;
+      n.b = var();
+      ++vi;
+      n.bn = bs + "/" + sub + "/batch_normalization" + (bi == 0 ? std::string() : "_" + std::to_string(bi));
+      ++bi;
+      return n;
+    };
+    for (int blk = 0; blk < 3; ++blk) {
+      const std::string sc = bs + "/encoder/block_" + std::to_string(blk + 1);
+      UnitNames n1 = names("encoder"), n2 = names("encoder"), n3 = names("encoder");
+      const int c1 = add_unit(U_CONV3, sc + "/conv1", x, -1, -1, nch, dims, CH_S, true, false, 0, &n1);
+      const int c2 = add_unit(U_CONV3, sc + "/conv2", c1, -1, -1, nch, dims, CH_S, false, false, 0, &n2);
+      x = add_unit(U_CONV1, sc, x, -1, c2, nch, dims, CH_S, true, false, 0, &n3);
+    }
+    vi = bi = 0;
+    UnitNames no = names("output");
+    return add_unit(U_CONV1, bs + "/output", x, -1, -1, cfg_.num_classes, dims, CH_S, false, false, 0, &no);
   }
 
   template <class T>
@@ -569,6 +655,7 @@ class Engine {
     for (Unit& u : units_) {
       const Act& o = acts_[u.out];
       const size_t n = static_cast<size_t>(voxels_of(o.dims, NB)) * o.C;
+      if (u.kind == U_GATE) continue;
       u.z = (u.kind == U_INPUT_TILE) ? acts_[u.in1].a : dev_alloc<float>(n);
       u.mean = dev_alloc<double>(u.Cout);
       u.var = dev_alloc<double>(u.Cout);
@@ -577,7 +664,14 @@ class Engine {
       u.P = dev_alloc<float>(u.Cout);
       u.Q = dev_alloc<float>(u.Cout);
       u.S = dev_alloc<float>(u.Cout);
-      if (u.kind == U_CONV5) max_w5 = std::max(max_w5, u.w_count);
+      if (u.kind == U_CONV5 || u.kind == U_CONV3) max_w5 = std::max(max_w5, u.w_count);
+    }
+    zero_alpha_ = dev_alloc<float>(maxC);
+    VNB_CUDA_OK(cudaMemset(zero_alpha_, 0, maxC * sizeof(float)));
+    if (cfg_.attention) {
+      gate_soft_ = dev_alloc<float>(voxels(NB) * cfg_.num_classes);
+      distmap_dev_ = dev_alloc<float>(voxels(NB));
+      att_partial_ = dev_alloc<double>(kMaxRedBlocks);
     }
     partial_ = dev_alloc<double>(static_cast<size_t>(kMaxRedBlocks) * 3 * std::max(maxC, 4 * kMaxClasses) + 64);
     wflip_ = dev_alloc<float>(max_w5);
@@ -656,10 +750,11 @@ class Engine {
     const int l = cfg_.loss;
     lc.jaccard = (l == LOSS_JACCARD || l == LOSS_WEIGHTED_JACCARD || l == LOSS_MIXED_JACCARD || l == LOSS_MIXED_WEIGHTED_JACCARD);
     lc.use_dice = !(l == LOSS_XENT || l == LOSS_WEIGHTED_XENT);
+    lc.fg_only = (l == LOSS_SORENSEN_FG);
     lc.weighted_dice = (l == LOSS_WEIGHTED_SORENSEN || l == LOSS_WEIGHTED_JACCARD || l == LOSS_MIXED_WEIGHTED_SORENSEN || l == LOSS_MIXED_WEIGHTED_JACCARD);
-    lc.use_xent = (l == LOSS_XENT || l == LOSS_WEIGHTED_XENT || l >= LOSS_MIXED_SORENSEN);
+    lc.use_xent = (l == LOSS_XENT || l == LOSS_WEIGHTED_XENT || (l >= LOSS_MIXED_SORENSEN && l <= LOSS_MIXED_WEIGHTED_JACCARD));
     lc.weighted_xent = (l == LOSS_WEIGHTED_XENT || l == LOSS_MIXED_WEIGHTED_SORENSEN || l == LOSS_MIXED_WEIGHTED_JACCARD);
-    lc.xent_alpha = (l >= LOSS_MIXED_SORENSEN) ? cfg_.loss_alpha : 1.0f;
+    lc.xent_alpha = (l >= LOSS_MIXED_SORENSEN && l <= LOSS_MIXED_WEIGHTED_JACCARD) ? cfg_.loss_alpha : 1.0f;
     lc.smooth = 1e-5f;
     for (int i = 0; i < kMaxClasses; ++i) lc.w[i] = cfg_.loss_weights[i];
     return lc;
@@ -697,6 +792,24 @@ class Engine {
       p.N = N;
       ProfScope ps(*this, 0, conv5_flops(u, N));
       launch_conv5(p);
+    } else if (u.kind == U_CONV3) {
+      Conv5Args p;
+      p.in1 = x1.a;
+      p.in2 = nullptr;
+      p.C1 = u.Cin1;
+      p.C2 = 0;
+      p.w = params_ + u.w_off;
+      p.bias = bias;
+      p.res = nullptr;
+      p.out1 = u.z;
+      p.out2 = nullptr;
+      p.Co1 = u.Cout;
+      p.Co2 = 0;
+      p.acc1 = p.acc2 = 0;
+      p.dims = o.dims;
+      p.N = N;
+      ProfScope ps(*this, 0, conv5_flops(u, N));
+      launch_conv3(p);
     } else if (u.kind == U_DOWN || u.kind == U_UP) {
       K2Args p{};
       p.w = params_ + u.w_off;
@@ -722,12 +835,52 @@ class Engine {
       const long long n = voxels_of(o.dims, N) * u.Cout;
       VNB_LAUNCH(add2_kernel, grid_for(n, 256), 256, 0, stream_, (const float*)x1.a, (const float*)acts_[u.res].a, u.z, n);
       ++launches_;
+    } else if (u.kind == U_CONV1 && conv1_general(u)) {
+      Conv1Args p;
+      p.x = x1.a;
+      p.w = params_ + u.w_off;
+      p.bias = bias;
+      p.res = u.res >= 0 ? acts_[u.res].a : nullptr;
+      p.out = u.z;
+      p.V = voxels_of(o.dims, N);
+      p.K = u.Cin1;
+      p.M = u.Cout;
+      p.transposed = 0;
+      p.accumulate = 0;
+      launch_conv1g(p);
     } else if (u.kind == U_CONV1) {
       const long long V = voxels_of(o.dims, N);
       VNB_LAUNCH(conv1_fprop_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, (const float*)x1.a,
                  (const float*)(params_ + u.w_off), bias, u.z, V, u.Cin1, u.Cout);
       ++launches_;
     }
+  }
+  // the small-shape 1^3 kernels serve the V-Net head; anything with a residual or a wide product goes general
+  static bool conv1_general(const Unit& u) { return u.res >= 0 || u.Cin1 * u.Cout > 256; }
+  void launch_conv1g(const Conv1Args& p) {
+    dim3 grid(static_cast<unsigned>((p.V + 63) / 64), (p.M + 63) / 64);
+    VNB_LAUNCH(conv1g_kernel, grid, 256, 0, stream_, p);
+    ++launches_;
+  }
+  void launch_conv3(const Conv5Args& p) {
+    const Dims& d = p.dims;
+    const int tiles = ((d.W + kC5_TW - 1) / kC5_TW) * ((d.H + kC5_TH - 1) / kC5_TH) * ((d.D + kC5_TD - 1) / kC5_TD);
+    dim3 grid(tiles, (p.Co1 + p.Co2 + kC5_CO - 1) / kC5_CO, p.N);
+    launch_conv5_attr_once();
+    VNB_LAUNCH(conv_ref_kernel<3>, grid, 256, ConvRefGeom<3>::SMEM, stream_, p);
+    ++launches_;
+  }
+  GateArgs gate_args(const Unit& u, int N) {
+    GateArgs g;
+    g.att = acts_[u.in1].a;
+    g.vnet = acts_[u.in2].a;
+    g.soft = gate_soft_;
+    g.masked = acts_[u.out].a;
+    g.distmap = (cfg_.attention_loss != ATT_NONE && distmap_valid_) ? distmap_dev_ : nullptr;
+    g.V = voxels_of(acts_[u.out].dims, N);
+    g.K = u.Cout;
+    g.att_loss = cfg_.attention_loss;
+    return g;
   }
   void launch_conv5(const Conv5Args& p) {
     const Dims& d = p.dims;
@@ -753,8 +906,17 @@ class Engine {
       Unit& u = units_[ui];
       const Act& o = acts_[u.out];
       const long long V = voxels_of(o.dims, N);
-      int nblk, nq_stride = 2;
-      if (u.kind == U_INPUT_TILE) {
+      int nblk = 1, nq_stride = 2;
+      if (u.kind == U_GATE) {  // train.py:295-302; also the attention-loss partial sums
+        const GateArgs g = gate_args(u, N);
+        att_nblk_ = grid_for(g.V, 256, kMaxRedBlocks);
+        VNB_LAUNCH(gate_fwd_kernel, att_nblk_, 256, 0, stream_, g, att_partial_);
+        ++launches_;
+        continue;
+      }
+      if (u.bn_inference) {
+        run_conv_fprop(u, N);
+      } else if (u.kind == U_INPUT_TILE) {
         nblk = grid_for(V, 256, kMaxRedBlocks);
         VNB_LAUNCH(image_stats_kernel, nblk, 256, 0, stream_, (const float*)u.z, V, partial_);
       } else {
@@ -776,7 +938,7 @@ class Engine {
       }
       VNB_LAUNCH(bn_finalize_fwd_kernel, u.Cout, 128, 0, stream_, (const double*)partial_, nblk, nq_stride,
                  u.Cout, static_cast<double>(V), u.chain, bn_params(u), u.kind == U_INPUT_TILE ? 1 : 0,
-                 update_moving ? 1 : 0, u.mean, u.var, u.scale, u.shift);
+                 update_moving ? 1 : 0, u.mean, u.var, u.scale, u.shift, u.bn_inference ? 1 : 0);
       ApplyArgs ap;
       ap.z = u.z;
       ap.a = acts_[u.out].a;
@@ -784,7 +946,7 @@ class Engine {
       ap.a_lo = acts_[u.out].a_lo;
       ap.scale = u.scale;
       ap.shift = u.shift;
-      ap.alpha = u.has_act ? params_ + u.alpha_off : nullptr;
+      ap.alpha = u.relu ? zero_alpha_ : (u.has_act ? params_ + u.alpha_off : nullptr);
       ap.total = V * u.Cout;
       ap.C = u.Cout;
       ap.tiled_input = u.kind == U_INPUT_TILE ? 1 : 0;
@@ -806,8 +968,16 @@ class Engine {
     dim3 grid(nblk, N);
     VNB_LAUNCH(softmax_loss_fwd_kernel, grid, 256, 0, stream_, (const float*)acts_[head_act_].a,
                (const int32_t*)labels_dev_, Vn, lc, (float*)nullptr, (long long*)nullptr, loss_partial_);
-    VNB_LAUNCH(loss_finalize_kernel, 1, 64, 0, stream_, (const double*)loss_partial_, N, nblk, Vn, lc, terms_dev_, coef_dev_, loss_dev_);
+    const bool att = cfg_.attention && cfg_.attention_loss != ATT_NONE;
+    if (att && !distmap_valid_) throw std::invalid_argument("attention loss configured but no distance map uploaded (vnb_set_distmap)");
+    VNB_LAUNCH(loss_finalize_kernel, 1, 64, 0, stream_, (const double*)loss_partial_, N, nblk, Vn, lc, terms_dev_, coef_dev_, loss_dev_,
+               (const double*)att_partial_, att ? att_nblk_ : 0, att_elements(N));
     launches_ += 2;
+  }
+
+  // number of elements the attention loss averages over (train.py:392,398)
+  double att_elements(int N) const {
+    return static_cast<double>(voxels(N)) * (cfg_.attention_loss == ATT_ABS ? 2.0 : 1.0);
   }
 
   // ---- backward -------------------------------------------------------------------------------
@@ -822,18 +992,27 @@ class Engine {
       Unit& u = units_[ui];
       Act& o = acts_[u.out];
       const long long V = voxels_of(o.dims, N);
+      if (u.kind == U_GATE) {
+        const GateArgs g = gate_args(u, N);
+        VNB_LAUNCH(gate_bwd_kernel, grid_for(g.V, 256, kMaxRedBlocks), 256, 0, stream_, g, (const float*)o.d, acts_[u.in1].d,
+                   u.in1_accumulate ? 1 : 0, acts_[u.in2].d, u.in2_accumulate ? 1 : 0,
+                   g.distmap ? static_cast<float>(1.0 / att_elements(N)) : 0.f);
+        ++launches_;
+        notify_bucket(ui);
+        continue;
+      }
       BwdArgs b;
       b.z = u.z;
       b.d = o.d;
-      b.d_hi = (u.kind == U_CONV5) ? o.d_hi : nullptr;
-      b.d_lo = (u.kind == U_CONV5) ? o.d_lo : nullptr;
+      b.d_hi = (u.kind == U_CONV5 || u.kind == U_CONV3) ? o.d_hi : nullptr;
+      b.d_lo = (u.kind == U_CONV5 || u.kind == U_CONV3) ? o.d_lo : nullptr;
       b.res_grad = u.res >= 0 ? acts_[u.res].d : nullptr;
       b.res_accumulate = u.res_accumulate ? 1 : 0;
       b.res_grad2 = u.kind == U_ADD ? acts_[u.in1].d : nullptr;
       b.res_accumulate2 = u.in1_accumulate ? 1 : 0;
       b.scale = u.scale;
       b.shift = u.shift;
-      b.alpha = u.has_act ? params_ + u.alpha_off : nullptr;
+      b.alpha = u.relu ? zero_alpha_ : (u.has_act ? params_ + u.alpha_off : nullptr);
       b.mean = u.mean;
       b.P = u.P;
       b.Q = u.Q;
@@ -865,9 +1044,11 @@ class Engine {
         gp.dgamma[k] = on ? grads_ + u.gamma_off[k] : nullptr;
         gp.dbeta[k] = on ? grads_ + u.beta_off[k] : nullptr;
       }
-      gp.dalpha = u.has_act ? grads_ + u.alpha_off : nullptr;
+      gp.dalpha = (u.has_act && !u.relu) ? grads_ + u.alpha_off : nullptr;
+      gp.dbias = u.bn_inference ? grads_ + u.b_off : nullptr;
       VNB_LAUNCH(bn_finalize_bwd_kernel, u.Cout, 128, 0, stream_, (const double*)partial_, nblk, u.Cout,
-                 static_cast<double>(V), u.chain, bn_params(u), (const double*)u.var, gp, u.P, u.Q, u.S);
+                 static_cast<double>(V), u.chain, bn_params(u), (const double*)u.var, gp, u.P, u.Q, u.S,
+                 u.bn_inference ? 1 : 0);
       ++launches_;
       if (u.kind == U_INPUT_TILE) {  // image needs no gradient
         notify_bucket(ui);
@@ -894,15 +1075,63 @@ class Engine {
     float* dw = grads_ + u.w_off;
     const float* dz = o.d;
     VNB_CUDA_OK(cudaMemsetAsync(dw, 0, u.w_count * sizeof(float), stream_));
-    VNB_CUDA_OK(cudaMemsetAsync(grads_ + u.b_off, 0, u.Cout * sizeof(float), stream_));
-    if (u.kind == U_CONV5) {
+    if (!u.bn_inference) VNB_CUDA_OK(cudaMemsetAsync(grads_ + u.b_off, 0, u.Cout * sizeof(float), stream_));
+    if (u.kind == U_CONV3) {
+      if (u.need_dgrad) {
+        VNB_LAUNCH(flip_transpose_w_kernel, grid_for(static_cast<long long>(u.w_count), 256), 256, 0, stream_,
+                   (const float*)(params_ + u.w_off), wflip_, u.Cin1, u.Cout, 27);
+        ++launches_;
+        Conv5Args p;
+        p.in1 = dz;
+        p.in2 = nullptr;
+        p.C1 = u.Cout;
+        p.C2 = 0;
+        p.w = wflip_;
+        p.bias = nullptr;
+        p.res = nullptr;
+        p.out1 = x1.d;
+        p.Co1 = u.Cin1;
+        p.acc1 = u.in1_accumulate ? 1 : 0;
+        p.out2 = nullptr;
+        p.Co2 = 0;
+        p.acc2 = 0;
+        p.dims = o.dims;
+        p.N = N;
+        ProfScope ps(*this, 0, conv5_flops(u, N));
+        launch_conv3(p);
+      }
+      Wgrad5Args w;
+      w.in1 = x1.a;
+      w.in2 = nullptr;
+      w.C1 = u.Cin1;
+      w.C2 = 0;
+      w.dz = dz;
+      w.Cout = u.Cout;
+      w.dw = dw;
+      w.dims = o.dims;
+      w.N = N;
+      const Dims& d = o.dims;
+      const long long ntiles = static_cast<long long>((d.W + kW5_TW - 1) / kW5_TW) * ((d.H + kW5_TH - 1) / kW5_TH) *
+                               ((d.D + kW5_TD - 1) / kW5_TD) * N;
+      const int pairs = ((u.Cin1 + 15) / 16) * ((u.Cout + 15) / 16);
+      long long splits = std::max<long long>(1, std::min<long long>(ntiles, (2 * 1184 + pairs - 1) / pairs));
+      w.tiles_per_block = static_cast<int>((ntiles + splits - 1) / splits);
+      splits = (ntiles + w.tiles_per_block - 1) / w.tiles_per_block;
+      dim3 grid(static_cast<unsigned>(splits), pairs);
+      launch_conv5_attr_once();
+      {
+        ProfScope ps(*this, 1, conv5_flops(u, N));
+        VNB_LAUNCH(conv_wgrad_ref_kernel<3>, grid, 256, WgradRefGeom<3>::SMEM, stream_, w);
+      }
+      ++launches_;
+    } else if (u.kind == U_CONV5) {
       const int Cin = u.Cin1 + u.Cin2;
       const bool tc = cfg_.precision != PREC_FP32;
       if (tc && u.need_dgrad && u.tc.dgrad.valid && !getenv("VNB_DEBUG_NO_TC_DGRAD")) {
         tc_run_dgrad(u, N);
       } else if (u.need_dgrad) {
-        VNB_LAUNCH(flip_transpose_w5_kernel, grid_for(static_cast<long long>(u.w_count), 256), 256, 0, stream_,
-                   (const float*)(params_ + u.w_off), wflip_, Cin, u.Cout);
+        VNB_LAUNCH(flip_transpose_w_kernel, grid_for(static_cast<long long>(u.w_count), 256), 256, 0, stream_,
+                   (const float*)(params_ + u.w_off), wflip_, Cin, u.Cout, 125);
         ++launches_;
         Conv5Args p;
         p.in1 = dz;
@@ -981,6 +1210,29 @@ class Engine {
       }
       p.bias = nullptr;
       launch_k2_wgrad(p);
+    } else if (u.kind == U_CONV1 && conv1_general(u)) {
+      const long long V = voxels_of(o.dims, N);
+      if (u.need_dgrad) {
+        Conv1Args p;
+        p.x = dz;
+        p.w = params_ + u.w_off;  // [Cin][Cout] read as the transposed product
+        p.bias = nullptr;
+        p.res = nullptr;
+        p.out = x1.d;
+        p.V = V;
+        p.K = u.Cout;
+        p.M = u.Cin1;
+        p.transposed = 1;
+        p.accumulate = u.in1_accumulate ? 1 : 0;
+        launch_conv1g(p);
+      }
+      const int gy = (u.Cin1 + 63) / 64, gz = (u.Cout + 63) / 64;
+      long long splits = std::max<long long>(1, std::min<long long>((V + 255) / 256, (4 * 148 + gy * gz - 1) / (gy * gz)));
+      const long long vpb = ((V + splits - 1) / splits + 31) / 32 * 32;
+      splits = (V + vpb - 1) / vpb;
+      dim3 grid(static_cast<unsigned>(splits), gy, gz);
+      VNB_LAUNCH(conv1g_wgrad_kernel, grid, 256, 0, stream_, (const float*)x1.a, dz, dw, V, u.Cin1, u.Cout, vpb);
+      ++launches_;
     } else if (u.kind == U_CONV1) {
       const long long V = voxels_of(o.dims, N);
       if (u.need_dgrad) {
@@ -1036,8 +1288,8 @@ class Engine {
     }
     ++launches_;
   }
-  double conv5_flops(const Unit& u, int N) const {  // 2*MAC of one 5^3 pass (fprop = dgrad = wgrad)
-    return 2.0 * 125.0 * (u.Cin1 + u.Cin2) * u.Cout * static_cast<double>(voxels_of(acts_[u.out].dims, N));
+  double conv5_flops(const Unit& u, int N) const {  // 2*MAC of one 5^3 (or 3^3) pass (fprop = dgrad = wgrad)
+    return 2.0 * (u.kind == U_CONV3 ? 27.0 : 125.0) * (u.Cin1 + u.Cin2) * u.Cout * static_cast<double>(voxels_of(acts_[u.out].dims, N));
   }
   void launch_conv5_attr_once() {
 #ifndef VNB_EMULATE
@@ -1045,6 +1297,8 @@ class Engine {
     if (!attr_set) {
       VNB_CUDA_OK(cudaFuncSetAttribute(conv5_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5_SMEM));
       VNB_CUDA_OK(cudaFuncSetAttribute(conv5_wgrad_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kW5_SMEM));
+      VNB_CUDA_OK(cudaFuncSetAttribute(conv_ref_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvRefGeom<3>::SMEM));
+      VNB_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_ref_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgradRefGeom<3>::SMEM));
       attr_set = true;
     }
 #endif
@@ -1073,6 +1327,11 @@ class Engine {
   std::function<void(int)> grad_hook_;
   size_t n_train_ = 0, n_state_ = 0;
   int image_act_ = -1, head_act_ = -1;
+  int vnet_logits_act_ = -1, att_logits_act_ = -1, gate_unit_ = -1;
+  float *zero_alpha_ = nullptr, *gate_soft_ = nullptr, *distmap_dev_ = nullptr;
+  double* att_partial_ = nullptr;
+  int att_nblk_ = 0;
+  bool distmap_valid_ = false;
   float *params_ = nullptr, *grads_ = nullptr, *adam_m_ = nullptr, *adam_v_ = nullptr, *state_ = nullptr;
   double* partial_ = nullptr;
   float* wflip_ = nullptr;

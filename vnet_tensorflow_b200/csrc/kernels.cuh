@@ -150,8 +150,18 @@ __global__ void bn_finalize_fwd_kernel(const double* __restrict__ partial, int n
                                        double count, int chain, BnParams bp, int single_channel_stats,
                                        int update_moving, double* __restrict__ mean_out,
                                        double* __restrict__ var_out, float* __restrict__ scale_out,
-                                       float* __restrict__ shift_out) {
+                                       float* __restrict__ shift_out, int inference = 0) {
   const int c = blockIdx.x;  // one block per channel; threads sum the per-block partials in a fixed order
+  if (inference) {  // training=False: normalise with the moving statistics (attention.py:69 fed train_phase=False)
+    if (threadIdx.x != 0) return;
+    const double mu = bp.moving_mean[0][c], var = bp.moving_var[0][c];
+    const double A = static_cast<double>(bp.gamma[0][c]) * rsqrt(var + static_cast<double>(kBnEps));
+    mean_out[c] = mu;
+    var_out[c] = var;
+    scale_out[c] = static_cast<float>(A);
+    shift_out[c] = static_cast<float>(static_cast<double>(bp.beta[0][c]) - A * mu);
+    return;
+  }
   const int pc = single_channel_stats ? 0 : c;
   const int PC = single_channel_stats ? 1 : C;
   __shared__ double fin_red[2][128];
@@ -292,12 +302,13 @@ struct BnGradPtrs {  // where the parameter gradients go (flat gradient buffer),
   float* dgamma[3];
   float* dbeta[3];
   float* dalpha;
+  float* dbias;  // only with inference-mode BN (batch statistics make the conv bias gradient exactly 0)
 };
 
 __global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int nblk, int C, double count,
                                        int chain, BnParams bp, const double* __restrict__ var,
                                        BnGradPtrs gp, float* __restrict__ P, float* __restrict__ Q,
-                                       float* __restrict__ S) {
+                                       float* __restrict__ S, int inference = 0) {
   const int c = blockIdx.x;  // one block per channel
   __shared__ double fin_red[3][128];
   double p0 = 0, p1 = 0, p2 = 0;
@@ -324,6 +335,16 @@ __global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int n
     bet[k] = bp.beta[k][c];
   }
   const ChainOut o = chain_eval(chain, var[c], gam, bet, static_cast<double>(kBnEps));
+  if (inference) {  // statistics are constants: dz = A*g, dgamma = R1*rsqrt(var+eps), dbeta = R0, dbias = A*R0
+    P[c] = static_cast<float>(o.A.v);
+    Q[c] = 0.f;
+    S[c] = 0.f;
+    if (gp.dgamma[0]) gp.dgamma[0][c] = static_cast<float>(R1 * o.A.d[1]);
+    if (gp.dbeta[0]) gp.dbeta[0][c] = static_cast<float>(R0);
+    if (gp.dbias) gp.dbias[c] = static_cast<float>(o.A.v * R0);
+    if (gp.dalpha) gp.dalpha[c] = static_cast<float>(Ra);
+    return;
+  }
   P[c] = static_cast<float>(o.A.v);
   Q[c] = static_cast<float>(-o.A.v * R0 / count);
   S[c] = static_cast<float>(2.0 * o.A.d[0] * R1 / count);
@@ -367,6 +388,7 @@ struct LossCfg {
   int use_dice;           // dice term present
   int use_xent;           // cross-entropy term present
   int weighted_xent;      // class-weighted cross entropy
+  int fg_only;            // legacy train.py:373-377 'sorensen': Dice of channel 1 against the label volume only
   float xent_alpha;       // multiplier of the x-ent term (Loss.Alpha for mixed_*, 1 for pure)
   float smooth;           // 1e-5
   float w[kMaxClasses];   // Loss.Weights
@@ -429,7 +451,8 @@ __global__ void softmax_loss_fwd_kernel(const float* __restrict__ logits, const 
 // terms_out [N][K][4]; coef_out [N][K][3] = (dLoss/dI, dLoss/dL, dLoss/dX-per-voxel-weight)
 __global__ void loss_finalize_kernel(const double* __restrict__ partial, int N, int nblk, long long Vn,
                                      LossCfg cfg, double* __restrict__ terms_out, float* __restrict__ coef_out,
-                                     float* __restrict__ loss_out) {
+                                     float* __restrict__ loss_out, const double* __restrict__ att_partial = nullptr,
+                                     int att_nblk = 0, double att_div = 1.0) {
   const int K = cfg.K;
   const int pairs = N * K;
   for (int pr = threadIdx.x; pr < pairs; pr += blockDim.x) {
@@ -447,7 +470,16 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partial, int N, 
   for (int i = 0; i < pairs * 3; ++i) coef_out[i] = 0.f;
   if (cfg.use_dice) {
     double dice = 0.0;
-    if (cfg.weighted_dice) {  // model.py:70-75
+    if (cfg.fg_only) {  // train.py:373-377: dice_coe(softmax[...,1:2], labels) averaged over the batch only
+      for (int n = 0; n < N; ++n) {
+        const double* t = terms_out + (static_cast<size_t>(n) * K + 1) * 4;
+        const double num = 2.0 * t[0] + s, den = t[1] + t[2] + s;
+        dice += num / den / N;
+        float* co = coef_out + (static_cast<size_t>(n) * K + 1) * 3;
+        co[0] = static_cast<float>(-(2.0 / den) / N);
+        co[1] = static_cast<float>((num / (den * den)) / N);
+      }
+    } else if (cfg.weighted_dice) {  // model.py:70-75
       for (int n = 0; n < N; ++n) {
         double num = 0.0, den = 0.0;
         for (int c = 0; c < K; ++c) {
@@ -486,7 +518,12 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partial, int N, 
       }
     loss += cfg.xent_alpha * xs / (static_cast<double>(N) * Vn);
   }
-  loss_out[0] = static_cast<float>(loss);
+  double att = 0.0;  // attention loss (train.py:383-399), partial sums from gate_fwd_kernel
+  for (int b = 0; b < att_nblk; ++b) att += att_partial[b];
+  att /= att_div;
+  loss_out[0] = static_cast<float>(loss + att);  // train.py:417 total_loss_op
+  loss_out[1] = static_cast<float>(loss);
+  loss_out[2] = static_cast<float>(att);
 }
 
 // dL/dlogits, written to `dlogits` (the output layer's activation-gradient buffer)
@@ -528,6 +565,101 @@ __global__ void softmax_loss_bwd_kernel(const float* __restrict__ logits, const 
       float gl = p[c] * (dp[c] - dot);
       if (valid) gl += cX[t] * (p[c] - (t == c ? 1.f : 0.f));
       dlogits[gv * K + c] = gl * grad_scale;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention gating of the legacy trainer (train.py:281-302,383-399):
+//   s = softmax(logits_attention);  logits_masked = (1 + s) * logits_vnet
+//   attention loss  l2: mean(100 * (s[...,1] - distmap)^2)     abs: mean(|s - [1 - distmap, distmap]|)
+// forward writes s and logits_masked and the per-block attention-loss partial sums; backward
+// turns dL/dlogits_masked (+ the attention-loss term) into dL/dlogits_attention and dL/dlogits_vnet.
+// ---------------------------------------------------------------------------------------------
+struct GateArgs {
+  const float* att;      // [V][K] logits_attention
+  const float* vnet;     // [V][K] logits_vnet
+  float* soft;           // [V][K] softmax_attention
+  float* masked;         // [V][K] logits_masked
+  const float* distmap;  // [V] or nullptr
+  long long V;
+  int K;
+  int att_loss;          // 0 none, 1 l2, 2 abs
+};
+
+__device__ __forceinline__ void gate_softmax(const float* __restrict__ a, int K, float (&s)[kMaxClasses]) {
+  float mx = -3.4e38f;
+  for (int c = 0; c < K; ++c) {
+    s[c] = a[c];
+    mx = s[c] > mx ? s[c] : mx;
+  }
+  float se = 0.f;
+  for (int c = 0; c < K; ++c) {
+    s[c] = expf(s[c] - mx);
+    se += s[c];
+  }
+  const float inv = 1.0f / se;
+  for (int c = 0; c < K; ++c) s[c] *= inv;
+}
+
+__global__ void gate_fwd_kernel(GateArgs p, double* __restrict__ partial) {
+  double acc = 0.0;
+  const int K = p.K;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < p.V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float s[kMaxClasses];
+    gate_softmax(p.att + v * K, K, s);
+    for (int c = 0; c < K; ++c) {
+      p.soft[v * K + c] = s[c];
+      p.masked[v * K + c] = (1.0f + s[c]) * p.vnet[v * K + c];
+    }
+    if (p.distmap && p.att_loss == 1) {
+      const float e = s[1] - p.distmap[v];
+      acc += static_cast<double>(e * e * 100.0f);
+    } else if (p.distmap && p.att_loss == 2) {
+      const float d = p.distmap[v];
+      acc += static_cast<double>(fabsf(s[0] - (1.0f - d)) + fabsf(s[1] - d));
+    }
+  }
+  __shared__ double red[kRedThreads];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (unsigned i = 0; i < blockDim.x; ++i) t += red[i];
+    partial[blockIdx.x] = t;
+  }
+}
+
+// att_coef = 1 / (number of elements the attention loss averages over)
+__global__ void gate_bwd_kernel(GateArgs p, const float* __restrict__ dmasked, float* __restrict__ datt, int acc_att,
+                                float* __restrict__ dvnet, int acc_vnet, float att_coef) {
+  const int K = p.K;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < p.V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float s[kMaxClasses], ds[kMaxClasses];
+    for (int c = 0; c < K; ++c) s[c] = p.soft[v * K + c];
+    float dot = 0.f;
+    for (int c = 0; c < K; ++c) {
+      const float dm = dmasked[v * K + c], x = p.vnet[v * K + c];
+      ds[c] = x * dm;
+      const float dv = (1.0f + s[c]) * dm;
+      float* o = dvnet + v * K + c;
+      *o = acc_vnet ? *o + dv : dv;
+    }
+    if (p.distmap && p.att_loss == 1) {
+      ds[1] += 200.0f * (s[1] - p.distmap[v]) * att_coef;
+    } else if (p.distmap && p.att_loss == 2) {
+      const float d = p.distmap[v];
+      const float e0 = s[0] - (1.0f - d), e1 = s[1] - d;
+      ds[0] += (e0 > 0.f ? 1.f : (e0 < 0.f ? -1.f : 0.f)) * att_coef;
+      ds[1] += (e1 > 0.f ? 1.f : (e1 < 0.f ? -1.f : 0.f)) * att_coef;
+    }
+    for (int c = 0; c < K; ++c) dot += s[c] * ds[c];
+    for (int c = 0; c < K; ++c) {
+      const float g = s[c] * (ds[c] - dot);
+      float* o = datt + v * K + c;
+      *o = acc_att ? *o + g : g;
     }
   }
 }

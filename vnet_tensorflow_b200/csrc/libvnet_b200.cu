@@ -105,7 +105,18 @@ int vnb_create(const vnb_config* c, int device, vnb_handle** out) {
     e.flavour = c->graph_flavour;
     if (e.flavour < 0 || e.flavour > 1) throw std::invalid_argument("graph_flavour must be 0 (networks.VNet) or 1 (VNet.py)");
     if (e.precision < 0 || e.precision > 2) throw std::invalid_argument("precision must be VNB_PREC_*");
-    if (e.loss < 0 || e.loss > VNB_LOSS_MIXED_WEIGHTED_JACCARD) throw std::invalid_argument("loss must be VNB_LOSS_*");
+    if (e.loss < 0 || e.loss > VNB_LOSS_SORENSEN_FG) throw std::invalid_argument("loss must be VNB_LOSS_*");
+    e.attention = c->attention;
+    e.attention_loss = c->attention_loss;
+    e.module_channels = c->module_channels > 0 ? c->module_channels : 64;
+    if (e.attention < 0 || e.attention > 1) throw std::invalid_argument("attention must be 0 or 1");
+    if (e.attention_loss < 0 || e.attention_loss > VNB_ATT_ABS) throw std::invalid_argument("attention_loss must be VNB_ATT_*");
+    if (e.attention_loss != VNB_ATT_NONE && !e.attention) throw std::invalid_argument("attention_loss needs attention = 1");
+    if (e.attention_loss == VNB_ATT_ABS && e.num_classes != 2)
+      throw std::invalid_argument("attention_loss abs is defined for 2 classes only (train.py:394-398)");
+    if (e.attention && e.num_classes < 2) throw std::invalid_argument("the attention path needs >= 2 classes");
+    if (e.loss == VNB_LOSS_SORENSEN_FG && e.num_classes < 2) throw std::invalid_argument("sorensen_fg needs >= 2 classes");
+    if (e.module_channels % 4 || e.module_channels > 256) throw std::invalid_argument("module_channels must be a multiple of 4, <= 256");
     if (e.optimizer < 0 || e.optimizer > VNB_OPT_NESTEROV) throw std::invalid_argument("optimizer must be VNB_OPT_*");
     for (int l = 0; l < e.num_levels && l < 8; ++l)
       if (e.num_convolutions[l] < 1) throw std::invalid_argument("NumConvolutions entries must be >= 1");
@@ -354,6 +365,34 @@ int vnb_profile_read(vnb_handle* h, int cls, double* ms, int64_t* launches, doub
   });
 }
 
+int vnb_set_distmap(vnb_handle* h, const float* distmap, int n) {
+  return guarded([&] {
+    need(h, "handle");
+    need(distmap, "distmap");
+    select_device(h);
+    h->engine->set_distmap(distmap, n);
+  });
+}
+int vnb_read_losses(vnb_handle* h, float out[3]) {
+  return guarded([&] {
+    need(h, "handle");
+    need(out, "out");
+    select_device(h);
+    h->engine->read_losses(out);
+  });
+}
+int vnb_read_softmax_attention(vnb_handle* h, float* host, size_t bytes, int n) {
+  return guarded([&] {
+    need(h, "handle");
+    need(host, "host");
+    select_device(h);
+    const vnb::EngineConfig& c = h->engine->config();
+    if (n < 1 || n > c.max_batch) throw std::invalid_argument("batch size outside [1, max_batch]");
+    if (bytes != sizeof(float) * n * (size_t)c.patch[0] * c.patch[1] * c.patch[2] * c.num_classes)
+      throw std::invalid_argument("read_softmax_attention size mismatch");
+    h->engine->read_softmax_attention(host, n);
+  });
+}
 int vnb_sync(vnb_handle* h) {
   return guarded([&] {
     need(h, "handle");
@@ -420,7 +459,7 @@ void op_conv5(int precision, const float* x, const float* w, const float* bias, 
 #endif
   const float* wk = dw.as<float>();
   if (dgrad_form) {
-    VNB_LAUNCH(flip_transpose_w5_kernel, 1024, 256, 0, 0, (const float*)dw.as<float>(), dwf.as<float>(), cin, cout);
+    VNB_LAUNCH(flip_transpose_w_kernel, 1024, 256, 0, 0, (const float*)dw.as<float>(), dwf.as<float>(), cin, cout, 125);
     wk = dwf.as<float>();
   }
   Conv5Args p;

@@ -27,6 +27,7 @@ class VNetEngine:
                  precision: str = "fp32", loss: str = "weighted_sorensen", loss_weights: Sequence[float] = (),
                  loss_alpha: float = 1.0, optimizer: str = "Adam", learning_rate: float = 1e-2,
                  decay_factor: float = 0.99, decay_steps: float = 100.0, momentum: float = 0.9, flavour: str = "networks", device: int = 0,
+                 attention: bool = False, attention_loss: Optional[str] = None, module_channels: int = 64,
                  library: Optional[_ffi.Library] = None):
         self.lib = library or _ffi.default_library()
         if precision not in _ffi.PRECISIONS:
@@ -62,6 +63,12 @@ class VNetEngine:
         if flavour not in ("networks", "legacy"):
             raise ValueError("flavour must be 'networks' (networks.VNet) or 'legacy' (VNet.py)")
         cfg.graph_flavour = 1 if flavour == "legacy" else 0
+        if attention_loss not in _ffi.ATTENTION_LOSSES:
+            raise SystemExit("Invalid loss function")  # train.py:399-400
+        cfg.attention = 1 if attention else 0
+        cfg.attention_loss = _ffi.ATTENTION_LOSSES[attention_loss]
+        cfg.module_channels = int(module_channels)
+        self.attention = bool(attention)
         self.cfg = cfg
         self.num_classes, self.in_channels = num_classes, in_channels
         self.patch_shape = tuple(int(p) for p in patch_shape)
@@ -131,6 +138,27 @@ class VNetEngine:
     @global_step.setter
     def global_step(self, v: int):
         self.lib.check(self.lib.vnb_set_step(self._h, int(v)))
+
+    # ---- attention path (train.py:281-312,383-418) ---------------------------------------------
+    def set_distmap(self, distmap: np.ndarray):
+        """Distance map in [0,1] fed to the attention loss, [N,X,Y,Z] (or [N,X,Y,Z,1]) float32."""
+        a = np.ascontiguousarray(distmap, dtype=np.float32)
+        if a.ndim == 5 and a.shape[-1] == 1:
+            a = np.ascontiguousarray(a[..., 0])
+        if a.ndim != 4 or tuple(a.shape[1:]) != self.patch_shape:
+            raise ValueError("distmap must be [N,%d,%d,%d] float32, got %s" % (self.patch_shape + (a.shape,)))
+        self.lib.check(self.lib.vnb_set_distmap(self._h, _ptr(a), a.shape[0]))
+
+    def losses(self) -> Tuple[float, float, float]:
+        """(total, segmentation, attention) loss of the last loss / training call."""
+        out = (C.c_float * 3)()
+        self.lib.check(self.lib.vnb_read_losses(self._h, out))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def softmax_attention(self, n: int) -> np.ndarray:
+        a = np.empty((n,) + self.patch_shape + (self.num_classes,), np.float32)
+        self.lib.check(self.lib.vnb_read_softmax_attention(self._h, _ptr(a), a.nbytes, n))
+        return a
 
     # ---- steps --------------------------------------------------------------------------------
     def _check_images(self, images: np.ndarray) -> np.ndarray:
