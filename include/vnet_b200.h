@@ -160,6 +160,14 @@ int vnb_op_conv5_dgrad(int device, int precision, const float* dy, const float* 
                        int h, int w_, int cin, int cout);
 int vnb_op_conv5_wgrad(int device, int precision, const float* x, const float* dy, float* dw, int n, int d,
                        int h, int w_, int cin, int cout);
+/* the same three ops for the 3x3x3 SAME convolution of the attention / output modules (attention.py:63-92);
+ * filters [27][Cin][Cout] */
+int vnb_op_conv3_fprop(int device, int precision, const float* x, const float* w, const float* bias,
+                       const float* residual, float* y, int n, int d, int h, int w_, int cin, int cout);
+int vnb_op_conv3_dgrad(int device, int precision, const float* dy, const float* w, float* dx, int n, int d,
+                       int h, int w_, int cin, int cout);
+int vnb_op_conv3_wgrad(int device, int precision, const float* x, const float* dy, float* dw, int n, int d,
+                       int h, int w_, int cin, int cout);
 
 #ifdef __cplusplus
 }

@@ -119,3 +119,70 @@ def test_multimodal_input_runs_on_tensor_cores_with_padded_channels(emul_lib):
     assert g.shape == (5, 5, 5, 3, 16)
     assert np.sqrt(((g - ref) ** 2).sum()) <= 2e-2 * np.sqrt((ref ** 2).sum())
     eng.close()
+
+
+@pytest.mark.parametrize("cin,cout,dims,n,prec", [
+    (16, 16, (2, 4, 32), 1, 2),     # CT=16, three tiles, streaming + resident
+    (64, 64, (3, 8, 16), 1, 1),     # the attention-module shape: 64 -> 64, CT=32, two slices, two k-chunks, bf16x3
+    (32, 64, (2, 5, 64), 2, 2),     # partial last h-block
+    (2, 64, (3, 4, 8), 1, 0),       # first module conv (K -> 64): exact fp32 kernel
+])
+def test_conv3_kernels_match_torch(emul_lib, cin, cout, dims, n, prec):
+    """3^3 SAME convolution of the attention / output modules (attention.py:63-92): forward, input gradient,
+    filter gradient -- tensor-core kernel with KS = 3 (fprop / dgrad) and the fp32 kernels."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(11)
+    x = rng.normal(0, 1, (n,) + dims + (cin,)).astype(np.float32)
+    w = rng.normal(0, 0.1, (3, 3, 3, cin, cout)).astype(np.float32)
+    b = rng.normal(0, 1, (cout,)).astype(np.float32)
+    dy = rng.normal(0, 1, (n,) + dims + (cout,)).astype(np.float32)
+    xr, wr, dyr = (_bf16(x), _bf16(w), _bf16(dy)) if prec == 2 else (x, w, dy)
+    tol = 1e-6 if prec == 2 else 3e-5
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def conv(xt, wt):
+        return F.conv3d(xt.permute(0, 4, 1, 2, 3), wt.permute(4, 3, 0, 1, 2), padding=1).permute(0, 2, 3, 4, 1)
+
+    xt = torch.from_numpy(xr).double().requires_grad_(True)
+    wt = torch.from_numpy(wr).double().requires_grad_(True)
+    y_ref = conv(xt, wt) + torch.from_numpy(b).double()
+    y = np.empty_like(dy)
+    emul_lib.check(emul_lib.vnb_op_conv3_fprop(0, prec, ptr(x), ptr(w), ptr(b), None, ptr(y), n, *dims, cin, cout))
+    assert rel_err(y, y_ref.detach().numpy()) < tol
+    y_ref.backward(torch.from_numpy(dyr).double())
+    dx = np.empty_like(x)
+    emul_lib.check(emul_lib.vnb_op_conv3_dgrad(0, prec, ptr(dy), ptr(w), ptr(dx), n, *dims, cin, cout))
+    assert rel_err(dx, xt.grad.numpy()) < tol
+    if prec == 0 or dims[2] in (8, 16, 32, 64, 128):
+        dw = np.empty_like(w)
+        emul_lib.check(emul_lib.vnb_op_conv3_wgrad(0, prec, ptr(x), ptr(dy), ptr(dw), n, *dims, cin, cout))
+        assert rel_err(dw, wt.grad.numpy()) < (3e-5 if prec != 2 else 1e-5)
+
+
+def test_attention_engine_bf16x3_matches_oracle(emul_lib):
+    """Gated network (row a15) with the module 3^3 convolutions on the tensor-core kernel (fprop + dgrad),
+    fp32 filter gradients, inference-mode batch norms, gate and attention loss."""
+    from tests.helpers import perturbed_attention_params
+    from vnet_tensorflow_b200.synthetic import synth_patch
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=16, num_levels=1, num_convolutions=(1,),
+                      bottom_convolutions=1, flavour="legacy")
+    P, N, nch = 8, 1, 16
+    params = perturbed_attention_params(spec, nch)
+    im, lb, dm = (a[None] for a in synth_patch(3, P, 1, 2))
+    eng = engine_for(spec, P, N, "jaccard", (), emul_lib, precision="bf16x3", attention=True, attention_loss="l2",
+                     module_channels=nch)
+    eng.set_params(params)
+    eng.set_distmap(dm)
+    tot, seg, att, out, go, _ = R.attention_loss_and_grads(params, im, lb, dm, spec, "jaccard", "l2")
+    l = eng.forward_backward(im, lb)
+    logits, _, am = eng.forward(im)
+    assert abs(l - float(tot)) < 1e-4 * max(1.0, abs(float(tot)))
+    assert rel_err(logits, out["logits_output"].numpy()) < 1e-4
+    assert int((am != R.predict(out["logits_output"]).numpy()).sum()) == 0
+    g = eng.get_grads()
+    for k, v in g.items():
+        if analytically_zero(k, spec):
+            continue
+        ref = go[k].numpy().astype(np.float64)
+        assert np.sqrt(((v - ref) ** 2).sum()) <= 5e-2 * max(np.sqrt((ref ** 2).sum()), 1e-9), k
+    eng.close()

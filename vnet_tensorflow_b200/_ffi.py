@@ -82,6 +82,10 @@ _PROTOTYPES = {
                                      C.c_void_p] + [C.c_int] * 6),
     "vnb_op_conv5_dgrad": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6),
     "vnb_op_conv5_wgrad": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6),
+    "vnb_op_conv3_fprop": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p] + [C.c_int] * 6),
+    "vnb_op_conv3_dgrad": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6),
+    "vnb_op_conv3_wgrad": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

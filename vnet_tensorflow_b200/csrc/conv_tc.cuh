@@ -34,10 +34,13 @@ constexpr int kTcThreads = 192;             // 2 control warps + 4 epilogue warp
 constexpr int kTcEpiRowPad = 20;  // floats per staged row (16 + 4: conflict-free float4 rows)
 constexpr int kTcEpiBytes = 5 * 128 * kTcEpiRowPad * 4;
 
-template <int CT, int TMAX, int KC, int NSPLIT>
+// KS = filter extent: 5 for the V-Net convolutions, 3 for the attention / output module convolutions
+// (attention.py:83-92, tf.pad 1 + VALID == SAME)
+template <int CT, int TMAX, int KC, int NSPLIT, int KS = 5>
 struct TcCfg {
   static constexpr int ROWB = KC * 2;                       // bytes per smem row (= swizzle span)
-  static constexpr int NB = 5 * CT;                         // GEMM N (kw-folded)
+  static constexpr int NB = KS * CT;                        // GEMM N (kw-folded)
+  static constexpr int R = KS / 2;
   static constexpr int NPL = NSPLIT == 3 ? 2 : 1;           // operand planes (hi, lo)
   static constexpr int A_BYTES = TMAX * 128 * ROWB;
   static constexpr int B_BYTES = ((NB * ROWB + 1023) / 1024) * 1024;
@@ -81,9 +84,10 @@ struct TcArgs {
 
 // epilogue shared by both pipeline modes: TMEM -> registers -> shift-sum over the 5 kw slices -> bias /
 // residual -> fp32 store.  Runs on warps 2..5 (128 threads = 128 TMEM lanes).
-template <int CT, int TMAX, int KC, int NSPLIT>
+template <int CT, int TMAX, int KC, int NSPLIT, int KS>
 __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_base, uint32_t tmem, uint32_t tfull0, uint32_t tempty0) {
-  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
+  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT, KS>;
+  constexpr int RC = KS / 2;  // centre tap
   using namespace sm100;
   const TcGeom& g = p.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,13 +125,13 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_ba
         for (int cc = 0; cc < CT / 16; ++cc) {
           float acc[16];
           {  // all five kw slices in flight, one wait; the centre slice (kw = 2) never leaves registers
-            uint32_t v[5][16];
+            uint32_t v[KS][16];
 #pragma unroll
-            for (int kw = 0; kw < 5; ++kw) tmem_ld16(t_addr + kw * CT + cc * 16, v[kw]);
+            for (int kw = 0; kw < KS; ++kw) tmem_ld16(t_addr + kw * CT + cc * 16, v[kw]);
             tmem_ld_wait();
 #pragma unroll
-            for (int kw = 0; kw < 5; ++kw) {
-              if (kw == 2) continue;
+            for (int kw = 0; kw < KS; ++kw) {
+              if (kw == RC) continue;
               float4* dst = reinterpret_cast<float4*>(epi + (kw * 128 + r) * kTcEpiRowPad);
 #pragma unroll
               for (int i = 0; i < 4; ++i)
@@ -135,15 +139,15 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_ba
                                      __uint_as_float(v[kw][4 * i + 2]), __uint_as_float(v[kw][4 * i + 3]));
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[2][i]);
+            for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[RC][i]);
           }
           named_bar_sync(bar_id, 128);
 #pragma unroll
-          for (int kw = 0; kw < 5; ++kw) {
-            if (kw == 2) continue;
-            const int ws = w + kw - 2;
+          for (int kw = 0; kw < KS; ++kw) {
+            if (kw == RC) continue;
+            const int ws = w + kw - RC;
             if (ws >= 0 && ws < g.W) {
-              const float4* src = reinterpret_cast<const float4*>(epi + (kw * 128 + r + kw - 2) * kTcEpiRowPad);
+              const float4* src = reinterpret_cast<const float4*>(epi + (kw * 128 + r + kw - RC) * kTcEpiRowPad);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float4 f = src[i];
@@ -206,11 +210,12 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_ba
 // all five kh taps of the item read (the kh shift is a start-address offset of kh*W rows inside the swizzled
 // tile); ring B streams the packed weights per (kd, kh, k-chunk).  Cuts the activation traffic L2->SMEM
 // from 25 to 5*(bh+4)/bh line loads per output line.
-template <int CT, int TMAX, int KC, int NSPLIT>
+template <int CT, int TMAX, int KC, int NSPLIT, int KS>
 __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const TmaDesc& a1_lo, const TmaDesc& a2_hi,
                                                   const TmaDesc& a2_lo, const TmaDesc& w_hi, const TmaDesc& w_lo,
                                                   const TcArgs& p, uint8_t* sm, uint32_t sm_addr) {
-  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
+  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT, KS>;
+  constexpr int RC = KS / 2;
   using namespace sm100;
   const TcGeom& g = p.g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -227,7 +232,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
   const uint32_t slot_addr = bar_base + 8u * 20;
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + epi_off + Cfg::EPI_BYTES + 8 * 20);
   const int kc1 = g.C1 / KC;
-  const int n_it = 25 * g.n_kc;
+  const int n_it = KS * KS * g.n_kc;
 
   if (tid == 0) {
     for (int s = 0; s < 4; ++s) {
@@ -250,7 +255,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *slot_ptr;
-  const uint32_t a_rows = static_cast<uint32_t>(g.T * 128 + 4 * g.W);   // rows held per A stage
+  const uint32_t a_rows = static_cast<uint32_t>(g.T * 128 + (KS - 1) * g.W);   // rows held per A stage
 
   if (warp == 0) {
     if (lane == 0) {
@@ -264,21 +269,21 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
         const int db = x % g.n_db;
         const int n = x / g.n_db;
         const int h0 = hb * g.bh, d0 = db;
-        for (int kd = 0; kd < 5; ++kd)
+        for (int kd = 0; kd < KS; ++kd)
           for (int kc = 0; kc < g.n_kc; ++kc) {
             mbar_wait(aempty(as), aph ^ 1u);
             mbar_expect_tx(afull(as), Cfg::NPL * a_rows * Cfg::ROWB);
             const bool src1 = kc < kc1;
             const int cch = (src1 ? kc : kc - kc1) * KC;
             const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
-            tma_load_5d(a_addr, src1 ? &a1_hi : &a2_hi, afull(as), cch, 0, h0 - 2, d0 + kd - 2, n);
-            if (NSPLIT == 3) tma_load_5d(a_addr + g.a_stage_bytes, src1 ? &a1_lo : &a2_lo, afull(as), cch, 0, h0 - 2, d0 + kd - 2, n);
+            tma_load_5d(a_addr, src1 ? &a1_hi : &a2_hi, afull(as), cch, 0, h0 - RC, d0 + kd - RC, n);
+            if (NSPLIT == 3) tma_load_5d(a_addr + g.a_stage_bytes, src1 ? &a1_lo : &a2_lo, afull(as), cch, 0, h0 - RC, d0 + kd - RC, n);
             if (++as == g.n_a) {
               as = 0;
               aph ^= 1u;
             }
-            for (int kh = 0; kh < 5; ++kh) {
-              const int it = (kd * 5 + kh) * g.n_kc + kc;
+            for (int kh = 0; kh < KS; ++kh) {
+              const int it = (kd * KS + kh) * g.n_kc + kc;
               mbar_wait(bempty(bs), bph ^ 1u);
               mbar_expect_tx(bfull(bs), Cfg::NPL * Cfg::NB * Cfg::ROWB);
               const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
@@ -306,14 +311,14 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
         tc_fence_after_sync();
         const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
         bool first = true;
-        for (int kd = 0; kd < 5; ++kd)
+        for (int kd = 0; kd < KS; ++kd)
           for (int kc = 0; kc < g.n_kc; ++kc) {
             mbar_wait(afull(as), aph);
             tc_fence_after_sync();
             const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
             const uint64_t da_hi0 = make_smem_desc(a_addr, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
             const uint64_t da_lo0 = da_hi0 + (static_cast<uint32_t>(g.a_stage_bytes) >> 4);
-            for (int kh = 0; kh < 5; ++kh) {
+            for (int kh = 0; kh < KS; ++kh) {
               mbar_wait(bfull(bs), bph);
               tc_fence_after_sync();
               const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
@@ -350,19 +355,20 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
       }
     }
   } else {
-    conv5_tc_epilogue<CT, TMAX, KC, NSPLIT>(p, epi, tmem, tfull0, tempty0);
+    conv5_tc_epilogue<CT, TMAX, KC, NSPLIT, KS>(p, epi, tmem, tfull0, tempty0);
   }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-template <int CT, int TMAX, int KC, int NSPLIT>
+template <int CT, int TMAX, int KC, int NSPLIT, int KS>
 __global__ void __launch_bounds__(64 + 128 * (NSPLIT == 3 ? 1 : 2), 1)
 conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ TmaDesc a1_lo,
                 const __grid_constant__ TmaDesc a2_hi, const __grid_constant__ TmaDesc a2_lo,
                 const __grid_constant__ TmaDesc w_hi, const __grid_constant__ TmaDesc w_lo, const TcArgs p) {
-  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
+  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT, KS>;
+  constexpr int RC = KS / 2;
   using namespace sm100;
   VNB_DYN_SMEM(uint8_t, smem_raw);
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -380,10 +386,10 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const TcGeom& g = p.g;
-  const int n_it = 25 * g.n_kc;
+  const int n_it = KS * KS * g.n_kc;
   const int kc1 = g.C1 / KC;
   if (g.resident) {
-    conv5_tc_resident<CT, TMAX, KC, NSPLIT>(a1_hi, a1_lo, a2_hi, a2_lo, w_hi, w_lo, p, sm, sm_addr);
+    conv5_tc_resident<CT, TMAX, KC, NSPLIT, KS>(a1_hi, a1_lo, a2_hi, a2_lo, w_hi, w_lo, p, sm, sm_addr);
     return;
   }
 
@@ -421,18 +427,18 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
         const int n = x / g.n_db;
         const int h0 = hb * g.bh, d0 = db * g.bd;
         for (int it = 0; it < n_it; ++it) {
-          const int kc = it % g.n_kc, kh = (it / g.n_kc) % 5, kd = it / (5 * g.n_kc);
+          const int kc = it % g.n_kc, kh = (it / g.n_kc) % KS, kd = it / (KS * g.n_kc);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t st_addr = sm_addr + stage * Cfg::STAGE_BYTES;
           const uint32_t a_bytes = static_cast<uint32_t>(g.T) * 128u * Cfg::ROWB;
           mbar_expect_tx(full_bar(stage), Cfg::NPL * (a_bytes + Cfg::NB * Cfg::ROWB));
           const bool src1 = kc < kc1;
           const int cch = (src1 ? kc : kc - kc1) * KC;
-          tma_load_5d(st_addr, src1 ? &a1_hi : &a2_hi, full_bar(stage), cch, 0, h0 + kh - 2, d0 + kd - 2, n);
+          tma_load_5d(st_addr, src1 ? &a1_hi : &a2_hi, full_bar(stage), cch, 0, h0 + kh - RC, d0 + kd - RC, n);
           const int brow = (slice * n_it + it) * Cfg::NB;
           tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES, &w_hi, full_bar(stage), 0, brow);
           if (NSPLIT == 3) {
-            tma_load_5d(st_addr + Cfg::A_BYTES, src1 ? &a1_lo : &a2_lo, full_bar(stage), cch, 0, h0 + kh - 2, d0 + kd - 2, n);
+            tma_load_5d(st_addr + Cfg::A_BYTES, src1 ? &a1_lo : &a2_lo, full_bar(stage), cch, 0, h0 + kh - RC, d0 + kd - RC, n);
             tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES + Cfg::B_BYTES, &w_lo, full_bar(stage), 0, brow);
           }
           if (++stage == kTcStages) {
@@ -489,7 +495,7 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
       }
     }
   } else {
-    conv5_tc_epilogue<CT, TMAX, KC, NSPLIT>(p, epi, tmem, tfull_bar(0), tempty_bar(0));
+    conv5_tc_epilogue<CT, TMAX, KC, NSPLIT, KS>(p, epi, tmem, tfull_bar(0), tempty_bar(0));
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -505,13 +511,13 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
 // One block per (slice, it): the [5*CT][KC] tile is gathered through shared memory so that both the fp32
 // reads (runs of CT or KC contiguous floats) and the bf16 writes (whole tile contiguous) are coalesced.
 __global__ void __launch_bounds__(256) pack_w5_kernel(const float* __restrict__ w, int Cin, int Cout, int dgrad, int CT, int KC,
-                                                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int Cin_gemm) {
+                                                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int Cin_gemm, int KS = 5) {
   // Cin_gemm >= Cin: input channels seen by the GEMM (zero rows beyond the real Cin; fprop only)
-  __shared__ float tile[160 * 33];         // [nrow][k] with a padded pitch of KC + 1
+  __shared__ float tile[192 * 33];         // [nrow][k] with a padded pitch of KC + 1
   const int Kin = dgrad ? Cout : Cin_gemm;  // GEMM K channels
-  const int n_kc = Kin / KC, n_it = 25 * n_kc, NB = 5 * CT, pitch = KC + 1;
+  const int n_kc = Kin / KC, n_it = KS * KS * n_kc, NB = KS * CT, pitch = KC + 1;
   const int it = blockIdx.x % n_it, slice = blockIdx.x / n_it;
-  const int kc = it % n_kc, kh = (it / n_kc) % 5, kd = it / (5 * n_kc);
+  const int kc = it % n_kc, kh = (it / n_kc) % KS, kd = it / (KS * n_kc);
   const int elems = NB * KC;
   for (int e = threadIdx.x; e < elems; e += blockDim.x) {
     int nrow, k;
@@ -519,14 +525,14 @@ __global__ void __launch_bounds__(256) pack_w5_kernel(const float* __restrict__ 
       const int cl = e % CT, k_ = (e / CT) % KC, kw = e / (CT * KC);
       nrow = kw * CT + cl;
       k = k_;
-      const int tap = (kd * 5 + kh) * 5 + kw;
+      const int tap = (kd * KS + kh) * KS + kw;
       const int kch = kc * KC + k;
       tile[nrow * pitch + k] = kch < Cin ? w[(static_cast<long long>(tap) * Cin + kch) * Cout + slice * CT + cl] : 0.f;
     } else {       // source rows: fixed (tap, input channel), KC contiguous output channels
       k = e % KC;
       nrow = e / KC;
       const int kw = nrow / CT, col = slice * CT + nrow % CT;
-      const int tap = 124 - ((kd * 5 + kh) * 5 + kw);
+      const int tap = KS * KS * KS - 1 - ((kd * KS + kh) * KS + kw);
       tile[nrow * pitch + k] = w[(static_cast<long long>(tap) * Cin + col) * Cout + kc * KC + k];
     }
   }
@@ -547,11 +553,12 @@ struct PackJob {
   uint16_t* lo;
   int Cin, Cout, dgrad, CT, KC, Cin_gemm;
   int first_block;   // prefix sum of tiles
+  int KS;            // filter extent (5 or 3)
 };
 __device__ __forceinline__ void pack_w5_tile(const PackJob& j, int tile_idx, float* tile);
 
 __global__ void __launch_bounds__(256) pack_w5_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
-  __shared__ float tile[160 * 33];
+  __shared__ float tile[192 * 33];
   int lo = 0, hi = njobs - 1;
   const int b = blockIdx.x;
   while (lo < hi) {  // last job with first_block <= b
@@ -564,20 +571,20 @@ __global__ void __launch_bounds__(256) pack_w5_multi_kernel(const PackJob* __res
 
 __device__ __forceinline__ void pack_w5_tile(const PackJob& j, int tile_idx, float* tile) {
   const int Kin = j.dgrad ? j.Cout : j.Cin_gemm;
-  const int KC = j.KC, CT = j.CT, Cin = j.Cin, Cout = j.Cout;
-  const int n_kc = Kin / KC, n_it = 25 * n_kc, NB = 5 * CT, pitch = KC + 1;
+  const int KC = j.KC, CT = j.CT, Cin = j.Cin, Cout = j.Cout, KS = j.KS;
+  const int n_kc = Kin / KC, n_it = KS * KS * n_kc, NB = KS * CT, pitch = KC + 1;
   const int it = tile_idx % n_it, slice = tile_idx / n_it;
-  const int kc = it % n_kc, kh = (it / n_kc) % 5, kd = it / (5 * n_kc);
+  const int kc = it % n_kc, kh = (it / n_kc) % KS, kd = it / (KS * n_kc);
   const int elems = NB * KC;
   for (int e = threadIdx.x; e < elems; e += blockDim.x) {
     if (!j.dgrad) {
       const int cl = e % CT, k = (e / CT) % KC, kw = e / (CT * KC);
-      const int tap = (kd * 5 + kh) * 5 + kw, kch = kc * KC + k;
+      const int tap = (kd * KS + kh) * KS + kw, kch = kc * KC + k;
       tile[(kw * CT + cl) * pitch + k] = kch < Cin ? j.w[(static_cast<long long>(tap) * Cin + kch) * Cout + slice * CT + cl] : 0.f;
     } else {
       const int k = e % KC, nrow = e / KC;
       const int kw = nrow / CT, col = slice * CT + nrow % CT;
-      const int tap = 124 - ((kd * 5 + kh) * 5 + kw);
+      const int tap = KS * KS * KS - 1 - ((kd * KS + kh) * KS + kw);
       tile[nrow * pitch + k] = j.w[(static_cast<long long>(tap) * Cin + col) * Cout + kc * KC + k];
     }
   }
@@ -656,7 +663,7 @@ inline void tma_encode_w(TmaDesc* out, const uint16_t* base, long long rows, int
 
 struct TcKernelPlan {   // one launch of conv5_tc_kernel
   bool valid = false;
-  int CT = 0, KC = 0;
+  int CT = 0, KC = 0, KS = 5;
   TcGeom g{};
   TmaDesc a1_hi, a1_lo, a2_hi, a2_lo, w_hi, w_lo;
   uint16_t* wp_hi = nullptr;   // packed weights
@@ -666,8 +673,10 @@ struct TcKernelPlan {   // one launch of conv5_tc_kernel
 };
 
 // geometry for a [N][D][H][W] activation, kernel-side channel counts (C1+C2 in, Co1+Co2 out)
-inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C1, int C2, int Co1, int Co2, bool split3) {
+inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C1, int C2, int Co1, int Co2, bool split3,
+                             int ks = 5) {
   auto mult = [](int v, int m) { return v % m == 0; };
+  pl.KS = ks;
   if (mult(C1, 32) && mult(C2, 32) && mult(Co1, 32) && mult(Co2, 32) && Co1 > 0) {
     pl.CT = 32;
     pl.KC = 32;
@@ -704,7 +713,7 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
     // shared-memory plan: resident-lines pipeline when the box is a single d-plane and the rings fit
     const int npl = split3 ? 2 : 1;
     const int rowb = pl.KC * 2;
-    const int b_bytes = ((5 * pl.CT * rowb + 1023) / 1024) * 1024;
+    const int b_bytes = ((ks * pl.CT * rowb + 1023) / 1024) * 1024;
     const int tmax_rows = tmax * 128;
     g.resident = 0;
     g.a_stage_bytes = 0;
@@ -712,7 +721,7 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
     const size_t epi_bytes = static_cast<size_t>(split3 ? 1 : 2) * kTcEpiBytes;
     pl.smem = static_cast<size_t>(kTcStages) * npl * (tmax_rows * rowb + b_bytes) + epi_bytes + 256 + 1024;
     if (bd == 1 && !getenv("VNB_TC_NO_RESIDENT")) {
-      const int a_stage = (((T * 128 + 4 * W) * rowb + 1023) / 1024) * 1024;
+      const int a_stage = (((T * 128 + (ks - 1) * W) * rowb + 1023) / 1024) * 1024;
       for (int nb = 4; nb >= 2; --nb) {
         const size_t need = 2ull * npl * a_stage + static_cast<size_t>(nb) * npl * b_bytes + epi_bytes + 256 + 1024;
         if (need <= 227 * 1024) {
@@ -730,10 +739,10 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
   return false;
 }
 
-template <int CT, int TMAX, int KC, int NSPLIT>
+template <int CT, int TMAX, int KC, int NSPLIT, int KS = 5>
 inline void tc_launch_inst(const TcKernelPlan& pl, const TcArgs& a, int sms, cudaStream_t stream) {
-  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT>;
-  auto kfn = conv5_tc_kernel<CT, TMAX, KC, NSPLIT>;
+  using Cfg = TcCfg<CT, TMAX, KC, NSPLIT, KS>;
+  auto kfn = conv5_tc_kernel<CT, TMAX, KC, NSPLIT, KS>;
 #ifndef VNB_EMULATE
   static bool attr = false;
   if (!attr) {
@@ -748,6 +757,16 @@ inline void tc_launch_inst(const TcKernelPlan& pl, const TcArgs& a, int sms, cud
 }
 
 inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int sms, cudaStream_t stream) {
+  if (pl.KS == 3) {
+    if (pl.CT == 16) {
+      if (split3) tc_launch_inst<16, 3, 16, 3, 3>(pl, a, sms, stream);
+      else tc_launch_inst<16, 3, 16, 1, 3>(pl, a, sms, stream);
+    } else {
+      if (split3) tc_launch_inst<32, 1, 32, 3, 3>(pl, a, sms, stream);
+      else tc_launch_inst<32, 1, 32, 1, 3>(pl, a, sms, stream);
+    }
+    return;
+  }
   if (pl.CT == 16) {
     if (split3) tc_launch_inst<16, 3, 16, 3>(pl, a, sms, stream);
     else tc_launch_inst<16, 3, 16, 1>(pl, a, sms, stream);

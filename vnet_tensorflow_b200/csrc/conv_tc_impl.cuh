@@ -20,7 +20,8 @@ inline int tc_query_sms() {
 inline void tc_encode_plan(TcKernelPlan& pl, int Nmax, const uint16_t* a1_hi, const uint16_t* a1_lo, const uint16_t* a2_hi,
                            const uint16_t* a2_lo) {
   const TcGeom& g = pl.g;
-  const int lines = g.resident ? g.bh + 4 : g.bh;   // resident mode: the box carries the 2+2 halo lines
+  const int ks = pl.KS;
+  const int lines = g.resident ? g.bh + ks - 1 : g.bh;   // resident mode: the box carries the halo lines
   tma_encode_act(&pl.a1_hi, a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, lines, g.bd);
   tma_encode_act(&pl.a1_lo, a1_lo ? a1_lo : a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, lines, g.bd);
   if (g.C2 > 0) {
@@ -30,9 +31,9 @@ inline void tc_encode_plan(TcKernelPlan& pl, int Nmax, const uint16_t* a1_hi, co
     pl.a2_hi = pl.a1_hi;
     pl.a2_lo = pl.a1_lo;
   }
-  const long long rows = static_cast<long long>(g.n_slices) * 25 * g.n_kc * 5 * pl.CT;
-  tma_encode_w(&pl.w_hi, pl.wp_hi, rows, pl.KC, 5 * pl.CT);
-  tma_encode_w(&pl.w_lo, pl.wp_lo ? pl.wp_lo : pl.wp_hi, rows, pl.KC, 5 * pl.CT);
+  const long long rows = static_cast<long long>(g.n_slices) * ks * ks * g.n_kc * ks * pl.CT;
+  tma_encode_w(&pl.w_hi, pl.wp_hi, rows, pl.KC, ks * pl.CT);
+  tma_encode_w(&pl.w_lo, pl.wp_lo ? pl.wp_lo : pl.wp_hi, rows, pl.KC, ks * pl.CT);
 }
 
 inline void Engine::tc_setup() {
@@ -41,7 +42,8 @@ inline void Engine::tc_setup() {
   const int NB = cfg_.max_batch;
   size_t wg_partial_floats = 0;
   for (Unit& u : units_) {
-    if (u.kind != U_CONV5) continue;
+    if (u.kind != U_CONV5 && u.kind != U_CONV3) continue;
+    const int ks = u.kind == U_CONV3 ? 3 : 5;
     const Act& x1 = acts_[u.in1];
     const Act& o = acts_[u.out];
     const Dims d = o.dims;
@@ -49,15 +51,15 @@ inline void Engine::tc_setup() {
     const bool padded_in = (u.in1 == image_act_) && image_cpad_ > 0;
     const int c1 = padded_in ? image_cpad_ : u.Cin1;
     TcKernelPlan& f = u.tc.fprop;
-    if (tc_plan_geometry(f, NB, d.D, d.H, d.W, c1, u.Cin2, u.Cout, 0, lo)) {
-      f.wp_elems = 125ull * (c1 + u.Cin2) * u.Cout;
+    if (tc_plan_geometry(f, NB, d.D, d.H, d.W, c1, u.Cin2, u.Cout, 0, lo, ks)) {
+      f.wp_elems = static_cast<size_t>(ks * ks * ks) * (c1 + u.Cin2) * u.Cout;
       f.wp_hi = dev_alloc<uint16_t>(f.wp_elems);
       f.wp_lo = lo ? dev_alloc<uint16_t>(f.wp_elems) : nullptr;
       tc_encode_plan(f, NB, x1.a_hi, x1.a_lo, u.in2 >= 0 ? acts_[u.in2].a_hi : nullptr, u.in2 >= 0 ? acts_[u.in2].a_lo : nullptr);
       f.valid = true;
     }
     TcKernelPlan& g = u.tc.dgrad;
-    if (u.need_dgrad && tc_plan_geometry(g, NB, d.D, d.H, d.W, u.Cout, 0, u.Cin1, u.Cin2, lo)) {
+    if (u.need_dgrad && tc_plan_geometry(g, NB, d.D, d.H, d.W, u.Cout, 0, u.Cin1, u.Cin2, lo, ks)) {
       g.wp_elems = u.w_count;
       g.wp_hi = dev_alloc<uint16_t>(g.wp_elems);
       g.wp_lo = lo ? dev_alloc<uint16_t>(g.wp_elems) : nullptr;
@@ -65,7 +67,7 @@ inline void Engine::tc_setup() {
       g.valid = true;
     }
     WgPlan& wg = u.tc.wgrad;
-    if (wg_plan_geometry(wg, NB, d.D, d.H, d.W, c1, u.Cin2, u.Cout, lo, sm_count_)) {
+    if (wg_plan_geometry(wg, NB, d.D, d.H, d.W, c1, u.Cin2, u.Cout, lo, sm_count_, ks)) {
       wg_encode_plan(wg, NB, x1.a_hi, x1.a_lo, u.in2 >= 0 ? acts_[u.in2].a_hi : nullptr,
                      u.in2 >= 0 ? acts_[u.in2].a_lo : nullptr, o.d_hi, o.d_lo);
       wg.valid = true;
@@ -81,7 +83,7 @@ inline void Engine::tc_prepare_weights() {
     std::vector<PackJob> jobs;
     int blocks = 0;
     for (Unit& u : units_) {
-      if (u.kind != U_CONV5) continue;
+      if (u.kind != U_CONV5 && u.kind != U_CONV3) continue;
       for (int pass = 0; pass < 2; ++pass) {
         TcKernelPlan& pl = pass == 0 ? u.tc.fprop : u.tc.dgrad;
         if (!pl.valid) continue;
@@ -96,7 +98,8 @@ inline void Engine::tc_prepare_weights() {
         j.KC = pl.KC;
         j.Cin_gemm = pl.g.C1 + pl.g.C2;
         j.first_block = blocks;
-        blocks += pl.g.n_slices * 25 * pl.g.n_kc;
+        j.KS = pl.KS;
+        blocks += pl.g.n_slices * pl.KS * pl.KS * pl.g.n_kc;
         jobs.push_back(j);
       }
     }
@@ -169,21 +172,22 @@ struct TcScratch {
 };
 
 inline void tc_op_conv5(int precision, const float* x, const float* w, const float* bias, const float* res, float* y, int n,
-                        Dims dims, int cin, int cout, bool dgrad_form) {
+                        Dims dims, int cin, int cout, bool dgrad_form, int ks = 5) {
   const bool lo = precision == PREC_BF16X3;
   const int ci = dgrad_form ? cout : cin, co = dgrad_form ? cin : cout;
   TcKernelPlan pl;
-  if (!tc_plan_geometry(pl, n, dims.D, dims.H, dims.W, ci, 0, co, 0, lo))
+  if (!tc_plan_geometry(pl, n, dims.D, dims.H, dims.W, ci, 0, co, 0, lo, ks))
     throw std::invalid_argument("shape not supported by the tensor-core convolution (channels % 16, W | 128)");
   TcScratch s;
   const size_t nx = static_cast<size_t>(n) * dims.D * dims.H * dims.W * ci;
   uint16_t* xh = s.alloc<uint16_t>(nx);
   uint16_t* xl = lo ? s.alloc<uint16_t>(nx) : nullptr;
   VNB_LAUNCH(split_bf16_kernel, 1024, 256, 0, 0, x, static_cast<long long>(nx), xh, xl);
-  pl.wp_elems = 125ull * cin * cout;
+  pl.wp_elems = static_cast<size_t>(ks * ks * ks) * cin * cout;
   pl.wp_hi = s.alloc<uint16_t>(pl.wp_elems);
   pl.wp_lo = lo ? s.alloc<uint16_t>(pl.wp_elems) : nullptr;
-  VNB_LAUNCH(pack_w5_kernel, pl.g.n_slices * 25 * pl.g.n_kc, 256, 0, 0, w, cin, cout, dgrad_form ? 1 : 0, pl.CT, pl.KC, pl.wp_hi, pl.wp_lo, cin);
+  VNB_LAUNCH(pack_w5_kernel, pl.g.n_slices * ks * ks * pl.g.n_kc, 256, 0, 0, w, cin, cout, dgrad_form ? 1 : 0, pl.CT, pl.KC, pl.wp_hi,
+             pl.wp_lo, cin, ks);
   tc_encode_plan(pl, n, xh, xl, nullptr, nullptr);
   TcArgs a;
   a.g = pl.g;
@@ -197,10 +201,10 @@ inline void tc_op_conv5(int precision, const float* x, const float* w, const flo
     throw std::runtime_error("CUDA: tensor-core convolution kernel failed");
 }
 
-inline void tc_op_wgrad5(int precision, const float* x, const float* dy, float* dw, int n, Dims dims, int cin, int cout) {
+inline void tc_op_wgrad5(int precision, const float* x, const float* dy, float* dw, int n, Dims dims, int cin, int cout, int ks = 5) {
   const bool lo = precision == PREC_BF16X3;
   WgPlan pl;
-  if (!wg_plan_geometry(pl, n, dims.D, dims.H, dims.W, cin, 0, cout, lo, tc_query_sms()))
+  if (!wg_plan_geometry(pl, n, dims.D, dims.H, dims.W, cin, 0, cout, lo, tc_query_sms(), ks))
     throw std::invalid_argument("shape not supported by the tensor-core wgrad (channels % 16, W in {8..128})");
   TcScratch s;
   const size_t V = static_cast<size_t>(n) * dims.D * dims.H * dims.W;

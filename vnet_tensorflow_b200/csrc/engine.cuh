@@ -793,6 +793,10 @@ class Engine {
       ProfScope ps(*this, 0, conv5_flops(u, N));
       launch_conv5(p);
     } else if (u.kind == U_CONV3) {
+      if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid && !getenv("VNB_DEBUG_NO_TC_FPROP")) {
+        tc_run_fprop(u, N);
+        return;
+      }
       Conv5Args p;
       p.in1 = x1.a;
       p.in2 = nullptr;
@@ -1077,7 +1081,9 @@ class Engine {
     VNB_CUDA_OK(cudaMemsetAsync(dw, 0, u.w_count * sizeof(float), stream_));
     if (!u.bn_inference) VNB_CUDA_OK(cudaMemsetAsync(grads_ + u.b_off, 0, u.Cout * sizeof(float), stream_));
     if (u.kind == U_CONV3) {
-      if (u.need_dgrad) {
+      if (cfg_.precision != PREC_FP32 && u.need_dgrad && u.tc.dgrad.valid && !getenv("VNB_DEBUG_NO_TC_DGRAD")) {
+        tc_run_dgrad(u, N);
+      } else if (u.need_dgrad) {
         VNB_LAUNCH(flip_transpose_w_kernel, grid_for(static_cast<long long>(u.w_count), 256), 256, 0, stream_,
                    (const float*)(params_ + u.w_off), wflip_, u.Cin1, u.Cout, 27);
         ++launches_;
@@ -1099,6 +1105,10 @@ class Engine {
         p.N = N;
         ProfScope ps(*this, 0, conv5_flops(u, N));
         launch_conv3(p);
+      }
+      if (cfg_.precision != PREC_FP32 && u.tc.wgrad.valid && !getenv("VNB_DEBUG_NO_TC_WGRAD")) {
+        tc_run_wgrad(u, N);
+        return;
       }
       Wgrad5Args w;
       w.in1 = x1.a;

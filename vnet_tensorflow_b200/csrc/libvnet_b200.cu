@@ -437,29 +437,47 @@ void op_device(int device) {
   (void)device;
 #endif
 }
-void op_conv5(int precision, const float* x, const float* w, const float* bias, const float* res, float* y, int n,
-              vnb::Dims dims, int cin, int cout, bool dgrad_form) {
+template <int KS>
+void launch_conv_ref(const vnb::Conv5Args& p, int co) {
+  using namespace vnb;
+#ifndef VNB_EMULATE
+  VNB_CUDA_OK(cudaFuncSetAttribute(conv_ref_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ConvRefGeom<KS>::SMEM));
+#endif
+  const Dims& dims = p.dims;
+  const int tiles = ((dims.W + kC5_TW - 1) / kC5_TW) * ((dims.H + kC5_TH - 1) / kC5_TH) * ((dims.D + kC5_TD - 1) / kC5_TD);
+  dim3 grid(tiles, (co + kC5_CO - 1) / kC5_CO, p.N);
+  VNB_LAUNCH(conv_ref_kernel<KS>, grid, 256, ConvRefGeom<KS>::SMEM, 0, p);
+}
+template <int KS>
+void launch_wgrad_ref(const vnb::Wgrad5Args& a, dim3 grid) {
+  using namespace vnb;
+#ifndef VNB_EMULATE
+  VNB_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_ref_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WgradRefGeom<KS>::SMEM));
+#endif
+  VNB_LAUNCH(conv_wgrad_ref_kernel<KS>, grid, 256, WgradRefGeom<KS>::SMEM, 0, a);
+}
+
+void op_conv(int ks, int precision, const float* x, const float* w, const float* bias, const float* res, float* y, int n,
+             vnb::Dims dims, int cin, int cout, bool dgrad_form) {
   using namespace vnb;
   const size_t V = static_cast<size_t>(n) * dims.D * dims.H * dims.W;
   const int ci = dgrad_form ? cout : cin, co = dgrad_form ? cin : cout;  // channels seen by the kernel
-  DevBuf dx(V * ci * 4), dw(125ull * cin * cout * 4), dwf(125ull * cin * cout * 4), dy(V * co * 4), db(co * 4), dr(V * co * 4);
+  const size_t wbytes = static_cast<size_t>(ks * ks * ks) * cin * cout * 4;
+  DevBuf dx(V * ci * 4), dw(wbytes), dwf(wbytes), dy(V * co * 4), db(co * 4), dr(V * co * 4);
   VNB_CUDA_OK(cudaMemcpy(dx.p, x, V * ci * 4, cudaMemcpyHostToDevice));
-  VNB_CUDA_OK(cudaMemcpy(dw.p, w, 125ull * cin * cout * 4, cudaMemcpyHostToDevice));
+  VNB_CUDA_OK(cudaMemcpy(dw.p, w, wbytes, cudaMemcpyHostToDevice));
   if (bias) VNB_CUDA_OK(cudaMemcpy(db.p, bias, co * 4, cudaMemcpyHostToDevice));
   if (res) VNB_CUDA_OK(cudaMemcpy(dr.p, res, V * co * 4, cudaMemcpyHostToDevice));
   if (precision != VNB_PREC_FP32) {
     tc_op_conv5(precision, dx.as<float>(), dw.as<float>(), bias ? db.as<float>() : nullptr, res ? dr.as<float>() : nullptr,
-                dy.as<float>(), n, dims, cin, cout, dgrad_form);
+                dy.as<float>(), n, dims, cin, cout, dgrad_form, ks);
     VNB_CUDA_OK(cudaDeviceSynchronize());
     VNB_CUDA_OK(cudaMemcpy(y, dy.p, V * co * 4, cudaMemcpyDeviceToHost));
     return;
   }
-#ifndef VNB_EMULATE
-  VNB_CUDA_OK(cudaFuncSetAttribute(conv5_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kC5_SMEM));
-#endif
   const float* wk = dw.as<float>();
   if (dgrad_form) {
-    VNB_LAUNCH(flip_transpose_w_kernel, 1024, 256, 0, 0, (const float*)dw.as<float>(), dwf.as<float>(), cin, cout, 125);
+    VNB_LAUNCH(flip_transpose_w_kernel, 1024, 256, 0, 0, (const float*)dw.as<float>(), dwf.as<float>(), cin, cout, ks * ks * ks);
     wk = dwf.as<float>();
   }
   Conv5Args p;
@@ -477,80 +495,84 @@ void op_conv5(int precision, const float* x, const float* w, const float* bias, 
   p.acc1 = p.acc2 = 0;
   p.dims = dims;
   p.N = n;
-  const int tiles = ((dims.W + kC5_TW - 1) / kC5_TW) * ((dims.H + kC5_TH - 1) / kC5_TH) * ((dims.D + kC5_TD - 1) / kC5_TD);
-  dim3 grid(tiles, (co + kC5_CO - 1) / kC5_CO, n);
-  VNB_LAUNCH(conv5_ref_kernel, grid, 256, kC5_SMEM, 0, p);
+  if (ks == 3) launch_conv_ref<3>(p, co); else launch_conv_ref<5>(p, co);
   VNB_CUDA_OK(cudaDeviceSynchronize());
   VNB_CUDA_OK(cudaGetLastError());
   VNB_CUDA_OK(cudaMemcpy(y, dy.p, V * co * 4, cudaMemcpyDeviceToHost));
+}
+
+void op_wgrad(int ks, int precision, const float* x, const float* dy, float* dw, int n, int d, int h, int w_, int cin, int cout) {
+  using namespace vnb;
+  const Dims dims{d, h, w_};
+  const size_t V = static_cast<size_t>(n) * d * h * w_;
+  const size_t wbytes = static_cast<size_t>(ks * ks * ks) * cin * cout * 4;
+  DevBuf bx(V * cin * 4), bdy(V * cout * 4), bdw(wbytes);
+  VNB_CUDA_OK(cudaMemcpy(bx.p, x, V * cin * 4, cudaMemcpyHostToDevice));
+  VNB_CUDA_OK(cudaMemcpy(bdy.p, dy, V * cout * 4, cudaMemcpyHostToDevice));
+  VNB_CUDA_OK(cudaMemset(bdw.p, 0, wbytes));
+  if (precision != VNB_PREC_FP32) {
+    tc_op_wgrad5(precision, bx.as<float>(), bdy.as<float>(), bdw.as<float>(), n, dims, cin, cout, ks);
+    VNB_CUDA_OK(cudaDeviceSynchronize());
+    VNB_CUDA_OK(cudaMemcpy(dw, bdw.p, wbytes, cudaMemcpyDeviceToHost));
+    return;
+  }
+  Wgrad5Args a;
+  a.in1 = bx.as<float>();
+  a.in2 = nullptr;
+  a.C1 = cin;
+  a.C2 = 0;
+  a.dz = bdy.as<float>();
+  a.Cout = cout;
+  a.dw = bdw.as<float>();
+  a.dims = dims;
+  a.N = n;
+  const long long ntiles = static_cast<long long>((w_ + kW5_TW - 1) / kW5_TW) * ((h + kW5_TH - 1) / kW5_TH) * ((d + kW5_TD - 1) / kW5_TD) * n;
+  const int pairs = ((cin + 15) / 16) * ((cout + 15) / 16);
+  a.tiles_per_block = static_cast<int>(std::max<long long>(1, ntiles / 64));
+  const long long splits = (ntiles + a.tiles_per_block - 1) / a.tiles_per_block;
+  dim3 grid(static_cast<unsigned>(splits), pairs);
+  if (ks == 3) launch_wgrad_ref<3>(a, grid); else launch_wgrad_ref<5>(a, grid);
+  VNB_CUDA_OK(cudaDeviceSynchronize());
+  VNB_CUDA_OK(cudaGetLastError());
+  VNB_CUDA_OK(cudaMemcpy(dw, bdw.p, wbytes, cudaMemcpyDeviceToHost));
 }
 }  // namespace
 
 extern "C" {
 
-int vnb_op_conv5_fprop(int device, int precision, const float* x, const float* w, const float* bias,
-                       const float* residual, float* y, int n, int d, int h, int w_, int cin, int cout) {
-  return guarded([&] {
-    need(x, "x");
-    need(w, "w");
-    need(y, "y");
-    op_device(device);
-    op_conv5(precision, x, w, bias, residual, y, n, vnb::Dims{d, h, w_}, cin, cout, false);
-  });
-}
-int vnb_op_conv5_dgrad(int device, int precision, const float* dy, const float* w, float* dx, int n, int d, int h,
-                       int w_, int cin, int cout) {
-  return guarded([&] {
-    need(dy, "dy");
-    need(w, "w");
-    need(dx, "dx");
-    op_device(device);
-    op_conv5(precision, dy, w, nullptr, nullptr, dx, n, vnb::Dims{d, h, w_}, cin, cout, true);
-  });
-}
-int vnb_op_conv5_wgrad(int device, int precision, const float* x, const float* dy, float* dw, int n, int d, int h,
-                       int w_, int cin, int cout) {
-  return guarded([&] {
-    using namespace vnb;
-    need(x, "x");
-    need(dy, "dy");
-    need(dw, "dw");
-    op_device(device);
-    const Dims dims{d, h, w_};
-    const size_t V = static_cast<size_t>(n) * d * h * w_;
-    DevBuf bx(V * cin * 4), bdy(V * cout * 4), bdw(125ull * cin * cout * 4);
-    VNB_CUDA_OK(cudaMemcpy(bx.p, x, V * cin * 4, cudaMemcpyHostToDevice));
-    VNB_CUDA_OK(cudaMemcpy(bdy.p, dy, V * cout * 4, cudaMemcpyHostToDevice));
-    VNB_CUDA_OK(cudaMemset(bdw.p, 0, 125ull * cin * cout * 4));
-    if (precision != VNB_PREC_FP32) {
-      tc_op_wgrad5(precision, bx.as<float>(), bdy.as<float>(), bdw.as<float>(), n, dims, cin, cout);
-      VNB_CUDA_OK(cudaDeviceSynchronize());
-      VNB_CUDA_OK(cudaMemcpy(dw, bdw.p, 125ull * cin * cout * 4, cudaMemcpyDeviceToHost));
-      return;
-    }
-#ifndef VNB_EMULATE
-    VNB_CUDA_OK(cudaFuncSetAttribute(conv5_wgrad_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kW5_SMEM));
-#endif
-    Wgrad5Args a;
-    a.in1 = bx.as<float>();
-    a.in2 = nullptr;
-    a.C1 = cin;
-    a.C2 = 0;
-    a.dz = bdy.as<float>();
-    a.Cout = cout;
-    a.dw = bdw.as<float>();
-    a.dims = dims;
-    a.N = n;
-    const long long ntiles = static_cast<long long>((w_ + kW5_TW - 1) / kW5_TW) * ((h + kW5_TH - 1) / kW5_TH) * ((d + kW5_TD - 1) / kW5_TD) * n;
-    const int pairs = ((cin + 15) / 16) * ((cout + 15) / 16);
-    a.tiles_per_block = static_cast<int>(std::max<long long>(1, ntiles / 64));
-    const long long splits = (ntiles + a.tiles_per_block - 1) / a.tiles_per_block;
-    dim3 grid(static_cast<unsigned>(splits), pairs);
-    VNB_LAUNCH(conv5_wgrad_ref_kernel, grid, 256, kW5_SMEM, 0, a);
-    VNB_CUDA_OK(cudaDeviceSynchronize());
-    VNB_CUDA_OK(cudaGetLastError());
-    VNB_CUDA_OK(cudaMemcpy(dw, bdw.p, 125ull * cin * cout * 4, cudaMemcpyDeviceToHost));
-  });
-}
+#define VNB_DEFINE_CONV_OPS(KS)                                                                                      \
+  int vnb_op_conv##KS##_fprop(int device, int precision, const float* x, const float* w, const float* bias,           \
+                              const float* residual, float* y, int n, int d, int h, int w_, int cin, int cout) {      \
+    return guarded([&] {                                                                                              \
+      need(x, "x");                                                                                                   \
+      need(w, "w");                                                                                                   \
+      need(y, "y");                                                                                                   \
+      op_device(device);                                                                                              \
+      op_conv(KS, precision, x, w, bias, residual, y, n, vnb::Dims{d, h, w_}, cin, cout, false);                      \
+    });                                                                                                               \
+  }                                                                                                                   \
+  int vnb_op_conv##KS##_dgrad(int device, int precision, const float* dy, const float* w, float* dx, int n, int d,    \
+                              int h, int w_, int cin, int cout) {                                                     \
+    return guarded([&] {                                                                                              \
+      need(dy, "dy");                                                                                                 \
+      need(w, "w");                                                                                                   \
+      need(dx, "dx");                                                                                                 \
+      op_device(device);                                                                                              \
+      op_conv(KS, precision, dy, w, nullptr, nullptr, dx, n, vnb::Dims{d, h, w_}, cin, cout, true);                   \
+    });                                                                                                               \
+  }                                                                                                                   \
+  int vnb_op_conv##KS##_wgrad(int device, int precision, const float* x, const float* dy, float* dw, int n, int d,    \
+                              int h, int w_, int cin, int cout) {                                                     \
+    return guarded([&] {                                                                                              \
+      need(x, "x");                                                                                                   \
+      need(dy, "dy");                                                                                                 \
+      need(dw, "dw");                                                                                                 \
+      op_device(device);                                                                                              \
+      op_wgrad(KS, precision, x, dy, dw, n, d, h, w_, cin, cout);                                                     \
+    });                                                                                                               \
+  }
+VNB_DEFINE_CONV_OPS(5)
+VNB_DEFINE_CONV_OPS(3)
+#undef VNB_DEFINE_CONV_OPS
 
 }  // extern "C"

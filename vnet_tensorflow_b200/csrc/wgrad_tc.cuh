@@ -33,14 +33,17 @@ struct WgGeom {
   int npl;           // 1 (bf16) or 2 (hi/lo)
 };
 
-template <int NSPLIT>
+// KS = 3 serves the attention / output module convolutions with the same scheme: 3 useful kw atoms of 8,
+// N = 3 x 16, three kd accumulators.
+template <int NSPLIT, int KS>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ TmaDesc x1_lo,
                  const __grid_constant__ TmaDesc x2_hi, const __grid_constant__ TmaDesc x2_lo,
                  const __grid_constant__ TmaDesc z_hi, const __grid_constant__ TmaDesc z_lo, const WgGeom g,
-                 float* __restrict__ partial /* [split][pair][125][16][16] */) {
+                 float* __restrict__ partial /* [split][pair][KS^3][16][16] */) {
   using namespace sm100;
   constexpr int NPL = NSPLIT == 3 ? 2 : 1;
+  constexpr int RC = KS / 2, NB = KS * 16, TAPS = KS * KS * KS;
   VNB_DYN_SMEM(uint8_t, smem_raw);
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -96,7 +99,7 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
       int xs = 0, zs = 0;
       uint32_t xph = 0, zph = 0;
       const uint32_t x_tx = static_cast<uint32_t>(g.HT) * (g.W + 8) * 32u * NPL;
-      const uint32_t z_tx = static_cast<uint32_t>(g.HT + 4) * g.W * 32u * NPL;
+      const uint32_t z_tx = static_cast<uint32_t>(g.HT + KS - 1) * g.W * 32u * NPL;
       for (int item = split; item < n_items; item += g.splits) {
         const int hb = item % g.n_hb;
         const int dx = (item / g.n_hb) % g.D;
@@ -104,18 +107,18 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
         const int h0 = hb * g.HT;
         mbar_wait(xempty(xs), xph ^ 1u);
         mbar_expect_tx(xfull(xs), x_tx);
-        tma_load_5d(x_ring + (xs * NPL) * g.xt_bytes, xh, xfull(xs), xc, -2, h0, dx, n);
-        if (NSPLIT == 3) tma_load_5d(x_ring + (xs * NPL + 1) * g.xt_bytes, xl, xfull(xs), xc, -2, h0, dx, n);
+        tma_load_5d(x_ring + (xs * NPL) * g.xt_bytes, xh, xfull(xs), xc, -RC, h0, dx, n);
+        if (NSPLIT == 3) tma_load_5d(x_ring + (xs * NPL + 1) * g.xt_bytes, xl, xfull(xs), xc, -RC, h0, dx, n);
         if (++xs == 2) {
           xs = 0;
           xph ^= 1u;
         }
-        for (int kd = 0; kd < 5; ++kd) {
-          const int dz = dx - kd + 2;
+        for (int kd = 0; kd < KS; ++kd) {
+          const int dz = dx - kd + RC;
           mbar_wait(zempty(zs), zph ^ 1u);
           mbar_expect_tx(zfull(zs), z_tx);
-          tma_load_5d(z_ring + (zs * NPL) * g.zt_bytes, &z_hi, zfull(zs), co_chunk * 16, 0, h0 - 2, dz, n);
-          if (NSPLIT == 3) tma_load_5d(z_ring + (zs * NPL + 1) * g.zt_bytes, &z_lo, zfull(zs), co_chunk * 16, 0, h0 - 2, dz, n);
+          tma_load_5d(z_ring + (zs * NPL) * g.zt_bytes, &z_hi, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
+          if (NSPLIT == 3) tma_load_5d(z_ring + (zs * NPL + 1) * g.zt_bytes, &z_lo, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
           if (++zs == g.z_stages) {
             zs = 0;
             zph ^= 1u;
@@ -125,7 +128,7 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_instr_desc(128, 80, FMT_BF16, 1, 1);
+      const uint32_t idesc = make_instr_desc(128, NB, FMT_BF16, 1, 1);
       const uint32_t sbo_a = lpm == 2 ? x_pitch : 256u;   // K rows 8..15: next line (W = 8) or next 8 voxels
       const uint32_t sbo_b = 256u;                         // dZ lines are contiguous, so both cases are +256 B
       int xs = 0, zs = 0;
@@ -135,11 +138,11 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
         mbar_wait(xfull(xs), xph);
         tc_fence_after_sync();
         const uint32_t xa_hi = x_ring + (xs * NPL) * g.xt_bytes;
-        for (int kd = 0; kd < 5; ++kd) {
+        for (int kd = 0; kd < KS; ++kd) {
           mbar_wait(zfull(zs), zph);
           tc_fence_after_sync();
           const uint32_t za_hi = z_ring + (zs * NPL) * g.zt_bytes;
-          const uint32_t d_addr = tmem + kd * 80;
+          const uint32_t d_addr = tmem + kd * NB;
           // only the start-address field changes between MMAs: one base descriptor per operand, 64-bit adds after
           const uint64_t da0 = make_smem_desc(xa_hi, 32, sbo_a, SWZ_32B);
           const uint64_t da0_lo = da0 + (static_cast<uint32_t>(g.xt_bytes) >> 4);
@@ -182,18 +185,18 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
     mbar_wait(done_bar, 0);
     tc_fence_after_sync();
     const bool has_work = split < n_items;
-    float* out = partial + (static_cast<size_t>(split) * (g.n_ci * g.n_co) + pair) * (125 * 256);
-    for (int kd = 0; kd < 5; ++kd)
-      for (int l = 0; l < 5; ++l) {
+    float* out = partial + (static_cast<size_t>(split) * (g.n_ci * g.n_co) + pair) * (TAPS * 256);
+    for (int kd = 0; kd < KS; ++kd)
+      for (int l = 0; l < KS; ++l) {
         uint32_t v[16];
         if (has_work) {
-          tmem_ld16(tmem + (static_cast<uint32_t>(q * 32) << 16) + kd * 80 + l * 16, v);
+          tmem_ld16(tmem + (static_cast<uint32_t>(q * 32) << 16) + kd * NB + l * 16, v);
           tmem_ld_wait();
         } else {
           for (int i = 0; i < 16; ++i) v[i] = 0u;
         }
-        if (j < 5) {
-          const int tap = (kd * 5 + (4 - l)) * 5 + j;
+        if (j < KS) {
+          const int tap = (kd * KS + (KS - 1 - l)) * KS + j;
           float4* o = reinterpret_cast<float4*>(out + (tap * 16 + ci) * 16);
           for (int i = 0; i < 4; ++i)
             o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
@@ -208,9 +211,9 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
 
 // dw[tap][ci][co] = sum_split partial[split][pair(ci/16, co/16)][tap][ci%16][co%16]   (fixed order)
 __global__ void wgrad5_reduce_kernel(const float* __restrict__ partial, int splits, int n_ci, int n_co, int Cin, int Cout,
-                                     float* __restrict__ dw) {
+                                     float* __restrict__ dw, int taps = 125) {
   // Cin = real input channels of dw; the GEMM may have run on a zero-padded multiple of 16 (n_ci chunks)
-  const long long total = 125LL * Cin * Cout;
+  const long long total = static_cast<long long>(taps) * Cin * Cout;
   const int pairs = n_ci * n_co;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -218,9 +221,9 @@ __global__ void wgrad5_reduce_kernel(const float* __restrict__ partial, int spli
     const int ci = static_cast<int>((i / Cout) % Cin);
     const int tap = static_cast<int>(i / (static_cast<long long>(Cout) * Cin));
     const int pair = (ci / 16) * n_co + co / 16;
-    const size_t off = (static_cast<size_t>(pair) * 125 + tap) * 256 + (ci % 16) * 16 + co % 16;
+    const size_t off = (static_cast<size_t>(pair) * taps + tap) * 256 + (ci % 16) * 16 + co % 16;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += partial[static_cast<size_t>(sp) * pairs * (125 * 256) + off];
+    for (int sp = 0; sp < splits; ++sp) s += partial[static_cast<size_t>(sp) * pairs * (static_cast<size_t>(taps) * 256) + off];
     dw[i] = s;
   }
 }
@@ -228,12 +231,15 @@ __global__ void wgrad5_reduce_kernel(const float* __restrict__ partial, int spli
 struct WgPlan {
   bool valid = false;
   WgGeom g{};
+  int KS = 5;
   TmaDesc x1_hi, x1_lo, x2_hi, x2_lo, z_hi, z_lo;
   size_t smem = 0;
   size_t partial_floats = 0;
 };
 
-inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int C2, int Cout, bool split3, int sms) {
+inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int C2, int Cout, bool split3, int sms,
+                             int ks = 5) {
+  pl.KS = ks;
   if (C1 % 16 || C2 % 16 || Cout % 16 || C1 <= 0) return false;
   if (!(W == 8 || W == 16 || W == 32 || W == 64 || W == 128)) return false;
   WgGeom& g = pl.g;
@@ -244,7 +250,7 @@ inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int
   if (split3) ht = std::max(2, ht / 2);
   ht = std::min(ht, H);
   if (W == 8 && (ht % 2)) return false;
-  if (ht + 4 > 256 || W + 8 > 256) return false;
+  if (ht + ks - 1 > 256 || W + 8 > 256) return false;
   g.HT = ht;
   g.n_hb = (H + ht - 1) / ht;
   g.n_ci = (C1 + C2) / 16;
@@ -253,12 +259,12 @@ inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int
   const int items = N * D * g.n_hb;
   g.splits = std::max(1, std::min(items, (sms + pairs - 1) / pairs));
   g.xt_bytes = ((ht * (W + 8) * 32 + 1023) / 1024) * 1024;
-  g.zt_bytes = (((ht + 4) * W * 32 + 1023) / 1024) * 1024;
+  g.zt_bytes = (((ht + ks - 1) * W * 32 + 1023) / 1024) * 1024;
   const int budget = 200 * 1024 - 2 * g.npl * g.xt_bytes - 1024;
   g.z_stages = std::min(8, budget / (g.npl * g.zt_bytes));
   if (g.z_stages < 2) return false;
   pl.smem = 2 * g.npl * g.xt_bytes + static_cast<size_t>(g.z_stages) * g.npl * g.zt_bytes + 256 + 1024;
-  pl.partial_floats = static_cast<size_t>(g.splits) * pairs * 125 * 256;
+  pl.partial_floats = static_cast<size_t>(g.splits) * pairs * (ks * ks * ks) * 256;
   return true;
 }
 
@@ -287,40 +293,39 @@ inline void wg_encode_plan(WgPlan& pl, int Nmax, const uint16_t* x1_hi, const ui
     pl.x2_hi = pl.x1_hi;
     pl.x2_lo = pl.x1_lo;
   }
-  wg_encode_act(&pl.z_hi, z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.W, g.HT + 4);
-  wg_encode_act(&pl.z_lo, z_lo ? z_lo : z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.W, g.HT + 4);
+  wg_encode_act(&pl.z_hi, z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.W, g.HT + pl.KS - 1);
+  wg_encode_act(&pl.z_lo, z_lo ? z_lo : z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.W, g.HT + pl.KS - 1);
+}
+
+template <int NSPLIT, int KS>
+inline void wg_launch_inst(const WgPlan& pl, const WgGeom& g, int grid, float* partial, cudaStream_t stream) {
+  auto kfn = wgrad5_tc_kernel<NSPLIT, KS>;
+#ifndef VNB_EMULATE
+  static bool attr = false;
+  if (!attr && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    throw std::runtime_error("CUDA: cannot reserve shared memory for wgrad5_tc_kernel");
+  attr = true;
+#endif
+  VNB_LAUNCH(kfn, grid, kWgThreads, pl.smem, stream, pl.x1_hi, pl.x1_lo, pl.x2_hi, pl.x2_lo, pl.z_hi, pl.z_lo, g, partial);
 }
 
 inline void wg_launch(const WgPlan& pl, int N, bool split3, float* partial, float* dw, cudaStream_t stream, int cin_real = 0) {
   WgGeom g = pl.g;
   g.N = N;
-  const int items = N * g.D * g.n_hb;
-  (void)items;
   const int pairs = g.n_ci * g.n_co;
   const int grid = pairs * g.splits;
-  if (split3) {
-    auto kfn = wgrad5_tc_kernel<3>;
-#ifndef VNB_EMULATE
-    static bool attr3 = false;
-    if (!attr3 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      throw std::runtime_error("CUDA: cannot reserve shared memory for wgrad5_tc_kernel");
-    attr3 = true;
-#endif
-    VNB_LAUNCH(kfn, grid, kWgThreads, pl.smem, stream, pl.x1_hi, pl.x1_lo, pl.x2_hi, pl.x2_lo, pl.z_hi, pl.z_lo, g, partial);
+  if (pl.KS == 3) {
+    if (split3) wg_launch_inst<3, 3>(pl, g, grid, partial, stream);
+    else wg_launch_inst<1, 3>(pl, g, grid, partial, stream);
   } else {
-    auto kfn = wgrad5_tc_kernel<1>;
-#ifndef VNB_EMULATE
-    static bool attr1 = false;
-    if (!attr1 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
-      throw std::runtime_error("CUDA: cannot reserve shared memory for wgrad5_tc_kernel");
-    attr1 = true;
-#endif
-    VNB_LAUNCH(kfn, grid, kWgThreads, pl.smem, stream, pl.x1_hi, pl.x1_lo, pl.x2_hi, pl.x2_lo, pl.z_hi, pl.z_lo, g, partial);
+    if (split3) wg_launch_inst<3, 5>(pl, g, grid, partial, stream);
+    else wg_launch_inst<1, 5>(pl, g, grid, partial, stream);
   }
   const int cin = cin_real > 0 ? cin_real : g.C1 + g.C2;
-  const long long total = 125LL * cin * g.Cout;
+  const int taps = pl.KS * pl.KS * pl.KS;
+  const long long total = static_cast<long long>(taps) * cin * g.Cout;
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 2368));
-  VNB_LAUNCH(wgrad5_reduce_kernel, blocks, 256, 0, stream, (const float*)partial, g.splits, g.n_ci, g.n_co, cin, g.Cout, dw);
+  VNB_LAUNCH(wgrad5_reduce_kernel, blocks, 256, 0, stream, (const float*)partial, g.splits, g.n_ci, g.n_co, cin, g.Cout, dw, taps);
 }
 
 }  // namespace vnb
