@@ -225,6 +225,38 @@ def test_conv5_ops_match_torch(gpu_lib, cin, cout, dims, precision):
     assert rel_err(dw, wt.grad.numpy()) < 5 * tol
 
 
+@pytest.mark.parametrize("cin,cout,dims", [(64, 64, (8, 8, 32)), (16, 64, (4, 6, 16)), (64, 32, (3, 8, 128)), (2, 64, (5, 6, 7))])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_conv3_ops_match_torch(gpu_lib, cin, cout, dims, precision):
+    """3^3 SAME convolution of the attention / output modules (attention.py:63-92): forward, input and filter gradient."""
+    import ctypes as C
+    import torch.nn.functional as F
+    if precision != "fp32" and (cin % 16 or cout % 16 or dims[2] not in (8, 16, 32, 64, 128)):
+        pytest.skip("shape outside the tensor-core kernels' domain: the engine runs such layers on the fp32 kernels")
+    rng = np.random.default_rng(9)
+    n = 2
+    x = rng.normal(0, 1, (n,) + dims + (cin,)).astype(np.float32)
+    w = rng.normal(0, 0.1, (3, 3, 3, cin, cout)).astype(np.float32)
+    b = rng.normal(0, 1, (cout,)).astype(np.float32)
+    dy = rng.normal(0, 1, (n,) + dims + (cout,)).astype(np.float32)
+    rnd = (lambda a: torch.from_numpy(a).to(torch.bfloat16).to(torch.float64)) if precision == "bf16" else (lambda a: torch.from_numpy(a).double())
+    xt, wt = rnd(x).requires_grad_(True), rnd(w).requires_grad_(True)
+    y_ref = F.conv3d(xt.permute(0, 4, 1, 2, 3), wt.permute(4, 3, 0, 1, 2), padding=1).permute(0, 2, 3, 4, 1) + torch.from_numpy(b).double()
+    y_ref.backward(rnd(dy))
+    prec = {"fp32": 0, "bf16x3": 1, "bf16": 2}[precision]
+    tol = {"fp32": 1e-5, "bf16x3": 3e-5, "bf16": 2e-6}[precision]   # bf16: exact products of the rounded operands
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    y = np.empty_like(dy)
+    gpu_lib.check(gpu_lib.vnb_op_conv3_fprop(0, prec, ptr(x), ptr(w), ptr(b), None, ptr(y), n, *dims, cin, cout))
+    assert rel_err(y, y_ref.detach().numpy()) < tol
+    dx = np.empty_like(x)
+    gpu_lib.check(gpu_lib.vnb_op_conv3_dgrad(0, prec, ptr(dy), ptr(w), ptr(dx), n, *dims, cin, cout))
+    assert rel_err(dx, xt.grad.numpy()) < tol
+    dw = np.empty_like(w)
+    gpu_lib.check(gpu_lib.vnb_op_conv3_wgrad(0, prec, ptr(x), ptr(dy), ptr(dw), n, *dims, cin, cout))
+    assert rel_err(dw, wt.grad.numpy()) < 5 * tol
+
+
 def test_full_size_properties_128cube(gpu_lib):
     """BASELINE config #2 size (128^3, batch 2): size-independent properties instead of the oracle --
     determinism of the forward, bias invariance of the logits, Dice of a perfect prediction,
