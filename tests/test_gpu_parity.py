@@ -192,13 +192,15 @@ def test_three_training_steps_follow_the_oracle(gpu_lib, precision):
 
 
 @pytest.mark.parametrize("cin,cout,dims", [(16, 16, (8, 8, 16)), (32, 16, (4, 8, 32)), (64, 32, (8, 8, 8)),
-                                           (4, 16, (6, 5, 9)), (128, 128, (4, 4, 4))])
+                                           (4, 16, (6, 5, 9)), (128, 128, (4, 4, 4)),
+                                           (16, 16, (4, 6, 24)), (32, 32, (2, 4, 48)), (64, 64, (2, 2, 96)),
+                                           (16, 32, (2, 3, 192)), (32, 16, (3, 4, 160)), (128, 128, (2, 12, 12))])
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_conv5_ops_match_torch(gpu_lib, cin, cout, dims, precision):
     """Per-op hooks: 5^3 SAME convolution forward, input gradient and filter gradient."""
     import ctypes as C
-    if precision != "fp32" and (cin % 16 or cout % 16 or dims[2] not in (8, 16, 32, 64, 128)):
-        pytest.skip("shape outside the tensor-core kernels' domain (channels % 16, W in 8..128): the engine runs "
+    if precision != "fp32" and (cin % 16 or cout % 16 or dims[2] < 8):
+        pytest.skip("shape outside the tensor-core kernels' domain (channels % 16, W >= 8): the engine runs "
                     "such layers on the fp32 kernels")
     rng = np.random.default_rng(7)
     n = 2
@@ -225,13 +227,14 @@ def test_conv5_ops_match_torch(gpu_lib, cin, cout, dims, precision):
     assert rel_err(dw, wt.grad.numpy()) < 5 * tol
 
 
-@pytest.mark.parametrize("cin,cout,dims", [(64, 64, (8, 8, 32)), (16, 64, (4, 6, 16)), (64, 32, (3, 8, 128)), (2, 64, (5, 6, 7))])
+@pytest.mark.parametrize("cin,cout,dims", [(64, 64, (8, 8, 32)), (16, 64, (4, 6, 16)), (64, 32, (3, 8, 128)), (2, 64, (5, 6, 7)),
+                                           (64, 64, (2, 3, 192)), (64, 64, (3, 5, 24))])
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
 def test_conv3_ops_match_torch(gpu_lib, cin, cout, dims, precision):
     """3^3 SAME convolution of the attention / output modules (attention.py:63-92): forward, input and filter gradient."""
     import ctypes as C
     import torch.nn.functional as F
-    if precision != "fp32" and (cin % 16 or cout % 16 or dims[2] not in (8, 16, 32, 64, 128)):
+    if precision != "fp32" and (cin % 16 or cout % 16 or dims[2] < 8):
         pytest.skip("shape outside the tensor-core kernels' domain: the engine runs such layers on the fp32 kernels")
     rng = np.random.default_rng(9)
     n = 2

@@ -22,6 +22,11 @@ def _bf16(x):
     (32, 32, (2, 4, 16), 2, 1),     # CT=32, SW64, two k-steps per stage
     (32, 16, (3, 8, 16), 1, 2),     # two output slices in dgrad
     (64, 32, (4, 8, 8), 1, 1),      # box spanning two d-planes
+    (16, 16, (2, 5, 24), 1, 1),     # W does not divide 128: five whole lines per MMA tile, tile stride 120 rows
+    (32, 32, (3, 4, 48), 1, 2),     # two lines per tile (96 of 128 rows used)
+    (16, 32, (2, 3, 192), 1, 1),    # W > 128: two haloed 96-wide segments per line
+    (32, 16, (2, 4, 160), 1, 2),    # W > 128, CT = 32 forward / 16 backward
+    (16, 16, (3, 5, 16), 1, 1),     # odd H: the box (5 lines x 4 planes) leaves MMA rows unused, last d-block partial
 ])
 def test_conv5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
     rng = np.random.default_rng(7)
@@ -46,11 +51,11 @@ def test_conv5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
 
 
 def test_unsupported_shapes_are_rejected_not_miscomputed(emul_lib):
-    x = np.zeros((1, 3, 5, 16, 16), np.float32)
-    w = np.zeros((5, 5, 5, 16, 16), np.float32)
+    x = np.zeros((1, 3, 5, 16, 8), np.float32)
+    w = np.zeros((5, 5, 5, 8, 16), np.float32)
     y = np.zeros((1, 3, 5, 16, 16), np.float32)
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
-    rc = emul_lib.vnb_op_conv5_fprop(0, 1, ptr(x), ptr(w), None, None, ptr(y), 1, 3, 5, 16, 16, 16)
+    rc = emul_lib.vnb_op_conv5_fprop(0, 1, ptr(x), ptr(w), None, None, ptr(y), 1, 3, 5, 16, 8, 16)   # Cin = 8
     assert rc == -1 and b"not supported" in emul_lib.vnb_last_error()
 
 
@@ -84,6 +89,9 @@ def test_engine_bf16x3_matches_oracle(emul_lib):
     (32, 16, (2, 4, 64), 1, 2),     # two ci chunks
     (16, 32, (3, 8, 8), 1, 1),      # W = 8: one K step spans two lines
     (16, 16, (2, 3, 128), 1, 2),    # full-width lines
+    (16, 16, (2, 4, 24), 1, 1),     # W not a multiple of the K step: boxes rounded to 32, TMA zero fill past the line
+    (16, 16, (2, 3, 12), 1, 2),     # W = 12 -> one K step of 16
+    (16, 16, (1, 3, 192), 1, 2),    # W > 128
 ])
 def test_wgrad5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
     """MN-major overlapping-atom tap folding (kw on M, kh on N, kd on five TMEM accumulators)."""
@@ -153,7 +161,7 @@ def test_conv3_kernels_match_torch(emul_lib, cin, cout, dims, n, prec):
     dx = np.empty_like(x)
     emul_lib.check(emul_lib.vnb_op_conv3_dgrad(0, prec, ptr(dy), ptr(w), ptr(dx), n, *dims, cin, cout))
     assert rel_err(dx, xt.grad.numpy()) < tol
-    if prec == 0 or dims[2] in (8, 16, 32, 64, 128):
+    if True:
         dw = np.empty_like(w)
         emul_lib.check(emul_lib.vnb_op_conv3_wgrad(0, prec, ptr(x), ptr(dy), ptr(dw), n, *dims, cin, cout))
         assert rel_err(dw, wt.grad.numpy()) < (3e-5 if prec != 2 else 1e-5)
@@ -181,6 +189,29 @@ def test_attention_engine_bf16x3_matches_oracle(emul_lib):
     assert int((am != R.predict(out["logits_output"]).numpy()).sum()) == 0
     g = eng.get_grads()
     for k, v in g.items():
+        if analytically_zero(k, spec):
+            continue
+        ref = go[k].numpy().astype(np.float64)
+        assert np.sqrt(((v - ref) ** 2).sum()) <= 5e-2 * max(np.sqrt((ref ** 2).sum()), 1e-9), k
+    eng.close()
+
+
+def test_engine_patch_24_runs_on_tensor_cores(emul_lib):
+    """PatchShape not a power of two (W = 24 and 12 along the levels, as in BASELINE config #5's 192 -> 96 -> 48 -> 24
+    -> 12): every 5^3 convolution still takes the tensor-core path (lines that do not divide the 128-row MMA tile)."""
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=16, num_levels=1, num_convolutions=(2,), bottom_convolutions=1)
+    P, N = 24, 1
+    params = perturbed_params(spec)
+    img, lab = synth_batch(2, N, P, 1, 2)
+    eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 1.0), emul_lib, precision="bf16x3")
+    eng.set_params(params)
+    l = eng.forward_backward(img, lab)
+    lo, lg, go, _ = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
+    logits, _, am = eng.forward(img)
+    assert abs(l - float(lo)) < 2e-6
+    assert rel_err(logits, lg.numpy()) < 1e-4
+    assert int((am != R.predict(lg).numpy()).sum()) == 0
+    for k, v in eng.get_grads().items():
         if analytically_zero(k, spec):
             continue
         ref = go[k].numpy().astype(np.float64)

@@ -61,8 +61,15 @@ struct TcGeom {
   int N, D, H, W;      // activation extents
   int C1, C2;          // channels of the two concatenated inputs (C2 may be 0)
   int Co1, Co2;        // output channel split (Co2 may be 0)
-  int T;               // 128-row tiles per work item (<= TMAX)
-  int bh, bd;          // box extent in lines (h) and planes (d): W*bh*bd == T*128
+  int T;               // 128-row MMA tiles per work item (<= TMAX)
+  int bh, bd;          // box extent in lines (h) and planes (d): bh*bd == T*lpt
+  // row geometry of a work item's A tile.  A "line" occupies LP consecutive rows: LP = W (whole lines, no halo:
+  // the kw neighbours of a voxel outside the line are SAME padding) or, for W > 128, LP = Wt + KS - 1 rows of a
+  // Wt-wide segment with its halo (TMA zero-fills what lies outside the volume).  MMA tile t starts at row
+  // t*tile_rows (tile_rows = lpt*LP <= 128) and always spans 128 rows; rows past lpt lines are ignored.
+  int LP, lpt, tile_rows;
+  int halo;            // 1: segment mode
+  int Wt, n_wb;        // segment width and segments per line (W, 1 without halo)
   int n_hb, n_db;      // blocks per sample along h and d
   int n_slices;        // (Co1+Co2) / CT
   int n_kc;            // (C1+C2) / KC
@@ -105,6 +112,8 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_ba
       if (Cfg::EG == 2 && (j & 1) != eg) continue;      // with two groups, group == accumulator buffer
       const int slice = item % g.n_slices;
       int x = item / g.n_slices;
+      const int wb = x % g.n_wb;
+      x /= g.n_wb;
       const int hb = x % g.n_hb;
       x /= g.n_hb;
       const int db = x % g.n_db;
@@ -114,11 +123,12 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_ba
       mbar_wait(tfull_bar(buf), use & 1u);
       tc_fence_after_sync();
       for (int t = 0; t < g.T; ++t) {
-        const int R = t * 128 + r;
-        const int w = R % g.W;
-        const int line = R / g.W;
+        const int lt = r / g.LP, i = r % g.LP;          // line inside this MMA tile, row inside the line
+        const int line = t * g.lpt + lt;
+        const int w = g.halo ? wb * g.Wt + i - RC : i;
         const int gh = hb * g.bh + line % g.bh, gd = db * g.bd + line / g.bh;
-        const bool valid = gh < g.H && gd < g.D;
+        const bool valid = lt < g.lpt && line < g.bh * g.bd && gh < g.H && gd < g.D && w >= 0 && w < g.W &&
+                           (!g.halo || (i >= RC && i < g.Wt + RC));
         const long long vox = ((static_cast<long long>(n) * g.D + gd) * g.H + gh) * g.W + w;
         const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::BUF_COLS + t * Cfg::NB;
 #pragma unroll 1
@@ -255,7 +265,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *slot_ptr;
-  const uint32_t a_rows = static_cast<uint32_t>(g.T * 128 + (KS - 1) * g.W);   // rows held per A stage
+  const uint32_t a_rows = static_cast<uint32_t>((g.bh + KS - 1) * g.LP);   // rows loaded per A stage
 
   if (warp == 0) {
     if (lane == 0) {
@@ -264,11 +274,14 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         const int slice = item % g.n_slices;
         int x = item / g.n_slices;
+        const int wb = x % g.n_wb;
+        x /= g.n_wb;
         const int hb = x % g.n_hb;
         x /= g.n_hb;
         const int db = x % g.n_db;
         const int n = x / g.n_db;
         const int h0 = hb * g.bh, d0 = db;
+        const int w0 = g.halo ? wb * g.Wt - RC : 0;
         for (int kd = 0; kd < KS; ++kd)
           for (int kc = 0; kc < g.n_kc; ++kc) {
             mbar_wait(aempty(as), aph ^ 1u);
@@ -276,8 +289,8 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
             const bool src1 = kc < kc1;
             const int cch = (src1 ? kc : kc - kc1) * KC;
             const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
-            tma_load_5d(a_addr, src1 ? &a1_hi : &a2_hi, afull(as), cch, 0, h0 - RC, d0 + kd - RC, n);
-            if (NSPLIT == 3) tma_load_5d(a_addr + g.a_stage_bytes, src1 ? &a1_lo : &a2_lo, afull(as), cch, 0, h0 - RC, d0 + kd - RC, n);
+            tma_load_5d(a_addr, src1 ? &a1_hi : &a2_hi, afull(as), cch, w0, h0 - RC, d0 + kd - RC, n);
+            if (NSPLIT == 3) tma_load_5d(a_addr + g.a_stage_bytes, src1 ? &a1_lo : &a2_lo, afull(as), cch, w0, h0 - RC, d0 + kd - RC, n);
             if (++as == g.n_a) {
               as = 0;
               aph ^= 1u;
@@ -327,7 +340,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
               for (int t = 0; t < g.T; ++t) {
 #pragma unroll
                 for (int ks = 0; ks < KC / 16; ++ks) {
-                  const uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t * 128 + kh * g.W) * Cfg::ROWB + ks * 32) >> 4);
+                  const uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t * g.tile_rows + kh * g.LP) * Cfg::ROWB + ks * 32) >> 4);
                   const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
                   const uint32_t acc = (first && ks == 0) ? 0u : 1u;
                   const uint32_t d_addr = d_base + t * Cfg::NB;
@@ -421,24 +434,27 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         const int slice = item % g.n_slices;
         int x = item / g.n_slices;
+        const int wb = x % g.n_wb;
+        x /= g.n_wb;
         const int hb = x % g.n_hb;
         x /= g.n_hb;
         const int db = x % g.n_db;
         const int n = x / g.n_db;
         const int h0 = hb * g.bh, d0 = db * g.bd;
+        const int w0 = g.halo ? wb * g.Wt - RC : 0;
         for (int it = 0; it < n_it; ++it) {
           const int kc = it % g.n_kc, kh = (it / g.n_kc) % KS, kd = it / (KS * g.n_kc);
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t st_addr = sm_addr + stage * Cfg::STAGE_BYTES;
-          const uint32_t a_bytes = static_cast<uint32_t>(g.T) * 128u * Cfg::ROWB;
+          const uint32_t a_bytes = static_cast<uint32_t>(g.bh * g.bd * g.LP) * Cfg::ROWB;
           mbar_expect_tx(full_bar(stage), Cfg::NPL * (a_bytes + Cfg::NB * Cfg::ROWB));
           const bool src1 = kc < kc1;
           const int cch = (src1 ? kc : kc - kc1) * KC;
-          tma_load_5d(st_addr, src1 ? &a1_hi : &a2_hi, full_bar(stage), cch, 0, h0 + kh - RC, d0 + kd - RC, n);
+          tma_load_5d(st_addr, src1 ? &a1_hi : &a2_hi, full_bar(stage), cch, w0, h0 + kh - RC, d0 + kd - RC, n);
           const int brow = (slice * n_it + it) * Cfg::NB;
           tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES, &w_hi, full_bar(stage), 0, brow);
           if (NSPLIT == 3) {
-            tma_load_5d(st_addr + Cfg::A_BYTES, src1 ? &a1_lo : &a2_lo, full_bar(stage), cch, 0, h0 + kh - RC, d0 + kd - RC, n);
+            tma_load_5d(st_addr + Cfg::A_BYTES, src1 ? &a1_lo : &a2_lo, full_bar(stage), cch, w0, h0 + kh - RC, d0 + kd - RC, n);
             tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES + Cfg::B_BYTES, &w_lo, full_bar(stage), 0, brow);
           }
           if (++stage == kTcStages) {
@@ -474,7 +490,7 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
           for (int t = 0; t < g.T; ++t) {
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks) {
-              const uint64_t aoff = static_cast<uint64_t>((t * 128 * Cfg::ROWB + ks * 32) >> 4);
+              const uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t * g.tile_rows) * Cfg::ROWB + ks * 32) >> 4);
               const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
               const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
               const uint32_t d_addr = d_base + t * Cfg::NB;
@@ -647,10 +663,10 @@ inline void tma_encode(TmaDesc* out, const void* base, int rank, const uint64_t*
 }
 
 // NDHWC bf16 activation [N][D][H][W][C] -> 5-D map (C, W, H, D, N) with box (KC, W, bh, bd, 1)
-inline void tma_encode_act(TmaDesc* out, const uint16_t* base, int N, int D, int H, int W, int C, int KC, int bh, int bd) {
+inline void tma_encode_act(TmaDesc* out, const uint16_t* base, int N, int D, int H, int W, int C, int KC, int bh, int bd, int bw = 0) {
   const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)N};
   const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2, (uint64_t)D * H * W * C * 2};
-  const uint32_t box[5] = {(uint32_t)KC, (uint32_t)W, (uint32_t)bh, (uint32_t)bd, 1};
+  const uint32_t box[5] = {(uint32_t)KC, (uint32_t)(bw > 0 ? bw : W), (uint32_t)bh, (uint32_t)bd, 1};
   tma_encode(out, base, 5, dims, str, box, KC * 2);
 }
 // packed weights [rows][KC] -> 2-D map, box (KC, NB)
@@ -686,30 +702,44 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
   } else {
     return false;
   }
-  if (W > 128 || W < 1 || 128 % W != 0) return false;
+  if (W < 1) return false;
+  // row geometry (see TcGeom): whole lines when a line fits one 128-row MMA tile, haloed segments otherwise
+  int LP, lpt, halo, Wt, n_wb;
+  if (W <= 128) {
+    halo = 0; Wt = W; n_wb = 1; LP = W; lpt = 128 / W;
+  } else {
+    halo = 1;
+    n_wb = (W + (128 - ks + 1) - 1) / (128 - ks + 1);
+    Wt = (W + n_wb - 1) / n_wb;
+    LP = Wt + ks - 1;
+    lpt = 1;
+  }
+  if (LP > 256) return false;
   const int tmax = pl.CT == 16 ? 3 : 1;
+  for (int pass = 0; pass < 2; ++pass)   // pass 0: boxes that tile the volume exactly; pass 1: accept unused rows
   for (int T = tmax; T >= 1; --T) {
-    const int lines = T * 128 / W;
+    const int lines = T * lpt;
     int bh, bd;
     if (lines <= H) {
       bh = lines;
       bd = 1;
     } else {
-      if (lines % H) continue;
+      const bool exact = lines % H == 0 && lines / H <= D && D % (lines / H) == 0;
+      if (pass == 0 && !exact) continue;
       bh = H;
-      bd = lines / H;
-      if (bd > D || D % bd) continue;
+      bd = std::min(lines / H, D);
     }
     if (bh > 256 || bd > 256) continue;
     TcGeom& g = pl.g;
     g.N = N; g.D = D; g.H = H; g.W = W;
     g.C1 = C1; g.C2 = C2; g.Co1 = Co1; g.Co2 = Co2;
     g.T = T; g.bh = bh; g.bd = bd;
+    g.LP = LP; g.lpt = lpt; g.tile_rows = lpt * LP; g.halo = halo; g.Wt = Wt; g.n_wb = n_wb;
     g.n_hb = (H + bh - 1) / bh;
-    g.n_db = D / bd;
+    g.n_db = (D + bd - 1) / bd;
     g.n_slices = (Co1 + Co2) / pl.CT;
     g.n_kc = (C1 + C2) / pl.KC;
-    g.n_items = N * g.n_db * g.n_hb * g.n_slices;
+    g.n_items = N * g.n_db * g.n_hb * g.n_wb * g.n_slices;
     // shared-memory plan: resident-lines pipeline when the box is a single d-plane and the rings fit
     const int npl = split3 ? 2 : 1;
     const int rowb = pl.KC * 2;
@@ -721,7 +751,9 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
     const size_t epi_bytes = static_cast<size_t>(split3 ? 1 : 2) * kTcEpiBytes;
     pl.smem = static_cast<size_t>(kTcStages) * npl * (tmax_rows * rowb + b_bytes) + epi_bytes + 256 + 1024;
     if (bd == 1 && !getenv("VNB_TC_NO_RESIDENT")) {
-      const int a_stage = (((T * 128 + (ks - 1) * W) * rowb + 1023) / 1024) * 1024;
+      // rows touched: loads fill (bh + ks - 1) lines, the last MMA tile reads 128 rows from its start row
+      const int rows = std::max((bh + ks - 1) * LP, (ks - 1) * LP + (T - 1) * g.tile_rows + 128);
+      const int a_stage = ((rows * rowb + 1023) / 1024) * 1024;
       for (int nb = 4; nb >= 2; --nb) {
         const size_t need = 2ull * npl * a_stage + static_cast<size_t>(nb) * npl * b_bytes + epi_bytes + 256 + 1024;
         if (need <= 227 * 1024) {

@@ -22,11 +22,11 @@ inline void tc_encode_plan(TcKernelPlan& pl, int Nmax, const uint16_t* a1_hi, co
   const TcGeom& g = pl.g;
   const int ks = pl.KS;
   const int lines = g.resident ? g.bh + ks - 1 : g.bh;   // resident mode: the box carries the halo lines
-  tma_encode_act(&pl.a1_hi, a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, lines, g.bd);
-  tma_encode_act(&pl.a1_lo, a1_lo ? a1_lo : a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, lines, g.bd);
+  tma_encode_act(&pl.a1_hi, a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, lines, g.bd, g.LP);
+  tma_encode_act(&pl.a1_lo, a1_lo ? a1_lo : a1_hi, Nmax, g.D, g.H, g.W, g.C1, pl.KC, lines, g.bd, g.LP);
   if (g.C2 > 0) {
-    tma_encode_act(&pl.a2_hi, a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, lines, g.bd);
-    tma_encode_act(&pl.a2_lo, a2_lo ? a2_lo : a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, lines, g.bd);
+    tma_encode_act(&pl.a2_hi, a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, lines, g.bd, g.LP);
+    tma_encode_act(&pl.a2_lo, a2_lo ? a2_lo : a2_hi, Nmax, g.D, g.H, g.W, g.C2, pl.KC, lines, g.bd, g.LP);
   } else {
     pl.a2_hi = pl.a1_hi;
     pl.a2_lo = pl.a1_lo;
@@ -122,7 +122,7 @@ inline void Engine::tc_run_fprop(Unit& u, int N) {
   TcArgs a;
   a.g = pl.g;
   a.g.N = N;
-  a.g.n_items = N * a.g.n_db * a.g.n_hb * a.g.n_slices;
+  a.g.n_items = N * a.g.n_db * a.g.n_hb * a.g.n_wb * a.g.n_slices;
   a.bias = params_ + u.b_off;
   a.res = u.res >= 0 ? acts_[u.res].a : nullptr;
   a.out1 = u.z;
@@ -138,7 +138,7 @@ inline void Engine::tc_run_dgrad(Unit& u, int N) {
   TcArgs a;
   a.g = pl.g;
   a.g.N = N;
-  a.g.n_items = N * a.g.n_db * a.g.n_hb * a.g.n_slices;
+  a.g.n_items = N * a.g.n_db * a.g.n_hb * a.g.n_wb * a.g.n_slices;
   a.bias = nullptr;
   a.res = nullptr;
   a.out1 = acts_[u.in1].d;
@@ -177,7 +177,7 @@ inline void tc_op_conv5(int precision, const float* x, const float* w, const flo
   const int ci = dgrad_form ? cout : cin, co = dgrad_form ? cin : cout;
   TcKernelPlan pl;
   if (!tc_plan_geometry(pl, n, dims.D, dims.H, dims.W, ci, 0, co, 0, lo, ks))
-    throw std::invalid_argument("shape not supported by the tensor-core convolution (channels % 16, W | 128)");
+    throw std::invalid_argument("shape not supported by the tensor-core convolution (channels % 16, line blocking)");
   TcScratch s;
   const size_t nx = static_cast<size_t>(n) * dims.D * dims.H * dims.W * ci;
   uint16_t* xh = s.alloc<uint16_t>(nx);

@@ -23,6 +23,7 @@ constexpr int kWgThreads = 192;
 
 struct WgGeom {
   int N, D, H, W;
+  int Wr;            // W rounded up to the MMA K step (16 voxels): boxes are Wr wide, TMA zero-fills past the line end
   int C1, C2, Cout;
   int HT;            // X lines per work item
   int n_hb;          // ceil(H / HT)
@@ -65,9 +66,9 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
   const int ci_chunk = pair / g.n_co, co_chunk = pair % g.n_co;
   const int n_items = g.N * g.D * g.n_hb;
   const int lpm = g.W == 8 ? 2 : 1;                // X lines covered by one K = 16 step
-  const int ksteps = g.W * lpm / 16;               // MMA k-steps per group of `lpm` lines
-  const uint32_t x_pitch = static_cast<uint32_t>(g.W + 8) * 32u;   // bytes between X lines in smem
-  const uint32_t z_pitch = static_cast<uint32_t>(g.W) * 32u;
+  const int ksteps = g.Wr * lpm / 16;              // MMA k-steps per group of `lpm` lines
+  const uint32_t x_pitch = static_cast<uint32_t>(g.Wr + 8) * 32u;  // bytes between X lines in smem
+  const uint32_t z_pitch = static_cast<uint32_t>(g.Wr) * 32u;
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -98,8 +99,8 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
       const TmaDesc* xl = src1 ? &x1_lo : &x2_lo;
       int xs = 0, zs = 0;
       uint32_t xph = 0, zph = 0;
-      const uint32_t x_tx = static_cast<uint32_t>(g.HT) * (g.W + 8) * 32u * NPL;
-      const uint32_t z_tx = static_cast<uint32_t>(g.HT + KS - 1) * g.W * 32u * NPL;
+      const uint32_t x_tx = static_cast<uint32_t>(g.HT) * (g.Wr + 8) * 32u * NPL;
+      const uint32_t z_tx = static_cast<uint32_t>(g.HT + KS - 1) * g.Wr * 32u * NPL;
       for (int item = split; item < n_items; item += g.splits) {
         const int hb = item % g.n_hb;
         const int dx = (item / g.n_hb) % g.D;
@@ -241,16 +242,18 @@ inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int
                              int ks = 5) {
   pl.KS = ks;
   if (C1 % 16 || C2 % 16 || Cout % 16 || C1 <= 0) return false;
-  if (!(W == 8 || W == 16 || W == 32 || W == 64 || W == 128)) return false;
+  if (W < 8) return false;
+  const int Wr = W == 8 ? 8 : (W + 15) / 16 * 16;
   WgGeom& g = pl.g;
   g.N = N; g.D = D; g.H = H; g.W = W;
+  g.Wr = Wr;
   g.C1 = C1; g.C2 = C2; g.Cout = Cout;
   g.npl = split3 ? 2 : 1;
-  int ht = std::max(2, 512 / W);
+  int ht = std::max(2, 512 / Wr);
   if (split3) ht = std::max(2, ht / 2);
   ht = std::min(ht, H);
   if (W == 8 && (ht % 2)) return false;
-  if (ht + ks - 1 > 256 || W + 8 > 256) return false;
+  if (ht + ks - 1 > 256 || Wr + 8 > 256) return false;
   g.HT = ht;
   g.n_hb = (H + ht - 1) / ht;
   g.n_ci = (C1 + C2) / 16;
@@ -258,8 +261,8 @@ inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int
   const int pairs = g.n_ci * g.n_co;
   const int items = N * D * g.n_hb;
   g.splits = std::max(1, std::min(items, (sms + pairs - 1) / pairs));
-  g.xt_bytes = ((ht * (W + 8) * 32 + 1023) / 1024) * 1024;
-  g.zt_bytes = (((ht + ks - 1) * W * 32 + 1023) / 1024) * 1024;
+  g.xt_bytes = ((ht * (Wr + 8) * 32 + 1023) / 1024) * 1024;
+  g.zt_bytes = (((ht + ks - 1) * Wr * 32 + 1023) / 1024) * 1024;
   const int budget = 200 * 1024 - 2 * g.npl * g.xt_bytes - 1024;
   g.z_stages = std::min(8, budget / (g.npl * g.zt_bytes));
   if (g.z_stages < 2) return false;
@@ -284,17 +287,17 @@ inline void wg_encode_act(TmaDesc* out, const uint16_t* base, int N, int D, int 
 inline void wg_encode_plan(WgPlan& pl, int Nmax, const uint16_t* x1_hi, const uint16_t* x1_lo, const uint16_t* x2_hi,
                            const uint16_t* x2_lo, const uint16_t* z_hi, const uint16_t* z_lo) {
   const WgGeom& g = pl.g;
-  wg_encode_act(&pl.x1_hi, x1_hi, Nmax, g.D, g.H, g.W, g.C1, g.W + 8, g.HT);
-  wg_encode_act(&pl.x1_lo, x1_lo ? x1_lo : x1_hi, Nmax, g.D, g.H, g.W, g.C1, g.W + 8, g.HT);
+  wg_encode_act(&pl.x1_hi, x1_hi, Nmax, g.D, g.H, g.W, g.C1, g.Wr + 8, g.HT);
+  wg_encode_act(&pl.x1_lo, x1_lo ? x1_lo : x1_hi, Nmax, g.D, g.H, g.W, g.C1, g.Wr + 8, g.HT);
   if (g.C2 > 0) {
-    wg_encode_act(&pl.x2_hi, x2_hi, Nmax, g.D, g.H, g.W, g.C2, g.W + 8, g.HT);
-    wg_encode_act(&pl.x2_lo, x2_lo ? x2_lo : x2_hi, Nmax, g.D, g.H, g.W, g.C2, g.W + 8, g.HT);
+    wg_encode_act(&pl.x2_hi, x2_hi, Nmax, g.D, g.H, g.W, g.C2, g.Wr + 8, g.HT);
+    wg_encode_act(&pl.x2_lo, x2_lo ? x2_lo : x2_hi, Nmax, g.D, g.H, g.W, g.C2, g.Wr + 8, g.HT);
   } else {
     pl.x2_hi = pl.x1_hi;
     pl.x2_lo = pl.x1_lo;
   }
-  wg_encode_act(&pl.z_hi, z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.W, g.HT + pl.KS - 1);
-  wg_encode_act(&pl.z_lo, z_lo ? z_lo : z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.W, g.HT + pl.KS - 1);
+  wg_encode_act(&pl.z_hi, z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.Wr, g.HT + pl.KS - 1);
+  wg_encode_act(&pl.z_lo, z_lo ? z_lo : z_hi, Nmax, g.D, g.H, g.W, g.Cout, g.Wr, g.HT + pl.KS - 1);
 }
 
 template <int NSPLIT, int KS>
