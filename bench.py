@@ -25,6 +25,19 @@ sys.path.insert(0, ROOT)
 
 TRAIN_GFLOP_PER_PATCH_128 = 3371.7   # BASELINE.md §2 (fprop + dgrad + wgrad, 128^3, M=1, K=2)
 
+# BASELINE.json configs[i]; [1] is the one the metric is quoted on (the default), the others are parity-test
+# configurations that can be timed on request with --config
+PRESETS = {
+    2: dict(patch=128, batch=2, M=1, K=2, precision="bf16x3", attention=False, weights=(0.1, 1.0), train_gflop=3371.7,
+            name="BASELINE configs[1]: 128^3, 1 modality, 2 classes, batch 2, fp32-grade"),
+    3: dict(patch=128, batch=2, M=4, K=4, precision="bf16", attention=False, weights=(0.01, 0.1, 0.5, 1.0), train_gflop=3439.0,
+            name="BASELINE configs[2]: 128^3, 4 modalities, 4 classes (BraTS-shaped), batch 2, bf16"),
+    4: dict(patch=128, batch=2, M=1, K=2, precision="bf16", attention=False, weights=(0.1, 1.0), train_gflop=3371.7,
+            name="BASELINE configs[3]: 128^3, 1 modality, 2 classes, 2 per GPU, bf16 (run with --gpus 8)"),
+    5: dict(patch=192, batch=1, M=2, K=3, precision="bf16", attention=True, weights=(0.01, 0.1, 1.0), train_gflop=59600.0,
+            name="BASELINE configs[4]: 192^3, 2 modalities, 3 classes, attention.py gating, 1 per GPU, bf16 (run with --gpus 8)"),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -32,15 +45,23 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--patch", type=int, default=128)
-    ap.add_argument("--batch", type=int, default=2, help="patches per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("VNB_BENCH_PRECISION", "bf16x3"),
-                    choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(PRESETS), help="BASELINE.json configs[i-1]")
+    ap.add_argument("--patch", type=int, default=None)
+    ap.add_argument("--batch", type=int, default=None, help="patches per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("VNB_BENCH_PRECISION"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    pre = PRESETS[args.config]
+    args.preset = pre
+    args.patch = args.patch or pre["patch"]
+    args.batch = args.batch or pre["batch"]
+    args.precision = args.precision or pre["precision"]
+    return args
 
 
-def train_gflop_per_patch(patch: int) -> float:
+def train_gflop_per_patch(patch: int, preset=None) -> float:
+    if preset is not None:
+        return preset["train_gflop"] * (patch / float(preset["patch"])) ** 3
     return TRAIN_GFLOP_PER_PATCH_128 * (patch / 128.0) ** 3
 
 
@@ -134,7 +155,8 @@ def cpu_reference_step_seconds(sample_patch: int, repeats: int, warmup: int):
     state = R.TrainState(params=R.init_params(spec, 42))
     times = []
     for i in range(warmup + repeats):
-        img, lab = synth_batch(i, 1, sample_patch, 1, 2)
+        # warm-up steps run on a 32^3 patch: they spin up the thread pool / allocator without costing a full step
+        img, lab = synth_batch(i, 1, sample_patch if i >= warmup else min(32, sample_patch), 1, 2)
         t0 = time.perf_counter()
         R.train_step(state, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
         dt = time.perf_counter() - t0
@@ -187,15 +209,18 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
     from vnet_tensorflow_b200.init import initialize
     from vnet_tensorflow_b200.engine import VNetEngine
-    from vnet_tensorflow_b200.synthetic import synth_batch
+    from vnet_tensorflow_b200.synthetic import synth_patch
 
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     P, B = args.patch, args.batch
-    eng = VNetEngine(num_classes=2, in_channels=1, patch_shape=(P, P, P), max_batch=B, precision=args.precision,
-                     loss="weighted_sorensen", loss_weights=(0.1, 1.0), optimizer="Adam", learning_rate=1e-2,
-                     decay_factor=0.99, decay_steps=100.0, device=local_rank)
+    pre = args.preset
+    M, K, att = pre["M"], pre["K"], pre["attention"]
+    eng = VNetEngine(num_classes=K, in_channels=M, patch_shape=(P, P, P), max_batch=B, precision=args.precision,
+                     loss="weighted_sorensen", loss_weights=pre["weights"], optimizer="Adam", learning_rate=1e-2,
+                     decay_factor=0.99, decay_steps=100.0, device=local_rank,
+                     attention=att, attention_loss="l2" if att else None)
     initialize(eng, 42)
     if world > 1:
         uid = [eng.comm_unique_id() if rank == 0 else None]
@@ -212,14 +237,15 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     nb = min(args.steps + args.warmup, 4)
     pinned = []
     for i in range(nb):
-        img, lab = synth_batch(i, B, P, 1, 2, rank=rank)
-        ti = torch.from_numpy(img).pin_memory()
-        tl = torch.from_numpy(lab).pin_memory()
-        pinned.append((ti, tl, ti.numpy(), tl.numpy()))
+        samples = [synth_patch(1234 + 1000 * rank + i + 100000 * b, P, M, K) for b in range(B)]
+        tens = [torch.from_numpy(np.stack([smp[j] for smp in samples], 0)).pin_memory() for j in range(3)]
+        pinned.append((tens, None, tens[0].numpy(), tens[1].numpy(), tens[2].numpy()))
     dropout = 0.01  # configs/*.json Networks.Dropout
 
     # ---- leg 1: device-resident inputs ("value") ------------------------------------------------
     eng.upload_batch(pinned[0][2], pinned[0][3])
+    if att:
+        eng.set_distmap(pinned[0][4])
     for i in range(args.warmup):
         eng.train_step_resident(B, dropout, seed=i)
     barrier()
@@ -237,12 +263,16 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
     # ---- leg 2: end to end through the public API with host buffers ("e2e") ---------------------
     for i in range(min(args.warmup, 2)):
+        if att:
+            eng.set_distmap(pinned[i % nb][4])
         eng.train_step(pinned[i % nb][2], pinned[i % nb][3], dropout, seed=i)
     barrier()
     t0 = time.perf_counter()
     eng.event_record(0)
     loss = None
     for i in range(args.steps):
+        if att:
+            eng.set_distmap(pinned[i % nb][4])
         loss = eng.train_step(pinned[i % nb][2], pinned[i % nb][3], dropout, seed=200 + i, want_loss=True)
     eng.event_record(1)
     barrier()
@@ -268,19 +298,22 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         patches = B * world * args.steps
         value = patches / (ms_dev / 1e3)
         e2e_val = patches / (ms_e2e / 1e3)
-        img_bytes = B * P ** 3 * 4
-        lab_bytes = B * P ** 3 * 4
-        step_tflops = value * train_gflop_per_patch(P) / 1e3 / world
+        img_bytes = B * P ** 3 * 4 * M
+        lab_bytes = B * P ** 3 * 4 * (2 if att else 1)   # labels (+ distance map)
+        step_tflops = value * train_gflop_per_patch(P, pre) / 1e3 / world
         line = {
             "metric": "patches/sec (128^3, 1ch->2cls) training step", "value": value, "unit": "patches/sec",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (fp32-grade split, fp32 accumulate)", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "V-Net 3D train step (fwd + weighted Dice + bwd + Adam%s), %d^3 patch, 1 modality, 2 classes, "
-                                   "batch %d per GPU (BASELINE configs[1])" % (" + ring all-reduce" if world > 1 else "", P, B),
+            "config": {"workload": "V-Net 3D train step (fwd + weighted Dice%s + bwd + Adam%s), %d^3 patch, %d modalit%s, %d classes, "
+                                   "batch %d per GPU (%s)" % (" + attention gating / attention loss" if att else "",
+                                                              " + ring all-reduce" if world > 1 else "", P, M,
+                                                              "y" if M == 1 else "ies", K, B, pre["name"]),
                        "patch": P, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                        "precision": args.precision, "dropout": dropout,
+                       "attention": bool(att),
                        "l2": "per-step working set (activations %.1f GB) >> 126 MB L2, no explicit flush" % (0.7 * 3 * B * (P / 128) ** 3)},
             "e2e": {"value": e2e_val, "unit": "patches/sec", "h2d_bytes_per_step": img_bytes + lab_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -290,7 +323,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                        ms_dev / args.steps, step_tflops),
             "final_loss": loss,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config == 2:
             line["cpu_baseline"] = cpu_baseline(P)
         print(json.dumps(line), flush=True)
     eng.close()

@@ -260,7 +260,8 @@ inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int
   g.n_co = Cout / 16;
   const int pairs = g.n_ci * g.n_co;
   const int items = N * D * g.n_hb;
-  g.splits = std::max(1, std::min(items, (sms + pairs - 1) / pairs));
+  // one CTA per SM (the rings fill shared memory): never spill a partial second wave of CTAs
+  g.splits = std::max(1, std::min(items, sms / pairs));
   g.xt_bytes = ((ht * (Wr + 8) * 32 + 1023) / 1024) * 1024;
   g.zt_bytes = (((ht + ks - 1) * Wr * 32 + 1023) / 1024) * 1024;
   const int budget = 200 * 1024 - 2 * g.npl * g.xt_bytes - 1024;

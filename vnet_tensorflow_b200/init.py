@@ -18,13 +18,26 @@ def xavier_uniform(shape, rng: np.random.Generator) -> np.ndarray:
     return rng.uniform(-lim, lim, size=tuple(shape)).astype(np.float32)
 
 
+def truncated_normal(shape, stddev: float, rng: np.random.Generator) -> np.ndarray:
+    """attention.py:25-27 tf.truncated_normal: N(0, stddev), values beyond two sigma are redrawn."""
+    w = rng.normal(0.0, stddev, size=tuple(shape))
+    bad = np.abs(w) > 2.0 * stddev
+    while bad.any():
+        w[bad] = rng.normal(0.0, stddev, size=int(bad.sum()))
+        bad = np.abs(w) > 2.0 * stddev
+    return w.astype(np.float32)
+
+
 def initial_values(variables, seed: int = 42) -> "OrderedDict[str, np.ndarray]":
     """variables: name -> (shape, trainable) as returned by VNetEngine.variables()."""
     rng = np.random.Generator(np.random.PCG64(seed))
+    mod_rng = np.random.Generator(np.random.PCG64(seed + 1))  # attention / output modules draw from their own stream
     out = OrderedDict()
     for name, (shape, _) in variables.items():
         if name.endswith("/weights"):
             out[name] = xavier_uniform(shape, rng)
+        elif "/Variable" in name and len(shape) == 5:
+            out[name] = truncated_normal(shape, 0.1, mod_rng)
         elif name.endswith(("/gamma", "/moving_variance")):
             out[name] = np.ones(shape, np.float32)
         elif name.endswith("/alpha"):
