@@ -696,11 +696,6 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
   if (mult(C1, 32) && mult(C2, 32) && mult(Co1, 32) && mult(Co2, 32) && Co1 > 0) {
     pl.CT = 32;
     pl.KC = 32;
-  } else if (ks == 5 && mult(C1, 16) && mult(C2, 16) && mult(Co1, 16) && mult(Co2, 16) && mult(Co1 + Co2, 32) && Co1 > 0 && C1 > 0) {
-    // wide N with a 16-channel K chunk (e.g. the dgrad of a 2c -> c decoder convolution at c = 16: 16 -> 16 + 16);
-    // the two output tensors may meet inside a 32-wide slice, the epilogue routes per 16-column chunk
-    pl.CT = 32;
-    pl.KC = 16;
   } else if (mult(C1, 16) && mult(C2, 16) && mult(Co1, 16) && mult(Co2, 16) && Co1 > 0 && C1 > 0) {
     pl.CT = 16;
     pl.KC = 16;
@@ -807,9 +802,6 @@ inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int 
   if (pl.CT == 16) {
     if (split3) tc_launch_inst<16, 3, 16, 3>(pl, a, sms, stream);
     else tc_launch_inst<16, 3, 16, 1>(pl, a, sms, stream);
-  } else if (pl.KC == 16) {
-    if (split3) tc_launch_inst<32, 1, 16, 3>(pl, a, sms, stream);
-    else tc_launch_inst<32, 1, 16, 1>(pl, a, sms, stream);
   } else {
     if (split3) tc_launch_inst<32, 1, 32, 3>(pl, a, sms, stream);
     else tc_launch_inst<32, 1, 32, 1>(pl, a, sms, stream);

@@ -43,9 +43,11 @@ __device__ __forceinline__ void k2_tile_fma(const float (*As)[kK2_BM + kK2_PAD],
 }
 
 // grid: (ceil(M/64), ceil(CC/64)); requires CF % 16 == 0, CC % 4 == 0
+// Software pipelined: the global loads of K chunk i+1 are in flight while chunk i is multiplied out of the other
+// shared-memory buffer (one barrier per chunk).
 __global__ void __launch_bounds__(256) k2_gather_tiled_kernel(K2Args p, long long M) {
-  __shared__ float As[kK2_BK][kK2_BM + kK2_PAD];
-  __shared__ float Bs[kK2_BK][kK2_BN + kK2_PAD];
+  __shared__ float As[2][kK2_BK][kK2_BM + kK2_PAD];
+  __shared__ float Bs[2][kK2_BK][kK2_BN + kK2_PAD];
   const int t = threadIdx.x, tx = t % 16, ty = t / 16;
   const long long m0 = static_cast<long long>(blockIdx.x) * kK2_BM;
   const int n0 = blockIdx.y * kK2_BN;
@@ -53,22 +55,30 @@ __global__ void __launch_bounds__(256) k2_gather_tiled_kernel(K2Args p, long lon
   const int arow = t / 4, akq = (t % 4) * 4;   // A loader: one float4 per thread
   const int bk = t / 16, bn4 = (t % 16) * 4;   // B loader
   const long long am = m0 + arow;
-  for (int tap = 0; tap < 8; ++tap) {
-    const long long child = am < M ? k2_child(p, am, tap) : 0;
-    for (int cf0 = 0; cf0 < p.CF; cf0 += kK2_BK) {
-      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (am < M) av = *reinterpret_cast<const float4*>(p.fine_in + child * p.CF + cf0 + akq);
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + bn4 < p.CC) bv = *reinterpret_cast<const float4*>(p.w + (static_cast<long long>(tap) * p.CF + cf0 + bk) * p.CC + n0 + bn4);
-      __syncthreads();
-      As[akq + 0][arow] = av.x;
-      As[akq + 1][arow] = av.y;
-      As[akq + 2][arow] = av.z;
-      As[akq + 3][arow] = av.w;
-      *reinterpret_cast<float4*>(&Bs[bk][bn4]) = bv;
-      __syncthreads();
-      k2_tile_fma(As, Bs, ty, tx, acc);
-    }
+  const int chunks_per_tap = p.CF / kK2_BK, n_it = 8 * chunks_per_tap;
+  float4 av, bv;
+  auto fetch = [&](int it) {
+    const int tap = it / chunks_per_tap, cf0 = (it % chunks_per_tap) * kK2_BK;
+    av = make_float4(0.f, 0.f, 0.f, 0.f);
+    bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (am < M) av = *reinterpret_cast<const float4*>(p.fine_in + k2_child(p, am, tap) * p.CF + cf0 + akq);
+    if (n0 + bn4 < p.CC) bv = *reinterpret_cast<const float4*>(p.w + (static_cast<long long>(tap) * p.CF + cf0 + bk) * p.CC + n0 + bn4);
+  };
+  auto stash = [&](int buf) {
+    As[buf][akq + 0][arow] = av.x;
+    As[buf][akq + 1][arow] = av.y;
+    As[buf][akq + 2][arow] = av.z;
+    As[buf][akq + 3][arow] = av.w;
+    *reinterpret_cast<float4*>(&Bs[buf][bk][bn4]) = bv;
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int it = 0; it < n_it; ++it) {
+    if (it + 1 < n_it) fetch(it + 1);
+    k2_tile_fma(As[it & 1], Bs[it & 1], ty, tx, acc);
+    if (it + 1 < n_it) stash((it + 1) & 1);
+    __syncthreads();
   }
   const int n = n0 + tx * 4;
   if (n >= p.CC) return;
@@ -92,23 +102,35 @@ __global__ void __launch_bounds__(256) k2_gather_tiled_kernel(K2Args p, long lon
 
 // grid: (ceil(M/64), ceil(8*CF/64)); requires CC % 16 == 0, CF % 4 == 0
 __global__ void __launch_bounds__(256) k2_scatter_tiled_kernel(K2Args p, long long M) {
-  __shared__ float As[kK2_BK][kK2_BM + kK2_PAD];
-  __shared__ float Bs[kK2_BK][kK2_BN + kK2_PAD];
+  __shared__ float As[2][kK2_BK][kK2_BM + kK2_PAD];
+  __shared__ float Bs[2][kK2_BK][kK2_BN + kK2_PAD];
   const int t = threadIdx.x, tx = t % 16, ty = t / 16;
   const long long m0 = static_cast<long long>(blockIdx.x) * kK2_BM;
   const int n0 = blockIdx.y * kK2_BN;  // n = tap*CF + cf
   const int NN = 8 * p.CF;
   float acc[4][4] = {};
   const int row = t / 4, kq = (t % 4) * 4;
-  for (int cc0 = 0; cc0 < p.CC; cc0 += kK2_BK) {
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n_it = p.CC / kK2_BK;
+  float4 av, bv;
+  auto fetch = [&](int it) {
+    const int cc0 = it * kK2_BK;
+    av = make_float4(0.f, 0.f, 0.f, 0.f);
+    bv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (m0 + row < M) av = *reinterpret_cast<const float4*>(p.coarse_in + (m0 + row) * p.CC + cc0 + kq);
     if (n0 + row < NN) bv = *reinterpret_cast<const float4*>(p.w + static_cast<long long>(n0 + row) * p.CC + cc0 + kq);
+  };
+  auto stash = [&](int buf) {
+    As[buf][kq + 0][row] = av.x; As[buf][kq + 1][row] = av.y; As[buf][kq + 2][row] = av.z; As[buf][kq + 3][row] = av.w;
+    Bs[buf][kq + 0][row] = bv.x; Bs[buf][kq + 1][row] = bv.y; Bs[buf][kq + 2][row] = bv.z; Bs[buf][kq + 3][row] = bv.w;
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int it = 0; it < n_it; ++it) {
+    if (it + 1 < n_it) fetch(it + 1);
+    k2_tile_fma(As[it & 1], Bs[it & 1], ty, tx, acc);
+    if (it + 1 < n_it) stash((it + 1) & 1);
     __syncthreads();
-    As[kq + 0][row] = av.x; As[kq + 1][row] = av.y; As[kq + 2][row] = av.z; As[kq + 3][row] = av.w;
-    Bs[kq + 0][row] = bv.x; Bs[kq + 1][row] = bv.y; Bs[kq + 2][row] = bv.z; Bs[kq + 3][row] = bv.w;
-    __syncthreads();
-    k2_tile_fma(As, Bs, ty, tx, acc);
   }
   const int n = n0 + tx * 4;
   if (n >= NN) return;
@@ -133,8 +155,8 @@ __global__ void __launch_bounds__(256) k2_scatter_tiled_kernel(K2Args p, long lo
 
 // grid: (ceil(8*CF/64), ceil(CC/64), splits); fp32 atomics into pre-zeroed dw; CF % 4 == 0, CC % 4 == 0
 __global__ void __launch_bounds__(256) k2_wgrad_tiled_kernel(K2Args p, long long M, long long m_per_split) {
-  __shared__ float As[kK2_BK][kK2_BM + kK2_PAD];   // [k = voxel][r = (tap,cf) row]
-  __shared__ float Bs[kK2_BK][kK2_BN + kK2_PAD];   // [k = voxel][n = cc]
+  __shared__ float As[2][kK2_BK][kK2_BM + kK2_PAD];   // [k = voxel][r = (tap,cf) row]
+  __shared__ float Bs[2][kK2_BK][kK2_BN + kK2_PAD];   // [k = voxel][n = cc]
   const int t = threadIdx.x, tx = t % 16, ty = t / 16;
   const int r0 = blockIdx.x * kK2_BM, n0 = blockIdx.y * kK2_BN;
   const int RR = 8 * p.CF;
@@ -144,18 +166,31 @@ __global__ void __launch_bounds__(256) k2_wgrad_tiled_kernel(K2Args p, long long
   const int lk = t / 16, l4 = (t % 16) * 4;
   const int r = r0 + l4;
   const int tap = r < RR ? r / p.CF : 0, cf = r < RR ? r % p.CF : 0;
-  for (long long mk = mb; mk < me; mk += kK2_BK) {
-    const long long m = mk + lk;
-    float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n_it = static_cast<int>((me - mb + kK2_BK - 1) / kK2_BK);
+  float4 av, bv;
+  auto fetch = [&](int it) {
+    const long long m = mb + static_cast<long long>(it) * kK2_BK + lk;
+    av = make_float4(0.f, 0.f, 0.f, 0.f);
+    bv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (m < me) {
       if (r < RR) av = *reinterpret_cast<const float4*>(p.fine_in + k2_child(p, m, tap) * p.CF + cf);
       if (n0 + l4 < p.CC) bv = *reinterpret_cast<const float4*>(p.coarse_in + m * p.CC + n0 + l4);
     }
+  };
+  auto stash = [&](int buf) {
+    *reinterpret_cast<float4*>(&As[buf][lk][l4]) = av;
+    *reinterpret_cast<float4*>(&Bs[buf][lk][l4]) = bv;
+  };
+  if (n_it > 0) {
+    fetch(0);
+    stash(0);
+  }
+  __syncthreads();
+  for (int it = 0; it < n_it; ++it) {
+    if (it + 1 < n_it) fetch(it + 1);
+    k2_tile_fma(As[it & 1], Bs[it & 1], ty, tx, acc);
+    if (it + 1 < n_it) stash((it + 1) & 1);
     __syncthreads();
-    *reinterpret_cast<float4*>(&As[lk][l4]) = av;
-    *reinterpret_cast<float4*>(&Bs[lk][l4]) = bv;
-    __syncthreads();
-    k2_tile_fma(As, Bs, ty, tx, acc);
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -36,6 +36,12 @@ struct WgGeom {
 
 // KS = 3 serves the attention / output module convolutions with the same scheme: 3 useful kw atoms of 8,
 // N = 3 x 16, three kd accumulators.
+//
+// Loop order ("rolling X planes"): a CTA walks runs of consecutive dZ planes dz for a fixed (sample, line block).
+// Step dz loads ONE dZ tile (HT + KS-1 lines) and ONE new X tile (plane dz + R); the X tiles of planes
+// dz-R .. dz+R stay resident in a ring of KS+1 slots and accumulator kd pairs dZ plane dz with X plane dz + kd - R.
+// Compared with re-loading the KS dZ planes of every X slab this cuts the L2 -> SMEM traffic ~4x (it was the
+// bound of the 16-channel layers at 128^3: 6 TB/s over the 148 SMs).  Planes outside the volume are TMA zero fill.
 template <int NSPLIT, int KS>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ TmaDesc x1_lo,
@@ -45,37 +51,38 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
   using namespace sm100;
   constexpr int NPL = NSPLIT == 3 ? 2 : 1;
   constexpr int RC = KS / 2, NB = KS * 16, TAPS = KS * KS * KS;
+  constexpr int XS = KS + 1;   // X ring slots: KS live planes + one being prefetched
   VNB_DYN_SMEM(uint8_t, smem_raw);
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const uint32_t sm_addr = smem_u32(sm);
-  const uint32_t x_ring = sm_addr;                                  // 2 x NPL x xt_bytes
-  const uint32_t z_ring = x_ring + 2u * NPL * g.xt_bytes;           // z_stages x NPL x zt_bytes
-  const uint32_t bar_off = 2u * NPL * g.xt_bytes + static_cast<uint32_t>(g.z_stages) * NPL * g.zt_bytes;
+  const uint32_t x_ring = sm_addr;                                      // XS x NPL x xt_bytes
+  const uint32_t z_ring = x_ring + static_cast<uint32_t>(XS) * NPL * g.xt_bytes;   // z_stages x NPL x zt_bytes
+  const uint32_t bar_off = static_cast<uint32_t>(XS) * NPL * g.xt_bytes + static_cast<uint32_t>(g.z_stages) * NPL * g.zt_bytes;
   const uint32_t bar_base = sm_addr + bar_off;
-  auto xfull = [&](int s) { return bar_base + 8u * s; };            // [2]
-  auto xempty = [&](int s) { return bar_base + 8u * (2 + s); };     // [2]
-  auto zfull = [&](int s) { return bar_base + 8u * (4 + s); };      // [8]
-  auto zempty = [&](int s) { return bar_base + 8u * (12 + s); };    // [8]
-  const uint32_t done_bar = bar_base + 8u * 20;
-  const uint32_t slot_addr = bar_base + 8u * 21;
-  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + bar_off + 8 * 21);
+  auto xfull = [&](int s) { return bar_base + 8u * s; };            // [8]
+  auto xempty = [&](int s) { return bar_base + 8u * (8 + s); };     // [8]
+  auto zfull = [&](int s) { return bar_base + 8u * (16 + s); };     // [8]
+  auto zempty = [&](int s) { return bar_base + 8u * (24 + s); };    // [8]
+  const uint32_t done_bar = bar_base + 8u * 32;
+  const uint32_t slot_addr = bar_base + 8u * 33;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + bar_off + 8 * 33);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pair = blockIdx.x / g.splits, split = blockIdx.x % g.splits;
   const int ci_chunk = pair / g.n_co, co_chunk = pair % g.n_co;
-  const int n_items = g.N * g.D * g.n_hb;
+  // work units u = ((n * n_hb + hb) * D + dz); this CTA owns the contiguous run [u0, u1)
+  const long long U = static_cast<long long>(g.N) * g.n_hb * g.D;
+  const long long u0 = U * split / g.splits, u1 = U * (split + 1) / g.splits;
   const int lpm = g.W == 8 ? 2 : 1;                // X lines covered by one K = 16 step
   const int ksteps = g.Wr * lpm / 16;              // MMA k-steps per group of `lpm` lines
   const uint32_t x_pitch = static_cast<uint32_t>(g.Wr + 8) * 32u;  // bytes between X lines in smem
   const uint32_t z_pitch = static_cast<uint32_t>(g.Wr) * 32u;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 8; ++s) {
       mbar_init(xfull(s), 1);
       mbar_init(xempty(s), 1);
-    }
-    for (int s = 0; s < 8; ++s) {
       mbar_init(zfull(s), 1);
       mbar_init(zempty(s), 1);
     }
@@ -97,33 +104,33 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
       const int xc = src1 ? ci_chunk * 16 : ci_chunk * 16 - g.C1;
       const TmaDesc* xh = src1 ? &x1_hi : &x2_hi;
       const TmaDesc* xl = src1 ? &x1_lo : &x2_lo;
-      int xs = 0, zs = 0;
-      uint32_t xph = 0, zph = 0;
+      int zs = 0;
+      uint32_t zph = 0;
+      long long xload = 0;   // running X-plane load index: slot = xload % XS, phase = (xload / XS) & 1
       const uint32_t x_tx = static_cast<uint32_t>(g.HT) * (g.Wr + 8) * 32u * NPL;
       const uint32_t z_tx = static_cast<uint32_t>(g.HT + KS - 1) * g.Wr * 32u * NPL;
-      for (int item = split; item < n_items; item += g.splits) {
-        const int hb = item % g.n_hb;
-        const int dx = (item / g.n_hb) % g.D;
-        const int n = item / (g.n_hb * g.D);
+      for (long long u = u0; u < u1; ++u) {
+        const int dz = static_cast<int>(u % g.D);
+        const int hb = static_cast<int>((u / g.D) % g.n_hb);
+        const int n = static_cast<int>(u / (static_cast<long long>(g.D) * g.n_hb));
         const int h0 = hb * g.HT;
-        mbar_wait(xempty(xs), xph ^ 1u);
-        mbar_expect_tx(xfull(xs), x_tx);
-        tma_load_5d(x_ring + (xs * NPL) * g.xt_bytes, xh, xfull(xs), xc, -RC, h0, dx, n);
-        if (NSPLIT == 3) tma_load_5d(x_ring + (xs * NPL + 1) * g.xt_bytes, xl, xfull(xs), xc, -RC, h0, dx, n);
-        if (++xs == 2) {
-          xs = 0;
-          xph ^= 1u;
+        const bool chain_start = (u == u0) || dz == 0;
+        for (int pl = chain_start ? dz - RC : dz + RC; pl <= dz + RC; ++pl) {
+          const int xs = static_cast<int>(xload % XS);
+          const uint32_t xph = static_cast<uint32_t>((xload / XS) & 1);
+          mbar_wait(xempty(xs), xph ^ 1u);
+          mbar_expect_tx(xfull(xs), x_tx);
+          tma_load_5d(x_ring + (xs * NPL) * g.xt_bytes, xh, xfull(xs), xc, -RC, h0, pl, n);
+          if (NSPLIT == 3) tma_load_5d(x_ring + (xs * NPL + 1) * g.xt_bytes, xl, xfull(xs), xc, -RC, h0, pl, n);
+          ++xload;
         }
-        for (int kd = 0; kd < KS; ++kd) {
-          const int dz = dx - kd + RC;
-          mbar_wait(zempty(zs), zph ^ 1u);
-          mbar_expect_tx(zfull(zs), z_tx);
-          tma_load_5d(z_ring + (zs * NPL) * g.zt_bytes, &z_hi, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
-          if (NSPLIT == 3) tma_load_5d(z_ring + (zs * NPL + 1) * g.zt_bytes, &z_lo, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
-          if (++zs == g.z_stages) {
-            zs = 0;
-            zph ^= 1u;
-          }
+        mbar_wait(zempty(zs), zph ^ 1u);
+        mbar_expect_tx(zfull(zs), z_tx);
+        tma_load_5d(z_ring + (zs * NPL) * g.zt_bytes, &z_hi, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
+        if (NSPLIT == 3) tma_load_5d(z_ring + (zs * NPL + 1) * g.zt_bytes, &z_lo, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
+        if (++zs == g.z_stages) {
+          zs = 0;
+          zph ^= 1u;
         }
       }
     }
@@ -132,24 +139,28 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
       const uint32_t idesc = make_instr_desc(128, NB, FMT_BF16, 1, 1);
       const uint32_t sbo_a = lpm == 2 ? x_pitch : 256u;   // K rows 8..15: next line (W = 8) or next 8 voxels
       const uint32_t sbo_b = 256u;                         // dZ lines are contiguous, so both cases are +256 B
-      int xs = 0, zs = 0;
-      uint32_t xph = 0, zph = 0;
-      bool first = true;
-      for (int item = split; item < n_items; item += g.splits) {
-        mbar_wait(xfull(xs), xph);
+      int zs = 0;
+      uint32_t zph = 0;
+      long long xlo = 0;     // load index of X plane dz - RC of the current step
+      for (long long u = u0; u < u1; ++u) {
+        const int dz = static_cast<int>(u % g.D);
+        const bool chain_end = (u + 1 == u1) || dz + 1 == g.D;
+        mbar_wait(zfull(zs), zph);
         tc_fence_after_sync();
-        const uint32_t xa_hi = x_ring + (xs * NPL) * g.xt_bytes;
+        const uint32_t za_hi = z_ring + (zs * NPL) * g.zt_bytes;
+        const uint64_t db0 = make_smem_desc(za_hi, z_pitch, sbo_b, SWZ_32B);
+        const uint64_t db0_lo = db0 + (static_cast<uint32_t>(g.zt_bytes) >> 4);
         for (int kd = 0; kd < KS; ++kd) {
-          mbar_wait(zfull(zs), zph);
+          const long long xi = xlo + kd;   // X plane dz + kd - RC
+          const int xs = static_cast<int>(xi % XS);
+          mbar_wait(xfull(xs), static_cast<uint32_t>((xi / XS) & 1));
           tc_fence_after_sync();
-          const uint32_t za_hi = z_ring + (zs * NPL) * g.zt_bytes;
+          const uint32_t xa_hi = x_ring + (xs * NPL) * g.xt_bytes;
           const uint32_t d_addr = tmem + kd * NB;
           // only the start-address field changes between MMAs: one base descriptor per operand, 64-bit adds after
           const uint64_t da0 = make_smem_desc(xa_hi, 32, sbo_a, SWZ_32B);
           const uint64_t da0_lo = da0 + (static_cast<uint32_t>(g.xt_bytes) >> 4);
-          const uint64_t db0 = make_smem_desc(za_hi, z_pitch, sbo_b, SWZ_32B);
-          const uint64_t db0_lo = db0 + (static_cast<uint32_t>(g.zt_bytes) >> 4);
-          uint32_t acc = first ? 0u : 1u;
+          uint32_t acc = (u == u0) ? 0u : 1u;
           for (int t = 0; t < g.HT; t += lpm) {
             uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t) * x_pitch) >> 4);
             uint64_t boff = static_cast<uint64_t>((static_cast<uint32_t>(t) * z_pitch) >> 4);
@@ -164,28 +175,26 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
               boff += 32;
             }
           }
-          mma_commit(zempty(zs));
-          if (++zs == g.z_stages) {
-            zs = 0;
-            zph ^= 1u;
-          }
         }
-        first = false;
-        mma_commit(xempty(xs));
-        if (++xs == 2) {
-          xs = 0;
-          xph ^= 1u;
+        mma_commit(zempty(zs));
+        if (++zs == g.z_stages) {
+          zs = 0;
+          zph ^= 1u;
         }
+        // X plane dz - RC is dead after this step; at the end of a run of planes so are the other KS-1
+        const int dead = chain_end ? KS : 1;
+        for (int k = 0; k < dead; ++k) mma_commit(xempty(static_cast<int>((xlo + k) % XS)));
+        xlo += dead;
       }
       mma_commit(done_bar);
     }
   } else {
-    // read-out: thread = accumulator row m = (kw slot j, ci); columns n = (l, co); kh = 4 - l
+    // read-out: thread = accumulator row m = (kw slot j, ci); columns n = (l, co); kh = KS-1 - l
     const int q = warp & 3, m = q * 32 + lane;
     const int j = m / 16, ci = m % 16;
     mbar_wait(done_bar, 0);
     tc_fence_after_sync();
-    const bool has_work = split < n_items;
+    const bool has_work = u0 < u1;
     float* out = partial + (static_cast<size_t>(split) * (g.n_ci * g.n_co) + pair) * (TAPS * 256);
     for (int kd = 0; kd < KS; ++kd)
       for (int l = 0; l < KS; ++l) {
@@ -254,20 +263,25 @@ inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int
   ht = std::min(ht, H);
   if (W == 8 && (ht % 2)) return false;
   if (ht + ks - 1 > 256 || Wr + 8 > 256) return false;
-  g.HT = ht;
-  g.n_hb = (H + ht - 1) / ht;
+  const int xslots = ks + 1;
+  for (;; ht = std::max(2, ht / 2)) {   // shrink the line block until the X ring + two dZ stages fit
+    g.HT = ht;
+    g.xt_bytes = ((ht * (Wr + 8) * 32 + 1023) / 1024) * 1024;
+    g.zt_bytes = (((ht + ks - 1) * Wr * 32 + 1023) / 1024) * 1024;
+    const int budget = 224 * 1024 - xslots * g.npl * g.xt_bytes - 2048;
+    g.z_stages = std::min(8, budget / (g.npl * g.zt_bytes));
+    if (g.z_stages >= 2 || ht <= 2) break;
+  }
+  if (g.z_stages < 2) return false;
+  if (W == 8 && (g.HT % 2)) return false;
+  g.n_hb = (H + g.HT - 1) / g.HT;
   g.n_ci = (C1 + C2) / 16;
   g.n_co = Cout / 16;
   const int pairs = g.n_ci * g.n_co;
   const int items = N * D * g.n_hb;
   // one CTA per SM (the rings fill shared memory): never spill a partial second wave of CTAs
   g.splits = std::max(1, std::min(items, sms / pairs));
-  g.xt_bytes = ((ht * (Wr + 8) * 32 + 1023) / 1024) * 1024;
-  g.zt_bytes = (((ht + ks - 1) * Wr * 32 + 1023) / 1024) * 1024;
-  const int budget = 200 * 1024 - 2 * g.npl * g.xt_bytes - 1024;
-  g.z_stages = std::min(8, budget / (g.npl * g.zt_bytes));
-  if (g.z_stages < 2) return false;
-  pl.smem = 2 * g.npl * g.xt_bytes + static_cast<size_t>(g.z_stages) * g.npl * g.zt_bytes + 256 + 1024;
+  pl.smem = static_cast<size_t>(xslots) * g.npl * g.xt_bytes + static_cast<size_t>(g.z_stages) * g.npl * g.zt_bytes + 512 + 1024;
   pl.partial_floats = static_cast<size_t>(g.splits) * pairs * (ks * ks * ks) * 256;
   return true;
 }
