@@ -130,6 +130,62 @@ __global__ void __launch_bounds__(128, 1)
 }
 
 // ---------------------------------------------------------------------------------------------
+// device: MMA issue-rate probe.  One thread issues `reps` passes over a short MMA script (operands are whatever
+// bytes sit in shared memory) and reports SM cycles from first issue to completion of the last MMA.
+// ---------------------------------------------------------------------------------------------
+struct RateOps {
+  uint64_t adesc[4], bdesc[4];
+  uint32_t idesc[4], dcol[4];
+};
+template <int NOPS>
+__global__ void __launch_bounds__(128, 1)
+    mma_rate_probe(uint32_t img_bytes, const RateOps ops, int reps, long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  for (uint32_t i = tid; i < img_bytes / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&tmem_slot), 512);
+    tmem_relinquish();
+  }
+  if (tid == 32) {
+    mbar_init(smem_u32(&mbar), 1);
+    fence_mbar_init();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    uint64_t ad[NOPS], bd[NOPS];
+    uint32_t id[NOPS], dc[NOPS];
+#pragma unroll
+    for (int i = 0; i < NOPS; ++i) {
+      ad[i] = ops.adesc[i] + static_cast<uint64_t>(base >> 4);
+      bd[i] = ops.bdesc[i] + static_cast<uint64_t>(base >> 4);
+      id[i] = ops.idesc[i];
+      dc[i] = tmem + ops.dcol[i];
+    }
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int i = 0; i < NOPS; ++i) mma_f16_ss(dc[i], ad[i], bd[i], id[i], 1u);
+    }
+    mma_commit(smem_u32(&mbar));
+    mbar_wait_bounded(smem_u32(&mbar), 0, 1u << 28);
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
 // device: TMA probe (one 5-D tiled load, dump the shared-memory image)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1)
@@ -490,11 +546,90 @@ static int test_tma(const char* name, int D, int H, int W, int C, int bc, int bw
 }
 
 // ---------------------------------------------------------------------------------------------
+// MMA issue-rate table: cycles per tcgen05.mma (M = 128, K = 16, bf16) for the operand layouts the kernels use
+static int run_rate(const char* name, const std::vector<MmaOp>& ops, uint32_t img_bytes, int ctas) {
+  long long* dcyc;
+  const int reps = 4000;
+  RateOps ro{};
+  for (size_t i = 0; i < ops.size() && i < 4; ++i) {
+    ro.adesc[i] = ops[i].adesc;
+    ro.bdesc[i] = ops[i].bdesc;
+    ro.idesc[i] = ops[i].idesc;
+    ro.dcol[i] = ops[i].dcol;
+  }
+  CK(cudaMalloc(&dcyc, ctas * sizeof(long long)));
+  size_t smem = img_bytes + 2048;
+  auto launch = [&](auto kfn) {
+    CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kfn<<<ctas, 128, smem>>>(img_bytes, ro, reps, dcyc);
+  };
+  switch (ops.size()) {
+    case 1: launch(mma_rate_probe<1>); break;
+    case 2: launch(mma_rate_probe<2>); break;
+    case 3: launch(mma_rate_probe<3>); break;
+    default: launch(mma_rate_probe<4>); break;
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("RATE %-34s FAULT (%s)\n", name, cudaGetErrorString(e));
+    return 1;
+  }
+  std::vector<long long> cyc(ctas);
+  CK(cudaMemcpy(cyc.data(), dcyc, ctas * sizeof(long long), cudaMemcpyDeviceToHost));
+  long long mx = 0;
+  for (long long c : cyc) mx = std::max(mx, c);
+  printf("RATE %-34s ctas=%3d  %.1f cycles/MMA\n", name, ctas, (double)mx / ((double)reps * ops.size()));
+  cudaFree(dcyc);
+  return 0;
+}
+
+static int test_rates() {
+  const uint32_t img = 160 * 1024;
+  const uint32_t offB = 64 * 1024;
+  for (int ctas : {1, 148}) {
+    for (int N : {16, 80, 160, 240, 256}) {   // K-major, 32-byte rows (CT=16 convolution kernels)
+      char nm[64];
+      snprintf(nm, sizeof nm, "kmajor_sw32_N%d", N);
+      run_rate(nm, {{make_smem_desc(0, 16, 256, SWZ_32B), make_smem_desc(offB, 16, 256, SWZ_32B), make_instr_desc(128, N, FMT_BF16), 0, 1, 0}}, img, ctas);
+    }
+    for (int N : {80, 160, 256}) {      // K-major, 64-byte rows: two K slices per row (CT=32 kernels)
+      char nm[64];
+      snprintf(nm, sizeof nm, "kmajor_sw64_N%d", N);
+      run_rate(nm, {{make_smem_desc(0, 16, 512, SWZ_64B), make_smem_desc(offB, 16, 512, SWZ_64B), make_instr_desc(128, N, FMT_BF16), 0, 1, 0},
+                    {make_smem_desc(32, 16, 512, SWZ_64B), make_smem_desc(offB + 32, 16, 512, SWZ_64B), make_instr_desc(128, N, FMT_BF16), 0, 1, 0}}, img, ctas);
+    }
+    for (int N : {80, 160, 256}) {      // K-major, 128-byte rows
+      char nm[64];
+      snprintf(nm, sizeof nm, "kmajor_sw128_N%d", N);
+      std::vector<MmaOp> ops;
+      for (int j = 0; j < 4; ++j)
+        ops.push_back({make_smem_desc(32 * j, 16, 1024, SWZ_128B), make_smem_desc(offB + 32 * j, 16, 1024, SWZ_128B), make_instr_desc(128, N, FMT_BF16), 0, 1, 0});
+      run_rate(nm, ops, img, ctas);
+    }
+    for (int nb : {1, 3, 5, 10, 15}) {  // MN-major overlapping atoms (filter-gradient kernel): A 8 shifted atoms, B nb atoms
+      char nm[64];
+      snprintf(nm, sizeof nm, "mnmajor_sw32_fold_N%d", 16 * nb);
+      run_rate(nm, {{make_smem_desc(0, 32, 256, SWZ_32B), make_smem_desc(offB, 128 * 32, 256, SWZ_32B) /* 15 atoms x 4 KB + tile < 96 KB */, make_instr_desc(128, 16 * nb, FMT_BF16, 1, 1), 0, 1, 0}}, img, ctas);
+    }
+    for (int N : {64, 128, 192, 256}) {  // MN-major canonical 128-byte atoms (64 MN elements x 8 K rows)
+      char nm[64];
+      snprintf(nm, sizeof nm, "mnmajor_sw128_N%d", N);
+      run_rate(nm, {{make_smem_desc(0, 1024, 2048, SWZ_128B), make_smem_desc(offB, 1024, static_cast<uint32_t>(N / 64) * 1024, SWZ_128B), make_instr_desc(128, N, FMT_BF16, 1, 1), 0, 1, 0}}, img, ctas);
+    }
+    // mixed: A K-major sw32 with B N = 80 accumulating into 3 different accumulators (independent chains)
+    run_rate("kmajor_sw32_N80_3acc", {{make_smem_desc(0, 16, 256, SWZ_32B), make_smem_desc(offB, 16, 256, SWZ_32B), make_instr_desc(128, 80, FMT_BF16), 0, 1, 0},
+                                      {make_smem_desc(4096, 16, 256, SWZ_32B), make_smem_desc(offB, 16, 256, SWZ_32B), make_instr_desc(128, 80, FMT_BF16), 80, 1, 0},
+                                      {make_smem_desc(8192, 16, 256, SWZ_32B), make_smem_desc(offB, 16, 256, SWZ_32B), make_instr_desc(128, 80, FMT_BF16), 160, 1, 0}}, img, ctas);
+  }
+  return 0;
+}
+
 struct TestEntry {
   const char* name;
   int (*fn)();
 };
 static const TestEntry kTests[] = {
+    {"rates", [] { return test_rates(); }},
     {"k_sw128_n80", [] { return test_k_sw(128, 80); }},
     {"k_sw64_n160", [] { return test_k_sw(64, 160); }},
     {"k_sw32_n80", [] { return test_k_sw(32, 80); }},

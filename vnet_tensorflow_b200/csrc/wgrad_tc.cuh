@@ -264,13 +264,14 @@ inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int
   if (W == 8 && (ht % 2)) return false;
   if (ht + ks - 1 > 256 || Wr + 8 > 256) return false;
   const int xslots = ks + 1;
-  for (;; ht = std::max(2, ht / 2)) {   // shrink the line block until the X ring + two dZ stages fit
+  const int ht_min = W == 8 ? 2 : 1;
+  for (;; ht = std::max(ht_min, ht / 2)) {   // shrink the line block until the X ring + two dZ stages fit
     g.HT = ht;
     g.xt_bytes = ((ht * (Wr + 8) * 32 + 1023) / 1024) * 1024;
     g.zt_bytes = (((ht + ks - 1) * Wr * 32 + 1023) / 1024) * 1024;
     const int budget = 224 * 1024 - xslots * g.npl * g.xt_bytes - 2048;
     g.z_stages = std::min(8, budget / (g.npl * g.zt_bytes));
-    if (g.z_stages >= 2 || ht <= 2) break;
+    if (g.z_stages >= 2 || ht <= ht_min) break;
   }
   if (g.z_stages < 2) return false;
   if (W == 8 && (g.HT % 2)) return false;
