@@ -247,12 +247,13 @@ inline T shfl_from(T v, int src_lane) {
 #define warpSize 32
 
 inline void __syncthreads() { emul::syncthreads(); }
-inline void __syncwarp(unsigned = 0xffffffffu) {}
+inline void __syncwarp(unsigned = 0xffffffffu);  // defined below: rendezvous of the warp's fibers
 inline void __threadfence() {}
 template <class T>
 inline T __shfl_sync(unsigned, T v, int lane) {
   return emul::shfl_from(v, lane);
 }
+inline void __syncwarp(unsigned) { (void)emul::shfl_from(0, 0); }
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int m) {
   return emul::shfl_from(v, (emul::cur()->lin & 31) ^ m);

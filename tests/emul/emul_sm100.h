@@ -72,9 +72,15 @@ inline void mbar_arrive(uint32_t bar) {
   b.pending--;
   bar_check(b);
 }
+inline bool elect_one() { return (emul::cur()->lin & 31) == 0; }
+inline uint32_t warp_uniform(uint32_t v) { return v; }
 inline bool mbar_try_wait(uint32_t bar, uint32_t parity) { return st().bars.at(bar).phase != (parity & 1u); }
 inline void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) emul::yield_wait();
+}
+inline void mbar_wait_warp(bool, uint32_t bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  __syncwarp();
 }
 inline bool mbar_wait_bounded(uint32_t bar, uint32_t parity, uint32_t) {
   mbar_wait(bar, parity);
@@ -196,6 +202,22 @@ inline void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t
     }
 }
 inline void mma_commit(uint32_t bar) { mbar_arrive(bar); }
+// predicated forms (see sm100_ptx.cuh)
+inline void mma_f16_ss_if(bool pred, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (pred) mma_f16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+}
+inline void mma_commit_if(bool pred, uint32_t bar) {
+  if (pred) mma_commit(bar);
+}
+inline void mbar_expect_tx_if(bool pred, uint32_t bar, uint32_t bytes) {
+  if (pred) mbar_expect_tx(bar, bytes);
+}
+inline void tma_load_2d_if(bool pred, uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  if (pred) tma_load_2d(dst, tmap, bar, c0, c1);
+}
+inline void tma_load_5d_if(bool pred, uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  if (pred) tma_load_5d(dst, tmap, bar, c0, c1, c2, c3, c4);
+}
 inline void tmem_ld_wait() {}
 inline void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   const uint32_t lane = (taddr >> 16) + (emul::cur()->lin & 31), col = taddr & 0xFFFF;

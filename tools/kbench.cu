@@ -1,0 +1,95 @@
+// Kernel micro-benchmark for the tensor-core convolution kernels (development tool, not part of the product):
+//   kbench wgrad|fprop N D H W Cin Cout precision(1=bf16,2=bf16x3) reps [ks]
+// Times `reps` back-to-back launches with CUDA events on random bf16 operands and prints us / launch and the
+// algorithmic TFLOP/s (2*ks^3*Cin*Cout*voxels).  VNB_KB_DBG=1 prints the MMA-warp cycle counters of CTA 0.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../vnet_tensorflow_b200/csrc/engine.cuh"
+#include "../vnet_tensorflow_b200/csrc/conv_tc_impl.cuh"
+
+using namespace vnb;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+__global__ void fill_bf16(uint16_t* p, size_t n, uint32_t seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u + seed;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    p[i] = f32_to_bf16(((h & 0xFFFF) / 65536.0f - 0.5f));
+  }
+}
+
+int main(int argc, char** argv) {
+  if (argc < 10) { printf("usage: kbench wgrad|fprop N D H W Cin Cout precision reps [ks] [cin2]\n"); return 2; }
+  const std::string op = argv[1];
+  const int N = atoi(argv[2]), D = atoi(argv[3]), H = atoi(argv[4]), W = atoi(argv[5]), Cin = atoi(argv[6]), Cout = atoi(argv[7]);
+  const int prec = atoi(argv[8]), reps = atoi(argv[9]);
+  const int ks = argc > 10 ? atoi(argv[10]) : 5;
+  const int cin2 = argc > 11 ? atoi(argv[11]) : 0;
+  const bool lo = prec == 2;
+  const size_t V = (size_t)N * D * H * W;
+  const int sms = tc_query_sms();
+  TcScratch s;
+  auto mk = [&](size_t n, uint32_t seed) { uint16_t* p = s.alloc<uint16_t>(n); fill_bf16<<<1024, 256>>>(p, n, seed); return p; };
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const double flops = 2.0 * ks * ks * ks * (Cin + cin2) * (double)Cout * (double)V;
+  float ms = 0;
+  if (op == "wgrad") {
+    WgPlan pl;
+    if (!wg_plan_geometry(pl, N, D, H, W, Cin, cin2, Cout, lo, sms, ks)) { printf("unsupported shape\n"); return 1; }
+    uint16_t *xh = mk(V * Cin, 1), *xl = lo ? mk(V * Cin, 2) : nullptr, *zh = mk(V * Cout, 3), *zl = lo ? mk(V * Cout, 4) : nullptr;
+    uint16_t *x2h = cin2 ? mk(V * cin2, 5) : nullptr, *x2l = (cin2 && lo) ? mk(V * cin2, 6) : nullptr;
+    float* partial = s.alloc<float>(pl.partial_floats);
+    float* dw = s.alloc<float>((size_t)ks * ks * ks * (Cin + cin2) * Cout);
+    wg_encode_plan(pl, N, xh, xl, x2h, x2l, zh, zl);
+    long long* dbg = nullptr;
+    if (getenv("VNB_KB_DBG")) { dbg = s.alloc<long long>(8 * 1024); CK(cudaMemset(dbg, 0, 8 * 1024 * sizeof(long long))); pl.g.dbg = dbg; }
+    printf("wgrad plan: HT=%d n_hb=%d z_stages=%d splits=%d pairs=%d grid=%d smem=%zu xt=%d zt=%d\n", pl.g.HT, pl.g.n_hb, pl.g.z_stages,
+           pl.g.splits, pl.g.n_ci * pl.g.n_co, pl.g.splits * pl.g.n_ci * pl.g.n_co, pl.smem, pl.g.xt_bytes, pl.g.zt_bytes);
+    for (int i = 0; i < 3; ++i) wg_launch(pl, N, lo, partial, dw, 0);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) wg_launch(pl, N, lo, partial, dw, 0);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (dbg) {
+      std::vector<long long> h(8 * 1024);
+      CK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      for (int c : {0, 1, sms / 2, sms - 1}) {
+        const long long* d = &h[8 * c];
+        printf("  cta %3d: loop cycles %lld  wait_full cycles %lld  mmas %lld  -> %.1f cyc/mma, wall %.1f us => %.0f MHz\n", c, d[0], d[1], d[2],
+               d[2] ? (double)d[0] / d[2] : 0.0, d[3] / 1e3, d[3] ? d[0] / (d[3] / 1e3) : 0.0);
+      }
+    }
+  } else {
+    TcKernelPlan pl;
+    if (!tc_plan_geometry(pl, N, D, H, W, Cin, cin2, Cout, 0, lo, ks)) { printf("unsupported shape\n"); return 1; }
+    uint16_t *xh = mk(V * Cin, 1), *xl = lo ? mk(V * Cin, 2) : nullptr;
+    uint16_t *x2h = cin2 ? mk(V * cin2, 5) : nullptr, *x2l = (cin2 && lo) ? mk(V * cin2, 6) : nullptr;
+    pl.wp_elems = (size_t)ks * ks * ks * (Cin + cin2) * Cout;
+    pl.wp_hi = mk(pl.wp_elems, 7);
+    pl.wp_lo = lo ? mk(pl.wp_elems, 8) : nullptr;
+    float* y = s.alloc<float>(V * Cout);
+    tc_encode_plan(pl, N, xh, xl, x2h, x2l);
+    TcArgs a;
+    a.g = pl.g; a.bias = nullptr; a.res = nullptr; a.out1 = y; a.out2 = nullptr; a.acc1 = a.acc2 = 0;
+    printf("fprop plan: CT=%d KC=%d T=%d bh=%d bd=%d LP=%d lpt=%d resident=%d n_a=%d n_b=%d items=%d smem=%zu\n", pl.CT, pl.KC, pl.g.T, pl.g.bh,
+           pl.g.bd, pl.g.LP, pl.g.lpt, pl.g.resident, pl.g.n_a, pl.g.n_b, pl.g.n_items, pl.smem);
+    for (int i = 0; i < 3; ++i) tc_launch(pl, a, lo, sms, 0);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) tc_launch(pl, a, lo, sms, 0);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+  }
+  CK(cudaGetLastError());
+  const double us = ms * 1e3 / reps;
+  printf("KBENCH %s N=%d %dx%dx%d Cin=%d+%d Cout=%d prec=%d ks=%d : %.1f us/launch  %.1f TFLOP/s (algorithmic)\n", op.c_str(), N, D, H, W, Cin, cin2,
+         Cout, prec, ks, us, flops / (us * 1e-6) / 1e12);
+  return 0;
+}

@@ -29,6 +29,22 @@ namespace vnb {
 
 using sm100::TmaDesc;
 
+// role-loop structure switches (development): *_SINGLE runs the role's loop on the elected lane only
+#ifdef VNB_TC_PRODUCER_SINGLE
+#define VNB_PROD_ENTER(leader) if (leader)
+#define VNB_PROD_WAIT(leader, bar, ph) mbar_wait(bar, ph)
+#else
+#define VNB_PROD_ENTER(leader)
+#define VNB_PROD_WAIT(leader, bar, ph) mbar_wait_warp(leader, bar, ph)
+#endif
+#ifdef VNB_TC_MMA_SINGLE
+#define VNB_MMA_ENTER(leader) if (leader)
+#define VNB_MMA_WAIT(leader, bar, ph) mbar_wait(bar, ph)
+#else
+#define VNB_MMA_ENTER(leader)
+#define VNB_MMA_WAIT(leader, bar, ph) mbar_wait_warp(leader, bar, ph)
+#endif
+
 constexpr int kTcStages = 4;
 constexpr int kTcThreads = 192;             // 2 control warps + 4 epilogue warps (one epilogue group)
 constexpr int kTcEpiRowPad = 20;  // floats per staged row (16 + 4: conflict-free float4 rows)
@@ -228,7 +244,8 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
   constexpr int RC = KS / 2;
   using namespace sm100;
   const TcGeom& g = p.g;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
+  const int warp = static_cast<int>(warp_uniform(static_cast<uint32_t>(tid >> 5)));
   const uint32_t a_ring = sm_addr;
   const uint32_t b_ring = a_ring + static_cast<uint32_t>(g.n_a) * Cfg::NPL * g.a_stage_bytes;
   const uint32_t epi_off = static_cast<uint32_t>(g.n_a) * Cfg::NPL * g.a_stage_bytes + static_cast<uint32_t>(g.n_b) * Cfg::NPL * Cfg::B_BYTES;
@@ -264,11 +281,13 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = *slot_ptr;
+  const uint32_t tmem = warp_uniform(*slot_ptr);
   const uint32_t a_rows = static_cast<uint32_t>((g.bh + KS - 1) * g.LP);   // rows loaded per A stage
 
+  // warps 0 and 1 run their loops with all lanes (warp-uniform state); one elected lane waits and issues
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    VNB_PROD_ENTER(leader) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
@@ -284,25 +303,26 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
         const int w0 = g.halo ? wb * g.Wt - RC : 0;
         for (int kd = 0; kd < KS; ++kd)
           for (int kc = 0; kc < g.n_kc; ++kc) {
-            mbar_wait(aempty(as), aph ^ 1u);
-            mbar_expect_tx(afull(as), Cfg::NPL * a_rows * Cfg::ROWB);
+            VNB_PROD_WAIT(leader, aempty(as), aph ^ 1u);
             const bool src1 = kc < kc1;
             const int cch = (src1 ? kc : kc - kc1) * KC;
             const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
-            tma_load_5d(a_addr, src1 ? &a1_hi : &a2_hi, afull(as), cch, w0, h0 - RC, d0 + kd - RC, n);
-            if (NSPLIT == 3) tma_load_5d(a_addr + g.a_stage_bytes, src1 ? &a1_lo : &a2_lo, afull(as), cch, w0, h0 - RC, d0 + kd - RC, n);
+            mbar_expect_tx_if(leader, afull(as), Cfg::NPL * a_rows * Cfg::ROWB);
+            tma_load_5d_if(leader, a_addr, src1 ? &a1_hi : &a2_hi, afull(as), cch, w0, h0 - RC, d0 + kd - RC, n);
+            if (NSPLIT == 3)
+              tma_load_5d_if(leader, a_addr + g.a_stage_bytes, src1 ? &a1_lo : &a2_lo, afull(as), cch, w0, h0 - RC, d0 + kd - RC, n);
             if (++as == g.n_a) {
               as = 0;
               aph ^= 1u;
             }
             for (int kh = 0; kh < KS; ++kh) {
               const int it = (kd * KS + kh) * g.n_kc + kc;
-              mbar_wait(bempty(bs), bph ^ 1u);
-              mbar_expect_tx(bfull(bs), Cfg::NPL * Cfg::NB * Cfg::ROWB);
+              VNB_PROD_WAIT(leader, bempty(bs), bph ^ 1u);
               const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
               const int brow = (slice * n_it + it) * Cfg::NB;
-              tma_load_2d(b_addr, &w_hi, bfull(bs), 0, brow);
-              if (NSPLIT == 3) tma_load_2d(b_addr + Cfg::B_BYTES, &w_lo, bfull(bs), 0, brow);
+              mbar_expect_tx_if(leader, bfull(bs), Cfg::NPL * Cfg::NB * Cfg::ROWB);
+              tma_load_2d_if(leader, b_addr, &w_hi, bfull(bs), 0, brow);
+              if (NSPLIT == 3) tma_load_2d_if(leader, b_addr + Cfg::B_BYTES, &w_lo, bfull(bs), 0, brow);
               if (++bs == g.n_b) {
                 bs = 0;
                 bph ^= 1u;
@@ -312,7 +332,8 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    VNB_MMA_ENTER(leader) {
       const uint32_t idesc = make_instr_desc(128, Cfg::NB, FMT_BF16);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
@@ -320,19 +341,19 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
         const int buf = j & 1;
         const uint32_t use = static_cast<uint32_t>(j >> 1);
-        mbar_wait(tempty0 + 8u * buf, (use & 1u) ^ 1u);
+        VNB_MMA_WAIT(leader, tempty0 + 8u * buf, (use & 1u) ^ 1u);
         tc_fence_after_sync();
         const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
         bool first = true;
         for (int kd = 0; kd < KS; ++kd)
           for (int kc = 0; kc < g.n_kc; ++kc) {
-            mbar_wait(afull(as), aph);
+            VNB_MMA_WAIT(leader, afull(as), aph);
             tc_fence_after_sync();
             const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
             const uint64_t da_hi0 = make_smem_desc(a_addr, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
             const uint64_t da_lo0 = da_hi0 + (static_cast<uint32_t>(g.a_stage_bytes) >> 4);
             for (int kh = 0; kh < KS; ++kh) {
-              mbar_wait(bfull(bs), bph);
+              VNB_MMA_WAIT(leader, bfull(bs), bph);
               tc_fence_after_sync();
               const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
               const uint64_t db_hi0 = make_smem_desc(b_addr, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
@@ -344,27 +365,27 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
                   const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
                   const uint32_t acc = (first && ks == 0) ? 0u : 1u;
                   const uint32_t d_addr = d_base + t * Cfg::NB;
-                  mma_f16_ss(d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
+                  mma_f16_ss_if(leader, d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
                   if (NSPLIT == 3) {
-                    mma_f16_ss(d_addr, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
-                    mma_f16_ss(d_addr, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
+                    mma_f16_ss_if(leader, d_addr, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
+                    mma_f16_ss_if(leader, d_addr, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
                   }
                 }
               }
               first = false;
-              mma_commit(bempty(bs));
+              mma_commit_if(leader, bempty(bs));
               if (++bs == g.n_b) {
                 bs = 0;
                 bph ^= 1u;
               }
             }
-            mma_commit(aempty(as));
+            mma_commit_if(leader, aempty(as));
             if (++as == g.n_a) {
               as = 0;
               aph ^= 1u;
             }
           }
-        mma_commit(tfull0 + 8u * buf);
+        mma_commit_if(leader, tfull0 + 8u * buf);
       }
     }
   } else {
@@ -397,7 +418,8 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
   const uint32_t slot_addr = bar_base + 8u * (2 * kTcStages + 4);
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTcStages * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + 8 * (2 * kTcStages + 4));
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
+  const int warp = static_cast<int>(warp_uniform(static_cast<uint32_t>(tid >> 5)));
   const TcGeom& g = p.g;
   const int n_it = KS * KS * g.n_kc;
   const int kc1 = g.C1 / KC;
@@ -424,11 +446,12 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = *slot_ptr;
+  const uint32_t tmem = warp_uniform(*slot_ptr);
 
   if (warp == 0) {
-    // ======================= TMA producer (one elected lane) =======================
-    if (lane == 0) {
+    // ======================= TMA producer (whole warp loops, one elected lane issues) =======================
+    const bool leader = elect_one();
+    VNB_PROD_ENTER(leader) {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
@@ -444,18 +467,18 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
         const int w0 = g.halo ? wb * g.Wt - RC : 0;
         for (int it = 0; it < n_it; ++it) {
           const int kc = it % g.n_kc, kh = (it / g.n_kc) % KS, kd = it / (KS * g.n_kc);
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          VNB_PROD_WAIT(leader, empty_bar(stage), phase ^ 1u);
           const uint32_t st_addr = sm_addr + stage * Cfg::STAGE_BYTES;
           const uint32_t a_bytes = static_cast<uint32_t>(g.bh * g.bd * g.LP) * Cfg::ROWB;
-          mbar_expect_tx(full_bar(stage), Cfg::NPL * (a_bytes + Cfg::NB * Cfg::ROWB));
           const bool src1 = kc < kc1;
           const int cch = (src1 ? kc : kc - kc1) * KC;
-          tma_load_5d(st_addr, src1 ? &a1_hi : &a2_hi, full_bar(stage), cch, w0, h0 + kh - RC, d0 + kd - RC, n);
           const int brow = (slice * n_it + it) * Cfg::NB;
-          tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES, &w_hi, full_bar(stage), 0, brow);
+          mbar_expect_tx_if(leader, full_bar(stage), Cfg::NPL * (a_bytes + Cfg::NB * Cfg::ROWB));
+          tma_load_5d_if(leader, st_addr, src1 ? &a1_hi : &a2_hi, full_bar(stage), cch, w0, h0 + kh - RC, d0 + kd - RC, n);
+          tma_load_2d_if(leader, st_addr + Cfg::NPL * Cfg::A_BYTES, &w_hi, full_bar(stage), 0, brow);
           if (NSPLIT == 3) {
-            tma_load_5d(st_addr + Cfg::A_BYTES, src1 ? &a1_lo : &a2_lo, full_bar(stage), cch, w0, h0 + kh - RC, d0 + kd - RC, n);
-            tma_load_2d(st_addr + Cfg::NPL * Cfg::A_BYTES + Cfg::B_BYTES, &w_lo, full_bar(stage), 0, brow);
+            tma_load_5d_if(leader, st_addr + Cfg::A_BYTES, src1 ? &a1_lo : &a2_lo, full_bar(stage), cch, w0, h0 + kh - RC, d0 + kd - RC, n);
+            tma_load_2d_if(leader, st_addr + Cfg::NPL * Cfg::A_BYTES + Cfg::B_BYTES, &w_lo, full_bar(stage), 0, brow);
           }
           if (++stage == kTcStages) {
             stage = 0;
@@ -465,8 +488,9 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer (one elected lane) =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (whole warp loops, one elected lane issues) =======================
+    const bool leader = elect_one();
+    VNB_MMA_ENTER(leader) {
       const uint32_t idesc = make_instr_desc(128, Cfg::NB, FMT_BF16);
       int stage = 0;
       uint32_t phase = 0;
@@ -474,11 +498,11 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
         const int buf = j & 1;
         const uint32_t use = static_cast<uint32_t>(j >> 1);
-        mbar_wait(tempty_bar(buf), (use & 1u) ^ 1u);
+        VNB_MMA_WAIT(leader, tempty_bar(buf), (use & 1u) ^ 1u);
         tc_fence_after_sync();
         const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
         for (int it = 0; it < n_it; ++it) {
-          mbar_wait(full_bar(stage), phase);
+          VNB_MMA_WAIT(leader, full_bar(stage), phase);
           tc_fence_after_sync();
           // descriptors differ between MMAs only in the start-address field (bits 0-13, units of 16 B):
           // build one base per operand per stage and advance it with a single 64-bit add
@@ -494,20 +518,20 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
               const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
               const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
               const uint32_t d_addr = d_base + t * Cfg::NB;
-              mma_f16_ss(d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
+              mma_f16_ss_if(leader, d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
               if (NSPLIT == 3) {
-                mma_f16_ss(d_addr, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
-                mma_f16_ss(d_addr, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
+                mma_f16_ss_if(leader, d_addr, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
+                mma_f16_ss_if(leader, d_addr, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
               }
             }
           }
-          mma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          mma_commit_if(leader, empty_bar(stage));  // smem slot reusable once these MMAs have read it
           if (++stage == kTcStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        mma_commit(tfull_bar(buf));  // accumulators of this item complete
+        mma_commit_if(leader, tfull_bar(buf));  // accumulators of this item complete
       }
     }
   } else {

@@ -108,6 +108,31 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+// One lane of a converged warp.  The producer / MMA warps run their loops with all 32 lanes (warp-uniform
+// control flow keeps descriptors, barrier addresses and loop state in uniform registers, so the asynchronous
+// instructions issue without per-instruction R2UR waterfalls) and only the elected lane issues them.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// tell the compiler a value is warp-uniform (same idiom as a canonical warp index)
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
+// Barrier wait of a whole role warp: every lane polls the barrier (all lanes observe the same phase in the same
+// instruction) and the warp reconverges before it goes on, so the loop state stays warp-uniform and the
+// asynchronous instructions that follow are issued once, from converged code.
+__device__ __forceinline__ void mbar_wait_warp(bool /*leader*/, uint32_t bar, uint32_t parity) {
+  mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 // named barrier among `count` threads (count a multiple of 32)
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -185,6 +210,66 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
         "=r"(r[7])
       : "r"(taddr)
+      : "memory");
+}
+
+
+// ----------------------------------------------------------------------------------------------
+// predicated forms: the instruction is guarded inside the asm block, so the surrounding control flow stays
+// warp-uniform (all lanes compute the operands in converged code; only the lane with pred != 0 issues)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_f16_ss_if(bool pred, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_if(bool pred, uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar),
+      "r"(static_cast<uint32_t>(pred))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_if(bool pred, uint32_t bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "}" ::"r"(bar),
+      "r"(bytes), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_if(bool pred, uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t"
+      "}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_if(bool pred, uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                               int c3, int c4) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %8, 0;\n\t"
+      "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t"
+      "}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+      "r"(static_cast<uint32_t>(pred))
       : "memory");
 }
 

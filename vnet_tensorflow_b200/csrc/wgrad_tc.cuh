@@ -19,6 +19,25 @@
 
 namespace vnb {
 
+// development counters of the MMA-issuing thread (see WgGeom::dbg); compiled out of the emulation build
+#ifndef VNB_EMULATE
+__device__ __forceinline__ unsigned long long vnb_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VNB_DBG_DECL long long dbg_t0 = clock64(), dbg_wait = 0, dbg_n = 0; unsigned long long dbg_g0 = vnb_globaltimer()
+#define VNB_DBG_WAIT(stmt) do { if (g.dbg) { const long long t_ = clock64(); stmt; dbg_wait += clock64() - t_; } else { stmt; } } while (0)
+#define VNB_DBG_COUNT(n) dbg_n += (n)
+#define VNB_DBG_STORE(ptr, bar) do { if (ptr) { mbar_wait(bar, 0); long long* d_ = (ptr) + 8 * blockIdx.x; d_[0] = clock64() - dbg_t0; d_[1] = dbg_wait; \
+  d_[2] = dbg_n; d_[3] = static_cast<long long>(vnb_globaltimer() - dbg_g0); } } while (0)
+#else
+#define VNB_DBG_DECL
+#define VNB_DBG_WAIT(stmt) stmt
+#define VNB_DBG_COUNT(n)
+#define VNB_DBG_STORE(ptr, bar)
+#endif
+
 constexpr int kWgThreads = 192;
 
 struct WgGeom {
@@ -32,6 +51,8 @@ struct WgGeom {
   int z_stages;
   int xt_bytes, zt_bytes;  // per-plane tile sizes (1024-aligned)
   int npl;           // 1 (bf16) or 2 (hi/lo)
+  long long* dbg;    // development counters (tools/kbench.cu), null in the product: per CTA {loop cycles, cycles
+                     // waiting on TMA data, MMAs issued, wall ns}
 };
 
 // KS = 3 serves the attention / output module convolutions with the same scheme: 3 useful kw atoms of 8,
@@ -68,7 +89,8 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
   const uint32_t slot_addr = bar_base + 8u * 33;
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + bar_off + 8 * 33);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = static_cast<int>(warp_uniform(static_cast<uint32_t>(tid >> 5)));
   const int pair = blockIdx.x / g.splits, split = blockIdx.x % g.splits;
   const int ci_chunk = pair / g.n_co, co_chunk = pair % g.n_co;
   // work units u = ((n * n_hb + hb) * D + dz); this CTA owns the contiguous run [u0, u1)
@@ -96,10 +118,13 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem = *slot_ptr;
+  const uint32_t tmem = warp_uniform(*slot_ptr);
 
+  // warps 0 and 1 run their loops with all lanes (uniform control flow and descriptors); one elected lane waits on
+  // the barriers and issues the TMA / MMA / commit instructions
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    {
       const bool src1 = ci_chunk * 16 < g.C1;
       const int xc = src1 ? ci_chunk * 16 : ci_chunk * 16 - g.C1;
       const TmaDesc* xh = src1 ? &x1_hi : &x2_hi;
@@ -118,16 +143,16 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
         for (int pl = chain_start ? dz - RC : dz + RC; pl <= dz + RC; ++pl) {
           const int xs = static_cast<int>(xload % XS);
           const uint32_t xph = static_cast<uint32_t>((xload / XS) & 1);
-          mbar_wait(xempty(xs), xph ^ 1u);
-          mbar_expect_tx(xfull(xs), x_tx);
-          tma_load_5d(x_ring + (xs * NPL) * g.xt_bytes, xh, xfull(xs), xc, -RC, h0, pl, n);
-          if (NSPLIT == 3) tma_load_5d(x_ring + (xs * NPL + 1) * g.xt_bytes, xl, xfull(xs), xc, -RC, h0, pl, n);
+          mbar_wait_warp(leader, xempty(xs), xph ^ 1u);
+          mbar_expect_tx_if(leader, xfull(xs), x_tx);
+          tma_load_5d_if(leader, x_ring + (xs * NPL) * g.xt_bytes, xh, xfull(xs), xc, -RC, h0, pl, n);
+          if (NSPLIT == 3) tma_load_5d_if(leader, x_ring + (xs * NPL + 1) * g.xt_bytes, xl, xfull(xs), xc, -RC, h0, pl, n);
           ++xload;
         }
-        mbar_wait(zempty(zs), zph ^ 1u);
-        mbar_expect_tx(zfull(zs), z_tx);
-        tma_load_5d(z_ring + (zs * NPL) * g.zt_bytes, &z_hi, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
-        if (NSPLIT == 3) tma_load_5d(z_ring + (zs * NPL + 1) * g.zt_bytes, &z_lo, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
+        mbar_wait_warp(leader, zempty(zs), zph ^ 1u);
+        mbar_expect_tx_if(leader, zfull(zs), z_tx);
+        tma_load_5d_if(leader, z_ring + (zs * NPL) * g.zt_bytes, &z_hi, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
+        if (NSPLIT == 3) tma_load_5d_if(leader, z_ring + (zs * NPL + 1) * g.zt_bytes, &z_lo, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
         if (++zs == g.z_stages) {
           zs = 0;
           zph ^= 1u;
@@ -135,17 +160,19 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    {
       const uint32_t idesc = make_instr_desc(128, NB, FMT_BF16, 1, 1);
       const uint32_t sbo_a = lpm == 2 ? x_pitch : 256u;   // K rows 8..15: next line (W = 8) or next 8 voxels
       const uint32_t sbo_b = 256u;                         // dZ lines are contiguous, so both cases are +256 B
       int zs = 0;
       uint32_t zph = 0;
       long long xlo = 0;     // load index of X plane dz - RC of the current step
+      VNB_DBG_DECL;
       for (long long u = u0; u < u1; ++u) {
         const int dz = static_cast<int>(u % g.D);
         const bool chain_end = (u + 1 == u1) || dz + 1 == g.D;
-        mbar_wait(zfull(zs), zph);
+        VNB_DBG_WAIT(mbar_wait_warp(leader, zfull(zs), zph));
         tc_fence_after_sync();
         const uint32_t za_hi = z_ring + (zs * NPL) * g.zt_bytes;
         const uint64_t db0 = make_smem_desc(za_hi, z_pitch, sbo_b, SWZ_32B);
@@ -153,7 +180,7 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
         for (int kd = 0; kd < KS; ++kd) {
           const long long xi = xlo + kd;   // X plane dz + kd - RC
           const int xs = static_cast<int>(xi % XS);
-          mbar_wait(xfull(xs), static_cast<uint32_t>((xi / XS) & 1));
+          VNB_DBG_WAIT(mbar_wait_warp(leader, xfull(xs), static_cast<uint32_t>((xi / XS) & 1)));
           tc_fence_after_sync();
           const uint32_t xa_hi = x_ring + (xs * NPL) * g.xt_bytes;
           const uint32_t d_addr = tmem + kd * NB;
@@ -165,28 +192,32 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
             uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t) * x_pitch) >> 4);
             uint64_t boff = static_cast<uint64_t>((static_cast<uint32_t>(t) * z_pitch) >> 4);
             for (int ks = 0; ks < ksteps; ++ks) {
-              mma_f16_ss(d_addr, da0 + aoff, db0 + boff, idesc, acc);
+              mma_f16_ss_if(leader, d_addr, da0 + aoff, db0 + boff, idesc, acc);
               if (NSPLIT == 3) {
-                mma_f16_ss(d_addr, da0_lo + aoff, db0 + boff, idesc, 1u);
-                mma_f16_ss(d_addr, da0 + aoff, db0_lo + boff, idesc, 1u);
+                mma_f16_ss_if(leader, d_addr, da0_lo + aoff, db0 + boff, idesc, 1u);
+                mma_f16_ss_if(leader, d_addr, da0 + aoff, db0_lo + boff, idesc, 1u);
               }
               acc = 1u;
+              VNB_DBG_COUNT(NSPLIT == 3 ? 3 : 1);
               aoff += 32;  // next 16 voxels: 16 rows x 32 B = 512 B (only taken when lpm == 1)
               boff += 32;
             }
           }
         }
-        mma_commit(zempty(zs));
+        mma_commit_if(leader, zempty(zs));
         if (++zs == g.z_stages) {
           zs = 0;
           zph ^= 1u;
         }
         // X plane dz - RC is dead after this step; at the end of a run of planes so are the other KS-1
         const int dead = chain_end ? KS : 1;
-        for (int k = 0; k < dead; ++k) mma_commit(xempty(static_cast<int>((xlo + k) % XS)));
+        for (int k = 0; k < dead; ++k) mma_commit_if(leader, xempty(static_cast<int>((xlo + k) % XS)));
         xlo += dead;
       }
-      mma_commit(done_bar);
+      mma_commit_if(leader, done_bar);
+      if (leader) {
+        VNB_DBG_STORE(g.dbg, done_bar);
+      }
     }
   } else {
     // read-out: thread = accumulator row m = (kw slot j, ci); columns n = (l, co); kh = KS-1 - l
