@@ -77,6 +77,8 @@ int main(int argc, char** argv) {
     tc_encode_plan(pl, N, xh, xl, x2h, x2l);
     TcArgs a;
     a.g = pl.g; a.bias = nullptr; a.res = nullptr; a.out1 = y; a.out2 = nullptr; a.acc1 = a.acc2 = 0;
+    long long* dbg = nullptr;
+    if (getenv("VNB_KB_DBG")) { dbg = s.alloc<long long>(8 * 1024); CK(cudaMemset(dbg, 0, 8 * 1024 * sizeof(long long))); a.dbg = dbg; }
     printf("fprop plan: CT=%d KC=%d T=%d bh=%d bd=%d LP=%d lpt=%d resident=%d n_a=%d n_b=%d items=%d smem=%zu\n", pl.CT, pl.KC, pl.g.T, pl.g.bh,
            pl.g.bd, pl.g.LP, pl.g.lpt, pl.g.resident, pl.g.n_a, pl.g.n_b, pl.g.n_items, pl.smem);
     for (int i = 0; i < 3; ++i) tc_launch(pl, a, lo, sms, 0);
@@ -86,6 +88,15 @@ int main(int argc, char** argv) {
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (dbg) {
+      std::vector<long long> h(8 * 1024);
+      CK(cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      for (int c : {0, sms - 1}) {
+        const long long* d = &h[8 * c];
+        printf("  cta %3d: loop cycles %lld  wait TMA %lld  wait accumulator %lld  mmas %lld  -> %.1f cyc/mma, wall %.1f us => %.0f MHz\n", c, d[0], d[1], d[4],
+               d[2], d[2] ? (double)d[0] / d[2] : 0.0, d[3] / 1e3, d[3] ? d[0] / (d[3] / 1e3) : 0.0);
+      }
+    }
   }
   CK(cudaGetLastError());
   const double us = ms * 1e3 / reps;

@@ -29,20 +29,25 @@ namespace vnb {
 
 using sm100::TmaDesc;
 
-// role-loop structure switches (development): *_SINGLE runs the role's loop on the elected lane only
-#ifdef VNB_TC_PRODUCER_SINGLE
-#define VNB_PROD_ENTER(leader) if (leader)
-#define VNB_PROD_WAIT(leader, bar, ph) mbar_wait(bar, ph)
+// development counters of the MMA-issuing thread (WgGeom::dbg, TcArgs::dbg); compiled out of the emulation build
+#ifndef VNB_EMULATE
+__device__ __forceinline__ unsigned long long vnb_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VNB_DBG_DECL long long dbg_t0 = clock64(), dbg_wait = 0, dbg_wait2 = 0, dbg_n = 0; unsigned long long dbg_g0 = vnb_globaltimer()
+#define VNB_DBG_WAITP(ptr, ctr, stmt) do { if (ptr) { const long long t_ = clock64(); stmt; ctr += clock64() - t_; } else { stmt; } } while (0)
+#define VNB_DBG_WAIT(stmt) VNB_DBG_WAITP(g.dbg, dbg_wait, stmt)
+#define VNB_DBG_COUNT(n) dbg_n += (n)
+#define VNB_DBG_STORE(ptr, bar, par) do { if (ptr) { mbar_wait(bar, par); long long* d_ = (ptr) + 8 * blockIdx.x; d_[0] = clock64() - dbg_t0; d_[1] = dbg_wait; \
+  d_[2] = dbg_n; d_[3] = static_cast<long long>(vnb_globaltimer() - dbg_g0); d_[4] = dbg_wait2; } } while (0)
 #else
-#define VNB_PROD_ENTER(leader)
-#define VNB_PROD_WAIT(leader, bar, ph) mbar_wait_warp(leader, bar, ph)
-#endif
-#ifdef VNB_TC_MMA_SINGLE
-#define VNB_MMA_ENTER(leader) if (leader)
-#define VNB_MMA_WAIT(leader, bar, ph) mbar_wait(bar, ph)
-#else
-#define VNB_MMA_ENTER(leader)
-#define VNB_MMA_WAIT(leader, bar, ph) mbar_wait_warp(leader, bar, ph)
+#define VNB_DBG_DECL
+#define VNB_DBG_WAIT(stmt) stmt
+#define VNB_DBG_WAITP(ptr, ctr, stmt) stmt
+#define VNB_DBG_COUNT(n)
+#define VNB_DBG_STORE(ptr, bar, par)
 #endif
 
 constexpr int kTcStages = 4;
@@ -103,6 +108,8 @@ struct TcArgs {
   float* out1;
   float* out2;
   int acc1, acc2;
+  long long* dbg = nullptr;   // development counters (tools/kbench.cu): per CTA {loop cycles, cycles waiting on TMA
+                              // data, MMAs, wall ns, cycles waiting for a free accumulator}
 };
 
 // epilogue shared by both pipeline modes: TMEM -> registers -> shift-sum over the 5 kw slices -> bias /
@@ -287,7 +294,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
   // warps 0 and 1 run their loops with all lanes (warp-uniform state); one elected lane waits and issues
   if (warp == 0) {
     const bool leader = elect_one();
-    VNB_PROD_ENTER(leader) {
+    {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
@@ -303,7 +310,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
         const int w0 = g.halo ? wb * g.Wt - RC : 0;
         for (int kd = 0; kd < KS; ++kd)
           for (int kc = 0; kc < g.n_kc; ++kc) {
-            VNB_PROD_WAIT(leader, aempty(as), aph ^ 1u);
+            mbar_wait_warp(aempty(as), aph ^ 1u);
             const bool src1 = kc < kc1;
             const int cch = (src1 ? kc : kc - kc1) * KC;
             const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
@@ -317,7 +324,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
             }
             for (int kh = 0; kh < KS; ++kh) {
               const int it = (kd * KS + kh) * g.n_kc + kc;
-              VNB_PROD_WAIT(leader, bempty(bs), bph ^ 1u);
+              mbar_wait_warp(bempty(bs), bph ^ 1u);
               const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
               const int brow = (slice * n_it + it) * Cfg::NB;
               mbar_expect_tx_if(leader, bfull(bs), Cfg::NPL * Cfg::NB * Cfg::ROWB);
@@ -333,28 +340,38 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    VNB_MMA_ENTER(leader) {
+    {
       const uint32_t idesc = make_instr_desc(128, Cfg::NB, FMT_BF16);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int j = 0;
+      bool a_rdy = false, b_rdy = false;   // look-ahead barrier tests (false: take the blocking wait)
+      VNB_DBG_DECL;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
         const int buf = j & 1;
         const uint32_t use = static_cast<uint32_t>(j >> 1);
-        VNB_MMA_WAIT(leader, tempty0 + 8u * buf, (use & 1u) ^ 1u);
+        VNB_DBG_WAITP(p.dbg, dbg_wait2, mbar_wait_warp(tempty0 + 8u * buf, (use & 1u) ^ 1u));
         tc_fence_after_sync();
         const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
         bool first = true;
         for (int kd = 0; kd < KS; ++kd)
           for (int kc = 0; kc < g.n_kc; ++kc) {
-            VNB_MMA_WAIT(leader, afull(as), aph);
+            VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(afull(as), aph, a_rdy));
             tc_fence_after_sync();
+            {  // look at the next A stage now, use the answer when we get there
+              const int as_n = as + 1 == g.n_a ? 0 : as + 1;
+              a_rdy = mbar_test(afull(as_n), as_n == 0 ? aph ^ 1u : aph);
+            }
             const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
             const uint64_t da_hi0 = make_smem_desc(a_addr, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
             const uint64_t da_lo0 = da_hi0 + (static_cast<uint32_t>(g.a_stage_bytes) >> 4);
             for (int kh = 0; kh < KS; ++kh) {
-              VNB_MMA_WAIT(leader, bfull(bs), bph);
+              VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(bfull(bs), bph, b_rdy));
               tc_fence_after_sync();
+              {
+                const int bs_n = bs + 1 == g.n_b ? 0 : bs + 1;
+                b_rdy = mbar_test(bfull(bs_n), bs_n == 0 ? bph ^ 1u : bph);
+              }
               const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
               const uint64_t db_hi0 = make_smem_desc(b_addr, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
               const uint64_t db_lo0 = db_hi0 + (Cfg::B_BYTES >> 4);
@@ -365,6 +382,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
                   const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
                   const uint32_t acc = (first && ks == 0) ? 0u : 1u;
                   const uint32_t d_addr = d_base + t * Cfg::NB;
+                  VNB_DBG_COUNT(NSPLIT == 3 ? 3 : 1);
                   mma_f16_ss_if(leader, d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
                   if (NSPLIT == 3) {
                     mma_f16_ss_if(leader, d_addr, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
@@ -386,6 +404,9 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
             }
           }
         mma_commit_if(leader, tfull0 + 8u * buf);
+      }
+      if (leader && j > 0) {
+        VNB_DBG_STORE(p.dbg, tfull0 + 8u * ((j - 1) & 1), ((j - 1) >> 1) & 1);
       }
     }
   } else {
@@ -451,7 +472,7 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
   if (warp == 0) {
     // ======================= TMA producer (whole warp loops, one elected lane issues) =======================
     const bool leader = elect_one();
-    VNB_PROD_ENTER(leader) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
@@ -467,7 +488,7 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
         const int w0 = g.halo ? wb * g.Wt - RC : 0;
         for (int it = 0; it < n_it; ++it) {
           const int kc = it % g.n_kc, kh = (it / g.n_kc) % KS, kd = it / (KS * g.n_kc);
-          VNB_PROD_WAIT(leader, empty_bar(stage), phase ^ 1u);
+          mbar_wait_warp(empty_bar(stage), phase ^ 1u);
           const uint32_t st_addr = sm_addr + stage * Cfg::STAGE_BYTES;
           const uint32_t a_bytes = static_cast<uint32_t>(g.bh * g.bd * g.LP) * Cfg::ROWB;
           const bool src1 = kc < kc1;
@@ -490,20 +511,26 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
   } else if (warp == 1) {
     // ======================= MMA issuer (whole warp loops, one elected lane issues) =======================
     const bool leader = elect_one();
-    VNB_MMA_ENTER(leader) {
+    {
       const uint32_t idesc = make_instr_desc(128, Cfg::NB, FMT_BF16);
       int stage = 0;
       uint32_t phase = 0;
       int j = 0;
+      bool rdy = false;   // look-ahead barrier test of the next stage
+      VNB_DBG_DECL;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
         const int buf = j & 1;
         const uint32_t use = static_cast<uint32_t>(j >> 1);
-        VNB_MMA_WAIT(leader, tempty_bar(buf), (use & 1u) ^ 1u);
+        VNB_DBG_WAITP(p.dbg, dbg_wait2, mbar_wait_warp(tempty_bar(buf), (use & 1u) ^ 1u));
         tc_fence_after_sync();
         const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
         for (int it = 0; it < n_it; ++it) {
-          VNB_MMA_WAIT(leader, full_bar(stage), phase);
+          VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(full_bar(stage), phase, rdy));
           tc_fence_after_sync();
+          {
+            const int st_n = stage + 1 == kTcStages ? 0 : stage + 1;
+            rdy = mbar_test(full_bar(st_n), st_n == 0 ? phase ^ 1u : phase);
+          }
           // descriptors differ between MMAs only in the start-address field (bits 0-13, units of 16 B):
           // build one base per operand per stage and advance it with a single 64-bit add
           const uint32_t a_hi = sm_addr + stage * Cfg::STAGE_BYTES;
@@ -518,6 +545,7 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
               const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
               const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
               const uint32_t d_addr = d_base + t * Cfg::NB;
+              VNB_DBG_COUNT(NSPLIT == 3 ? 3 : 1);
               mma_f16_ss_if(leader, d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
               if (NSPLIT == 3) {
                 mma_f16_ss_if(leader, d_addr, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
@@ -532,6 +560,9 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
           }
         }
         mma_commit_if(leader, tfull_bar(buf));  // accumulators of this item complete
+      }
+      if (leader && j > 0) {
+        VNB_DBG_STORE(p.dbg, tfull_bar((j - 1) & 1), ((j - 1) >> 1) & 1);
       }
     }
   } else {

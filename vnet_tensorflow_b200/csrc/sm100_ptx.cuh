@@ -125,11 +125,27 @@ __device__ __forceinline__ bool elect_one() {
 // tell the compiler a value is warp-uniform (same idiom as a canonical warp index)
 __device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 
+// Non-blocking look at a barrier phase.  The role warps issue it one pipeline stage early and consume the result a
+// stage later, which takes the ~100-cycle round trip of a barrier query off the per-stage critical path.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Barrier wait of a whole role warp: every lane polls the barrier (all lanes observe the same phase in the same
 // instruction) and the warp reconverges before it goes on, so the loop state stays warp-uniform and the
-// asynchronous instructions that follow are issued once, from converged code.
-__device__ __forceinline__ void mbar_wait_warp(bool /*leader*/, uint32_t bar, uint32_t parity) {
-  mbar_wait(bar, parity);
+// asynchronous instructions that follow are issued once, from converged code.  `ready` = an earlier mbar_test of
+// the same phase already succeeded.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, bool ready = false) {
+  if (!ready) mbar_wait(bar, parity);
   __syncwarp();
 }
 

@@ -19,25 +19,6 @@
 
 namespace vnb {
 
-// development counters of the MMA-issuing thread (see WgGeom::dbg); compiled out of the emulation build
-#ifndef VNB_EMULATE
-__device__ __forceinline__ unsigned long long vnb_globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-#define VNB_DBG_DECL long long dbg_t0 = clock64(), dbg_wait = 0, dbg_n = 0; unsigned long long dbg_g0 = vnb_globaltimer()
-#define VNB_DBG_WAIT(stmt) do { if (g.dbg) { const long long t_ = clock64(); stmt; dbg_wait += clock64() - t_; } else { stmt; } } while (0)
-#define VNB_DBG_COUNT(n) dbg_n += (n)
-#define VNB_DBG_STORE(ptr, bar) do { if (ptr) { mbar_wait(bar, 0); long long* d_ = (ptr) + 8 * blockIdx.x; d_[0] = clock64() - dbg_t0; d_[1] = dbg_wait; \
-  d_[2] = dbg_n; d_[3] = static_cast<long long>(vnb_globaltimer() - dbg_g0); } } while (0)
-#else
-#define VNB_DBG_DECL
-#define VNB_DBG_WAIT(stmt) stmt
-#define VNB_DBG_COUNT(n)
-#define VNB_DBG_STORE(ptr, bar)
-#endif
-
 constexpr int kWgThreads = 192;
 
 struct WgGeom {
@@ -143,13 +124,13 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
         for (int pl = chain_start ? dz - RC : dz + RC; pl <= dz + RC; ++pl) {
           const int xs = static_cast<int>(xload % XS);
           const uint32_t xph = static_cast<uint32_t>((xload / XS) & 1);
-          mbar_wait_warp(leader, xempty(xs), xph ^ 1u);
+          mbar_wait_warp(xempty(xs), xph ^ 1u);
           mbar_expect_tx_if(leader, xfull(xs), x_tx);
           tma_load_5d_if(leader, x_ring + (xs * NPL) * g.xt_bytes, xh, xfull(xs), xc, -RC, h0, pl, n);
           if (NSPLIT == 3) tma_load_5d_if(leader, x_ring + (xs * NPL + 1) * g.xt_bytes, xl, xfull(xs), xc, -RC, h0, pl, n);
           ++xload;
         }
-        mbar_wait_warp(leader, zempty(zs), zph ^ 1u);
+        mbar_wait_warp(zempty(zs), zph ^ 1u);
         mbar_expect_tx_if(leader, zfull(zs), z_tx);
         tma_load_5d_if(leader, z_ring + (zs * NPL) * g.zt_bytes, &z_hi, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
         if (NSPLIT == 3) tma_load_5d_if(leader, z_ring + (zs * NPL + 1) * g.zt_bytes, &z_lo, zfull(zs), co_chunk * 16, 0, h0 - RC, dz, n);
@@ -168,11 +149,12 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
       int zs = 0;
       uint32_t zph = 0;
       long long xlo = 0;     // load index of X plane dz - RC of the current step
+      long long x_seen = -1; // newest X-plane load whose barrier this warp has already observed
       VNB_DBG_DECL;
       for (long long u = u0; u < u1; ++u) {
         const int dz = static_cast<int>(u % g.D);
         const bool chain_end = (u + 1 == u1) || dz + 1 == g.D;
-        VNB_DBG_WAIT(mbar_wait_warp(leader, zfull(zs), zph));
+        VNB_DBG_WAIT(mbar_wait_warp(zfull(zs), zph));
         tc_fence_after_sync();
         const uint32_t za_hi = z_ring + (zs * NPL) * g.zt_bytes;
         const uint64_t db0 = make_smem_desc(za_hi, z_pitch, sbo_b, SWZ_32B);
@@ -180,8 +162,11 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
         for (int kd = 0; kd < KS; ++kd) {
           const long long xi = xlo + kd;   // X plane dz + kd - RC
           const int xs = static_cast<int>(xi % XS);
-          VNB_DBG_WAIT(mbar_wait_warp(leader, xfull(xs), static_cast<uint32_t>((xi / XS) & 1)));
-          tc_fence_after_sync();
+          if (xi > x_seen) {   // planes of earlier steps were waited for then (only the newest plane of a step is new)
+            VNB_DBG_WAIT(mbar_wait_warp(xfull(xs), static_cast<uint32_t>((xi / XS) & 1)));
+            tc_fence_after_sync();
+            x_seen = xi;
+          }
           const uint32_t xa_hi = x_ring + (xs * NPL) * g.xt_bytes;
           const uint32_t d_addr = tmem + kd * NB;
           // only the start-address field changes between MMAs: one base descriptor per operand, 64-bit adds after
@@ -216,7 +201,7 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
       }
       mma_commit_if(leader, done_bar);
       if (leader) {
-        VNB_DBG_STORE(g.dbg, done_bar);
+        VNB_DBG_STORE(g.dbg, done_bar, 0);
       }
     }
   } else {
