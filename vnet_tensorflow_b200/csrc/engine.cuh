@@ -1260,9 +1260,11 @@ class Engine {
   static bool k2_tiled_ok(const K2Args& p) { return p.CF % 16 == 0 && p.CC % 16 == 0; }
   void launch_k2_gather(const K2Args& p) {
     const long long M = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
+    if (M > 0xFFFFFFFFLL) throw std::invalid_argument("2x2x2 convolution: more than 2^32 coarse voxels per batch");
     if (k2_tiled_ok(p)) {
       dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (p.CC + kK2_BN - 1) / kK2_BN);
-      VNB_LAUNCH(k2_gather_tiled_kernel, grid, 256, 0, stream_, p, M);
+      if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_gather_tiled_kernel<true>, grid, 256, 0, stream_, p, M);
+      else VNB_LAUNCH(k2_gather_tiled_kernel<false>, grid, 256, 0, stream_, p, M);
     } else {
       VNB_LAUNCH(k2_gather_kernel, grid_for(M * p.CC, 256), 256, 0, stream_, p);
     }
@@ -1270,9 +1272,11 @@ class Engine {
   }
   void launch_k2_scatter(const K2Args& p) {
     const long long M = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
+    if (M > 0xFFFFFFFFLL) throw std::invalid_argument("2x2x2 convolution: more than 2^32 coarse voxels per batch");
     if (k2_tiled_ok(p)) {
       dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (8 * p.CF + kK2_BN - 1) / kK2_BN);
-      VNB_LAUNCH(k2_scatter_tiled_kernel, grid, 256, 0, stream_, p, M);
+      if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_scatter_tiled_kernel<true>, grid, 256, 0, stream_, p, M);
+      else VNB_LAUNCH(k2_scatter_tiled_kernel<false>, grid, 256, 0, stream_, p, M);
     } else {
       VNB_LAUNCH(k2_scatter_kernel, grid_for(M * 8 * p.CF, 256), 256, 0, stream_, p);
     }
@@ -1280,13 +1284,15 @@ class Engine {
   }
   void launch_k2_wgrad(const K2Args& p) {
     const long long M = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
+    if (M > 0xFFFFFFFFLL) throw std::invalid_argument("2x2x2 convolution: more than 2^32 coarse voxels per batch");
     if (k2_tiled_ok(p)) {
       const int gx = (8 * p.CF + kK2_BM - 1) / kK2_BM, gy = (p.CC + kK2_BN - 1) / kK2_BN;
       long long splits = std::max<long long>(1, std::min<long long>((M + 255) / 256, (4 * 148 + gx * gy - 1) / (gx * gy)));
       long long mps = ((M + splits - 1) / splits + kK2_BK - 1) / kK2_BK * kK2_BK;
       splits = (M + mps - 1) / mps;
       dim3 grid(gx, gy, static_cast<unsigned>(splits));
-      VNB_LAUNCH(k2_wgrad_tiled_kernel, grid, 256, 0, stream_, p, M, mps);
+      if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_wgrad_tiled_kernel<true>, grid, 256, 0, stream_, p, M, mps);
+      else VNB_LAUNCH(k2_wgrad_tiled_kernel<false>, grid, 256, 0, stream_, p, M, mps);
     } else {
       const long long outs = 8LL * p.CF * p.CC;
       const int oblocks = static_cast<int>((outs + 255) / 256);

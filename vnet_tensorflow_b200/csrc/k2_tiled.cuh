@@ -5,29 +5,110 @@
 //   gather  C[m][cc]        = sum_{tap,cf} fine[child(m,tap)][cf] * w[tap][cf][cc]      (down fprop, up dgrad)
 //   scatter fine[child][cf] = sum_cc coarse[m][cc] * w[tap][cf][cc]                     (up fprop, down dgrad)
 //   wgrad   dw[tap][cf][cc] = sum_m fine[child(m,tap)][cf] * coarse[m][cc]              (both)
-// 64x64 output tile per 256-thread block, 4x4 outputs per thread, K chunks of 16 through shared memory.
+// 64x64 output tile per 256-thread block, K chunks of 16 through shared memory.  Inner product, by template flag:
+//   MMA = false : exact fp32 FMA, 4x4 outputs per thread (the fp32 parity path)
+//   MMA = true  : warp-level mma.sync m16n8k8 TF32 on (big, small) splits of both operands, small*big + big*small +
+//                 big*big with fp32 accumulate ("3xTF32": fp32-grade products, like the bf16x3 convolutions); the
+//                 kernels are then bound by the activation traffic instead of the FMA pipe.  Used by the
+//                 tensor-core precision modes.
 #pragma once
 #include "conv_ref.cuh"
 
 namespace vnb {
 
-constexpr int kK2_BM = 64, kK2_BN = 64, kK2_BK = 16, kK2_PAD = 4;
+constexpr int kK2_BM = 64, kK2_BN = 64, kK2_BK = 16, kK2_PAD = 8;   // pitch 72: conflict-free MMA fragment reads
 
-__device__ __forceinline__ long long k2_child(const K2Args& p, long long m, int tap) {
-  // m: flat coarse voxel index over [N][Dc][Hc][Wc]; returns flat fine voxel index
-  long long o = m;
-  const int ow = static_cast<int>(o % p.cd.W);
-  o /= p.cd.W;
-  const int oh = static_cast<int>(o % p.cd.H);
-  o /= p.cd.H;
-  const int od = static_cast<int>(o % p.cd.D);
-  const long long n = o / p.cd.D;
-  const int fd = 2 * od + (tap >> 2), fh = 2 * oh + ((tap >> 1) & 1), fw = 2 * ow + (tap & 1);
-  return ((n * (2 * p.cd.D) + fd) * (2 * p.cd.H) + fh) * (2 * p.cd.W) + fw;
+#ifndef VNB_EMULATE
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+#else
+// CPU model of the warp-level MMA (tests): lanes publish their fragments, rendezvous, then each lane forms its four
+// outputs.  Fragment layout of mma.m16n8k8 (g = lane / 4, q = lane % 4):
+//   a0 (g, q)  a1 (g+8, q)  a2 (g, q+4)  a3 (g+8, q+4);  b0 (k=q, n=g)  b1 (k=q+4, n=g);  c0,c1 (g, 2q+{0,1})  c2,c3 (g+8, ..)
+inline void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  static uint32_t fa[64][32][4], fb[64][32][2];
+  const int lin = emul::cur()->lin, w = (lin / 32) % 64, lane = lin & 31;
+  for (int i = 0; i < 4; ++i) fa[w][lane][i] = a[i] & 0xFFFFE000u;   // TF32 keeps 10 mantissa bits
+  for (int i = 0; i < 2; ++i) fb[w][lane][i] = b[i] & 0xFFFFE000u;
+  __syncwarp();
+  const int g = lane >> 2, q = lane & 3;
+  auto A = [&](int row, int k) {
+    const uint32_t u = fa[w][(row & 7) * 4 + (k & 3)][(row >> 3) + 2 * (k >> 2)];
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  auto B = [&](int k, int n) {
+    const uint32_t u = fb[w][n * 4 + (k & 3)][k >> 2];
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  for (int h = 0; h < 2; ++h)
+    for (int j = 0; j < 2; ++j) {
+      float sum = c[2 * h + j];
+      for (int k = 0; k < 8; ++k) sum += A(g + 8 * h, k) * B(k, 2 * q + j);
+      c[2 * h + j] = sum;
+    }
+  __syncwarp();
+}
+#endif
+
+// big / small TF32 split of an fp32 value: big keeps the top 11 significant bits, small = x - big is exact
+__device__ __forceinline__ void tf32_split(float x, uint32_t& big, uint32_t& small) {
+#if defined(__CUDA_ARCH__)
+  big = __float_as_uint(x) & 0xFFFFE000u;
+  small = __float_as_uint(x - __uint_as_float(big));
+#else
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  big = u & 0xFFFFE000u;
+  float fb, fs;
+  memcpy(&fb, &big, 4);
+  fs = x - fb;
+  memcpy(&small, &fs, 4);
+#endif
 }
 
-__device__ __forceinline__ void k2_tile_fma(const float (*As)[kK2_BM + kK2_PAD], const float (*Bs)[kK2_BN + kK2_PAD],
-                                            int ty, int tx, float (&acc)[4][4]) {
+// accumulators of one thread: FMA path acc[i][j] = (row ty*4+i, col tx*4+j); MMA path: warp tile 32 x 16 at
+// (wm*32, wn*16), v[mi*8 + ni*4 + e] = MMA tile (mi, ni) element e
+struct K2Acc {
+  float v[16];
+};
+
+template <bool MMA>
+__device__ __forceinline__ void k2_tile_product(const float (*As)[kK2_BM + kK2_PAD], const float (*Bs)[kK2_BN + kK2_PAD], int t,
+                                                K2Acc& acc);
+
+// Fine-grid index arithmetic.  A coarse voxel m = ((n*Dc + od)*Hc + oh)*Wc + ow owns the 2x2x2 fine block whose
+// first voxel (tap 0) is k2_fine_base(m); tap = (a, b, c) adds k2_tap_offset.  Voxel counts fit 32 bits (the engine
+// checks this when it builds the graph), so the decomposition uses 32-bit divisions and is hoisted out of the K loops.
+__device__ __forceinline__ long long k2_fine_base(const K2Args& p, long long m) {
+  unsigned o = static_cast<unsigned>(m);
+  const unsigned W = p.cd.W, H = p.cd.H, D = p.cd.D;
+  const unsigned ow = o % W;
+  o /= W;
+  const unsigned oh = o % H;
+  o /= H;
+  const unsigned od = o % D;
+  const unsigned n = o / D;
+  return ((static_cast<long long>(n) * (2 * D) + 2 * od) * (2 * H) + 2 * oh) * (2 * W) + 2 * ow;
+}
+__device__ __forceinline__ long long k2_tap_offset(const K2Args& p, int tap) {
+  return (static_cast<long long>(tap >> 2) * (2 * p.cd.H) + ((tap >> 1) & 1)) * (2 * p.cd.W) + (tap & 1);
+}
+__device__ __forceinline__ long long k2_child(const K2Args& p, long long m, int tap) {
+  return k2_fine_base(p, m) + k2_tap_offset(p, tap);
+}
+
+template <>
+__device__ __forceinline__ void k2_tile_product<false>(const float (*As)[kK2_BM + kK2_PAD], const float (*Bs)[kK2_BN + kK2_PAD],
+                                                       int t, K2Acc& acc) {
+  const int tx = t % 16, ty = t / 16;
 #pragma unroll
   for (int k = 0; k < kK2_BK; ++k) {
     float a[4], b[4];
@@ -38,30 +119,105 @@ __device__ __forceinline__ void k2_tile_fma(const float (*As)[kK2_BM + kK2_PAD],
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+      for (int j = 0; j < 4; ++j) acc.v[i * 4 + j] += a[i] * b[j];
   }
+}
+
+template <>
+__device__ __forceinline__ void k2_tile_product<true>(const float (*As)[kK2_BM + kK2_PAD], const float (*Bs)[kK2_BN + kK2_PAD],
+                                                      int t, K2Acc& acc) {
+  const int warp = t >> 5, lane = t & 31, g = lane >> 2, q = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
+#pragma unroll
+  for (int ks = 0; ks < kK2_BK; ks += 8) {
+    uint32_t ab[2][4], as_[2][4], bb[2][2], bs[2][2];
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+      const int m = wm * 32 + mi * 16 + g;
+      tf32_split(As[ks + q][m], ab[mi][0], as_[mi][0]);
+      tf32_split(As[ks + q][m + 8], ab[mi][1], as_[mi][1]);
+      tf32_split(As[ks + q + 4][m], ab[mi][2], as_[mi][2]);
+      tf32_split(As[ks + q + 4][m + 8], ab[mi][3], as_[mi][3]);
+    }
+#pragma unroll
+    for (int ni = 0; ni < 2; ++ni) {
+      const int n = wn * 16 + ni * 8 + g;
+      tf32_split(Bs[ks + q][n], bb[ni][0], bs[ni][0]);
+      tf32_split(Bs[ks + q + 4][n], bb[ni][1], bs[ni][1]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        float(&c)[4] = *reinterpret_cast<float(*)[4]>(&acc.v[mi * 8 + ni * 4]);
+        mma_tf32_16x8x8(c, as_[mi], bb[ni]);   // small terms first
+        mma_tf32_16x8x8(c, ab[mi], bs[ni]);
+        mma_tf32_16x8x8(c, ab[mi], bb[ni]);
+      }
+  }
+}
+
+// A thread's outputs are 4 rows x 2 pairs of horizontally adjacent columns (both inner-product paths):
+// k2_thread_rows_cols gives the tile-local rows / first columns, k2_pair(acc, ri, ci, v0, v1) the values.
+template <bool MMA>
+__device__ __forceinline__ void k2_thread_rows_cols(int t, int (&rows)[4], int (&cols)[2]) {
+  if (MMA) {
+    const int warp = t >> 5, lane = t & 31, g = lane >> 2, q = lane & 3;
+    const int wm = warp & 1, wn = warp >> 1;
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) rows[ri] = wm * 32 + (ri >> 1) * 16 + g + 8 * (ri & 1);
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) cols[ci] = wn * 16 + ci * 8 + 2 * q;
+  } else {
+    const int tx = t % 16, ty = t / 16;
+#pragma unroll
+    for (int ri = 0; ri < 4; ++ri) rows[ri] = ty * 4 + ri;
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) cols[ci] = tx * 4 + 2 * ci;
+  }
+}
+template <bool MMA>
+__device__ __forceinline__ void k2_pair(const K2Acc& acc, int ri, int ci, float& v0, float& v1) {
+  const int i = MMA ? (ri >> 1) * 8 + ci * 4 + 2 * (ri & 1) : ri * 4 + 2 * ci;
+  v0 = acc.v[i];
+  v1 = acc.v[i + 1];
+}
+template <bool MMA, class F>
+__device__ __forceinline__ void k2_for_each_pair(const K2Acc& acc, int t, F&& f) {
+  int rows[4], cols[2];
+  k2_thread_rows_cols<MMA>(t, rows, cols);
+#pragma unroll
+  for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      float v0, v1;
+      k2_pair<MMA>(acc, ri, ci, v0, v1);
+      f(rows[ri], cols[ci], v0, v1);
+    }
 }
 
 // grid: (ceil(M/64), ceil(CC/64)); requires CF % 16 == 0, CC % 4 == 0
 // Software pipelined: the global loads of K chunk i+1 are in flight while chunk i is multiplied out of the other
 // shared-memory buffer (one barrier per chunk).
+template <bool MMA>
 __global__ void __launch_bounds__(256) k2_gather_tiled_kernel(K2Args p, long long M) {
   __shared__ float As[2][kK2_BK][kK2_BM + kK2_PAD];
   __shared__ float Bs[2][kK2_BK][kK2_BN + kK2_PAD];
-  const int t = threadIdx.x, tx = t % 16, ty = t / 16;
+  const int t = threadIdx.x;
   const long long m0 = static_cast<long long>(blockIdx.x) * kK2_BM;
   const int n0 = blockIdx.y * kK2_BN;
-  float acc[4][4] = {};
+  K2Acc acc = {};
   const int arow = t / 4, akq = (t % 4) * 4;   // A loader: one float4 per thread
   const int bk = t / 16, bn4 = (t % 16) * 4;   // B loader
   const long long am = m0 + arow;
+  const long long abase = am < M ? k2_fine_base(p, am) : 0;
   const int chunks_per_tap = p.CF / kK2_BK, n_it = 8 * chunks_per_tap;
   float4 av, bv;
   auto fetch = [&](int it) {
     const int tap = it / chunks_per_tap, cf0 = (it % chunks_per_tap) * kK2_BK;
     av = make_float4(0.f, 0.f, 0.f, 0.f);
     bv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (am < M) av = *reinterpret_cast<const float4*>(p.fine_in + k2_child(p, am, tap) * p.CF + cf0 + akq);
+    if (am < M) av = *reinterpret_cast<const float4*>(p.fine_in + (abase + k2_tap_offset(p, tap)) * p.CF + cf0 + akq);
     if (n0 + bn4 < p.CC) bv = *reinterpret_cast<const float4*>(p.w + (static_cast<long long>(tap) * p.CF + cf0 + bk) * p.CC + n0 + bn4);
   };
   auto stash = [&](int buf) {
@@ -76,39 +232,39 @@ __global__ void __launch_bounds__(256) k2_gather_tiled_kernel(K2Args p, long lon
   __syncthreads();
   for (int it = 0; it < n_it; ++it) {
     if (it + 1 < n_it) fetch(it + 1);
-    k2_tile_fma(As[it & 1], Bs[it & 1], ty, tx, acc);
+    k2_tile_product<MMA>(As[it & 1], Bs[it & 1], t, acc);
     if (it + 1 < n_it) stash((it + 1) & 1);
     __syncthreads();
   }
-  const int n = n0 + tx * 4;
-  if (n >= p.CC) return;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-    float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  k2_for_each_pair<MMA>(acc, t, [&](int row, int col, float v0, float v1) {
+    const long long m = m0 + row;
+    const int n = n0 + col;
+    if (m >= M || n >= p.CC) return;
+    float2 o = make_float2(v0, v1);
     if (p.bias) {
-      const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
-      o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+      o.x += p.bias[n];
+      o.y += p.bias[n + 1];
     }
-    float4* dst = reinterpret_cast<float4*>(p.coarse_out + m * p.CC + n);
+    float2* dst = reinterpret_cast<float2*>(p.coarse_out + m * p.CC + n);
     if (p.accumulate) {
-      const float4 old = *dst;
-      o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      const float2 old = *dst;
+      o.x += old.x;
+      o.y += old.y;
     }
     *dst = o;
-  }
+  });
 }
 
 // grid: (ceil(M/64), ceil(8*CF/64)); requires CC % 16 == 0, CF % 4 == 0
+template <bool MMA>
 __global__ void __launch_bounds__(256) k2_scatter_tiled_kernel(K2Args p, long long M) {
   __shared__ float As[2][kK2_BK][kK2_BM + kK2_PAD];
   __shared__ float Bs[2][kK2_BK][kK2_BN + kK2_PAD];
-  const int t = threadIdx.x, tx = t % 16, ty = t / 16;
+  const int t = threadIdx.x;
   const long long m0 = static_cast<long long>(blockIdx.x) * kK2_BM;
   const int n0 = blockIdx.y * kK2_BN;  // n = tap*CF + cf
   const int NN = 8 * p.CF;
-  float acc[4][4] = {};
+  K2Acc acc = {};
   const int row = t / 4, kq = (t % 4) * 4;
   const int n_it = p.CC / kK2_BK;
   float4 av, bv;
@@ -128,52 +284,71 @@ __global__ void __launch_bounds__(256) k2_scatter_tiled_kernel(K2Args p, long lo
   __syncthreads();
   for (int it = 0; it < n_it; ++it) {
     if (it + 1 < n_it) fetch(it + 1);
-    k2_tile_fma(As[it & 1], Bs[it & 1], ty, tx, acc);
+    k2_tile_product<MMA>(As[it & 1], Bs[it & 1], t, acc);
     if (it + 1 < n_it) stash((it + 1) & 1);
     __syncthreads();
   }
-  const int n = n0 + tx * 4;
-  if (n >= NN) return;
-  const int tap = n / p.CF, cf = n % p.CF;
+  // epilogue: the fine-grid index is split into a per-row base and a per-column tap offset, each computed once
+  int rows[4], cols[2];
+  k2_thread_rows_cols<MMA>(t, rows, cols);
+  long long fbase[4], toff[2];
+  int cfs[2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-    float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    if (p.bias) {
-      const float4 b = *reinterpret_cast<const float4*>(p.bias + cf);
-      o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+  for (int ri = 0; ri < 4; ++ri) fbase[ri] = m0 + rows[ri] < M ? k2_fine_base(p, m0 + rows[ri]) : -1;
+#pragma unroll
+  for (int ci = 0; ci < 2; ++ci) {
+    const int n = n0 + cols[ci];
+    cfs[ci] = -1;
+    toff[ci] = 0;
+    if (n < NN) {   // CF % 4 == 0: a pair never straddles two taps
+      cfs[ci] = n % p.CF;
+      toff[ci] = k2_tap_offset(p, n / p.CF);
     }
-    float4* dst = reinterpret_cast<float4*>(p.fine_out + k2_child(p, m, tap) * p.CF + cf);
-    if (p.accumulate) {
-      const float4 old = *dst;
-      o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-    }
-    *dst = o;
   }
+#pragma unroll
+  for (int ri = 0; ri < 4; ++ri)
+#pragma unroll
+    for (int ci = 0; ci < 2; ++ci) {
+      if (fbase[ri] < 0 || cfs[ci] < 0) continue;
+      float2 o;
+      k2_pair<MMA>(acc, ri, ci, o.x, o.y);
+      if (p.bias) {
+        o.x += p.bias[cfs[ci]];
+        o.y += p.bias[cfs[ci] + 1];
+      }
+      float2* dst = reinterpret_cast<float2*>(p.fine_out + (fbase[ri] + toff[ci]) * p.CF + cfs[ci]);
+      if (p.accumulate) {
+        const float2 old = *dst;
+        o.x += old.x;
+        o.y += old.y;
+      }
+      *dst = o;
+    }
 }
 
 // grid: (ceil(8*CF/64), ceil(CC/64), splits); fp32 atomics into pre-zeroed dw; CF % 4 == 0, CC % 4 == 0
+template <bool MMA>
 __global__ void __launch_bounds__(256) k2_wgrad_tiled_kernel(K2Args p, long long M, long long m_per_split) {
   __shared__ float As[2][kK2_BK][kK2_BM + kK2_PAD];   // [k = voxel][r = (tap,cf) row]
   __shared__ float Bs[2][kK2_BK][kK2_BN + kK2_PAD];   // [k = voxel][n = cc]
-  const int t = threadIdx.x, tx = t % 16, ty = t / 16;
+  const int t = threadIdx.x;
   const int r0 = blockIdx.x * kK2_BM, n0 = blockIdx.y * kK2_BN;
   const int RR = 8 * p.CF;
   const long long mb = static_cast<long long>(blockIdx.z) * m_per_split;
   const long long me = mb + m_per_split < M ? mb + m_per_split : M;
-  float acc[4][4] = {};
+  K2Acc acc = {};
   const int lk = t / 16, l4 = (t % 16) * 4;
   const int r = r0 + l4;
   const int tap = r < RR ? r / p.CF : 0, cf = r < RR ? r % p.CF : 0;
   const int n_it = static_cast<int>((me - mb + kK2_BK - 1) / kK2_BK);
+  const long long tap_off = k2_tap_offset(p, tap);
   float4 av, bv;
   auto fetch = [&](int it) {
     const long long m = mb + static_cast<long long>(it) * kK2_BK + lk;
     av = make_float4(0.f, 0.f, 0.f, 0.f);
     bv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (m < me) {
-      if (r < RR) av = *reinterpret_cast<const float4*>(p.fine_in + k2_child(p, m, tap) * p.CF + cf);
+      if (r < RR) av = *reinterpret_cast<const float4*>(p.fine_in + (k2_fine_base(p, m) + tap_off) * p.CF + cf);
       if (n0 + l4 < p.CC) bv = *reinterpret_cast<const float4*>(p.coarse_in + m * p.CC + n0 + l4);
     }
   };
@@ -188,20 +363,16 @@ __global__ void __launch_bounds__(256) k2_wgrad_tiled_kernel(K2Args p, long long
   __syncthreads();
   for (int it = 0; it < n_it; ++it) {
     if (it + 1 < n_it) fetch(it + 1);
-    k2_tile_fma(As[it & 1], Bs[it & 1], ty, tx, acc);
+    k2_tile_product<MMA>(As[it & 1], Bs[it & 1], t, acc);
     if (it + 1 < n_it) stash((it + 1) & 1);
     __syncthreads();
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = r0 + ty * 4 + i;
-    if (rr >= RR) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < p.CC) atomicAdd(p.dw + static_cast<long long>(rr) * p.CC + n, acc[i][j]);
-    }
-  }
+  k2_for_each_pair<MMA>(acc, t, [&](int row, int col, float v0, float v1) {
+    const int rr = r0 + row, n = n0 + col;
+    if (rr >= RR || n >= p.CC) return;   // CC % 4 == 0: n + 1 < CC as well
+    atomicAdd(p.dw + static_cast<long long>(rr) * p.CC + n, v0);
+    atomicAdd(p.dw + static_cast<long long>(rr) * p.CC + n + 1, v1);
+  });
 }
 
 }  // namespace vnb
