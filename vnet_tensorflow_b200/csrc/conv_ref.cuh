@@ -386,6 +386,124 @@ __global__ void __launch_bounds__(256) conv1_wgrad_kernel(const float* __restric
   }
 }
 
+// Voxel-per-thread forms of the three head kernels for Cin % 4 == 0, Cin <= 32, K <= 4 (every V-Net head): one thread
+// streams a voxel's Cin inputs as float4 (warps read contiguous memory), the [Cin][K] filter sits in shared memory.
+// Same arithmetic order over c as the scalar kernels above.
+constexpr int kC1MaxCin = 32, kC1MaxK = 4;
+__global__ void __launch_bounds__(256) conv1_fprop_vox_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ z, long long V,
+                                                              int Cin, int K) {
+  __shared__ float ws[kC1MaxCin * kC1MaxK];
+  for (int i = threadIdx.x; i < Cin * K; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int C4 = Cin / 4;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc[kC1MaxK];
+#pragma unroll
+    for (int k = 0; k < kC1MaxK; ++k) acc[k] = (bias && k < K) ? bias[k] : 0.f;
+    const float4* xv = reinterpret_cast<const float4*>(x + v * Cin);
+    for (int c4 = 0; c4 < C4; ++c4) {
+      const float4 f = xv[c4];
+      const float xs[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < kC1MaxK; ++k)
+          if (k < K) acc[k] += xs[j] * ws[(c4 * 4 + j) * K + k];
+    }
+    if (K == 2) {
+      *reinterpret_cast<float2*>(z + v * 2) = make_float2(acc[0], acc[1]);
+    } else if (K == 4) {
+      *reinterpret_cast<float4*>(z + v * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kC1MaxK; ++k)
+        if (k < K) z[v * K + k] = acc[k];
+    }
+  }
+}
+__global__ void __launch_bounds__(256) conv1_dgrad_vox_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                                              float* __restrict__ dx, long long V, int Cin, int K, int accumulate) {
+  __shared__ float ws[kC1MaxCin * kC1MaxK];
+  for (int i = threadIdx.x; i < Cin * K; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int C4 = Cin / 4;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float g[kC1MaxK];
+#pragma unroll
+    for (int k = 0; k < kC1MaxK; ++k) g[k] = k < K ? dz[v * K + k] : 0.f;
+    float4* out = reinterpret_cast<float4*>(dx + v * Cin);
+    for (int c4 = 0; c4 < C4; ++c4) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int k = 0; k < kC1MaxK; ++k)
+          if (k < K) sacc += g[k] * ws[(c4 * 4 + j) * K + k];
+        o[j] = sacc;
+      }
+      float4 r = make_float4(o[0], o[1], o[2], o[3]);
+      if (accumulate) {
+        const float4 old = out[c4];
+        r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+      }
+      out[c4] = r;
+    }
+  }
+}
+// dw[c][k] += sum_v x[v][c] dz[v][k] for Cin <= 16: 16 x 4 register accumulators per thread over a strided voxel set
+// (all indices static after unrolling), a warp butterfly, a shared-memory sum over the 8 warps and one atomic per
+// (c, k) and block
+constexpr int kC1WgMaxCin = 16;
+__global__ void __launch_bounds__(256) conv1_wgrad_vox_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                              float* __restrict__ dw, long long V, int Cin, int K) {
+  __shared__ float red[8][kC1WgMaxCin * kC1MaxK];
+  float acc[kC1WgMaxCin][kC1MaxK];
+#pragma unroll
+  for (int c = 0; c < kC1WgMaxCin; ++c)
+#pragma unroll
+    for (int k = 0; k < kC1MaxK; ++k) acc[c][k] = 0.f;
+  const int C4 = Cin / 4;
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float g[kC1MaxK];
+#pragma unroll
+    for (int k = 0; k < kC1MaxK; ++k) g[k] = k < K ? dz[v * K + k] : 0.f;
+    const float4* xv = reinterpret_cast<const float4*>(x + v * Cin);
+#pragma unroll
+    for (int c4 = 0; c4 < kC1WgMaxCin / 4; ++c4) {
+      if (c4 < C4) {
+        const float4 f = xv[c4];
+        const float xs[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < kC1MaxK; ++k) acc[c4 * 4 + j][k] += xs[j] * g[k];   // g[k] = 0 for k >= K
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < kC1WgMaxCin; ++c)
+#pragma unroll
+    for (int k = 0; k < kC1MaxK; ++k) {
+      float sacc = acc[c][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (lane == 0) red[warp][c * kC1MaxK + k] = sacc;
+    }
+  __syncthreads();
+  if (threadIdx.x < Cin * K) {
+    const int c = threadIdx.x / K, k = threadIdx.x % K;
+    float tot = 0.f;
+    for (int wq = 0; wq < 8; ++wq) tot += red[wq][c * kC1MaxK + k];
+    atomicAdd(dw + threadIdx.x, tot);
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // General 1x1x1 convolution (shortcut branch and output layer of the attention / output modules,
 // attention.py:98-100,111): a [V][Cin] x [Cin][Cout] matrix product, fp32 FMA.

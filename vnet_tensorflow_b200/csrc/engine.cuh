@@ -854,13 +854,21 @@ class Engine {
       launch_conv1g(p);
     } else if (u.kind == U_CONV1) {
       const long long V = voxels_of(o.dims, N);
-      VNB_LAUNCH(conv1_fprop_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, (const float*)x1.a,
-                 (const float*)(params_ + u.w_off), bias, u.z, V, u.Cin1, u.Cout);
+      if (conv1_vox_ok(u))
+        VNB_LAUNCH(conv1_fprop_vox_kernel, grid_for(V, 256), 256, 0, stream_, (const float*)x1.a,
+                   (const float*)(params_ + u.w_off), bias, u.z, V, u.Cin1, u.Cout);
+      else
+        VNB_LAUNCH(conv1_fprop_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, (const float*)x1.a,
+                   (const float*)(params_ + u.w_off), bias, u.z, V, u.Cin1, u.Cout);
       ++launches_;
     }
   }
   // the small-shape 1^3 kernels serve the V-Net head; anything with a residual or a wide product goes general
   static bool conv1_general(const Unit& u) { return u.res >= 0 || u.Cin1 * u.Cout > 256; }
+  // voxel-per-thread head kernels (float4 input rows): every V-Net head (16 -> K)
+  static bool conv1_vox_ok(const Unit& u) {
+    return u.Cin1 % 4 == 0 && u.Cin1 <= kC1WgMaxCin && u.Cout >= 2 && u.Cout <= kC1MaxK;
+  }
   void launch_conv1g(const Conv1Args& p) {
     dim3 grid(static_cast<unsigned>((p.V + 63) / 64), (p.M + 63) / 64);
     VNB_LAUNCH(conv1g_kernel, grid, 256, 0, stream_, p);
@@ -1245,15 +1253,25 @@ class Engine {
       ++launches_;
     } else if (u.kind == U_CONV1) {
       const long long V = voxels_of(o.dims, N);
+      const bool vox = conv1_vox_ok(u);
       if (u.need_dgrad) {
-        VNB_LAUNCH(conv1_dgrad_kernel, grid_for(V * u.Cin1, 256), 256, 0, stream_, dz, (const float*)(params_ + u.w_off),
-                   x1.d, V, u.Cin1, u.Cout, u.in1_accumulate ? 1 : 0);
+        if (vox)
+          VNB_LAUNCH(conv1_dgrad_vox_kernel, grid_for(V, 256), 256, 0, stream_, dz, (const float*)(params_ + u.w_off), x1.d, V,
+                     u.Cin1, u.Cout, u.in1_accumulate ? 1 : 0);
+        else
+          VNB_LAUNCH(conv1_dgrad_kernel, grid_for(V * u.Cin1, 256), 256, 0, stream_, dz, (const float*)(params_ + u.w_off),
+                     x1.d, V, u.Cin1, u.Cout, u.in1_accumulate ? 1 : 0);
         ++launches_;
       }
       if (u.Cin1 * u.Cout > 256) throw std::runtime_error("output layer wider than 256 (Cin*K) is not supported");
-      const int vpb = 4096;
-      const int blocks = static_cast<int>((V + vpb - 1) / vpb);
-      VNB_LAUNCH(conv1_wgrad_kernel, blocks, 256, 0, stream_, (const float*)x1.a, dz, dw, V, u.Cin1, u.Cout, vpb);
+      if (vox) {
+        const int blocks = static_cast<int>(std::min<long long>((V + 255) / 256, 4 * 148));
+        VNB_LAUNCH(conv1_wgrad_vox_kernel, blocks, 256, 0, stream_, (const float*)x1.a, dz, dw, V, u.Cin1, u.Cout);
+      } else {
+        const int vpb = 4096;
+        const int blocks = static_cast<int>((V + vpb - 1) / vpb);
+        VNB_LAUNCH(conv1_wgrad_kernel, blocks, 256, 0, stream_, (const float*)x1.a, dz, dw, V, u.Cin1, u.Cout, vpb);
+      }
       ++launches_;
     }
   }
@@ -1263,7 +1281,7 @@ class Engine {
     if (M > 0xFFFFFFFFLL) throw std::invalid_argument("2x2x2 convolution: more than 2^32 coarse voxels per batch");
     if (k2_tiled_ok(p)) {
       dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (p.CC + kK2_BN - 1) / kK2_BN);
-      if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_gather_tiled_kernel<true>, grid, 256, 0, stream_, p, M);
+      if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_gather_mma_kernel, grid, 256, 0, stream_, p, M);
       else VNB_LAUNCH(k2_gather_tiled_kernel<false>, grid, 256, 0, stream_, p, M);
     } else {
       VNB_LAUNCH(k2_gather_kernel, grid_for(M * p.CC, 256), 256, 0, stream_, p);
@@ -1275,7 +1293,7 @@ class Engine {
     if (M > 0xFFFFFFFFLL) throw std::invalid_argument("2x2x2 convolution: more than 2^32 coarse voxels per batch");
     if (k2_tiled_ok(p)) {
       dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (8 * p.CF + kK2_BN - 1) / kK2_BN);
-      if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_scatter_tiled_kernel<true>, grid, 256, 0, stream_, p, M);
+      if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_scatter_mma_kernel, grid, 256, 0, stream_, p, M);
       else VNB_LAUNCH(k2_scatter_tiled_kernel<false>, grid, 256, 0, stream_, p, M);
     } else {
       VNB_LAUNCH(k2_scatter_kernel, grid_for(M * 8 * p.CF, 256), 256, 0, stream_, p);
@@ -1291,7 +1309,7 @@ class Engine {
       long long mps = ((M + splits - 1) / splits + kK2_BK - 1) / kK2_BK * kK2_BK;
       splits = (M + mps - 1) / mps;
       dim3 grid(gx, gy, static_cast<unsigned>(splits));
-      if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_wgrad_tiled_kernel<true>, grid, 256, 0, stream_, p, M, mps);
+      if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_wgrad_mma_kernel, grid, 256, 0, stream_, p, M, mps);
       else VNB_LAUNCH(k2_wgrad_tiled_kernel<false>, grid, 256, 0, stream_, p, M, mps);
     } else {
       const long long outs = 8LL * p.CF * p.CC;

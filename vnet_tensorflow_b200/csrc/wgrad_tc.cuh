@@ -235,22 +235,41 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
-// dw[tap][ci][co] = sum_split partial[split][pair(ci/16, co/16)][tap][ci%16][co%16]   (fixed order)
-__global__ void wgrad5_reduce_kernel(const float* __restrict__ partial, int splits, int n_ci, int n_co, int Cin, int Cout,
-                                     float* __restrict__ dw, int taps = 125) {
+// dw[tap][ci][co] = sum_split partial[split][pair(ci/16, co/16)][tap][ci%16][co%16]   (fixed order: deterministic)
+// A block reduces 256 / nsub consecutive outputs per trip: thread group s (of nsub = 1, 2, 4 or 8) sums splits
+// s, s+nsub, ... with coalesced reads of one split each, then the group sums are added in group order.  The
+// summation tree depends only on (splits, nsub), both fixed by the layer geometry.
+__global__ void __launch_bounds__(256) wgrad5_reduce_kernel(const float* __restrict__ partial, int splits, int n_ci, int n_co,
+                                                            int Cin, int Cout, float* __restrict__ dw, int taps, int nsub) {
   // Cin = real input channels of dw; the GEMM may have run on a zero-padded multiple of 16 (n_ci chunks)
-  const long long total = static_cast<long long>(taps) * Cin * Cout;
+  __shared__ float red[256];
+  const unsigned total = static_cast<unsigned>(taps) * Cin * Cout;   // < 2^31 (largest filter: 8.2 M elements)
   const int pairs = n_ci * n_co;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int co = static_cast<int>(i % Cout);
-    const int ci = static_cast<int>((i / Cout) % Cin);
-    const int tap = static_cast<int>(i / (static_cast<long long>(Cout) * Cin));
-    const int pair = (ci / 16) * n_co + co / 16;
-    const size_t off = (static_cast<size_t>(pair) * taps + tap) * 256 + (ci % 16) * 16 + co % 16;
+  const unsigned per = 256u / nsub;
+  const unsigned lane = threadIdx.x % per, sub = threadIdx.x / per;
+  const size_t split_stride = static_cast<size_t>(pairs) * (static_cast<size_t>(taps) * 256);
+  for (unsigned base = blockIdx.x * per; base < total; base += gridDim.x * per) {
+    const unsigned i = base + lane;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += partial[static_cast<size_t>(sp) * pairs * (static_cast<size_t>(taps) * 256) + off];
-    dw[i] = s;
+    if (i < total) {
+      const unsigned co = i % Cout, r = i / Cout;
+      const unsigned ci = r % Cin, tap = r / Cin;
+      const unsigned pair = (ci / 16) * n_co + co / 16;
+      const size_t off = (static_cast<size_t>(pair) * taps + tap) * 256 + (ci % 16) * 16 + co % 16;
+      for (int sp = sub; sp < splits; sp += nsub) s += partial[static_cast<size_t>(sp) * split_stride + off];
+    }
+    if (nsub == 1) {
+      if (i < total) dw[i] = s;
+      continue;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (sub == 0 && i < total) {
+      float t = 0.f;
+      for (int w = 0; w < nsub; ++w) t += red[w * per + lane];
+      dw[i] = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -359,8 +378,10 @@ inline void wg_launch(const WgPlan& pl, int N, bool split3, float* partial, floa
   const int cin = cin_real > 0 ? cin_real : g.C1 + g.C2;
   const int taps = pl.KS * pl.KS * pl.KS;
   const long long total = static_cast<long long>(taps) * cin * g.Cout;
-  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 2368));
-  VNB_LAUNCH(wgrad5_reduce_kernel, blocks, 256, 0, stream, (const float*)partial, g.splits, g.n_ci, g.n_co, cin, g.Cout, dw, taps);
+  const int nsub = g.splits >= 32 ? 8 : g.splits >= 8 ? 4 : g.splits >= 4 ? 2 : 1;
+  const int per = 256 / nsub;
+  const int blocks = static_cast<int>(std::min<long long>((total + per - 1) / per, 148 * 16));
+  VNB_LAUNCH(wgrad5_reduce_kernel, blocks, 256, 0, stream, (const float*)partial, g.splits, g.n_ci, g.n_co, cin, g.Cout, dw, taps, nsub);
 }
 
 }  // namespace vnb
