@@ -37,7 +37,48 @@ int main(int argc, char** argv) {
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   const double flops = 2.0 * ks * ks * ks * (Cin + cin2) * (double)Cout * (double)V;
   float ms = 0;
-  if (op == "wgrad") {
+  if (op == "k2g" || op == "k2s" || op == "k2w") {
+    // 2x2x2 stride-2 kernels: (D, H, W) are the COARSE dims, Cin = fine channels CF, Cout = coarse channels CC
+    const size_t Vc = V, Vf = V * 8;
+    float* fine = s.alloc<float>(Vf * Cin);
+    float* coarse = s.alloc<float>(Vc * Cout);
+    float* wt = s.alloc<float>((size_t)8 * Cin * Cout);
+    float* dwt = s.alloc<float>((size_t)8 * Cin * Cout);
+    CK(cudaMemset(fine, 0, Vf * Cin * 4)); CK(cudaMemset(coarse, 0, Vc * Cout * 4)); CK(cudaMemset(wt, 0, (size_t)8 * Cin * Cout * 4));
+    CK(cudaMemset(dwt, 0, (size_t)8 * Cin * Cout * 4));
+    K2Args p{};
+    p.fine_in = fine; p.coarse_in = coarse; p.fine_out = fine; p.coarse_out = coarse; p.w = wt; p.dw = dwt; p.bias = nullptr;
+    p.CF = Cin; p.CC = Cout; p.cd = Dims{D, H, W}; p.N = N; p.accumulate = 0;
+    const long long M = (long long)Vc;
+    auto launch = [&]() {
+      if (op == "k2g") {
+        dim3 grid((unsigned)((M + kK2_BM - 1) / kK2_BM), (p.CC + kK2_BN - 1) / kK2_BN);
+        k2_gather_mma_kernel<<<grid, 256>>>(p, M);
+      } else if (op == "k2s") {
+        dim3 grid((unsigned)((M + kK2_BM - 1) / kK2_BM), (8 * p.CF + kK2_BN - 1) / kK2_BN);
+        k2_scatter_mma_kernel<<<grid, 256>>>(p, M);
+      } else {
+        const int gx = (8 * p.CF + kK2_BM - 1) / kK2_BM, gy = (p.CC + kK2_BN - 1) / kK2_BN;
+        long long splits = std::max<long long>(1, std::min<long long>((M + 255) / 256, (4 * 148 + gx * gy - 1) / (gx * gy)));
+        long long mps = ((M + splits - 1) / splits + kK2_BK - 1) / kK2_BK * kK2_BK;
+        splits = (M + mps - 1) / mps;
+        dim3 grid(gx, gy, (unsigned)splits);
+        k2_wgrad_mma_kernel<<<grid, 256>>>(p, M, mps);
+      }
+    };
+    for (int i = 0; i < 3; ++i) launch();
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) launch();
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double us2 = ms * 1e3 / reps;
+    const double bytes = (double)Vf * Cin * 4 + (double)Vc * Cout * 4;
+    printf("KBENCH %s N=%d coarse %dx%dx%d CF=%d CC=%d : %.1f us/launch  %.0f GB/s (fine + coarse tensor once)\n", op.c_str(), N, D, H, W, Cin, Cout,
+           us2, bytes / (us2 * 1e-6) / 1e9);
+    return 0;
+  } else if (op == "wgrad") {
     WgPlan pl;
     if (!wg_plan_geometry(pl, N, D, H, W, Cin, cin2, Cout, lo, sms, ks)) { printf("unsupported shape\n"); return 1; }
     uint16_t *xh = mk(V * Cin, 1), *xl = lo ? mk(V * Cin, 2) : nullptr, *zh = mk(V * Cout, 3), *zl = lo ? mk(V * Cout, 4) : nullptr;

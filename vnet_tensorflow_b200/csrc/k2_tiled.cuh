@@ -430,10 +430,12 @@ __device__ __forceinline__ float k2_tile_at(const float* T, int r, int k) {
   return KMAJOR ? T[k * kK2_PK + r] : T[r * kK2_PR + k];
 }
 
+// m_valid / n_valid: rows / columns of the 64 x 64 tile that exist; warps whose 32 x 16 sub-tile lies outside skip
 template <bool A_KMAJOR, bool B_KMAJOR>
-__device__ __forceinline__ void k2_tile_product_mma(const float* As, const float* Bs, int t, K2Acc& acc) {
+__device__ __forceinline__ void k2_tile_product_mma(const float* As, const float* Bs, int t, K2Acc& acc, int m_valid, int n_valid) {
   const int warp = t >> 5, lane = t & 31, g = lane >> 2, q = lane & 3;
   const int wm = warp & 1, wn = warp >> 1;
+  if (wm * 32 >= m_valid || wn * 16 >= n_valid) return;
 #pragma unroll
   for (int ks = 0; ks < kK2_BK; ks += 8) {
     uint32_t ab[2][4], as_[2][4], bb[2][2], bs[2][2];
@@ -465,7 +467,7 @@ __device__ __forceinline__ void k2_tile_product_mma(const float* As, const float
 
 // generic pipeline driver: issue(it, As_stage, Bs_stage) enqueues the copies of K chunk `it`
 template <bool A_KMAJOR, bool B_KMAJOR, class Issue>
-__device__ __forceinline__ void k2_mma_mainloop(float* smem, int n_it, int t, K2Acc& acc, Issue&& issue) {
+__device__ __forceinline__ void k2_mma_mainloop(float* smem, int n_it, int t, K2Acc& acc, int m_valid, int n_valid, Issue&& issue) {
   auto As = [&](int s) { return smem + s * 2 * kK2_TILE_FLOATS; };
   auto Bs = [&](int s) { return smem + s * 2 * kK2_TILE_FLOATS + kK2_TILE_FLOATS; };
 #pragma unroll
@@ -479,7 +481,7 @@ __device__ __forceinline__ void k2_mma_mainloop(float* smem, int n_it, int t, K2
     const int nx = it + kK2_STAGES - 1;
     if (nx < n_it) issue(nx, As(nx % kK2_STAGES), Bs(nx % kK2_STAGES));   // refills the buffer of chunk it-1
     cp_async_commit();
-    k2_tile_product_mma<A_KMAJOR, B_KMAJOR>(As(it % kK2_STAGES), Bs(it % kK2_STAGES), t, acc);
+    k2_tile_product_mma<A_KMAJOR, B_KMAJOR>(As(it % kK2_STAGES), Bs(it % kK2_STAGES), t, acc, m_valid, n_valid);
   }
   cp_async_wait<0>();
 }
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(256) k2_gather_mma_kernel(K2Args p, long long 
   const bool a_ok = am < M, b_ok = n0 + bn4 < p.CC;
   const long long abase = a_ok ? k2_fine_base(p, am) : 0;
   const int chunks_per_tap = p.CF / kK2_BK;
-  k2_mma_mainloop<false, true>(smem, 8 * chunks_per_tap, t, acc, [&](int it, float* As, float* Bs) {
+  k2_mma_mainloop<false, true>(smem, 8 * chunks_per_tap, t, acc, 64, p.CC - n0, [&](int it, float* As, float* Bs) {
     const int tap = it / chunks_per_tap, cf0 = (it % chunks_per_tap) * kK2_BK;
     cp_async16(As + arow * kK2_PR + akq, p.fine_in + (a_ok ? (abase + k2_tap_offset(p, tap)) * p.CF + cf0 + akq : 0), a_ok);
     cp_async16(Bs + bk * kK2_PK + bn4, p.w + (b_ok ? (static_cast<long long>(tap) * p.CF + cf0 + bk) * p.CC + n0 + bn4 : 0), b_ok);
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(256) k2_scatter_mma_kernel(K2Args p, long long
   K2Acc acc = {};
   const int row = t / 4, kq = (t % 4) * 4;     // A [m][k] and B [n][k]: both row-major
   const bool a_ok = m0 + row < M, b_ok = n0 + row < NN;
-  k2_mma_mainloop<false, false>(smem, p.CC / kK2_BK, t, acc, [&](int it, float* As, float* Bs) {
+  k2_mma_mainloop<false, false>(smem, p.CC / kK2_BK, t, acc, 64, NN - n0, [&](int it, float* As, float* Bs) {
     const int cc0 = it * kK2_BK;
     cp_async16(As + row * kK2_PR + kq, p.coarse_in + (a_ok ? (m0 + row) * p.CC + cc0 + kq : 0), a_ok);
     cp_async16(Bs + row * kK2_PR + kq, p.w + (b_ok ? static_cast<long long>(n0 + row) * p.CC + cc0 + kq : 0), b_ok);
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(256) k2_wgrad_mma_kernel(K2Args p, long long M
   const int tap = r < RR ? r / p.CF : 0, cf = r < RR ? r % p.CF : 0;
   const long long tap_off = k2_tap_offset(p, tap);
   const int n_it = static_cast<int>((me - mb + kK2_BK - 1) / kK2_BK);
-  k2_mma_mainloop<true, true>(smem, n_it, t, acc, [&](int it, float* As, float* Bs) {
+  k2_mma_mainloop<true, true>(smem, n_it, t, acc, RR - r0, p.CC - n0, [&](int it, float* As, float* Bs) {
     const long long m = mb + static_cast<long long>(it) * kK2_BK + lk;
     const bool a_ok = m < me && r < RR, b_ok = m < me && n0 + l4 < p.CC;
     cp_async16(As + lk * kK2_PK + l4, p.fine_in + (a_ok ? (k2_fine_base(p, m) + tap_off) * p.CF + cf : 0), a_ok);
