@@ -1,11 +1,15 @@
 mkdir -p gpurun_out
+export VNB_KB_DBG=1
 (
-build/kbench k2g 2 64 64 64 16 32 2 10
-build/kbench k2s 2 64 64 64 16 32 2 10
-build/kbench k2w 2 64 64 64 16 32 2 10
-build/kbench k2g 2 32 32 32 32 64 2 10
-build/kbench k2s 2 32 32 32 32 64 2 10
-build/kbench k2w 2 32 32 32 32 64 2 10
-build/kbench k2g 2 8 8 8 128 256 2 10
+build/kbench fprop 1 16 16 16 16 16 2 2 || exit 1
+python -m pytest tests/test_gpu_parity.py -x -q -k "conv5_ops or conv3_ops" 2>&1 | tail -3
+build/kbench fprop 2 128 128 128 16 16 2 5
+build/kbench fprop 2 128 128 128 16 16 1 5
+build/kbench fprop 2 128 128 128 16 16 2 5 5 16
+build/kbench fprop 2 64 64 64 32 32 2 5
+build/kbench fprop 2 64 64 64 32 32 1 5
+build/kbench fprop 2 32 32 32 64 64 2 5
+build/kbench fprop 2 16 16 16 128 128 2 5
+build/kbench fprop 2 8 8 8 256 256 2 5
 ) > gpurun_out/kb1.log 2>&1
-cat gpurun_out/kb1.log
+grep -v "timed out" gpurun_out/kb1.log | head -60

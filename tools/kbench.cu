@@ -2,6 +2,7 @@
 //   kbench wgrad|fprop N D H W Cin Cout precision(1=bf16,2=bf16x3) reps [ks]
 // Times `reps` back-to-back launches with CUDA events on random bf16 operands and prints us / launch and the
 // algorithmic TFLOP/s (2*ks^3*Cin*Cout*voxels).  VNB_KB_DBG=1 prints the MMA-warp cycle counters of CTA 0.
+#define VNB_KB_COUNTERS 1   // MMA-warp cycle counters (compiled out of the product library)
 #include <cstdio>
 #include <cstdlib>
 #include <vector>

@@ -139,9 +139,10 @@ struct RateOps {
 };
 template <int NOPS>
 __global__ void __launch_bounds__(128, 1)
-    mma_rate_probe(uint32_t img_bytes, const RateOps ops, int reps, long long* __restrict__ cycles) {
+    mma_rate_probe(uint32_t img_bytes, const RateOps ops, int reps, long long* __restrict__ cycles, int commit_every = 0) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t mbar;
+  __shared__ uint64_t mbar2;   // target of the intermediate commits (never waited on)
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t raw = smem_u32(smem_raw);
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(128, 1)
   }
   if (tid == 32) {
     mbar_init(smem_u32(&mbar), 1);
+    mbar_init(smem_u32(&mbar2), 1);
     fence_mbar_init();
   }
   tc_fence_before_sync();
@@ -172,9 +174,28 @@ __global__ void __launch_bounds__(128, 1)
       dc[i] = tmem + ops.dcol[i];
     }
     const long long t0 = clock64();
-    for (int r = 0; r < reps; ++r) {
+    if (commit_every <= 0) {
+      for (int r = 0; r < reps; ++r) {
 #pragma unroll
-      for (int i = 0; i < NOPS; ++i) mma_f16_ss(dc[i], ad[i], bd[i], id[i], 1u);
+        for (int i = 0; i < NOPS; ++i) mma_f16_ss(dc[i], ad[i], bd[i], id[i], 1u);
+      }
+    } else if (commit_every < 100) {   // a commit after every `commit_every` passes over the script (no division in the loop)
+      const uint32_t bar2 = smem_u32(&mbar2);
+      for (int r = 0; r < reps; r += commit_every) {
+        for (int c = 0; c < commit_every; ++c) {
+#pragma unroll
+          for (int i = 0; i < NOPS; ++i) mma_f16_ss(dc[i], ad[i], bd[i], id[i], 1u);
+        }
+        mma_commit(bar2);
+      }
+    } else {   // commit_every - 100 dependent integer operations between consecutive passes (issue-gap sensitivity)
+      uint32_t x = static_cast<uint32_t>(clock64());
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) mma_f16_ss(dc[i], ad[i], bd[i], id[i], 1u);
+        for (int k = 0; k < commit_every - 100; ++k) x = x * 1664525u + 1013904223u;
+      }
+      if (x == 0x12345u) cycles[blockIdx.x + 1] = 1;   // keep the chain alive
     }
     mma_commit(smem_u32(&mbar));
     mbar_wait_bounded(smem_u32(&mbar), 0, 1u << 28);
@@ -547,6 +568,7 @@ static int test_tma(const char* name, int D, int H, int W, int C, int bc, int bw
 
 // ---------------------------------------------------------------------------------------------
 // MMA issue-rate table: cycles per tcgen05.mma (M = 128, K = 16, bf16) for the operand layouts the kernels use
+static int g_commit_every = 0;
 static int run_rate(const char* name, const std::vector<MmaOp>& ops, uint32_t img_bytes, int ctas) {
   long long* dcyc;
   const int reps = 4000;
@@ -557,11 +579,11 @@ static int run_rate(const char* name, const std::vector<MmaOp>& ops, uint32_t im
     ro.idesc[i] = ops[i].idesc;
     ro.dcol[i] = ops[i].dcol;
   }
-  CK(cudaMalloc(&dcyc, ctas * sizeof(long long)));
+  CK(cudaMalloc(&dcyc, (ctas + 1) * sizeof(long long)));
   size_t smem = img_bytes + 2048;
   auto launch = [&](auto kfn) {
     CK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kfn<<<ctas, 128, smem>>>(img_bytes, ro, reps, dcyc);
+    kfn<<<ctas, 128, smem>>>(img_bytes, ro, reps, dcyc, g_commit_every);
   };
   switch (ops.size()) {
     case 1: launch(mma_rate_probe<1>); break;
@@ -615,6 +637,16 @@ static int test_rates() {
       char nm[64];
       snprintf(nm, sizeof nm, "mnmajor_sw128_N%d", N);
       run_rate(nm, {{make_smem_desc(0, 1024, 2048, SWZ_128B), make_smem_desc(offB, 1024, static_cast<uint32_t>(N / 64) * 1024, SWZ_128B), make_instr_desc(128, N, FMT_BF16, 1, 1), 0, 1, 0}}, img, ctas);
+    }
+    // cost of tcgen05.commit in the issue stream: one commit after every pass over the 2-MMA script / every 3 passes
+    for (int ce : {1, 3, 6, 110, 120, 140}) {
+      g_commit_every = ce;
+      char nm[64];
+      if (ce < 100) snprintf(nm, sizeof nm, "kmajor_sw64_N160_commit_per_%dmma", 2 * ce);
+      else snprintf(nm, sizeof nm, "kmajor_sw64_N160_gap_%dalu_per_2mma", ce - 100);
+      run_rate(nm, {{make_smem_desc(0, 16, 512, SWZ_64B), make_smem_desc(offB, 16, 512, SWZ_64B), make_instr_desc(128, 160, FMT_BF16), 0, 1, 0},
+                    {make_smem_desc(32, 16, 512, SWZ_64B), make_smem_desc(offB + 32, 16, 512, SWZ_64B), make_instr_desc(128, 160, FMT_BF16), 0, 1, 0}}, img, ctas);
+      g_commit_every = 0;
     }
     // mixed: A K-major sw32 with B N = 80 accumulating into 3 different accumulators (independent chains)
     run_rate("kmajor_sw32_N80_3acc", {{make_smem_desc(0, 16, 256, SWZ_32B), make_smem_desc(offB, 16, 256, SWZ_32B), make_instr_desc(128, 80, FMT_BF16), 0, 1, 0},

@@ -30,7 +30,7 @@ namespace vnb {
 using sm100::TmaDesc;
 
 // development counters of the MMA-issuing thread (WgGeom::dbg, TcArgs::dbg); compiled out of the emulation build
-#ifndef VNB_EMULATE
+#if !defined(VNB_EMULATE) && defined(VNB_KB_COUNTERS)
 __device__ __forceinline__ unsigned long long vnb_globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -297,6 +297,8 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
     {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
+      uint32_t afull_cur = afull(0), bfull_cur = bfull(0), a_addr_cur = a_ring, b_addr_cur = b_ring;
+      const uint32_t a_stage_all = static_cast<uint32_t>(Cfg::NPL * g.a_stage_bytes);
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
         const int slice = item % g.n_slices;
         int x = item / g.n_slices;
@@ -308,31 +310,45 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
         const int n = x / g.n_db;
         const int h0 = hb * g.bh, d0 = db;
         const int w0 = g.halo ? wb * g.Wt - RC : 0;
+        // running ring state (barrier address, destination, weight row) instead of indices: the producer's scalar
+        // work per stage adds to the refill latency of a B slot
+        const int brow_item = slice * n_it * Cfg::NB, brow_kh = g.n_kc * Cfg::NB;
         for (int kd = 0; kd < KS; ++kd)
           for (int kc = 0; kc < g.n_kc; ++kc) {
-            mbar_wait_warp(aempty(as), aph ^ 1u);
+            mbar_wait_warp(afull_cur + 32u, aph ^ 1u);   // aempty
             const bool src1 = kc < kc1;
             const int cch = (src1 ? kc : kc - kc1) * KC;
-            const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
-            mbar_expect_tx_if(leader, afull(as), Cfg::NPL * a_rows * Cfg::ROWB);
-            tma_load_5d_if(leader, a_addr, src1 ? &a1_hi : &a2_hi, afull(as), cch, w0, h0 - RC, d0 + kd - RC, n);
-            if (NSPLIT == 3)
-              tma_load_5d_if(leader, a_addr + g.a_stage_bytes, src1 ? &a1_lo : &a2_lo, afull(as), cch, w0, h0 - RC, d0 + kd - RC, n);
+            if (leader) {
+              mbar_expect_tx(afull_cur, Cfg::NPL * a_rows * Cfg::ROWB);
+              tma_load_5d(a_addr_cur, src1 ? &a1_hi : &a2_hi, afull_cur, cch, w0, h0 - RC, d0 + kd - RC, n);
+              if (NSPLIT == 3)
+                tma_load_5d(a_addr_cur + g.a_stage_bytes, src1 ? &a1_lo : &a2_lo, afull_cur, cch, w0, h0 - RC, d0 + kd - RC, n);
+            }
+            afull_cur += 8u;
+            a_addr_cur += a_stage_all;
             if (++as == g.n_a) {
               as = 0;
               aph ^= 1u;
+              afull_cur = afull(0);
+              a_addr_cur = a_ring;
             }
+            int brow = brow_item + (kd * KS * g.n_kc + kc) * Cfg::NB;
+#pragma unroll
             for (int kh = 0; kh < KS; ++kh) {
-              const int it = (kd * KS + kh) * g.n_kc + kc;
-              mbar_wait_warp(bempty(bs), bph ^ 1u);
-              const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
-              const int brow = (slice * n_it + it) * Cfg::NB;
-              mbar_expect_tx_if(leader, bfull(bs), Cfg::NPL * Cfg::NB * Cfg::ROWB);
-              tma_load_2d_if(leader, b_addr, &w_hi, bfull(bs), 0, brow);
-              if (NSPLIT == 3) tma_load_2d_if(leader, b_addr + Cfg::B_BYTES, &w_lo, bfull(bs), 0, brow);
+              mbar_wait_warp(bfull_cur + 32u, bph ^ 1u);   // bempty
+              if (leader) {
+                mbar_expect_tx(bfull_cur, Cfg::NPL * Cfg::NB * Cfg::ROWB);
+                tma_load_2d(b_addr_cur, &w_hi, bfull_cur, 0, brow);
+                if (NSPLIT == 3) tma_load_2d(b_addr_cur + Cfg::B_BYTES, &w_lo, bfull_cur, 0, brow);
+              }
+              brow += brow_kh;
+              bfull_cur += 8u;
+              b_addr_cur += Cfg::NPL * Cfg::B_BYTES;
               if (++bs == g.n_b) {
                 bs = 0;
                 bph ^= 1u;
+                bfull_cur = bfull(0);
+                b_addr_cur = b_ring;
               }
             }
           }
@@ -341,11 +357,23 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
   } else if (warp == 1) {
     const bool leader = elect_one();
     {
+      // The issue loop is the critical path of the kernel (tools/probe_tcgen05 `rates`, tools/kbench): the tensor pipe
+      // only reaches its floor when MMAs arrive back to back, and every scalar instruction between two MMAs is
+      // exposed.  Hence: descriptors are advanced incrementally (they differ only in the 14-bit start-address field,
+      // in units of 16 bytes), the kh / tile / k-slice loops are fully unrolled, ring state is a running barrier
+      // address + descriptor instead of an index, and nothing but the barrier wait sits between two stages.
       const uint32_t idesc = make_instr_desc(128, Cfg::NB, FMT_BF16);
+      const uint64_t desc0 = make_smem_desc(0, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
+      const uint32_t a_stride16 = static_cast<uint32_t>(Cfg::NPL * g.a_stage_bytes) >> 4, a_lo16 = static_cast<uint32_t>(g.a_stage_bytes) >> 4;
+      constexpr uint32_t b_stride16 = (Cfg::NPL * Cfg::B_BYTES) >> 4, b_lo16 = Cfg::B_BYTES >> 4;
+      const uint32_t kh_step16 = static_cast<uint32_t>(g.LP * Cfg::ROWB) >> 4, t_step16 = static_cast<uint32_t>(g.tile_rows * Cfg::ROWB) >> 4;
+      const uint64_t da_slot0 = desc0 + (a_ring >> 4), db_slot0 = desc0 + (b_ring >> 4);
+      const uint32_t afull0 = afull(0), bfull0 = bfull(0);   // aempty(s) = afull(s) + 32, bempty(s) = bfull(s) + 32
+      uint64_t da_cur = da_slot0, db_cur = db_slot0;
+      uint32_t afull_cur = afull0, bfull_cur = bfull0;
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int j = 0;
-      bool a_rdy = false, b_rdy = false;   // look-ahead barrier tests (false: take the blocking wait)
       VNB_DBG_DECL;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
         const int buf = j & 1;
@@ -353,56 +381,56 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
         VNB_DBG_WAITP(p.dbg, dbg_wait2, mbar_wait_warp(tempty0 + 8u * buf, (use & 1u) ^ 1u));
         tc_fence_after_sync();
         const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
-        bool first = true;
-        for (int kd = 0; kd < KS; ++kd)
-          for (int kc = 0; kc < g.n_kc; ++kc) {
-            VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(afull(as), aph, a_rdy));
-            tc_fence_after_sync();
-            {  // look at the next A stage now, use the answer when we get there
-              const int as_n = as + 1 == g.n_a ? 0 : as + 1;
-              a_rdy = mbar_test(afull(as_n), as_n == 0 ? aph ^ 1u : aph);
-            }
-            const uint32_t a_addr = a_ring + static_cast<uint32_t>(as) * Cfg::NPL * g.a_stage_bytes;
-            const uint64_t da_hi0 = make_smem_desc(a_addr, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
-            const uint64_t da_lo0 = da_hi0 + (static_cast<uint32_t>(g.a_stage_bytes) >> 4);
-            for (int kh = 0; kh < KS; ++kh) {
-              VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(bfull(bs), bph, b_rdy));
-              tc_fence_after_sync();
-              {
-                const int bs_n = bs + 1 == g.n_b ? 0 : bs + 1;
-                b_rdy = mbar_test(bfull(bs_n), bs_n == 0 ? bph ^ 1u : bph);
-              }
-              const uint32_t b_addr = b_ring + static_cast<uint32_t>(bs) * Cfg::NPL * Cfg::B_BYTES;
-              const uint64_t db_hi0 = make_smem_desc(b_addr, 16, 8 * Cfg::ROWB, Cfg::LAYOUT);
-              const uint64_t db_lo0 = db_hi0 + (Cfg::B_BYTES >> 4);
-              for (int t = 0; t < g.T; ++t) {
+        uint32_t acc0 = 0u;   // 0 for the first MMA of every tile of the item, 1 afterwards
+        const int n_ak = KS * g.n_kc;
+        for (int ak = 0; ak < n_ak; ++ak) {   // one A stage per (kd, k-chunk)
+          VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(afull_cur, aph));
+          tc_fence_after_sync();
+          uint64_t da_kh = da_cur;
 #pragma unroll
-                for (int ks = 0; ks < KC / 16; ++ks) {
-                  const uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t * g.tile_rows + kh * g.LP) * Cfg::ROWB + ks * 32) >> 4);
-                  const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
-                  const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+          for (int kh = 0; kh < KS; ++kh) {
+            VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(bfull_cur, bph));
+            tc_fence_after_sync();
+            if (leader) {
+#pragma unroll
+              for (int t = 0; t < TMAX; ++t) {
+                if (t < g.T) {
+                  const uint64_t da_t = da_kh + static_cast<uint64_t>(static_cast<uint32_t>(t) * t_step16);
                   const uint32_t d_addr = d_base + t * Cfg::NB;
-                  VNB_DBG_COUNT(NSPLIT == 3 ? 3 : 1);
-                  mma_f16_ss_if(leader, d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
-                  if (NSPLIT == 3) {
-                    mma_f16_ss_if(leader, d_addr, da_lo0 + aoff, db_hi0 + boff, idesc, 1u);
-                    mma_f16_ss_if(leader, d_addr, da_hi0 + aoff, db_lo0 + boff, idesc, 1u);
+#pragma unroll
+                  for (int ks = 0; ks < KC / 16; ++ks) {
+                    VNB_DBG_COUNT(NSPLIT == 3 ? 3 : 1);
+                    mma_f16_ss(d_addr, da_t + 2 * ks, db_cur + 2 * ks, idesc, ks == 0 ? acc0 : 1u);
+                    if (NSPLIT == 3) {
+                      mma_f16_ss(d_addr, da_t + a_lo16 + 2 * ks, db_cur + 2 * ks, idesc, 1u);
+                      mma_f16_ss(d_addr, da_t + 2 * ks, db_cur + b_lo16 + 2 * ks, idesc, 1u);
+                    }
                   }
                 }
               }
-              first = false;
-              mma_commit_if(leader, bempty(bs));
-              if (++bs == g.n_b) {
-                bs = 0;
-                bph ^= 1u;
-              }
+              mma_commit(bfull_cur + 32u);   // bempty: the slot is free once these MMAs have read it
             }
-            mma_commit_if(leader, aempty(as));
-            if (++as == g.n_a) {
-              as = 0;
-              aph ^= 1u;
+            acc0 = 1u;
+            da_kh += kh_step16;
+            db_cur += b_stride16;
+            bfull_cur += 8u;
+            if (++bs == g.n_b) {
+              bs = 0;
+              bph ^= 1u;
+              db_cur = db_slot0;
+              bfull_cur = bfull0;
             }
           }
+          mma_commit_if(leader, afull_cur + 32u);   // aempty
+          da_cur += a_stride16;
+          afull_cur += 8u;
+          if (++as == g.n_a) {
+            as = 0;
+            aph ^= 1u;
+            da_cur = da_slot0;
+            afull_cur = afull0;
+          }
+        }
         mma_commit_if(leader, tfull0 + 8u * buf);
       }
       if (leader && j > 0) {

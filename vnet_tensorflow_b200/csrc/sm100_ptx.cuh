@@ -231,9 +231,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 
 
 // ----------------------------------------------------------------------------------------------
-// predicated forms: the instruction is guarded inside the asm block, so the surrounding control flow stays
-// warp-uniform (all lanes compute the operands in converged code; only the lane with pred != 0 issues)
+// issue-by-one-lane forms.  The role warps run their loops converged; the lane with pred != 0 issues.
+// VNB_ISSUE_PREDICATED_ASM selects instruction-level predication inside the asm block (ptxas then moves every
+// operand with `@p R2UR.BROADCAST`, a cross-lane operation per register); the default is a plain branch around the
+// instruction, for which ptxas keeps the warp-uniform operands in uniform registers or moves them with plain R2UR.
 // ----------------------------------------------------------------------------------------------
+#ifdef VNB_ISSUE_PREDICATED_ASM
 __device__ __forceinline__ void mma_f16_ss_if(bool pred, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
                                               uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -288,6 +291,26 @@ __device__ __forceinline__ void tma_load_5d_if(bool pred, uint32_t dst, const vo
       "r"(static_cast<uint32_t>(pred))
       : "memory");
 }
+
+#else
+__device__ __forceinline__ void mma_f16_ss_if(bool pred, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if (pred) mma_f16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
+}
+__device__ __forceinline__ void mma_commit_if(bool pred, uint32_t bar) {
+  if (pred) mma_commit(bar);
+}
+__device__ __forceinline__ void mbar_expect_tx_if(bool pred, uint32_t bar, uint32_t bytes) {
+  if (pred) mbar_expect_tx(bar, bytes);
+}
+__device__ __forceinline__ void tma_load_2d_if(bool pred, uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  if (pred) tma_load_2d(dst, tmap, bar, c0, c1);
+}
+__device__ __forceinline__ void tma_load_5d_if(bool pred, uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                               int c3, int c4) {
+  if (pred) tma_load_5d(dst, tmap, bar, c0, c1, c2, c3, c4);
+}
+#endif
 
 }  // namespace sm100
 #endif  // VNB_EMULATE
