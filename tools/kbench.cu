@@ -109,7 +109,7 @@ int main(int argc, char** argv) {
     }
   } else {
     TcKernelPlan pl;
-    if (!tc_plan_geometry(pl, N, D, H, W, Cin, cin2, Cout, 0, lo, ks)) { printf("unsupported shape\n"); return 1; }
+    if (!tc_plan_geometry(pl, N, D, H, W, Cin, cin2, Cout, 0, lo, ks, sms)) { printf("unsupported shape\n"); return 1; }
     uint16_t *xh = mk(V * Cin, 1), *xl = lo ? mk(V * Cin, 2) : nullptr;
     uint16_t *x2h = cin2 ? mk(V * cin2, 5) : nullptr, *x2l = (cin2 && lo) ? mk(V * cin2, 6) : nullptr;
     pl.wp_elems = (size_t)ks * ks * ks * (Cin + cin2) * Cout;

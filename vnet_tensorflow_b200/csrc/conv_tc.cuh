@@ -51,6 +51,7 @@ __device__ __forceinline__ unsigned long long vnb_globaltimer() {
 #endif
 
 constexpr int kTcStages = 4;
+constexpr int kTcSlots = 6;                 // barrier pairs reserved for accumulator tile slots (>= any NSLOT)
 constexpr int kTcThreads = 192;             // 2 control warps + 4 epilogue warps (one epilogue group)
 constexpr int kTcEpiRowPad = 20;  // floats per staged row (16 + 4: conflict-free float4 rows)
 constexpr int kTcEpiBytes = 5 * 128 * kTcEpiRowPad * 4;
@@ -63,10 +64,14 @@ struct TcCfg {
   static constexpr int NB = KS * CT;                        // GEMM N (kw-folded)
   static constexpr int R = KS / 2;
   static constexpr int NPL = NSPLIT == 3 ? 2 : 1;           // operand planes (hi, lo)
-  static constexpr int A_BYTES = TMAX * 128 * ROWB;
+  // TMEM: the 512 columns are a ring of NSLOT accumulator tile slots of NB columns each; an item takes T <= TMAX
+  // consecutive slots (one per 128-row tile), the epilogue hands every slot back as soon as its tile is stored.
+  // CT = 16: six slots = two items of three tiles; CT = 32: three slots, items of one or two tiles.
+  static constexpr int NSLOT = 512 / NB > 6 ? 6 : 512 / NB;
+  static constexpr int TSTREAM = CT == 32 ? 1 : TMAX;       // tiles per item of the streaming (non-resident) pipeline
+  static constexpr int A_BYTES = TSTREAM * 128 * ROWB;
   static constexpr int B_BYTES = ((NB * ROWB + 1023) / 1024) * 1024;
   static constexpr int STAGE_BYTES = NPL * (A_BYTES + B_BYTES);
-  static constexpr int BUF_COLS = TMAX * NB;                // TMEM columns per accumulator buffer
   // single-pass bf16 is epilogue-bound on the Cout = 16 layers: it gets one epilogue group (4 warps, own
   // staging buffer) per TMEM accumulator buffer; the 3-pass mode is MMA-bound and keeps one group
   static constexpr int EG = NSPLIT == 3 ? 1 : 2;
@@ -74,7 +79,7 @@ struct TcCfg {
   static constexpr int EPI_BYTES = EG * kTcEpiBytes;
   static constexpr int SMEM_BYTES = kTcStages * STAGE_BYTES + EPI_BYTES + 256 + 1024;
   static constexpr uint32_t LAYOUT = ROWB == 32 ? sm100::SWZ_32B : ROWB == 64 ? sm100::SWZ_64B : sm100::SWZ_128B;
-  static_assert(2 * BUF_COLS <= 512, "TMEM overflow");
+  static_assert(TMAX <= NSLOT && NSLOT * NB <= 512, "TMEM overflow");
   static_assert(NB % 16 == 0 && NB <= 256, "invalid UMMA N");
 };
 
@@ -132,7 +137,7 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_ba
     const int Ctot = g.Co1 + g.Co2;
     int j = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
-      if (Cfg::EG == 2 && (j & 1) != eg) continue;      // with two groups, group == accumulator buffer
+      if (Cfg::EG == 2 && (j & 1) != eg) continue;      // two groups: alternate items
       const int slice = item % g.n_slices;
       int x = item / g.n_slices;
       const int wb = x % g.n_wb;
@@ -141,11 +146,12 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_ba
       x /= g.n_hb;
       const int db = x % g.n_db;
       const int n = x / g.n_db;
-      const int buf = j & 1;
-      const uint32_t use = static_cast<uint32_t>(j >> 1);
-      mbar_wait(tfull_bar(buf), use & 1u);
-      tc_fence_after_sync();
       for (int t = 0; t < g.T; ++t) {
+        const int gi = j * g.T + t;                     // running tile index of this CTA -> accumulator slot, use count
+        const int slot = gi % Cfg::NSLOT;
+        const uint32_t use = static_cast<uint32_t>(gi / Cfg::NSLOT);
+        mbar_wait(tfull_bar(slot), use & 1u);
+        tc_fence_after_sync();
         const int lt = r / g.LP, i = r % g.LP;          // line inside this MMA tile, row inside the line
         const int line = t * g.lpt + lt;
         const int w = g.halo ? wb * g.Wt + i - RC : i;
@@ -153,7 +159,7 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_ba
         const bool valid = lt < g.lpt && line < g.bh * g.bd && gh < g.H && gd < g.D && w >= 0 && w < g.W &&
                            (!g.halo || (i >= RC && i < g.Wt + RC));
         const long long vox = ((static_cast<long long>(n) * g.D + gd) * g.H + gh) * g.W + w;
-        const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * Cfg::BUF_COLS + t * Cfg::NB;
+        const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + slot * Cfg::NB;
 #pragma unroll 1
         for (int cc = 0; cc < CT / 16; ++cc) {
           float acc[16];
@@ -232,9 +238,9 @@ __device__ __forceinline__ void conv5_tc_epilogue(const TcArgs& p, float* epi_ba
             }
           }
         }
+        tc_fence_before_sync();
+        mbar_arrive(tempty_bar(slot));  // 128 arrivals hand the tile slot back to the MMA warp
       }
-      tc_fence_before_sync();
-      mbar_arrive(tempty_bar(buf));  // 128 arrivals free the accumulator buffer
     }
   }
 }
@@ -262,9 +268,9 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
   auto aempty = [&](int s) { return bar_base + 8u * (4 + s); };   // [4]
   auto bfull = [&](int s) { return bar_base + 8u * (8 + s); };    // [4]
   auto bempty = [&](int s) { return bar_base + 8u * (12 + s); };  // [4]
-  const uint32_t tfull0 = bar_base + 8u * 16, tempty0 = bar_base + 8u * 18;
-  const uint32_t slot_addr = bar_base + 8u * 20;
-  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + epi_off + Cfg::EPI_BYTES + 8 * 20);
+  const uint32_t tfull0 = bar_base + 8u * 16, tempty0 = bar_base + 8u * (16 + kTcSlots);   // [kTcSlots] each
+  const uint32_t slot_addr = bar_base + 8u * (16 + 2 * kTcSlots);
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + epi_off + Cfg::EPI_BYTES + 8 * (16 + 2 * kTcSlots));
   const int kc1 = g.C1 / KC;
   const int n_it = KS * KS * g.n_kc;
 
@@ -275,7 +281,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
       mbar_init(bfull(s), 1);
       mbar_init(bempty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < Cfg::NSLOT; ++b) {
       mbar_init(tfull0 + 8u * b, 1);
       mbar_init(tempty0 + 8u * b, 128);
     }
@@ -376,11 +382,19 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
       int j = 0;
       VNB_DBG_DECL;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
-        const int buf = j & 1;
-        const uint32_t use = static_cast<uint32_t>(j >> 1);
-        VNB_DBG_WAITP(p.dbg, dbg_wait2, mbar_wait_warp(tempty0 + 8u * buf, (use & 1u) ^ 1u));
+        // accumulator slots of the item's tiles: running tile index gi -> slot gi % NSLOT, use count gi / NSLOT
+        uint32_t d_tile[TMAX], tslot[TMAX];
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t) {
+          const int gi = j * g.T + t;
+          tslot[t] = static_cast<uint32_t>(gi % Cfg::NSLOT);
+          d_tile[t] = tmem + tslot[t] * Cfg::NB;
+          if (t < g.T) {
+            const uint32_t use = static_cast<uint32_t>(gi / Cfg::NSLOT);
+            VNB_DBG_WAITP(p.dbg, dbg_wait2, mbar_wait_warp(tempty0 + 8u * tslot[t], (use & 1u) ^ 1u));
+          }
+        }
         tc_fence_after_sync();
-        const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
         uint32_t acc0 = 0u;   // 0 for the first MMA of every tile of the item, 1 afterwards
         const int n_ak = KS * g.n_kc;
         for (int ak = 0; ak < n_ak; ++ak) {   // one A stage per (kd, k-chunk)
@@ -396,7 +410,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
               for (int t = 0; t < TMAX; ++t) {
                 if (t < g.T) {
                   const uint64_t da_t = da_kh + static_cast<uint64_t>(static_cast<uint32_t>(t) * t_step16);
-                  const uint32_t d_addr = d_base + t * Cfg::NB;
+                  const uint32_t d_addr = d_tile[t];
 #pragma unroll
                   for (int ks = 0; ks < KC / 16; ++ks) {
                     VNB_DBG_COUNT(NSPLIT == 3 ? 3 : 1);
@@ -431,10 +445,13 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
             afull_cur = afull0;
           }
         }
-        mma_commit_if(leader, tfull0 + 8u * buf);
+#pragma unroll
+        for (int t = 0; t < TMAX; ++t)
+          if (t < g.T) mma_commit_if(leader, tfull0 + 8u * tslot[t]);   // the item's accumulators are complete
       }
       if (leader && j > 0) {
-        VNB_DBG_STORE(p.dbg, tfull0 + 8u * ((j - 1) & 1), ((j - 1) >> 1) & 1);
+        const int gl = j * g.T - 1;   // last tile issued
+        VNB_DBG_STORE(p.dbg, tfull0 + 8u * (gl % Cfg::NSLOT), (gl / Cfg::NSLOT) & 1);
       }
     }
   } else {
@@ -459,13 +476,13 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
   const uint32_t sm_addr = smem_u32(sm);
   float* epi = reinterpret_cast<float*>(sm + kTcStages * Cfg::STAGE_BYTES);
   const uint32_t bar_base = sm_addr + kTcStages * Cfg::STAGE_BYTES + Cfg::EPI_BYTES;
-  // barriers: full[0..S), empty[S..2S), tmem_full[2S..2S+2), tmem_empty[2S+2..2S+4); then TMEM slot
+  // barriers: full[0..S), empty[S..2S), tmem_full[kTcSlots], tmem_empty[kTcSlots]; then the TMEM base word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kTcStages + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + 2 + b); };
-  const uint32_t slot_addr = bar_base + 8u * (2 * kTcStages + 4);
-  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTcStages * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + 8 * (2 * kTcStages + 4));
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kTcStages + kTcSlots + b); };
+  const uint32_t slot_addr = bar_base + 8u * (2 * kTcStages + 2 * kTcSlots);
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + kTcStages * Cfg::STAGE_BYTES + Cfg::EPI_BYTES + 8 * (2 * kTcStages + 2 * kTcSlots));
 
   const int tid = threadIdx.x;
   const int warp = static_cast<int>(warp_uniform(static_cast<uint32_t>(tid >> 5)));
@@ -482,7 +499,7 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < Cfg::NSLOT; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 128);
     }
@@ -544,21 +561,23 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
       int stage = 0;
       uint32_t phase = 0;
       int j = 0;
-      bool rdy = false;   // look-ahead barrier test of the next stage
       VNB_DBG_DECL;
       for (int item = blockIdx.x; item < g.n_items; item += gridDim.x, ++j) {
-        const int buf = j & 1;
-        const uint32_t use = static_cast<uint32_t>(j >> 1);
-        VNB_DBG_WAITP(p.dbg, dbg_wait2, mbar_wait_warp(tempty_bar(buf), (use & 1u) ^ 1u));
-        tc_fence_after_sync();
-        const uint32_t d_base = tmem + buf * Cfg::BUF_COLS;
-        for (int it = 0; it < n_it; ++it) {
-          VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(full_bar(stage), phase, rdy));
-          tc_fence_after_sync();
-          {
-            const int st_n = stage + 1 == kTcStages ? 0 : stage + 1;
-            rdy = mbar_test(full_bar(st_n), st_n == 0 ? phase ^ 1u : phase);
+        uint32_t d_tile[Cfg::TSTREAM], tslot[Cfg::TSTREAM];
+#pragma unroll
+        for (int t = 0; t < Cfg::TSTREAM; ++t) {
+          const int gi = j * g.T + t;
+          tslot[t] = static_cast<uint32_t>(gi % Cfg::NSLOT);
+          d_tile[t] = tmem + tslot[t] * Cfg::NB;
+          if (t < g.T) {
+            const uint32_t use = static_cast<uint32_t>(gi / Cfg::NSLOT);
+            VNB_DBG_WAITP(p.dbg, dbg_wait2, mbar_wait_warp(tempty_bar(tslot[t]), (use & 1u) ^ 1u));
           }
+        }
+        tc_fence_after_sync();
+        for (int it = 0; it < n_it; ++it) {
+          VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(full_bar(stage), phase));
+          tc_fence_after_sync();
           // descriptors differ between MMAs only in the start-address field (bits 0-13, units of 16 B):
           // build one base per operand per stage and advance it with a single 64-bit add
           const uint32_t a_hi = sm_addr + stage * Cfg::STAGE_BYTES;
@@ -566,13 +585,15 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
           const uint64_t da_lo0 = da_hi0 + (Cfg::A_BYTES >> 4);
           const uint64_t db_hi0 = da_hi0 + ((Cfg::NPL * Cfg::A_BYTES) >> 4);
           const uint64_t db_lo0 = db_hi0 + (Cfg::B_BYTES >> 4);
-          for (int t = 0; t < g.T; ++t) {
+#pragma unroll
+          for (int t = 0; t < Cfg::TSTREAM; ++t) {
+            if (t >= g.T) continue;
 #pragma unroll
             for (int ks = 0; ks < KC / 16; ++ks) {
               const uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t * g.tile_rows) * Cfg::ROWB + ks * 32) >> 4);
               const uint64_t boff = static_cast<uint64_t>((ks * 32) >> 4);
               const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-              const uint32_t d_addr = d_base + t * Cfg::NB;
+              const uint32_t d_addr = d_tile[t];
               VNB_DBG_COUNT(NSPLIT == 3 ? 3 : 1);
               mma_f16_ss_if(leader, d_addr, da_hi0 + aoff, db_hi0 + boff, idesc, acc);
               if (NSPLIT == 3) {
@@ -587,10 +608,13 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
             phase ^= 1u;
           }
         }
-        mma_commit_if(leader, tfull_bar(buf));  // accumulators of this item complete
+#pragma unroll
+        for (int t = 0; t < Cfg::TSTREAM; ++t)
+          if (t < g.T) mma_commit_if(leader, tfull_bar(tslot[t]));  // accumulators of this item complete
       }
       if (leader && j > 0) {
-        VNB_DBG_STORE(p.dbg, tfull_bar((j - 1) & 1), ((j - 1) >> 1) & 1);
+        const int gl = j * g.T - 1;
+        VNB_DBG_STORE(p.dbg, tfull_bar(gl % Cfg::NSLOT), (gl / Cfg::NSLOT) & 1);
       }
     }
   } else {
@@ -773,7 +797,7 @@ struct TcKernelPlan {   // one launch of conv5_tc_kernel
 
 // geometry for a [N][D][H][W] activation, kernel-side channel counts (C1+C2 in, Co1+Co2 out)
 inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C1, int C2, int Co1, int Co2, bool split3,
-                             int ks = 5) {
+                             int ks = 5, int sms = 148) {
   auto mult = [](int v, int m) { return v % m == 0; };
   pl.KS = ks;
   if (mult(C1, 32) && mult(C2, 32) && mult(Co1, 32) && mult(Co2, 32) && Co1 > 0) {
@@ -798,9 +822,10 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
     lpt = 1;
   }
   if (LP > 256) return false;
-  const int tmax = pl.CT == 16 ? 3 : 1;
+  const int tmax = pl.CT == 16 ? 3 : 2;          // template TMAX of the kernel instances
+  const int tstream = pl.CT == 16 ? 3 : 1;      // the streaming pipeline of the CT = 32 instances keeps one tile
   for (int pass = 0; pass < 2; ++pass)   // pass 0: boxes that tile the volume exactly; pass 1: accept unused rows
-  for (int T = tmax; T >= 1; --T) {
+  for (int T = (getenv("VNB_TC_TMAX") ? std::min(tmax, atoi(getenv("VNB_TC_TMAX"))) : tmax); T >= 1; --T) {
     const int lines = T * lpt;
     int bh, bd;
     if (lines <= H) {
@@ -827,7 +852,7 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
     const int npl = split3 ? 2 : 1;
     const int rowb = pl.KC * 2;
     const int b_bytes = ((ks * pl.CT * rowb + 1023) / 1024) * 1024;
-    const int tmax_rows = tmax * 128;
+    const int tmax_rows = tstream * 128;
     g.resident = 0;
     g.a_stage_bytes = 0;
     g.n_a = g.n_b = 0;
@@ -848,6 +873,17 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
           break;
         }
       }
+    }
+    if (T > tstream && !g.resident) continue;   // more tiles than the streaming pipeline holds: try a smaller item
+    if (pl.CT == 32 && T == 2 && !getenv("VNB_TC_TMAX")) {
+      // Two tiles per weight tile halve the weight traffic (measured per-tile cost 0.9x with three MMA passes,
+      // 0.78x with one) but double the item size: keep one tile when the coarser items leave more of the last
+      // wave of persistent CTAs idle than that buys.
+      const double f = split3 ? 0.9 : 0.78;
+      const long long items2 = g.n_items, items1 = 2LL * g.n_items;   // one-tile items of the same layer (exact boxes)
+      const double cost2 = static_cast<double>((items2 + sms - 1) / sms) * 2.0 * f;
+      const double cost1 = static_cast<double>((items1 + sms - 1) / sms);
+      if (cost1 < cost2) continue;
     }
     return true;
   }
@@ -877,8 +913,8 @@ inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int 
       if (split3) tc_launch_inst<16, 3, 16, 3, 3>(pl, a, sms, stream);
       else tc_launch_inst<16, 3, 16, 1, 3>(pl, a, sms, stream);
     } else {
-      if (split3) tc_launch_inst<32, 1, 32, 3, 3>(pl, a, sms, stream);
-      else tc_launch_inst<32, 1, 32, 1, 3>(pl, a, sms, stream);
+      if (split3) tc_launch_inst<32, 2, 32, 3, 3>(pl, a, sms, stream);
+      else tc_launch_inst<32, 2, 32, 1, 3>(pl, a, sms, stream);
     }
     return;
   }
@@ -886,8 +922,8 @@ inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int 
     if (split3) tc_launch_inst<16, 3, 16, 3>(pl, a, sms, stream);
     else tc_launch_inst<16, 3, 16, 1>(pl, a, sms, stream);
   } else {
-    if (split3) tc_launch_inst<32, 1, 32, 3>(pl, a, sms, stream);
-    else tc_launch_inst<32, 1, 32, 1>(pl, a, sms, stream);
+    if (split3) tc_launch_inst<32, 2, 32, 3>(pl, a, sms, stream);
+    else tc_launch_inst<32, 2, 32, 1>(pl, a, sms, stream);
   }
 }
 

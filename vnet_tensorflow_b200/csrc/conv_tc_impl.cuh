@@ -51,7 +51,7 @@ inline void Engine::tc_setup() {
     const bool padded_in = (u.in1 == image_act_) && image_cpad_ > 0;
     const int c1 = padded_in ? image_cpad_ : u.Cin1;
     TcKernelPlan& f = u.tc.fprop;
-    if (tc_plan_geometry(f, NB, d.D, d.H, d.W, c1, u.Cin2, u.Cout, 0, lo, ks)) {
+    if (tc_plan_geometry(f, NB, d.D, d.H, d.W, c1, u.Cin2, u.Cout, 0, lo, ks, sm_count_)) {
       f.wp_elems = static_cast<size_t>(ks * ks * ks) * (c1 + u.Cin2) * u.Cout;
       f.wp_hi = dev_alloc<uint16_t>(f.wp_elems);
       f.wp_lo = lo ? dev_alloc<uint16_t>(f.wp_elems) : nullptr;
@@ -59,7 +59,7 @@ inline void Engine::tc_setup() {
       f.valid = true;
     }
     TcKernelPlan& g = u.tc.dgrad;
-    if (u.need_dgrad && tc_plan_geometry(g, NB, d.D, d.H, d.W, u.Cout, 0, u.Cin1, u.Cin2, lo, ks)) {
+    if (u.need_dgrad && tc_plan_geometry(g, NB, d.D, d.H, d.W, u.Cout, 0, u.Cin1, u.Cin2, lo, ks, sm_count_)) {
       g.wp_elems = u.w_count;
       g.wp_hi = dev_alloc<uint16_t>(g.wp_elems);
       g.wp_lo = lo ? dev_alloc<uint16_t>(g.wp_elems) : nullptr;
@@ -176,7 +176,7 @@ inline void tc_op_conv5(int precision, const float* x, const float* w, const flo
   const bool lo = precision == PREC_BF16X3;
   const int ci = dgrad_form ? cout : cin, co = dgrad_form ? cin : cout;
   TcKernelPlan pl;
-  if (!tc_plan_geometry(pl, n, dims.D, dims.H, dims.W, ci, 0, co, 0, lo, ks))
+  if (!tc_plan_geometry(pl, n, dims.D, dims.H, dims.W, ci, 0, co, 0, lo, ks, tc_query_sms()))
     throw std::invalid_argument("shape not supported by the tensor-core convolution (channels % 16, line blocking)");
   TcScratch s;
   const size_t nx = static_cast<size_t>(n) * dims.D * dims.H * dims.W * ci;
