@@ -158,7 +158,6 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
         tc_fence_after_sync();
         const uint32_t za_hi = z_ring + (zs * NPL) * g.zt_bytes;
         const uint64_t db0 = make_smem_desc(za_hi, z_pitch, sbo_b, SWZ_32B);
-        const uint64_t db0_lo = db0 + (static_cast<uint32_t>(g.zt_bytes) >> 4);
         for (int kd = 0; kd < KS; ++kd) {
           const long long xi = xlo + kd;   // X plane dz + kd - RC
           const int xs = static_cast<int>(xi % XS);
@@ -171,21 +170,27 @@ wgrad5_tc_kernel(const __grid_constant__ TmaDesc x1_hi, const __grid_constant__ 
           const uint32_t d_addr = tmem + kd * NB;
           // only the start-address field changes between MMAs: one base descriptor per operand, 64-bit adds after
           const uint64_t da0 = make_smem_desc(xa_hi, 32, sbo_a, SWZ_32B);
-          const uint64_t da0_lo = da0 + (static_cast<uint32_t>(g.xt_bytes) >> 4);
           uint32_t acc = (u == u0) ? 0u : 1u;
-          for (int t = 0; t < g.HT; t += lpm) {
-            uint64_t aoff = static_cast<uint64_t>((static_cast<uint32_t>(t) * x_pitch) >> 4);
-            uint64_t boff = static_cast<uint64_t>((static_cast<uint32_t>(t) * z_pitch) >> 4);
-            for (int ks = 0; ks < ksteps; ++ks) {
-              mma_f16_ss_if(leader, d_addr, da0 + aoff, db0 + boff, idesc, acc);
-              if (NSPLIT == 3) {
-                mma_f16_ss_if(leader, d_addr, da0_lo + aoff, db0 + boff, idesc, 1u);
-                mma_f16_ss_if(leader, d_addr, da0 + aoff, db0_lo + boff, idesc, 1u);
+          VNB_DBG_COUNT((NSPLIT == 3 ? 3 : 1) * ((g.HT + lpm - 1) / lpm) * ksteps);
+          if (leader) {   // one branch around the whole burst: the MMAs of a (plane, kd) pair issue back to back
+            // running descriptors; a line advances A by x_pitch and B by z_pitch, a k-step both by 512 B
+            uint64_t da_t = da0, db_t = db0;
+            const uint32_t a_line16 = (static_cast<uint32_t>(lpm) * x_pitch) >> 4, b_line16 = (static_cast<uint32_t>(lpm) * z_pitch) >> 4;
+            const uint32_t a_lo16 = static_cast<uint32_t>(g.xt_bytes) >> 4, b_lo16 = static_cast<uint32_t>(g.zt_bytes) >> 4;
+            for (int t = 0; t < g.HT; t += lpm) {
+              uint64_t da = da_t, db = db_t;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                mma_f16_ss(d_addr, da, db, idesc, acc);
+                if (NSPLIT == 3) {
+                  mma_f16_ss(d_addr, da + a_lo16, db, idesc, 1u);
+                  mma_f16_ss(d_addr, da, db + b_lo16, idesc, 1u);
+                }
+                acc = 1u;
+                da += 32;  // next 16 voxels: 16 rows x 32 B = 512 B (only taken when lpm == 1)
+                db += 32;
               }
-              acc = 1u;
-              VNB_DBG_COUNT(NSPLIT == 3 ? 3 : 1);
-              aoff += 32;  // next 16 voxels: 16 rows x 32 B = 512 B (only taken when lpm == 1)
-              boff += 32;
+              da_t += a_line16;
+              db_t += b_line16;
             }
           }
         }
