@@ -8,6 +8,7 @@
  *   vnb_create            networks.VNet(...).GetNetwork + build_model_graph     networks.py:209-305, model.py:297-630
  *   vnb_set/get_param     tf.train.Saver restore/save by variable name          model.py:689-699,758-764
  *   vnb_forward           sess.run(['predicted_label/prediction:0','softmax:0']) model.py:914-917
+ *   vnb_evaluate_volume   evaluate_single_3D window loop + accumulation + argmax model.py:866-937
  *   vnb_loss              sess.run([summary_op, loss_op]) test step             model.py:784-789
  *   vnb_train_step        sess.run([train_op, summary_op, loss_op])             model.py:743-748
  *   vnb_forward_backward  the gradient half of optimizer.minimize               model.py:660
@@ -111,6 +112,12 @@ int vnb_set_step(vnb_handle* h, int64_t global_step);
 
 /* inference: any of logits / softmax / argmax may be NULL */
 int vnb_forward(vnb_handle* h, const float* images, int n, float* logits, float* softmax, int64_t* argmax);
+/* sliding-window evaluation of one padded case (model.py:866-937): volume [X][Y][Z][M] float32 with every extent >=
+ * the patch extent; windows in (i,j,k) order, last one clamped, batches of `batch` consecutive windows (batch norm
+ * uses each batch's own statistics); outputs (any may be NULL): label int64 [X][Y][Z] = argmax of the un-normalised
+ * softmax sums, softmax_sum [X][Y][Z][K], weight [X][Y][Z] = number of windows covering a voxel */
+int vnb_evaluate_volume(vnb_handle* h, const float* volume, const int32_t dims[3], const int32_t stride[3], int batch,
+                        int64_t* label, float* softmax_sum, float* weight);
 /* loss without update; dice_terms (optional) receives [n][K][4] = (I, L, R, xent-sum) per sample/class */
 int vnb_loss(vnb_handle* h, const float* images, const int32_t* labels, int n, float* loss_out, double* dice_terms);
 /* one optimiser step; loss_out may be NULL (then the call does not synchronise) */

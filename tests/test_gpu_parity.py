@@ -356,3 +356,29 @@ def test_attention_path_trains(gpu_lib):
             p[k] = u.numpy()
     assert eng.global_step == 3
     eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_sliding_window_evaluation_matches_the_reference_loop(gpu_lib, precision):
+    """vnb_evaluate_volume (window gather, accumulation and argmax on the device) against the oracle restatement of
+    model.py:866-937 fed by vnb_forward: identical windows / batches / order of additions -> bit-exact."""
+    from oracle import ref_eval
+    from vnet_tensorflow_b200.engine import VNetEngine
+    spec = R.VNetSpec(num_classes=3, in_channels=2, num_channels=16, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=1)
+    P, B = (16, 16, 16), 3
+    eng = VNetEngine(num_classes=3, in_channels=2, patch_shape=P, max_batch=B, num_channels=16, num_levels=2,
+                     num_convolutions=(1, 2), bottom_convolutions=1, precision=precision, library=gpu_lib)
+    eng.set_params(R.init_params(spec, 7))
+    rng = np.random.default_rng(3)
+    vol = rng.uniform(0, 255, (37, 16, 29, 2)).astype(np.float32)   # ragged: clamped last windows, a unit axis
+    stride = (9, 8, 16)
+    lab, sums, wgt = eng.evaluate_volume(vol, stride, B)
+    lab_o, sums_o, wgt_o = ref_eval.evaluate_volume(vol, P, stride, B, 3, lambda x: eng.forward(x, want_logits=False, want_argmax=False)[1])
+    assert np.array_equal(wgt, wgt_o) and wgt.min() >= 1
+    assert np.array_equal(sums, sums_o)
+    assert np.array_equal(lab, lab_o) and lab.dtype == np.int64
+    np.testing.assert_allclose(sums.sum(-1), wgt, rtol=1e-5)   # softmax rows sum to one per covering window
+    with pytest.raises(Exception):
+        eng.evaluate_volume(vol[:8], stride, B)                 # smaller than the patch: the caller must pad
+    eng.close()

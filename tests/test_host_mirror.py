@@ -85,6 +85,14 @@ def test_train_checkpoint_restore_evaluate_roundtrip(emul_lib, tmp_path):
     lab, sm, w = m2.evaluate_single_3D(vol[..., None])
     assert w.max() == 4 and w.min() == 1  # overlap counts of 2x2x1 windows
     assert np.array_equal(lab, np.argmax(sm, -1))
+    # the device window loop (vnb_evaluate_volume) against the oracle restatement of model.py:866-937 fed by
+    # vnb_forward: same windows, same batches, same order of additions -> bit-exact sums, weights and labels
+    from oracle import ref_eval
+    P, S, B = m2.patch_shape, m2.evaluate_stride, m2.evaluate_batch
+    assert ref_eval.window_starts((12, 10, 8), P, S)[-1] == (12 - P[0], 10 - P[1], 8 - P[2])
+    lab_o, sm_o, w_o = ref_eval.evaluate_volume(vol[..., None], P, S, B, m2.output_channel_num,
+                                                lambda x: m2.engine.forward(x, want_logits=False, want_argmax=False)[1])
+    assert np.array_equal(sm, sm_o) and np.array_equal(w, w_o) and np.array_equal(lab, lab_o)
 
 
 def test_restore_continues_from_latest_checkpoint(emul_lib, tmp_path):

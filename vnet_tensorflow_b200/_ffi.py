@@ -57,6 +57,8 @@ _PROTOTYPES = {
     "vnb_get_step": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "vnb_set_step": (C.c_int, [C.c_void_p, C.c_int64]),
     "vnb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vnb_evaluate_volume": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
     "vnb_loss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.c_void_p]),
     "vnb_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint64,
                                  C.POINTER(C.c_float)]),

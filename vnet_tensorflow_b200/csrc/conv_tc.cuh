@@ -451,6 +451,7 @@ __device__ __forceinline__ void conv5_tc_resident(const TmaDesc& a1_hi, const Tm
       }
       if (leader && j > 0) {
         const int gl = j * g.T - 1;   // last tile issued
+        (void)gl;
         VNB_DBG_STORE(p.dbg, tfull0 + 8u * (gl % Cfg::NSLOT), (gl / Cfg::NSLOT) & 1);
       }
     }
@@ -614,6 +615,7 @@ conv5_tc_kernel(const __grid_constant__ TmaDesc a1_hi, const __grid_constant__ T
       }
       if (leader && j > 0) {
         const int gl = j * g.T - 1;
+        (void)gl;
         VNB_DBG_STORE(p.dbg, tfull_bar(gl % Cfg::NSLOT), (gl / Cfg::NSLOT) & 1);
       }
     }

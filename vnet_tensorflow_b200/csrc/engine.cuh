@@ -188,6 +188,86 @@ class Engine {
     VNB_CUDA_OK(cudaStreamSynchronize(stream_));
   }
 
+  // Sliding-window evaluation of one case (model.py:866-937): `volume` is [X][Y][Z][M] with every extent >= the
+  // patch extent (the caller pads, as the reference's Padding transform does).  Windows are enumerated in (i, j, k)
+  // order with the last one clamped to the border, grouped into batches of `batch` consecutive windows (the grouping
+  // matters: batch norm uses the statistics of each evaluation batch), run through the network and
+  // accumulated on the device.  Outputs (each optional): label int64 [X][Y][Z], softmax sums [X][Y][Z][K], hit counts.
+  void evaluate_volume_host(const float* volume, const int dims[3], const int stride[3], int batch, long long* label,
+                            float* sum_out, float* weight_out) {
+    const Dims P = acts_[image_act_].dims;
+    const int M = cfg_.in_channels, K = cfg_.num_classes;
+    check_batch(batch);
+    if (dims[0] < P.D || dims[1] < P.H || dims[2] < P.W)
+      throw std::invalid_argument("evaluate_volume: the volume must be padded to at least the patch size");
+    if (stride[0] < 1 || stride[1] < 1 || stride[2] < 1) throw std::invalid_argument("evaluate_volume: stride must be >= 1");
+    WindowGeom wg{dims[0], dims[1], dims[2], P.D, P.H, P.W, M, K};
+    const long long V = static_cast<long long>(dims[0]) * dims[1] * dims[2];
+    std::vector<int> starts;
+    const int pd[3] = {P.D, P.H, P.W};
+    int num[3];
+    for (int a = 0; a < 3; ++a) num[a] = (dims[a] - pd[a] + stride[a] - 1) / stride[a] + 1;   // ceil((dim-patch)/stride)+1
+    for (int i = 0; i < num[0]; ++i)
+      for (int j = 0; j < num[1]; ++j)
+        for (int k = 0; k < num[2]; ++k) {
+          const int idx[3] = {i, j, k};
+          for (int a = 0; a < 3; ++a) {
+            int st = idx[a] * stride[a];
+            if (st + pd[a] > dims[a]) st = dims[a] - pd[a];   // last window clamped (model.py:879-892)
+            starts.push_back(st);
+          }
+        }
+    const int nwin = static_cast<int>(starts.size() / 3);
+    struct Scratch {
+      std::vector<void*> p;
+      ~Scratch() {
+        for (void* q : p) cudaFree(q);
+      }
+      void* get(size_t bytes) {
+        void* q = nullptr;
+        if (cudaMalloc(&q, bytes ? bytes : 1) != cudaSuccess) throw std::runtime_error("CUDA: out of memory in evaluate_volume");
+        p.push_back(q);
+        return q;
+      }
+    } sc;
+    float* vol_dev = static_cast<float*>(sc.get(V * M * sizeof(float)));
+    float* sum_dev = static_cast<float*>(sc.get(V * K * sizeof(float)));
+    float* wgt_dev = static_cast<float*>(sc.get(V * sizeof(float)));
+    long long* lab_dev = static_cast<long long*>(sc.get(V * sizeof(long long)));
+    int* starts_dev = static_cast<int*>(sc.get(starts.size() * sizeof(int)));
+    VNB_CUDA_OK(cudaMemcpyAsync(vol_dev, volume, V * M * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    VNB_CUDA_OK(cudaMemcpyAsync(starts_dev, starts.data(), starts.size() * sizeof(int), cudaMemcpyHostToDevice, stream_));
+    VNB_CUDA_OK(cudaMemsetAsync(sum_dev, 0, V * K * sizeof(float), stream_));
+    VNB_CUDA_OK(cudaMemsetAsync(wgt_dev, 0, V * sizeof(float), stream_));
+    const long long per = static_cast<long long>(P.D) * P.H * P.W;
+    const LossCfg lc = loss_cfg();
+    for (int b0 = 0; b0 < nwin; b0 += batch) {
+      const int nb = std::min(batch, nwin - b0);
+      VNB_LAUNCH(window_gather_kernel, grid_for(per * M * nb, 256), 256, 0, stream_, (const float*)vol_dev, wg,
+                 (const int*)(starts_dev + 3 * b0), nb, acts_[image_act_].a);
+      ++launches_;
+      forward(nb, 0.f, 0, false);
+      dim3 grid(loss_blocks(), nb);
+      VNB_LAUNCH(softmax_loss_fwd_kernel, grid, 256, 0, stream_, acts_[head_act_].a, (const int32_t*)nullptr, per, lc, softmax_dev_,
+                 (long long*)nullptr, (double*)nullptr);
+      ++launches_;
+      for (int j = 0; j < nb; ++j) {
+        const int* st = &starts[3 * (b0 + j)];
+        VNB_LAUNCH(window_accumulate_kernel, grid_for(per, 256), 256, 0, stream_, (const float*)(softmax_dev_ + j * per * K), wg,
+                   st[0], st[1], st[2], sum_dev, wgt_dev);
+        ++launches_;
+      }
+    }
+    if (label) {
+      VNB_LAUNCH(volume_argmax_kernel, grid_for(V, 256), 256, 0, stream_, (const float*)sum_dev, V, K, lab_dev);
+      ++launches_;
+      VNB_CUDA_OK(cudaMemcpyAsync(label, lab_dev, V * sizeof(long long), cudaMemcpyDeviceToHost, stream_));
+    }
+    if (sum_out) VNB_CUDA_OK(cudaMemcpyAsync(sum_out, sum_dev, V * K * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    if (weight_out) VNB_CUDA_OK(cudaMemcpyAsync(weight_out, wgt_dev, V * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+  }
+
   // loss only (the in-loop test step of model.py:784-789): returns loss, optional dice terms [N][K][4]
   float loss_host(const float* images, const int32_t* labels, int N, double* terms) {
     check_batch(N);

@@ -934,3 +934,73 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_v4_kernel(BwdArgs p, unsign
 }
 
 }  // namespace vnb
+
+// =================================================================================================
+// Sliding-window evaluation (model.py:866-937): window gather, softmax accumulation, final argmax.
+// The volume, the un-normalised softmax sums and the hit counts stay on the device for a whole case.
+// =================================================================================================
+namespace vnb {
+
+struct WindowGeom {
+  int X, Y, Z;      // (padded) volume extents
+  int PX, PY, PZ;   // patch extents
+  int M, K;         // modalities, classes
+};
+
+// images[b][x][y][z][m] = volume[sx+x][sy+y][sz+z][m] for the windows of one batch (model.py:895-903)
+__global__ void window_gather_kernel(const float* __restrict__ vol, WindowGeom g, const int* __restrict__ starts, int nwin,
+                                     float* __restrict__ images) {
+  const long long per = static_cast<long long>(g.PX) * g.PY * g.PZ * g.M;
+  const long long total = per * nwin;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per);
+    long long r = i % per;
+    const int m = static_cast<int>(r % g.M);
+    r /= g.M;
+    const int z = static_cast<int>(r % g.PZ);
+    r /= g.PZ;
+    const int y = static_cast<int>(r % g.PY);
+    const int x = static_cast<int>(r / g.PY);
+    const int sx = starts[3 * b], sy = starts[3 * b + 1], sz = starts[3 * b + 2];
+    images[i] = vol[((static_cast<long long>(sx + x) * g.Y + sy + y) * g.Z + sz + z) * g.M + m];
+  }
+}
+
+// softmax_np[c][window] += softmax[j,...,c]; weight_np[window] += 1 (model.py:919-929) for ONE window: windows of a
+// batch overlap, so they are accumulated by consecutive launches in window order -- the same order of float
+// additions per voxel as the reference's NumPy loop
+__global__ void window_accumulate_kernel(const float* __restrict__ softmax, WindowGeom g, int sx, int sy, int sz,
+                                         float* __restrict__ sum, float* __restrict__ weight) {
+  const long long per = static_cast<long long>(g.PX) * g.PY * g.PZ;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < per;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long r = i;
+    const int z = static_cast<int>(r % g.PZ);
+    r /= g.PZ;
+    const int y = static_cast<int>(r % g.PY);
+    const int x = static_cast<int>(r / g.PY);
+    const long long v = (static_cast<long long>(sx + x) * g.Y + sy + y) * g.Z + sz + z;
+    for (int c = 0; c < g.K; ++c) sum[v * g.K + c] += softmax[i * g.K + c];
+    weight[v] += 1.0f;
+  }
+}
+
+// label = argmax_c of the accumulated (un-normalised) sums, lowest index on ties (np.argmax, model.py:934)
+__global__ void volume_argmax_kernel(const float* __restrict__ sum, long long V, int K, long long* __restrict__ label) {
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float mx = sum[v * K];
+    int am = 0;
+    for (int c = 1; c < K; ++c) {
+      const float x = sum[v * K + c];
+      if (x > mx) {
+        mx = x;
+        am = c;
+      }
+    }
+    label[v] = am;
+  }
+}
+
+}  // namespace vnb

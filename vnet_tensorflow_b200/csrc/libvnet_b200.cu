@@ -211,6 +211,19 @@ int vnb_forward(vnb_handle* h, const float* images, int n, float* logits, float*
   });
 }
 
+int vnb_evaluate_volume(vnb_handle* h, const float* volume, const int32_t dims[3], const int32_t stride[3], int batch,
+                        int64_t* label, float* softmax_sum, float* weight) {
+  return guarded([&] {
+    need(h, "handle");
+    need(volume, "volume");
+    need(dims, "dims");
+    need(stride, "stride");
+    select_device(h);
+    const int d[3] = {dims[0], dims[1], dims[2]}, st[3] = {stride[0], stride[1], stride[2]};
+    h->engine->evaluate_volume_host(volume, d, st, batch, reinterpret_cast<long long*>(label), softmax_sum, weight);
+  });
+}
+
 int vnb_loss(vnb_handle* h, const float* images, const int32_t* labels, int n, float* loss_out, double* terms) {
   return guarded([&] {
     need(h, "handle");

@@ -189,6 +189,20 @@ class VNetEngine:
         self.lib.check(self.lib.vnb_forward(self._h, _ptr(a), n, _ptr(logits), _ptr(softmax), _ptr(argmax)))
         return logits, softmax, argmax
 
+    def evaluate_volume(self, volume, stride, batch=1, want_sums=True, want_weight=True):
+        """Window loop of model.py:866-937 on the device: `volume` [X,Y,Z,M] (every extent >= the patch extent).
+        Returns (label int64 [X,Y,Z], softmax sums [X,Y,Z,K] or None, weight [X,Y,Z] or None)."""
+        v = np.ascontiguousarray(volume, dtype=np.float32)
+        if v.ndim != 4 or v.shape[3] != self.in_channels:
+            raise ValueError("volume must be [X,Y,Z,%d], got %r" % (self.in_channels, v.shape))
+        dims = (C.c_int32 * 3)(*v.shape[:3])
+        st = (C.c_int32 * 3)(*[int(x) for x in stride])
+        label = np.empty(v.shape[:3], np.int64)
+        sums = np.empty(v.shape[:3] + (self.num_classes,), np.float32) if want_sums else None
+        weight = np.empty(v.shape[:3], np.float32) if want_weight else None
+        self.lib.check(self.lib.vnb_evaluate_volume(self._h, _ptr(v), dims, st, int(batch), _ptr(label), _ptr(sums), _ptr(weight)))
+        return label, sums, weight
+
     def loss(self, images, labels, want_terms=False):
         a = self._check_images(images)
         l = self._check_labels(labels, a.shape[0])

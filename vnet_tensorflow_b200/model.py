@@ -183,37 +183,14 @@ class image2label(object):
 
     # ---- evaluation ---------------------------------------------------------------------------
     def evaluate_single_3D(self, images_np: np.ndarray):
-        """model.py:866-937 on an [X,Y,Z,M] array: returns (label int64 [X,Y,Z], softmax sums list, weight)."""
+        """model.py:866-937 on an [X,Y,Z,M] array: returns (label int64 [X,Y,Z], softmax sums [X,Y,Z,K], weight)."""
         P, S = self.patch_shape, self.evaluate_stride
         dims = images_np.shape[:3]
         pads = [(0, max(p - d, 0)) for d, p in zip(dims, P)] + [(0, 0)]
         if any(p[1] for p in pads):
             images_np = np.pad(images_np, pads)
-        vol = images_np.shape[:3]
-        num = [int(math.ceil((vol[a] - P[a]) / float(S[a]))) + 1 for a in range(3)]
-        windows = []
-        for i in range(num[0]):
-            for j in range(num[1]):
-                for k in range(num[2]):
-                    st = []
-                    for a, idx in enumerate((i, j, k)):
-                        s = idx * S[a]
-                        if s + P[a] > vol[a]:  # last patch clamped (model.py:879-892)
-                            s = vol[a] - P[a]
-                        st.append(s)
-                    windows.append(tuple(st))
-        softmax_np = np.zeros(vol + (self.output_channel_num,), np.float32)
-        weight_np = np.zeros(vol, np.float32)
-        B = self.evaluate_batch
-        for b0 in range(0, len(windows), B):
-            group = windows[b0:b0 + B]
-            batch = np.stack([images_np[s[0]:s[0] + P[0], s[1]:s[1] + P[1], s[2]:s[2] + P[2], :] for s in group], 0)
-            _, softmax, _ = self.engine.forward(batch, want_logits=False, want_argmax=False)
-            for j, s in enumerate(group):
-                sl = (slice(s[0], s[0] + P[0]), slice(s[1], s[1] + P[1]), slice(s[2], s[2] + P[2]))
-                softmax_np[sl] += softmax[j]
-                weight_np[sl] += 1.0
-        label_np = np.argmax(softmax_np, axis=-1)  # model.py:934 (un-normalised sums)
+        # window loop, softmax accumulation and final argmax run on the device (vnb_evaluate_volume)
+        label_np, softmax_np, weight_np = self.engine.evaluate_volume(images_np, S, self.evaluate_batch)
         crop = tuple(slice(0, d) for d in dims)
         return label_np[crop], softmax_np[crop], weight_np[crop]
 
