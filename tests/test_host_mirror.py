@@ -123,3 +123,47 @@ def test_nifti_dataset_patch_contract(tmp_path):
     assert label.shape == (16, 16, 16) and label.dtype == np.int32 and set(np.unique(label)) <= {0, 1}
     assert label.sum() > 0  # ConfidenceCrop2 centred on the labelled component
     assert -1 <= image.min() and image.max() <= 256
+
+
+def test_native_inference_driver_matches_the_python_evaluator(emul_lib, tmp_path):
+    """cxx/vnb_infer.cpp (C++ over the C ABI, the counterpart of the reference's cxx/ program) on the emulated library:
+    same label volume as image2label.evaluate_single_3D for the same weights, case, stride and batch."""
+    from tests.conftest import EMUL_LIB
+    _native_driver_case(emul_lib, EMUL_LIB, "fp32", tmp_path)
+
+
+@pytest.mark.gpu
+def test_native_inference_driver_on_the_gpu(gpu_lib, tmp_path):
+    _native_driver_case(gpu_lib, gpu_lib.path, "bf16x3", tmp_path)
+
+
+def _native_driver_case(lib, lib_path, precision, tmp_path):
+    import subprocess
+    from tests.conftest import ROOT
+    from vnet_tensorflow_b200.engine import VNetEngine
+    exe = tmp_path / "vnb_infer"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "cxx", "vnb_infer.cpp"), "-ldl"], check=True)
+    P, B, K = (8, 8, 8), 2, 3
+    eng = VNetEngine(num_classes=K, in_channels=2, patch_shape=P, max_batch=B, num_channels=16, num_levels=2,
+                     num_convolutions=(1, 1), bottom_convolutions=1, precision=precision, library=lib)
+    spec = R.VNetSpec(num_classes=K, in_channels=2, num_channels=16, num_levels=2, num_convolutions=(1, 1), bottom_convolutions=1)
+    eng.set_params(R.init_params(spec, 11))
+    checkpoint.export_binary(eng, str(tmp_path / "w.vnbw"))
+    rng = np.random.default_rng(5)
+    a = rng.uniform(-1200, 1500, (11, 6, 9)).astype(np.float32)     # smaller than the patch along y: padded
+    b = rng.integers(0, 255, (11, 6, 9)).astype(np.int16)
+    nifti.write(str(tmp_path / "a.nii"), nifti.Image(a, (0.5, 0.5, 2.0), (1.0, 2.0, 3.0)))
+    nifti.write(str(tmp_path / "b.nii"), nifti.Image(b))
+    subprocess.run([str(exe), "--lib", lib_path, "--weights", str(tmp_path / "w.vnbw"), "--image", str(tmp_path / "a.nii"),
+                    "--image", str(tmp_path / "b.nii"), "--out", str(tmp_path / "label.nii"), "--patch", "8", "8", "8",
+                    "--stride", "3", "4", "8", "--batch", str(B), "--classes", str(K), "--labels", "0", "5", "9",
+                    "--precision", precision, "--channels", "16", "--levels", "2", "--convs", "1", "1", "--bottom", "1"], check=True)
+    out = nifti.read(str(tmp_path / "label.nii"))
+    vol = np.stack([a, b.astype(np.float32)], -1)
+    vol = np.pad(vol, [(0, 0), (0, 2), (0, 0), (0, 0)])
+    lab, _, _ = eng.evaluate_volume(vol, (3, 4, 8), B)
+    want = np.asarray([0, 5, 9], np.int32)[lab[:, :6, :]]
+    assert out.array.shape == (11, 6, 9) and out.array.dtype == np.int32
+    assert np.array_equal(out.array, want)
+    assert out.spacing == (0.5, 0.5, 2.0) and out.origin == (1.0, 2.0, 3.0)
+    eng.close()

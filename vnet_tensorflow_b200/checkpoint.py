@@ -57,3 +57,20 @@ def restore(engine, prefix: str):
         epoch = int(z["start_epoch"][0]) if "start_epoch" in z else 0
     engine.global_step = step
     return step, epoch
+
+
+def export_binary(engine, path: str) -> str:
+    """Flat binary dump of the model variables for the native driver (cxx/vnb_infer.cpp), the role of the
+    reference's meta_to_pb.py (frozen `nWeights` assigns consumed by cxx/tf_inference.cpp:110-144):
+    "VNBW" u32 version=1 u32 count, then per variable u32 name length, name (TF variable name), u32 ndim,
+    i64 dims[ndim], float32 data."""
+    import struct
+    names = list(engine.variables().items())
+    with open(path, "wb") as f:
+        f.write(b"VNBW" + struct.pack("<II", 1, len(names)))
+        for name, _ in names:
+            a = np.ascontiguousarray(engine.get_param(name), np.float32)
+            nb = name.encode()
+            f.write(struct.pack("<I", len(nb)) + nb + struct.pack("<I", a.ndim) + struct.pack("<%dq" % a.ndim, *a.shape))
+            f.write(a.tobytes())
+    return path
