@@ -151,8 +151,9 @@ inline void Engine::tc_run_dgrad(Unit& u, int N) {
 }
 
 inline void Engine::tc_run_wgrad(Unit& u, int N) {
-  ProfScope ps(*this, 1, conv5_flops(u, N));
-  wg_launch(u.tc.wgrad, N, cfg_.precision == PREC_BF16X3, wg_partial_, grads_ + u.w_off, stream_, u.Cin1 + u.Cin2);
+  cudaStream_t st = wgrad_stream_begin();
+  ProfScope ps(*this, 1, conv5_flops(u, N), st);
+  wg_launch(u.tc.wgrad, N, cfg_.precision == PREC_BF16X3, wg_partial_, grads_ + u.w_off, st, u.Cin1 + u.Cin2);
   launches_ += 2;
 }
 

@@ -114,12 +114,32 @@ class Engine {
   explicit Engine(const EngineConfig& cfg) : cfg_(cfg) {
     validate();
     VNB_CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+#ifndef VNB_EMULATE
+    // Filter gradients are off the critical path of the backward pass (nothing downstream reads them before the
+    // optimiser): they run on a second, lower-priority stream so that the HBM-bound batch-norm / 2x2x2 passes of the
+    // following units share the SMs with the tensor-bound filter-gradient kernel.  VNB_WGRAD_STREAM=0 disables it.
+    const char* ws = getenv("VNB_WGRAD_STREAM");
+    if (!(ws && ws[0] == '0') && cfg_.precision != PREC_FP32) {
+      int least = 0, greatest = 0;
+      VNB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      VNB_CUDA_OK(cudaStreamCreateWithPriority(&wg_stream_, cudaStreamNonBlocking, least));
+      VNB_CUDA_OK(cudaEventCreateWithFlags(&wg_ready_ev_, cudaEventDisableTiming));
+      VNB_CUDA_OK(cudaEventCreateWithFlags(&wg_done_ev_, cudaEventDisableTiming));
+    }
+#endif
     build_graph();
     allocate();
     init_default_params();
   }
   ~Engine() {
     for (void* p : allocs_) cudaFree(p);
+#ifndef VNB_EMULATE
+    if (wg_stream_) {
+      cudaStreamDestroy(wg_stream_);
+      cudaEventDestroy(wg_ready_ev_);
+      cudaEventDestroy(wg_done_ev_);
+    }
+#endif
     cudaStreamDestroy(stream_);
   }
 
@@ -407,7 +427,8 @@ class Engine {
   struct ProfScope {  // brackets one kernel launch with events when profiling is on
     Engine& e;
     long long idx = -1;
-    ProfScope(Engine& eng, int cls, double flops) : e(eng) {
+    cudaStream_t st;
+    ProfScope(Engine& eng, int cls, double flops, cudaStream_t stream = 0) : e(eng), st(stream ? stream : eng.stream_) {
 #ifndef VNB_EMULATE
       if (!e.profiling_) return;
       if (e.prof_used_ == e.prof_.size()) {
@@ -419,7 +440,7 @@ class Engine {
       idx = static_cast<long long>(e.prof_used_++);
       e.prof_[idx].cls = cls;
       e.prof_[idx].flops = flops;
-      cudaEventRecord(e.prof_[idx].a, e.stream_);
+      cudaEventRecord(e.prof_[idx].a, st);
 #else
       (void)cls;
       (void)flops;
@@ -427,7 +448,7 @@ class Engine {
     }
     ~ProfScope() {
 #ifndef VNB_EMULATE
-      if (idx >= 0) cudaEventRecord(e.prof_[idx].b, e.stream_);
+      if (idx >= 0) cudaEventRecord(e.prof_[idx].b, st);
 #endif
     }
   };
@@ -1154,9 +1175,35 @@ class Engine {
       if (u.kind != U_ADD) run_conv_backward(u, N);
       notify_bucket(ui);
     }
+    join_wgrad_stream();   // the optimiser (and the next step's passes) read what the filter-gradient stream wrote
+  }
+  // stream on which the filter gradient of the current unit is launched: the side stream, ordered after everything
+  // the main stream has enqueued so far (dz and its bf16 copies are complete)
+  cudaStream_t wgrad_stream_begin() {
+#ifndef VNB_EMULATE
+    if (wg_stream_) {
+      VNB_CUDA_OK(cudaEventRecord(wg_ready_ev_, stream_));
+      VNB_CUDA_OK(cudaStreamWaitEvent(wg_stream_, wg_ready_ev_, 0));
+      wg_pending_ = true;
+      return wg_stream_;
+    }
+#endif
+    return stream_;
+  }
+  void join_wgrad_stream() {
+#ifndef VNB_EMULATE
+    if (wg_stream_ && wg_pending_) {
+      VNB_CUDA_OK(cudaEventRecord(wg_done_ev_, wg_stream_));
+      VNB_CUDA_OK(cudaStreamWaitEvent(stream_, wg_done_ev_, 0));
+      wg_pending_ = false;
+    }
+#endif
   }
   void notify_bucket(int ui) {
     if (!grad_hook_) return;
+    bool any = false;
+    for (size_t b = 0; b < buckets_.size(); ++b) any = any || buckets_[b].unit_lo == ui;
+    if (any) join_wgrad_stream();   // the all-reduce of a bucket waits on the main stream only
     for (size_t b = 0; b < buckets_.size(); ++b)
       if (buckets_[b].unit_lo == ui) grad_hook_(static_cast<int>(b));
   }
@@ -1432,6 +1479,11 @@ class Engine {
 
   EngineConfig cfg_;
   cudaStream_t stream_ = 0;
+  cudaStream_t wg_stream_ = 0;   // filter-gradient side stream (null: everything on stream_)
+#ifndef VNB_EMULATE
+  cudaEvent_t wg_ready_ev_ = nullptr, wg_done_ev_ = nullptr;
+#endif
+  bool wg_pending_ = false;
   std::vector<ParamEntry> entries_;
   std::map<std::string, size_t> index_;
   std::vector<Act> acts_;
