@@ -104,7 +104,9 @@ def roofline_block(precision, peaks, fd_ms, fd_n, fd_fl, wg_ms, wg_n, wg_fl, pro
         "all_conv5_tflops": (fd_fl + wg_fl) / ((fd_ms + wg_ms) * 1e-3) / 1e12 if fd_ms + wg_ms > 0 else 0.0,
         "conv_share_of_step": (fd_ms + wg_ms) / max(prof_steps, 1) / ms_per_step,
         "whole_step_tflops_per_gpu": step_tflops,
-        "method": "CUDA events around every 5^3 convolution launch on the engine stream, %d profiled steps" % prof_steps,
+        "method": "CUDA events around every 5^3 convolution launch on the engine stream, %d profiled steps after the "
+                  "timed region (filter gradients serialised on the main stream while profiling, so every launch is "
+                  "timed alone; in the timed steps they overlap the following units on a side stream)" % prof_steps,
     }
 
 
@@ -365,6 +367,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
 
 
 def main():
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION on some hosts) out of it
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

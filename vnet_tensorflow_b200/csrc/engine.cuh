@@ -1181,7 +1181,7 @@ class Engine {
   // the main stream has enqueued so far (dz and its bf16 copies are complete)
   cudaStream_t wgrad_stream_begin() {
 #ifndef VNB_EMULATE
-    if (wg_stream_) {
+    if (wg_stream_ && !profiling_) {   // per-kernel profiling times every launch alone on the main stream
       VNB_CUDA_OK(cudaEventRecord(wg_ready_ev_, stream_));
       VNB_CUDA_OK(cudaStreamWaitEvent(wg_stream_, wg_ready_ev_, 0));
       wg_pending_ = true;
