@@ -78,9 +78,8 @@ inline bool mbar_try_wait(uint32_t bar, uint32_t parity) { return st().bars.at(b
 inline void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) emul::yield_wait();
 }
-inline bool mbar_test(uint32_t bar, uint32_t parity) { return mbar_try_wait(bar, parity); }
-inline void mbar_wait_warp(uint32_t bar, uint32_t parity, bool ready = false) {
-  if (!ready) mbar_wait(bar, parity);
+inline void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  mbar_wait(bar, parity);
   __syncwarp();
 }
 inline bool mbar_wait_bounded(uint32_t bar, uint32_t parity, uint32_t) {

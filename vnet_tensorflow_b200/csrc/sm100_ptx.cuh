@@ -125,27 +125,14 @@ __device__ __forceinline__ bool elect_one() {
 // tell the compiler a value is warp-uniform (same idiom as a canonical warp index)
 __device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 
-// Non-blocking look at a barrier phase.  The role warps issue it one pipeline stage early and consume the result a
-// stage later, which takes the ~100-cycle round trip of a barrier query off the per-stage critical path.
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 // Barrier wait of a whole role warp: every lane polls the barrier (all lanes observe the same phase in the same
 // instruction) and the warp reconverges before it goes on, so the loop state stays warp-uniform and the
-// asynchronous instructions that follow are issued once, from converged code.  `ready` = an earlier mbar_test of
-// the same phase already succeeded.
-__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, bool ready = false) {
-  if (!ready) mbar_wait(bar, parity);
+// asynchronous instructions that follow are issued once, from converged code.  (Two things that were tried and do
+// not work: a leader-only wait followed by __syncwarp -- the warp can stay split and the uniform-datapath instructions
+// then execute once per fragment; and a look-ahead mbarrier.test_wait of the next stage -- the predicate is consumed
+// by the selp inside the same asm block, so the ~150-cycle query latency lands on the issue path anyway.)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  mbar_wait(bar, parity);
   __syncwarp();
 }
 
@@ -231,68 +218,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 
 
 // ----------------------------------------------------------------------------------------------
-// issue-by-one-lane forms.  The role warps run their loops converged; the lane with pred != 0 issues.
-// VNB_ISSUE_PREDICATED_ASM selects instruction-level predication inside the asm block (ptxas then moves every
-// operand with `@p R2UR.BROADCAST`, a cross-lane operation per register); the default is a plain branch around the
-// instruction, for which ptxas keeps the warp-uniform operands in uniform registers or moves them with plain R2UR.
+// issue-by-one-lane forms.  The role warps run their loops converged; the lane with pred != 0 issues, through a plain
+// branch around the instruction: ptxas then keeps the warp-uniform operands in uniform registers.  (Predicating the
+// instruction inside the asm block instead makes ptxas move every operand with `@p R2UR.BROADCAST`, a cross-lane
+// operation per register; issuing from inside `if (lane == 0)` loops wraps every instruction in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall.)
 // ----------------------------------------------------------------------------------------------
-#ifdef VNB_ISSUE_PREDICATED_ASM
-__device__ __forceinline__ void mma_f16_ss_if(bool pred, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                              uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(pred))
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit_if(bool pred, uint32_t bar) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}" ::"r"(bar),
-      "r"(static_cast<uint32_t>(pred))
-      : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_if(bool pred, uint32_t bar, uint32_t bytes) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
-      "}" ::"r"(bar),
-      "r"(bytes), "r"(static_cast<uint32_t>(pred))
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_if(bool pred, uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t"
-      "}" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(static_cast<uint32_t>(pred))
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_5d_if(bool pred, uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
-                                               int c3, int c4) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %8, 0;\n\t"
-      "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n\t"
-      "}" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
-      "r"(static_cast<uint32_t>(pred))
-      : "memory");
-}
-
-#else
 __device__ __forceinline__ void mma_f16_ss_if(bool pred, uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                               uint32_t accumulate) {
   if (pred) mma_f16_ss(d_tmem, adesc, bdesc, idesc, accumulate);
@@ -310,7 +241,6 @@ __device__ __forceinline__ void tma_load_5d_if(bool pred, uint32_t dst, const vo
                                                int c3, int c4) {
   if (pred) tma_load_5d(dst, tmap, bar, c0, c1, c2, c3, c4);
 }
-#endif
 
 }  // namespace sm100
 #endif  // VNB_EMULATE
