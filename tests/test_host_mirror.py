@@ -125,6 +125,37 @@ def test_nifti_dataset_patch_contract(tmp_path):
     assert -1 <= image.min() and image.max() <= 256
 
 
+def test_parallel_patch_pipeline_keeps_order_and_propagates_errors(tmp_path):
+    """get_dataset(num_parallel_calls=N): same patches in the same order as the sequential map; prefetch_iter hands
+    items through unchanged and re-raises producer errors in the consumer."""
+    rng = np.random.default_rng(2)
+    for c in range(5):
+        os.makedirs(tmp_path / str(c))
+        img = rng.normal(50 + 10 * c, 5, (12, 10, 9)).astype(np.float32)
+        lab = np.zeros((12, 10, 9), np.int16)
+        lab[2:6, 3:7, 1:5] = 1
+        nifti.write(str(tmp_path / str(c) / "image.nii"), nifti.Image(img))
+        nifti.write(str(tmp_path / str(c) / "label.nii"), nifti.Image(lab))
+    tfm = [NiftiDataset3D.ManualNormalization(0, 100), NiftiDataset3D.Padding((16, 16, 16))]
+    mk = lambda: NiftiDataset3D.NiftiDataset(str(tmp_path), ["image.nii"], "label.nii", tfm, train=True, labels=[0, 1])
+    seq = list(mk().get_dataset())
+    par = list(mk().get_dataset(num_parallel_calls=3, prefetch=4))
+    assert len(seq) == len(par) == 5
+    for (a, la), (b, lb) in zip(seq, par):
+        assert np.array_equal(a, b) and np.array_equal(la, lb)
+    assert list(NiftiDataset3D.prefetch_iter(iter(range(7)), depth=2)) == list(range(7))
+
+    def boom():
+        yield 1
+        raise ValueError("broken case")
+    it = NiftiDataset3D.prefetch_iter(boom(), depth=2)
+    assert next(it) == 1
+    with pytest.raises(ValueError):
+        next(it)
+    with pytest.raises(ZeroDivisionError):
+        list(NiftiDataset3D.parallel_map(lambda x: 1 // x, [1, 0, 2], workers=2))
+
+
 def test_native_inference_driver_matches_the_python_evaluator(emul_lib, tmp_path):
     """cxx/vnb_infer.cpp (C++ over the C ABI, the counterpart of the reference's cxx/ program) on the emulated library:
     same label volume as image2label.evaluate_single_3D for the same weights, case, stride and batch."""

@@ -4,7 +4,8 @@ None of the JSON files shipped with the reference loads cleanly with the referen
 (`NumCovolutions` vs `NumConvolutions`, missing `MaxIterations` / `TestStep` / `Pipeline`,
 `LargestConnectedComponent`, `VolumeThreshold`, ...).  This loader accepts both spellings and applies
 the documented defaults (networks.py:213-216), and adds optional keys for the B200 engine:
-`TrainingSetting.Precision` ("fp32" | "bf16x3" | "bf16") and `TrainingSetting.Synthetic`.
+`TrainingSetting.Precision` ("fp32" | "bf16x3" | "bf16"), `TrainingSetting.Synthetic` and
+`TrainingSetting.DataWorkers` (patch-pipeline threads; the reference maps with num_parallel_calls=1).
 """
 from __future__ import annotations
 
@@ -63,6 +64,7 @@ class Config:
     training_pipeline: Optional[str] = None
     precision: str = "bf16x3"
     synthetic: bool = False
+    data_workers: int = 4
     # evaluation (model.py:227-241)
     checkpoint_path: str = "./tmp/ckpt/checkpoint-latest"
     evaluate_data_dir: str = "./data/evaluate"
@@ -126,6 +128,7 @@ def from_dict(cfg: dict) -> Config:
     c.training_pipeline = _get(t, "Pipeline", default=None)
     c.precision = _get(t, "Precision", default="bf16x3")
     c.synthetic = bool(_get(t, "Synthetic", default=False))
+    c.data_workers = max(1, int(_get(t, "DataWorkers", default=4)))
     ed = e.get("Data", {})
     c.checkpoint_path = _get(e, "CheckpointPath", default=c.checkpoint_path)
     c.evaluate_data_dir = _get(ed, "EvaluateDataDirectory", default=c.evaluate_data_dir)

@@ -77,13 +77,16 @@ class image2label(object):
         if usable:
             ds = NiftiDataset3D.NiftiDataset(data_dir=data_dir, image_filenames=self.image_filenames,
                                              label_filename=self.label_filename, transforms=transforms, train=train,
-                                             labels=self.label_classes).get_dataset()
+                                             labels=self.label_classes).get_dataset(num_parallel_calls=self.cfg.data_workers)
         else:
             print("{}: no readable NIfTI data in {} -- using synthetic patches".format(_now(), data_dir))
             ds = NiftiDataset3D.SyntheticDataset(self.patch_shape, self.input_channel_num, self.output_channel_num,
                                                  size=4 * self.batch_size, seed=0 if train else 10 ** 6).get_dataset()
 
         def batches():
+            return NiftiDataset3D.prefetch_iter(_batches(), depth=2)
+
+        def _batches():
             buf: List = []
             it = iter(ds)
             pending = []

@@ -56,13 +56,16 @@ class NiftiDataset(object):
         image_np = np.stack([np.asarray(im.array, np.float32) for im in sample['image']], axis=-1)
         return image_np.astype(np.float32), remapped
 
-    def get_dataset(self):
+    def get_dataset(self, num_parallel_calls=1, prefetch=None):
+        """NiftiDataset3D.py:39-55.  The reference maps `input_parser` through tf.py_func with
+        num_parallel_calls=1 (one SimpleITK pipeline at a time); here `num_parallel_calls` cases are parsed
+        concurrently (NumPy / SciPy release the GIL in the resampling and filtering kernels) and handed out in the
+        original order, at most `prefetch` cases ahead of the consumer."""
         ds = self
 
         class _Iterable:
             def __iter__(self_inner):
-                for case in ds.case_dirs():
-                    yield ds.input_parser(case)
+                return parallel_map(ds.input_parser, ds.case_dirs(), num_parallel_calls, prefetch)
 
             def __len__(self_inner):
                 return len(ds.case_dirs())
@@ -70,6 +73,68 @@ class NiftiDataset(object):
         self.dataset = _Iterable()
         self.data_size = len(self.case_dirs())
         return self.dataset
+
+
+def parallel_map(fn, items, workers=1, depth=None):
+    """Order-preserving map over `items` on a thread pool with a bounded look-ahead window."""
+    workers = max(1, int(workers))
+    if workers == 1:
+        for item in items:
+            yield fn(item)
+        return
+    from collections import deque
+    from concurrent.futures import ThreadPoolExecutor
+    depth = max(workers, int(depth)) if depth else 2 * workers
+    pending = deque()
+    ex = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="vnb-data")
+    try:
+        for item in items:
+            pending.append(ex.submit(fn, item))
+            if len(pending) >= depth:
+                yield pending.popleft().result()
+        while pending:
+            yield pending.popleft().result()
+    finally:
+        for f in pending:
+            f.cancel()
+        ex.shutdown(wait=True)
+
+
+def prefetch_iter(iterable, depth=2):
+    """Runs `iterable` on a background thread, `depth` items ahead: batch assembly and file I/O of the next step
+    overlap the (GIL-free) engine call of the current one."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=max(1, int(depth)))
+    end, stop = object(), threading.Event()
+
+    def work():
+        try:
+            for item in iterable:
+                while not stop.is_set():
+                    try:
+                        q.put(item, timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+                if stop.is_set():
+                    return
+            q.put(end)
+        except BaseException as e:  # re-raised in the consumer
+            q.put(e)
+
+    t = threading.Thread(target=work, name="vnb-prefetch", daemon=True)
+    t.start()
+    try:
+        while True:
+            item = q.get()
+            if item is end:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
 
 
 class SyntheticDataset(object):
