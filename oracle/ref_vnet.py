@@ -4,11 +4,16 @@ This module is the *checker*, never the product: only ``tests/``, ``__graft_entr
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The product path
 (``vnet_tensorflow_b200``) never routes through it and fails loudly without its CUDA library.
 
-PARITY UNPINNED: the reference ships no tests, no golden vectors and no runnable TensorFlow in this
-environment.  This restatement therefore follows the reference *source* line by
-line (citations below) plus the documented TensorFlow-1.15 op semantics (SAME padding, training-mode
-batch norm with biased variance, conv3d_transpose = input-gradient of conv3d, Adam epsilon-hat form,
-non-staircase exponential decay).  Its own self-checks (fp64 finite differences, structural
+PINNING.  The reference ships no tests and no golden vectors, and TensorFlow cannot run in this environment
+(SURVEY.md §4, §8c), so the numerics of TensorFlow's own kernels stay UNPINNED: every op below follows the
+documented TensorFlow-1.15 semantics (SAME padding, training-mode batch norm with biased variance,
+conv3d_transpose = input-gradient of conv3d, Adam epsilon-hat form, non-staircase exponential decay).
+What IS pinned is the graph the reference builds: ``tests/golden/make_reference_fixtures.py`` imports the
+reference's own ``networks.py`` / ``layers2.py`` / ``VNet.py`` / ``Layers.py`` / ``attention.py`` /
+``OutputModule.py`` unmodified (and compiles ``dice_coe`` out of ``model.py`` / ``train.py``), executes them over an
+eager stand-in for the ~30 TF symbols they touch (``tests/tf1_shim.py``) and stores logits, losses, every gradient,
+the UPDATE_OPS moving statistics and the variable names in creation order; ``tests/test_reference_pin.py`` holds this
+restatement to those vectors (1e-9 on tensors in fp64).  Further self-checks (fp64 finite differences, structural
 invariances, analytic Dice cases) live in ``tests/test_oracle.py``.
 
 Reference files restated (paths relative to /root/reference):
