@@ -92,3 +92,35 @@ def test_attention_path_matches_the_reference_modules():
     assert abs(float(seg) - float(ref["seg_loss"])) < 1e-6
     assert abs(float(total) - float(ref["total_loss"])) < 1e-6
     _check_gradients(grads, ref, 2e-6)
+
+
+@pytest.mark.parametrize("name", ["m1_k2_c12", "legacy_m1_k2_c12"])
+def test_cuda_engine_sources_match_the_reference_code(emul_lib, name):
+    """The product's kernel + engine sources (compiled for the CPU, tests/emul) against the vectors computed by the
+    reference's own code -- the same comparison the GPU suite makes against the oracle, one link shorter."""
+    from vnet_tensorflow_b200.engine import VNetEngine
+    kw, M, P, N, loss_type, weights = CASES[name]
+    legacy = name.startswith("legacy_")
+    spec = R.VNetSpec(in_channels=M, flavour="legacy" if legacy else "networks", **kw)
+    params = perturbed_params(spec)
+    img, lab = synth_batch(0, N, P, M, kw["num_classes"])
+    with np.load(os.path.join(GOLDEN, "ref_%s.npz" % name)) as z:
+        ref = {k: z[k] for k in z.files}
+    eng = VNetEngine(num_classes=kw["num_classes"], in_channels=M, patch_shape=(P, P, P), max_batch=N,
+                     num_channels=kw["num_channels"], num_levels=kw["num_levels"], num_convolutions=kw["num_convolutions"],
+                     bottom_convolutions=kw["bottom_convolutions"], precision="fp32", loss=_loss_name(loss_type, weights),
+                     loss_weights=weights, flavour="legacy" if legacy else "networks", library=emul_lib)
+    assert list(eng.variables().keys()) == list(ref["variable_names"])   # TF names, TF creation order
+    eng.set_params(params)
+    loss = eng.forward_backward(img, lab)
+    logits, _, _ = eng.forward(img)
+    assert np.abs(logits - ref["logits"]).max() <= 2e-4 * np.abs(ref["logits"]).max()
+    assert abs(loss - float(ref["loss"])) < 1e-5
+    grads = eng.get_grads()
+    gscale = max(float(ref[k]) for k in ref if k.startswith("gnorm/"))
+    for k, g in grads.items():
+        if k.endswith("biases"):   # analytically zero (every convolution feeds a batch-statistics norm, SURVEY R9)
+            continue
+        norm = float(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        assert abs(norm - float(ref["gnorm/" + k])) <= 2e-3 * gscale, k
+    eng.close()
