@@ -55,14 +55,42 @@ def grad_digest(g):
     return np.float64(np.sqrt((a ** 2).sum())), np.float64(a.sum()), a[::step][:512].astype(np.float32)
 
 
-def reference_dice_coe(tf, module="model.py"):
-    """`dice_coe` exactly as written in model.py:26-85 (or train.py:100-149), compiled from the reference file."""
+def reference_function(tf, name, module="model.py"):
+    """A top-level function exactly as written in the reference file, compiled on its own (the files themselves
+    cannot be imported: SimpleITK / NiftiDataset imports at module level)."""
     src = open(os.path.join(REFERENCE, module)).read()
     tree = ast.parse(src)
-    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "dice_coe"][0]
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name][0]
     ns = {"tf": tf}
-    exec(compile(ast.Module(body=[fn], type_ignores=[]), os.path.join(REFERENCE, "model.py"), "exec"), ns)
-    return ns["dice_coe"]
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), os.path.join(REFERENCE, module), "exec"), ns)
+    return ns[name]
+
+
+def reference_dice_coe(tf, module="model.py"):
+    """`dice_coe` of model.py:26-85 (or train.py:100-149)."""
+    return reference_function(tf, "dice_coe", module)
+
+
+def run_reference_losses(dtype=torch.float64):
+    """model.py:26-92 on random inputs: dice_coe in all four forms and weighted_softmax_cross_entropy_with_logits."""
+    rng = np.random.default_rng(5)
+    K, shape = 3, (2, 5, 4, 3)
+    logits = rng.normal(0, 2, shape + (K,))
+    labels = rng.integers(0, K, shape)
+    weights = [0.01, 0.1, 1.0]
+    tf1_shim.uninstall()
+    tf = tf1_shim.install({}, dtype)
+    sm = tf.nn.softmax(tf1_shim.T(torch.from_numpy(logits).to(dtype)))
+    oh = tf.one_hot(tf1_shim.T(torch.from_numpy(labels)), K)
+    dice = reference_dice_coe(tf)
+    out = {"logits": logits, "labels": labels, "weights": np.asarray(weights)}
+    for kind in ("sorensen", "jaccard"):
+        out["dice_" + kind] = np.float64(dice(sm, oh, loss_type=kind).v)
+        out["dice_weighted_" + kind] = np.float64(dice(sm, oh, loss_type=kind, weights=list(weights)).v)
+    wx = reference_function(tf, "weighted_softmax_cross_entropy_with_logits")
+    out["weighted_xent"] = np.float64(wx(oh, tf1_shim.T(torch.from_numpy(logits).to(dtype)), weights).v)
+    tf1_shim.uninstall()
+    return out
 
 
 def run_reference(kw, in_channels, P, N, loss_type, weights, dtype=torch.float64, legacy=False):
@@ -163,6 +191,7 @@ def run_reference_attention(dtype=torch.float64):
 
 
 def main():
+    np.savez_compressed(os.path.join(HERE, "ref_losses.npz"), **run_reference_losses())
     spec, params, img, lab, dist, out = run_reference_attention()
     np.savez_compressed(os.path.join(HERE, "ref_attention_k2.npz"), **out)
     print("attention_k2 variables", len(out["variable_names"]), "total loss", float(out["total_loss"]))

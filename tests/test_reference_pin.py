@@ -124,3 +124,17 @@ def test_cuda_engine_sources_match_the_reference_code(emul_lib, name):
         norm = float(np.sqrt((g.astype(np.float64) ** 2).sum()))
         assert abs(norm - float(ref["gnorm/" + k])) <= 2e-3 * gscale, k
     eng.close()
+
+
+def test_loss_functions_match_model_py():
+    """model.py:26-92 (`dice_coe` in its four forms, `weighted_softmax_cross_entropy_with_logits`) compiled from the
+    reference file and run on random inputs, against the oracle's restatements."""
+    with np.load(os.path.join(GOLDEN, "ref_losses.npz")) as z:
+        ref = {k: z[k] for k in z.files}
+    logits = torch.from_numpy(ref["logits"])
+    lab = torch.from_numpy(ref["labels"])
+    w = tuple(float(x) for x in ref["weights"])
+    for name in ("sorensen", "jaccard", "weighted_sorensen", "weighted_jaccard"):
+        loss = R.loss_from_logits(logits, lab, name, w)
+        assert abs((1.0 - float(loss)) - float(ref["dice_" + name])) < 1e-8, name
+    assert abs(float(R.loss_from_logits(logits, lab, "weighted_xent", w)) - float(ref["weighted_xent"])) < 1e-8

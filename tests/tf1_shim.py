@@ -154,7 +154,11 @@ def install(params, dtype=torch.float64):
     tf.name_scope, tf.Variable, tf.pad = name_scope, Variable, pad
     tf.truncated_normal = lambda shape, mean=0.0, stddev=1.0: ("init", _shape_tuple(shape))
     tf.zeros = lambda shape: ("init", _shape_tuple(shape))
-    tf.constant = lambda value, dtype=None, shape=None: (np.asarray(value) if np.ndim(value) else T(torch.tensor(float(value), dtype=st.dtype)))
+    def constant(value, dtype=None, shape=None):
+        a = np.asarray(value)
+        return T(torch.as_tensor(a) if a.dtype.kind in "iu" else torch.as_tensor(a.astype(np.float64)).to(st.dtype))
+
+    tf.constant = constant
     tf.multiply = lambda a, b: T(_unwrap(a) * _unwrap(b))
 
     def get_variable(name, shape=None, dtype=None, initializer=None, trainable=True):
@@ -277,6 +281,8 @@ def install(params, dtype=torch.float64):
     nn.relu = lambda x: T(torch.relu(_unwrap(x)))
     nn.leaky_relu = lambda x, alpha=0.2: T(torch.nn.functional.leaky_relu(_unwrap(x), alpha))
     nn.softmax = lambda x, name=None: T(torch.softmax(_unwrap(x), dim=-1))
+    nn.softmax_cross_entropy_with_logits = lambda labels=None, logits=None: T(
+        -(_unwrap(labels) * torch.log_softmax(_unwrap(logits), dim=-1)).sum(dim=-1))
     tf.nn = nn
 
     # ---- tf.layers ----------------------------------------------------------------------------------------------
