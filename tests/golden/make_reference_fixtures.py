@@ -87,6 +87,17 @@ def run_reference_losses(dtype=torch.float64):
     for kind in ("sorensen", "jaccard"):
         out["dice_" + kind] = np.float64(dice(sm, oh, loss_type=kind).v)
         out["dice_weighted_" + kind] = np.float64(dice(sm, oh, loss_type=kind, weights=list(weights)).v)
+    # layers2.py:4-30: the reference's own initialisers (NumPy global RNG, seeded here only to make the file stable)
+    sys.path.insert(0, REFERENCE)
+    try:
+        layers2 = importlib.import_module("layers2")
+        np.random.seed(0)
+        out["xavier_5x5x5x16x32"] = layers2.xavier_initializer_convolution([5, 5, 5, 16, 32]).astype(np.float32)[::7, 0, 0, 0, 0]
+        out["xavier_5x5x5x16x32_absmax"] = np.float64(np.abs(layers2.xavier_initializer_convolution([5, 5, 5, 16, 32])).max())
+        out["xavier_2x2x2x32x16_absmax"] = np.float64(np.abs(layers2.xavier_initializer_convolution([2, 2, 2, 32, 16])).max())
+        out["constant_init"] = layers2.constant_initializer(0, shape=7)
+    finally:
+        sys.path.remove(REFERENCE)
     wx = reference_function(tf, "weighted_softmax_cross_entropy_with_logits")
     out["weighted_xent"] = np.float64(wx(oh, tf1_shim.T(torch.from_numpy(logits).to(dtype)), weights).v)
     tf1_shim.uninstall()

@@ -138,3 +138,10 @@ def test_loss_functions_match_model_py():
         loss = R.loss_from_logits(logits, lab, name, w)
         assert abs((1.0 - float(loss)) - float(ref["dice_" + name])) < 1e-8, name
     assert abs(float(R.loss_from_logits(logits, lab, "weighted_xent", w)) - float(ref["weighted_xent"])) < 1e-8
+    # layers2.py:4-30 initialisers: uniform in +-sqrt(6 / (patch volume * (Cin + Cout))), zeros for the biases
+    for key, shape in (("xavier_5x5x5x16x32_absmax", (5, 5, 5, 16, 32)), ("xavier_2x2x2x32x16_absmax", (2, 2, 2, 32, 16))):
+        lim = np.abs(R.xavier_uniform(shape, np.random.Generator(np.random.PCG64(0)))).max()
+        bound = np.sqrt(6.0 / (np.prod(shape[:3]) * (shape[3] + shape[4])))
+        assert lim <= bound + 1e-7 and float(ref[key]) <= bound + 1e-7
+        assert lim > 0.999 * bound and float(ref[key]) > 0.999 * bound
+    assert ref["constant_init"].shape == (7,) and not ref["constant_init"].any()
