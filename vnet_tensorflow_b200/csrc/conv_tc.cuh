@@ -12,9 +12,11 @@
 //     Cout = 16/32 layers (65 % of the FLOPs) becomes an N = 80/160 MMA.
 //   * accumulators stay in TMEM over all 25*Cin/KC k-steps; the epilogue re-aligns the 5 kw slices
 //     (y[w] = sum_kw D[w+kw-2][kw]) through shared memory, adds bias / residual and stores fp32.
-//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 = epilogue;
-//     4-stage smem ring (full/empty mbarriers), double-buffered TMEM (tmem_full/tmem_empty) so the
-//     epilogue of tile i overlaps the main loop of tile i+1; persistent CTAs, one per SM.
+//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 (and 6-9 in single-pass
+//     mode) = epilogue; the producer / issuer warps run their loops converged and one elected lane issues
+//     (sm100_ptx.cuh).  Shared-memory rings with full/empty mbarriers; TMEM is a ring of per-tile accumulator
+//     slots (tmem_full/tmem_empty per slot) so the epilogue of one item overlaps the main loop of the next;
+//     persistent CTAs, one per SM.
 //   * precision: bf16 operands, fp32 accumulate.  NSPLIT = 3 runs hi*hi + lo*hi + hi*lo on
 //     (hi, lo) bf16 splits of activations and weights = fp32-grade products ("bf16x3").
 #pragma once
