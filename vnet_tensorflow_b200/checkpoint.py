@@ -1,10 +1,13 @@
 """Checkpoint save / restore with the reference's conventions (model.py:676-709,758-764,803-809).
 
 The reference writes TF bundle files `CheckpointDir/checkpoint-<global_step>.{meta,index,data-*}` and a
-`checkpoint-latest` state file through tf.train.Saver.  The TF bundle format cannot be produced without
-TensorFlow, so this module stores one `.npz` per checkpoint under the *same names and variable keys*
-(`vnet/encoder/level_1/conv_1/weights`, ..., Adam slots `<var>/Adam`, `<var>/Adam_1`, `global_step`,
-`start_epoch`) and keeps the `checkpoint-latest` pointer + `CheckpointPath` semantics.
+`checkpoint-latest` state file through tf.train.Saver.  The native format here is one `.npz` per checkpoint
+under the *same names and variable keys* (`vnet/encoder/level_1/conv_1/weights`, ..., Adam slots
+`<var>/Adam`, `<var>/Adam_1`, `global_step`, `start_epoch`) with the `checkpoint-latest` pointer +
+`CheckpointPath` semantics kept.  TF bundles themselves are read and written through tf_bundle.py
+(`format="tf"` / `"both"`, `TrainingSetting.CheckpointFormat`): `restore` takes either kind of prefix, so a
+run of the reference can be resumed or evaluated here, and `export_tf` writes the `.index` / `.data` pair
+the reference's Saver restores (its `.meta` graph file stays TensorFlow's to write).
 """
 from __future__ import annotations
 
@@ -13,14 +16,23 @@ from typing import Optional
 
 import numpy as np
 
-from . import _ffi
+from . import _ffi, tf_bundle
 
 LATEST = "checkpoint-latest"
+FORMATS = ("npz", "tf", "both")
+
+# The optimizer is built under tf.name_scope("training") (model.py:646): slot variables come from get_variable
+# under the primary's own scope (`<var>/Adam`), the two Adam accumulators are plain tf.Variables and take the scope.
+OPTIMIZER_SCOPE = "training/"
+_BETA1, _BETA2 = 0.9, 0.999  # tf.train.AdamOptimizer defaults, model.py:652
 
 
-def save(engine, ckpt_dir: str, global_step: int, start_epoch: int = 0) -> str:
-    os.makedirs(ckpt_dir, exist_ok=True)
-    prefix = os.path.join(ckpt_dir, "checkpoint-%d" % global_step)
+def _optimizer_name(engine) -> str:
+    code = int(engine.cfg.optimizer)
+    return next(k for k, v in _ffi.OPTIMIZERS.items() if v == code)
+
+
+def _npz_arrays(engine, global_step: int, start_epoch: int):
     arrays = {}
     for name, (_, trainable) in engine.variables().items():
         arrays[name] = engine.get_param(name)
@@ -29,7 +41,76 @@ def save(engine, ckpt_dir: str, global_step: int, start_epoch: int = 0) -> str:
             arrays[name + "/Adam_1"] = engine.get_param(name, _ffi.SLOT_ADAM_V)
     arrays["global_step"] = np.asarray(global_step, np.int64)
     arrays["start_epoch"] = np.asarray([start_epoch], np.int32)
-    np.savez(prefix + ".npz", **arrays)
+    return arrays
+
+
+def tf_variables(engine, global_step: int, start_epoch: int = 0):
+    """Every variable tf.train.Saver() would save for the reference's training graph, by TF name: the model
+    variables, the optimizer's slots (tf.train.{Adam,Momentum}Optimizer), `global_step` (int64 scalar,
+    model.py:299) and `start_epoch` (int32 [1], model.py:668)."""
+    opt = _optimizer_name(engine)
+    out = {}
+    for name, (_, trainable) in engine.variables().items():
+        out[name] = engine.get_param(name)
+        if not trainable:
+            continue
+        if opt == "Adam":
+            out[name + "/Adam"] = engine.get_param(name, _ffi.SLOT_ADAM_M)
+            out[name + "/Adam_1"] = engine.get_param(name, _ffi.SLOT_ADAM_V)
+        elif opt in ("Momentum", "NesterovMomentum"):
+            out[name + "/Momentum"] = engine.get_param(name, _ffi.SLOT_ADAM_M)
+    if opt == "Adam":  # beta^t accumulators: initialised to beta, multiplied by beta after every step
+        out[OPTIMIZER_SCOPE + "beta1_power"] = np.asarray(_BETA1 ** (int(global_step) + 1), np.float32)
+        out[OPTIMIZER_SCOPE + "beta2_power"] = np.asarray(_BETA2 ** (int(global_step) + 1), np.float32)
+    out["global_step"] = np.asarray(global_step, np.int64)
+    out["start_epoch"] = np.asarray([start_epoch], np.int32)
+    return out
+
+
+def export_tf(engine, prefix: str, global_step: int, start_epoch: int = 0) -> str:
+    """Write `<prefix>.index` + `<prefix>.data-00000-of-00001` for the reference's Saver (model.py:696-699)."""
+    tf_bundle.write_bundle(prefix, tf_variables(engine, global_step, start_epoch))
+    return prefix
+
+
+def import_tf(engine, prefix: str):
+    """Load a checkpoint written by the reference (model.py:758-764,803-809). Returns (global_step, start_epoch).
+
+    Model variables must all be present, as Saver.restore demands; optimizer slots, `global_step` and
+    `start_epoch` are taken when present (a checkpoint of another optimizer still evaluates)."""
+    reader = tf_bundle.BundleReader(prefix)
+    missing = [n for n in engine.variables() if n not in reader]
+    if missing:
+        raise KeyError("Key %s not found in checkpoint %s (%d of %d variables missing)"
+                       % (missing[0], prefix, len(missing), len(engine.variables())))
+    opt = _optimizer_name(engine)
+    for name, (shape, trainable) in engine.variables().items():
+        value = reader.get_tensor(name)
+        if tuple(value.shape) != tuple(shape):
+            raise ValueError("%s: checkpoint shape %s, graph shape %s" % (name, value.shape, shape))
+        engine.set_param(name, value)
+        if not trainable:
+            continue
+        if opt == "Adam" and name + "/Adam" in reader and name + "/Adam_1" in reader:
+            engine.set_param(name, reader.get_tensor(name + "/Adam"), _ffi.SLOT_ADAM_M)
+            engine.set_param(name, reader.get_tensor(name + "/Adam_1"), _ffi.SLOT_ADAM_V)
+        elif opt in ("Momentum", "NesterovMomentum") and name + "/Momentum" in reader:
+            engine.set_param(name, reader.get_tensor(name + "/Momentum"), _ffi.SLOT_ADAM_M)
+    step = int(reader.get_tensor("global_step")) if "global_step" in reader else 0
+    epoch = int(reader.get_tensor("start_epoch").reshape(-1)[0]) if "start_epoch" in reader else 0
+    engine.global_step = step
+    return step, epoch
+
+
+def save(engine, ckpt_dir: str, global_step: int, start_epoch: int = 0, format: str = "npz") -> str:
+    if format not in FORMATS:
+        raise ValueError("CheckpointFormat must be one of %s" % (FORMATS,))
+    os.makedirs(ckpt_dir, exist_ok=True)
+    prefix = os.path.join(ckpt_dir, "checkpoint-%d" % global_step)
+    if format in ("npz", "both"):
+        np.savez(prefix + ".npz", **_npz_arrays(engine, global_step, start_epoch))
+    if format in ("tf", "both"):
+        export_tf(engine, prefix, global_step, start_epoch)
     with open(os.path.join(ckpt_dir, LATEST), "w") as f:  # same role as tf's latest_filename
         f.write('model_checkpoint_path: "%s"\n' % os.path.basename(prefix))
     return prefix
@@ -45,8 +126,13 @@ def latest(ckpt_dir: str) -> Optional[str]:
 
 
 def restore(engine, prefix: str):
-    """prefix: path without extension, as in EvaluationSetting.CheckpointPath. Returns (global_step, start_epoch)."""
+    """prefix: path without extension, as in EvaluationSetting.CheckpointPath. Returns (global_step, start_epoch).
+    Takes the native `.npz` when it exists, else a TensorFlow bundle of that prefix."""
     path = prefix if prefix.endswith(".npz") else prefix + ".npz"
+    if not os.path.exists(path):
+        for cand in (prefix, prefix[:-len(".index")] if prefix.endswith(".index") else None):
+            if cand and tf_bundle.is_bundle(cand):
+                return import_tf(engine, cand)
     with np.load(path) as z:
         for name, (_, trainable) in engine.variables().items():
             engine.set_param(name, z[name])

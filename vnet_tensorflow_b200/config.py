@@ -65,6 +65,7 @@ class Config:
     precision: str = "bf16x3"
     synthetic: bool = False
     data_workers: int = 4
+    checkpoint_format: str = "npz"
     # evaluation (model.py:227-241)
     checkpoint_path: str = "./tmp/ckpt/checkpoint-latest"
     evaluate_data_dir: str = "./data/evaluate"
@@ -129,6 +130,7 @@ def from_dict(cfg: dict) -> Config:
     c.precision = _get(t, "Precision", default="bf16x3")
     c.synthetic = bool(_get(t, "Synthetic", default=False))
     c.data_workers = max(1, int(_get(t, "DataWorkers", default=4)))
+    c.checkpoint_format = _get(t, "CheckpointFormat", default="npz")  # "npz" | "tf" | "both" (checkpoint.py)
     ed = e.get("Data", {})
     c.checkpoint_path = _get(e, "CheckpointPath", default=c.checkpoint_path)
     c.evaluate_data_dir = _get(ed, "EvaluateDataDirectory", default=c.evaluate_data_dir)

@@ -169,7 +169,7 @@ class image2label(object):
                 self._log("train", step, total_loss=loss)
                 if step % self.log_interval == 0:
                     print("{}: Saving checkpoint of step {} at {}...".format(_now(), step, self.ckpt_dir))
-                    checkpoint.save(self.engine, self.ckpt_dir, step, epoch)
+                    checkpoint.save(self.engine, self.ckpt_dir, step, epoch, self.cfg.checkpoint_format)
                 if self.testing and step % self.test_step == 0:
                     try:
                         timg, tlab = next(test_iter)
@@ -181,7 +181,7 @@ class image2label(object):
                     self._log("test", step, total_loss=tloss)
             print("{}: Training of epoch {} complete, epoch loss: {}".format(_now(), epoch + 1, loss_sum / max(count, 1)))
             print("{}: Saving checkpoint of epoch {} at {}...".format(_now(), epoch + 1, self.ckpt_dir))
-            checkpoint.save(self.engine, self.ckpt_dir, self.engine.global_step, epoch + 1)
+            checkpoint.save(self.engine, self.ckpt_dir, self.engine.global_step, epoch + 1, self.cfg.checkpoint_format)
             print("{}: Saving checkpoint succeed".format(_now()))
 
     # ---- evaluation ---------------------------------------------------------------------------
