@@ -55,6 +55,21 @@ def test_reference_config_files_load_with_tolerant_reader():
         config_mod.from_dict(shipped)
 
 
+def _check_event_files(log_dir, losses):
+    """LogDir/{train,test} hold TensorBoard event files (tf.summary.FileWriter, model.py:705-709) that TensorBoard's
+    own reader accepts: version record first, then one scalar event per step under the reference's tags."""
+    loader_mod = pytest.importorskip("tensorboard.backend.event_processing.event_file_loader")
+    files = [f for f in os.listdir(log_dir / "train") if f.startswith("events.out.tfevents.")]
+    assert len(files) == 1 and any(f.startswith("events.out.tfevents.") for f in os.listdir(log_dir / "test"))
+    evs = list(loader_mod.LegacyEventFileLoader(str(log_dir / "train" / files[0])).Load())
+    assert evs[0].file_version == "brain.Event:2" and len(evs) == 1 + len(losses)
+    for k, ev in enumerate(evs[1:]):
+        vals = {v.tag: v.simple_value for v in ev.summary.value}
+        assert ev.step == k + 1 and ev.wall_time > 1e9
+        assert vals["loss/0.total_loss"] == np.float32(losses[k])
+        assert vals["learning_rate"] == np.float32(1e-2 * 0.99 ** (k / 100))   # exponential_decay at the step's start
+
+
 def test_train_checkpoint_restore_evaluate_roundtrip(emul_lib, tmp_path):
     cfg = _config(tmp_path)
     m = image2label(None, cfg, library=emul_lib)
@@ -65,6 +80,7 @@ def test_train_checkpoint_restore_evaluate_roundtrip(emul_lib, tmp_path):
     losses = [json.loads(l)["total_loss"] for l in open(tmp_path / "log" / "train" / "scalars.jsonl")]
     assert len(losses) == 8 and all(np.isfinite(losses)) and losses[-1] < losses[0]
     assert os.path.exists(tmp_path / "log" / "test" / "scalars.jsonl")
+    _check_event_files(tmp_path / "log", losses)
     with np.load(str(tmp_path / "ckpt" / "checkpoint-8.npz")) as z:  # TF variable names + Adam slots
         assert "vnet/encoder/level_1/conv_1/weights" in z and "vnet/encoder/level_1/conv_1/weights/Adam_1" in z
         assert int(z["global_step"]) == 8

@@ -9,8 +9,9 @@ Mapped reference code:
   train                  model.py:632-815   -> epoch / step loop, LogInterval checkpoints, TestStep test loss
   evaluate_single_3D     model.py:817-977   -> sliding windows, softmax accumulation, argmax, optional LCC / volume threshold
   evaluate               model.py:1131-1243 -> per-case loop, NIfTI outputs
-TensorBoard image/metric summaries (model.py:314-334,449-463,570-626) are out of scope; scalars go to
-`LogDir/{train,test}/scalars.jsonl`.
+TensorBoard image/metric summaries (model.py:314-334,449-463,570-626) are out of scope; the loss and learning-rate
+scalars go to `LogDir/{train,test}/scalars.jsonl` and, under the reference's tags, to TensorBoard event files there
+(events.py).
 """
 from __future__ import annotations
 
@@ -25,7 +26,7 @@ from typing import List
 
 import numpy as np
 
-from . import checkpoint, config as config_mod, nifti
+from . import checkpoint, config as config_mod, events, nifti
 from .engine import VNetEngine
 from .init import initialize
 from .pipeline import NiftiDataset3D
@@ -133,6 +134,16 @@ class image2label(object):
         os.makedirs(d, exist_ok=True)
         with open(os.path.join(d, "scalars.jsonl"), "a") as f:
             f.write(json.dumps(dict(step=step, **scalars)) + "\n")
+        # the same scalars under the reference's summary tags, for `tensorboard --logdir LogDir` (model.py:562,644)
+        writers = self.__dict__.setdefault("_event_writers", {})
+        if which not in writers:
+            writers[which] = events.EventFileWriter(d)
+        tags = {"total_loss": "loss/0.total_loss", "learning_rate": "learning_rate"}
+        writers[which].add_scalars(step, {tags.get(k, k): v for k, v in scalars.items()})
+
+    def _learning_rate(self, step):
+        """tf.train.exponential_decay(lr0, global_step, decay_steps, decay_factor, staircase=False), model.py:641-643."""
+        return self.initial_learning_rate * self.decay_factor ** (step / self.decay_steps)
 
     def train(self):
         print("{}: VNet Tensorflow training start...".format(_now()))
@@ -166,7 +177,7 @@ class image2label(object):
                 loss_sum += loss
                 count += 1
                 step = self.engine.global_step
-                self._log("train", step, total_loss=loss)
+                self._log("train", step, total_loss=loss, learning_rate=self._learning_rate(step - 1))
                 if step % self.log_interval == 0:
                     print("{}: Saving checkpoint of step {} at {}...".format(_now(), step, self.ckpt_dir))
                     checkpoint.save(self.engine, self.ckpt_dir, step, epoch, self.cfg.checkpoint_format)
