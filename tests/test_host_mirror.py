@@ -214,3 +214,66 @@ def _native_driver_case(lib, lib_path, precision, tmp_path):
     assert np.array_equal(out.array, want)
     assert out.spacing == (0.5, 0.5, 2.0) and out.origin == (1.0, 2.0, 3.0)
     eng.close()
+
+
+def test_remaining_reference_transforms(tmp_path):
+    """ExtremumNormalization, Reorient, ConfidenceCrop, BSplineDeformation (NiftiDataset3D.py:256-283,310-328,574-659,
+    795-835) under the names the pipeline YAML resolves."""
+    import random
+    random.seed(3)
+    np.random.seed(3)
+    rng = np.random.default_rng(0)
+    vol = rng.normal(100, 30, (40, 36, 32)).astype(np.float32)
+    lab = np.zeros((40, 36, 32), np.int16)
+    lab[10:14, 20:24, 5:9] = 3
+    lab[30:33, 4:8, 20:26] = 1
+    sample = {'image': [nifti.Image(vol, (1.0, 2.0, 0.5), (5.0, 6.0, 7.0))], 'label': nifti.Image(lab, (1.0, 2.0, 0.5), (5.0, 6.0, 7.0))}
+
+    out = NiftiDataset3D.ExtremumNormalization(0.05)(sample)['image'][0].array
+    lo, hi = vol.min() + 0.05 * (vol.max() - vol.min()), vol.min() + 0.95 * (vol.max() - vol.min())
+    assert out.min() == 0 and out.max() == 255 and out.dtype == np.float32
+    inside = (vol > lo) & (vol < hi)
+    assert np.allclose(out[inside], (vol[inside] - lo) / (hi - lo) * 255, atol=1e-3)
+    assert np.all(out[vol <= lo] == 0) and np.all(out[vol >= hi] == 255)
+
+    out = NiftiDataset3D.Reorient([2, 0, 1])(sample)
+    assert out['image'][0].array.shape == (32, 40, 36) and out['image'][0].spacing == (0.5, 1.0, 2.0)
+    assert out['image'][0].origin == (7.0, 5.0, 6.0)
+    assert out['image'][0].array[3, 1, 2] == vol[1, 2, 3] and out['label'].array[6, 11, 21] == 3
+
+    crop = NiftiDataset3D.ConfidenceCrop((16, 12, 8), 0.25)
+    hits = 0
+    for _ in range(20):
+        o = crop(sample)
+        assert o['image'][0].array.shape == (16, 12, 8) and o['label'].array.shape == (16, 12, 8)
+        hits += bool(o['label'].array.any())
+    assert hits >= 15                                   # small sigma: the crop stays on the chosen component
+    empty = {'image': sample['image'], 'label': nifti.Image(np.zeros_like(lab))}
+    assert NiftiDataset3D.ConfidenceCrop(16, 0.1)(empty)['image'][0].array.shape == (16, 16, 16)
+    assert NiftiDataset3D.ConfidenceCrop((40, 36, 32))(sample)['image'][0].array.shape == (40, 36, 32)  # only offset 0 fits
+    with pytest.raises(ValueError, match="smaller than the crop"):
+        NiftiDataset3D.ConfidenceCrop(48)(sample)
+
+    bs = NiftiDataset3D.BSplineDeformation(4)
+    n = bs.MESH + bs.ORDER
+    # cubic B-splines sum to one and reproduce linear functions: constant coefficients = a rigid shift of c / spacing
+    # voxels, coefficients equal to the control index = the continuous grid coordinate itself
+    const = np.stack([np.full((n, n, n), c) for c in (2.0, 3.0, 1.0)])
+    d = bs.displacement(vol.shape, (1.0, 2.0, 0.5), const)
+    assert np.allclose(d[0], 2.0) and np.allclose(d[1], 1.5) and np.allclose(d[2], 2.0)
+    ramp = np.stack([np.broadcast_to(np.arange(n, dtype=np.float64).reshape([-1 if a == c else 1 for a in range(3)]), (n, n, n))
+                     for c in range(3)])
+    d = bs.displacement(vol.shape, (1.0, 1.0, 1.0), ramp)
+    assert np.allclose(d[0][:, 0, 0], np.arange(40) * 10 / 40 + 1) and np.allclose(d[2][0, 0, :], np.arange(32) * 10 / 32 + 1)
+    o = bs(sample)
+    assert o['image'][0].array.shape == vol.shape and o['image'][0].array.dtype == np.float32
+    assert set(np.unique(o['label'].array)) <= {0, 1, 3} and o['label'].array.dtype == lab.dtype
+    assert 0 < (o['label'].array > 0).sum() < 2 * (lab > 0).sum()
+    assert not np.array_equal(o['image'][0].array, vol)
+    with pytest.raises(RuntimeError):
+        NiftiDataset3D.BSplineDeformation(0)
+    # the YAML resolver finds every transform class the reference defines
+    for name in ("Normalization", "RandomFlip", "StatisticalNormalization", "ExtremumNormalization", "ManualNormalization",
+                 "Reorient", "Invert", "Resample", "Padding", "RandomCrop", "RandomNoise", "ConfidenceCrop",
+                 "ConfidenceCrop2", "BSplineDeformation"):
+        assert callable(getattr(NiftiDataset3D, name))

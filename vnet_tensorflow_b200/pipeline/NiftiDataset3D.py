@@ -339,3 +339,129 @@ class Invert(object):
 
     def __call__(self, sample):
         return _map(sample, lambda im: nifti.Image(255.0 - np.asarray(im.array, np.float32), im.spacing, im.origin, im.direction))
+
+
+class ExtremumNormalization(object):
+    """NiftiDataset3D.py:256-283: window [min + percent*range, min + (1-percent)*range] of each modality -> 0..255,
+    values outside the window clamped (IntensityWindowingImageFilter)."""
+
+    def __init__(self, percent=0.05):
+        self.name = 'ExtremumNormalization'
+        assert isinstance(percent, float)
+        self.percent = percent
+
+    def __call__(self, sample):
+        def norm(im):
+            a = np.asarray(im.array, np.float32)
+            lo_all, hi_all = float(a.min()), float(a.max())
+            lo = (hi_all - lo_all) * self.percent + lo_all
+            hi = (hi_all - lo_all) * (1 - self.percent) + lo_all
+            a = (np.clip(a, lo, hi) - lo) / max(hi - lo, 1e-6) * 255.0
+            return nifti.Image(a.astype(np.float32), im.spacing, im.origin, im.direction)
+        return _map(sample, norm)
+
+
+class Reorient(object):
+    """NiftiDataset3D.py:310-328 (PermuteAxesImageFilter): output axis i is input axis order[i]; spacing and
+    origin follow their axes.  Applied to every modality and to the label."""
+
+    def __init__(self, order):
+        self.name = 'Reoreient'
+        assert isinstance(order, (tuple, list)) and len(order) == 3 and sorted(order) == [0, 1, 2]
+        self.order = tuple(int(o) for o in order)
+
+    def __call__(self, sample):
+        def perm(im):
+            o = self.order
+            return nifti.Image(np.ascontiguousarray(np.transpose(np.asarray(im.array), o)), tuple(im.spacing[k] for k in o),
+                               tuple(im.origin[k] for k in o), im.direction)
+        return _map(sample, perm, perm)
+
+
+class ConfidenceCrop(RandomCrop):
+    """NiftiDataset3D.py:574-659: crop of `output_size` around the centroid of a randomly chosen connected
+    foreground component (the volume's first-octant centre when there is none), shifted per axis by a rounded
+    N(0, sigma * size / 2) offset that is redrawn until the crop lies inside the volume."""
+
+    def __init__(self, output_size, sigma=2.5):
+        super().__init__(output_size)
+        self.name = 'Confidence Crop'
+        assert isinstance(sigma, (float, tuple, list))
+        self.sigma = (sigma,) * 3 if isinstance(sigma, float) else tuple(sigma)
+        assert len(self.sigma) == 3 and all(s >= 0 for s in self.sigma)
+
+    def NormalOffset(self, size, sigma):
+        s = np.random.normal(0, size * sigma / 2, 100)
+        return int(round(random.choice(s)))
+
+    def __call__(self, sample):
+        lab = np.asarray(sample['label'].array)
+        size = self.output_size
+        if any(s < o for s, o in zip(lab.shape, size)):
+            raise ValueError("ConfidenceCrop: volume %s is smaller than the crop %s (pad first)" % (lab.shape, tuple(size)))
+        from scipy import ndimage
+        comp, n = ndimage.label(lab.astype(np.int8) != 0)
+        if n == 0:
+            centroid = [int(o / 2) for o in size]
+        else:
+            k = random.randint(1, n)
+            centroid = [int(round(c)) for c in ndimage.center_of_mass(comp == k)]
+        start = [0, 0, 0]
+        for i in range(3):
+            if centroid[i] < size[i] / 2:
+                centroid[i] = int(size[i] / 2)
+            elif lab.shape[i] - centroid[i] < size[i] / 2:
+                centroid[i] = lab.shape[i] - int(size[i] / 2) - 1
+            if self.sigma[i] == 0 or lab.shape[i] == size[i]:   # a zero offset is the only one that can be accepted
+                start[i] = min(max(centroid[i] - int(size[i] / 2), 0), lab.shape[i] - size[i])
+                continue
+            while True:
+                start[i] = centroid[i] + self.NormalOffset(size[i], self.sigma[i]) - int(size[i] / 2)
+                if start[i] >= 0 and start[i] + size[i] - 1 <= lab.shape[i] - 1:
+                    break
+        return _map(sample, lambda im: self._crop(im, start), lambda lb: self._crop(lb, start))
+
+
+class BSplineDeformation(object):
+    """NiftiDataset3D.py:795-835: free-form deformation by a cubic B-spline over a 10x10x10 mesh of the image domain
+    (13^3 control points per displacement component, ITK's BSplineTransform layout: grid spacing = extent / 10, first
+    control point one grid step before the origin) whose coefficients are uniform in [0, randomness) physical units;
+    output(x) = input(x + d(x)).  Images are interpolated linearly as sitk.Resample's default does; labels with
+    nearest neighbour, which keeps them class values (the reference resamples them linearly and truncates)."""
+
+    MESH, ORDER = 10, 3
+
+    def __init__(self, randomness=10):
+        self.name = 'BSpline Deformation'
+        assert isinstance(randomness, (int, float))
+        if randomness > 0:
+            self.randomness = randomness
+        else:
+            raise RuntimeError('Randomness should be non zero values')
+
+    def displacement(self, shape, spacing, coeffs):
+        """d[c][x,y,z] in voxels of axis c: the B-spline with control coefficients `coeffs` [3,13,13,13] (physical units)."""
+        from scipy import ndimage
+        # continuous control-grid index of voxel i along an axis: position i*spacing over grid step extent/MESH, plus
+        # the (ORDER-1)/2 = 1 control point that sits before the domain origin
+        u = [np.arange(n, dtype=np.float64) * self.MESH / n + (self.ORDER - 1) / 2 for n in shape]
+        grid = np.meshgrid(*u, indexing="ij")
+        return [ndimage.map_coordinates(coeffs[c], grid, order=3, prefilter=False, mode="nearest") / spacing[c]
+                for c in range(3)]
+
+    def __call__(self, sample):
+        from scipy import ndimage
+        ref = sample['image'][0]
+        shape = np.asarray(ref.array).shape
+        n_ctrl = self.MESH + self.ORDER
+        coeffs = np.random.random(3 * n_ctrl ** 3).reshape(3, n_ctrl, n_ctrl, n_ctrl) * self.randomness
+        # ITK stores the parameters x-fastest per component; the draw is i.i.d., so the order has no effect here
+        d = self.displacement(shape, ref.spacing, coeffs)
+        idx = np.meshgrid(*[np.arange(n, dtype=np.float64) for n in shape], indexing="ij")
+        coords = [i + dd for i, dd in zip(idx, d)]
+
+        def warp(im, order):
+            a = np.asarray(im.array)
+            out = ndimage.map_coordinates(a.astype(np.float32) if order else a, coords, order=order, mode="constant", cval=0)
+            return nifti.Image(out.astype(a.dtype), im.spacing, im.origin, im.direction)
+        return _map(sample, lambda im: warp(im, 1), lambda lb: warp(lb, 0))
