@@ -273,7 +273,8 @@ int main(int argc, char** argv) {
     const int32_t dims32[3] = {pd[0], pd[1], pd[2]}, stride32[3] = {a.stride[0], a.stride[1], a.stride[2]};
     api.check(api.evaluate_volume(h, vol.data(), dims32, stride32, a.batch, label.data(), nullptr, nullptr), "vnb_evaluate_volume");
     api.destroy(h);
-    // crop the padding, map class indices to label values (model.py:1207-1215), back to file order
+    // crop the padding, back to file order; the reference writes the class index (model.py:934,945), --labels
+    // (optional) writes that index's label value instead
     std::vector<int32_t> out(static_cast<size_t>(dim[0]) * dim[1] * dim[2]);
     for (int z = 0; z < dim[2]; ++z)
       for (int y = 0; y < dim[1]; ++y)

@@ -277,3 +277,91 @@ def test_remaining_reference_transforms(tmp_path):
                  "Reorient", "Invert", "Resample", "Padding", "RandomCrop", "RandomNoise", "ConfidenceCrop",
                  "ConfidenceCrop2", "BSplineDeformation"):
         assert callable(getattr(NiftiDataset3D, name))
+
+
+def test_resample_image_follows_itk_index_arithmetic():
+    """sitk.ResampleImageFilter with the identity transform, as NiftiDataset3D.py:378-396 and model.py:957-975 set it."""
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(10, 12, 8)).astype(np.float32)
+    im = nifti.Image(a, (1.0, 2.0, 0.5), (3.0, 4.0, 5.0))
+    res = NiftiDataset3D.resample_image
+    assert np.array_equal(res(im, im.spacing, im.GetSize(), im.origin, 1).array, a)
+    assert np.array_equal(res(im, im.spacing, im.GetSize(), im.origin, 0).array, a)
+    up = res(im, (0.5, 2.0, 0.5), (20, 12, 8), im.origin, 1).array
+    assert np.array_equal(up[::2], a) and np.allclose(up[1:-1:2], (a[:-1] + a[1:]) / 2, atol=1e-6)
+    assert not up[-1].any()                                 # continuous index 9.5 is outside [-0.5, 9.5)
+    near = res(im, (0.5, 2.0, 0.5), (20, 12, 8), im.origin, 0).array
+    assert np.array_equal(near[0::2], a) and np.array_equal(near[1:-1:2], a[1:])   # halves round up
+    lab = nifti.Image((a > 0).astype(np.int16), im.spacing, im.origin)
+    assert res(lab, (0.5, 2.0, 0.5), (20, 12, 8), im.origin, 0).array.dtype == np.int16
+    # a shifted, larger output grid: zeros outside the input, input values where the grids coincide
+    big = res(im, im.spacing, (14, 12, 8), (1.0, 4.0, 5.0), 1).array
+    assert not big[:2].any() and np.array_equal(big[2:12], a) and not big[12:].any()
+    # the Resample transform: grid size ceil(extent / voxel), same origin; Padding appends at the far end only
+    s = NiftiDataset3D.Resample((2.0, 2.0, 2.0))({'image': [im], 'label': lab})
+    assert s['image'][0].array.shape == (5, 12, 2) and s['label'].array.shape == (5, 12, 2) and s['image'][0].origin == im.origin
+    assert np.array_equal(s['image'][0].array[:, :, 0], a[::2, :, 0])
+    p = NiftiDataset3D.Padding((12, 12, 16))({'image': [im], 'label': lab})
+    assert p['image'][0].array.shape == (12, 12, 16) and np.array_equal(p['image'][0].array[:10, :, :8], a)
+    assert not p['image'][0].array[10:].any() and not p['image'][0].array[:, :, 8:].any() and p['image'][0].origin == im.origin
+    c = NiftiDataset3D.RandomCrop((4, 4, 4))._crop(im, [2, 3, 1])
+    assert c.origin == (5.0, 10.0, 5.5) and np.array_equal(c.array, a[2:6, 3:7, 1:5])
+
+
+def test_label_postprocessing_matches_the_reference_filters():
+    from vnet_tensorflow_b200.model import postprocess_label
+    lab = np.zeros((12, 12, 12), np.int32)
+    lab[1:4, 1:4, 1:4] = 2            # 27 voxels
+    lab[6:10, 6:10, 6:10] = 1         # 64 voxels, touching the next block only by an edge (not face-connected)
+    lab[10:12, 10:12, 5] = 3          # 4 voxels
+    assert postprocess_label(lab, (1, 1, 1)) is lab
+    lcc = postprocess_label(lab, (1, 1, 1), lcc=True)
+    assert lcc.dtype == np.uint8 and lcc.sum() == 64 and lcc[7, 7, 7] == 1      # binary mask of the largest component
+    vt = postprocess_label(lab, (1.0, 1.0, 0.5), volume_threshold=13.5)          # physical size, strict '>'
+    assert vt.sum() == 64 and set(np.unique(vt)) == {0, 1}                        # 27 * 0.5 = 13.5 is not kept
+    assert postprocess_label(lab, (1.0, 1.0, 0.5), volume_threshold=13.4).sum() == 64 + 27
+    both = postprocess_label(lab, (1, 1, 1), lcc=True, volume_threshold=100.0)
+    assert both.shape == lab.shape and not both.any()
+    assert not postprocess_label(np.zeros((4, 4, 4), np.int32), (1, 1, 1), lcc=True).any()
+
+
+def test_evaluate_with_a_pipeline_returns_to_the_input_grid(emul_lib, tmp_path):
+    """model.py:817-977,1196-1243: evaluate transforms (Resample, Padding) run before the window loop; the label comes
+    back on the input image's grid by nearest neighbour, the probabilities linearly; the label holds class indices."""
+    import yaml
+    pipe = {"preprocess": {"evaluate": {"3D": [{"name": "StatisticalNormalization", "variables": {"sigma": 2.5}},
+                                                {"name": "Resample", "variables": {"voxel_size": [2.0, 2.0, 2.0]}},
+                                                {"name": "Padding", "variables": {"output_size": [8, 8, 8]}}]}}}
+    with open(tmp_path / "pipe.yaml", "w") as f:
+        yaml.safe_dump(pipe, f)
+    cfg = _config(tmp_path, Epoches=1, Testing=False, SegmentationClasses=[0, 4])
+    cfg["EvaluationSetting"]["Pipeline"] = str(tmp_path / "pipe.yaml")
+    cfg["EvaluationSetting"]["CheckpointPath"] = str(tmp_path / "ckpt" / "checkpoint-4")
+    image2label(None, cfg, library=emul_lib).train()
+    case = tmp_path / "eval" / "case0"
+    os.makedirs(case)
+    rng = np.random.default_rng(0)
+    vol = rng.uniform(0, 255, (20, 14, 9)).astype(np.float32)          # 1 mm voxels -> 10 x 7 x 5 at 2 mm -> padded to 10 x 8 x 8
+    nifti.write(str(case / "image.nii"), nifti.Image(vol, (1.0, 1.0, 1.0), (-3.0, 2.0, 9.0)))
+    m = image2label(None, cfg, library=emul_lib)
+    m.evaluate()
+    out = nifti.read(str(case / "label_out.nii.gz"))
+    assert out.array.shape == (20, 14, 9) and out.spacing == (1.0, 1.0, 1.0) and out.origin == (-3.0, 2.0, 9.0)
+    assert set(np.unique(out.array)) <= {0, 1}                          # class indices, as the reference writes them
+    prob = [nifti.read(str(case / ("prob_out_%d.nii.gz" % v))).array for v in (0, 4)]
+    assert prob[0].shape == (20, 14, 9) and np.allclose((prob[0] + prob[1])[:19, :13, :9], 1.0, atol=1e-5)
+    # the same numbers by hand: transforms, window loop, resample back
+    sample = {'image': [nifti.Image(vol, (1.0, 1.0, 1.0), (-3.0, 2.0, 9.0))], 'label': nifti.Image(np.zeros(vol.shape, np.int32))}
+    for t in m._transforms(str(tmp_path / "pipe.yaml"), "evaluate"):
+        sample = t(sample)
+    assert sample['image'][0].array.shape == (10, 8, 8)
+    lab, sm, w = m.evaluate_single_3D(sample['image'][0].array[..., None])
+    ref = sample['image'][0]
+    back = NiftiDataset3D.resample_image(nifti.Image(lab.astype(np.int32), ref.spacing, ref.origin), (1.0, 1.0, 1.0), (20, 14, 9), (-3.0, 2.0, 9.0), 0)
+    assert np.array_equal(back.array, out.array)
+    assert np.array_equal(out.array[::2, ::2, ::2], lab[:10, :7, :5])   # even voxels coincide with the 2 mm grid
+    # MapLabelValues (extension): SegmentationClasses values instead of indices
+    cfg["EvaluationSetting"]["MapLabelValues"] = True
+    image2label(None, cfg, library=emul_lib).evaluate()
+    mapped = nifti.read(str(case / "label_out.nii.gz")).array
+    assert np.array_equal(mapped, out.array * 4)

@@ -78,6 +78,7 @@ class Config:
     evaluate_lcc: bool = False
     evaluate_volume_threshold: int = 0
     evaluate_pipeline: Optional[str] = None
+    evaluate_map_label_values: bool = False
 
     @property
     def dimension(self) -> int:
@@ -143,6 +144,7 @@ def from_dict(cfg: dict) -> Config:
     c.evaluate_lcc = bool(_get(e, "LargestConnectedComponent", default=False))
     c.evaluate_volume_threshold = int(_get(e, "VolumeThreshold", default=0))
     c.evaluate_pipeline = _get(e, "Pipeline", default=None)
+    c.evaluate_map_label_values = bool(_get(e, "MapLabelValues", default=False))  # extension: class index -> SegmentationClasses value
     if c.network_name != "VNet":
         raise SystemExit("Invalid Network")  # model.py:439-440 (UNet / Dense are outside the accelerated path)
     if len(c.num_convolutions) != c.num_levels:

@@ -36,6 +36,32 @@ def _now():
     return datetime.datetime.now()
 
 
+def postprocess_label(label, spacing, lcc=False, volume_threshold=0.0):
+    """model.py:1217-1223 with ExtractLargestConnectedComponents (:142-167) and volume_threshold (:117-140): face-
+    connected components of the non-zero voxels; `lcc` keeps the one of largest physical size (first on ties),
+    `volume_threshold` > 0 then keeps components whose physical size (mm^3) is strictly larger.  Both return a
+    0/1 uint8 mask as the reference's filters do - class values do not survive them.  One deviation: a volume
+    without foreground stays empty (the reference thresholds at label 0 there and returns all ones)."""
+    if not lcc and not volume_threshold > 0:
+        return label
+    from scipy import ndimage
+    voxel = float(np.prod(spacing))
+    for which in ("lcc", "volume"):
+        if (which == "lcc" and not lcc) or (which == "volume" and not volume_threshold > 0):
+            continue
+        comp, n = ndimage.label(np.asarray(label) != 0)
+        if n == 0:
+            return np.zeros(np.shape(label), np.uint8)
+        sizes = ndimage.sum(np.ones(comp.shape, np.int64), comp, range(1, n + 1)) * voxel
+        keep = np.zeros(n + 1, bool)
+        if which == "lcc":
+            keep[1 + int(np.argmax(sizes))] = True   # argmax = first maximum, as the strict `>` scan
+        else:
+            keep[1:] = sizes > volume_threshold
+        label = keep[comp].astype(np.uint8)
+    return label
+
+
 class image2label(object):
     def __init__(self, sess, config, device: int = 0, library=None):
         self.sess = sess  # kept for signature compatibility (model.py:170); unused
@@ -225,25 +251,28 @@ class image2label(object):
                 sample = t(sample)
             arr = np.stack([np.asarray(im.array, np.float32) for im in sample['image']], -1)
             label_np, softmax_np, weight_np = self.evaluate_single_3D(arr)
-            out = np.zeros(label_np.shape, np.int32)
-            for idx, value in enumerate(self.label_classes):  # class index -> label value
-                out[label_np == idx] = value
-            if self.evaluate_lcc or self.evaluate_volume_threshold > 0:  # model.py:1217-1223
-                from scipy import ndimage
-                comp, n = ndimage.label(out > 0)
-                if n > 0:
-                    sizes = ndimage.sum(out > 0, comp, range(1, n + 1))
-                    keep = np.zeros(n + 1, bool)
-                    if self.evaluate_lcc:
-                        keep[1 + int(np.argmax(sizes))] = True
-                    else:
-                        keep[1:] = sizes >= self.evaluate_volume_threshold
-                    out[~keep[comp]] = 0
-            ref = sample['image'][0]
-            nifti.write(os.path.join(case_dir, self.evaluate_label_filename), nifti.Image(out, ref.spacing, ref.origin))
+            # back to the input image's grid (model.py:957-975): nearest for the label, linear for the probabilities
+            ref, orig = sample['image'][0], images[0]
+            same_grid = (ref.GetSize() == orig.GetSize() and np.allclose(ref.spacing, orig.spacing) and np.allclose(ref.origin, orig.origin))
+
+            def back(arr, order):
+                im = nifti.Image(arr, ref.spacing, ref.origin, ref.direction)
+                if not same_grid:
+                    im = NiftiDataset3D.resample_image(im, orig.spacing, orig.GetSize(), orig.origin, order)
+                return nifti.Image(im.array, orig.spacing, orig.origin, orig.direction)
+            if not same_grid:
+                print("{}: Resampling label back to original image space...".format(_now()))
+            # the reference writes the argmax class *index* (model.py:934,945); `MapLabelValues` writes the
+            # SegmentationClasses value of that index instead
+            out = label_np.astype(np.int32)
+            if self.cfg.evaluate_map_label_values:
+                out = np.asarray(self.label_classes, np.int32)[label_np]
+            out = back(out, 0).array
+            out = postprocess_label(out, orig.spacing, self.evaluate_lcc, self.evaluate_volume_threshold)
+            nifti.write(os.path.join(case_dir, self.evaluate_label_filename), nifti.Image(out, orig.spacing, orig.origin, orig.direction))
             if self.evaluate_probability_output:  # model.py:935-937,1234-1243
                 prob = softmax_np / np.maximum(weight_np[..., None], 1.0)
                 for c, value in enumerate(self.label_classes):
                     name = self.evaluate_probability_filename.replace(".nii", "_%s.nii" % value, 1)
-                    nifti.write(os.path.join(case_dir, name), nifti.Image(prob[..., c].astype(np.float32), ref.spacing, ref.origin))
+                    nifti.write(os.path.join(case_dir, name), back(prob[..., c].astype(np.float32), 1))
         print("{}: Evaluation complete".format(_now()))

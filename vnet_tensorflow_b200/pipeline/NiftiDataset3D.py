@@ -4,9 +4,9 @@ Kept: the class / constructor names that the YAML pipelines resolve by `getattr(
 (**variables)` (model.py:341-402), the sample dict {'image': [img per modality], 'label': img}, and the
 output contract of `NiftiDataset.get_dataset()`: (image float32 [X,Y,Z,M], label int32 [X,Y,Z]) with
 labels remapped to class *indices* (NiftiDataset3D.py:119-137,150-165).  Images are vnet_tensorflow_b200.
-nifti.Image objects (NumPy array[x,y,z] + spacing/origin).  The resampling transforms use trilinear /
-nearest interpolation from SciPy instead of ITK's B-spline (SURVEY.md "next" row N1); accelerating this
-CPU stage is out of the hot path's scope.
+nifti.Image objects (NumPy array[x,y,z] + spacing/origin).  Resampling follows sitk.ResampleImageFilter's
+index arithmetic (`resample_image`: linear / nearest, zero outside the input) in NumPy; accelerating this CPU
+stage is out of the hot path's scope (SURVEY.md "next" row N1).
 """
 from __future__ import annotations
 
@@ -168,6 +168,32 @@ def _map(sample, fn_img, fn_lbl=None):
     return out
 
 
+def resample_image(im, spacing, size, origin, order):
+    """sitk.ResampleImageFilter with an identity transform, as the reference configures it (output spacing / size /
+    origin given, direction kept; NiftiDataset3D.py:378-396, model.py:957-975): output voxel j of an axis sits at
+    origin + j*spacing and reads the input at continuous index (origin + j*spacing - im.origin) / im.spacing, linearly
+    (order 1, neighbours clamped to the edge) or at the nearest voxel (order 0, halves round up); positions outside
+    [-0.5, n-0.5) give 0.  Axes are independent because the direction matrix is shared."""
+    a = np.asarray(im.array)
+    out = a.astype(np.float32) if order else a
+    for axis in range(3):
+        n = a.shape[axis]
+        c = (origin[axis] + np.arange(size[axis], dtype=np.float64) * spacing[axis] - im.origin[axis]) / im.spacing[axis]
+        inside = (c >= -0.5) & (c < n - 0.5)
+        shape = [1, 1, 1]
+        shape[axis] = -1
+        if order:
+            i0 = np.floor(c).astype(np.int64)
+            f = (c - i0).astype(np.float32).reshape(shape)
+            lo, hi = np.clip(i0, 0, n - 1), np.clip(i0 + 1, 0, n - 1)
+            out = np.take(out, lo, axis) * (1 - f) + np.take(out, hi, axis) * f
+        else:
+            out = np.take(out, np.clip(np.floor(c + 0.5).astype(np.int64), 0, n - 1), axis)
+        out = out * inside.reshape(shape).astype(out.dtype)
+    return nifti.Image(out.astype(np.float32 if order else a.dtype), tuple(float(v) for v in spacing),
+                       tuple(float(v) for v in origin), im.direction)
+
+
 class StatisticalNormalization(object):
     """NiftiDataset3D.py:210-254: clamp to mean +- sigma*std, rescale to 0..255."""
 
@@ -216,32 +242,35 @@ class Normalization(StatisticalNormalization):
 
 
 class Resample(object):
-    """NiftiDataset3D.py:345-398: resample to `voxel_size` (linear for images, nearest for labels)."""
+    """NiftiDataset3D.py:345-398: resample to `voxel_size` on the grid size ceil(extent / voxel_size) from the same
+    origin (linear for images, nearest for the label)."""
 
     def __init__(self, voxel_size):
         self.name = 'Resample'
         self.voxel_size = (voxel_size,) * 3 if isinstance(voxel_size, (int, float)) else tuple(voxel_size)
 
-    def _res(self, im, order):
-        from scipy import ndimage
-        zoom = [s / v for s, v in zip(im.spacing, self.voxel_size)]
-        a = ndimage.zoom(np.asarray(im.array), zoom, order=order, mode="nearest")
-        return nifti.Image(a.astype(im.array.dtype), tuple(float(v) for v in self.voxel_size), im.origin, im.direction)
+    def _res(self, im, order, like=None):
+        like = like or im
+        size = [int(np.ceil(sp * n / v)) for sp, n, v in zip(like.spacing, like.GetSize(), self.voxel_size)]
+        return resample_image(im, self.voxel_size, size, im.origin, order)
 
     def __call__(self, sample):
-        return _map(sample, lambda im: self._res(im, 1), lambda lb: self._res(lb, 0))
+        last = sample['image'][-1]  # the label reuses the resampler of the last modality (NiftiDataset3D.py:391-396)
+        return _map(sample, lambda im: self._res(im, 1), lambda lb: self._res(lb, 0, last))
 
 
 class Padding(object):
-    """NiftiDataset3D.py:400-456: zero-pad symmetric up to at least `output_size`."""
+    """NiftiDataset3D.py:400-456: when any axis is shorter than `output_size`, resample onto the larger grid from
+    the same origin - zeros appended at the far end of the short axes, voxel (0,0,0) stays where it was."""
 
     def __init__(self, output_size):
         self.name = 'Padding'
         self.output_size = (output_size,) * 3 if isinstance(output_size, int) else tuple(output_size)
+        assert all(i > 0 for i in self.output_size)
 
     def _pad(self, im):
         a = np.asarray(im.array)
-        pads = [(max(o - s, 0) // 2, max(o - s, 0) - max(o - s, 0) // 2) for s, o in zip(a.shape, self.output_size)]
+        pads = [(0, max(o - s, 0)) for s, o in zip(a.shape, self.output_size)]
         return nifti.Image(np.pad(a, pads), im.spacing, im.origin, im.direction)
 
     def __call__(self, sample):
@@ -270,7 +299,8 @@ class RandomCrop(object):
 
     def _crop(self, im, st):
         sl = tuple(slice(s, s + o) for s, o in zip(st, self.output_size))
-        return nifti.Image(np.asarray(im.array)[sl], im.spacing, im.origin, im.direction)
+        origin = tuple(o + k * sp for o, k, sp in zip(im.origin, st, im.spacing))  # RegionOfInterest keeps physical positions
+        return nifti.Image(np.asarray(im.array)[sl], im.spacing, origin, im.direction)
 
     def __call__(self, sample):
         lab = np.asarray(sample['label'].array)
