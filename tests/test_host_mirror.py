@@ -365,3 +365,102 @@ def test_evaluate_with_a_pipeline_returns_to_the_input_grid(emul_lib, tmp_path):
     image2label(None, cfg, library=emul_lib).evaluate()
     mapped = nifti.read(str(case / "label_out.nii.gz")).array
     assert np.array_equal(mapped, out.array * 4)
+
+
+def test_transform_semantics_follow_the_simpleitk_filters():
+    """Details of NiftiDataset3D.py the YAML pipelines rely on: constructor argument names, pixel-type casts of the
+    intensity filters, the N-1 standard deviation, one flip coin, the crop index arithmetic."""
+    import random
+    rng = np.random.default_rng(0)
+    ct = rng.normal(40, 300, (24, 20, 16)).astype(np.int16)
+    lab = np.zeros(ct.shape, np.uint8)
+    lab[4:8, 10:15, 6:9] = 1
+    sample = {'image': [nifti.Image(ct)], 'label': nifti.Image(lab)}
+
+    # StatisticalNormalization on an integer image: window bounds and outputs truncated to the pixel type
+    out = NiftiDataset3D.StatisticalNormalization(2.5)(sample)['image'][0].array
+    d = ct.astype(np.float64)
+    lo, hi = int(d.mean() - 2.5 * d.std(ddof=1)), int(d.mean() + 2.5 * d.std(ddof=1))
+    want = np.where(ct < lo, 0, np.where(ct > hi, 255, np.trunc((d - lo) * (255.0 / (hi - lo)))))
+    assert out.dtype == np.int16 and np.abs(out - want).max() <= 1 and (out == want).mean() > 0.999
+    assert out.min() == 0 and out.max() == 255
+    f32 = NiftiDataset3D.StatisticalNormalization(2.5)({'image': [nifti.Image(ct.astype(np.float32))], 'label': nifti.Image(lab)})['image'][0].array
+    assert f32.dtype == np.float32 and not np.array_equal(f32, np.trunc(f32)) and np.abs(f32 - out).max() < 1.5
+    pre = NiftiDataset3D.StatisticalNormalization(2.5, pre_norm=True)(sample)['image'][0].array
+    assert pre.dtype == np.float32 and np.abs(pre - f32).max() < 1e-2
+    with pytest.raises(AssertionError):
+        NiftiDataset3D.StatisticalNormalization(2)                       # the reference insists on a float sigma
+    man = NiftiDataset3D.ManualNormalization(-100, 155)(sample)['image'][0].array
+    assert man.dtype == np.int16 and man[ct <= -100].max() == 0 and man[ct >= 155].min() == 255
+    k = (ct > -100) & (ct < 155)
+    assert np.array_equal(man[k], ct[k] + 100)                           # scale 1: exact
+    resc = NiftiDataset3D.Normalization()(sample)['image'][0].array
+    assert resc.dtype == np.int16 and resc.min() == 0 and resc.max() == 255
+    inv = NiftiDataset3D.Invert()({'image': [nifti.Image(man)], 'label': nifti.Image(lab)})['image'][0].array
+    assert np.array_equal(inv, 255 - man)
+
+    # RandomNoise(sigma=5): the YAML keyword is `sigma`
+    np.random.seed(0)
+    noisy = NiftiDataset3D.RandomNoise(sigma=5)({'image': [nifti.Image(ct.astype(np.float32))], 'label': nifti.Image(lab)})['image'][0].array
+    assert 4.5 < (noisy - ct).std() < 5.5 and NiftiDataset3D.RandomNoise().sigma == 5
+    assert NiftiDataset3D.RandomNoise(5)(sample)['image'][0].array.dtype == np.int16
+
+    # RandomFlip: one coin for all marked axes
+    np.random.seed(1)
+    seen = set()
+    for _ in range(16):
+        o = NiftiDataset3D.RandomFlip([True, False, True])(sample)
+        flipped = np.array_equal(o['image'][0].array, ct[::-1, :, ::-1]) and np.array_equal(o['label'].array, lab[::-1, :, ::-1])
+        assert flipped or o['image'][0].array is ct
+        seen.add(flipped)
+    assert seen == {True, False}
+
+    # RandomCrop: redraws until min_pixel foreground voxels are inside; never draws the last admissible start
+    np.random.seed(2)
+    random.seed(2)
+    crop = NiftiDataset3D.RandomCrop((8, 8, 8), drop_ratio=0, min_pixel=20)
+    starts = set()
+    for _ in range(40):
+        o = crop(sample)
+        assert o['label'].array.shape == (8, 8, 8) and o['label'].array.sum() >= 20
+        starts.add(tuple(int(v) for v in o['label'].origin))
+    assert max(s[0] for s in starts) <= 24 - 8 - 1 and len(starts) > 3
+    with pytest.raises(RuntimeError):
+        NiftiDataset3D.RandomCrop(8, drop_ratio=1.5)
+
+    # ConfidenceCrop2: bounding-box centre + integer offset, clamped with the reference's "- 1"
+    c2 = NiftiDataset3D.ConfidenceCrop2((8, 8, 8), rand_range=0, probability=1.0)
+    o = c2(sample)
+    assert tuple(int(v) for v in o['label'].origin) == (4 + 2 - 4, 10 + 2 - 4, 6 + 1 - 4)  # start + int(extent/2) - int(size/2)
+    edge = np.zeros(ct.shape, np.uint8)
+    edge[22:24, 0:2, 14:16] = 1
+    o = c2({'image': [nifti.Image(ct)], 'label': nifti.Image(edge)})
+    assert tuple(int(v) for v in o['label'].origin) == (24 - 8 - 1, 0, 16 - 8 - 1)
+    neg = NiftiDataset3D.ConfidenceCrop2((8, 8, 8), rand_range=(1, 2, 3), probability=0.0, random_empty_region=True)
+    for _ in range(10):
+        assert not neg(sample)['label'].array.any()
+    tight = NiftiDataset3D.ConfidenceCrop2((24, 19, 16), probability=0.0)(sample)    # margins 0, 1, 0 -> start 0
+    assert tight['label'].array.shape == (24, 19, 16)
+    assert NiftiDataset3D.ConfidenceCrop2(8, probability=0.75).probability == 0.75
+
+
+def test_labels_are_remapped_before_the_transforms(tmp_path):
+    """NiftiDataset3D.py:119-137 runs before the transform loop: a crop never centres on a label value outside `labels`."""
+    case = tmp_path / "0"
+    os.makedirs(case)
+    img = np.zeros((20, 20, 20), np.float32)
+    lab = np.zeros((20, 20, 20), np.int16)
+    lab[1:4, 1:4, 1:4] = 9            # not a segmentation class: background for the pipeline
+    lab[14:18, 14:18, 14:18] = 7
+    nifti.write(str(case / "image.nii"), nifti.Image(img))
+    nifti.write(str(case / "label.nii"), nifti.Image(lab))
+    nifti.write(str(tmp_path / ".DS_Store"), nifti.Image(img))          # skipped like NiftiDataset3D.py:41-45
+    tfm = [NiftiDataset3D.ConfidenceCrop2((8, 8, 8), rand_range=0, probability=1.0)]
+    ds = NiftiDataset3D.NiftiDataset(str(tmp_path), ["image.nii"], "label.nii", tfm, train=True, labels=[0, 7])
+    assert len(ds.get_dataset()) == 1
+    for _ in range(5):
+        image, label = next(iter(ds.get_dataset()))
+        assert label.dtype == np.int32 and label.sum() == 64 and set(np.unique(label)) == {0, 1}
+    nifti.write(str(case / "label.nii"), nifti.Image(lab, (2.0, 1.0, 1.0)))
+    with pytest.raises(Exception, match="Header info inconsistent"):
+        next(iter(ds.get_dataset()))

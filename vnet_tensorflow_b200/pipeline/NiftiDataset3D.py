@@ -34,27 +34,51 @@ class NiftiDataset(object):
         return nifti.read(path)
 
     def case_dirs(self) -> List[str]:
-        return [os.path.join(self.data_dir, c) for c in sorted(os.listdir(self.data_dir))]
+        skip = (".DS_Store", "@eaDir")  # NiftiDataset3D.py:41-45
+        return [os.path.join(self.data_dir, c) for c in sorted(os.listdir(self.data_dir)) if c not in skip]
+
+    @staticmethod
+    def _same_header(a, b):
+        return (a.GetSize() == b.GetSize(), tuple(a.GetSpacing()) == tuple(b.GetSpacing()),
+                tuple(a.GetDirection()) == tuple(b.GetDirection()))
 
     def input_parser(self, case_dir):
-        images = [self.read_image(os.path.join(case_dir, ch)) for ch in self.image_filenames]
-        for im in images[1:]:  # NiftiDataset3D.py:66-82: all modalities must share the grid
-            if im.GetSize() != images[0].GetSize():
-                raise Exception("Header info inconsistent: {}".format(case_dir))
+        images = []
+        for ch in self.image_filenames:
+            try:
+                images.append(self.read_image(os.path.join(case_dir, ch)))
+            except Exception:
+                raise Exception("Error loading image: {}".format(os.path.join(case_dir, ch)))
+        for ch, im in zip(self.image_filenames, images):  # NiftiDataset3D.py:72-86: all modalities share the grid
+            same = self._same_header(im, images[0])
+            if not all(same):
+                raise Exception('Header info inconsistent: {}\nSame size: {}\nSame spacing: {}\nSame direction: {}'
+                                .format(os.path.join(case_dir, ch), *same))
+        ref = images[0]
+        label = nifti.Image(np.zeros(ref.GetSize(), np.uint8), ref.spacing, ref.origin, ref.direction)
         if self.train:
-            label = self.read_image(os.path.join(case_dir, self.label_filename))
-        else:  # NiftiDataset3D.py:104-111: empty label
-            label = nifti.Image(np.zeros(images[0].GetSize(), np.int32), images[0].spacing, images[0].origin)
+            path = os.path.join(case_dir, self.label_filename)
+            try:
+                label_ = self.read_image(path)
+            except Exception:
+                raise Exception("Error loading label: {}".format(path))
+            same = self._same_header(label_, ref)
+            if not all(same):
+                raise Exception('Header info inconsistent: {}\nSame size: {}\nSame spacing: {}\nSame direction: {}'
+                                .format(path, *same))
+            # NiftiDataset3D.py:119-137: label value -> class index *before* the transforms see it; values that are
+            # not in `labels` become background
+            src = np.asarray(label_.array)
+            remapped = np.zeros(src.shape, np.uint8)
+            for idx, value in enumerate(self.labels):
+                remapped[src == value] = idx
+            label = nifti.Image(remapped, ref.spacing, ref.origin, ref.direction)
         sample = {'image': images, 'label': label}
         if self.transforms:
             for transform in self.transforms:
                 sample = transform(sample)
-        label_np = np.asarray(sample['label'].array)
-        remapped = np.zeros(label_np.shape, np.int32)  # NiftiDataset3D.py:119-137: label value -> class index
-        for idx, value in enumerate(self.labels):
-            remapped[label_np == value] = idx
         image_np = np.stack([np.asarray(im.array, np.float32) for im in sample['image']], axis=-1)
-        return image_np.astype(np.float32), remapped
+        return image_np.astype(np.float32), np.asarray(sample['label'].array).astype(np.int32)
 
     def get_dataset(self, num_parallel_calls=1, prefetch=None):
         """NiftiDataset3D.py:39-55.  The reference maps `input_parser` through tf.py_func with
@@ -194,21 +218,56 @@ def resample_image(im, spacing, size, origin, order):
                        tuple(float(v) for v in origin), im.direction)
 
 
+def _like(im, array):
+    return nifti.Image(array, im.spacing, im.origin, im.direction)
+
+
+def _cast(values, dtype):
+    """static_cast<pixel type>: truncation toward zero for integer images (after clamping to the type's range, as
+    NumPy leaves an out-of-range cast undefined), rounding to nearest for float32."""
+    dtype = np.dtype(dtype)
+    if dtype.kind in "iu":
+        info = np.iinfo(dtype)
+        return np.trunc(np.clip(values, info.min, info.max)).astype(dtype)
+    return np.asarray(values).astype(dtype)
+
+
+def intensity_window(a, window_min, window_max, out_min=0.0, out_max=255.0):
+    """sitk.IntensityWindowingImageFilter: below / above the window -> out_min / out_max, inside x * scale + shift in
+    double precision, cast back to the image's own pixel type; the window bounds are first cast to that type, which
+    truncates them for integer images (CT in int16 comes out as whole numbers 0..255)."""
+    a = np.asarray(a)
+    if a.dtype.kind in "iu":
+        lo, hi = int(_cast(window_min, a.dtype)), int(_cast(window_max, a.dtype))
+    else:
+        lo, hi = float(a.dtype.type(window_min)), float(a.dtype.type(window_max))
+    scale = (out_max - out_min) / (hi - lo) if hi != lo else 0.0
+    v = a.astype(np.float64) * scale + (out_min - lo * scale)
+    v = np.where(a < lo, out_min, np.where(a > hi, out_max, v))
+    return _cast(v, a.dtype)
+
+
 class StatisticalNormalization(object):
-    """NiftiDataset3D.py:210-254: clamp to mean +- sigma*std, rescale to 0..255."""
+    """NiftiDataset3D.py:210-254: window mean +- sigma * std (StatisticsImageFilter: the N-1 estimate), clamped to the
+    pixel type's range, mapped to 0..255; `pre_norm` first standardises the image (NormalizeImageFilter, float)."""
 
     def __init__(self, sigma, pre_norm=False):
         self.name = 'StatisticalNormalization'
+        assert isinstance(sigma, float)
         self.sigma, self.pre_norm = sigma, pre_norm
 
     def __call__(self, sample):
         def norm(im):
-            a = np.asarray(im.array, np.float32)
+            a = np.asarray(im.array)
             if self.pre_norm:
-                a = (a - a.mean()) / max(a.std(), 1e-6)
-            lo, hi = a.mean() - self.sigma * a.std(), a.mean() + self.sigma * a.std()
-            a = (np.clip(a, lo, hi) - lo) / max(hi - lo, 1e-6) * 255.0
-            return nifti.Image(a.astype(np.float32), im.spacing, im.origin, im.direction)
+                d = a.astype(np.float64)
+                a = ((d - d.mean()) / max(d.std(ddof=1), 1e-30)).astype(np.float32)
+            d = a.astype(np.float64)
+            mean, std = d.mean(), (d.std(ddof=1) if d.size > 1 else 0.0)
+            info = np.iinfo(a.dtype) if a.dtype.kind in "iu" else np.finfo(a.dtype)
+            hi = min(mean + self.sigma * std, float(info.max))
+            lo = max(mean - self.sigma * std, float(info.min))
+            return _like(im, intensity_window(a, lo, hi))
         return _map(sample, norm)
 
 
@@ -217,27 +276,26 @@ class ManualNormalization(object):
 
     def __init__(self, windowMin, windowMax):
         self.name = 'ManualNormalization'
+        assert isinstance(windowMax, (int, float)) and isinstance(windowMin, (int, float))
         self.windowMin, self.windowMax = float(windowMin), float(windowMax)
 
     def __call__(self, sample):
-        def norm(im):
-            a = (np.clip(np.asarray(im.array, np.float32), self.windowMin, self.windowMax) - self.windowMin) \
-                / max(self.windowMax - self.windowMin, 1e-6) * 255.0
-            return nifti.Image(a.astype(np.float32), im.spacing, im.origin, im.direction)
-        return _map(sample, norm)
+        return _map(sample, lambda im: _like(im, intensity_window(im.array, self.windowMin, self.windowMax)))
 
 
-class Normalization(StatisticalNormalization):
-    """NiftiDataset3D.py:167-185 (0..255 rescale of the full range)."""
+class Normalization(object):
+    """NiftiDataset3D.py:167-185 (RescaleIntensityImageFilter): the full intensity range -> 0..255, in the image's
+    pixel type.  Applied per modality (the reference hands the filter the modality list itself)."""
 
     def __init__(self):
         self.name = 'Normalization'
 
     def __call__(self, sample):
         def norm(im):
-            a = np.asarray(im.array, np.float32)
-            a = (a - a.min()) / max(a.max() - a.min(), 1e-6) * 255.0
-            return nifti.Image(a, im.spacing, im.origin, im.direction)
+            a = np.asarray(im.array)
+            lo, hi = float(a.min()), float(a.max())
+            scale = 255.0 / (hi - lo) if hi != lo else 0.0
+            return _like(im, _cast(a.astype(np.float64) * scale - lo * scale, a.dtype))
         return _map(sample, norm)
 
 
@@ -278,97 +336,143 @@ class Padding(object):
 
 
 class RandomCrop(object):
-    """NiftiDataset3D.py:458-551: random crop of `output_size`; with probability 1-drop_ratio the crop
-    must contain at least `min_pixel` foreground voxels."""
+    """NiftiDataset3D.py:458-551: random crop of `output_size`, redrawn until it holds at least `min_pixel` foreground
+    voxels or, with probability `drop_ratio` per failed draw, is accepted anyway."""
+
+    MAX_DRAWS = 100000  # the reference loops for ever on a label-free case with drop_ratio 0
 
     def __init__(self, output_size, drop_ratio=0.1, min_pixel=1):
         self.name = 'Random Crop'
+        assert isinstance(output_size, (int, tuple, list))
         self.output_size = (output_size,) * 3 if isinstance(output_size, int) else tuple(output_size)
+        assert len(self.output_size) == 3
+        assert isinstance(drop_ratio, (int, float))
+        if not 0 <= drop_ratio <= 1:
+            raise RuntimeError('Drop ratio should be between 0 and 1')
+        assert isinstance(min_pixel, int)
+        if min_pixel < 0:
+            raise RuntimeError('Min label pixel count should be integer larger than 0')
         self.drop_ratio, self.min_pixel = drop_ratio, min_pixel
 
-    def _starts(self, shape, centre=None, jitter=None):
-        out = []
-        for i, (s, o) in enumerate(zip(shape, self.output_size)):
-            hi = s - o
-            if centre is None:
-                out.append(random.randint(0, hi) if hi > 0 else 0)
-            else:
-                c = int(centre[i] + random.uniform(-jitter, jitter)) - o // 2
-                out.append(min(max(c, 0), hi) if hi > 0 else 0)
-        return out
+    def drop(self, probability):
+        return random.random() <= probability
 
     def _crop(self, im, st):
         sl = tuple(slice(s, s + o) for s, o in zip(st, self.output_size))
         origin = tuple(o + k * sp for o, k, sp in zip(im.origin, st, im.spacing))  # RegionOfInterest keeps physical positions
         return nifti.Image(np.asarray(im.array)[sl], im.spacing, origin, im.direction)
 
-    def __call__(self, sample):
-        lab = np.asarray(sample['label'].array)
-        st = self._starts(lab.shape)
-        for _ in range(50):
-            st = self._starts(lab.shape)
-            sl = tuple(slice(s, s + o) for s, o in zip(st, self.output_size))
-            if (lab[sl] > 0).sum() >= self.min_pixel or random.random() < self.drop_ratio:
-                break
+    def _crop_sample(self, sample, st):
         return _map(sample, lambda im: self._crop(im, st), lambda lb: self._crop(lb, st))
+
+    def __call__(self, sample):
+        fg = np.asarray(sample['label'].array) >= 1
+        old, new = fg.shape, self.output_size
+        for _ in range(self.MAX_DRAWS):
+            # np.random.randint's upper bound is exclusive: the last admissible start is never drawn (as in the reference)
+            st = [0 if old[i] <= new[i] else int(np.random.randint(0, old[i] - new[i])) for i in range(3)]
+            sl = tuple(slice(s, s + o) for s, o in zip(st, new))
+            if fg[sl].sum() >= self.min_pixel or self.drop(self.drop_ratio):
+                break
+        return self._crop_sample(sample, st)
 
 
 class ConfidenceCrop2(RandomCrop):
-    """NiftiDataset3D.py:661-793: crop centred on a random connected foreground component with
-    probability `probability`, jittered by `rand_range`; random crop otherwise."""
+    """NiftiDataset3D.py:661-793: with probability `probability` (in tenths: int(10p) ones against int(10(1-p)) zeros)
+    a crop centred on the bounding box of a random connected foreground component, shifted per axis by a uniform
+    integer in [-rand_range, rand_range] and clamped into the volume; otherwise a random region (`random_empty_region`:
+    redrawn until it holds no foreground)."""
 
     def __init__(self, output_size, rand_range=3, probability=0.5, random_empty_region=False):
         super().__init__(output_size)
         self.name = 'Confidence Crop 2'
-        self.rand_range, self.probability = rand_range, probability
+        assert isinstance(rand_range, (int, tuple, list))
+        self.rand_range = (rand_range,) * 3 if isinstance(rand_range, int) else tuple(rand_range)
+        assert len(self.rand_range) == 3 and all(r >= 0 for r in self.rand_range)
+        assert isinstance(probability, float) and 0 <= probability <= 1
+        self.probability = probability
+        assert isinstance(random_empty_region, bool)
+        self.random_empty_region = random_empty_region
+
+    def _random_index(self, shape):
+        # range(0, size - crop - 1): the reference raises on a one-voxel margin; that case starts at 0 here
+        return [0 if shape[i] - self.output_size[i] - 1 <= 0 else random.choice(range(0, shape[i] - self.output_size[i] - 1))
+                for i in range(3)]
+
+    def RandomRegion(self, sample):
+        return self._crop_sample(sample, self._random_index(np.asarray(sample['label'].array).shape))
+
+    def RandomEmptyRegion(self, sample):
+        lab = np.asarray(sample['label'].array)
+        for _ in range(self.MAX_DRAWS):
+            st = self._random_index(lab.shape)
+            if lab[tuple(slice(s, s + o) for s, o in zip(st, self.output_size))].sum() < 1:
+                break
+        return self._crop_sample(sample, st)
 
     def __call__(self, sample):
-        lab = np.asarray(sample['label'].array)
-        st = self._starts(lab.shape)
-        if random.random() <= self.probability and (lab > 0).any():
+        lab = np.asarray(sample['label'].array).astype(np.int16)
+        choices = [0] * int(10 * (1 - self.probability)) + [1] * int(10 * self.probability)
+        positive = random.choice(choices)
+        n = 0
+        if positive:
             from scipy import ndimage
-            comp, n = ndimage.label(lab > 0)
-            k = random.randint(1, n)
-            centre = [float(c) for c in ndimage.center_of_mass(comp == k)]
-            st = self._starts(lab.shape, centre, self.rand_range)
-        return _map(sample, lambda im: self._crop(im, st), lambda lb: self._crop(lb, st))
+            comp, n = ndimage.label(lab != 0)
+        if not positive or n == 0:
+            return self.RandomEmptyRegion(sample) if self.random_empty_region else self.RandomRegion(sample)
+        selected = random.choice(range(0, n)) + 1
+        box = ndimage.find_objects(comp)[selected - 1]
+        index = [0, 0, 0]
+        for i in range(3):
+            extent = box[i].stop - box[i].start
+            index[i] = box[i].start + int(extent / 2) - int(self.output_size[i] / 2) + \
+                random.choice(range(-1 * self.rand_range[i], self.rand_range[i] + 1))
+            if lab.shape[i] - index[i] - 1 < self.output_size[i]:
+                index[i] = lab.shape[i] - self.output_size[i] - 1
+            if index[i] < 0:
+                index[i] = 0
+        return self._crop_sample(sample, index)
 
 
 class RandomNoise(object):
-    """NiftiDataset3D.py:553-572: additive Gaussian noise on the images."""
+    """NiftiDataset3D.py:553-572 (AdditiveGaussianNoiseImageFilter): x + N(0, sigma) on every modality, clamped and
+    cast back to the pixel type."""
 
-    def __init__(self, std=0.1):
+    def __init__(self, sigma=5):
         self.name = 'Random Noise'
-        self.std = std
+        self.sigma = sigma
 
     def __call__(self, sample):
         def noise(im):
-            a = np.asarray(im.array, np.float32)
-            return nifti.Image(a + np.random.normal(0, self.std, a.shape).astype(np.float32), im.spacing, im.origin, im.direction)
+            a = np.asarray(im.array)
+            return _like(im, _cast(a.astype(np.float64) + np.random.normal(0, self.sigma, a.shape), a.dtype))
         return _map(sample, noise)
 
 
 class RandomFlip(object):
-    """NiftiDataset3D.py:187-208."""
+    """NiftiDataset3D.py:187-208: one coin per sample; heads flips all the axes marked in `axes` together."""
 
-    def __init__(self, axes=[False, False, False]):
+    def __init__(self, axes):
         self.name = 'Flip'
+        assert len(axes) > 0 and len(axes) <= 3
         self.axes = axes
 
     def __call__(self, sample):
-        flips = [ax for ax, on in enumerate(self.axes) if on and random.random() > 0.5]
-        f = lambda im: nifti.Image(np.flip(np.asarray(im.array), flips).copy() if flips else im.array, im.spacing, im.origin, im.direction)
+        if not np.random.randint(2, size=1)[0]:
+            return sample
+        flips = [ax for ax, on in enumerate(self.axes) if on]
+        f = lambda im: _like(im, np.flip(np.asarray(im.array), flips).copy() if flips else im.array)
         return _map(sample, f, f)
 
 
 class Invert(object):
-    """NiftiDataset3D.py:330-343."""
+    """NiftiDataset3D.py:330-343 (InvertIntensityImageFilter, maximum 255): 255 - x in the image's pixel type."""
 
     def __init__(self):
         self.name = 'Invert'
 
     def __call__(self, sample):
-        return _map(sample, lambda im: nifti.Image(255.0 - np.asarray(im.array, np.float32), im.spacing, im.origin, im.direction))
+        return _map(sample, lambda im: _like(im, _cast(255.0 - np.asarray(im.array).astype(np.float64), np.asarray(im.array).dtype)))
 
 
 class ExtremumNormalization(object):
