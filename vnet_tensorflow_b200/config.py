@@ -76,7 +76,7 @@ class Config:
     evaluate_batch: int = 1
     evaluate_probability_output: bool = True
     evaluate_lcc: bool = False
-    evaluate_volume_threshold: int = 0
+    evaluate_volume_threshold: float = 0.0
     evaluate_pipeline: Optional[str] = None
     evaluate_map_label_values: bool = False
 
@@ -142,7 +142,7 @@ def from_dict(cfg: dict) -> Config:
     c.evaluate_batch = int(_get(e, "BatchSize", default=1))
     c.evaluate_probability_output = bool(_get(e, "ProbabilityOutput", default=True))
     c.evaluate_lcc = bool(_get(e, "LargestConnectedComponent", default=False))
-    c.evaluate_volume_threshold = int(_get(e, "VolumeThreshold", default=0))
+    c.evaluate_volume_threshold = float(_get(e, "VolumeThreshold", default=0))  # physical size, model.py:125
     c.evaluate_pipeline = _get(e, "Pipeline", default=None)
     c.evaluate_map_label_values = bool(_get(e, "MapLabelValues", default=False))  # extension: class index -> SegmentationClasses value
     if c.network_name != "VNet":

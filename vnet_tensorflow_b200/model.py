@@ -220,6 +220,8 @@ class image2label(object):
             print("{}: Saving checkpoint of epoch {} at {}...".format(_now(), epoch + 1, self.ckpt_dir))
             checkpoint.save(self.engine, self.ckpt_dir, self.engine.global_step, epoch + 1, self.cfg.checkpoint_format)
             print("{}: Saving checkpoint succeed".format(_now()))
+        for w in self.__dict__.pop("_event_writers", {}).values():  # model.py:812-815
+            w.close()
 
     # ---- evaluation ---------------------------------------------------------------------------
     def evaluate_single_3D(self, images_np: np.ndarray):
