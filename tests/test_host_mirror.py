@@ -464,3 +464,30 @@ def test_labels_are_remapped_before_the_transforms(tmp_path):
     nifti.write(str(case / "label.nii"), nifti.Image(lab, (2.0, 1.0, 1.0)))
     with pytest.raises(Exception, match="Header info inconsistent"):
         next(iter(ds.get_dataset()))
+
+
+def test_shipped_config_and_pipeline_produce_training_patches(tmp_path):
+    """configs/config_b200_64.json + configs/pipeline3D_b200.yaml: every key loads, every transform resolves and the
+    training pipeline turns a NIfTI case into a 64^3 patch with the (float32 [X,Y,Z,M], int32 [X,Y,Z]) contract."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = config_mod.load(os.path.join(root, "configs", "config_b200_64.json"))
+    assert cfg.patch_shape == (64, 64, 64) and cfg.num_convolutions == (1, 2, 3, 3) and cfg.loss_weights == (0.1, 1.0)
+    assert cfg.evaluate_stride == (32, 32, 32) and cfg.checkpoint_format == "npz" and cfg.data_workers == 4
+    m = image2label.__new__(image2label)
+    pipe = os.path.join(root, cfg.training_pipeline)
+    names = {ph: [t.name for t in m._transforms(pipe, ph)] for ph in ("train", "test", "evaluate")}
+    assert names["train"] == ['StatisticalNormalization', 'Resample', 'Padding', 'Confidence Crop 2', 'Flip', 'Random Noise']
+    assert names["test"] == names["train"][:4] and names["evaluate"] == names["train"][:3]
+    case = tmp_path / "case"
+    os.makedirs(case)
+    rng = np.random.default_rng(0)
+    vol = rng.normal(30, 200, (50, 44, 30)).astype(np.int16)
+    lab = np.zeros(vol.shape, np.uint8)
+    lab[20:30, 10:20, 8:16] = 1
+    nifti.write(str(case / "image.nii"), nifti.Image(vol, (1.0, 1.0, 1.5)))
+    nifti.write(str(case / "label.nii"), nifti.Image(lab, (1.0, 1.0, 1.5)))
+    ds = NiftiDataset3D.NiftiDataset(str(tmp_path), cfg.image_filenames, cfg.label_filename, m._transforms(pipe, "train"),
+                                     train=True, labels=cfg.label_classes).get_dataset()
+    image, label = next(iter(ds))
+    assert image.shape == (64, 64, 64, 1) and image.dtype == np.float32 and label.shape == (64, 64, 64) and label.dtype == np.int32
+    assert set(np.unique(label)) <= {0, 1} and -30 <= image.min() and image.max() <= 285
