@@ -242,6 +242,8 @@ class _Ctx:
         """tf.layers.batch_normalization(momentum=.99, epsilon=1e-3, training=True) on a 5-D tensor
         (non-fused path): biased batch variance over (N,X,Y,Z); moving stats updated with the same."""
         base = scope + "/batch_normalization" + ("" if idx == 0 else "_%d" % idx)
+        if self.collect is not None and idx == 0:
+            self.collect[scope + ":bn_in"] = x  # what the first batch norm of the scope normalises (conv [+ block input])
         mean = x.mean(dim=(0, 1, 2, 3))
         var = ((x - mean) ** 2).mean(dim=(0, 1, 2, 3))
         y = (x - mean) * torch.rsqrt(var + BN_EPS) * self.p[base + "/gamma"] + self.p[base + "/beta"]

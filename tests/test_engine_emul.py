@@ -275,3 +275,47 @@ def test_attention_path_training_steps_follow_oracle(emul_lib):
     for k in ("attention/AttentionModule/encoder/Variable", "output/output/output/Variable_1", "output/encoder/batch_normalization_8/gamma"):
         assert np.abs(eng.get_param(k) - p[k]).max() < 2e-4, k  # two Adam steps move each weight by ~2e-3
     eng.close()
+
+
+@pytest.mark.parametrize("spec,N", [(SPEC_A, 2), (SPEC_B, 1)])
+def test_every_unit_against_the_oracle_taps(emul_lib, spec, N):
+    """The per-op view the fused engine offers (vnb_read_tensor around vnb_forward_backward): for every unit the
+    tensor its first batch norm normalises (convolution output, plus the block input where networks.py:318 adds it),
+    the unit's output activation after the BN chain / PReLU, and dL/d(that BN input) - against the oracle's taps.
+    Covers layers2.convolution / down_convolution / up_convolution, the batch-norm chains, PReLU and, at the output
+    layer, the softmax-Dice backward (dL/dlogits reaches the head's batch norm)."""
+    P = 8
+    params = perturbed_params(spec, 3)
+    img, lab = synth_batch(1, N, P, spec.in_channels, spec.num_classes)
+    weights = (0.1, 0.5, 1.0)[-spec.num_classes:]
+    eng = engine_for(spec, P, N, "weighted_sorensen", weights, emul_lib)
+    eng.set_params(params)
+    loss = eng.forward_backward(img, lab, dropout_rate=0.0)
+    col = {}
+    tp = R.to_torch(params, torch.float64, requires_grad=True)
+    logits, _ = R.forward(tp, torch.from_numpy(img).double(), spec, collect=col)
+    for t in col.values():
+        if t.requires_grad:  # (the tiled image in front of the input batch norm is a constant)
+            t.retain_grad()
+    ref_loss = R.loss_from_logits(logits, torch.from_numpy(lab), "weighted_sorensen", weights)
+    ref_loss.backward()
+    assert abs(loss - float(ref_loss.detach())) < 2e-6
+    seen = {"act": 0, "bn_in": 0}
+    for name, t in col.items():
+        scope, _, kind = name.partition(":")
+        shape = tuple(t.shape)
+        if kind == "bn_in":
+            if scope == "vnet/input_layer" and spec.in_channels == 1:
+                continue  # the tiled image itself (networks.py:258): no convolution unit in front of this batch norm
+            z = eng.read_tensor(scope, 2, N, shape[-1], shape[1:4])
+            dz = eng.read_tensor(scope, 1, N, shape[-1], shape[1:4])
+            assert rel_err(z, t.detach().numpy()) < 5e-6, name
+            assert rel_err(dz, t.grad.numpy()) < 2e-5, name
+            seen["bn_in"] += 1
+        else:
+            a = eng.read_tensor(scope, 0, N, shape[-1], shape[1:4])
+            assert rel_err(a, t.detach().numpy()) < 5e-6, name
+            seen["act"] += 1
+    n_units = sum(1 for k in eng.variables() if k.endswith("/weights"))
+    assert seen["bn_in"] >= n_units - 2 * spec.num_levels and seen["act"] >= n_units  # up-convolutions tap outputs only
+    eng.close()
