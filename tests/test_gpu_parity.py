@@ -382,3 +382,38 @@ def test_sliding_window_evaluation_matches_the_reference_loop(gpu_lib, precision
     with pytest.raises(Exception):
         eng.evaluate_volume(vol[:8], stride, B)                 # smaller than the patch: the caller must pad
     eng.close()
+
+
+def test_every_unit_against_the_oracle_taps(gpu_lib):
+    """vnb_read_tensor around vnb_forward_backward on the exact-fp32 path: every unit's batch-norm input, output
+    activation and dL/d(BN input) against the oracle's taps (the per-op view of the fused BN / PReLU / loss passes)."""
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=4, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=2)
+    P, N = 16, 2
+    params = perturbed_params(spec, 3)
+    img, lab = synth_batch(1, N, P, 1, 2)
+    eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 1.0), gpu_lib)
+    eng.set_params(params)
+    loss = eng.forward_backward(img, lab, dropout_rate=0.0)
+    col = {}
+    tp = R.to_torch(params, torch.float64, requires_grad=True)
+    logits, _ = R.forward(tp, torch.from_numpy(img).double(), spec, collect=col)
+    for t in col.values():
+        if t.requires_grad:
+            t.retain_grad()
+    ref_loss = R.loss_from_logits(logits, torch.from_numpy(lab), "weighted_sorensen", (0.1, 1.0))
+    ref_loss.backward()
+    assert abs(loss - float(ref_loss.detach())) < 1e-5
+    worst = {"z": 0.0, "a": 0.0, "dz": 0.0}
+    for name, t in col.items():
+        scope, _, kind = name.partition(":")
+        shape = tuple(t.shape)
+        if kind == "bn_in":
+            if scope == "vnet/input_layer":
+                continue
+            worst["z"] = max(worst["z"], rel_err(eng.read_tensor(scope, 2, N, shape[-1], shape[1:4]), t.detach().numpy()))
+            worst["dz"] = max(worst["dz"], rel_err(eng.read_tensor(scope, 1, N, shape[-1], shape[1:4]), t.grad.numpy()))
+        else:
+            worst["a"] = max(worst["a"], rel_err(eng.read_tensor(scope, 0, N, shape[-1], shape[1:4]), t.detach().numpy()))
+    print("per-unit worst relative errors:", worst)
+    assert worst["z"] < LOGIT_TOL["fp32"] and worst["a"] < LOGIT_TOL["fp32"] and worst["dz"] < GRAD_TOL["fp32"]
+    eng.close()
