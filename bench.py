@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=None, help="patches per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("VNB_BENCH_PRECISION"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-bn", action="store_true", help="N>1: batch-norm statistics of the global batch (off: local statistics)")
     args = ap.parse_args()
     pre = PRESETS[args.config]
     args.preset = pre
@@ -261,6 +262,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         uid = [eng.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         eng.comm_init(rank, world, uid[0])
+        if args.sync_bn:
+            eng.comm_sync_bn(True)
 
     def barrier():
         if world > 1:
@@ -347,6 +350,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                                               " + ring all-reduce" if world > 1 else "", P, M,
                                                               "y" if M == 1 else "ies", K, B, pre["name"]),
                        "patch": P, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "batch_norm": "synchronised" if (args.sync_bn and world > 1) else "local statistics",
                        "precision": args.precision, "dropout": dropout,
                        "attention": bool(att),
                        "l2": "per-step working set (activations %.1f GB) >> 126 MB L2, no explicit flush" % (0.7 * 3 * B * (P / 128) ** 3)},

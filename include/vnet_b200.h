@@ -132,6 +132,14 @@ int vnb_apply_gradients(vnb_handle* h);
 int vnb_comm_unique_id(void* id_out_128_bytes);
 int vnb_comm_init(vnb_handle* h, int rank, int world, const void* unique_id_128_bytes);
 int vnb_comm_world(vnb_handle* h, int* rank, int* world);
+/* synchronised batch norm: batch statistics (sum z, sum z^2) and the two backward sums of every
+ * training-mode batch norm are summed over the ranks, which makes `world` ranks with local batch n reproduce one
+ * device with batch world*n (the reference's own arithmetic at that batch size).  Off by default: local statistics,
+ * no extra exchange.  vnb_comm_sync_bn uses a second NCCL communicator on the compute stream; the callback form
+ * hands each [n] double row to the caller on the host (used with gloo in the CPU tests; NULL switches it off). */
+int vnb_comm_sync_bn(vnb_handle* h, int on);
+typedef int (*vnb_allreduce_fn)(double* host_values, int n, void* user); /* sum in place over the ranks; 0 = ok */
+int vnb_set_stats_allreduce(vnb_handle* h, vnb_allreduce_fn fn, void* user, int world);
 
 /* device-resident stepping (benchmark 'value' leg): upload once, then step on the resident batch */
 int vnb_upload_batch(vnb_handle* h, const float* images, const int32_t* labels, int n);

@@ -21,6 +21,7 @@ LOSSES = {
 ATTENTION_LOSSES = {None: 0, "none": 0, "l2": 1, "abs": 2}
 OPTIMIZERS = {"Adam": 0, "SGD": 1, "Momentum": 2, "NesterovMomentum": 3}
 SLOT_VALUE, SLOT_GRAD, SLOT_ADAM_M, SLOT_ADAM_V = 0, 1, 2, 3
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.c_void_p)  # vnb_allreduce_fn
 
 
 class VnbConfig(C.Structure):
@@ -68,6 +69,8 @@ _PROTOTYPES = {
     "vnb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "vnb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vnb_comm_world": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vnb_comm_sync_bn": (C.c_int, [C.c_void_p, C.c_int]),
+    "vnb_set_stats_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "vnb_upload_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "vnb_train_step_resident": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_uint64]),
     "vnb_event_record": (C.c_int, [C.c_void_p, C.c_int]),

@@ -27,6 +27,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;  // NCCL >= 2.18 (optional)
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -51,6 +52,7 @@ struct NcclApi {
     a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(sym("ncclGetUniqueId"));
     a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(sym("ncclCommInitRank"));
     a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
+    a.CommSplit = reinterpret_cast<decltype(a.CommSplit)>(dlsym(h, "ncclCommSplit"));
     a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
     a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
     a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
@@ -101,6 +103,7 @@ class Comm {
     e.set_grad_hook([this, &e](int bucket) { this->on_bucket_ready(e, bucket); });
   }
   ~Comm() {
+    if (stats_comm_) NcclApi::get().CommDestroy(stats_comm_);
     if (scratch_) cudaFree(scratch_);
     for (auto ev : events_) cudaEventDestroy(ev);
     cudaEventDestroy(done_);
@@ -111,6 +114,28 @@ class Comm {
   int world() const { return world_; }
 
   void begin_step(Engine&) { pending_ = 0; }
+
+  // Synchronised batch norm: the per-channel statistic rows are summed with ncclAllReduce on the *compute* stream
+  // (they sit on the critical path between a reduction kernel and its finalize kernel), through a communicator of
+  // their own so that they never queue behind the gradient buckets on the side stream.  Every rank issues the same
+  // sequence of collectives on both communicators (the schedule is data independent).  Collective call.
+  void enable_sync_bn(Engine& e, bool on) {
+    if (!on || world_ == 1) {
+      e.set_stats_hook(nullptr, 1);
+      return;
+    }
+    NcclApi& api = NcclApi::get();
+    if (!stats_comm_) {
+      if (!api.CommSplit) throw std::runtime_error("NCCL: synchronised batch norm needs ncclCommSplit (NCCL >= 2.18)");
+      VNB_NCCL_OK(api.CommSplit(comm_, 0, rank_, &stats_comm_, nullptr));
+    }
+    ncclComm_t c = stats_comm_;
+    e.set_stats_hook(
+        [c, &e](double* dev, int n) {
+          VNB_NCCL_OK(NcclApi::get().AllReduce(dev, dev, static_cast<size_t>(n), ncclDouble, ncclSum, c, e.stream()));
+        },
+        world_);
+  }
 
   // called from Engine::backward (host side, in stream order) when bucket `bi` is complete
   void on_bucket_ready(Engine& e, int bi) {
@@ -172,6 +197,7 @@ class Comm {
 
   int rank_, world_;
   ncclComm_t comm_ = nullptr;
+  ncclComm_t stats_comm_ = nullptr;
   cudaStream_t stream_ = nullptr;
   bool use_ring_ = true;
   float* scratch_ = nullptr;

@@ -149,6 +149,13 @@ class Engine {
   };
   const std::vector<Bucket>& buckets() const { return buckets_; }
   void set_grad_hook(std::function<void(int)> hook) { grad_hook_ = std::move(hook); }
+  // Synchronised batch norm: `hook(dev, n)` sums n doubles in place over `world` ranks, ordered after everything
+  // enqueued on stream() and before anything enqueued later; an empty hook restores local statistics.
+  void set_stats_hook(std::function<void(double*, int)> hook, int world) {
+    stats_hook_ = std::move(hook);
+    stats_world_ = stats_hook_ ? std::max(world, 1) : 1;
+  }
+  bool sync_bn() const { return static_cast<bool>(stats_hook_); }
 
   const std::vector<ParamEntry>& params() const { return entries_; }
   const EngineConfig& config() const { return cfg_; }
@@ -775,6 +782,8 @@ class Engine {
       att_partial_ = dev_alloc<double>(kMaxRedBlocks);
     }
     partial_ = dev_alloc<double>(static_cast<size_t>(kMaxRedBlocks) * 3 * std::max(maxC, 4 * kMaxClasses) + 64);
+    sync_stride_ = std::max(maxC, 4);
+    sync_buf_ = dev_alloc<double>(static_cast<size_t>(5) * sync_stride_);
     wflip_ = dev_alloc<float>(max_w5);
     labels_dev_ = dev_alloc<int32_t>(voxels(NB));
     softmax_dev_ = dev_alloc<float>(voxels(NB) * cfg_.num_classes);
@@ -1049,8 +1058,19 @@ class Engine {
           }
         }
       }
-      VNB_LAUNCH(bn_finalize_fwd_kernel, u.Cout, 128, 0, stream_, (const double*)partial_, nblk, nq_stride,
-                 u.Cout, static_cast<double>(V), u.chain, bn_params(u), u.kind == U_INPUT_TILE ? 1 : 0,
+      const double* fin_partial = partial_;
+      double count = static_cast<double>(V);
+      if (stats_hook_ && !u.bn_inference) {  // global-batch statistics: (sum z, sum z^2) summed over the ranks
+        const int PC = u.kind == U_INPUT_TILE ? 1 : u.Cout;
+        VNB_LAUNCH(partial_collapse_kernel, nq_stride * PC, 128, 0, stream_, (const double*)partial_, nblk, nq_stride, PC, sync_buf_);
+        ++launches_;
+        stats_hook_(sync_buf_, nq_stride * PC);
+        fin_partial = sync_buf_;
+        nblk = 1;
+        count *= stats_world_;
+      }
+      VNB_LAUNCH(bn_finalize_fwd_kernel, u.Cout, 128, 0, stream_, fin_partial, nblk, nq_stride,
+                 u.Cout, count, u.chain, bn_params(u), u.kind == U_INPUT_TILE ? 1 : 0,
                  update_moving ? 1 : 0, u.mean, u.var, u.scale, u.shift, u.bn_inference ? 1 : 0);
       ApplyArgs ap;
       ap.z = u.z;
@@ -1159,9 +1179,22 @@ class Engine {
       }
       gp.dalpha = (u.has_act && !u.relu) ? grads_ + u.alpha_off : nullptr;
       gp.dbias = u.bn_inference ? grads_ + u.b_off : nullptr;
-      VNB_LAUNCH(bn_finalize_bwd_kernel, u.Cout, 128, 0, stream_, (const double*)partial_, nblk, u.Cout,
+      const double* fin_partial = partial_;
+      const double* gsum = nullptr;
+      if (stats_hook_ && !u.bn_inference) {  // R0, R1 of the global batch for dL/dz; parameter gradients stay local
+        double* local = sync_buf_;
+        double* global = sync_buf_ + static_cast<size_t>(3) * sync_stride_;
+        VNB_LAUNCH(partial_collapse_kernel, 3 * u.Cout, 128, 0, stream_, (const double*)partial_, nblk, 3, u.Cout, local);
+        ++launches_;
+        VNB_CUDA_OK(cudaMemcpyAsync(global, local, sizeof(double) * 2 * u.Cout, cudaMemcpyDeviceToDevice, stream_));
+        stats_hook_(global, 2 * u.Cout);
+        fin_partial = local;
+        gsum = global;
+        nblk = 1;
+      }
+      VNB_LAUNCH(bn_finalize_bwd_kernel, u.Cout, 128, 0, stream_, fin_partial, nblk, u.Cout,
                  static_cast<double>(V), u.chain, bn_params(u), (const double*)u.var, gp, u.P, u.Q, u.S,
-                 u.bn_inference ? 1 : 0);
+                 u.bn_inference ? 1 : 0, gsum, static_cast<double>(V) * stats_world_);
       ++launches_;
       if (u.kind == U_INPUT_TILE) {  // image needs no gradient
         notify_bucket(ui);
@@ -1491,6 +1524,10 @@ class Engine {
   std::vector<void*> allocs_;
   std::vector<Bucket> buckets_;
   std::function<void(int)> grad_hook_;
+  std::function<void(double*, int)> stats_hook_;   // synchronised batch norm: sum over the ranks (empty = local statistics)
+  int stats_world_ = 1;
+  double* sync_buf_ = nullptr;                       // [3][sync_stride_] collapsed local sums + [2][sync_stride_] exchanged sums
+  int sync_stride_ = 0;
   size_t n_train_ = 0, n_state_ = 0;
   int image_act_ = -1, head_act_ = -1;
   int vnet_logits_act_ = -1, att_logits_act_ = -1, gate_unit_ = -1;

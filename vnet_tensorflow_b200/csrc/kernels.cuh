@@ -135,6 +135,25 @@ __global__ void image_stats_kernel(const float* __restrict__ img, long long V, d
 }
 
 // ---------------------------------------------------------------------------------------------
+// Synchronised batch norm (data parallel, optional): the per-block partial sums partial[blk][nq][PC] are collapsed
+// to one row out[nq][PC] in a fixed order; the engine sums that row over the ranks and hands it to the finalize
+// kernels as a one-block partial array.  One block per (quantity, channel).
+// ---------------------------------------------------------------------------------------------
+__global__ void partial_collapse_kernel(const double* __restrict__ partial, int nblk, int nq, int PC,
+                                        double* __restrict__ out) {
+  const int qc = blockIdx.x;
+  __shared__ double col_red[128];
+  double s = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) s += partial[static_cast<size_t>(b) * nq * PC + qc];
+  col_red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double t = 0.0;
+  for (unsigned i = 0; i < blockDim.x; ++i) t += col_red[i];
+  out[qc] = t;
+}
+
+// ---------------------------------------------------------------------------------------------
 // BN forward finalize: partial sums -> mu, sigma^2 -> chain closed form -> scale/shift; optional
 // moving-average update (only train_op runs UPDATE_OPS, model.py:665-666).
 // One thread per channel. `single_channel_stats`: all channels share partial column 0 (tiled input).
@@ -308,7 +327,8 @@ struct BnGradPtrs {  // where the parameter gradients go (flat gradient buffer),
 __global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int nblk, int C, double count,
                                        int chain, BnParams bp, const double* __restrict__ var,
                                        BnGradPtrs gp, float* __restrict__ P, float* __restrict__ Q,
-                                       float* __restrict__ S, int inference = 0) {
+                                       float* __restrict__ S, int inference = 0,
+                                       const double* __restrict__ gsum = nullptr, double gcount = 0.0) {
   const int c = blockIdx.x;  // one block per channel
   __shared__ double fin_red[3][128];
   double p0 = 0, p1 = 0, p2 = 0;
@@ -345,9 +365,12 @@ __global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int n
     if (gp.dalpha) gp.dalpha[c] = static_cast<float>(Ra);
     return;
   }
+  // synchronised batch norm: the statistics belong to the global batch, so dL/dz takes R0, R1 and the count summed
+  // over the ranks (gsum = [2][C]); the parameter gradients below stay local sums - the gradient exchange averages them
+  const double G0 = gsum ? gsum[c] : R0, G1 = gsum ? gsum[C + c] : R1, gc = gsum ? gcount : count;
   P[c] = static_cast<float>(o.A.v);
-  Q[c] = static_cast<float>(-o.A.v * R0 / count);
-  S[c] = static_cast<float>(2.0 * o.A.d[0] * R1 / count);
+  Q[c] = static_cast<float>(-o.A.v * G0 / gc);
+  S[c] = static_cast<float>(2.0 * o.A.d[0] * G1 / gc);
   for (int k = 0; k < nbn; ++k) {
     if (gp.dgamma[k]) gp.dgamma[k][c] = static_cast<float>(R1 * o.A.d[1 + k]);
     if (gp.dbeta[k]) gp.dbeta[k][c] = (k == o.beta_idx) ? static_cast<float>(R0) : 0.f;

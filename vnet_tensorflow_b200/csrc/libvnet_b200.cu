@@ -315,6 +315,42 @@ int vnb_comm_world(vnb_handle* h, int* rank, int* world) {
   });
 }
 
+int vnb_comm_sync_bn(vnb_handle* h, int on) {
+  return guarded([&] {
+    need(h, "handle");
+#ifndef VNB_EMULATE
+    select_device(h);
+    if (!h->comm) throw std::invalid_argument("vnb_comm_sync_bn needs vnb_comm_init first");
+    h->comm->enable_sync_bn(*h->engine, on != 0);
+#else
+    (void)on;
+    throw std::runtime_error("the NCCL communicator is not part of the emulation build; use vnb_set_stats_allreduce");
+#endif
+  });
+}
+
+int vnb_set_stats_allreduce(vnb_handle* h, vnb_allreduce_fn fn, void* user, int world) {
+  return guarded([&] {
+    need(h, "handle");
+    if (!fn) {
+      h->engine->set_stats_hook(nullptr, 1);
+      return;
+    }
+    if (world < 1) throw std::invalid_argument("world must be >= 1");
+    vnb::Engine* e = h->engine.get();
+    e->set_stats_hook(
+        [e, fn, user](double* dev, int n) {  // host round trip: the exchange itself belongs to the caller
+          std::vector<double> host(static_cast<size_t>(n));
+          VNB_CUDA_OK(cudaMemcpyAsync(host.data(), dev, sizeof(double) * n, cudaMemcpyDeviceToHost, e->stream()));
+          VNB_CUDA_OK(cudaStreamSynchronize(e->stream()));
+          if (fn(host.data(), n, user) != 0) throw std::runtime_error("statistics all-reduce callback failed");
+          VNB_CUDA_OK(cudaMemcpyAsync(dev, host.data(), sizeof(double) * n, cudaMemcpyHostToDevice, e->stream()));
+          VNB_CUDA_OK(cudaStreamSynchronize(e->stream()));
+        },
+        world);
+  });
+}
+
 int vnb_upload_batch(vnb_handle* h, const float* images, const int32_t* labels, int n) {
   return guarded([&] {
     need(h, "handle");

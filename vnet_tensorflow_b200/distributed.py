@@ -2,7 +2,8 @@
 broadcast of the NCCL unique id, barriers); gradients move through the engine's own NCCL communicator
 (csrc/comm.cuh).  The reference has no multi-GPU path; semantics are the usual DP ones:
 each rank steps on its own shard of the global batch with *local* batch-norm statistics, gradients are
-averaged, every rank applies the identical optimiser update."""
+averaged, every rank applies the identical optimiser update.  `enable_sync_bn` switches the statistics to the
+global batch: world ranks x local batch n then compute what one device computes at batch world*n."""
 from __future__ import annotations
 
 import os
@@ -51,3 +52,21 @@ def broadcast_params(engine, src: int = 0):
             t = t.cuda()
         dist.broadcast(t, src=src)
         engine.set_param(name, t.cpu().numpy())
+
+
+def enable_sync_bn(engine, on: bool = True):
+    """Synchronised batch norm.  With the NCCL process group the engine exchanges the statistic rows itself
+    (vnb_comm_sync_bn, after init_engine_comm); with gloo (CPU tests) they travel through torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    _, world, _ = env_world()
+    if world == 1 or not on:
+        if not on and dist.is_initialized() and dist.get_backend() == "nccl":
+            engine.comm_sync_bn(False)
+        else:
+            engine.set_stats_allreduce(None, 1)
+        return
+    if dist.get_backend() == "nccl":
+        engine.comm_sync_bn(True)
+    else:
+        engine.set_stats_allreduce(lambda row: dist.all_reduce(torch.from_numpy(row)), world)

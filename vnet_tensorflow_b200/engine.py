@@ -278,3 +278,26 @@ class VNetEngine:
     def comm_init(self, rank: int, world: int, unique_id: bytes):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self.lib.check(self.lib.vnb_comm_init(self._h, rank, world, buf))
+
+    def comm_sync_bn(self, on: bool = True):
+        """Synchronised batch norm over the engine's NCCL communicator (collective: every rank calls it)."""
+        self.lib.check(self.lib.vnb_comm_sync_bn(self._h, 1 if on else 0))
+
+    def set_stats_allreduce(self, fn, world: int):
+        """Synchronised batch norm with the exchange done by the caller: `fn(values)` sums a float64 NumPy row in
+        place over `world` ranks (None switches back to local statistics)."""
+        if fn is None:
+            self._stats_cb = None
+            self.lib.check(self.lib.vnb_set_stats_allreduce(self._h, None, None, 1))
+            return
+
+        def trampoline(ptr, n, _user):
+            try:
+                fn(np.ctypeslib.as_array(ptr, shape=(n,)))
+                return 0
+            except Exception:  # never unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._stats_cb = _ffi.ALLREDUCE_FN(trampoline)  # keep the thunk alive as long as the engine uses it
+        self.lib.check(self.lib.vnb_set_stats_allreduce(self._h, C.cast(self._stats_cb, C.c_void_p), None, int(world)))
