@@ -98,6 +98,8 @@ class Comm {
     for (const auto& b : buckets) max_chunk = std::max(max_chunk, chunk_elems(b.hi - b.lo));
     events_.resize(buckets.size());
     for (auto& ev : events_) VNB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    wg_events_.resize(buckets.size());
+    for (auto& ev : wg_events_) VNB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     VNB_CUDA_OK(cudaEventCreateWithFlags(&done_, cudaEventDisableTiming));
     if (world_ > 1) VNB_CUDA_OK(cudaMalloc(&scratch_, std::max<size_t>(max_chunk, 4) * sizeof(float)));
     e.set_grad_hook([this, &e](int bucket) { this->on_bucket_ready(e, bucket); });
@@ -106,6 +108,7 @@ class Comm {
     if (stats_comm_) NcclApi::get().CommDestroy(stats_comm_);
     if (scratch_) cudaFree(scratch_);
     for (auto ev : events_) cudaEventDestroy(ev);
+    for (auto ev : wg_events_) cudaEventDestroy(ev);
     cudaEventDestroy(done_);
     cudaStreamDestroy(stream_);
     if (comm_) NcclApi::get().CommDestroy(comm_);
@@ -143,6 +146,10 @@ class Comm {
     const Engine::Bucket& b = e.buckets()[bi];
     VNB_CUDA_OK(cudaEventRecord(events_[bi], e.stream()));
     VNB_CUDA_OK(cudaStreamWaitEvent(stream_, events_[bi], 0));
+    if (cudaStream_t ws = e.pending_wgrad_stream()) {  // dual-wait mode: filter gradients of this bucket still in flight
+      VNB_CUDA_OK(cudaEventRecord(wg_events_[bi], ws));
+      VNB_CUDA_OK(cudaStreamWaitEvent(stream_, wg_events_[bi], 0));
+    }
     float* g = e.grad_buffer() + b.lo;
     const size_t n = b.hi - b.lo;
     if (use_ring_)
@@ -202,6 +209,7 @@ class Comm {
   bool use_ring_ = true;
   float* scratch_ = nullptr;
   std::vector<cudaEvent_t> events_;
+  std::vector<cudaEvent_t> wg_events_;
   cudaEvent_t done_ = nullptr;
   int pending_ = 0;
 };

@@ -126,6 +126,10 @@ class Engine {
       VNB_CUDA_OK(cudaEventCreateWithFlags(&wg_ready_ev_, cudaEventDisableTiming));
       VNB_CUDA_OK(cudaEventCreateWithFlags(&wg_done_ev_, cudaEventDisableTiming));
     }
+    // VNB_COMM_DUAL_WAIT=1 (experimental, not yet measured): a gradient bucket's all-reduce waits on the main and on
+    // the filter-gradient stream itself instead of the main stream joining the latter at every bucket boundary.
+    const char* dw = getenv("VNB_COMM_DUAL_WAIT");
+    comm_waits_wgrad_ = dw && dw[0] == '1';
 #endif
     build_graph();
     allocate();
@@ -149,6 +153,8 @@ class Engine {
   };
   const std::vector<Bucket>& buckets() const { return buckets_; }
   void set_grad_hook(std::function<void(int)> hook) { grad_hook_ = std::move(hook); }
+  // the filter-gradient stream while it holds work the main stream has not joined yet (communicator, dual-wait mode)
+  cudaStream_t pending_wgrad_stream() const { return (comm_waits_wgrad_ && wg_stream_ && wg_pending_) ? wg_stream_ : 0; }
   // Synchronised batch norm: `hook(dev, n)` sums n doubles in place over `world` ranks, ordered after everything
   // enqueued on stream() and before anything enqueued later; an empty hook restores local statistics.
   void set_stats_hook(std::function<void(double*, int)> hook, int world) {
@@ -1236,7 +1242,7 @@ class Engine {
     if (!grad_hook_) return;
     bool any = false;
     for (size_t b = 0; b < buckets_.size(); ++b) any = any || buckets_[b].unit_lo == ui;
-    if (any) join_wgrad_stream();   // the all-reduce of a bucket waits on the main stream only
+    if (any && !comm_waits_wgrad_) join_wgrad_stream();   // the all-reduce of a bucket waits on the main stream only
     for (size_t b = 0; b < buckets_.size(); ++b)
       if (buckets_[b].unit_lo == ui) grad_hook_(static_cast<int>(b));
   }
@@ -1517,6 +1523,7 @@ class Engine {
   cudaEvent_t wg_ready_ev_ = nullptr, wg_done_ev_ = nullptr;
 #endif
   bool wg_pending_ = false;
+  bool comm_waits_wgrad_ = false;
   std::vector<ParamEntry> entries_;
   std::map<std::string, size_t> index_;
   std::vector<Act> acts_;
