@@ -387,7 +387,7 @@ def test_sliding_window_evaluation_matches_the_reference_loop(gpu_lib, precision
 def test_every_unit_against_the_oracle_taps(gpu_lib):
     """vnb_read_tensor around vnb_forward_backward on the exact-fp32 path: every unit's batch-norm input, output
     activation and dL/d(BN input) against the oracle's taps (the per-op view of the fused BN / PReLU / loss passes)."""
-    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=4, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=2)
+    spec = R.VNetSpec(**CASES["tiny_m1_k2"][0])   # 16 channels, two levels: the shapes of the golden-fixture case
     P, N = 16, 2
     params = perturbed_params(spec, 3)
     img, lab = synth_batch(1, N, P, 1, 2)
