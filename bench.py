@@ -201,38 +201,54 @@ def cpu_reference_step_seconds(sample_patch: int, repeats: int, warmup: int):
     return times, cores
 
 
+CPU_SAMPLE_MAX_PATCH = 128   # one 128^3 patch: ~5-15 s per optimiser step and ~7.5 GB of host memory on 8-16 cores
+
+
+def _cpu_sample(patch: int):
+    """The bounded CPU sample is the workload's own patch size (one patch instead of the batch); only patches
+    above 128^3 (configs[4]) are sampled at 128^3 and scaled by the voxel ratio."""
+    sample = min(patch, CPU_SAMPLE_MAX_PATCH)
+    return sample, (sample / patch) ** 3
+
+
+def _sample_text(steps: int, sample: int, patch: int, cores: int, seconds: float) -> str:
+    txt = ("%d optimiser step%s on one %d^3 patch each (fwd+Dice+bwd+Adam, TF1-semantics CPU restatement on "
+           "PyTorch/oneDNN, %d threads), %.2f s per step" % (steps, "" if steps == 1 else "s", sample, cores, seconds))
+    if sample != patch:
+        txt += ", scaled by (%d/%d)^3 voxels to %d^3" % (sample, patch, patch)
+    return txt
+
+
 def cpu_baseline(patch: int):
-    """Bounded sample: one 64^3 (or 32^3) training step of the same network on all host cores, scaled
-    to `patch`^3 units by the voxel ratio (the conv stack's work is linear in voxels)."""
-    sample = 64 if patch >= 64 else patch
-    times, cores = cpu_reference_step_seconds(sample, 1, 1)
-    t = float(np.median(times))
-    scale = (sample / patch) ** 3
+    """Bounded sample of the same workload: two optimiser steps of the same network on one `patch`^3 patch each
+    (not the whole batch), all host cores, after a 32^3 warm-up step; 10-30 s of CPU work at 128^3."""
+    sample, scale = _cpu_sample(patch)
+    times, cores = cpu_reference_step_seconds(sample, 2, 1)
+    t = float(np.mean(times))
     return {"value": scale / t, "unit": "patches/sec", "cores": cores, "kind": "port",
-            "sample": "1 optimiser step on one %d^3 patch (fwd+Dice+bwd+Adam, torch-CPU oracle, %d threads), %.2f s, "
-                      "scaled by (%d/%d)^3 voxels" % (sample, cores, t, sample, patch)}
+            "sample": _sample_text(len(times), sample, patch, cores, t)}
 
 
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    sample = 64 if args.patch >= 64 else args.patch
-    steps = max(1, min(args.steps, 3))        # bounded: one CPU training step on a 64^3 patch takes ~30 s
+    sample, scale = _cpu_sample(args.patch)
+    steps = max(1, min(args.steps, 3))        # bounded: one CPU optimiser step on a 128^3 patch takes 5-15 s
     warm = 1
     times, cores = cpu_reference_step_seconds(sample, steps, warm)
     t = float(np.mean(times))
-    scale = (sample / args.patch) ** 3
     value = scale / t
     line = {
         "impl": "reference", "metric": "patches/sec (128^3, 1ch->2cls) training step", "value": value,
         "unit": "patches/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t / scale, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * args.batch * t / scale, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "V-Net 3D train step, %d^3 patch, 1 modality, 2 classes, weighted_sorensen, Adam" % args.patch,
+        "config": {"workload": "V-Net 3D train step (fwd + weighted Dice + bwd + Adam), %d^3 patch, 1 modality, 2 classes, "
+                               "batch %d (%s); each timed step is one patch of that batch on the host cores"
+                               % (args.patch, args.batch, args.preset["name"]),
                    "patch": args.patch, "batch_per_gpu": args.batch, "timed_steps": steps, "timed_warmup": warm},
         "cpu_baseline": {"value": value, "unit": "patches/sec", "cores": cores, "kind": "port",
-                         "sample": "%d timed optimiser steps on one %d^3 patch each (TF1-semantics CPU restatement on "
-                                   "PyTorch/oneDNN, %d threads), scaled by voxel count to %d^3" % (steps, sample, cores, args.patch)},
+                         "sample": _sample_text(steps, sample, args.patch, cores, t)},
         "e2e": {"value": value, "unit": "patches/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
