@@ -144,3 +144,23 @@ def test_oracle_reproduces_golden(name):
     for k, g in grads.items():
         gn = float(np.sqrt((g.numpy().astype(np.float64) ** 2).sum()))
         assert abs(gn - float(gold["gnorm/" + k])) <= 2e-3 * max(gn, 1e-6) + 1e-7, k
+
+
+def test_golden_manifest_matches_the_committed_fixtures():
+    """tests/golden/MANIFEST.json: every .npz is listed with its SHA-256 and generator script, and
+    nothing listed is missing - a fixture regenerated without updating the manifest (or the reverse) fails here."""
+    import hashlib
+    import json
+    import os
+
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    with open(os.path.join(gold, "MANIFEST.json")) as f:
+        manifest = json.load(f)
+    on_disk = sorted(f for f in os.listdir(gold) if f.endswith(".npz"))
+    assert on_disk == sorted(manifest)
+    for name, entry in manifest.items():
+        with open(os.path.join(gold, name), "rb") as f:
+            blob = f.read()
+        assert hashlib.sha256(blob).hexdigest() == entry["sha256"], name
+        assert len(blob) == entry["bytes"]
+        assert os.path.exists(os.path.join(gold, entry["generator"]))
