@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=None, help="patches per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("VNB_BENCH_PRECISION"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-layer", default=None, metavar="FILE",
+                    help="also write the per-layer roofline table (every 5^3 / 3^3 convolution launch of one profiled step: "
+                         "layer, pass, ms, algorithmic TFLOP/s, fraction of the measured peak) as JSON to FILE")
     ap.add_argument("--sync-bn", action="store_true", help="N>1: batch-norm statistics of the global batch (off: local statistics)")
     args = ap.parse_args()
     pre = PRESETS[args.config]
@@ -109,6 +112,26 @@ def roofline_block(precision, peaks, fd_ms, fd_n, fd_fl, wg_ms, wg_n, wg_fl, pro
                   "timed region (filter gradients serialised on the main stream while profiling, so every launch is "
                   "timed alone; in the timed steps they overlap the following units on a side stream)" % prof_steps,
     }
+
+
+def write_per_layer_table(path, launches, prof_steps, peaks, precision):
+    """SURVEY H1's per-layer roofline table: the profiled launches of each (layer, pass) averaged over the profiled
+    steps, with the algorithmic rate (one MMA pass counted, whatever the precision mode issues) over the measured peak."""
+    rows = {}
+    for label, cls, ms, flops in launches:
+        r = rows.setdefault(label, {"layer": label, "class": "wgrad" if cls == 1 else "fprop/dgrad", "ms": 0.0, "gflop": 0.0, "n": 0})
+        r["ms"] += ms
+        r["gflop"] += flops / 1e9
+        r["n"] += 1
+    table = []
+    for r in rows.values():
+        tflops = r["gflop"] / r["ms"] if r["ms"] > 0 else 0.0     # GFLOP / ms = TFLOP/s
+        table.append({"layer": r["layer"], "class": r["class"], "launches_per_step": r["n"] / max(prof_steps, 1),
+                      "ms_per_launch": r["ms"] / r["n"], "gflop_per_launch": r["gflop"] / r["n"],
+                      "tflops": tflops, "frac_of_peak": tflops / peaks["tflops"]})
+    with open(path, "w") as f:
+        json.dump({"precision": precision, "peak_tflops": peaks["tflops"], "peak_source": peaks["source"],
+                   "profiled_steps": prof_steps, "rows": table}, f, indent=1)
 
 
 class ClockSampler(threading.Thread):
@@ -341,6 +364,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         eng.train_step_resident(B, dropout, seed=300 + i)
     conv_ms, conv_n, conv_fl = eng.profile_read(0)
     wg_ms, wg_n, wg_fl = eng.profile_read(1)
+    if args.per_layer and rank == 0:
+        write_per_layer_table(args.per_layer, eng.profile_launches(), prof_steps, measured_peaks(), args.precision)
     eng.profile_enable(False)
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")

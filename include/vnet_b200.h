@@ -151,6 +151,12 @@ int vnb_event_elapsed_ms(vnb_handle* h, float* ms);
  * enable, run steps, then read (sum of device ms, launches, algorithmic FLOPs) for class 0 fprop+dgrad, 1 wgrad */
 int vnb_profile_enable(vnb_handle* h, int on);
 int vnb_profile_read(vnb_handle* h, int kernel_class, double* ms, int64_t* launches, double* flops);
+/* the same records one by one (per-layer roofline table): number of profiled launches since vnb_profile_enable, and
+ * launch `index` = its class, device ms, algorithmic FLOPs and a label "scope pass Cin->Cout @DxHxW" (NUL-terminated,
+ * truncated to label_bytes); VNB_ERR_INVALID_ARG past the last record */
+int vnb_profile_count(vnb_handle* h, int64_t* launches);
+int vnb_profile_launch(vnb_handle* h, int64_t index, int* kernel_class, double* ms, double* flops, char* label,
+                       size_t label_bytes);
 
 /* attention path (vnb_config.attention = 1): the distance map fed as distmap_placeholder (train.py:176-179,
  * 536) for the next loss / training calls, [n][X][Y][Z] floats in [0,1]; the three loss scalars of the last

@@ -319,3 +319,36 @@ def test_every_unit_against_the_oracle_taps(emul_lib, spec, N):
     n_units = sum(1 for k in eng.variables() if k.endswith("/weights"))
     assert seen["bn_in"] >= n_units - 2 * spec.num_levels and seen["act"] >= n_units  # up-convolutions tap outputs only
     eng.close()
+
+
+def test_profile_records_name_every_convolution_launch(emul_lib):
+    """vnb_profile_count / vnb_profile_launch (the per-layer roofline table of bench.py --per-layer): one
+    forward + backward pass yields one labelled record per 5^3 convolution and pass, whose algorithmic FLOPs are
+    2 * 125 * Cin * Cout * voxels, and the per-class totals agree with vnb_profile_read."""
+    spec, P, N = SPEC_A, 8, 2
+    eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 1.0), emul_lib)
+    eng.set_params(perturbed_params(spec))
+    img, lab = synth_batch(0, N, P, spec.in_channels, spec.num_classes)
+    assert eng.profile_launches() == []
+    eng.profile_enable(True)
+    eng.forward_backward(img, lab)
+    recs = eng.profile_launches()
+    conv5 = [n[:-len("/weights")] for n, s, k in R.param_specs(spec) if k == "weights" and tuple(s[:3]) == (5, 5, 5)]
+    by_pass = {p: [r for r in recs if r[0].split(" ")[1] == p] for p in ("fprop", "dgrad", "wgrad")}
+    assert sorted(r[0].split(" ")[0] for r in by_pass["fprop"]) == sorted(conv5)
+    assert sorted(r[0].split(" ")[0] for r in by_pass["wgrad"]) == sorted(conv5)
+    assert len(by_pass["dgrad"]) == len(conv5)       # M = 1: the input convolution feeds a batch norm, so it has a dgrad
+    shapes = {n[:-len("/weights")]: s for n, s, k in R.param_specs(spec) if k == "weights"}
+    for label, cls, ms, flops in recs:
+        scope, pas, chans, at = label.split(" ")
+        cin, cout = (int(v) for v in chans.split("->"))
+        d, h, w = (int(v) for v in at[1:].split("x"))
+        assert (cin, cout) == tuple(shapes[scope][3:5])
+        assert flops == 2.0 * 125 * cin * cout * N * d * h * w
+        assert cls == (1 if pas == "wgrad" else 0) and ms == 0.0      # no device clock in the emulation build
+    for cls in (0, 1):
+        _, n, fl = eng.profile_read(cls)
+        assert n == sum(r[1] == cls for r in recs) and fl == sum(r[3] for r in recs if r[1] == cls)
+    eng.profile_enable(False)
+    assert eng.profile_launches() == []
+    eng.close()

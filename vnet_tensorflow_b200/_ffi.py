@@ -77,6 +77,9 @@ _PROTOTYPES = {
     "vnb_event_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "vnb_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "vnb_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "vnb_profile_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "vnb_profile_launch": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.c_char_p, C.c_size_t]),
     "vnb_set_distmap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "vnb_read_losses": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "vnb_read_softmax_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),

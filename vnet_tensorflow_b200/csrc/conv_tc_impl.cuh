@@ -128,7 +128,7 @@ inline void Engine::tc_run_fprop(Unit& u, int N) {
   a.out1 = u.z;
   a.out2 = nullptr;
   a.acc1 = a.acc2 = 0;
-  ProfScope ps(*this, 0, conv5_flops(u, N));
+  ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "fprop");
   tc_launch(pl, a, cfg_.precision == PREC_BF16X3, sm_count_, stream_);
   ++launches_;
 }
@@ -145,14 +145,14 @@ inline void Engine::tc_run_dgrad(Unit& u, int N) {
   a.acc1 = u.in1_accumulate ? 1 : 0;
   a.out2 = u.in2 >= 0 ? acts_[u.in2].d : nullptr;
   a.acc2 = u.in2_accumulate ? 1 : 0;
-  ProfScope ps(*this, 0, conv5_flops(u, N));
+  ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "dgrad");
   tc_launch(pl, a, cfg_.precision == PREC_BF16X3, sm_count_, stream_);
   ++launches_;
 }
 
 inline void Engine::tc_run_wgrad(Unit& u, int N) {
   cudaStream_t st = wgrad_stream_begin();
-  ProfScope ps(*this, 1, conv5_flops(u, N), st);
+  ProfScope ps(*this, 1, conv5_flops(u, N), st, &u, "wgrad");
   wg_launch(u.tc.wgrad, N, cfg_.precision == PREC_BF16X3, wg_partial_, grads_ + u.w_off, st, u.Cin1 + u.Cin2);
   launches_ += 2;
 }

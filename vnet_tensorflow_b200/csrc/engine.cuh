@@ -424,39 +424,65 @@ class Engine {
     long long n = 0;
 #ifndef VNB_EMULATE
     VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+#endif
     for (size_t i = 0; i < prof_used_; ++i) {
       if (prof_[i].cls != cls) continue;
       float e = 0.f;
+#ifndef VNB_EMULATE
       VNB_CUDA_OK(cudaEventElapsedTime(&e, prof_[i].a, prof_[i].b));
+#endif
       t += e;
       f += prof_[i].flops;
       ++n;
     }
-#endif
     *ms = t;
     *launches = n;
     *flops = f;
+  }
+  // one profiled launch: class, time, algorithmic FLOPs and "scope pass Cin->Cout @DxHxW"; false past the last record
+  size_t profile_count() const { return prof_used_; }
+  bool profile_launch(size_t i, int* cls, double* ms, double* flops, std::string* label) {
+    if (i >= prof_used_) return false;
+    float e = 0.f;
+#ifndef VNB_EMULATE
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+    if (wg_stream_) VNB_CUDA_OK(cudaStreamSynchronize(wg_stream_));
+    VNB_CUDA_OK(cudaEventElapsedTime(&e, prof_[i].a, prof_[i].b));
+#endif
+    *cls = prof_[i].cls;
+    *ms = e;
+    *flops = prof_[i].flops;
+    label->clear();
+    if (const Unit* u = prof_[i].unit) {
+      const Dims& d = acts_[u->out].dims;
+      *label = u->scope + " " + prof_[i].pass + " " + std::to_string(u->Cin1 + u->Cin2) + "->" + std::to_string(u->Cout) +
+               " @" + std::to_string(d.D) + "x" + std::to_string(d.H) + "x" + std::to_string(d.W);
+    }
+    return true;
   }
   struct ProfScope {  // brackets one kernel launch with events when profiling is on
     Engine& e;
     long long idx = -1;
     cudaStream_t st;
-    ProfScope(Engine& eng, int cls, double flops, cudaStream_t stream = 0) : e(eng), st(stream ? stream : eng.stream_) {
-#ifndef VNB_EMULATE
+    ProfScope(Engine& eng, int cls, double flops, cudaStream_t stream = 0, const Unit* unit = nullptr,
+              const char* pass = "")
+        : e(eng), st(stream ? stream : eng.stream_) {
       if (!e.profiling_) return;
       if (e.prof_used_ == e.prof_.size()) {
         ProfRec r;
+#ifndef VNB_EMULATE
         cudaEventCreate(&r.a);
         cudaEventCreate(&r.b);
+#endif
         e.prof_.push_back(r);
       }
       idx = static_cast<long long>(e.prof_used_++);
       e.prof_[idx].cls = cls;
       e.prof_[idx].flops = flops;
+      e.prof_[idx].unit = unit;
+      e.prof_[idx].pass = pass;
+#ifndef VNB_EMULATE
       cudaEventRecord(e.prof_[idx].a, st);
-#else
-      (void)cls;
-      (void)flops;
 #endif
     }
     ~ProfScope() {
@@ -906,7 +932,7 @@ class Engine {
       p.acc1 = p.acc2 = 0;
       p.dims = o.dims;
       p.N = N;
-      ProfScope ps(*this, 0, conv5_flops(u, N));
+      ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "fprop");
       launch_conv5(p);
     } else if (u.kind == U_CONV3) {
       if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid && !getenv("VNB_DEBUG_NO_TC_FPROP")) {
@@ -928,7 +954,7 @@ class Engine {
       p.acc1 = p.acc2 = 0;
       p.dims = o.dims;
       p.N = N;
-      ProfScope ps(*this, 0, conv5_flops(u, N));
+      ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "fprop");
       launch_conv3(p);
     } else if (u.kind == U_DOWN || u.kind == U_UP) {
       K2Args p{};
@@ -1277,7 +1303,7 @@ class Engine {
         p.acc2 = 0;
         p.dims = o.dims;
         p.N = N;
-        ProfScope ps(*this, 0, conv5_flops(u, N));
+        ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "dgrad");
         launch_conv3(p);
       }
       if (cfg_.precision != PREC_FP32 && u.tc.wgrad.valid && !getenv("VNB_DEBUG_NO_TC_WGRAD")) {
@@ -1304,7 +1330,7 @@ class Engine {
       dim3 grid(static_cast<unsigned>(splits), pairs);
       launch_conv5_attr_once();
       {
-        ProfScope ps(*this, 1, conv5_flops(u, N));
+        ProfScope ps(*this, 1, conv5_flops(u, N), 0, &u, "wgrad");
         VNB_LAUNCH(conv_wgrad_ref_kernel<3>, grid, 256, WgradRefGeom<3>::SMEM, stream_, w);
       }
       ++launches_;
@@ -1333,7 +1359,7 @@ class Engine {
         p.acc2 = u.in2_accumulate ? 1 : 0;
         p.dims = o.dims;
         p.N = N;
-        ProfScope ps(*this, 0, conv5_flops(u, N));
+        ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "dgrad");
         launch_conv5(p);
       }
       if (tc && u.tc.wgrad.valid && !getenv("VNB_DEBUG_NO_TC_WGRAD")) {
@@ -1360,7 +1386,7 @@ class Engine {
       dim3 grid(static_cast<unsigned>(splits), pairs);
       launch_conv5_attr_once();
       {
-        ProfScope ps(*this, 1, conv5_flops(u, N));
+        ProfScope ps(*this, 1, conv5_flops(u, N), 0, &u, "wgrad");
         VNB_LAUNCH(conv5_wgrad_ref_kernel, grid, 256, kW5_SMEM, stream_, w);
       }
       ++launches_;
@@ -1559,6 +1585,8 @@ class Engine {
     cudaEvent_t a{}, b{};
     int cls = 0;
     double flops = 0;
+    const Unit* unit = nullptr;   // the layer this launch belongs to (per-layer roofline table)
+    const char* pass = "";        // "fprop" | "dgrad" | "wgrad"
   };
   std::vector<ProfRec> prof_;
   size_t prof_used_ = 0;

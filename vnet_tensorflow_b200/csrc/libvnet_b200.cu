@@ -413,6 +413,30 @@ int vnb_profile_read(vnb_handle* h, int cls, double* ms, int64_t* launches, doub
     *launches = n;
   });
 }
+int vnb_profile_count(vnb_handle* h, int64_t* launches) {
+  return guarded([&] {
+    need(h, "handle");
+    need(launches, "launches");
+    *launches = static_cast<int64_t>(h->engine->profile_count());
+  });
+}
+int vnb_profile_launch(vnb_handle* h, int64_t index, int* cls, double* ms, double* flops, char* label, size_t label_bytes) {
+  return guarded([&] {
+    need(h, "handle");
+    need(cls, "kernel_class");
+    need(ms, "ms");
+    need(flops, "flops");
+    select_device(h);
+    std::string text;
+    if (index < 0 || !h->engine->profile_launch(static_cast<size_t>(index), cls, ms, flops, &text))
+      throw std::invalid_argument("profile record index out of range");
+    if (label && label_bytes) {
+      const size_t n = std::min(text.size(), label_bytes - 1);
+      memcpy(label, text.data(), n);
+      label[n] = 0;
+    }
+  });
+}
 
 int vnb_set_distmap(vnb_handle* h, const float* distmap, int n) {
   return guarded([&] {

@@ -256,6 +256,18 @@ class VNetEngine:
         self.lib.check(self.lib.vnb_profile_read(self._h, kernel_class, C.byref(ms), C.byref(n), C.byref(fl)))
         return ms.value, n.value, fl.value
 
+    def profile_launches(self):
+        """Every profiled launch since profile_enable(True): (label "scope pass Cin->Cout @DxHxW", class, ms, FLOPs)."""
+        n = C.c_int64()
+        self.lib.check(self.lib.vnb_profile_count(self._h, C.byref(n)))
+        out = []
+        buf = C.create_string_buffer(256)
+        for i in range(n.value):
+            cls, ms, fl = C.c_int(), C.c_double(), C.c_double()
+            self.lib.check(self.lib.vnb_profile_launch(self._h, i, C.byref(cls), C.byref(ms), C.byref(fl), buf, len(buf)))
+            out.append((buf.value.decode(), cls.value, ms.value, fl.value))
+        return out
+
     def sync(self):
         self.lib.check(self.lib.vnb_sync(self._h))
 
