@@ -352,3 +352,27 @@ def test_profile_records_name_every_convolution_launch(emul_lib):
     eng.profile_enable(False)
     assert eng.profile_launches() == []
     eng.close()
+
+
+def test_ragged_batches_below_max_batch(emul_lib):
+    """A handle created for max_batch = 3 serves batches of 3, 1 and 2 in turn (the last batch of an epoch is short,
+    model.py:716-748 feeds whatever the dataset yields): batch statistics, loss mean over n and gradients belong to
+    the n patches of the call, nothing of an earlier, larger batch leaks in; n = 0 and n > max_batch are errors."""
+    spec, P = SPEC_A, 8
+    params = perturbed_params(spec)
+    eng = engine_for(spec, P, 3, "weighted_sorensen", (0.1, 1.0), emul_lib)
+    eng.set_params(params)
+    for seed, n in ((0, 3), (1, 1), (2, 2)):
+        img, lab = synth_batch(seed, n, P, spec.in_channels, spec.num_classes)
+        loss_o, logits_o, grads_o, _ = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
+        loss = eng.forward_backward(img, lab)
+        assert abs(loss - float(loss_o)) < 2e-6, n
+        _grad_check(eng, grads_o, spec, 2e-4)
+        logits, _, argmax = eng.forward(img)
+        assert logits.shape[0] == n and rel_err(logits, logits_o.numpy()) < 2e-5
+        assert int((argmax != R.predict(logits_o).numpy()).sum()) == 0
+    with pytest.raises(ValueError):
+        eng.forward(np.zeros((4, P, P, P, 1), np.float32))
+    with pytest.raises((ValueError, _ffi.VnbError)):
+        eng.forward(np.zeros((0, P, P, P, 1), np.float32))
+    eng.close()

@@ -419,3 +419,29 @@ def test_every_unit_against_the_oracle_taps(gpu_lib):
     print("per-unit worst relative errors:", worst)
     assert worst["z"] < LOGIT_TOL["fp32"] and worst["a"] < LOGIT_TOL["fp32"] and worst["dz"] < GRAD_TOL["fp32"]
     eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_short_batch_after_a_full_one(gpu_lib, precision):
+    """A handle created for max_batch = 2 serves a full batch and then one patch (the last batch of an epoch is short):
+    statistics, loss and gradients of the second call belong to its single patch.  CPU twin of the tensor-core form:
+    tests/test_tc_emul.py::test_engine_bf16x3_short_batch_after_a_full_one.  (Added after the round-1 GPU budget was
+    spent: first run on hardware is the round-end GPU suite.)"""
+    spec = R.VNetSpec(**CASES["tiny_m1_k2"][0])
+    P = 16
+    params = perturbed_params(spec)
+    eng = engine_for(spec, P, 2, "weighted_sorensen", (0.1, 1.0), gpu_lib, precision=precision)
+    eng.set_params(params)
+    img2, lab2 = synth_batch(0, 2, P, 1, 2)
+    l2 = eng.forward_backward(img2, lab2)
+    lo2 = R.loss_and_grads(params, img2, lab2, spec, "weighted_sorensen", (0.1, 1.0))[0]
+    assert abs(l2 - float(lo2)) < 5e-5
+    img, lab = synth_batch(5, 1, P, 1, 2)
+    l = eng.forward_backward(img, lab)
+    lo, lg, go, _ = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
+    assert abs(l - float(lo)) < 5e-5
+    _check_grads(eng, {k: v.numpy() for k, v in go.items()}, spec, GRAD_TOL[precision], l2=True)
+    logits, _, argmax = eng.forward(img)
+    assert logits.shape[0] == 1 and rel_err(logits, lg.numpy()) < LOGIT_TOL[precision]
+    assert int((argmax != R.predict(lg).numpy()).sum()) <= 2
+    eng.close()

@@ -83,6 +83,34 @@ def test_engine_bf16x3_matches_oracle(emul_lib):
     eng.close()
 
 
+def test_engine_bf16x3_short_batch_after_a_full_one(emul_lib):
+    """Tensor-core plans are built for max_batch; a shorter batch (last batch of an epoch) only shrinks the item count
+    and the statistics count - nothing of the earlier full batch may leak into it (TMA boxes, split-K partials,
+    bf16 copies of patch 1 are still in memory)."""
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=16, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=2)
+    P = 16
+    params = perturbed_params(spec)
+    eng = engine_for(spec, P, 2, "weighted_sorensen", (0.1, 1.0), emul_lib, precision="bf16x3")
+    eng.set_params(params)
+    img2, lab2 = synth_batch(0, 2, P, 1, 2)
+    l2 = eng.forward_backward(img2, lab2)
+    lo2 = R.loss_and_grads(params, img2, lab2, spec, "weighted_sorensen", (0.1, 1.0))[0]
+    assert abs(l2 - float(lo2)) < 2e-6
+    img, lab = synth_batch(5, 1, P, 1, 2)
+    l = eng.forward_backward(img, lab)
+    lo, lg, go, _ = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
+    assert abs(l - float(lo)) < 2e-6
+    g = eng.get_grads()
+    for k, v in g.items():
+        if analytically_zero(k, spec):
+            continue
+        ref = go[k].numpy().astype(np.float64)
+        assert np.sqrt(((v - ref) ** 2).sum()) <= 5e-2 * max(np.sqrt((ref ** 2).sum()), 1e-9), k
+    logits, _, am = eng.forward(img)
+    assert rel_err(logits, lg.numpy()) < 1e-4 and int((am != R.predict(lg).numpy()).sum()) == 0
+    eng.close()
+
+
 @pytest.mark.parametrize("cin,cout,dims,n,prec", [
     (16, 16, (3, 6, 16), 1, 2),     # one (ci,co) pair, split-K over slabs
     (16, 16, (2, 5, 32), 2, 1),     # odd H (partial last slab), bf16x3
