@@ -110,6 +110,12 @@ int vnb_get_slot(vnb_handle* h, const char* tf_name, int slot, void* host, size_
 int vnb_get_step(vnb_handle* h, int64_t* global_step);
 int vnb_set_step(vnb_handle* h, int64_t global_step);
 
+/* Batch buffers - `images`, `labels` (and the distance map of vnb_set_distmap) going in, logits / softmax / argmax of
+ * vnb_forward coming out - are caller-owned and may live in HOST memory or in DEVICE memory of the handle's GPU (the
+ * SURVEY 8(b) "*_dev" variants: the direction is resolved through unified addressing, a batch produced on the GPU is
+ * copied device to device).  The copies run on the handle's own stream: a device buffer must be complete before the
+ * call (synchronise the stream that produced it), and device outputs are complete when vnb_forward returns.
+ * Scalars (loss_out, dice_terms) and parameter buffers are host memory. */
 /* inference: any of logits / softmax / argmax may be NULL */
 int vnb_forward(vnb_handle* h, const float* images, int n, float* logits, float* softmax, int64_t* argmax);
 /* sliding-window evaluation of one padded case (model.py:866-937): volume [X][Y][Z][M] float32 with every extent >=

@@ -445,3 +445,40 @@ def test_short_batch_after_a_full_one(gpu_lib, precision):
     assert logits.shape[0] == 1 and rel_err(logits, lg.numpy()) < LOGIT_TOL[precision]
     assert int((argmax != R.predict(lg).numpy()).sum()) <= 2
     eng.close()
+
+
+def test_device_resident_batches_give_identical_results(gpu_lib):
+    """SURVEY 8(b) '*_dev' variants: images / labels (and forward outputs) in caller-owned CUDA memory take the same
+    kernels as host buffers - logits, argmax, loss and the trained weights are bit-identical; wrong dtype / device is
+    refused before anything reaches the C ABI.  (Added after the round-1 GPU budget was spent: first run on hardware is
+    the round-end GPU suite.)"""
+    import ctypes as C
+    spec = R.VNetSpec(**CASES["tiny_m1_k2"][0])
+    P, N = 16, 2
+    img, lab = synth_batch(3, N, P, 1, 2)
+    img_d, lab_d = torch.from_numpy(img).cuda(), torch.from_numpy(lab).cuda()
+    results = []
+    for images, labels in ((img, lab), (img_d, lab_d)):
+        eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 1.0), gpu_lib, precision="bf16x3")
+        eng.set_params(perturbed_params(spec))
+        logits, _, argmax = eng.forward(images)
+        loss = eng.loss(images, labels)
+        step_loss = eng.train_step(images, labels, dropout_rate=0.0)
+        results.append((logits, argmax, loss, step_loss, eng.get_param("vnet/encoder/level_1/conv_1/weights")))
+        if images is img_d:   # outputs straight into CUDA memory through the C ABI (after the step: new weights)
+            ref_logits, _, ref_argmax = eng.forward(img)
+            out = torch.empty((N, P, P, P, 2), dtype=torch.float32, device="cuda")
+            am = torch.empty((N, P, P, P), dtype=torch.int64, device="cuda")
+            gpu_lib.check(gpu_lib.vnb_forward(eng._h, C.c_void_p(img_d.data_ptr()), N, C.c_void_p(out.data_ptr()), None,
+                                              C.c_void_p(am.data_ptr())))
+            assert np.array_equal(out.cpu().numpy(), ref_logits) and np.array_equal(am.cpu().numpy(), ref_argmax)
+            with pytest.raises(ValueError):
+                eng.forward(img_d.double())
+            with pytest.raises(ValueError):
+                eng.loss(img_d, lab_d.long())
+        eng.close()
+    host, dev = results
+    assert np.array_equal(host[0], dev[0]) and np.array_equal(host[1], dev[1])
+    assert host[2] == dev[2] and host[3] == dev[3]
+    # the 2x2x2 / 1x1x1 filter gradients combine their splits with fp32 atomics (DESIGN 4): last-bit freedom only
+    assert np.abs(host[4] - dev[4]).max() <= 1e-6 * np.abs(host[4]).max()

@@ -215,9 +215,9 @@ class Engine {
                  V / N, lc, softmax ? softmax_dev_ : (float*)nullptr, argmax ? argmax_dev_ : (long long*)nullptr,
                  (double*)nullptr);
     }
-    if (logits) VNB_CUDA_OK(cudaMemcpyAsync(logits, acts_[head_act_].a, V * K * sizeof(float), cudaMemcpyDeviceToHost, stream_));
-    if (softmax) VNB_CUDA_OK(cudaMemcpyAsync(softmax, softmax_dev_, V * K * sizeof(float), cudaMemcpyDeviceToHost, stream_));
-    if (argmax) VNB_CUDA_OK(cudaMemcpyAsync(argmax, argmax_dev_, V * sizeof(long long), cudaMemcpyDeviceToHost, stream_));
+    if (logits) VNB_CUDA_OK(cudaMemcpyAsync(logits, acts_[head_act_].a, V * K * sizeof(float), cudaMemcpyDefault, stream_));
+    if (softmax) VNB_CUDA_OK(cudaMemcpyAsync(softmax, softmax_dev_, V * K * sizeof(float), cudaMemcpyDefault, stream_));
+    if (argmax) VNB_CUDA_OK(cudaMemcpyAsync(argmax, argmax_dev_, V * sizeof(long long), cudaMemcpyDefault, stream_));
     VNB_CUDA_OK(cudaStreamSynchronize(stream_));
   }
 
@@ -365,7 +365,7 @@ class Engine {
   void set_distmap(const float* distmap, int N) {
     if (!cfg_.attention) throw std::invalid_argument("set_distmap: the attention path is not enabled");
     check_batch(N);
-    VNB_CUDA_OK(cudaMemcpyAsync(distmap_dev_, distmap, voxels(N) * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    VNB_CUDA_OK(cudaMemcpyAsync(distmap_dev_, distmap, voxels(N) * sizeof(float), cudaMemcpyDefault, stream_));
     distmap_valid_ = true;
   }
   void read_losses(float out[3]) {  // total, segmentation, attention (train.py:417)
@@ -850,12 +850,14 @@ class Engine {
   void check_batch(int N) const {
     if (N < 1 || N > cfg_.max_batch) throw std::invalid_argument("batch size outside [1, max_batch]");
   }
+  // images / labels / distance maps / forward outputs: caller-owned HOST or DEVICE memory (cudaMemcpyDefault resolves
+  // the direction through unified addressing), so a batch produced on the GPU never bounces through the host
   void upload_images(const float* images, int N) {
     const Act& a = acts_[image_act_];
-    VNB_CUDA_OK(cudaMemcpyAsync(a.a, images, voxels_of(a.dims, N) * a.C * sizeof(float), cudaMemcpyHostToDevice, stream_));
+    VNB_CUDA_OK(cudaMemcpyAsync(a.a, images, voxels_of(a.dims, N) * a.C * sizeof(float), cudaMemcpyDefault, stream_));
   }
   void upload_labels(const int32_t* labels, int N) {
-    VNB_CUDA_OK(cudaMemcpyAsync(labels_dev_, labels, voxels(N) * sizeof(int32_t), cudaMemcpyHostToDevice, stream_));
+    VNB_CUDA_OK(cudaMemcpyAsync(labels_dev_, labels, voxels(N) * sizeof(int32_t), cudaMemcpyDefault, stream_));
   }
   BnParams bn_params(const Unit& u) {
     BnParams bp;

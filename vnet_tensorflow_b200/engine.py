@@ -16,8 +16,20 @@ import numpy as np
 from . import _ffi
 
 
-def _ptr(a: Optional[np.ndarray]):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+class _DevBuf:
+    """A torch CUDA tensor seen as a raw device pointer (keeps the tensor alive for the duration of the call)."""
+
+    def __init__(self, t):
+        self.t = t
+        self.shape = tuple(t.shape)
+        self.ndim = t.ndim
+        self.ptr = C.c_void_p(t.data_ptr())
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return a.ptr if isinstance(a, _DevBuf) else a.ctypes.data_as(C.c_void_p)
 
 
 class VNetEngine:
@@ -74,6 +86,7 @@ class VNetEngine:
         self.patch_shape = tuple(int(p) for p in patch_shape)
         self.max_batch = max_batch
         self.precision = precision
+        self.device = int(device)
         self._h = C.c_void_p()
         self.lib.check(self.lib.vnb_create(C.byref(cfg), device, C.byref(self._h)))
         self._specs = self._read_specs()
@@ -142,11 +155,15 @@ class VNetEngine:
     # ---- attention path (train.py:281-312,383-418) ---------------------------------------------
     def set_distmap(self, distmap: np.ndarray):
         """Distance map in [0,1] fed to the attention loss, [N,X,Y,Z] (or [N,X,Y,Z,1]) float32."""
-        a = np.ascontiguousarray(distmap, dtype=np.float32)
-        if a.ndim == 5 and a.shape[-1] == 1:
-            a = np.ascontiguousarray(a[..., 0])
+        if self._is_device_tensor(distmap):
+            a = self._device_tensor(distmap[..., 0] if distmap.ndim == 5 and distmap.shape[-1] == 1 else distmap,
+                                    "float32", "distmap")
+        else:
+            a = np.ascontiguousarray(distmap, dtype=np.float32)
+            if a.ndim == 5 and a.shape[-1] == 1:
+                a = np.ascontiguousarray(a[..., 0])
         if a.ndim != 4 or tuple(a.shape[1:]) != self.patch_shape:
-            raise ValueError("distmap must be [N,%d,%d,%d] float32, got %s" % (self.patch_shape + (a.shape,)))
+            raise ValueError("distmap must be [N,%d,%d,%d] float32, got %s" % (self.patch_shape + (tuple(a.shape),)))
         self.lib.check(self.lib.vnb_set_distmap(self._h, _ptr(a), a.shape[0]))
 
     def losses(self) -> Tuple[float, float, float]:
@@ -161,21 +178,42 @@ class VNetEngine:
         return a
 
     # ---- steps --------------------------------------------------------------------------------
-    def _check_images(self, images: np.ndarray) -> np.ndarray:
-        a = np.ascontiguousarray(images, dtype=np.float32)
+    @staticmethod
+    def _is_device_tensor(x) -> bool:
+        return type(x).__module__.split(".")[0] == "torch" and bool(getattr(x, "is_cuda", False))
+
+    def _device_tensor(self, t, dtype_name: str, what: str):
+        """A torch CUDA tensor handed straight to the C ABI (no host bounce): right dtype, contiguous, on the handle's
+        GPU; the producing stream is synchronised here because the engine copies on its own stream."""
+        import torch
+        if t.dtype != getattr(torch, dtype_name) or not t.is_contiguous():
+            raise ValueError("%s on the device must be a contiguous %s tensor" % (what, dtype_name))
+        if t.device.index != self.device:
+            raise ValueError("%s lives on cuda:%s, the engine on cuda:%d" % (what, t.device.index, self.device))
+        torch.cuda.current_stream(t.device).synchronize()
+        return _DevBuf(t)
+
+    def _check_images(self, images):
+        dev = self._is_device_tensor(images)
+        a = self._device_tensor(images, "float32", "images") if dev else np.ascontiguousarray(images, dtype=np.float32)
         want = self.patch_shape + (self.in_channels,)
         if a.ndim != 5 or tuple(a.shape[1:]) != want:
-            raise ValueError("images must be [N,%d,%d,%d,%d] float32, got %s" % (want + (a.shape,)))
+            raise ValueError("images must be [N,%d,%d,%d,%d] float32, got %s" % (want + (tuple(a.shape),)))
         if not 1 <= a.shape[0] <= self.max_batch:
             raise ValueError("batch %d outside [1, %d]" % (a.shape[0], self.max_batch))
         return a
 
-    def _check_labels(self, labels: np.ndarray, n: int) -> np.ndarray:
-        l = np.ascontiguousarray(labels, dtype=np.int32)
-        if l.ndim == 5 and l.shape[-1] == 1:  # model.py:741 feeds [...,np.newaxis]
-            l = np.ascontiguousarray(l[..., 0])
+    def _check_labels(self, labels, n: int):
+        if self._is_device_tensor(labels):
+            if labels.ndim == 5 and labels.shape[-1] == 1:
+                labels = labels[..., 0]      # a view: still contiguous
+            l = self._device_tensor(labels, "int32", "labels")
+        else:
+            l = np.ascontiguousarray(labels, dtype=np.int32)
+            if l.ndim == 5 and l.shape[-1] == 1:  # model.py:741 feeds [...,np.newaxis]
+                l = np.ascontiguousarray(l[..., 0])
         if tuple(l.shape) != (n,) + self.patch_shape:
-            raise ValueError("labels must be [N,X,Y,Z] int32 class indices, got %s" % (l.shape,))
+            raise ValueError("labels must be [N,X,Y,Z] int32 class indices, got %s" % (tuple(l.shape),))
         return l
 
     def forward(self, images, want_logits=True, want_softmax=True, want_argmax=True):
