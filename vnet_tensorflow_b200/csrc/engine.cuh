@@ -131,6 +131,10 @@ class Engine {
     const char* dw = getenv("VNB_COMM_DUAL_WAIT");
     comm_waits_wgrad_ = dw && dw[0] == '1';
 #endif
+    // debugging switches (route one pass of the tensor-core modes through the exact-fp32 kernels), read once
+    dbg_no_tc_fprop_ = getenv("VNB_DEBUG_NO_TC_FPROP") != nullptr;
+    dbg_no_tc_dgrad_ = getenv("VNB_DEBUG_NO_TC_DGRAD") != nullptr;
+    dbg_no_tc_wgrad_ = getenv("VNB_DEBUG_NO_TC_WGRAD") != nullptr;
     build_graph();
     allocate();
     init_default_params();
@@ -915,7 +919,7 @@ class Engine {
     const Act& o = acts_[u.out];
     const float* bias = u.b_off >= 0 ? params_ + u.b_off : nullptr;
     if (u.kind == U_CONV5) {
-      if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid && !getenv("VNB_DEBUG_NO_TC_FPROP")) {
+      if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid && !dbg_no_tc_fprop_) {
         tc_run_fprop(u, N);
         return;
       }
@@ -937,7 +941,7 @@ class Engine {
       ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "fprop");
       launch_conv5(p);
     } else if (u.kind == U_CONV3) {
-      if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid && !getenv("VNB_DEBUG_NO_TC_FPROP")) {
+      if (cfg_.precision != PREC_FP32 && u.tc.fprop.valid && !dbg_no_tc_fprop_) {
         tc_run_fprop(u, N);
         return;
       }
@@ -1283,7 +1287,7 @@ class Engine {
     VNB_CUDA_OK(cudaMemsetAsync(dw, 0, u.w_count * sizeof(float), stream_));
     if (!u.bn_inference) VNB_CUDA_OK(cudaMemsetAsync(grads_ + u.b_off, 0, u.Cout * sizeof(float), stream_));
     if (u.kind == U_CONV3) {
-      if (cfg_.precision != PREC_FP32 && u.need_dgrad && u.tc.dgrad.valid && !getenv("VNB_DEBUG_NO_TC_DGRAD")) {
+      if (cfg_.precision != PREC_FP32 && u.need_dgrad && u.tc.dgrad.valid && !dbg_no_tc_dgrad_) {
         tc_run_dgrad(u, N);
       } else if (u.need_dgrad) {
         VNB_LAUNCH(flip_transpose_w_kernel, grid_for(static_cast<long long>(u.w_count), 256), 256, 0, stream_,
@@ -1308,7 +1312,7 @@ class Engine {
         ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "dgrad");
         launch_conv3(p);
       }
-      if (cfg_.precision != PREC_FP32 && u.tc.wgrad.valid && !getenv("VNB_DEBUG_NO_TC_WGRAD")) {
+      if (cfg_.precision != PREC_FP32 && u.tc.wgrad.valid && !dbg_no_tc_wgrad_) {
         tc_run_wgrad(u, N);
         return;
       }
@@ -1339,7 +1343,7 @@ class Engine {
     } else if (u.kind == U_CONV5) {
       const int Cin = u.Cin1 + u.Cin2;
       const bool tc = cfg_.precision != PREC_FP32;
-      if (tc && u.need_dgrad && u.tc.dgrad.valid && !getenv("VNB_DEBUG_NO_TC_DGRAD")) {
+      if (tc && u.need_dgrad && u.tc.dgrad.valid && !dbg_no_tc_dgrad_) {
         tc_run_dgrad(u, N);
       } else if (u.need_dgrad) {
         VNB_LAUNCH(flip_transpose_w_kernel, grid_for(static_cast<long long>(u.w_count), 256), 256, 0, stream_,
@@ -1364,7 +1368,7 @@ class Engine {
         ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "dgrad");
         launch_conv5(p);
       }
-      if (tc && u.tc.wgrad.valid && !getenv("VNB_DEBUG_NO_TC_WGRAD")) {
+      if (tc && u.tc.wgrad.valid && !dbg_no_tc_wgrad_) {
         tc_run_wgrad(u, N);
         return;
       }
@@ -1552,6 +1556,7 @@ class Engine {
 #endif
   bool wg_pending_ = false;
   bool comm_waits_wgrad_ = false;
+  bool dbg_no_tc_fprop_ = false, dbg_no_tc_dgrad_ = false, dbg_no_tc_wgrad_ = false;
   std::vector<ParamEntry> entries_;
   std::map<std::string, size_t> index_;
   std::vector<Act> acts_;
