@@ -126,6 +126,16 @@ int vnb_evaluate_volume(vnb_handle* h, const float* volume, const int32_t dims[3
                         int64_t* label, float* softmax_sum, float* weight);
 /* loss without update; dice_terms (optional) receives [n][K][4] = (I, L, R, xent-sum) per sample/class */
 int vnb_loss(vnb_handle* h, const float* images, const int32_t* labels, int n, float* loss_out, double* dice_terms);
+/* step metrics, the tf.metrics block of summary_op (model.py:586-626) that the reference fetches with every training
+ * step (model.py:743-748), for the batch of the last vnb_loss / vnb_forward_backward / vnb_train_step[_resident] call
+ * (n = its batch size; the logits are those of that call's forward pass, i.e. before the weight update).  Integer counts:
+ *   confusion [(K+1)][K]   rows = label class (row K: labels outside [0,K), whose one-hot row is all zero), columns =
+ *                          argmax class; accuracy and the true/false positive/negative counts of every class follow
+ *   auc_hist  [K][2][201]  (optional, may be NULL) per class c >= 1 and truth value (label != c, label == c) the
+ *                          histogram of "number of tf.metrics.auc thresholds below softmax[c]" (200 thresholds)
+ * vnet_tensorflow_b200/metrics.py turns them into accuracy / sensitivity / specificity / dice / auc as TF computes them. */
+#define VNB_AUC_BINS 201
+int vnb_read_metrics(vnb_handle* h, int n, uint64_t* confusion, uint64_t* auc_hist);
 /* one optimiser step; loss_out may be NULL (then the call does not synchronise) */
 int vnb_train_step(vnb_handle* h, const float* images, const int32_t* labels, int n, float dropout_rate,
                    uint64_t seed, float* loss_out);

@@ -376,3 +376,50 @@ def test_ragged_batches_below_max_batch(emul_lib):
     with pytest.raises((ValueError, _ffi.VnbError)):
         eng.forward(np.zeros((0, P, P, P, 1), np.float32))
     eng.close()
+
+
+@pytest.mark.parametrize("spec,N", [(SPEC_A, 2), (SPEC_B, 1)])
+def test_step_metrics_match_the_reference_metric_block(emul_lib, spec, N):
+    """vnb_read_metrics (model.py:586-626, part of summary_op in the training sess.run): the confusion counts are
+    bit-exact against argmax / labels, the AUC histograms bit-exact against the engine's own softmax at the 200
+    tf.metrics.auc thresholds, and the derived scalars equal the literal restatement of the reference block -
+    including labels outside [0, K) (all-zero one-hot row) and a class that never occurs (0/0 = NaN like tf.divide)."""
+    from oracle import ref_metrics as RM
+    from vnet_tensorflow_b200 import metrics as M
+    P, K = 8, spec.num_classes
+    eng = engine_for(spec, P, N, "sorensen", (), emul_lib)
+    eng.set_params(perturbed_params(spec))
+    img, lab = synth_batch(2, N, P, spec.in_channels, K)
+    lab = lab.copy()
+    lab[0, 0, 0, :3] = (K, -1, K + 5)           # no class
+    if K == 3:
+        lab[lab == 2] = 0                       # class 2 never occurs as a label
+    with pytest.raises(_ffi.VnbError):
+        eng.metric_counts(N)                    # no call with labels yet
+    eng.forward_backward(img, lab)
+    cm, hist = eng.metric_counts(N)
+    logits, softmax, argmax = eng.forward(img)
+    with pytest.raises(_ffi.VnbError):
+        eng.metric_counts(N)                    # vnb_forward dropped the pairing of logits and labels
+    want_cm = np.zeros_like(cm)
+    for t, p in zip(lab.reshape(-1), argmax.reshape(-1)):
+        want_cm[t if 0 <= t < K else K, p] += 1
+    assert np.array_equal(cm, want_cm) and int(cm.sum()) == lab.size
+    thr = M.auc_thresholds()
+    want_hist = np.zeros_like(hist)
+    for c in range(1, K):
+        bins = (softmax[..., c].reshape(-1)[:, None] > thr[None, :]).sum(1)
+        np.add.at(want_hist[c], ((lab.reshape(-1) == c).astype(int), bins), 1)
+    assert np.array_equal(hist, want_hist)
+    got = M.step_metrics(cm, hist, list(range(K)))
+    ref = RM.step_metrics(logits, lab, softmax, list(range(K)))
+    assert list(got) == list(ref)
+    for k in got:
+        same = got[k] == ref[k] or (np.isnan(got[k]) and np.isnan(ref[k]))
+        assert same or (k.startswith("auc_") and abs(got[k] - ref[k]) < 1e-6), (k, got[k], ref[k])
+    if K == 3:
+        assert np.isnan(got["sensitivity_2"]) and got["true_positives_2"] == 0
+    eng.loss(img, lab)
+    cm2, hist2 = eng.metric_counts(N, want_auc=False)
+    assert hist2 is None and np.array_equal(cm2, cm)
+    eng.close()

@@ -482,3 +482,41 @@ def test_device_resident_batches_give_identical_results(gpu_lib):
     assert host[2] == dev[2] and host[3] == dev[3]
     # the 2x2x2 / 1x1x1 filter gradients combine their splits with fp32 atomics: last-bit freedom only
     assert np.abs(host[4] - dev[4]).max() <= 1e-6 * np.abs(host[4]).max()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_step_metrics_match_the_reference_metric_block(gpu_lib, precision):
+    """vnb_read_metrics on the device (model.py:586-626): confusion counts bit-exact against the engine's argmax, AUC
+    histograms bit-exact against the engine's softmax at the 200 tf.metrics.auc thresholds, derived scalars equal to the
+    literal restatement of the reference block.  CPU twin: tests/test_engine_emul.py.  (Added after the round-1 GPU
+    budget was spent: first run on hardware is the round-end GPU suite.)"""
+    from oracle import ref_metrics as RM
+    from vnet_tensorflow_b200 import metrics as M
+    spec = R.VNetSpec(num_classes=3, in_channels=2, num_channels=16, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=1)
+    P, N, K = 32, 2, 3
+    eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 0.5, 1.0), gpu_lib, precision=precision)
+    eng.set_params(perturbed_params(spec))
+    img, lab = synth_batch(2, N, P, 2, K)
+    lab = lab.copy()
+    lab[0, 0, 0, :3] = (K, -1, K + 5)           # labels outside [0, K): all-zero one-hot rows
+    eng.forward_backward(img, lab)
+    cm, hist = eng.metric_counts(N)
+    logits, softmax, argmax = eng.forward(img)
+    want_cm = np.zeros_like(cm)
+    np.add.at(want_cm, (np.where((lab >= 0) & (lab < K), lab, K).reshape(-1), argmax.reshape(-1)), 1)
+    assert np.array_equal(cm, want_cm) and int(cm.sum()) == lab.size
+    thr = M.auc_thresholds()
+    want_hist = np.zeros_like(hist)
+    for c in range(1, K):
+        bins = np.searchsorted(thr, softmax[..., c].reshape(-1), side="left")      # number of thresholds below p
+        np.add.at(want_hist[c], ((lab.reshape(-1) == c).astype(int), bins), 1)
+    assert np.array_equal(hist, want_hist)
+    got = M.step_metrics(cm, hist, [0, 1, 2])
+    ref = RM.step_metrics(logits, lab, softmax, [0, 1, 2])
+    for k in got:
+        same = got[k] == ref[k] or (np.isnan(got[k]) and np.isnan(ref[k]))
+        assert same or (k.startswith("auc_") and abs(got[k] - ref[k]) < 1e-6), (k, got[k], ref[k])
+    # and against the oracle's own forward pass: same hard counts wherever the argmax agrees (it does, bit-exactly)
+    lg_o = R.forward(R.to_torch(perturbed_params(spec)), torch.from_numpy(img), spec)[0]
+    assert int((argmax != R.predict(lg_o).numpy()).sum()) <= 2
+    eng.close()

@@ -80,6 +80,11 @@ def test_train_checkpoint_restore_evaluate_roundtrip(emul_lib, tmp_path):
     losses = [json.loads(l)["total_loss"] for l in open(tmp_path / "log" / "train" / "scalars.jsonl")]
     assert len(losses) == 8 and all(np.isfinite(losses)) and losses[-1] < losses[0]
     assert os.path.exists(tmp_path / "log" / "test" / "scalars.jsonl")
+    # the tf.metrics block of summary_op (model.py:586-626) is logged with every step under the reference's tags
+    rows = [json.loads(l) for l in open(tmp_path / "log" / "train" / "scalars.jsonl")]
+    for tag in ("metrics/accuracy", "metrics/sensitivity_1", "metrics/specificity_1", "metrics/dice_1", "metrics/auc_1"):
+        assert all(tag in r for r in rows), tag
+        assert all(r[tag] is None or 0.0 <= r[tag] <= 1.0 + 1e-6 for r in rows), tag
     _check_event_files(tmp_path / "log", losses)
     with np.load(str(tmp_path / "ckpt" / "checkpoint-8.npz")) as z:  # TF variable names + Adam slots
         assert "vnet/encoder/level_1/conv_1/weights" in z and "vnet/encoder/level_1/conv_1/weights/Adam_1" in z

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libvnet_b200.so")
 
 PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+AUC_BINS = 201   # VNB_AUC_BINS: tf.metrics.auc has 200 thresholds, a probability lies above 0..200 of them
 LOSSES = {
     "xent": 0, "weighted_xent": 1, "sorensen": 2, "weighted_sorensen": 3, "jaccard": 4,
     "weighted_jaccard": 5, "mixed_sorensen": 6, "mixed_weighted_sorensen": 7, "mixed_jaccard": 8,
@@ -77,6 +78,7 @@ _PROTOTYPES = {
     "vnb_event_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "vnb_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "vnb_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "vnb_read_metrics": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vnb_profile_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "vnb_profile_launch": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                      C.c_char_p, C.c_size_t]),

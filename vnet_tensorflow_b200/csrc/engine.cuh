@@ -209,6 +209,7 @@ class Engine {
   void forward_host(const float* images, int N, float* logits, float* softmax, long long* argmax) {
     check_batch(N);
     upload_images(images, N);
+    labelled_n_ = 0;   // the logits no longer belong to the labels on the device
     forward(N, 0.f, 0, false);
     const long long V = voxels(N);
     const int K = cfg_.num_classes;
@@ -363,6 +364,25 @@ class Engine {
     forward_backward_device(N, dropout, seed, true);
     optimizer_step(1);
     return want_loss ? read_loss() : 0.f;
+  }
+  // step metrics of model.py:586-626 for the batch of the last call that was given labels (loss / forward_backward /
+  // train step): integer counts, see metrics_kernel.  confusion [(K+1)][K], auc_hist (optional) [K][2][kAucBins].
+  void read_metrics(int N, unsigned long long* confusion, unsigned long long* auc_hist) {
+    check_batch(N);
+    if (N != labelled_n_)
+      throw std::invalid_argument("read_metrics: the last call with labels (loss / forward_backward / train step) had a batch of " +
+                                  std::to_string(labelled_n_));
+    const int K = cfg_.num_classes;
+    const size_t n_cm = static_cast<size_t>(K + 1) * K, n_hist = static_cast<size_t>(K) * 2 * kAucBins;
+    VNB_CUDA_OK(cudaMemsetAsync(metrics_dev_, 0, (n_cm + n_hist) * sizeof(unsigned long long), stream_));
+    const long long V = voxels(N);
+    VNB_LAUNCH(metrics_kernel, grid_for(V, 256, 4 * sm_count_), 256, 0, stream_, (const float*)acts_[head_act_].a,
+               (const int32_t*)labels_dev_, V, K, auc_hist ? 1 : 0, metrics_dev_, metrics_dev_ + n_cm);
+    ++launches_;
+    VNB_CUDA_OK(cudaMemcpyAsync(confusion, metrics_dev_, n_cm * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    if (auc_hist)
+      VNB_CUDA_OK(cudaMemcpyAsync(auc_hist, metrics_dev_ + n_cm, n_hist * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
   }
   void sync() { VNB_CUDA_OK(cudaStreamSynchronize(stream_)); }
   // distance map of the attention loss (train.py:176-179 distmap_placeholder), [N][D][H][W] in [0,1]
@@ -822,6 +842,7 @@ class Engine {
     sync_buf_ = dev_alloc<double>(static_cast<size_t>(5) * sync_stride_);
     wflip_ = dev_alloc<float>(max_w5);
     labels_dev_ = dev_alloc<int32_t>(voxels(NB));
+    metrics_dev_ = dev_alloc<unsigned long long>(static_cast<size_t>(kMaxClasses + 1) * kMaxClasses + static_cast<size_t>(kMaxClasses) * 2 * kAucBins);
     softmax_dev_ = dev_alloc<float>(voxels(NB) * cfg_.num_classes);
     argmax_dev_ = dev_alloc<long long>(voxels(NB));
     loss_partial_ = dev_alloc<double>(static_cast<size_t>(NB) * kLossBlocks * kMaxClasses * 4);
@@ -862,6 +883,7 @@ class Engine {
   }
   void upload_labels(const int32_t* labels, int N) {
     VNB_CUDA_OK(cudaMemcpyAsync(labels_dev_, labels, voxels(N) * sizeof(int32_t), cudaMemcpyDefault, stream_));
+    labelled_n_ = N;
   }
   BnParams bn_params(const Unit& u) {
     BnParams bp;
@@ -1579,6 +1601,8 @@ class Engine {
   double* partial_ = nullptr;
   float* wflip_ = nullptr;
   int32_t* labels_dev_ = nullptr;
+  unsigned long long* metrics_dev_ = nullptr;   // confusion matrix + AUC histograms of read_metrics
+  int labelled_n_ = 0;                            // batch size of the labels that belong to the logits on the device
   float* softmax_dev_ = nullptr;
   long long* argmax_dev_ = nullptr;
   double *loss_partial_ = nullptr, *terms_dev_ = nullptr;

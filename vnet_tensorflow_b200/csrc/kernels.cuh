@@ -470,6 +470,74 @@ __global__ void softmax_loss_fwd_kernel(const float* __restrict__ logits, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Step metrics: the tf.metrics block of summary_op (model.py:586-626), which the reference fetches in the same
+// sess.run as train_op (model.py:743-748).  Everything there is a function of integer counts over the batch:
+//   confusion[(K+1)][K]: rows = label class (row K collects labels outside [0,K), whose one-hot row is all zero),
+//                        columns = argmax class (first maximum).  accuracy, true/false positives/negatives,
+//                        sensitivity / specificity / dice per class follow on the host (tf.metrics semantics).
+//   auc_hist[K][2][kAucBins]: per class and per truth value (label != c | label == c) the histogram of
+//                        bin = number of tf.metrics.auc thresholds strictly below softmax[c]  (200 thresholds:
+//                        -1e-7, j/199 for j = 1..198, 1 + 1e-7, compared in fp32 as `prediction > threshold`);
+//                        the confusion matrix at every threshold is a suffix sum of it.
+// HBM-bound: (K + 1) * 4 B read per voxel; block-local integer histograms in shared memory, integer atomics to the
+// global counters (exact, order independent).
+// ---------------------------------------------------------------------------------------------
+constexpr int kAucThresholds = 200;             // tf.metrics.auc default num_thresholds
+constexpr int kAucBins = kAucThresholds + 1;
+
+__global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels,
+                                                      long long V, int K, int want_auc,
+                                                      unsigned long long* __restrict__ confusion,
+                                                      unsigned long long* __restrict__ auc_hist) {
+  __shared__ unsigned int cm[(kMaxClasses + 1) * kMaxClasses];
+  __shared__ unsigned int hist[kMaxClasses * 2 * kAucBins];
+  __shared__ float thr[kAucThresholds];
+  for (int i = threadIdx.x; i < (kMaxClasses + 1) * kMaxClasses; i += blockDim.x) cm[i] = 0u;
+  for (int i = threadIdx.x; i < kMaxClasses * 2 * kAucBins; i += blockDim.x) hist[i] = 0u;
+  for (int j = threadIdx.x; j < kAucThresholds; j += blockDim.x)
+    thr[j] = j == 0 ? -1e-7f
+                    : (j == kAucThresholds - 1 ? static_cast<float>(1.0 + 1e-7)
+                                               : static_cast<float>(static_cast<double>(j) / (kAucThresholds - 1)));
+  __syncthreads();
+  for (long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; v < V;
+       v += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float x[kMaxClasses];
+    float mx = -3.4e38f;
+    int am = 0;
+    for (int c = 0; c < K; ++c) {
+      x[c] = logits[v * K + c];
+      if (x[c] > mx) {  // strict > : lowest index wins ties (tf.argmax)
+        mx = x[c];
+        am = c;
+      }
+    }
+    const int t = labels[v];
+    atomicAdd(&cm[((t >= 0 && t < K) ? t : K) * K + am], 1u);
+    if (!want_auc) continue;
+    float se = 0.f;   // same arithmetic as softmax_loss_fwd_kernel: the probabilities are the ones vnb_forward returns
+    for (int c = 0; c < K; ++c) {
+      x[c] = expf(x[c] - mx);
+      se += x[c];
+    }
+    const float inv = 1.0f / se;
+    for (int c = 1; c < K; ++c) {   // model.py:601-603 skips class 0
+      const float pc = x[c] * inv;
+      int b = static_cast<int>(pc * static_cast<float>(kAucThresholds - 1)) + 1;   // first guess, then exact against the table
+      b = b < 0 ? 0 : (b > kAucThresholds ? kAucThresholds : b);
+      while (b < kAucThresholds && pc > thr[b]) ++b;
+      while (b > 0 && !(pc > thr[b - 1])) --b;
+      atomicAdd(&hist[(c * 2 + (t == c ? 1 : 0)) * kAucBins + b], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (K + 1) * K; i += blockDim.x)
+    if (cm[i]) atomicAdd(&confusion[i], static_cast<unsigned long long>(cm[i]));
+  if (want_auc)
+    for (int i = threadIdx.x; i < K * 2 * kAucBins; i += blockDim.x)
+      if (hist[i]) atomicAdd(&auc_hist[i], static_cast<unsigned long long>(hist[i]));
+}
+
 // single block: sums partials, evaluates the configured loss and d(loss)/d(I,L,X) per (n,c)
 // terms_out [N][K][4]; coef_out [N][K][3] = (dLoss/dI, dLoss/dL, dLoss/dX-per-voxel-weight)
 __global__ void loss_finalize_kernel(const double* __restrict__ partial, int N, int nblk, long long Vn,

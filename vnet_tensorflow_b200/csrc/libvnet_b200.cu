@@ -413,6 +413,15 @@ int vnb_profile_read(vnb_handle* h, int cls, double* ms, int64_t* launches, doub
     *launches = n;
   });
 }
+int vnb_read_metrics(vnb_handle* h, int n, uint64_t* confusion, uint64_t* auc_hist) {
+  return guarded([&] {
+    need(h, "handle");
+    need(confusion, "confusion");
+    select_device(h);
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t) && VNB_AUC_BINS == vnb::kAucBins, "metrics layout");
+    h->engine->read_metrics(n, reinterpret_cast<unsigned long long*>(confusion), reinterpret_cast<unsigned long long*>(auc_hist));
+  });
+}
 int vnb_profile_count(vnb_handle* h, int64_t* launches) {
   return guarded([&] {
     need(h, "handle");

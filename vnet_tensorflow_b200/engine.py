@@ -266,6 +266,15 @@ class VNetEngine:
                                                      C.byref(out) if want_loss else None))
         return out.value if want_loss else None
 
+    def metric_counts(self, n: int, want_auc: bool = True):
+        """Integer counts behind the tf.metrics block of model.py:586-626 for the last batch that came with labels:
+        (confusion uint64 [K+1, K] (label row, argmax column; row K = labels outside [0, K)),
+         auc_hist uint64 [K, 2, 201] or None).  `metrics.step_metrics` turns them into the reference's scalars."""
+        cm = np.zeros((self.num_classes + 1, self.num_classes), np.uint64)
+        hist = np.zeros((self.num_classes, 2, _ffi.AUC_BINS), np.uint64) if want_auc else None
+        self.lib.check(self.lib.vnb_read_metrics(self._h, int(n), _ptr(cm), _ptr(hist)))
+        return cm, hist
+
     def apply_gradients(self):
         self.lib.check(self.lib.vnb_apply_gradients(self._h))
 

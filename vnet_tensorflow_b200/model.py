@@ -26,7 +26,7 @@ from typing import List
 
 import numpy as np
 
-from . import checkpoint, config as config_mod, events, nifti
+from . import checkpoint, config as config_mod, events, metrics, nifti
 from .engine import VNetEngine
 from .init import initialize
 from .pipeline import NiftiDataset3D
@@ -159,13 +159,24 @@ class image2label(object):
         d = os.path.join(self.log_dir, which)
         os.makedirs(d, exist_ok=True)
         with open(os.path.join(d, "scalars.jsonl"), "a") as f:
-            f.write(json.dumps(dict(step=step, **scalars)) + "\n")
+            # 0/0 metrics (a class absent from the batch) are NaN as in the reference's summaries; JSON has no NaN
+            f.write(json.dumps(dict(step=step, **{k: (None if isinstance(v, float) and math.isnan(v) else v)
+                                                  for k, v in scalars.items()})) + "\n")
         # the same scalars under the reference's summary tags, for `tensorboard --logdir LogDir` (model.py:562,644)
         writers = self.__dict__.setdefault("_event_writers", {})
         if which not in writers:
             writers[which] = events.EventFileWriter(d)
         tags = {"total_loss": "loss/0.total_loss", "learning_rate": "learning_rate"}
         writers[which].add_scalars(step, {tags.get(k, k): v for k, v in scalars.items()})
+
+    def _step_metrics(self, n):
+        """The tf.metrics block of summary_op (model.py:586-626), fetched with every training / test step
+        (model.py:743-748,784-789): accuracy and, per foreground class, sensitivity / specificity / dice / auc under
+        the reference's summary tags.  The counts come from the device (vnb_read_metrics)."""
+        cm, hist = self.engine.metric_counts(n)
+        scalars = metrics.step_metrics(cm, hist, self.label_classes)
+        keep = ("accuracy", "sensitivity_", "specificity_", "dice_", "auc_")
+        return {"metrics/" + k: float(v) for k, v in scalars.items() if k.startswith(keep)}
 
     def _learning_rate(self, step):
         """tf.train.exponential_decay(lr0, global_step, decay_steps, decay_factor, staircase=False), model.py:641-643."""
@@ -203,7 +214,8 @@ class image2label(object):
                 loss_sum += loss
                 count += 1
                 step = self.engine.global_step
-                self._log("train", step, total_loss=loss, learning_rate=self._learning_rate(step - 1))
+                self._log("train", step, total_loss=loss, learning_rate=self._learning_rate(step - 1),
+                          **self._step_metrics(len(image)))
                 if step % self.log_interval == 0:
                     print("{}: Saving checkpoint of step {} at {}...".format(_now(), step, self.ckpt_dir))
                     checkpoint.save(self.engine, self.ckpt_dir, step, epoch, self.cfg.checkpoint_format)
@@ -215,7 +227,7 @@ class image2label(object):
                         timg, tlab = next(test_iter)
                     tloss = self.engine.loss(timg, tlab)  # dropout 0, batch statistics, no update (model.py:784-789)
                     print('{}: Segmentation testing loss: {}'.format(_now(), str(tloss)))
-                    self._log("test", step, total_loss=tloss)
+                    self._log("test", step, total_loss=tloss, **self._step_metrics(len(timg)))
             print("{}: Training of epoch {} complete, epoch loss: {}".format(_now(), epoch + 1, loss_sum / max(count, 1)))
             print("{}: Saving checkpoint of epoch {} at {}...".format(_now(), epoch + 1, self.ckpt_dir))
             checkpoint.save(self.engine, self.ckpt_dir, self.engine.global_step, epoch + 1, self.cfg.checkpoint_format)
