@@ -23,6 +23,9 @@
 #include "conv_tc.cuh"
 #include "vnb_cuda.h"
 #include "wgrad_tc.cuh"
+#ifndef VNB_EMULATE
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: no link dependency, a no-op unless a profiler injects itself
+#endif
 
 namespace vnb {
 
@@ -109,6 +112,27 @@ struct Unit {
   TcConvPlan tc;                      // tensor-core plan (precision != fp32)
 };
 
+// NVTX range around the launches of one unit and pass ("vnet/decoder/level_1/conv_1 fwd"), on with VNB_NVTX=1:
+// `ncu --nvtx --nvtx-include "<scope> fwd/"` then captures the kernels of a single layer.
+struct NvtxRange {
+  bool on;
+  NvtxRange(bool enabled, const std::string& scope, const char* pass) : on(enabled) {
+#ifndef VNB_EMULATE
+    if (on) nvtxRangePushA((scope + pass).c_str());
+#else
+    (void)scope;
+    (void)pass;
+#endif
+  }
+  ~NvtxRange() {
+#ifndef VNB_EMULATE
+    if (on) nvtxRangePop();
+#endif
+  }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 class Engine {
  public:
   explicit Engine(const EngineConfig& cfg) : cfg_(cfg) {
@@ -135,6 +159,8 @@ class Engine {
     dbg_no_tc_fprop_ = getenv("VNB_DEBUG_NO_TC_FPROP") != nullptr;
     dbg_no_tc_dgrad_ = getenv("VNB_DEBUG_NO_TC_DGRAD") != nullptr;
     dbg_no_tc_wgrad_ = getenv("VNB_DEBUG_NO_TC_WGRAD") != nullptr;
+    const char* nv = getenv("VNB_NVTX");
+    nvtx_ = nv && nv[0] == '1';
     build_graph();
     allocate();
     init_default_params();
@@ -1086,6 +1112,7 @@ class Engine {
     }
     for (size_t ui = 0; ui < units_.size(); ++ui) {
       Unit& u = units_[ui];
+      NvtxRange range(nvtx_, u.scope, " fwd");
       const Act& o = acts_[u.out];
       const long long V = voxels_of(o.dims, N);
       int nblk = 1, nq_stride = 2;
@@ -1183,6 +1210,7 @@ class Engine {
     ++launches_;
     for (int ui = static_cast<int>(units_.size()) - 1; ui >= 0; --ui) {
       Unit& u = units_[ui];
+      NvtxRange range(nvtx_, u.scope, " bwd");
       Act& o = acts_[u.out];
       const long long V = voxels_of(o.dims, N);
       if (u.kind == U_GATE) {
@@ -1579,6 +1607,7 @@ class Engine {
   bool wg_pending_ = false;
   bool comm_waits_wgrad_ = false;
   bool dbg_no_tc_fprop_ = false, dbg_no_tc_dgrad_ = false, dbg_no_tc_wgrad_ = false;
+  bool nvtx_ = false;   // VNB_NVTX=1: NVTX range per unit and pass
   std::vector<ParamEntry> entries_;
   std::map<std::string, size_t> index_;
   std::vector<Act> acts_;
