@@ -423,3 +423,43 @@ def test_step_metrics_match_the_reference_metric_block(emul_lib, spec, N):
     cm2, hist2 = eng.metric_counts(N, want_auc=False)
     assert hist2 is None and np.array_equal(cm2, cm)
     eng.close()
+
+
+def test_staged_input_steps_equal_direct_steps(emul_lib):
+    """vnb_stage_batch / vnb_train_step_staged (the feed_dict copy taken off the critical path) is the same arithmetic
+    as vnb_train_step: three steps with a one-batch look-ahead from page-locked arrays give bit-identical losses and
+    weights; a staged step without a staged batch is an error; a short last batch is staged like any other."""
+    spec, P = SPEC_A, 8
+    params = perturbed_params(spec)
+    batches = [synth_batch(s, n, P, spec.in_channels, spec.num_classes) for s, n in ((0, 2), (1, 2), (2, 1))]
+    direct = engine_for(spec, P, 2, "weighted_sorensen", (0.1, 1.0), emul_lib)
+    direct.set_params(params)
+    want = [direct.train_step(img, lab, 0.0, seed=i) for i, (img, lab) in enumerate(batches)]
+    eng = engine_for(spec, P, 2, "weighted_sorensen", (0.1, 1.0), emul_lib)
+    eng.set_params(params)
+    with pytest.raises(_ffi.VnbError):
+        eng.train_step_staged()
+    pin_img = [eng.pinned_array((2, P, P, P, 1), np.float32) for _ in range(2)]
+    pin_lab = [eng.pinned_array((2, P, P, P), np.int32) for _ in range(2)]
+
+    def stage(i):
+        img, lab = batches[i]
+        n = img.shape[0]
+        pin_img[i % 2][:n], pin_lab[i % 2][:n] = img, lab
+        eng.stage_batch(pin_img[i % 2][:n], pin_lab[i % 2][:n])
+
+    got = []
+    stage(0)
+    for i in range(len(batches)):
+        eng.train_step_staged(0.0, seed=i, want_loss=False)
+        if i + 1 < len(batches):
+            stage(i + 1)              # overlaps step i on the device
+        got.append(eng.last_loss())
+    assert got == want
+    for k in ("vnet/encoder/level_1/conv_1/weights", "vnet/output_layer/weights", "vnet/decoder/level_1/up_convolution/weights"):
+        assert np.array_equal(eng.get_param(k), direct.get_param(k)), k
+    assert eng.global_step == direct.global_step == 3
+    cm, _ = eng.metric_counts(1, want_auc=False)          # the labels of the staged short batch are the current ones
+    assert int(cm.sum()) == P ** 3
+    eng.close()
+    direct.close()

@@ -520,3 +520,45 @@ def test_step_metrics_match_the_reference_metric_block(gpu_lib, precision):
     lg_o = R.forward(R.to_torch(perturbed_params(spec)), torch.from_numpy(img), spec)[0]
     assert int((argmax != R.predict(lg_o).numpy()).sum()) <= 2
     eng.close()
+
+
+def test_staged_input_steps_equal_direct_steps(gpu_lib):
+    """vnb_stage_batch / vnb_train_step_staged on the device: copy stream, events and the device-to-device commit give
+    the losses and weights of vnb_train_step bit for bit, with the next batch staged while a step runs.  CPU twin:
+    tests/test_engine_emul.py.  (Added after the round-1 GPU budget was spent: first run on hardware is the round-end
+    GPU suite.)"""
+    spec = R.VNetSpec(**CASES["tiny_m1_k2"][0])
+    P = 16
+    params = perturbed_params(spec)
+    batches = [synth_batch(s, n, P, 1, 2) for s, n in ((0, 2), (1, 2), (2, 1), (3, 2))]
+    direct = engine_for(spec, P, 2, "weighted_sorensen", (0.1, 1.0), gpu_lib, precision="bf16x3")
+    direct.set_params(params)
+    want = [direct.train_step(img, lab, 0.0, seed=i) for i, (img, lab) in enumerate(batches)]
+    eng = engine_for(spec, P, 2, "weighted_sorensen", (0.1, 1.0), gpu_lib, precision="bf16x3")
+    eng.set_params(params)
+    pins = [(eng.pinned_array((2, P, P, P, 1), np.float32), eng.pinned_array((2, P, P, P), np.int32)) for _ in range(2)]
+
+    def stage(i):
+        img, lab = batches[i]
+        n = img.shape[0]
+        pi, pl = pins[i % 2]
+        pi[:n], pl[:n] = img, lab
+        eng.stage_batch(pi[:n], pl[:n])
+
+    got = []
+    stage(0)
+    for i in range(len(batches)):
+        eng.train_step_staged(0.0, seed=i, want_loss=False)
+        if i + 1 < len(batches):
+            stage(i + 1)
+        got.append(eng.last_loss())
+    # the first step is bit-identical; from the second on the 2x2x2 / 1x1x1 filter gradients (fp32 atomics over their
+    # voxel splits, DESIGN 4) leave the two engines last-bit freedom, so the trajectories are compared to rounding
+    assert got[0] == want[0]
+    assert max(abs(a - b) for a, b in zip(got, want)) < 1e-4
+    k = "vnet/encoder/level_1/conv_1/weights"
+    a, b = eng.get_param(k).astype(np.float64), direct.get_param(k).astype(np.float64)
+    assert np.sqrt(((a - b) ** 2).sum()) <= 1e-3 * np.sqrt((b ** 2).sum())
+    assert eng.global_step == direct.global_step == len(batches)
+    eng.close()
+    direct.close()

@@ -174,6 +174,11 @@ class Engine {
       cudaEventDestroy(wg_done_ev_);
     }
 #endif
+    if (copy_stream_) {
+      cudaStreamDestroy(copy_stream_);
+      cudaEventDestroy(staged_ev_);
+      cudaEventDestroy(staging_free_ev_);
+    }
     cudaStreamDestroy(stream_);
   }
 
@@ -357,6 +362,38 @@ class Engine {
     check_batch(N);
     upload_images(images, N);
     upload_labels(labels, N);
+  }
+  // Input staging (the step before the hot path): the next batch is copied into staging buffers on a copy
+  // stream while the current step computes; commit_staged() orders the compute stream after that copy, moves the batch
+  // into the network's input buffers device to device (microseconds) and frees the staging buffers for the next one.
+  void stage_batch(const float* images, const int32_t* labels, int N) {
+    check_batch(N);
+    const Act& a = acts_[image_act_];
+    if (!copy_stream_) {
+      VNB_CUDA_OK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+      VNB_CUDA_OK(cudaEventCreateWithFlags(&staged_ev_, cudaEventDisableTiming));
+      VNB_CUDA_OK(cudaEventCreateWithFlags(&staging_free_ev_, cudaEventDisableTiming));
+      stage_img_ = dev_alloc<float>(voxels_of(a.dims, cfg_.max_batch) * a.C);
+      stage_lab_ = dev_alloc<int32_t>(voxels(cfg_.max_batch));
+    } else {
+      VNB_CUDA_OK(cudaStreamWaitEvent(copy_stream_, staging_free_ev_, 0));   // the previous commit has read the buffers
+    }
+    VNB_CUDA_OK(cudaMemcpyAsync(stage_img_, images, voxels_of(a.dims, N) * a.C * sizeof(float), cudaMemcpyDefault, copy_stream_));
+    VNB_CUDA_OK(cudaMemcpyAsync(stage_lab_, labels, voxels(N) * sizeof(int32_t), cudaMemcpyDefault, copy_stream_));
+    VNB_CUDA_OK(cudaEventRecord(staged_ev_, copy_stream_));
+    staged_n_ = N;
+  }
+  int commit_staged() {
+    if (staged_n_ == 0) throw std::invalid_argument("no staged batch: call vnb_stage_batch first");
+    const Act& a = acts_[image_act_];
+    const int N = staged_n_;
+    VNB_CUDA_OK(cudaStreamWaitEvent(stream_, staged_ev_, 0));
+    VNB_CUDA_OK(cudaMemcpyAsync(a.a, stage_img_, voxels_of(a.dims, N) * a.C * sizeof(float), cudaMemcpyDeviceToDevice, stream_));
+    VNB_CUDA_OK(cudaMemcpyAsync(labels_dev_, stage_lab_, voxels(N) * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream_));
+    VNB_CUDA_OK(cudaEventRecord(staging_free_ev_, stream_));
+    labelled_n_ = N;
+    staged_n_ = 0;
+    return N;
   }
   // optimiser over the flat buffers; `world` folds the data-parallel mean into the update
   void optimizer_step(int world) {
@@ -1631,6 +1668,11 @@ class Engine {
   float* wflip_ = nullptr;
   int32_t* labels_dev_ = nullptr;
   unsigned long long* metrics_dev_ = nullptr;   // confusion matrix + AUC histograms of read_metrics
+  cudaStream_t copy_stream_ = 0;                  // input staging (stage_batch / commit_staged), created on first use
+  cudaEvent_t staged_ev_{}, staging_free_ev_{};
+  float* stage_img_ = nullptr;
+  int32_t* stage_lab_ = nullptr;
+  int staged_n_ = 0;
   int labelled_n_ = 0;                            // batch size of the labels that belong to the logits on the device
   float* softmax_dev_ = nullptr;
   long long* argmax_dev_ = nullptr;

@@ -380,6 +380,40 @@ int vnb_train_step_resident(vnb_handle* h, int n, float dropout, uint64_t seed) 
     h->engine->optimizer_step(world);
   });
 }
+int vnb_stage_batch(vnb_handle* h, const float* images, const int32_t* labels, int n) {
+  return guarded([&] {
+    need(h, "handle");
+    need(images, "images");
+    need(labels, "labels");
+    select_device(h);
+    h->engine->stage_batch(images, labels, n);
+  });
+}
+int vnb_train_step_staged(vnb_handle* h, float dropout, uint64_t seed, float* loss_out) {
+  int n = 0;
+  int rc = guarded([&] {
+    need(h, "handle");
+    select_device(h);
+    n = h->engine->commit_staged();
+  });
+  if (rc != VNB_OK) return rc;
+  rc = vnb_train_step_resident(h, n, dropout, seed);
+  if (rc != VNB_OK) return rc;
+  if (loss_out) return guarded([&] { *loss_out = h->engine->read_loss(); });
+  return VNB_OK;
+}
+int vnb_host_alloc(size_t bytes, void** out) {
+  return guarded([&] {
+    need(out, "out");
+    *out = nullptr;
+    VNB_CUDA_OK(cudaMallocHost(out, bytes ? bytes : 1));
+  });
+}
+int vnb_host_free(void* p) {
+  return guarded([&] {
+    if (p) VNB_CUDA_OK(cudaFreeHost(p));
+  });
+}
 int vnb_event_record(vnb_handle* h, int which) {
   return guarded([&] {
     need(h, "handle");

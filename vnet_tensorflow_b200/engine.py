@@ -284,6 +284,46 @@ class VNetEngine:
         self.lib.check(self.lib.vnb_upload_batch(self._h, _ptr(a), _ptr(l), a.shape[0]))
         return a.shape[0]
 
+    def stage_batch(self, images, labels):
+        """Enqueue the copy of the NEXT batch on the copy stream (overlaps the running step when the arrays are
+        page-locked, see pinned_array); pair with train_step_staged."""
+        a = self._check_images(images)
+        l = self._check_labels(labels, a.shape[0])
+        self.lib.check(self.lib.vnb_stage_batch(self._h, _ptr(a), _ptr(l), a.shape[0]))
+        self._staged = (a, l)        # keep the host buffers alive until the staged step has consumed them
+        return a.shape[0]
+
+    def train_step_staged(self, dropout_rate=0.0, seed=0, want_loss=True):
+        out = C.c_float()
+        self.lib.check(self.lib.vnb_train_step_staged(self._h, float(dropout_rate), int(seed),
+                                                      C.byref(out) if want_loss else None))
+        return out.value if want_loss else None
+
+    def last_loss(self) -> float:
+        """Loss of the last step issued with want_loss=False (synchronises)."""
+        return self.losses()[0]
+
+    def pinned_array(self, shape, dtype) -> np.ndarray:
+        """NumPy array over page-locked host memory (cudaMallocHost), freed with the array."""
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        p = C.c_void_p()
+        self.lib.check(self.lib.vnb_host_alloc(nbytes, C.byref(p)))
+        lib = self.lib
+
+        class _Owner:
+            def __init__(self, ptr):
+                self.ptr = ptr
+                self.buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+
+            def __del__(self):
+                lib.vnb_host_free(self.ptr)
+
+        owner = _Owner(p)
+        arr = np.frombuffer(owner.buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        self.__dict__.setdefault("_pinned_owners", []).append(owner)   # freed with the engine object, not before its views
+        return arr
+
     def train_step_resident(self, n, dropout_rate=0.0, seed=0):
         self.lib.check(self.lib.vnb_train_step_resident(self._h, int(n), float(dropout_rate), int(seed)))
 

@@ -98,8 +98,10 @@ class image2label(object):
             out.append(cls(**(t.get("variables") or {})))
         return out
 
-    def dataset_iterator(self, data_dir, transforms, train=True):
-        """model.py:267-295: dataset -> shuffle(buffer 3) -> batch(drop_remainder)."""
+    def dataset_iterator(self, data_dir, transforms, train=True, pinned_ring=None):
+        """model.py:267-295: dataset -> shuffle(buffer 3) -> batch(drop_remainder).  `pinned_ring` (optional): list of
+        (images, labels) page-locked arrays of one batch each; batches are then collated straight into them, in turn,
+        by the prefetch thread, so that the asynchronous host-to-device copy of the staged step needs no extra copy."""
         usable = (not self.cfg.synthetic) and os.path.isdir(data_dir) and self._has_nifti(data_dir)
         if usable:
             ds = NiftiDataset3D.NiftiDataset(data_dir=data_dir, image_filenames=self.image_filenames,
@@ -117,6 +119,7 @@ class image2label(object):
             buf: List = []
             it = iter(ds)
             pending = []
+            produced = 0
             while True:
                 while len(buf) < 3:  # tf.data shuffle(buffer_size=3)
                     try:
@@ -127,7 +130,14 @@ class image2label(object):
                     break
                 pending.append(buf.pop(random.randrange(len(buf))))
                 if len(pending) == self.batch_size:
-                    yield np.stack([p[0] for p in pending], 0), np.stack([p[1] for p in pending], 0)
+                    if pinned_ring:
+                        img_out, lab_out = pinned_ring[produced % len(pinned_ring)]
+                        np.stack([p[0] for p in pending], 0, out=img_out)
+                        np.stack([np.asarray(p[1]).reshape(lab_out.shape[1:]) for p in pending], 0, out=lab_out)
+                        yield img_out, lab_out
+                    else:
+                        yield np.stack([p[0] for p in pending], 0), np.stack([p[1] for p in pending], 0)
+                    produced += 1
                     pending = []
         return batches
 
@@ -186,7 +196,12 @@ class image2label(object):
         print("{}: VNet Tensorflow training start...".format(_now()))
         self.read_config()
         self.build_model_graph()
-        train_batches = self.dataset_iterator(self.train_data_dir, self._transforms(self.training_pipeline, "train"), True)
+        # page-locked batch buffers for the staged input copy: 2 queued by the prefetch thread + 1 collated and waiting
+        # for a queue slot + 1 in flight to the device + 1 whose step is running, + 1 spare
+        ring = [(self.engine.pinned_array((self.batch_size,) + tuple(self.patch_shape) + (self.input_channel_num,), np.float32),
+                 self.engine.pinned_array((self.batch_size,) + tuple(self.patch_shape), np.int32)) for _ in range(6)]
+        train_batches = self.dataset_iterator(self.train_data_dir, self._transforms(self.training_pipeline, "train"), True,
+                                              pinned_ring=ring)
         test_batches = self.dataset_iterator(self.test_data_dir, self._transforms(self.training_pipeline, "test"), True) if self.testing else None
         start_epoch = 0
         print("{}: Start training...".format(_now()))
@@ -206,10 +221,21 @@ class image2label(object):
         for epoch in range(start_epoch, self.epoches):
             print("{}: Epoch {} starts...".format(_now(), epoch + 1))
             loss_sum, count = 0.0, 0
-            for image, label in train_batches():
+            # model.py:736-748 with the feed_dict copy taken off the critical path: the next batch is staged (copied
+            # to the device on a copy stream) while the step on the current one runs; same arithmetic, same order
+            batch_iter = iter(train_batches())
+            staged = next(batch_iter, None)
+            if staged is not None:
+                self.engine.stage_batch(*staged)
+            while staged is not None:
+                image = staged[0]
                 if self.engine.global_step > self.max_itr:
                     sys.exit("{}: Reach maximum iteration steps, training abort.".format(_now()))
-                loss = self.engine.train_step(image, label, self.dropout_rate, seed=self.engine.global_step)
+                self.engine.train_step_staged(self.dropout_rate, seed=self.engine.global_step, want_loss=False)
+                staged = next(batch_iter, None)
+                if staged is not None:
+                    self.engine.stage_batch(*staged)
+                loss = self.engine.last_loss()
                 print('{}: Segmentation training loss: {}'.format(_now(), str(loss)))
                 loss_sum += loss
                 count += 1
