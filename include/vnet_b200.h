@@ -165,11 +165,11 @@ int vnb_train_step_resident(vnb_handle* h, int n, float dropout_rate, uint64_t s
  * stream after it, moves the batch into the input buffers device to device and runs one optimiser step on it (same
  * arithmetic as vnb_train_step).  Pattern: stage(b0); loop { step_staged(loss_out = NULL); stage(b_next);
  * vnb_read_losses } - the host-to-device copy of b_next then overlaps the step on b.  The copy is asynchronous only
- * from page-locked memory (vnb_host_alloc / vnb_host_free = cudaMallocHost / cudaFreeHost); such a buffer must stay
+ * from page-locked memory (vnb_host_alloc / vnb_host_free = cudaMallocHost / cudaFreeHost in the context of the handle); such a buffer must stay
  * untouched until the staged step has been issued and a later call synchronised (vnb_read_losses, vnb_sync). */
 int vnb_stage_batch(vnb_handle* h, const float* images, const int32_t* labels, int n);
 int vnb_train_step_staged(vnb_handle* h, float dropout_rate, uint64_t seed, float* loss_out);
-int vnb_host_alloc(size_t bytes, void** out);
+int vnb_host_alloc(vnb_handle* h, size_t bytes, void** out);
 int vnb_host_free(void* p);
 /* CUDA-event timing on the handle's compute stream: record event 0 / 1, then read the elapsed ms */
 int vnb_event_record(vnb_handle* h, int which);

@@ -402,10 +402,12 @@ int vnb_train_step_staged(vnb_handle* h, float dropout, uint64_t seed, float* lo
   if (loss_out) return guarded([&] { *loss_out = h->engine->read_loss(); });
   return VNB_OK;
 }
-int vnb_host_alloc(size_t bytes, void** out) {
+int vnb_host_alloc(vnb_handle* h, size_t bytes, void** out) {
   return guarded([&] {
+    need(h, "handle");
     need(out, "out");
     *out = nullptr;
+    select_device(h);   // page-locked through the handle's own context (no stray context on device 0)
     VNB_CUDA_OK(cudaMallocHost(out, bytes ? bytes : 1));
   });
 }

@@ -308,7 +308,7 @@ class VNetEngine:
         dt = np.dtype(dtype)
         nbytes = int(np.prod(shape)) * dt.itemsize
         p = C.c_void_p()
-        self.lib.check(self.lib.vnb_host_alloc(nbytes, C.byref(p)))
+        self.lib.check(self.lib.vnb_host_alloc(self._h, nbytes, C.byref(p)))
         lib = self.lib
 
         class _Owner:
