@@ -463,3 +463,56 @@ def test_staged_input_steps_equal_direct_steps(emul_lib):
     assert int(cm.sum()) == P ** 3
     eng.close()
     direct.close()
+
+
+class _FakeCudaTensor:
+    """Stand-in for a torch CUDA tensor over NumPy memory: in the emulation build a 'device pointer' is a host pointer,
+    so VNetEngine's device-tensor path (dtype / contiguity / device checks, raw data_ptr hand-over) runs on the CPU."""
+    __module__ = "torch"
+    is_cuda = True
+
+    class _Dev:
+        index = 0
+
+    def __init__(self, array, torch_dtype):
+        self._a = np.ascontiguousarray(array)
+        self.dtype, self.device = torch_dtype, self._Dev()
+        self.shape, self.ndim = self._a.shape, self._a.ndim
+
+    def is_contiguous(self):
+        return True
+
+    def data_ptr(self):
+        return self._a.ctypes.data
+
+    def __getitem__(self, idx):
+        return _FakeCudaTensor(self._a[idx], self.dtype)
+
+
+def test_device_tensor_inputs_take_the_raw_pointer_path(emul_lib, monkeypatch):
+    """CPU twin of the GPU test test_device_resident_batches_give_identical_results: same results as host arrays,
+    [N,X,Y,Z,1] labels accepted as a view, wrong dtype / wrong GPU refused before the C ABI is reached."""
+    class _Stream:
+        def synchronize(self):
+            pass
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    spec, P, N = SPEC_A, 8, 2
+    img, lab = synth_batch(4, N, P, 1, 2)
+    eng = engine_for(spec, P, N, "weighted_sorensen", (0.1, 1.0), emul_lib)
+    eng.set_params(perturbed_params(spec))
+    want_logits = eng.forward(img)[0]
+    want_loss = eng.loss(img, lab)
+    d_img, d_lab = _FakeCudaTensor(img, torch.float32), _FakeCudaTensor(lab[..., None], torch.int32)
+    assert np.array_equal(eng.forward(d_img)[0], want_logits)
+    assert eng.loss(d_img, d_lab) == want_loss
+    assert eng.forward_backward(d_img, d_lab) == want_loss
+    assert eng.stage_batch(d_img, d_lab) == N and eng.train_step_staged(want_loss=True) == want_loss
+    with pytest.raises(ValueError):
+        eng.forward(_FakeCudaTensor(img.astype(np.float64), torch.float64))
+    with pytest.raises(ValueError):
+        eng.loss(d_img, _FakeCudaTensor(lab.astype(np.int64), torch.int64))
+    other = _FakeCudaTensor(img, torch.float32)
+    other.device.index = 1      # a tensor on another GPU than the handle's
+    with pytest.raises(ValueError):
+        eng.forward(other)
+    eng.close()
