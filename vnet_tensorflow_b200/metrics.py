@@ -5,6 +5,8 @@ false_negatives / auc` on one-hot label and prediction volumes and derives sensi
 update ops; `accuracy` is the mean of `pred == label`.  Its accumulators are reset before every step (model.py:730), so
 each value describes one batch.  tf.metrics counts are float32 variables and the derived scalars are float32 divisions
 (0/0 gives NaN, as `tf.divide` does); this module follows that arithmetic on the counts the device produced.
+Counts are exact integers here and rounded to float32 once; TensorFlow sums 0/1 floats, which is the same number up
+to 2^24 = 16.7 M voxels per count (a batch of eight 128^3 patches) and may differ in the last float32 digit beyond.
 """
 from __future__ import annotations
 
