@@ -191,6 +191,10 @@ int vnb_profile_launch(vnb_handle* h, int64_t index, int* kernel_class, double* 
  * softmax_attention of the last forward pass (train.py:288), [n][X][Y][Z][K] */
 int vnb_set_distmap(vnb_handle* h, const float* distmap, int n);
 int vnb_read_losses(vnb_handle* h, float out_total_seg_att[3]);
+/* the two summands of the segmentation loss of the last loss / training call as the reference's summaries name them
+ * (model.py:529-530,537-538,545-546,553-554): out[0] = '1.dice' = 1 - dice, out[1] = '2.regularized_xent' =
+ * Loss.Alpha * cross entropy (out[0] = 0 for the cross-entropy losses, out[1] = 0 for the pure Dice losses) */
+int vnb_read_loss_parts(vnb_handle* h, float out_dice_xent[2]);
 int vnb_read_softmax_attention(vnb_handle* h, float* host, size_t bytes, int n);
 
 int vnb_sync(vnb_handle* h);

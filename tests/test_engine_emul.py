@@ -516,3 +516,29 @@ def test_device_tensor_inputs_take_the_raw_pointer_path(emul_lib, monkeypatch):
     with pytest.raises(ValueError):
         eng.forward(other)
     eng.close()
+
+
+@pytest.mark.parametrize("loss,weights,alpha", [("mixed_sorensen", (), 0.7), ("mixed_weighted_jaccard", (0.2, 1.0), 1.5),
+                                                ("weighted_sorensen", (0.1, 1.0), 1.0), ("xent", (), 1.0)])
+def test_loss_parts_are_the_two_summaries_of_the_mixed_losses(emul_lib, loss, weights, alpha):
+    """vnb_read_loss_parts: '1.dice' = 1 - dice and '2.regularized_xent' = Loss.Alpha * xent (model.py:529-530)."""
+    spec, P, N = SPEC_A, 8, 2
+    params = perturbed_params(spec)
+    img, lab = synth_batch(1, N, P, 1, 2)
+    eng = engine_for(spec, P, N, loss, weights, emul_lib, loss_alpha=alpha)
+    eng.set_params(params)
+    total = eng.loss(img, lab)
+    dice_part, xent_part = eng.loss_parts()
+    logits = R.forward(R.to_torch(params), torch.from_numpy(img), spec)[0]
+    want_total = float(R.loss_from_logits(logits, torch.from_numpy(lab), loss, weights, alpha))
+    assert abs(total - want_total) < 2e-6 and abs(dice_part + xent_part - total) < 1e-6
+    if loss == "xent":
+        assert dice_part == 0.0
+    else:
+        kind = "sorensen" if "sorensen" in loss else "jaccard"
+        onehot = torch.nn.functional.one_hot(torch.from_numpy(lab).long(), 2).float()
+        d = R.dice_coe(torch.softmax(logits, -1), onehot, loss_type=kind, weights=tuple(weights) if "weighted" in loss else ())
+        assert abs(dice_part - (1.0 - float(d))) < 2e-6
+        if not loss.startswith("mixed"):
+            assert abs(xent_part) < 1e-6
+    eng.close()

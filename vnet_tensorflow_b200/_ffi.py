@@ -82,6 +82,7 @@ _PROTOTYPES = {
     "vnb_train_step_staged": (C.c_int, [C.c_void_p, C.c_float, C.c_uint64, C.POINTER(C.c_float)]),
     "vnb_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "vnb_host_free": (C.c_int, [C.c_void_p]),
+    "vnb_read_loss_parts": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "vnb_read_metrics": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "vnb_profile_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "vnb_profile_launch": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -459,6 +459,15 @@ class Engine {
     VNB_CUDA_OK(cudaMemcpyAsync(out, loss_dev_, 3 * sizeof(float), cudaMemcpyDeviceToHost, stream_));
     VNB_CUDA_OK(cudaStreamSynchronize(stream_));
   }
+  // the two summands of a mixed loss as the reference logs them (model.py:529-530): '1.dice' = 1 - dice and
+  // '2.regularized_xent' = Loss.Alpha * cross entropy (0 for the pure Dice losses; the whole loss for the x-ent ones)
+  void read_loss_parts(float out[2]) {
+    float l[4];
+    VNB_CUDA_OK(cudaMemcpyAsync(l, loss_dev_, 4 * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+    VNB_CUDA_OK(cudaStreamSynchronize(stream_));
+    out[0] = l[3];
+    out[1] = l[1] - l[3];
+  }
   // softmax_attention of the last forward pass (train.py:288), [N][D][H][W][K]
   void read_softmax_attention(float* host, int N) {
     if (!cfg_.attention) throw std::invalid_argument("the attention path is not enabled");

@@ -556,7 +556,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partial, int N, 
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
-  double loss = 0.0;
+  double loss = 0.0, dice_part = 0.0;
   const double s = cfg.smooth;
   for (int i = 0; i < pairs * 3; ++i) coef_out[i] = 0.f;
   if (cfg.use_dice) {
@@ -597,6 +597,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partial, int N, 
         }
     }
     loss += 1.0 - dice;
+    dice_part = 1.0 - dice;
   }
   if (cfg.use_xent) {  // reduce_mean over all N*V voxels (model.py:91,496)
     double xs = 0.0;
@@ -615,6 +616,7 @@ __global__ void loss_finalize_kernel(const double* __restrict__ partial, int N, 
   loss_out[0] = static_cast<float>(loss + att);  // train.py:417 total_loss_op
   loss_out[1] = static_cast<float>(loss);
   loss_out[2] = static_cast<float>(att);
+  loss_out[3] = static_cast<float>(dice_part);   // summary '1.dice' of the mixed losses (model.py:529,537,545,553)
 }
 
 // dL/dlogits, written to `dlogits` (the output layer's activation-gradient buffer)

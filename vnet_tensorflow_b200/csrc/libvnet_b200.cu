@@ -499,6 +499,14 @@ int vnb_read_losses(vnb_handle* h, float out[3]) {
     h->engine->read_losses(out);
   });
 }
+int vnb_read_loss_parts(vnb_handle* h, float out[2]) {
+  return guarded([&] {
+    need(h, "handle");
+    need(out, "out");
+    select_device(h);
+    h->engine->read_loss_parts(out);
+  });
+}
 int vnb_read_softmax_attention(vnb_handle* h, float* host, size_t bytes, int n) {
   return guarded([&] {
     need(h, "handle");

@@ -172,6 +172,13 @@ class VNetEngine:
         self.lib.check(self.lib.vnb_read_losses(self._h, out))
         return float(out[0]), float(out[1]), float(out[2])
 
+    def loss_parts(self) -> Tuple[float, float]:
+        """('1.dice' = 1 - dice, '2.regularized_xent' = Loss.Alpha * cross entropy) of the last loss / training call,
+        the two scalars the reference logs next to the total of a mixed loss (model.py:529-530)."""
+        out = (C.c_float * 2)()
+        self.lib.check(self.lib.vnb_read_loss_parts(self._h, out))
+        return float(out[0]), float(out[1])
+
     def softmax_attention(self, n: int) -> np.ndarray:
         a = np.empty((n,) + self.patch_shape + (self.num_classes,), np.float32)
         self.lib.check(self.lib.vnb_read_softmax_attention(self._h, _ptr(a), a.nbytes, n))

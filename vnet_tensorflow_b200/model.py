@@ -186,7 +186,10 @@ class image2label(object):
         cm, hist = self.engine.metric_counts(n)
         scalars = metrics.step_metrics(cm, hist, self.label_classes)
         keep = ("accuracy", "sensitivity_", "specificity_", "dice_", "auc_")
-        return {"metrics/" + k: float(v) for k, v in scalars.items() if k.startswith(keep)}
+        out = {"metrics/" + k: float(v) for k, v in scalars.items() if k.startswith(keep)}
+        if self.loss_name.startswith("mixed"):      # model.py:529-530: the two summands of a mixed loss
+            out["loss/1.dice"], out["loss/2.regularized_xent"] = self.engine.loss_parts()
+        return out
 
     def _learning_rate(self, step):
         """tf.train.exponential_decay(lr0, global_step, decay_steps, decay_factor, staircase=False), model.py:641-643."""
