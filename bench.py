@@ -24,6 +24,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TRAIN_GFLOP_PER_PATCH_128 = 3371.7   # BASELINE.md §2 (fprop + dgrad + wgrad, 128^3, M=1, K=2)
+METRIC = "patches/sec (128^3, 1ch->2cls) training step"
+DROPOUT = 0.01                       # configs/*.json Networks.Dropout
 
 # BASELINE.json configs[i]; [1] is the one the metric is quoted on (the default), the others are parity-test
 # configurations that can be timed on request with --config
@@ -93,15 +95,22 @@ def roofline_block(precision, peaks, fd_ms, fd_n, fd_fl, wg_ms, wg_n, wg_fl, pro
     dom = max(classes, key=lambda k: classes[k][0])
     ms, n, fl = classes[dom]
     achieved = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            traffic = json.load(f).get(precision, {}).get(dom.split(" ")[0])
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    for fn in ("r02_traffic.json", "r01_traffic.json"):   # committed ncu --set full capture: ONE launch of that class
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                traffic = json.load(f).get(precision, {}).get(dom.split(" ")[0])
+            if traffic is not None:
+                traffic_src = "profiles/" + fn
+                break
+        except Exception:
+            pass
     return {
         "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tflops"], "traffic": traffic,
+        "traffic_source": (traffic_src + ": dram__bytes_read.sum + dram__bytes_write.sum of a single level-1 launch of this "
+                           "kernel in a committed ncu --set full capture (not measured in this run, not a class average)")
+        if traffic_src else None,
         "launches_per_step": n / max(prof_steps, 1), "avg_launch_ms": ms / max(n, 1),
         "share_of_step": ms / max(prof_steps, 1) / ms_per_step,
         "peak_source": peaks["source"] + " cuBLAS bf16 sustained (MEASURED_PEAKS.json)",
@@ -206,79 +215,167 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------
 # CPU reference leg (oracle port of the reference's TF1 graph; TensorFlow itself cannot run here)
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_step_seconds(sample_patch: int, repeats: int, warmup: int):
+def _oracle_setup():
     import torch
     from oracle import ref_vnet as R
-    from vnet_tensorflow_b200.synthetic import synth_batch
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    return R, cores
+
+
+def cpu_reference_steps(sample_patch: int, batch: int, steps: int, warmup: int, budget_s: float = 240.0):
+    """`warmup` untimed + `steps` timed optimiser steps of the oracle (oracle/ref_vnet.py: the TF1-semantics CPU
+    restatement of networks.py / model.py on PyTorch/oneDNN, all host threads) on `batch` synthetic patches of
+    `sample_patch`^3 each.  When the first warm-up step shows that warmup + steps would overrun `budget_s`, the sample
+    shrinks to 64^3 patches (returned with its voxel ratio, which the caller scales by).  Returns
+    (seconds per timed step, patch extent used, cores)."""
+    R, cores = _oracle_setup()
+    from vnet_tensorflow_b200.synthetic import synth_batch
     spec = R.VNetSpec(num_classes=2, in_channels=1)
     state = R.TrainState(params=R.init_params(spec, 42))
+    # thread pool / allocator spin-up on a 32^3 patch (not one of the W warm-up steps)
+    R.train_step(state, *synth_batch(0, 1, min(32, sample_patch), 1, 2), spec, "weighted_sorensen", (0.1, 1.0))
+    used = sample_patch
     times = []
-    for i in range(warmup + repeats):
-        # warm-up steps run on a 32^3 patch: they spin up the thread pool / allocator without costing a full step
-        img, lab = synth_batch(i, 1, sample_patch if i >= warmup else min(32, sample_patch), 1, 2)
+    i = 0
+    while i < warmup + steps:
+        img, lab = synth_batch(i, batch, used, 1, 2)
         t0 = time.perf_counter()
         R.train_step(state, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
         dt = time.perf_counter() - t0
+        if i == 0 and used > 64 and dt * (warmup + steps) > budget_s:
+            used = 64          # too slow for the requested K + W on these cores: bounded sample of 64^3 patches
+            continue
         if i >= warmup:
             times.append(dt)
-    return times, cores
+        i += 1
+    return times, used, cores
 
 
-CPU_SAMPLE_MAX_PATCH = 128   # one 128^3 patch: ~5-15 s per optimiser step and ~7.5 GB of host memory on 8-16 cores
-
-
-def _cpu_sample(patch: int):
-    """The bounded CPU sample is the workload's own patch size (one patch instead of the batch); only patches
-    above 128^3 (configs[4]) are sampled at 128^3 and scaled by the voxel ratio."""
-    sample = min(patch, CPU_SAMPLE_MAX_PATCH)
-    return sample, (sample / patch) ** 3
-
-
-def _sample_text(steps: int, sample: int, patch: int, cores: int, seconds: float) -> str:
-    txt = ("%d optimiser step%s on one %d^3 patch each (fwd+Dice+bwd+Adam, TF1-semantics CPU restatement on "
-           "PyTorch/oneDNN, %d threads), %.2f s per step" % (steps, "" if steps == 1 else "s", sample, cores, seconds))
+def _sample_text(steps: int, warmup: int, sample: int, patch: int, batch: int, cores: int, seconds: float) -> str:
+    txt = ("%d timed + %d warm-up optimiser steps, each on %d synthetic %d^3 patch%s (fwd + weighted Dice + bwd + Adam; "
+           "oracle/ref_vnet.py = TF1-semantics CPU restatement on PyTorch/oneDNN, not TensorFlow; %d threads), "
+           "%.2f s per step" % (steps, warmup, batch, sample, "" if batch == 1 else "es", cores, seconds))
     if sample != patch:
-        txt += ", scaled by (%d/%d)^3 voxels to %d^3" % (sample, patch, patch)
+        txt += "; patches/sec scaled by (%d/%d)^3 voxels to %d^3 patches" % (sample, patch, patch)
     return txt
 
 
-def cpu_baseline(patch: int):
-    """Bounded sample of the same workload: two optimiser steps of the same network on one `patch`^3 patch each
-    (not the whole batch), all host cores, after a 32^3 warm-up step; 10-30 s of CPU work at 128^3."""
-    sample, scale = _cpu_sample(patch)
-    times, cores = cpu_reference_step_seconds(sample, 2, 1)
-    t = float(np.mean(times))
-    return {"value": scale / t, "unit": "patches/sec", "cores": cores, "kind": "port",
-            "sample": _sample_text(len(times), sample, patch, cores, t)}
+def workload_config(args, world: int, dropout: float):
+    """The `config` object of the JSON line -- identical for both arms (the reference arm describes how it sampled
+    this workload in cpu_baseline.sample)."""
+    pre = args.preset
+    P, B, M, K, att = args.patch, args.batch, pre["M"], pre["K"], pre["attention"]
+    return {"workload": "V-Net 3D train step (fwd + weighted Dice%s + bwd + Adam%s), %d^3 patch, %d modalit%s, %d classes, "
+                        "batch %d per GPU (%s)" % (" + attention gating / attention loss" if att else "",
+                                                   " + hand-rolled all-reduce" if world > 1 else "", P, M,
+                                                   "y" if M == 1 else "ies", K, B, pre["name"]),
+            "patch": P, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+            "batch_norm": "synchronised" if (args.sync_bn and world > 1) else "local statistics",
+            "precision": args.precision, "dropout": dropout, "attention": bool(att),
+            "l2": "per-step working set (activations %.1f GB) >> 126 MB L2, no explicit flush" % (0.7 * 3 * B * (P / 128) ** 3)}
 
 
 def run_reference(args, rank: int, world: int):
+    """Reference arm: the reference's CPU path for this workload = the oracle port (TensorFlow 1.15 cannot be installed
+    here), on all host threads.  Runs exactly W warm-up + K timed steps; each step is a bounded sample of
+    the workload: ONE patch of the batch (same FLOPs per patch; its batch norm sees one patch instead of two)."""
     if rank != 0:
         return
-    sample, scale = _cpu_sample(args.patch)
-    steps = max(1, min(args.steps, 3))        # bounded: one CPU optimiser step on a 128^3 patch takes 5-15 s
-    warm = 1
-    times, cores = cpu_reference_step_seconds(sample, steps, warm)
+    times, used, cores = cpu_reference_steps(min(args.patch, 128), 1, args.steps, args.warmup)
     t = float(np.mean(times))
+    scale = (used / args.patch) ** 3
     value = scale / t
+    sample = _sample_text(len(times), args.warmup, used, args.patch, 1, cores, t)
     line = {
-        "impl": "reference", "metric": "patches/sec (128^3, 1ch->2cls) training step", "value": value,
+        "impl": "reference", "metric": METRIC, "value": value,
         "unit": "patches/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * args.batch * t / scale, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "V-Net 3D train step (fwd + weighted Dice + bwd + Adam), %d^3 patch, 1 modality, 2 classes, "
-                               "batch %d (%s); each timed step is one patch of that batch on the host cores"
-                               % (args.patch, args.batch, args.preset["name"]),
-                   "patch": args.patch, "batch_per_gpu": args.batch, "timed_steps": steps, "timed_warmup": warm},
-        "cpu_baseline": {"value": value, "unit": "patches/sec", "cores": cores, "kind": "port",
-                         "sample": _sample_text(steps, sample, args.patch, cores, t)},
+        "config": workload_config(args, max(args.gpus, 1), DROPOUT),
+        "cpu_baseline": {"value": value, "unit": "patches/sec", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "patches/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# Parity of the CUDA engine against the oracle on the benchmarked configuration (BASELINE.md 3: "parity printed
+# next to the timings").  The oracle is the checker here, never the thing measured.
+# --------------------------------------------------------------------------------------------------
+def parity_and_cpu_baseline(eng, patch: int, batch: int, precision: str, timed_steps: int = 2):
+    """Runs the oracle's optimiser step on the workload's own batch (`batch` x `patch`^3, seed-42 weights) -- timed,
+    which is the cpu_baseline -- and the engine's forward / loss / backward on the identical tensors.
+    Returns (parity dict, cpu_baseline dict)."""
+    R, cores = _oracle_setup()
+    from vnet_tensorflow_b200.synthetic import synth_batch
+    spec = R.VNetSpec(num_classes=2, in_channels=1)
+    weights = (0.1, 1.0)
+    params = R.init_params(spec, 42)
+    state = R.TrainState(params={k: v.copy() for k, v in params.items()})
+    R.train_step(state, *synth_batch(0, 1, min(32, patch), 1, 2), spec, "weighted_sorensen", weights)   # spin-up
+    state = R.TrainState(params={k: v.copy() for k, v in params.items()})
+    img, lab = synth_batch(0, batch, patch, 1, 2)
+    times = []
+    t0 = time.perf_counter()
+    loss_o, logits_o, grads_o = R.train_step(state, img, lab, spec, "weighted_sorensen", weights)
+    times.append(time.perf_counter() - t0)
+    for i in range(1, timed_steps):
+        im2, lb2 = synth_batch(i, batch, patch, 1, 2)
+        t0 = time.perf_counter()
+        R.train_step(state, im2, lb2, spec, "weighted_sorensen", weights)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    cpu = {"value": batch / t, "unit": "patches/sec", "cores": cores, "kind": "port",
+           "sample": _sample_text(len(times), 0, patch, patch, batch, cores, t) + " (after a 32^3 spin-up step)"}
+    parity = engine_parity(eng, params, img, lab, loss_o, logits_o, grads_o, precision)
+    return parity, cpu
+
+
+def engine_parity(eng, params, img, lab, loss_o, logits_o, grads_o, precision):
+    """Engine (through the C ABI) vs oracle outputs on identical inputs: north_star's bars are logits within 1e-3
+    relative, bit-exact argmax label volume and hard Dice."""
+    eng.set_params(params)
+    logits, _, argmax = eng.forward(img, want_softmax=False)
+    loss = eng.forward_backward(img, lab, dropout_rate=0.0)
+    ref = np.asarray(logits_o, np.float32)
+    scale = float(np.abs(ref).max())
+    err = float(np.abs(logits - ref).max() / scale)
+    ref_arg = np.argmax(ref, -1)          # first maximum, as tf.argmax (model.py:568)
+    mism = int((argmax != ref_arg).sum())
+    K = ref.shape[-1]
+    hard = {}
+    dice_equal = True
+    for c in range(1, K):
+        a = [int(((x == c) & (lab == c)).sum()) for x in (argmax, ref_arg)]          # TP
+        b = [int(((x == c) & (lab != c)).sum()) for x in (argmax, ref_arg)]          # FP
+        d = [int(((x != c) & (lab == c)).sum()) for x in (argmax, ref_arg)]          # FN
+        hard["class_%d" % c] = {"tp": a[0], "fp": b[0], "fn": d[0], "oracle_tp": a[1], "oracle_fp": b[1], "oracle_fn": d[1]}
+        dice_equal = dice_equal and a[0] == a[1] and b[0] == b[1] and d[0] == d[1]
+    g = eng.get_grads()
+    worst, worst_name = 0.0, ""
+    top = max(float(np.sqrt((np.asarray(r, np.float64) ** 2).sum())) for r in grads_o.values())
+    for k, v in g.items():
+        r = np.asarray(grads_o[k], np.float64)
+        den = float(np.sqrt((r ** 2).sum()))
+        if k.endswith("/biases") or den < 1e-5 * top:
+            continue   # analytically zero gradients (conv biases and the dead / re-normalised batch norms, SURVEY R9, DESIGN 2):
+                       # autodiff leaves rounding noise there, the engine writes exact zeros
+        e = float(np.sqrt(((v.astype(np.float64) - r) ** 2).sum()) / den)
+        if e > worst:
+            worst, worst_name = e, k
+    w1 = "vnet/encoder/level_1/conv_1/weights"
+    r1 = np.asarray(grads_o[w1], np.float64)
+    e1 = float(np.sqrt(((g[w1].astype(np.float64) - r1) ** 2).sum()) / max(float(np.sqrt((r1 ** 2).sum())), 1e-30))
+    return {"against": "oracle/ref_vnet.py (fp32, CPU) on identical synthetic tensors and seed-42 weights, dropout 0",
+            "shape": list(img.shape), "precision": precision,
+            "logits_max_rel_err": err, "logits_tol": 1e-3, "argmax_mismatches": mism, "voxels": int(ref_arg.size),
+            "hard_dice_counts_equal": bool(dice_equal), "hard_dice": hard,
+            "loss": float(loss), "oracle_loss": float(loss_o), "abs_loss_diff": abs(float(loss) - float(loss_o)),
+            "grad_rel_l2_worst": worst, "grad_rel_l2_worst_tensor": worst_name, "grad_rel_l2_first_conv": e1,
+            "pass": bool(err <= 1e-3 and mism == 0 and dice_equal)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -289,7 +386,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     from vnet_tensorflow_b200.engine import VNetEngine
     from vnet_tensorflow_b200.synthetic import synth_patch
 
-    torch.cuda.set_device(local_rank)
+    # VNB_BENCH_DRYRUN=1 (tests/test_host_mirror.py): the flow of this script against the CPU emulation of the kernels
+    # (VNB_LIBRARY points at tests/emul's build) -- test infrastructure; without it a missing GPU is an error here
+    dry = os.environ.get("VNB_BENCH_DRYRUN") == "1"
+    if not dry:
+        torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     P, B = args.patch, args.batch
@@ -310,7 +411,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     def barrier():
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+        if not dry:
+            torch.cuda.synchronize()
         eng.sync()
 
     # synthetic batches in pinned host memory (one per step so the e2e leg really moves new data)
@@ -318,9 +420,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     pinned = []
     for i in range(nb):
         samples = [synth_patch(1234 + 1000 * rank + i + 100000 * b, P, M, K) for b in range(B)]
-        tens = [torch.from_numpy(np.stack([smp[j] for smp in samples], 0)).pin_memory() for j in range(3)]
+        tens = [torch.from_numpy(np.stack([smp[j] for smp in samples], 0)) for j in range(3)]
+        if not dry:
+            tens = [x.pin_memory() for x in tens]
         pinned.append((tens, None, tens[0].numpy(), tens[1].numpy(), tens[2].numpy()))
-    dropout = 0.01  # configs/*.json Networks.Dropout
+    dropout = DROPOUT
 
     # ---- leg 1: device-resident inputs ("value") ------------------------------------------------
     eng.upload_batch(pinned[0][2], pinned[0][3])
@@ -338,6 +442,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     eng.event_record(1)
     barrier()
     ms_dev = eng.event_elapsed_ms()
+    if dry:
+        ms_dev = max(ms_dev, 1e-3)   # the emulation has no device clock
     clocks = sampler.stop()
     launches = eng.gpu_launches() - l0
 
@@ -392,11 +498,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         write_per_layer_table(args.per_layer, eng.profile_launches(), prof_steps, measured_peaks(), args.precision)
     eng.profile_enable(False)
 
-    t = torch.tensor([ms_dev, ms_e2e, ms_staged or 0.0], dtype=torch.float64, device="cuda")
-    if world > 1:
+    if world > 1:   # max over ranks of the device-timed regions
+        t = torch.tensor([ms_dev, ms_e2e, ms_staged or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
-    ms_staged = float(t[2]) if ms_staged is not None else None
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+        ms_staged = float(t[2]) if ms_staged is not None else None
     if rank == 0:
         peaks = measured_peaks()
         patches = B * world * args.steps
@@ -406,20 +512,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         lab_bytes = B * P ** 3 * 4 * (2 if att else 1)   # labels (+ distance map)
         step_tflops = value * train_gflop_per_patch(P, pre) / 1e3 / world
         line = {
-            "metric": "patches/sec (128^3, 1ch->2cls) training step", "value": value, "unit": "patches/sec",
+            "metric": METRIC, "value": value, "unit": "patches/sec",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (fp32-grade split, fp32 accumulate)", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "V-Net 3D train step (fwd + weighted Dice%s + bwd + Adam%s), %d^3 patch, %d modalit%s, %d classes, "
-                                   "batch %d per GPU (%s)" % (" + attention gating / attention loss" if att else "",
-                                                              " + ring all-reduce" if world > 1 else "", P, M,
-                                                              "y" if M == 1 else "ies", K, B, pre["name"]),
-                       "patch": P, "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
-                       "batch_norm": "synchronised" if (args.sync_bn and world > 1) else "local statistics",
-                       "precision": args.precision, "dropout": dropout,
-                       "attention": bool(att),
-                       "l2": "per-step working set (activations %.1f GB) >> 126 MB L2, no explicit flush" % (0.7 * 3 * B * (P / 128) ** 3)},
+            "config": workload_config(args, world, dropout),
             "e2e": {"value": e2e_val, "unit": "patches/sec", "h2d_bytes_per_step": img_bytes + lab_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -433,7 +531,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                   "how": "vnb_stage_batch of batch i+1 on a copy stream while vnb_train_step_staged of batch i runs; "
                                          "same pinned host buffers and per-step loss read-back as e2e"}
         if world == 1 and not args.no_cpu_baseline and args.config == 2:
-            line["cpu_baseline"] = cpu_baseline(P)
+            # oracle on the workload's own batch, timed (cpu_baseline), and the engine held against it (parity)
+            line["parity"], line["cpu_baseline"] = parity_and_cpu_baseline(eng, P, B, args.precision)
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

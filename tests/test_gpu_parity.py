@@ -53,15 +53,11 @@ def test_golden_fixtures(gpu_lib, name, precision):
     eng.set_params(perturbed_params(spec))
     logits, _, argmax = eng.forward(img)
     assert rel_err(logits, gold["logits"]) < LOGIT_TOL[precision]
-    margin = np.sort(gold["logits"], -1)
-    margin = margin[..., -1] - margin[..., -2]
     flips = (argmax != gold["argmax"])
     if precision == "bf16":
         assert flips.mean() < 0.02
-    else:  # bit-exact label volume wherever the class margin exceeds the numerical error bound
-        safe = margin > 2 * LOGIT_TOL[precision] * np.abs(gold["logits"]).max()
-        assert int((flips & safe).sum()) == 0
-        assert int(flips.sum()) <= 2
+    else:  # bit-exact label volume (north_star)
+        assert int(flips.sum()) == 0
     l, terms = eng.loss(img, lab, want_terms=True)
     assert abs(l - float(gold["loss"])) < (5e-3 if precision == "bf16" else 5e-5)
     if precision != "bf16":
@@ -102,15 +98,11 @@ def test_config1_64cube_forward_dice_matches_oracle(gpu_lib, precision):
     err = rel_err(logits, ref)
     assert err < LOGIT_TOL[precision], err
     ref_arg = R.predict(lo).numpy()
-    margin = np.abs(ref[..., 1] - ref[..., 0])
     flips = argmax != ref_arg
-    assert int((flips & (margin > 2 * LOGIT_TOL[precision] * np.abs(ref).max())).sum()) == 0
-    assert flips.mean() < 1e-4
-    # hard Dice from the label volumes (integer TP/FP/FN) is exact when the labels are
-    if not flips.any():
-        tp = int(((argmax == 1) & (lab == 1)).sum())
-        tp_o = int(((ref_arg == 1) & (lab == 1)).sum())
-        assert tp == tp_o
+    assert int(flips.sum()) == 0          # bit-exact label volume, hence identical hard-Dice TP / FP / FN counts
+    for mine, theirs in ((argmax, ref_arg),):
+        assert int(((mine == 1) & (lab == 1)).sum()) == int(((theirs == 1) & (lab == 1)).sum())
+        assert int(((mine == 1) & (lab != 1)).sum()) == int(((theirs == 1) & (lab != 1)).sum())
     assert abs(eng.loss(img, lab) - float(loss_o)) < 5e-5
     eng.close()
 
@@ -170,7 +162,7 @@ def test_legacy_vnet_py_flavour(gpu_lib, precision):
     logits, _, am = eng.forward(img)
     assert abs(l - float(lo)) < 5e-5
     assert rel_err(logits, lg.numpy()) < LOGIT_TOL[precision]
-    assert (am != R.predict(lg).numpy()).mean() < 1e-4
+    assert int((am != R.predict(lg).numpy()).sum()) == 0
     _check_grads(eng, {k: v.numpy() for k, v in go.items()}, spec, max(GRAD_TOL[precision], 3e-2), l2=True)
     eng.close()
 
@@ -316,8 +308,8 @@ def test_attention_gating_path(gpu_lib, flavour, K, M, loss, att_loss, precision
     tol = LOGIT_TOL[precision]
     assert rel_err(logits, out["logits_output"].numpy()) < tol
     assert rel_err(eng.softmax_attention(N), out["softmax_attention"].numpy()) < tol
-    flips = (am != R.predict(out["logits_output"]).numpy()).mean()
-    assert flips < (0.02 if precision == "bf16" else 1e-4)
+    flips = (am != R.predict(out["logits_output"]).numpy())
+    assert flips.mean() < 0.02 if precision == "bf16" else int(flips.sum()) == 0
     eng.set_distmap(dm)
     l = eng.forward_backward(img, lab, update_moving_stats=True)
     t3 = eng.losses()
@@ -443,7 +435,7 @@ def test_short_batch_after_a_full_one(gpu_lib, precision):
     _check_grads(eng, {k: v.numpy() for k, v in go.items()}, spec, GRAD_TOL[precision], l2=True)
     logits, _, argmax = eng.forward(img)
     assert logits.shape[0] == 1 and rel_err(logits, lg.numpy()) < LOGIT_TOL[precision]
-    assert int((argmax != R.predict(lg).numpy()).sum()) <= 2
+    assert int((argmax != R.predict(lg).numpy()).sum()) == 0
     eng.close()
 
 
@@ -518,7 +510,7 @@ def test_step_metrics_match_the_reference_metric_block(gpu_lib, precision):
         assert same or (k.startswith("auc_") and abs(got[k] - ref[k]) < 1e-6), (k, got[k], ref[k])
     # and against the oracle's own forward pass: same hard counts wherever the argmax agrees (it does, bit-exactly)
     lg_o = R.forward(R.to_torch(perturbed_params(spec)), torch.from_numpy(img), spec)[0]
-    assert int((argmax != R.predict(lg_o).numpy()).sum()) <= 2
+    assert int((argmax != R.predict(lg_o).numpy()).sum()) == 0
     eng.close()
 
 
@@ -562,3 +554,88 @@ def test_staged_input_steps_equal_direct_steps(gpu_lib):
     assert eng.global_step == direct.global_step == len(batches)
     eng.close()
     direct.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Parity at the BASELINE sizes: the oracle runs a 128^3 x 2 optimiser step in seconds on the GPU
+# box's host cores, so the benchmarked configuration itself is compared, not a scaled-down stand-in.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_benchmarked_config2_128cube_batch2_matches_oracle(gpu_lib, precision):
+    """BASELINE configs[1] (the benchmarked workload): 128^3, 1 modality, 2 classes, batch 2, seed-42 weights.
+    north_star bars: logits within 1e-3 relative, argmax label volume and hard-Dice counts bit-exact, plus |dloss| and
+    the step-1 gradients per tensor in relative L2 (the same function bench.py prints as its `parity` block)."""
+    import bench
+    spec = R.VNetSpec(num_classes=2, in_channels=1)
+    params = R.init_params(spec, 42)
+    img, lab = synth_batch(0, 2, 128, 1, 2)
+    lo, lg, go, _ = R.loss_and_grads(params, img, lab, spec, "weighted_sorensen", (0.1, 1.0))
+    eng = engine_for(spec, 128, 2, "weighted_sorensen", (0.1, 1.0), gpu_lib, precision=precision)
+    rep = bench.engine_parity(eng, params, img, lab, float(lo), lg.numpy(), {k: v.numpy() for k, v in go.items()}, precision)
+    print("parity[%s]:" % precision, {k: v for k, v in rep.items() if k not in ("hard_dice", "against")})
+    assert rep["logits_max_rel_err"] <= (2e-4 if precision == "fp32" else 1e-3)
+    assert rep["argmax_mismatches"] == 0
+    assert rep["hard_dice_counts_equal"]
+    assert rep["abs_loss_diff"] < 5e-5
+    assert rep["grad_rel_l2_worst"] < (5e-3 if precision == "fp32" else 3e-2), rep["grad_rel_l2_worst_tensor"]
+    eng.close()
+
+
+def test_config3_128cube_four_modalities_four_classes_matches_oracle(gpu_lib):
+    """BASELINE configs[2]: 128^3, 4 modalities, 4 classes (BraTS-shaped), batch 2.  The configuration is quoted in
+    bf16; the parity anchor at this size is the fp32-grade bf16x3 mode (bit-exact argmax), and the single-pass bf16
+    numbers are measured and recorded, with the bound the mode is documented to meet."""
+    spec = R.VNetSpec(num_classes=4, in_channels=4)
+    weights = (0.01, 0.1, 0.5, 1.0)
+    params = R.init_params(spec, 42)
+    img, lab = synth_batch(0, 2, 128, 4, 4)
+    p = R.to_torch(params)
+    with torch.no_grad():
+        lg, _ = R.forward(p, torch.from_numpy(img), spec)
+        loss_o = float(R.loss_from_logits(lg, torch.from_numpy(lab), "weighted_sorensen", weights))
+    ref = lg.numpy()
+    ref_arg = R.predict(lg).numpy()
+    for precision in ("bf16x3", "bf16"):
+        eng = engine_for(spec, 128, 2, "weighted_sorensen", weights, gpu_lib, precision=precision)
+        eng.set_params(params)
+        logits, _, argmax = eng.forward(img, want_softmax=False)
+        err = rel_err(logits, ref)
+        flips = int((argmax != ref_arg).sum())
+        dl = abs(eng.loss(img, lab) - loss_o)
+        print("config3 128^3 [%s]: logits rel err %.3e, argmax flips %d of %d, |dloss| %.3e" % (precision, err, flips, ref_arg.size, dl))
+        if precision == "bf16x3":
+            assert err <= 1e-3 and flips == 0 and dl < 5e-5
+        else:
+            assert err <= LOGIT_TOL["bf16"] and flips <= 0.02 * ref_arg.size and dl < 5e-3
+        eng.close()
+
+
+def test_config5_192cube_attention_forward_matches_oracle(gpu_lib):
+    """BASELINE configs[4]: one 192^3, 2-modality, 3-class patch through V-Net -> AttentionModule -> gating -> OutputModule
+    (forward only at this size: the oracle's 64-channel 3^3 modules at 192^3 take ~a minute on the host cores)."""
+    from tests.helpers import perturbed_attention_params
+    from vnet_tensorflow_b200.synthetic import synth_patch
+    spec = R.VNetSpec(num_classes=3, in_channels=2)
+    nch = 64
+    params = perturbed_attention_params(spec, nch, weight_scale=0.25)
+    im, lb, dm = synth_patch(1234, 192, 2, 3)
+    img = im[None]
+    with torch.no_grad():
+        out = R.attention_forward(R.to_torch(params), torch.from_numpy(img), spec)
+    out = out[0] if isinstance(out, tuple) else out
+    ref = out["logits_output"].numpy()
+    ref_arg = R.predict(out["logits_output"]).numpy()
+    for precision in ("bf16x3", "bf16"):
+        eng = engine_for(spec, 192, 1, "weighted_sorensen", (0.01, 0.1, 1.0), gpu_lib, precision=precision, attention=True,
+                         attention_loss="l2")
+        eng.set_params(params)
+        logits, _, argmax = eng.forward(img, want_softmax=False)
+        err = rel_err(logits, ref)
+        flips = int((argmax != ref_arg).sum())
+        print("config5 192^3 attention [%s]: logits rel err %.3e, argmax flips %d of %d" % (precision, err, flips, ref_arg.size))
+        if precision == "bf16x3":
+            assert err <= 1e-3 and flips == 0
+            assert rel_err(eng.softmax_attention(1), out["softmax_attention"].numpy()) <= 1e-3
+        else:
+            assert err <= LOGIT_TOL["bf16"] and flips <= 0.02 * ref_arg.size
+        eng.close()
