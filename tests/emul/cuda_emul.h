@@ -276,6 +276,10 @@ template <class T>
 inline T __ldg(const T* p) {
   return *p;
 }
+template <class T>
+inline T __ldcg(const T* p) {
+  return *p;
+}
 inline float __uint_as_float(unsigned u) {
   float f;
   memcpy(&f, &u, 4);

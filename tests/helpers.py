@@ -89,3 +89,26 @@ def perturbed_attention_params(spec, nch, seed=42, weight_scale=1.0):
         elif kind in ("gamma", "moving_variance"):
             p[name] = rng.uniform(0.6, 1.4, shape).astype(np.float32)
     return p
+
+
+def argmax_parity(argmax, logits, ref_logits, ref_argmax=None):
+    """Label-volume parity with the oracle (north_star: bit-exact argmax).  Two fp32 evaluations of the same graph that
+    differ only in summation order (the oracle on oneDNN vs the CUDA engine; the oracle itself in fp32 vs fp64; TensorFlow
+    with another thread count) cannot agree on argmax at a voxel whose two top logits are closer than their own rounding
+    error, so the bar is: every mismatch lies inside the rounding band |top1 - top2| <= 2 * max|logits - ref| of the
+    oracle's logits, and none outside it.  Returns (mismatches, mismatches outside the band, band width)."""
+    ref_logits = np.asarray(ref_logits, np.float64)
+    if ref_argmax is None:
+        ref_argmax = np.argmax(ref_logits, -1)
+    flips = np.asarray(argmax) != np.asarray(ref_argmax)
+    band = 2.0 * float(np.abs(np.asarray(logits, np.float64) - ref_logits).max())
+    top = np.sort(ref_logits, -1)
+    margin = top[..., -1] - top[..., -2]
+    return int(flips.sum()), int((flips & (margin > band)).sum()), band
+
+
+def assert_argmax_parity(argmax, logits, ref_logits, ref_argmax=None, max_frac=1e-4):
+    n, outside, band = argmax_parity(argmax, logits, ref_logits, ref_argmax)
+    assert outside == 0, "%d argmax mismatches outside the rounding band (%.3g)" % (outside, band)
+    assert n <= max(1, int(max_frac * np.asarray(argmax).size)), "%d argmax mismatches" % n
+    return n

@@ -14,6 +14,8 @@ from vnet_tensorflow_b200.synthetic import synth_batch
 SPEC_A = R.VNetSpec(num_classes=2, in_channels=1, num_channels=4, num_levels=2, num_convolutions=(1, 2), bottom_convolutions=2)
 SPEC_B = R.VNetSpec(num_classes=3, in_channels=2, num_channels=4, num_levels=2, num_convolutions=(3, 1), bottom_convolutions=1)
 SPEC_C = R.VNetSpec(num_classes=4, in_channels=1, num_channels=8, num_levels=1, num_convolutions=(4,), bottom_convolutions=1)
+# wide channels on a tiny volume: 64 / 128 channels put a whole warp (and more) of channel quads into the per-channel reductions
+SPEC_W = R.VNetSpec(num_classes=2, in_channels=1, num_channels=64, num_levels=1, num_convolutions=(1,), bottom_convolutions=1)
 
 
 def _grad_check(eng, grads_o, spec, tol):
@@ -36,6 +38,7 @@ def _grad_check(eng, grads_o, spec, tol):
     (SPEC_B, 2, "weighted_xent", (0.2, 0.3, 1.0)),
     (SPEC_A, 2, "mixed_sorensen", ()),
     (SPEC_A, 2, "sorensen", ()),
+    (SPEC_W, 2, "weighted_sorensen", (0.3, 1.0)),
 ])
 def test_forward_loss_backward_match_oracle(emul_lib, spec, N, loss, weights):
     P = 8
@@ -55,7 +58,13 @@ def test_forward_loss_backward_match_oracle(emul_lib, spec, N, loss, weights):
     assert rel_err(terms[..., :3], R.dice_terms(logits_o, torch.from_numpy(lab), kind).numpy()) < 1e-5
     l2 = eng.forward_backward(img, lab, update_moving_stats=True)
     assert abs(l2 - float(loss_o)) < 2e-6
-    _grad_check(eng, grads_o, spec, 2e-4)
+    if spec is SPEC_W:   # batch norm over 128 values per channel at the bottom amplifies fp32 rounding: per-tensor relative L2
+        for k, v in eng.get_grads().items():
+            ref = grads_o[k].numpy().astype(np.float64)
+            if not analytically_zero(k, spec):
+                assert np.sqrt(((v - ref) ** 2).sum()) <= 5e-3 * np.sqrt((ref ** 2).sum()), k
+    else:
+        _grad_check(eng, grads_o, spec, 2e-4)
     for k, u in upd.items():  # UPDATE_OPS (model.py:665-666)
         assert np.abs(eng.get_param(k) - u.numpy()).max() < 1e-4 * max(1.0, float(u.abs().max())), k
     eng.close()

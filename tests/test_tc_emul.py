@@ -27,6 +27,7 @@ def _bf16(x):
     (16, 32, (2, 3, 192), 1, 1),    # W > 128: two haloed 96-wide segments per line
     (32, 16, (2, 4, 160), 1, 2),    # W > 128, CT = 32 forward / 16 backward
     (16, 16, (3, 5, 16), 1, 1),     # odd H: the box (5 lines x 4 planes) leaves MMA rows unused, last d-block partial
+    (32, 16, (2, 6, 64), 2, 1),     # dgrad 16 -> 32 on one N = 160 slice over 16-channel k-chunks (CT = 32, KC = 16), bf16x3
 ])
 def test_conv5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
     rng = np.random.default_rng(7)
@@ -120,6 +121,10 @@ def test_engine_bf16x3_short_batch_after_a_full_one(emul_lib):
     (16, 16, (2, 4, 24), 1, 1),     # W not a multiple of the K step: boxes rounded to 32, TMA zero fill past the line
     (16, 16, (2, 3, 12), 1, 2),     # W = 12 -> one K step of 16
     (16, 16, (1, 3, 192), 1, 2),    # W > 128
+    (32, 32, (2, 4, 128), 1, 1),    # N = 160 (two dZ chunks), bf16x3: lines cut into two 64-voxel K segments, two plane-offset groups
+    (64, 16, (3, 6, 32), 2, 1),     # Cout = 16, Cin = 64: roles swapped (P = dZ, Q = two X chunks per CTA), mirrored taps
+    (16, 64, (6, 5, 16), 1, 2),     # two Q chunk groups, odd H, D > plane-offset group size
+    (32, 32, (2, 8, 8), 1, 1),      # W = 8 with two interleaved chunks: K rows 8..15 come from the next line
 ])
 def test_wgrad5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
     """MN-major overlapping-atom tap folding (kw on M, kh on N, kd on five TMEM accumulators)."""

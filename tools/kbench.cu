@@ -89,8 +89,9 @@ int main(int argc, char** argv) {
     wg_encode_plan(pl, N, xh, xl, x2h, x2l, zh, zl);
     long long* dbg = nullptr;
     if (getenv("VNB_KB_DBG")) { dbg = s.alloc<long long>(8 * 1024); CK(cudaMemset(dbg, 0, 8 * 1024 * sizeof(long long))); pl.g.dbg = dbg; }
-    printf("wgrad plan: HT=%d n_hb=%d z_stages=%d splits=%d pairs=%d grid=%d smem=%zu xt=%d zt=%d\n", pl.g.HT, pl.g.n_hb, pl.g.z_stages,
-           pl.g.splits, pl.g.n_ci * pl.g.n_co, pl.g.splits * pl.g.n_ci * pl.g.n_co, pl.smem, pl.g.xt_bytes, pl.g.zt_bytes);
+    printf("wgrad plan: nch=%d swap=%d q_split=%d Wr=%d n_wb=%d HT=%d n_hb=%d z_stages=%d groups=%d splits=%d+%d pairs=%d grid=%d smem=%zu xt=%d zt=%d\n",
+           pl.g.nch, pl.g.swap, pl.g.q_split, pl.g.Wr, pl.g.n_wb, pl.g.HT, pl.g.n_hb, pl.g.z_stages, pl.g.ngroups, pl.g.splits[0], pl.g.splits[1],
+           pl.g.n_pc * pl.g.n_qg, (pl.g.splits[0] + pl.g.splits[1]) * pl.g.n_pc * pl.g.n_qg, pl.smem, pl.g.xt_bytes, pl.g.zt_bytes);
     for (int i = 0; i < 3; ++i) wg_launch(pl, N, lo, partial, dw, 0);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));

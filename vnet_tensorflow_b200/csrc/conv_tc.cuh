@@ -807,6 +807,12 @@ inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C
   if (mult(C1, 32) && mult(C2, 32) && mult(Co1, 32) && mult(Co2, 32) && Co1 > 0) {
     pl.CT = 32;
     pl.KC = 32;
+  } else if (mult(C1, 16) && mult(C2, 16) && mult(Co1, 16) && mult(Co2, 16) && mult(Co1 + Co2, 32) && Co1 > 0 && C1 > 0 &&
+             ks == 5 && !getenv("VNB_TC_NO_CT32K16")) {
+    // 32 output channels over 16-channel k-chunks (the input gradient of decoder level 1: 16 -> 16 + 16): one N = 160
+    // slice instead of two N = 80 slices that would each re-read the activation tile
+    pl.CT = 32;
+    pl.KC = 16;
   } else if (mult(C1, 16) && mult(C2, 16) && mult(Co1, 16) && mult(Co2, 16) && Co1 > 0 && C1 > 0) {
     pl.CT = 16;
     pl.KC = 16;
@@ -925,6 +931,9 @@ inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int 
   if (pl.CT == 16) {
     if (split3) tc_launch_inst<16, 3, 16, 3>(pl, a, sms, stream);
     else tc_launch_inst<16, 3, 16, 1>(pl, a, sms, stream);
+  } else if (pl.KC == 16) {
+    if (split3) tc_launch_inst<32, 2, 16, 3>(pl, a, sms, stream);
+    else tc_launch_inst<32, 2, 16, 1>(pl, a, sms, stream);
   } else {
     if (split3) tc_launch_inst<32, 2, 32, 3>(pl, a, sms, stream);
     else tc_launch_inst<32, 2, 32, 1>(pl, a, sms, stream);

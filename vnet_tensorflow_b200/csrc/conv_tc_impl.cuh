@@ -77,16 +77,32 @@ inline void Engine::tc_setup() {
   if (wg_partial_floats) wg_partial_ = dev_alloc<float>(wg_partial_floats);
 }
 
+// Weight packing (fp32 master -> bf16 hi/lo GEMM-B tiles) after every optimiser step.  The packs of the first forward
+// units (a few percent of the bytes) run on the compute stream; everything else -- the deep layers' forward packs and all
+// input-gradient packs, ~95 % of the 0.7 GB this pass moves -- runs on the filter-gradient side stream (idle during the
+// forward pass) under the tensor-bound first convolutions, and the compute stream waits for it right before the first
+// unit that needs it (Engine::tc_wait_late_packs).
 inline void Engine::tc_prepare_weights() {
   if (!weights_dirty_) return;
-  if (!pack_jobs_dev_) {  // one table for every (layer, fprop|dgrad) pack, built once
-    std::vector<PackJob> jobs;
-    int blocks = 0;
-    for (Unit& u : units_) {
+  if (!pack_built_) {  // job tables, built once
+    std::vector<PackJob> early, late;
+    int eb = 0, lb = 0;
+    size_t seen = 0, total = 0;
+    for (const Unit& u : units_)
+      if (u.kind == U_CONV5 || u.kind == U_CONV3) total += u.w_count;
+    pack_first_late_unit_ = static_cast<int>(units_.size());
+    for (size_t ui = 0; ui < units_.size(); ++ui) {
+      Unit& u = units_[ui];
       if (u.kind != U_CONV5 && u.kind != U_CONV3) continue;
+      const bool is_early = wg_stream_ && (seen + u.w_count) * 20 <= total;   // first <= 5 % of the filter elements
+      seen += u.w_count;
+      if (!is_early && pack_first_late_unit_ == static_cast<int>(units_.size())) pack_first_late_unit_ = static_cast<int>(ui);
       for (int pass = 0; pass < 2; ++pass) {
         TcKernelPlan& pl = pass == 0 ? u.tc.fprop : u.tc.dgrad;
         if (!pl.valid) continue;
+        const bool e = is_early && pass == 0 && pack_first_late_unit_ == static_cast<int>(units_.size());
+        std::vector<PackJob>& jobs = e ? early : late;
+        int& blocks = e ? eb : lb;
         PackJob j;
         j.w = params_ + u.w_off;
         j.hi = pl.wp_hi;
@@ -103,18 +119,53 @@ inline void Engine::tc_prepare_weights() {
         jobs.push_back(j);
       }
     }
-    pack_blocks_ = blocks;
-    pack_njobs_ = static_cast<int>(jobs.size());
-    if (pack_njobs_) {
-      pack_jobs_dev_ = dev_alloc<PackJob>(jobs.size());
-      VNB_CUDA_OK(cudaMemcpy(pack_jobs_dev_, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+    pack_blocks_[0] = eb;
+    pack_blocks_[1] = lb;
+    pack_njobs_[0] = static_cast<int>(early.size());
+    pack_njobs_[1] = static_cast<int>(late.size());
+    for (int k = 0; k < 2; ++k) {
+      const std::vector<PackJob>& jobs = k == 0 ? early : late;
+      if (jobs.empty()) continue;
+      pack_jobs_dev_[k] = dev_alloc<PackJob>(jobs.size());
+      VNB_CUDA_OK(cudaMemcpy(pack_jobs_dev_[k], jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
     }
+    pack_built_ = true;
   }
-  if (pack_njobs_) {
-    VNB_LAUNCH(pack_w5_multi_kernel, pack_blocks_, 256, 0, stream_, (const PackJob*)pack_jobs_dev_, pack_njobs_);
+  if (pack_njobs_[0]) {
+    VNB_LAUNCH(pack_w5_multi_kernel, pack_blocks_[0], 256, 0, stream_, (const PackJob*)pack_jobs_dev_[0], pack_njobs_[0]);
     ++launches_;
   }
+  if (pack_njobs_[1]) {
+    cudaStream_t st = stream_;
+#ifndef VNB_EMULATE
+    if (wg_stream_ && pack_njobs_[0]) {   // after the optimiser step (compute stream), beside the first forward units
+      VNB_CUDA_OK(cudaEventRecord(wg_ready_ev_, stream_));
+      VNB_CUDA_OK(cudaStreamWaitEvent(wg_stream_, wg_ready_ev_, 0));
+      st = wg_stream_;
+    }
+#endif
+    VNB_LAUNCH(pack_w5_multi_kernel, pack_blocks_[1], 256, 0, st, (const PackJob*)pack_jobs_dev_[1], pack_njobs_[1]);
+    ++launches_;
+#ifndef VNB_EMULATE
+    if (st != stream_) {
+      VNB_CUDA_OK(cudaEventRecord(pack_done_ev_, st));
+      late_packs_pending_ = true;
+    }
+#endif
+  }
   weights_dirty_ = false;
+}
+
+// called by forward() before unit `ui` (and by the backward pass): the compute stream joins the side-stream pack
+inline void Engine::tc_wait_late_packs(int ui) {
+#ifndef VNB_EMULATE
+  if (late_packs_pending_ && ui >= pack_first_late_unit_) {
+    VNB_CUDA_OK(cudaStreamWaitEvent(stream_, pack_done_ev_, 0));
+    late_packs_pending_ = false;
+  }
+#else
+  (void)ui;
+#endif
 }
 
 inline void Engine::tc_run_fprop(Unit& u, int N) {

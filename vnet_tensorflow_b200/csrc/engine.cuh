@@ -149,6 +149,7 @@ class Engine {
       VNB_CUDA_OK(cudaStreamCreateWithPriority(&wg_stream_, cudaStreamNonBlocking, least));
       VNB_CUDA_OK(cudaEventCreateWithFlags(&wg_ready_ev_, cudaEventDisableTiming));
       VNB_CUDA_OK(cudaEventCreateWithFlags(&wg_done_ev_, cudaEventDisableTiming));
+      VNB_CUDA_OK(cudaEventCreateWithFlags(&pack_done_ev_, cudaEventDisableTiming));
     }
     // VNB_COMM_DUAL_WAIT=1 (experimental, not yet measured): a gradient bucket's all-reduce waits on the main and on
     // the filter-gradient stream itself instead of the main stream joining the latter at every bucket boundary.
@@ -172,6 +173,7 @@ class Engine {
       cudaStreamDestroy(wg_stream_);
       cudaEventDestroy(wg_ready_ev_);
       cudaEventDestroy(wg_done_ev_);
+      cudaEventDestroy(pack_done_ev_);
     }
 #endif
     if (copy_stream_) {
@@ -971,7 +973,11 @@ class Engine {
   static bool v4_ok(int C, long long total) { return C % 4 == 0 && C >= 4 && 256 % (C / 4) == 0 && total < (1LL << 31); }
   static int v4_blocks(long long total4, int C) {  // grid stride must keep (i % C4) fixed per thread: any multiple of 256 threads does
     (void)C;
-    return static_cast<int>(std::max<long long>(1, std::min<long long>((total4 + 256 * 8 - 1) / (256 * 8), kMaxRedBlocks)));
+    // at most four blocks per SM: every block ends with a cross-warp combine and its partial row is re-read by the
+    // finalize kernel, so fewer, longer-running blocks are cheaper than the 8 per SM the grid-stride loop would fill.
+    // (A fused "last block finalizes" form was measured and dropped: the ticket atomics of ~600 blocks on one address
+    // serialise in L2, +15 us per launch against the 8 us of the separate one-block-per-channel finalize kernel.)
+    return static_cast<int>(std::max<long long>(1, std::min<long long>((total4 + 256 * 8 - 1) / (256 * 8), kMaxRedBlocks / 2)));
   }
   static RedGeom red_geom(int C, int c0, long long V) {
     RedGeom g;
@@ -1158,6 +1164,7 @@ class Engine {
     }
     for (size_t ui = 0; ui < units_.size(); ++ui) {
       Unit& u = units_[ui];
+      if (cfg_.precision != PREC_FP32) tc_wait_late_packs(static_cast<int>(ui));
       NvtxRange range(nvtx_, u.scope, " fwd");
       const Act& o = acts_[u.out];
       const long long V = voxels_of(o.dims, N);
@@ -1174,6 +1181,7 @@ class Engine {
       } else if (u.kind == U_INPUT_TILE) {
         nblk = grid_for(V, 256, kMaxRedBlocks);
         VNB_LAUNCH(image_stats_kernel, nblk, 256, 0, stream_, (const float*)u.z, V, partial_);
+        ++launches_;
       } else {
         run_conv_fprop(u, N);
         if (v4_ok(u.Cout, V * u.Cout)) {
@@ -1205,6 +1213,7 @@ class Engine {
       VNB_LAUNCH(bn_finalize_fwd_kernel, u.Cout, 128, 0, stream_, fin_partial, nblk, nq_stride,
                  u.Cout, count, u.chain, bn_params(u), u.kind == U_INPUT_TILE ? 1 : 0,
                  update_moving ? 1 : 0, u.mean, u.var, u.scale, u.shift, u.bn_inference ? 1 : 0);
+      ++launches_;
       ApplyArgs ap;
       ap.z = u.z;
       ap.a = acts_[u.out].a;
@@ -1223,7 +1232,7 @@ class Engine {
         VNB_LAUNCH(bn_apply_v4_kernel, grid_for(ap.total / 4, 256), 256, 0, stream_, ap);
       else
         VNB_LAUNCH(bn_apply_kernel, grid_for(ap.total, 256), 256, 0, stream_, ap);
-      launches_ += 3;
+      ++launches_;
     }
   }
 
@@ -1248,6 +1257,7 @@ class Engine {
 
   // ---- backward -------------------------------------------------------------------------------
   void backward(int N, float dropout, uint64_t seed) {
+    if (cfg_.precision != PREC_FP32) tc_wait_late_packs(static_cast<int>(units_.size()));
     const LossCfg lc = loss_cfg();
     const long long Vn = voxels(1);
     dim3 lgrid(loss_blocks(), N);
@@ -1291,6 +1301,14 @@ class Engine {
       b.unit = static_cast<uint32_t>(ui);
       const bool v4 = v4_ok(u.Cout, V * u.Cout);
       int nblk;
+      BnGradPtrs gp;
+      for (int k = 0; k < 3; ++k) {
+        const bool on = k < chain_num_bn(u.chain);
+        gp.dgamma[k] = on ? grads_ + u.gamma_off[k] : nullptr;
+        gp.dbeta[k] = on ? grads_ + u.beta_off[k] : nullptr;
+      }
+      gp.dalpha = (u.has_act && !u.relu) ? grads_ + u.alpha_off : nullptr;
+      gp.dbias = u.bn_inference ? grads_ + u.b_off : nullptr;
       if (v4) {
         const unsigned total4 = static_cast<unsigned>(V * u.Cout / 4);
         nblk = v4_blocks(total4, u.Cout);
@@ -1305,14 +1323,6 @@ class Engine {
           ++launches_;
         }
       }
-      BnGradPtrs gp;
-      for (int k = 0; k < 3; ++k) {
-        const bool on = k < chain_num_bn(u.chain);
-        gp.dgamma[k] = on ? grads_ + u.gamma_off[k] : nullptr;
-        gp.dbeta[k] = on ? grads_ + u.beta_off[k] : nullptr;
-      }
-      gp.dalpha = (u.has_act && !u.relu) ? grads_ + u.alpha_off : nullptr;
-      gp.dbias = u.bn_inference ? grads_ + u.b_off : nullptr;
       const double* fin_partial = partial_;
       const double* gsum = nullptr;
       if (stats_hook_ && !u.bn_inference) {  // R0, R1 of the global batch for dL/dz; parameter gradients stay local
@@ -1635,20 +1645,23 @@ class Engine {
   // tensor-core path (conv_tc.cuh / conv_tc_impl.cuh)
   void tc_setup();
   void tc_prepare_weights();
+  void tc_wait_late_packs(int ui);
   void tc_run_fprop(Unit& u, int N);
   void tc_run_dgrad(Unit& u, int N);
   void tc_run_wgrad(Unit& u, int N);
   int sm_count_ = 148;
   int image_cpad_ = 0;
-  PackJob* pack_jobs_dev_ = nullptr;
-  int pack_blocks_ = 0, pack_njobs_ = 0;
+  PackJob* pack_jobs_dev_[2] = {nullptr, nullptr};   // [0] early forward packs (compute stream), [1] the rest (side stream)
+  int pack_blocks_[2] = {0, 0}, pack_njobs_[2] = {0, 0};
+  bool pack_built_ = false, late_packs_pending_ = false;
+  int pack_first_late_unit_ = 0;
   float* wg_partial_ = nullptr;
 
   EngineConfig cfg_;
   cudaStream_t stream_ = 0;
   cudaStream_t wg_stream_ = 0;   // filter-gradient side stream (null: everything on stream_)
 #ifndef VNB_EMULATE
-  cudaEvent_t wg_ready_ev_ = nullptr, wg_done_ev_ = nullptr;
+  cudaEvent_t wg_ready_ev_ = nullptr, wg_done_ev_ = nullptr, pack_done_ev_ = nullptr;
 #endif
   bool wg_pending_ = false;
   bool comm_waits_wgrad_ = false;

@@ -165,6 +165,36 @@ struct BnParams {       // device pointers into the flat parameter / state buffe
   float* moving_var[3];
 };
 
+// per-channel forward finalize: (sum z, sum z^2) -> mu, sigma^2 -> chain closed form -> scale / shift (+ UPDATE_OPS)
+__device__ __forceinline__ void bn_fwd_channel(int c, double s, double s2, double count, int chain, const BnParams& bp,
+                                               int update_moving, double* __restrict__ mean_out, double* __restrict__ var_out,
+                                               float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const double mu = s / count;
+  double var = s2 / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  double gam[3] = {1, 1, 1}, bet[3] = {0, 0, 0};
+  const int nbn = chain_num_bn(chain);
+  for (int k = 0; k < nbn; ++k) {
+    gam[k] = bp.gamma[k][c];
+    bet[k] = bp.beta[k][c];
+  }
+  const ChainOut o = chain_eval(chain, var, gam, bet, static_cast<double>(kBnEps));
+  mean_out[c] = mu;
+  var_out[c] = var;
+  const double A = o.A.v, B = bet[o.beta_idx];
+  scale_out[c] = static_cast<float>(A);
+  shift_out[c] = static_cast<float>(B - A * mu);
+  if (update_moving) {
+    for (int k = 0; k < nbn; ++k) {
+      const float bm = static_cast<float>((o.mean_is_mu[k] ? mu : 0.0) + o.bn_mean[k]);
+      const float bv = static_cast<float>(o.bn_var[k]);
+      // assign_moving_average: var -= (var - value) * (1 - momentum)
+      bp.moving_mean[k][c] -= (bp.moving_mean[k][c] - bm) * (1.0f - kBnMomentum);
+      bp.moving_var[k][c] -= (bp.moving_var[k][c] - bv) * (1.0f - kBnMomentum);
+    }
+  }
+}
+
 __global__ void bn_finalize_fwd_kernel(const double* __restrict__ partial, int nblk, int nq_stride, int C,
                                        double count, int chain, BnParams bp, int single_channel_stats,
                                        int update_moving, double* __restrict__ mean_out,
@@ -198,30 +228,7 @@ __global__ void bn_finalize_fwd_kernel(const double* __restrict__ partial, int n
     s += fin_red[0][i];
     s2 += fin_red[1][i];
   }
-  const double mu = s / count;
-  double var = s2 / count - mu * mu;
-  if (var < 0.0) var = 0.0;
-  double gam[3] = {1, 1, 1}, bet[3] = {0, 0, 0};
-  const int nbn = chain_num_bn(chain);
-  for (int k = 0; k < nbn; ++k) {
-    gam[k] = bp.gamma[k][c];
-    bet[k] = bp.beta[k][c];
-  }
-  const ChainOut o = chain_eval(chain, var, gam, bet, static_cast<double>(kBnEps));
-  mean_out[c] = mu;
-  var_out[c] = var;
-  const double A = o.A.v, B = bet[o.beta_idx];
-  scale_out[c] = static_cast<float>(A);
-  shift_out[c] = static_cast<float>(B - A * mu);
-  if (update_moving) {
-    for (int k = 0; k < nbn; ++k) {
-      const float bm = static_cast<float>((o.mean_is_mu[k] ? mu : 0.0) + o.bn_mean[k]);
-      const float bv = static_cast<float>(o.bn_var[k]);
-      // assign_moving_average: var -= (var - value) * (1 - momentum)
-      bp.moving_mean[k][c] -= (bp.moving_mean[k][c] - bm) * (1.0f - kBnMomentum);
-      bp.moving_var[k][c] -= (bp.moving_var[k][c] - bv) * (1.0f - kBnMomentum);
-    }
-  }
+  bn_fwd_channel(c, s, s2, count, chain, bp, update_moving, mean_out, var_out, scale_out, shift_out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -324,30 +331,11 @@ struct BnGradPtrs {  // where the parameter gradients go (flat gradient buffer),
   float* dbias;  // only with inference-mode BN (batch statistics make the conv bias gradient exactly 0)
 };
 
-__global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int nblk, int C, double count,
-                                       int chain, BnParams bp, const double* __restrict__ var,
-                                       BnGradPtrs gp, float* __restrict__ P, float* __restrict__ Q,
-                                       float* __restrict__ S, int inference = 0,
-                                       const double* __restrict__ gsum = nullptr, double gcount = 0.0) {
-  const int c = blockIdx.x;  // one block per channel
-  __shared__ double fin_red[3][128];
-  double p0 = 0, p1 = 0, p2 = 0;
-  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
-    p0 += partial[(static_cast<size_t>(b) * 3 + 0) * C + c];
-    p1 += partial[(static_cast<size_t>(b) * 3 + 1) * C + c];
-    p2 += partial[(static_cast<size_t>(b) * 3 + 2) * C + c];
-  }
-  fin_red[0][threadIdx.x] = p0;
-  fin_red[1][threadIdx.x] = p1;
-  fin_red[2][threadIdx.x] = p2;
-  __syncthreads();
-  if (threadIdx.x != 0) return;
-  double R0 = 0, R1 = 0, Ra = 0;
-  for (unsigned i = 0; i < blockDim.x; ++i) {
-    R0 += fin_red[0][i];
-    R1 += fin_red[1][i];
-    Ra += fin_red[2][i];
-  }
+// per-channel backward finalize: (R0, R1, Ralpha) -> parameter gradients and the dL/dz coefficients P, Q, S
+__device__ __forceinline__ void bn_bwd_channel(int c, double R0, double R1, double Ra, int C, double count, int chain,
+                                               const BnParams& bp, const double* __restrict__ var, const BnGradPtrs& gp,
+                                               float* __restrict__ P, float* __restrict__ Q, float* __restrict__ S, int inference,
+                                               const double* __restrict__ gsum, double gcount) {
   double gam[3] = {1, 1, 1}, bet[3] = {0, 0, 0};
   const int nbn = chain_num_bn(chain);
   for (int k = 0; k < nbn; ++k) {
@@ -376,6 +364,33 @@ __global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int n
     if (gp.dbeta[k]) gp.dbeta[k][c] = (k == o.beta_idx) ? static_cast<float>(R0) : 0.f;
   }
   if (gp.dalpha) gp.dalpha[c] = static_cast<float>(Ra);
+}
+
+__global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int nblk, int C, double count,
+                                       int chain, BnParams bp, const double* __restrict__ var,
+                                       BnGradPtrs gp, float* __restrict__ P, float* __restrict__ Q,
+                                       float* __restrict__ S, int inference = 0,
+                                       const double* __restrict__ gsum = nullptr, double gcount = 0.0) {
+  const int c = blockIdx.x;  // one block per channel
+  __shared__ double fin_red[3][128];
+  double p0 = 0, p1 = 0, p2 = 0;
+  for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+    p0 += partial[(static_cast<size_t>(b) * 3 + 0) * C + c];
+    p1 += partial[(static_cast<size_t>(b) * 3 + 1) * C + c];
+    p2 += partial[(static_cast<size_t>(b) * 3 + 2) * C + c];
+  }
+  fin_red[0][threadIdx.x] = p0;
+  fin_red[1][threadIdx.x] = p1;
+  fin_red[2][threadIdx.x] = p2;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  double R0 = 0, R1 = 0, Ra = 0;
+  for (unsigned i = 0; i < blockDim.x; ++i) {
+    R0 += fin_red[0][i];
+    R1 += fin_red[1][i];
+    Ra += fin_red[2][i];
+  }
+  bn_bwd_channel(c, R0, R1, Ra, C, count, chain, bp, var, gp, P, Q, S, inference, gsum, gcount);
 }
 
 // dL/dz = P*g + Q + S*(z - mu), in place over d; optional residual-branch gradient and bf16 copies
@@ -963,10 +978,41 @@ __global__ void add2_kernel(const float* __restrict__ a, const float* __restrict
 // per-channel reductions, 4 channels per thread. blockDim = 256, C4 = C/4 divides 256.
 // partial layout identical to the scalar kernels: [block][NQ][C] doubles.
 template <int NQ>
-__device__ __forceinline__ void block_channel_combine_v4(const float (&acc)[NQ][4], unsigned C4, int C,
+__device__ __forceinline__ void block_channel_combine_v4(float (&acc)[NQ][4], unsigned C4, int C,
                                                          double* __restrict__ partial) {
-  __shared__ float red[NQ * 4][256];
   const unsigned t = threadIdx.x;
+  if (C4 <= 32u) {
+    // Thread t owns channel quad t % C4 = lane % C4 (C4 is a power of two): a butterfly over the lane offsets >= C4
+    // leaves every lane with the warp's sum of its quad (fixed tree), then the eight warp sums are added in warp order
+    // in double.  (The earlier form -- C4 threads walking 256 / C4 shared-memory entries each for every quantity -- made
+    // the tail of a block as long as its main loop on the 16- and 32-channel tensors.)
+    __shared__ float wred[8][NQ * 4][32];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v = acc[q][k];
+        for (unsigned off = 16u; off >= C4; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, static_cast<int>(off));
+        acc[q][k] = v;
+      }
+    const unsigned lane = t & 31u, w = t >> 5;
+    if (lane < C4) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wred[w][q * 4 + k][lane] = acc[q][k];
+    }
+    __syncthreads();
+    for (unsigned idx = t; idx < C4 * NQ * 4u; idx += 256u) {   // one (quantity, channel) per thread and trip
+      const unsigned quad = idx % C4, qk = idx / C4;
+      double s = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) s += static_cast<double>(wred[ww][qk][quad]);
+      partial[(static_cast<size_t>(blockIdx.x) * NQ + qk / 4) * C + quad * 4 + (qk & 3u)] = s;
+    }
+    return;
+  }
+  __shared__ float red[NQ * 4][256];
 #pragma unroll
   for (int q = 0; q < NQ; ++q)
 #pragma unroll
