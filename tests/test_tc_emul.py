@@ -27,7 +27,9 @@ def _bf16(x):
     (16, 32, (2, 3, 192), 1, 1),    # W > 128: two haloed 96-wide segments per line
     (32, 16, (2, 4, 160), 1, 2),    # W > 128, CT = 32 forward / 16 backward
     (16, 16, (3, 5, 16), 1, 1),     # odd H: the box (5 lines x 4 planes) leaves MMA rows unused, last d-block partial
-    (32, 16, (2, 6, 64), 2, 1),     # dgrad 16 -> 32 on one N = 160 slice over 16-channel k-chunks (CT = 32, KC = 16), bf16x3
+    (32, 16, (2, 6, 64), 2, 1),     # fprop: two 16-channel k-chunks accumulate; dgrad 16 -> 32: two slices (column kernel), bf16x3
+    (16, 16, (19, 3, 128), 1, 1),   # column kernel: 19 planes walked with five accumulators in flight, slot ring wraps, bf16x3
+    (16, 16, (40, 2, 64), 1, 2),    # column kernel: two 20-plane segments per column (halo planes re-loaded), two lines per tile
 ])
 def test_conv5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
     rng = np.random.default_rng(7)

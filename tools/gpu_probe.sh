@@ -1,4 +1,1 @@
-mkdir -p gpurun_out
-(time python -m pytest tests -m gpu -q -x --durations=8 -k "dropout_with or loss_zoo or optimizers_follow or sync_bn_over") > gpurun_out/pytest_gpu.log 2>&1
-tail -16 gpurun_out/pytest_gpu.log
-cat gpurun_out/parity_report.txt
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x -rP -k "sync_bn_over" 2>&1 | grep -E "SYNC_BN_CHECK|passed|failed" | tee gpurun_out/sync_bn_2gpu.txt

@@ -122,8 +122,8 @@ int main(int argc, char** argv) {
     a.g = pl.g; a.bias = nullptr; a.res = nullptr; a.out1 = y; a.out2 = nullptr; a.acc1 = a.acc2 = 0;
     long long* dbg = nullptr;
     if (getenv("VNB_KB_DBG")) { dbg = s.alloc<long long>(8 * 1024); CK(cudaMemset(dbg, 0, 8 * 1024 * sizeof(long long))); a.dbg = dbg; }
-    printf("fprop plan: CT=%d KC=%d T=%d bh=%d bd=%d LP=%d lpt=%d resident=%d n_a=%d n_b=%d items=%d smem=%zu\n", pl.CT, pl.KC, pl.g.T, pl.g.bh,
-           pl.g.bd, pl.g.LP, pl.g.lpt, pl.g.resident, pl.g.n_a, pl.g.n_b, pl.g.n_items, pl.smem);
+    printf("fprop plan: col=%d (ds=%d n_seg=%d) CT=%d KC=%d T=%d bh=%d bd=%d LP=%d lpt=%d resident=%d n_a=%d n_b=%d items=%d smem=%zu\n", (int)pl.col,
+           pl.cg.ds, pl.cg.n_seg, pl.CT, pl.KC, pl.g.T, pl.g.bh, pl.g.bd, pl.g.LP, pl.g.lpt, pl.g.resident, pl.g.n_a, pl.g.n_b, pl.g.n_items, pl.smem);
     for (int i = 0; i < 3; ++i) tc_launch(pl, a, lo, sms, 0);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));

@@ -48,9 +48,10 @@ def main():
     eng.comm_init(rank, world, uid[0])
     eng.comm_sync_bn(True)
     loss = eng.forward_backward(img[lo:hi], lab[lo:hi], update_moving_stats=True)
-    eng.apply_gradients()                                   # waits for the bucket all-reduces; gradients now hold the sums
-    grads = {k: v / world for k, v in eng.get_grads().items()}
+    # logits with the step's own weights (apply_gradients below runs the optimiser), statistics of the global batch
     logits = eng.forward(img[lo:hi], want_softmax=False, want_argmax=False)[0]
+    eng.apply_gradients()                                   # exchanges the gradient buckets; gradients now hold the sums
+    grads = {k: v / world for k, v in eng.get_grads().items()}
     losses = torch.tensor([loss], dtype=torch.float64, device="cuda")
     dist.all_reduce(losses)
     gathered = [torch.zeros(logits.shape, dtype=torch.float32, device="cuda") for _ in range(world)]

@@ -788,8 +788,14 @@ inline void tma_encode_w(TmaDesc* out, const uint16_t* base, long long rows, int
   tma_encode(out, base, 2, dims, str, box, KC * 2);
 }
 
-struct TcKernelPlan {   // one launch of conv5_tc_kernel
+struct ColPlanGeom {    // conv_col.cuh: plane-sliding columns with resident weights (16 -> 16 channel layers)
+  int lpt = 0, n_hb = 0, ds = 0, n_seg = 0, n_a = 0, a_stage_bytes = 0;
+};
+
+struct TcKernelPlan {   // one launch of conv5_tc_kernel (or, col: one conv5_col_kernel launch per 16-channel slice and k-chunk)
   bool valid = false;
+  bool col = false;
+  ColPlanGeom cg{};
   int CT = 0, KC = 0, KS = 5;
   TcGeom g{};
   TmaDesc a1_hi, a1_lo, a2_hi, a2_lo, w_hi, w_lo;
@@ -800,10 +806,14 @@ struct TcKernelPlan {   // one launch of conv5_tc_kernel
 };
 
 // geometry for a [N][D][H][W] activation, kernel-side channel counts (C1+C2 in, Co1+Co2 out)
+inline bool col_plan_try(TcKernelPlan& pl, int N, int D, int H, int W, int C1, int C2, int Co1, int Co2, bool split3, int sms);
+
 inline bool tc_plan_geometry(TcKernelPlan& pl, int N, int D, int H, int W, int C1, int C2, int Co1, int Co2, bool split3,
                              int ks = 5, int sms = 148) {
   auto mult = [](int v, int m) { return v % m == 0; };
   pl.KS = ks;
+  pl.col = false;
+  if (ks == 5 && col_plan_try(pl, N, D, H, W, C1, C2, Co1, Co2, split3, sms)) return true;
   if (mult(C1, 32) && mult(C2, 32) && mult(Co1, 32) && mult(Co2, 32) && Co1 > 0) {
     pl.CT = 32;
     pl.KC = 32;
@@ -917,7 +927,11 @@ inline void tc_launch_inst(const TcKernelPlan& pl, const TcArgs& a, int sms, cud
   VNB_LAUNCH(kfn, grid, Cfg::THREADS, pl.smem, stream, pl.a1_hi, pl.a1_lo, pl.a2_hi, pl.a2_lo, pl.w_hi, pl.w_lo, a);
 }
 
-inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int sms, cudaStream_t stream) {
+inline int col_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int sms, cudaStream_t stream);
+
+// returns the number of kernels launched
+inline int tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int sms, cudaStream_t stream) {
+  if (pl.col) return col_launch(pl, a, split3, sms, stream);
   if (pl.KS == 3) {
     if (pl.CT == 16) {
       if (split3) tc_launch_inst<16, 3, 16, 3, 3>(pl, a, sms, stream);
@@ -926,7 +940,7 @@ inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int 
       if (split3) tc_launch_inst<32, 2, 32, 3, 3>(pl, a, sms, stream);
       else tc_launch_inst<32, 2, 32, 1, 3>(pl, a, sms, stream);
     }
-    return;
+    return 1;
   }
   if (pl.CT == 16) {
     if (split3) tc_launch_inst<16, 3, 16, 3>(pl, a, sms, stream);
@@ -938,6 +952,9 @@ inline void tc_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int 
     if (split3) tc_launch_inst<32, 2, 32, 3>(pl, a, sms, stream);
     else tc_launch_inst<32, 2, 32, 1>(pl, a, sms, stream);
   }
+  return 1;
 }
 
 }  // namespace vnb
+
+#include "conv_col.cuh"

@@ -180,8 +180,7 @@ inline void Engine::tc_run_fprop(Unit& u, int N) {
   a.out2 = nullptr;
   a.acc1 = a.acc2 = 0;
   ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "fprop");
-  tc_launch(pl, a, cfg_.precision == PREC_BF16X3, sm_count_, stream_);
-  ++launches_;
+  launches_ += tc_launch(pl, a, cfg_.precision == PREC_BF16X3, sm_count_, stream_);
 }
 
 inline void Engine::tc_run_dgrad(Unit& u, int N) {
@@ -197,8 +196,7 @@ inline void Engine::tc_run_dgrad(Unit& u, int N) {
   a.out2 = u.in2 >= 0 ? acts_[u.in2].d : nullptr;
   a.acc2 = u.in2_accumulate ? 1 : 0;
   ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "dgrad");
-  tc_launch(pl, a, cfg_.precision == PREC_BF16X3, sm_count_, stream_);
-  ++launches_;
+  launches_ += tc_launch(pl, a, cfg_.precision == PREC_BF16X3, sm_count_, stream_);
 }
 
 inline void Engine::tc_run_wgrad(Unit& u, int N) {

@@ -151,10 +151,11 @@ class Engine {
       VNB_CUDA_OK(cudaEventCreateWithFlags(&wg_done_ev_, cudaEventDisableTiming));
       VNB_CUDA_OK(cudaEventCreateWithFlags(&pack_done_ev_, cudaEventDisableTiming));
     }
-    // VNB_COMM_DUAL_WAIT=1 (experimental, not yet measured): a gradient bucket's all-reduce waits on the main and on
-    // the filter-gradient stream itself instead of the main stream joining the latter at every bucket boundary.
+    // A gradient bucket's all-reduce waits on the main and on the filter-gradient stream itself (default); with
+    // VNB_COMM_DUAL_WAIT=0 the main stream joins the filter-gradient stream at every bucket boundary instead, which
+    // serialises the overlap of the two streams there.
     const char* dw = getenv("VNB_COMM_DUAL_WAIT");
-    comm_waits_wgrad_ = dw && dw[0] == '1';
+    comm_waits_wgrad_ = !(dw && dw[0] == '0');
 #endif
     // debugging switches (route one pass of the tensor-core modes through the exact-fp32 kernels), read once
     dbg_no_tc_fprop_ = getenv("VNB_DEBUG_NO_TC_FPROP") != nullptr;
