@@ -62,6 +62,10 @@ struct Api {
 struct Volume {
   int dim[3] = {0, 0, 0};
   float pixdim[3] = {1, 1, 1}, origin[3] = {0, 0, 0};
+  float qfac = 1.f;          // pixdim[0]: handedness of the qform
+  char orient[96] = {0};     // header bytes 252..347 verbatim: qform / sform codes, quaternion, offsets, srow_x/y/z,
+                             // intent name -- written back unchanged so the label volume overlays the input
+  bool has_orient = false;
   std::vector<float> data;   // file order: x fastest
 };
 
@@ -96,6 +100,9 @@ Volume read_nifti(const std::string& path) {
     v.pixdim[a] = pixdim[1 + a];
     v.origin[a] = qoff[a];
   }
+  v.qfac = pixdim[0];
+  std::memcpy(v.orient, raw.data() + 252, 92);
+  v.has_orient = true;
   const size_t n = static_cast<size_t>(v.dim[0]) * v.dim[1] * v.dim[2];
   const size_t off = std::max<size_t>(static_cast<size_t>(vox_offset), 352);
   const size_t bytes[] = {1, 2, 4, 4, 8};
@@ -128,14 +135,18 @@ void write_nifti_i32(const std::string& path, const Volume& geom, const std::vec
   const int16_t datatype = 8, bitpix = 32, qform = 1;
   std::memcpy(hdr.data() + 70, &datatype, 2);
   std::memcpy(hdr.data() + 72, &bitpix, 2);
-  const float pixdim[8] = {1.f, geom.pixdim[0], geom.pixdim[1], geom.pixdim[2], 1.f, 1.f, 1.f, 1.f};
+  const float pixdim[8] = {geom.has_orient ? geom.qfac : 1.f, geom.pixdim[0], geom.pixdim[1], geom.pixdim[2], 1.f, 1.f, 1.f, 1.f};
   std::memcpy(hdr.data() + 76, pixdim, 32);
   const float vox_offset = 352.f, slope = 1.f, inter = 0.f;
   std::memcpy(hdr.data() + 108, &vox_offset, 4);
   std::memcpy(hdr.data() + 112, &slope, 4);
   std::memcpy(hdr.data() + 116, &inter, 4);
-  std::memcpy(hdr.data() + 252, &qform, 2);
-  std::memcpy(hdr.data() + 268, geom.origin, 12);
+  if (geom.has_orient) {   // the input scan's qform / sform (direction, origin) carried through verbatim
+    std::memcpy(hdr.data() + 252, geom.orient, 92);
+  } else {
+    std::memcpy(hdr.data() + 252, &qform, 2);
+    std::memcpy(hdr.data() + 268, geom.origin, 12);
+  }
   std::memcpy(hdr.data() + 344, "n+1", 4);
   std::ofstream f(path, std::ios::binary);
   if (!f) throw std::runtime_error("cannot write " + path);

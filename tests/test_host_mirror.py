@@ -104,7 +104,13 @@ def test_train_checkpoint_restore_evaluate_roundtrip(emul_lib, tmp_path):
     # the evaluator's window grid equals the reference arithmetic (model.py:866-892)
     assert R.window_starts(12, 8, 4) == [0, 4] and R.window_starts(10, 8, 4) == [0, 2]
     lab, sm, w = m2.evaluate_single_3D(vol[..., None])
-    assert w.max() == 4 and w.min() == 1  # overlap counts of 2x2x1 windows
+    # overlap counts of the 2x2x1 windows, with the reference's quirk: the last batch is on the work list twice
+    # (model.py:898-904), so its windows count double
+    from oracle import ref_eval as _re
+    w_plain = _re.evaluate_volume(vol[..., None], m2.patch_shape, m2.evaluate_stride, m2.evaluate_batch, m2.output_channel_num,
+                                  lambda x: np.zeros(x.shape[:4] + (m2.output_channel_num,), np.float32), replay_last_batch=False)[2]
+    assert w_plain.max() == 4 and w_plain.min() == 1
+    assert w.min() >= 1 and w.max() > w_plain.max() - 1 and (w - w_plain).max() >= 1 and w.sum() > w_plain.sum()
     assert np.array_equal(lab, np.argmax(sm, -1))
     # the device window loop (vnb_evaluate_volume) against the oracle restatement of model.py:866-937 fed by
     # vnb_forward: same windows, same batches, same order of additions -> bit-exact sums, weights and labels
@@ -496,3 +502,114 @@ def test_shipped_config_and_pipeline_produce_training_patches(tmp_path):
     image, label = next(iter(ds))
     assert image.shape == (64, 64, 64, 1) and image.dtype == np.float32 and label.shape == (64, 64, 64) and label.dtype == np.int32
     assert set(np.unique(label)) <= {0, 1} and -30 <= image.min() and image.max() <= 285
+
+
+def test_last_evaluation_batch_is_replayed_like_the_reference():
+    """model.py:898-904: the work list holds the last batch twice, so its windows enter the sums and the weights twice."""
+    from oracle import ref_eval
+    vol = np.arange(6 * 4 * 4, dtype=np.float32).reshape(6, 4, 4, 1)
+    calls = []
+
+    def softmax_fn(x):
+        calls.append(x.shape[0])
+        return np.ones(x.shape[:4] + (2,), np.float32) * np.array([0.25, 0.75], np.float32)
+    # windows along x at 0, 1, 2 (patch 4, stride 1), batches of two: [0, 1], [2], and [2] again
+    lab, sums, w = ref_eval.evaluate_volume(vol, (4, 4, 4), (1, 4, 4), 2, 2, softmax_fn)
+    assert calls == [2, 1, 1]
+    assert list(w[:, 0, 0]) == [1, 2, 4, 4, 3, 2]
+    assert np.allclose(sums[..., 1], 0.75 * w) and np.array_equal(lab, np.ones((6, 4, 4), np.int64))
+    _, _, w1 = ref_eval.evaluate_volume(vol, (4, 4, 4), (1, 4, 4), 2, 2, softmax_fn, replay_last_batch=False)
+    assert list(w1[:, 0, 0]) == [1, 2, 3, 3, 2, 1]
+
+
+def test_nifti_orientation_round_trip_and_itk_convention(tmp_path):
+    """qform (quaternion + qfac) and sform are read into Image.direction / origin in ITK's LPS convention
+    and written back, so an output volume keeps the input scan's orientation."""
+    import struct
+    rng = np.random.default_rng(0)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    for flip in (False, True):
+        R = q.copy()
+        if (np.linalg.det(R) < 0) != flip:
+            R[:, 2] = -R[:, 2]
+        img = nifti.Image(rng.integers(0, 5, (4, 5, 6)).astype(np.int16), (0.5, 1.5, 2.0), (10.0, -20.0, 30.0), tuple(R.reshape(-1)))
+        p = str(tmp_path / ("a%d.nii.gz" % flip))
+        nifti.write(p, img)
+        back = nifti.read(p)
+        assert np.abs(np.array(back.direction) - np.array(img.direction)).max() < 1e-6
+        assert np.allclose(back.origin, img.origin) and np.allclose(back.spacing, img.spacing) and np.array_equal(back.array, img.array)
+        # sform-only file (qform_code = 0): same geometry
+        raw = bytearray(open(p, "rb").read() if not p.endswith(".gz") else __import__("gzip").open(p, "rb").read())
+        struct.pack_into("<h", raw, 252, 0)
+        p2 = str(tmp_path / ("s%d.nii" % flip))
+        open(p2, "wb").write(bytes(raw))
+        s_only = nifti.read(p2)
+        assert np.abs(np.array(s_only.direction) - np.array(img.direction)).max() < 1e-6 and np.allclose(s_only.origin, img.origin)
+        assert np.allclose(s_only.spacing, img.spacing)
+    # a plain RAS-identity NIfTI (what dcm2niix writes for an axial LAS->RAS scan) is ITK direction diag(-1, -1, 1)
+    hdr = bytearray(352)
+    struct.pack_into("<i", hdr, 0, 348)
+    struct.pack_into("<8h", hdr, 40, 3, 2, 2, 2, 1, 1, 1, 1)
+    struct.pack_into("<h", hdr, 70, 2)
+    struct.pack_into("<h", hdr, 72, 8)
+    struct.pack_into("<8f", hdr, 76, 1.0, 1.0, 1.0, 1.0, 1, 1, 1, 1)
+    struct.pack_into("<f", hdr, 108, 352.0)
+    struct.pack_into("<h", hdr, 252, 1)
+    struct.pack_into("<3f", hdr, 268, 5.0, 6.0, 7.0)
+    hdr[344:348] = b"n+1\0"
+    p3 = str(tmp_path / "ras.nii")
+    open(p3, "wb").write(bytes(hdr) + bytes(8))
+    ras = nifti.read(p3)
+    assert ras.direction == (-1.0, 0.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, 1.0) and ras.origin == (-5.0, -6.0, 7.0)
+    # the header check of NiftiDataset now sees real directions
+    other = nifti.Image(ras.array, ras.spacing, ras.origin)
+    assert NiftiDataset3D.NiftiDataset._same_header(ras, other)[2] is False
+
+
+def test_checkpoint_retention_follows_tf_saver(emul_lib, tmp_path):
+    """tf.train.Saver(keep_checkpoint_every_n_hours=5) with the default max_to_keep=5 (model.py:676): older
+    checkpoints are deleted, no temporary files stay behind, the state file lists what is kept."""
+    from tests.helpers import engine_for
+    from oracle import ref_vnet as R
+    from vnet_tensorflow_b200 import checkpoint
+    spec = R.VNetSpec(num_classes=2, in_channels=1, num_channels=4, num_levels=1, num_convolutions=(1,), bottom_convolutions=1)
+    eng = engine_for(spec, 8, 1, "sorensen", (), emul_lib)
+    d = str(tmp_path / "ckpt")
+    for step in range(1, 9):
+        checkpoint.save(eng, d, step, 0, "both" if step % 2 else "npz")
+    files = sorted(os.listdir(d))
+    assert not [f for f in files if ".tmp" in f]
+    kept = sorted(int(f.split("-")[1].split(".")[0]) for f in files if f.endswith(".npz"))
+    assert kept == [4, 5, 6, 7, 8]
+    assert not os.path.exists(os.path.join(d, "checkpoint-3.index")) and os.path.exists(os.path.join(d, "checkpoint-5.index"))
+    assert checkpoint.latest(d).endswith("checkpoint-8")
+    state = open(os.path.join(d, checkpoint.LATEST)).read()
+    assert state.count("all_model_checkpoint_paths") == 5
+    # a checkpoint older than keep_every_n_hours relative to the last preserved one survives the rotation
+    d2 = str(tmp_path / "ckpt2")
+    checkpoint.save(eng, d2, 1, 0, "npz", max_to_keep=1, keep_every_n_hours=1e9)      # the clock starts here
+    import time
+    time.sleep(0.05)
+    checkpoint.save(eng, d2, 2, 0, "npz", max_to_keep=1, keep_every_n_hours=1e9)      # rotates 1 out: deleted
+    checkpoint.save(eng, d2, 3, 0, "npz", max_to_keep=1, keep_every_n_hours=1e-9)     # rotates 2 out: old enough, preserved
+    assert not os.path.exists(os.path.join(d2, "checkpoint-1.npz")) and os.path.exists(os.path.join(d2, "checkpoint-2.npz"))
+    step, _ = checkpoint.restore(eng, checkpoint.latest(d2))
+    assert step == 3
+    eng.close()
+
+
+def test_missing_pipeline_or_unknown_transform_is_an_error(emul_lib, tmp_path):
+    """the reference opens the pipeline YAML unconditionally and getattr()s every transform by name
+    (model.py:341-356); silently running without preprocessing is not an option."""
+    cfg = _config(tmp_path)
+    cfg["TrainingSetting"]["Synthetic"] = False
+    m = image2label(None, cfg, library=emul_lib)
+    m.read_config()
+    with pytest.raises(FileNotFoundError):
+        m._transforms(str(tmp_path / "nope.yaml"), "train")
+    y = tmp_path / "p.yaml"
+    y.write_text("preprocess:\n  train:\n    3D:\n      - name: NoSuchTransform\n        variables: {}\n")
+    with pytest.raises(AttributeError):
+        m._transforms(str(y), "train")
+    y.write_text("preprocess:\n  train:\n    3D:\n      - name: ManualNormalization\n        variables: {windowMin: 0, windowMax: 100}\n")
+    assert len(m._transforms(str(y), "train")) == 1

@@ -102,17 +102,74 @@ def import_tf(engine, prefix: str):
     return step, epoch
 
 
-def save(engine, ckpt_dir: str, global_step: int, start_epoch: int = 0, format: str = "npz") -> str:
+MAX_TO_KEEP = 5                 # tf.train.Saver default max_to_keep (model.py:676 passes none)
+KEEP_EVERY_N_HOURS = 5.0        # model.py:676: tf.train.Saver(keep_checkpoint_every_n_hours=5)
+_SUFFIXES = (".npz", ".index", ".data-00000-of-00001", ".meta")
+
+
+def _checkpoint_files(prefix: str):
+    return [prefix + s for s in _SUFFIXES if os.path.exists(prefix + s)]
+
+
+def _read_state(ckpt_dir: str):
+    """(latest prefix basename, recent basenames oldest first, timestamp of the last checkpoint kept for good)."""
+    latest_name, recent, kept_at = None, [], None
+    p = os.path.join(ckpt_dir, LATEST)
+    if os.path.exists(p):
+        with open(p) as f:
+            for line in f:
+                key, _, val = line.partition(":")
+                val = val.strip().strip('"')
+                if key == "model_checkpoint_path":
+                    latest_name = val
+                elif key == "all_model_checkpoint_paths":
+                    recent.append(val)
+                elif key == "last_preserved_timestamp":
+                    kept_at = float(val)
+    return latest_name, recent, kept_at
+
+
+def save(engine, ckpt_dir: str, global_step: int, start_epoch: int = 0, format: str = "npz",
+         max_to_keep: int = MAX_TO_KEEP, keep_every_n_hours: float = KEEP_EVERY_N_HOURS) -> str:
+    """One checkpoint per call, with tf.train.Saver's retention (model.py:676,696-699): the last `max_to_keep` are kept,
+    older ones are deleted unless `keep_every_n_hours` have passed since the last one that was kept for good.  Files are
+    written under a temporary name and renamed, so a crash never leaves a truncated checkpoint behind the pointer."""
+    import time
     if format not in FORMATS:
         raise ValueError("CheckpointFormat must be one of %s" % (FORMATS,))
     os.makedirs(ckpt_dir, exist_ok=True)
-    prefix = os.path.join(ckpt_dir, "checkpoint-%d" % global_step)
+    name = "checkpoint-%d" % global_step
+    prefix = os.path.join(ckpt_dir, name)
     if format in ("npz", "both"):
-        np.savez(prefix + ".npz", **_npz_arrays(engine, global_step, start_epoch))
+        tmp = prefix + ".tmp.npz"
+        np.savez(tmp, **_npz_arrays(engine, global_step, start_epoch))
+        os.replace(tmp, prefix + ".npz")
     if format in ("tf", "both"):
-        export_tf(engine, prefix, global_step, start_epoch)
-    with open(os.path.join(ckpt_dir, LATEST), "w") as f:  # same role as tf's latest_filename
-        f.write('model_checkpoint_path: "%s"\n' % os.path.basename(prefix))
+        tmp_prefix = prefix + ".tmp"
+        export_tf(engine, tmp_prefix, global_step, start_epoch)
+        for suffix in (".data-00000-of-00001", ".index"):   # data first: the index is what marks the bundle complete
+            os.replace(tmp_prefix + suffix, prefix + suffix)
+    _, recent, kept_at = _read_state(ckpt_dir)
+    now = time.time()
+    if kept_at is None:
+        kept_at = now
+    recent = [r for r in recent if r != name] + [name]
+    while max_to_keep and len(recent) > max_to_keep:
+        old = recent.pop(0)
+        files = _checkpoint_files(os.path.join(ckpt_dir, old))
+        stamp = max([os.path.getmtime(f) for f in files], default=now)
+        if keep_every_n_hours and stamp - kept_at >= keep_every_n_hours * 3600.0:
+            kept_at = stamp          # this one stays on disk, like Saver's keep_checkpoint_every_n_hours
+            continue
+        for f in files:
+            os.remove(f)
+    tmp = os.path.join(ckpt_dir, LATEST + ".tmp")
+    with open(tmp, "w") as f:  # same role and keys as tf's CheckpointState file
+        f.write('model_checkpoint_path: "%s"\n' % name)
+        for r in recent:
+            f.write('all_model_checkpoint_paths: "%s"\n' % r)
+        f.write("last_preserved_timestamp: %r\n" % kept_at)
+    os.replace(tmp, os.path.join(ckpt_dir, LATEST))
     return prefix
 
 

@@ -323,12 +323,17 @@ class Engine {
       VNB_LAUNCH(softmax_loss_fwd_kernel, grid, 256, 0, stream_, acts_[head_act_].a, (const int32_t*)nullptr, per, lc, softmax_dev_,
                  (long long*)nullptr, (double*)nullptr);
       ++launches_;
-      for (int j = 0; j < nb; ++j) {
-        const int* st = &starts[3 * (b0 + j)];
-        VNB_LAUNCH(window_accumulate_kernel, grid_for(per, 256), 256, 0, stream_, (const float*)(softmax_dev_ + j * per * K), wg,
-                   st[0], st[1], st[2], sum_dev, wgt_dev);
-        ++launches_;
-      }
+      // The reference puts the last batch on its work list twice (model.py:903-904 appends the list object that
+      // model.py:898-899 already appended), so that batch is run and accumulated twice; its second run produces the same
+      // softmax (same windows, same batch statistics), so only the accumulation is repeated here.
+      const int reps = (b0 + batch >= nwin) ? 2 : 1;
+      for (int rep = 0; rep < reps; ++rep)
+        for (int j = 0; j < nb; ++j) {
+          const int* st = &starts[3 * (b0 + j)];
+          VNB_LAUNCH(window_accumulate_kernel, grid_for(per, 256), 256, 0, stream_, (const float*)(softmax_dev_ + j * per * K), wg,
+                     st[0], st[1], st[2], sum_dev, wgt_dev);
+          ++launches_;
+        }
     }
     if (label) {
       VNB_LAUNCH(volume_argmax_kernel, grid_for(V, 256), 256, 0, stream_, (const float*)sum_dev, V, K, lab_dev);

@@ -85,16 +85,22 @@ class image2label(object):
     def _transforms(self, yaml_path, phase):
         """model.py:341-402: instantiate NiftiDataset3D transforms by name from the pipeline YAML."""
         if not yaml_path or not os.path.exists(yaml_path):
-            return []
+            # the reference opens the file unconditionally (model.py:341-343): a missing pipeline is an error, not an
+            # empty one -- training without normalisation / resampling / cropping would only fail later, or silently.
+            # Synthetic runs have no files to transform and may leave it out.
+            if self.cfg.synthetic:
+                return []
+            raise FileNotFoundError("pipeline YAML not found: {!r} (set TrainingSetting.Pipeline / "
+                                    "EvaluationSetting.Pipeline, or Synthetic for a dry run)".format(yaml_path))
         import yaml
         with open(yaml_path) as f:
             spec = yaml.safe_load(f)
         out = []
         for t in (spec.get("preprocess", {}).get(phase, {}) or {}).get("3D", []) or []:
             cls = getattr(NiftiDataset3D, t["name"], None)
-            if cls is None:
-                print("{}: transform {} is not available in this port, skipped".format(_now(), t["name"]))
-                continue
+            if cls is None:   # the reference's getattr raises on an unknown class name (model.py:352-356)
+                raise AttributeError("pipeline {}: unknown transform {!r} (module pipeline.NiftiDataset3D)"
+                                     .format(yaml_path, t["name"]))
             out.append(cls(**(t.get("variables") or {})))
         return out
 
