@@ -221,6 +221,31 @@ int vnb_op_conv3_dgrad(int device, int precision, const float* dy, const float* 
 int vnb_op_conv3_wgrad(int device, int precision, const float* x, const float* dy, float* dw, int n, int d,
                        int h, int w_, int cin, int cout);
 
+/* ---- per-op hooks of the remaining hot-path kernels (tests; host buffers in and out) ------------------------------
+ * 2x2x2 stride-2 down / transposed-up convolution kernels, layers2.py:65-94 (networks.py:278,292):
+ *   op 0 "gather"  : coarse[m][cc] = bias[cc] + sum_{tap,cf} fine[child(m,tap)][cf] * w[tap][cf][cc]   (down fprop, up dgrad)
+ *   op 1 "scatter" : fine[child][cf] = bias[cf] + sum_cc coarse[m][cc] * w[tap][cf][cc]                (up fprop, down dgrad)
+ *   op 2 "wgrad"   : dw[tap][cf][cc] = sum_m fine[child(m,tap)][cf] * coarse[m][cc]
+ * fine [n][2dc][2hc][2wc][cf], coarse [n][dc][hc][wc][cc], w / dw [2][2][2][cf][cc]; `out` is the op's result tensor. */
+int vnb_op_k2(int device, int precision, int op, const float* fine, const float* coarse, const float* w, const float* bias,
+              float* out, int n, int dc, int hc, int wc, int cf, int cc);
+/* tf.layers.batch_normalization(training=True, momentum=.99, epsilon=1e-3) + prelu (networks.py:319, layers2.py:97-99)
+ * on a [voxels][c] tensor and its backward pass; alpha / dalpha may be NULL (no activation) */
+int vnb_op_bn_fwd(int device, const float* z, const float* gamma, const float* beta, const float* alpha, float* y,
+                  double* mean_out, double* var_out, long long voxels, int c);
+int vnb_op_bn_bwd(int device, const float* z, const float* dy, const float* gamma, const float* beta, const float* alpha,
+                  float* dz, float* dgamma, float* dbeta, float* dalpha, long long voxels, int c);
+/* softmax, one-hot, Dice / Jaccard / cross-entropy loss zoo and argmax of model.py:26-92,447,477,495-568 on logits
+ * [n][voxels][k] and int32 labels [n][voxels]; `loss` is a VNB_LOSS_* code, terms_out [n][k][4] = (I, L, R, X) */
+int vnb_op_softmax_dice_fwd(int device, const float* logits, const int32_t* labels, int n, long long voxels, int k, int loss,
+                            const float* weights, float alpha, float* loss_out, float* softmax_out, long long* argmax_out,
+                            double* terms_out);
+int vnb_op_softmax_dice_bwd(int device, const float* logits, const int32_t* labels, int n, long long voxels, int k, int loss,
+                            const float* weights, float alpha, float* dlogits);
+/* one tf.train.AdamOptimizer step (model.py:652; epsilon-hat form, beta1 .9, beta2 .999, epsilon 1e-8) in place on flat
+ * vectors; t = 1-based step count, lr = exponential_decay value of that step (model.py:649) */
+int vnb_op_adam(int device, float* p, const float* g, float* m, float* v, long long count, float lr, long long t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,9 +36,27 @@ def test_header_ffi_and_shared_object_agree(product_lib):
 
 
 def test_sass_is_blackwell_native(product_lib):
-    """The shipped .so carries sm_100a SASS (and, once the tensor-core path is in, UTC*MMA / UTMALDG)."""
+    """The shipped .so carries sm_100a SASS whose convolution kernels are tcgen05 / TMA / TMEM code: every instance of
+    the three tensor-core kernels issues UTCHMMA (tcgen05.mma), UTMALDG (TMA tensor loads), LDTM (tcgen05.ld) and UTCBAR
+    (tcgen05.commit); profiles/r02_sass_summary.txt is the committed listing of the same counts."""
+    import importlib.util
     out = subprocess.run(["cuobjdump", "-lelf", product_lib.path], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+    spec = importlib.util.spec_from_file_location("sass_summary", os.path.join(ROOT, "tools", "sass_summary.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    per = mod.summarise(product_lib.path)
+    names = mod.demangle(list(per))
+    seen = {"conv5_tc_kernel": 0, "conv5_col_kernel": 0, "wgrad5_tc_kernel": 0}
+    for k, c in per.items():
+        for kern in seen:
+            if kern + "<" in names[k]:
+                seen[kern] += 1
+                assert c["UTCHMMA"] >= 7 and c["UTMALDG"] >= 8 and c["LDTM"] >= 1 and c["UTCBAR"] >= 6, (names[k], dict(c))
+                assert c["HMMA"] == 0, names[k]          # no legacy mma.sync in the tcgen05 kernels
+    assert seen["conv5_tc_kernel"] >= 8 and seen["conv5_col_kernel"] == 2 and seen["wgrad5_tc_kernel"] == 8, seen
+    total = sum(c["UTCHMMA"] for c in per.values())
+    assert total >= 500, total
 
 
 def test_create_fails_loudly_without_gpu(product_lib):

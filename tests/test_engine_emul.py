@@ -551,3 +551,17 @@ def test_loss_parts_are_the_two_summaries_of_the_mixed_losses(emul_lib, loss, we
         if not loss.startswith("mixed"):
             assert abs(xent_part) < 1e-6
     eng.close()
+
+
+# ---- per-op hooks: CPU twins of the GPU tests in tests/test_gpu_parity.py -----------------------------------
+def test_op_hooks_k2_bn_softmax_dice_adam(emul_lib):
+    from tests import op_hook_cases as H
+    H.check_k2_ops(emul_lib, "fp32", 16, 32, (3, 4, 5))
+    H.check_k2_ops(emul_lib, "bf16x3", 16, 32, (2, 4, 8))       # mma.sync 3xTF32 tiles (CPU model of the warp MMA)
+    H.check_k2_ops(emul_lib, "fp32", 4, 6, (2, 3, 2), n=1)      # channels outside the tiled kernels' domain
+    H.check_bn_ops(emul_lib, 4096, 16)
+    H.check_bn_ops(emul_lib, 1000, 128, with_alpha=False)
+    H.check_softmax_dice_ops(emul_lib, "weighted_sorensen", (0.1, 0.5, 1.0), 1.0)
+    H.check_softmax_dice_ops(emul_lib, "mixed_weighted_jaccard", (0.2, 0.3, 1.0), 1.5)
+    H.check_softmax_dice_ops(emul_lib, "xent", (), 1.0, k=2)
+    H.check_adam_op(emul_lib)

@@ -789,3 +789,25 @@ def test_sync_bn_over_nccl_two_gpus_equal_one_device_at_the_global_batch(gpu_lib
     line = [l for l in r.stdout.splitlines() if l.startswith("SYNC_BN_CHECK")]
     assert line and "ok=True" in line[-1], r.stdout[-2000:]
     print(line[-1])
+
+
+# ---- per-op hooks on the device ------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("cf,cc,dims", [(16, 32, (8, 8, 8)), (32, 64, (4, 6, 8)), (64, 128, (3, 4, 4)), (128, 256, (2, 2, 4)),
+                                        (16, 32, (5, 3, 7))])
+def test_k2_stride2_ops_match_torch(gpu_lib, cf, cc, dims, precision):
+    """SURVEY 8 rows a2 / a3 per op: the 2^3 stride-2 down convolution, the transposed up convolution (= its input
+    gradient) and their filter gradient, against torch (layers2.py:65-94)."""
+    from tests import op_hook_cases as H
+    H.check_k2_ops(gpu_lib, precision, cf, cc, dims)
+
+
+def test_bn_softmax_dice_adam_ops_match_oracle(gpu_lib):
+    from tests import op_hook_cases as H
+    H.check_bn_ops(gpu_lib, 32768, 16)
+    H.check_bn_ops(gpu_lib, 4096, 256, with_alpha=False)
+    for loss, w, a, k in (("weighted_sorensen", (0.1, 1.0), 1.0, 2), ("jaccard", (), 1.0, 3), ("xent", (), 1.0, 2),
+                          ("weighted_xent", (0.2, 0.3, 1.0), 1.0, 3), ("mixed_weighted_jaccard", (0.2, 0.3, 1.0), 1.5, 3),
+                          ("mixed_sorensen", (), 0.7, 4)):
+        H.check_softmax_dice_ops(gpu_lib, loss, w, a, voxels=32768, k=k)
+    H.check_adam_op(gpu_lib, 1 << 20)

@@ -101,6 +101,14 @@ _PROTOTYPES = {
                                      C.c_void_p] + [C.c_int] * 6),
     "vnb_op_conv3_dgrad": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6),
     "vnb_op_conv3_wgrad": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6),
+    "vnb_op_k2": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 6),
+    "vnb_op_bn_fwd": (C.c_int, [C.c_int] + [C.c_void_p] * 7 + [C.c_longlong, C.c_int]),
+    "vnb_op_bn_bwd": (C.c_int, [C.c_int] + [C.c_void_p] * 9 + [C.c_longlong, C.c_int]),
+    "vnb_op_softmax_dice_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_float, C.POINTER(C.c_float), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vnb_op_softmax_dice_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_float, C.c_void_p]),
+    "vnb_op_adam": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_longlong]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 

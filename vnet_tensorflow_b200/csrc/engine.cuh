@@ -66,6 +66,23 @@ struct EngineConfig {
   int module_channels = 64;  // attention.py:41 num_channels
 };
 
+// LossCfg of a configuration (Loss.Name / Weights / Alpha of the config JSON, model.py:495-560)
+inline LossCfg loss_cfg_of(const EngineConfig& cfg) {
+  LossCfg lc;
+  lc.K = cfg.num_classes;
+  const int l = cfg.loss;
+  lc.jaccard = (l == LOSS_JACCARD || l == LOSS_WEIGHTED_JACCARD || l == LOSS_MIXED_JACCARD || l == LOSS_MIXED_WEIGHTED_JACCARD);
+  lc.use_dice = !(l == LOSS_XENT || l == LOSS_WEIGHTED_XENT);
+  lc.fg_only = (l == LOSS_SORENSEN_FG);
+  lc.weighted_dice = (l == LOSS_WEIGHTED_SORENSEN || l == LOSS_WEIGHTED_JACCARD || l == LOSS_MIXED_WEIGHTED_SORENSEN || l == LOSS_MIXED_WEIGHTED_JACCARD);
+  lc.use_xent = (l == LOSS_XENT || l == LOSS_WEIGHTED_XENT || (l >= LOSS_MIXED_SORENSEN && l <= LOSS_MIXED_WEIGHTED_JACCARD));
+  lc.weighted_xent = (l == LOSS_WEIGHTED_XENT || l == LOSS_MIXED_WEIGHTED_SORENSEN || l == LOSS_MIXED_WEIGHTED_JACCARD);
+  lc.xent_alpha = (l >= LOSS_MIXED_SORENSEN && l <= LOSS_MIXED_WEIGHTED_JACCARD) ? cfg.loss_alpha : 1.0f;
+  lc.smooth = 1e-5f;
+  for (int i = 0; i < kMaxClasses; ++i) lc.w[i] = cfg.loss_weights[i];
+  return lc;
+}
+
 enum UnitKind : int { U_INPUT_TILE = 0, U_CONV5, U_DOWN, U_UP, U_CONV1, U_ADD, U_CONV3, U_GATE };
 
 struct ParamEntry {
@@ -998,21 +1015,7 @@ class Engine {
     const long long per_block = static_cast<long long>(red_threads(g) / g.CW) * 16;  // >= 16 voxels per thread group
     return static_cast<int>(std::max<long long>(1, std::min<long long>((g.V + per_block - 1) / per_block, kMaxRedBlocks)));
   }
-  LossCfg loss_cfg() const {
-    LossCfg lc;
-    lc.K = cfg_.num_classes;
-    const int l = cfg_.loss;
-    lc.jaccard = (l == LOSS_JACCARD || l == LOSS_WEIGHTED_JACCARD || l == LOSS_MIXED_JACCARD || l == LOSS_MIXED_WEIGHTED_JACCARD);
-    lc.use_dice = !(l == LOSS_XENT || l == LOSS_WEIGHTED_XENT);
-    lc.fg_only = (l == LOSS_SORENSEN_FG);
-    lc.weighted_dice = (l == LOSS_WEIGHTED_SORENSEN || l == LOSS_WEIGHTED_JACCARD || l == LOSS_MIXED_WEIGHTED_SORENSEN || l == LOSS_MIXED_WEIGHTED_JACCARD);
-    lc.use_xent = (l == LOSS_XENT || l == LOSS_WEIGHTED_XENT || (l >= LOSS_MIXED_SORENSEN && l <= LOSS_MIXED_WEIGHTED_JACCARD));
-    lc.weighted_xent = (l == LOSS_WEIGHTED_XENT || l == LOSS_MIXED_WEIGHTED_SORENSEN || l == LOSS_MIXED_WEIGHTED_JACCARD);
-    lc.xent_alpha = (l >= LOSS_MIXED_SORENSEN && l <= LOSS_MIXED_WEIGHTED_JACCARD) ? cfg_.loss_alpha : 1.0f;
-    lc.smooth = 1e-5f;
-    for (int i = 0; i < kMaxClasses; ++i) lc.w[i] = cfg_.loss_weights[i];
-    return lc;
-  }
+  LossCfg loss_cfg() const { return loss_cfg_of(cfg_); }
   static constexpr int kLossBlocks = 296;
   int loss_blocks() const {
     const long long Vn = voxels(1);

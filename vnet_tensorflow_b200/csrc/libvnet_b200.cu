@@ -702,3 +702,270 @@ VNB_DEFINE_CONV_OPS(3)
 #undef VNB_DEFINE_CONV_OPS
 
 }  // extern "C"
+
+// ---- per-op hooks of the remaining hot-path kernels: host buffers in, host buffers out -----------------
+namespace {
+struct HostToDev {   // device copy of a host array (nullptr stays nullptr)
+  DevBuf buf;
+  HostToDev(const void* host, size_t bytes) : buf(bytes) {
+    if (host) VNB_CUDA_OK(cudaMemcpy(buf.p, host, bytes, cudaMemcpyHostToDevice));
+    else VNB_CUDA_OK(cudaMemset(buf.p, 0, bytes ? bytes : 16));
+  }
+};
+void op_sync_and_check() {
+  VNB_CUDA_OK(cudaDeviceSynchronize());
+  VNB_CUDA_OK(cudaGetLastError());
+}
+inline int op_blocks(long long n, int block, int cap) {
+  return static_cast<int>(std::max<long long>(1, std::min<long long>((n + block - 1) / block, cap)));
+}
+}  // namespace
+
+extern "C" {
+
+/* 2x2x2 stride-2 kernels (layers2.py:65-94), op: 0 down fprop / up dgrad (gather), 1 up fprop / down dgrad (scatter),
+ * 2 filter gradient.  fine [n][2dc][2hc][2wc][cf], coarse [n][dc][hc][wc][cc], w and dw [2][2][2][cf][cc]. */
+int vnb_op_k2(int device, int precision, int op, const float* fine, const float* coarse, const float* w, const float* bias,
+              float* out, int n, int dc, int hc, int wc, int cf, int cc) {
+  return guarded([&] {
+    using namespace vnb;
+    if (op != 2) need(w, "w");
+    need(out, "out");
+    if (op < 0 || op > 2) throw std::invalid_argument("vnb_op_k2: op must be 0 (gather), 1 (scatter) or 2 (filter gradient)");
+    op_device(device);
+    const long long M = static_cast<long long>(n) * dc * hc * wc;
+    const size_t fine_b = static_cast<size_t>(M) * 8 * cf * 4, coarse_b = static_cast<size_t>(M) * cc * 4, w_b = static_cast<size_t>(8) * cf * cc * 4;
+    HostToDev dfine(op != 1 ? fine : nullptr, fine_b), dcoarse(op != 0 ? coarse : nullptr, coarse_b), dw_(op != 2 ? w : nullptr, w_b);
+    HostToDev db(bias, static_cast<size_t>(op == 0 ? cc : cf) * 4);
+    K2Args p{};
+    p.fine_in = dfine.buf.as<float>();
+    p.coarse_in = dcoarse.buf.as<float>();
+    p.fine_out = dfine.buf.as<float>();
+    p.coarse_out = dcoarse.buf.as<float>();
+    p.w = dw_.buf.as<float>();
+    p.dw = dw_.buf.as<float>();
+    p.bias = bias ? db.buf.as<float>() : nullptr;
+    p.CF = cf;
+    p.CC = cc;
+    p.cd = Dims{dc, hc, wc};
+    p.N = n;
+    p.accumulate = 0;
+    const bool tiled = cf % 16 == 0 && cc % 16 == 0, mma = precision != VNB_PREC_FP32;
+    if (op == 0) {
+      if (tiled) {
+        dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (cc + kK2_BN - 1) / kK2_BN);
+        if (mma) VNB_LAUNCH(k2_gather_mma_kernel, grid, 256, 0, 0, p, M);
+        else VNB_LAUNCH(k2_gather_tiled_kernel<false>, grid, 256, 0, 0, p, M);
+      } else {
+        VNB_LAUNCH(k2_gather_kernel, op_blocks(M * cc, 256, 1 << 20), 256, 0, 0, p);
+      }
+      op_sync_and_check();
+      VNB_CUDA_OK(cudaMemcpy(out, dcoarse.buf.p, coarse_b, cudaMemcpyDeviceToHost));
+    } else if (op == 1) {
+      if (tiled) {
+        dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (8 * cf + kK2_BN - 1) / kK2_BN);
+        if (mma) VNB_LAUNCH(k2_scatter_mma_kernel, grid, 256, 0, 0, p, M);
+        else VNB_LAUNCH(k2_scatter_tiled_kernel<false>, grid, 256, 0, 0, p, M);
+      } else {
+        VNB_LAUNCH(k2_scatter_kernel, op_blocks(M * 8 * cf, 256, 1 << 20), 256, 0, 0, p);
+      }
+      op_sync_and_check();
+      VNB_CUDA_OK(cudaMemcpy(out, dfine.buf.p, fine_b, cudaMemcpyDeviceToHost));
+    } else {
+      VNB_CUDA_OK(cudaMemset(dw_.buf.p, 0, w_b));
+      if (tiled) {
+        const int gx = (8 * cf + kK2_BM - 1) / kK2_BM, gy = (cc + kK2_BN - 1) / kK2_BN;
+        long long splits = std::max<long long>(1, std::min<long long>((M + 255) / 256, (4 * 148 + gx * gy - 1) / (gx * gy)));
+        const long long mps = ((M + splits - 1) / splits + kK2_BK - 1) / kK2_BK * kK2_BK;
+        splits = (M + mps - 1) / mps;
+        dim3 grid(gx, gy, static_cast<unsigned>(splits));
+        if (mma) VNB_LAUNCH(k2_wgrad_mma_kernel, grid, 256, 0, 0, p, M, mps);
+        else VNB_LAUNCH(k2_wgrad_tiled_kernel<false>, grid, 256, 0, 0, p, M, mps);
+      } else {
+        const long long outs = 8LL * cf * cc;
+        const int oblocks = static_cast<int>((outs + 255) / 256);
+        long long splits = std::max<long long>(1, std::min<long long>(M, (2 * 1184 + oblocks - 1) / oblocks));
+        const int vps = static_cast<int>((M + splits - 1) / splits);
+        splits = (M + vps - 1) / vps;
+        dim3 grid(oblocks, static_cast<unsigned>(splits));
+        VNB_LAUNCH(k2_wgrad_kernel, grid, 256, 0, 0, p, vps);
+      }
+      op_sync_and_check();
+      VNB_CUDA_OK(cudaMemcpy(out, dw_.buf.p, w_b, cudaMemcpyDeviceToHost));
+    }
+  });
+}
+
+/* Training-mode batch norm + PReLU (networks.py:319, layers2.py:97-99) on a [V][C] tensor, plain chain:
+ * y = prelu(gamma * (z - mean) / sqrt(var + 1e-3) + beta); alpha may be null (no activation). */
+int vnb_op_bn_fwd(int device, const float* z, const float* gamma, const float* beta, const float* alpha, float* y,
+                  double* mean_out, double* var_out, long long voxels, int c) {
+  return guarded([&] {
+    using namespace vnb;
+    need(z, "z"); need(gamma, "gamma"); need(beta, "beta"); need(y, "y");
+    if (c % 4 || 256 % (c / 4)) throw std::invalid_argument("vnb_op_bn_fwd: C must be a multiple of 4 with C/4 dividing 256");
+    op_device(device);
+    const size_t nb = static_cast<size_t>(voxels) * c * 4;
+    HostToDev dz(z, nb), dg(gamma, c * 4), dbt(beta, c * 4), da(alpha, c * 4), dmm(nullptr, c * 4), dmv(nullptr, c * 4);
+    DevBuf dy(nb), partial(static_cast<size_t>(kMaxRedBlocks) * 2 * c * 8), mean(c * 8), var(c * 8), scale(c * 4), shift(c * 4);
+    const unsigned total4 = static_cast<unsigned>(voxels * c / 4);
+    const int nblk = op_blocks(total4, 256 * 8, kMaxRedBlocks / 2);
+    VNB_LAUNCH(bn_stats_v4_kernel, nblk, 256, 0, 0, (const float*)dz.buf.as<float>(), c, total4, partial.as<double>());
+    BnParams bp{};
+    bp.gamma[0] = dg.buf.as<float>();
+    bp.beta[0] = dbt.buf.as<float>();
+    bp.moving_mean[0] = dmm.buf.as<float>();
+    bp.moving_var[0] = dmv.buf.as<float>();
+    VNB_LAUNCH(bn_finalize_fwd_kernel, c, 128, 0, 0, (const double*)partial.as<double>(), nblk, 2, c, static_cast<double>(voxels), (int)CH_S, bp,
+               0, 0, mean.as<double>(), var.as<double>(), scale.as<float>(), shift.as<float>(), 0);
+    ApplyArgs ap{};
+    ap.z = dz.buf.as<float>();
+    ap.a = dy.as<float>();
+    ap.scale = scale.as<float>();
+    ap.shift = shift.as<float>();
+    ap.alpha = alpha ? da.buf.as<float>() : nullptr;
+    ap.total = voxels * c;
+    ap.C = c;
+    VNB_LAUNCH(bn_apply_v4_kernel, op_blocks(ap.total / 4, 256, 2 * kMaxRedBlocks), 256, 0, 0, ap);
+    op_sync_and_check();
+    VNB_CUDA_OK(cudaMemcpy(y, dy.p, nb, cudaMemcpyDeviceToHost));
+    if (mean_out) VNB_CUDA_OK(cudaMemcpy(mean_out, mean.p, c * 8, cudaMemcpyDeviceToHost));
+    if (var_out) VNB_CUDA_OK(cudaMemcpy(var_out, var.p, c * 8, cudaMemcpyDeviceToHost));
+  });
+}
+
+/* backward of vnb_op_bn_fwd: dz, dgamma, dbeta, dalpha (dalpha may be null when alpha is) from dL/dy */
+int vnb_op_bn_bwd(int device, const float* z, const float* dy, const float* gamma, const float* beta, const float* alpha,
+                  float* dz, float* dgamma, float* dbeta, float* dalpha, long long voxels, int c) {
+  return guarded([&] {
+    using namespace vnb;
+    need(z, "z"); need(dy, "dy"); need(gamma, "gamma"); need(beta, "beta"); need(dz, "dz");
+    if (c % 4 || 256 % (c / 4)) throw std::invalid_argument("vnb_op_bn_bwd: C must be a multiple of 4 with C/4 dividing 256");
+    op_device(device);
+    const size_t nb = static_cast<size_t>(voxels) * c * 4;
+    HostToDev dzb(z, nb), dd(dy, nb), dg(gamma, c * 4), dbt(beta, c * 4), da(alpha, c * 4), dmm(nullptr, c * 4), dmv(nullptr, c * 4);
+    DevBuf partial(static_cast<size_t>(kMaxRedBlocks) * 3 * c * 8), mean(c * 8), var(c * 8), scale(c * 4), shift(c * 4);
+    DevBuf P(c * 4), Q(c * 4), S(c * 4), gg(c * 4), gb(c * 4), ga(c * 4);
+    const unsigned total4 = static_cast<unsigned>(voxels * c / 4);
+    const int nblk = op_blocks(total4, 256 * 8, kMaxRedBlocks / 2);
+    BnParams bp{};
+    bp.gamma[0] = dg.buf.as<float>();
+    bp.beta[0] = dbt.buf.as<float>();
+    bp.moving_mean[0] = dmm.buf.as<float>();
+    bp.moving_var[0] = dmv.buf.as<float>();
+    VNB_LAUNCH(bn_stats_v4_kernel, nblk, 256, 0, 0, (const float*)dzb.buf.as<float>(), c, total4, partial.as<double>());
+    VNB_LAUNCH(bn_finalize_fwd_kernel, c, 128, 0, 0, (const double*)partial.as<double>(), nblk, 2, c, static_cast<double>(voxels), (int)CH_S, bp,
+               0, 0, mean.as<double>(), var.as<double>(), scale.as<float>(), shift.as<float>(), 0);
+    BwdArgs b{};
+    b.z = dzb.buf.as<float>();
+    b.d = dd.buf.as<float>();
+    b.scale = scale.as<float>();
+    b.shift = shift.as<float>();
+    b.alpha = alpha ? da.buf.as<float>() : nullptr;
+    b.mean = mean.as<double>();
+    b.P = P.as<float>();
+    b.Q = Q.as<float>();
+    b.S = S.as<float>();
+    b.C = c;
+    VNB_LAUNCH(bn_bwd_reduce_v4_kernel, nblk, 256, 0, 0, b, total4, partial.as<double>());
+    BnGradPtrs gp{};
+    gp.dgamma[0] = gg.as<float>();
+    gp.dbeta[0] = gb.as<float>();
+    gp.dalpha = alpha ? ga.as<float>() : nullptr;
+    VNB_LAUNCH(bn_finalize_bwd_kernel, c, 128, 0, 0, (const double*)partial.as<double>(), nblk, c, static_cast<double>(voxels), (int)CH_S, bp,
+               (const double*)var.as<double>(), gp, P.as<float>(), Q.as<float>(), S.as<float>(), 0, (const double*)nullptr, 0.0);
+    VNB_LAUNCH(bn_bwd_apply_v4_kernel, op_blocks(voxels * c / 4, 256, 2 * kMaxRedBlocks), 256, 0, 0, b, voxels * c);
+    op_sync_and_check();
+    VNB_CUDA_OK(cudaMemcpy(dz, dd.buf.p, nb, cudaMemcpyDeviceToHost));
+    if (dgamma) VNB_CUDA_OK(cudaMemcpy(dgamma, gg.p, c * 4, cudaMemcpyDeviceToHost));
+    if (dbeta) VNB_CUDA_OK(cudaMemcpy(dbeta, gb.p, c * 4, cudaMemcpyDeviceToHost));
+    if (dalpha && alpha) VNB_CUDA_OK(cudaMemcpy(dalpha, ga.p, c * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+/* softmax + one-hot + Dice / Jaccard / cross-entropy loss of model.py:26-92,447,477,495-560 and argmax (model.py:568) on
+ * logits [n][voxels][k], labels int32 [n][voxels]; `loss` is a VNB_LOSS_* code.  Outputs optional except loss_out. */
+int vnb_op_softmax_dice_fwd(int device, const float* logits, const int32_t* labels, int n, long long voxels, int k, int loss,
+                            const float* weights, float alpha, float* loss_out, float* softmax_out, long long* argmax_out,
+                            double* terms_out /* [n][k][4] = (I, L, R, X) */) {
+  return guarded([&] {
+    using namespace vnb;
+    need(logits, "logits"); need(labels, "labels"); need(loss_out, "loss_out");
+    if (k < 1 || k > kMaxClasses) throw std::invalid_argument("num_classes out of range (1..8)");
+    op_device(device);
+    EngineConfig ec;
+    ec.num_classes = k;
+    ec.loss = loss;
+    ec.loss_alpha = alpha;
+    for (int i = 0; i < kMaxClasses; ++i) ec.loss_weights[i] = (weights && i < k) ? weights[i] : 1.0f;
+    const LossCfg lc = loss_cfg_of(ec);
+    const size_t nl = static_cast<size_t>(n) * voxels * k * 4;
+    HostToDev dl(logits, nl), dlab(labels, static_cast<size_t>(n) * voxels * 4);
+    const int nblk = op_blocks(voxels, 2048, 296);
+    DevBuf sm(nl), am(static_cast<size_t>(n) * voxels * 8), partial(static_cast<size_t>(n) * nblk * kMaxClasses * 4 * 8);
+    DevBuf terms(static_cast<size_t>(n) * kMaxClasses * 4 * 8), coef(static_cast<size_t>(n) * kMaxClasses * 3 * 4), lossd(16);
+    dim3 grid(nblk, n);
+    VNB_LAUNCH(softmax_loss_fwd_kernel, grid, 256, 0, 0, (const float*)dl.buf.as<float>(), (const int32_t*)dlab.buf.as<int32_t>(), voxels, lc,
+               softmax_out ? sm.as<float>() : (float*)nullptr, argmax_out ? am.as<long long>() : (long long*)nullptr, partial.as<double>());
+    VNB_LAUNCH(loss_finalize_kernel, 1, 64, 0, 0, (const double*)partial.as<double>(), n, nblk, voxels, lc, terms.as<double>(), coef.as<float>(),
+               lossd.as<float>(), (const double*)nullptr, 0, 1.0);
+    op_sync_and_check();
+    VNB_CUDA_OK(cudaMemcpy(loss_out, lossd.p, 4, cudaMemcpyDeviceToHost));
+    if (softmax_out) VNB_CUDA_OK(cudaMemcpy(softmax_out, sm.p, nl, cudaMemcpyDeviceToHost));
+    if (argmax_out) VNB_CUDA_OK(cudaMemcpy(argmax_out, am.p, static_cast<size_t>(n) * voxels * 8, cudaMemcpyDeviceToHost));
+    if (terms_out) VNB_CUDA_OK(cudaMemcpy(terms_out, terms.p, static_cast<size_t>(n) * k * 4 * 8, cudaMemcpyDeviceToHost));
+  });
+}
+
+/* dL/dlogits of the same loss */
+int vnb_op_softmax_dice_bwd(int device, const float* logits, const int32_t* labels, int n, long long voxels, int k, int loss,
+                            const float* weights, float alpha, float* dlogits) {
+  return guarded([&] {
+    using namespace vnb;
+    need(logits, "logits"); need(labels, "labels"); need(dlogits, "dlogits");
+    if (k < 1 || k > kMaxClasses) throw std::invalid_argument("num_classes out of range (1..8)");
+    op_device(device);
+    EngineConfig ec;
+    ec.num_classes = k;
+    ec.loss = loss;
+    ec.loss_alpha = alpha;
+    for (int i = 0; i < kMaxClasses; ++i) ec.loss_weights[i] = (weights && i < k) ? weights[i] : 1.0f;
+    const LossCfg lc = loss_cfg_of(ec);
+    const size_t nl = static_cast<size_t>(n) * voxels * k * 4;
+    HostToDev dl(logits, nl), dlab(labels, static_cast<size_t>(n) * voxels * 4);
+    const int nblk = op_blocks(voxels, 2048, 296);
+    DevBuf partial(static_cast<size_t>(n) * nblk * kMaxClasses * 4 * 8), terms(static_cast<size_t>(n) * kMaxClasses * 4 * 8);
+    DevBuf coef(static_cast<size_t>(n) * kMaxClasses * 3 * 4), lossd(16), dg(nl);
+    dim3 grid(nblk, n);
+    VNB_LAUNCH(softmax_loss_fwd_kernel, grid, 256, 0, 0, (const float*)dl.buf.as<float>(), (const int32_t*)dlab.buf.as<int32_t>(), voxels, lc,
+               (float*)nullptr, (long long*)nullptr, partial.as<double>());
+    VNB_LAUNCH(loss_finalize_kernel, 1, 64, 0, 0, (const double*)partial.as<double>(), n, nblk, voxels, lc, terms.as<double>(), coef.as<float>(),
+               lossd.as<float>(), (const double*)nullptr, 0, 1.0);
+    VNB_LAUNCH(softmax_loss_bwd_kernel, grid, 256, 0, 0, (const float*)dl.buf.as<float>(), (const int32_t*)dlab.buf.as<int32_t>(), voxels, lc,
+               (const float*)coef.as<float>(), 1.0f, dg.as<float>());
+    op_sync_and_check();
+    VNB_CUDA_OK(cudaMemcpy(dlogits, dg.p, nl, cudaMemcpyDeviceToHost));
+  });
+}
+
+/* one tf.train.AdamOptimizer step (epsilon-hat form, model.py:652) on a flat parameter vector, in place:
+ * t = 1-based step count, lr = the decayed learning rate of that step */
+int vnb_op_adam(int device, float* p, const float* g, float* m, float* v, long long count, float lr, long long t) {
+  return guarded([&] {
+    using namespace vnb;
+    need(p, "p"); need(g, "g"); need(m, "m"); need(v, "v");
+    op_device(device);
+    const size_t nb = static_cast<size_t>(count) * 4;
+    HostToDev dp(p, nb), dg(g, nb), dm(m, nb), dv(v, nb);
+    const double b1 = 0.9, b2 = 0.999;
+    const float lr_t = static_cast<float>(lr * std::sqrt(1.0 - std::pow(b2, (double)t)) / (1.0 - std::pow(b1, (double)t)));
+    VNB_LAUNCH(adam_step_kernel, op_blocks(count, 256, 2 * kMaxRedBlocks), 256, 0, 0, dp.buf.as<float>(), (const float*)dg.buf.as<float>(),
+               dm.buf.as<float>(), dv.buf.as<float>(), count, lr_t, 0.9f, 0.999f, 1e-8f, 1.0f);
+    op_sync_and_check();
+    VNB_CUDA_OK(cudaMemcpy(p, dp.buf.p, nb, cudaMemcpyDeviceToHost));
+    VNB_CUDA_OK(cudaMemcpy(m, dm.buf.p, nb, cudaMemcpyDeviceToHost));
+    VNB_CUDA_OK(cudaMemcpy(v, dv.buf.p, nb, cudaMemcpyDeviceToHost));
+  });
+}
+
+}  // extern "C"
