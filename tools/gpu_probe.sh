@@ -1,1 +1,6 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -q -x -rP -k "sync_bn_over" 2>&1 | grep -E "SYNC_BN_CHECK|passed|failed" | tee gpurun_out/sync_bn_2gpu.txt
+mkdir -p gpurun_out; rm -f gpurun_out/parity_report.txt
+(time python -m pytest tests -m gpu -q -x --durations=5) > gpurun_out/pytest_gpu.log 2>&1
+tail -12 gpurun_out/pytest_gpu.log
+cat gpurun_out/parity_report.txt
+VNB_NO_FUSED_STATS=1 python tools/step_probe.py bf16x3
+python tools/step_probe.py bf16x3

@@ -22,9 +22,9 @@
 namespace vnb {
 
 constexpr int kColThreads = 192;
-constexpr int kColSlots = 6;                       // 80-column accumulator slots
+constexpr int kColSlots = 3;                       // 160-column accumulator slots, one per pair of output planes
 constexpr int kColWTile = 80 * 32;                 // one (kd, kh) weight tile: 80 rows x 16 bf16
-constexpr int kColEpiBytes = 2 * 128 * kTcEpiRowPad * 4;   // two kw slices staged at a time
+constexpr int kColEpiBytes = 2 * 4 * 96 * 4 + 1024;        // warp-boundary exchange of the shift-sum epilogue, double-buffered (3 KB) + pad
 
 struct ColGeom {
   int N, D, H, W;
@@ -47,6 +47,11 @@ struct ColArgs {
   float* out;          // [V][out_stride], already offset to the slice's first channel
   int out_stride;
   int accumulate;
+  // batch-norm statistics of the stored values, folded into the epilogue (networks.py:319: tf.layers.batch_normalization
+  // right after the convolution): per-CTA (sum z, sum z^2) rows partial[(cta * 2 + q) * stats_c + stats_c0 + channel],
+  // the layout bn_finalize_fwd_kernel reads.  nullptr: no statistics (input gradients, all but the last k-chunk).
+  double* stats = nullptr;
+  int stats_c = 0, stats_c0 = 0;
   long long* dbg = nullptr;
 };
 
@@ -121,8 +126,9 @@ conv5_col_kernel(const __grid_constant__ sm100::TmaDesc a_hi, const __grid_const
     const bool leader = elect_one();
     if (leader) {   // the filter: 25 tiles per operand plane, once
       mbar_expect_tx(wfull, NPL * Cfg::W_BYTES);
-      for (int t = 0; t < 25; ++t) {
-        const int row = (p.wrow + t * p.wrow_step) * NB;
+      for (int t = 0; t < 25; ++t) {   // shared-memory order [kh][kd]: the tiles of taps kd, kd + 1 are adjacent (N = 160 operand)
+        const int kd = t % KS, kh = t / KS;
+        const int row = (p.wrow + (kd * KS + kh) * p.wrow_step) * NB;
         tma_load_2d(w_base + t * kColWTile, &w_hi, wfull, 0, row);
         if (NSPLIT == 3) tma_load_2d(w_base + Cfg::W_BYTES + t * kColWTile, &w_lo, wfull, 0, row);
       }
@@ -151,72 +157,99 @@ conv5_col_kernel(const __grid_constant__ sm100::TmaDesc a_hi, const __grid_const
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
+    // Output planes are accumulated in PAIRS (pb, pb + 1) sharing one 160-column slot: columns [0, 80) belong to the top
+    // plane pt = pb + 1, columns [80, 160) to pb.  At input plane p the pair takes taps kd0 = p - pt + 2 (top) and kd0 + 1
+    // (bottom), whose weight tiles are adjacent in shared memory ([kh][kd] order), so one N = 160 MMA feeds both planes:
+    // tensor-pipe bound (80 cycles) where two N = 80 MMAs cost ~65 each.  Where only one of the two taps exists (the first
+    // and last input plane of a pair, volume / segment borders) an N = 80 MMA writes that half alone, and the first MMA
+    // of every (pair, step) is issued as two halves because the halves start accumulating at different steps.
     const bool leader = elect_one();
-    const uint32_t idesc = make_instr_desc(128, NB, FMT_BF16);
+    const uint32_t idesc80 = make_instr_desc(128, 80, FMT_BF16), idesc160 = make_instr_desc(128, 160, FMT_BF16);
     const uint64_t desc0 = make_smem_desc(0, 16, 256, SWZ_32B);
     const uint64_t dw0 = desc0 + (w_base >> 4);
     constexpr uint32_t w_lo16 = Cfg::W_BYTES >> 4, w_tile16 = kColWTile >> 4;
     const uint32_t a_lo16 = static_cast<uint32_t>(g.a_stage_bytes) >> 4, kh_step16 = static_cast<uint32_t>(g.W * 32) >> 4;
     int as = 0;
     uint32_t aph = 0;
-    uint32_t gi0 = 0;   // running output-plane index of this CTA at the item's first plane: slot = gi % 6, use = gi / 6
+    uint32_t gi0 = 0;   // running pair index of this CTA at the item's first pair: slot = gi % 3, use = gi / 3
     VNB_DBG_DECL;
     mbar_wait_warp(wfull, 0);
     tc_fence_after_sync();
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
       int n, hb, d0, dn;
       decode(item, n, hb, d0, dn);
+      const int npairs = (dn + 1) >> 1;
       const int p_lo = d0 - RC > 0 ? d0 - RC : 0, p_hi = d0 + dn - 1 + RC < g.D - 1 ? d0 + dn - 1 + RC : g.D - 1;
       for (int pl = p_lo; pl <= p_hi; ++pl) {
-        // output planes fed by this input plane
-        const int dlo = pl - RC > d0 ? pl - RC : d0, dhi = pl + RC < d0 + dn - 1 ? pl + RC : d0 + dn - 1;
-        uint32_t d_addr[KS], first[KS];
-        uint64_t dwk[KS];
-#pragma unroll
-        for (int j = 0; j < KS; ++j) {
-          const int d = dlo + j;
-          const uint32_t gi = gi0 + static_cast<uint32_t>(d - d0);
-          d_addr[j] = tmem + (gi % kColSlots) * NB;
-          first[j] = (pl == (d - RC > 0 ? d - RC : 0)) ? 1u : 0u;      // first input plane of output plane d
-          dwk[j] = dw0 + static_cast<uint64_t>(static_cast<uint32_t>((pl - d + RC) * KS) * w_tile16);   // tile (kd, kh = 0)
-          if (d <= dhi && first[j]) {   // a fresh accumulator: wait until the epilogue has drained the slot's previous use
-            VNB_DBG_WAITP(p.dbg, dbg_wait2, mbar_wait_warp(tempty0 + 8u * (gi % kColSlots), ((gi / kColSlots) & 1u) ^ 1u));
-          }
-        }
-        tc_fence_after_sync();
         VNB_DBG_WAITP(p.dbg, dbg_wait, mbar_wait_warp(afull(as), aph));
         tc_fence_after_sync();
         const uint64_t da0 = desc0 + ((a_ring + static_cast<uint32_t>(as) * NPL * g.a_stage_bytes) >> 4);
-        const int nd = dhi - dlo + 1;
-        VNB_DBG_COUNT((NSPLIT == 3 ? 3 : 1) * KS * nd);
-        if (leader) {
-          uint64_t da = da0;
+        // pairs whose planes this input plane feeds: pb in [pl - 3, pl + 2]
+        int k_first = pl - 3 - d0;
+        k_first = k_first > 0 ? (k_first + 1) >> 1 : 0;
+        uint32_t done_mask = 0;
+        for (int j = 0; j < 3; ++j) {
+          const int k = k_first + j;
+          const int pb = d0 + 2 * k, pt = pb + 1;
+          if (k >= npairs || pb > pl + 2) break;
+          const bool top = pt < d0 + dn;
+          const int kd0 = pl - pt + 2;                      // tap of the top plane; the bottom plane takes kd0 + 1
+          const bool v0 = top && kd0 >= 0 && kd0 <= 4, v1 = kd0 + 1 >= 0 && kd0 + 1 <= 4;
+          if (!v0 && !v1) continue;
+          const uint32_t f0 = (v0 && pl == (pt - RC > 0 ? pt - RC : 0)) ? 1u : 0u;   // first input plane of the top plane
+          const uint32_t f1 = (v1 && pl == (pb - RC > 0 ? pb - RC : 0)) ? 1u : 0u;
+          const uint32_t gi = gi0 + static_cast<uint32_t>(k), slot = gi % kColSlots;
+          if (f1) {   // the pair starts here: its slot must have been drained (the two older pairs of this step go first)
+            VNB_DBG_WAITP(p.dbg, dbg_wait2, mbar_wait_warp(tempty0 + 8u * slot, ((gi / kColSlots) & 1u) ^ 1u));
+            tc_fence_after_sync();
+          }
+          const uint32_t d_top = tmem + slot * 160u, d_bot = d_top + 80u;
+          const uint64_t db_top = dw0 + static_cast<uint64_t>(static_cast<uint32_t>(kd0 < 0 ? 0 : kd0) * w_tile16);   // tile (kd0, kh = 0)
+          const uint64_t db_bot = dw0 + static_cast<uint64_t>(static_cast<uint32_t>(kd0 + 1 > 4 ? 4 : kd0 + 1) * w_tile16);
+          VNB_DBG_COUNT((NSPLIT == 3 ? 3 : 1) * KS * ((v0 ? 1 : 0) + (v1 ? 1 : 0)));
+          if (leader) {
+            uint64_t da = da0;
+            if (v0 && v1) {
 #pragma unroll
-          for (int kh = 0; kh < KS; ++kh) {
-#pragma unroll
-            for (int j = 0; j < KS; ++j) {
-              if (j < nd) {
-                const uint64_t db = dwk[j] + static_cast<uint64_t>(kh * w_tile16);
-                const uint32_t acc = (kh == 0 && first[j]) ? 0u : 1u;
-                mma_f16_ss(d_addr[j], da, db, idesc, acc);
-                if (NSPLIT == 3) {
-                  mma_f16_ss(d_addr[j], da + a_lo16, db, idesc, 1u);
-                  mma_f16_ss(d_addr[j], da, db + w_lo16, idesc, 1u);
+              for (int kh = 0; kh < KS; ++kh) {
+                const uint64_t b0 = db_top + static_cast<uint64_t>(kh * KS * w_tile16);
+                if (kh == 0) {
+                  mma_f16_ss(d_top, da, b0, idesc80, f0 ^ 1u);
+                  mma_f16_ss(d_bot, da, b0 + w_tile16, idesc80, f1 ^ 1u);
+                } else {
+                  mma_f16_ss(d_top, da, b0, idesc160, 1u);
                 }
+                if (NSPLIT == 3) {
+                  mma_f16_ss(d_top, da + a_lo16, b0, idesc160, 1u);
+                  mma_f16_ss(d_top, da, b0 + w_lo16, idesc160, 1u);
+                }
+                da += kh_step16;
+              }
+            } else {
+              const uint32_t d_addr = v0 ? d_top : d_bot, first = v0 ? f0 : f1;
+              const uint64_t bb = v0 ? db_top : db_bot;
+#pragma unroll
+              for (int kh = 0; kh < KS; ++kh) {
+                const uint64_t b0 = bb + static_cast<uint64_t>(kh * KS * w_tile16);
+                mma_f16_ss(d_addr, da, b0, idesc80, (kh == 0 && first) ? 0u : 1u);
+                if (NSPLIT == 3) {
+                  mma_f16_ss(d_addr, da + a_lo16, b0, idesc80, 1u);
+                  mma_f16_ss(d_addr, da, b0 + w_lo16, idesc80, 1u);
+                }
+                da += kh_step16;
               }
             }
-            da += kh_step16;
           }
+          __syncwarp();
+          // last input plane of the pair: that of its top plane (of the bottom plane when the segment ends on it)
+          const int last_plane = top ? pt : pb;
+          if (pl == (last_plane + RC < g.D - 1 ? last_plane + RC : g.D - 1)) done_mask |= 1u << slot;
+        }
+        if (leader) {
           mma_commit(afull(as) + 32u);   // aempty: the stage is free once these MMAs have read it
-          // output planes whose last input plane this was: d = pl - 2, and at the last plane of the volume the rest
 #pragma unroll
-          for (int j = 0; j < KS; ++j) {
-            const int d = dlo + j;
-            if (j < nd && pl == (d + RC < g.D - 1 ? d + RC : g.D - 1)) {
-              const uint32_t gi = gi0 + static_cast<uint32_t>(d - d0);
-              mma_commit(tfull0 + 8u * (gi % kColSlots));
-            }
-          }
+          for (uint32_t sl = 0; sl < kColSlots; ++sl)
+            if (done_mask & (1u << sl)) mma_commit(tfull0 + 8u * sl);
         }
         __syncwarp();
         if (++as == g.n_a) {
@@ -224,7 +257,7 @@ conv5_col_kernel(const __grid_constant__ sm100::TmaDesc a_hi, const __grid_const
           aph ^= 1u;
         }
       }
-      gi0 += static_cast<uint32_t>(dn);
+      gi0 += static_cast<uint32_t>(npairs);
     }
     if (leader && gi0 > 0) {
       const uint32_t gl = gi0 - 1;
@@ -237,88 +270,138 @@ conv5_col_kernel(const __grid_constant__ sm100::TmaDesc a_hi, const __grid_const
     const int q = warp & 3;
     const int r = q * 32 + lane;             // row inside the 128-row tile
     const int lt = r / g.W, w = r % g.W;     // line inside the tile, voxel inside the line
-    uint32_t gi = 0;
+    const bool ok0 = w - 2 >= 0, ok1 = w - 1 >= 0, ok3 = w + 1 < g.W, ok4 = w + 2 < g.W;   // kw neighbours inside the line
+    uint32_t gi = 0, ti = 0;                 // running pair / plane counters of this CTA
+    float st1[16], st2[16];                  // this row's running sum z, sum z^2 over the CTA's tiles (BN statistics)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st1[i] = st2[i] = 0.f;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
       int n, hb, d0, dn;
       decode(item, n, hb, d0, dn);
       const int gh = hb * g.lpt + lt;
       const bool valid = lt < g.lpt && gh < g.H;
-      for (int d = d0; d < d0 + dn; ++d, ++gi) {
+      const int npairs = (dn + 1) >> 1;
+      for (int k = 0; k < npairs; ++k, ++gi) {
         const uint32_t slot = gi % kColSlots;
         mbar_wait(tfull0 + 8u * slot, (gi / kColSlots) & 1u);
         tc_fence_after_sync();
-        const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + slot * NB;
-        float acc[16];
-        uint32_t v[KS][16];
+        const int pb = d0 + 2 * k;
+        const bool top = pb + 1 < d0 + dn;
+        for (int half = 1; half >= (top ? 0 : 1); --half, ++ti) {   // bottom plane (columns 80..159) first
+          const int d = half ? pb : pb + 1;
+          const uint32_t t_addr = tmem + (static_cast<uint32_t>(q * 32) << 16) + slot * 160u + static_cast<uint32_t>(half) * 80u;
+          float acc[16];
+          uint32_t v[KS][16];
 #pragma unroll
-        for (int kw = 0; kw < KS; ++kw) tmem_ld16(t_addr + kw * 16, v[kw]);
-        tmem_ld_wait();
-        tc_fence_before_sync();
-        mbar_arrive(tempty0 + 8u * slot);   // the accumulator is in registers: hand the slot back
+          for (int kw = 0; kw < KS; ++kw) tmem_ld16(t_addr + kw * 16, v[kw]);
+          tmem_ld_wait();
+          if (half == (top ? 0 : 1)) {   // both planes of the pair are in registers: hand the slot back
+            tc_fence_before_sync();
+            mbar_arrive(tempty0 + 8u * slot);
+          }
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[RC][i]);
-        // shift-sum over the kw slices, two slices staged at a time: y[w] = sum_kw D[w + kw - 2][kw]
+          for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[RC][i]);
+          // shift-sum over the kw slices, y[w] = sum_kw D[w + kw - 2][kw]: row r needs slice kw of row r + kw - 2, i.e. of the
+          // lane two / one below or above -- warp shuffles, plus a 1.5 KB exchange for the two rows either side of a warp
+          // boundary (double-buffered by plane parity: one named barrier per plane)
+          float* xch = epi + (ti & 1u) * (4 * 96);
+          float* mine = xch + q * 96;   // [0,32): slice 0 of lanes 30, 31  [32,48): slice 1 of lane 31  [48,80): slice 4 of lanes 0, 1
+                                        // [80,96): slice 3 of lane 0
+          if (lane >= 30) {
 #pragma unroll
-        for (int round = 0; round < 2; ++round) {
+            for (int i = 0; i < 16; ++i) mine[(lane - 30) * 16 + i] = __uint_as_float(v[0][i]);
+          }
+          if (lane == 31) {
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int kw = round == 0 ? s : 3 + s;
-            float4* dst = reinterpret_cast<float4*>(epi + (s * 128 + r) * kTcEpiRowPad);
+            for (int i = 0; i < 16; ++i) mine[32 + i] = __uint_as_float(v[1][i]);
+          }
+          if (lane <= 1) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_float4(__uint_as_float(v[kw][4 * i]), __uint_as_float(v[kw][4 * i + 1]),
-                                   __uint_as_float(v[kw][4 * i + 2]), __uint_as_float(v[kw][4 * i + 3]));
+            for (int i = 0; i < 16; ++i) mine[48 + lane * 16 + i] = __uint_as_float(v[4][i]);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mine[80 + i] = __uint_as_float(v[3][i]);
           }
           named_bar_sync(1, 128);
+          const float* below = xch + (q - 1) * 96;   // previous warp = the rows below this warp's first row
+          const float* above = xch + (q + 1) * 96;
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int kw = round == 0 ? s : 3 + s;
-            const int ws = w + kw - RC;
-            if (ws >= 0 && ws < g.W) {
-              const float4* src = reinterpret_cast<const float4*>(epi + (s * 128 + r + kw - RC) * kTcEpiRowPad);
+          for (int i = 0; i < 16; ++i) {
+            float a0 = __shfl_up_sync(0xffffffffu, __uint_as_float(v[0][i]), 2);
+            float a1 = __shfl_up_sync(0xffffffffu, __uint_as_float(v[1][i]), 1);
+            float a3 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[3][i]), 1);
+            float a4 = __shfl_down_sync(0xffffffffu, __uint_as_float(v[4][i]), 2);
+            if (lane < 2) a0 = (q > 0 && ok0) ? below[lane * 16 + i] : 0.f;
+            if (lane < 1) a1 = (q > 0 && ok1) ? below[32 + i] : 0.f;
+            if (lane > 30) a3 = (q < 3 && ok3) ? above[80 + i] : 0.f;
+            if (lane > 29) a4 = (q < 3 && ok4) ? above[48 + (lane - 30) * 16 + i] : 0.f;
+            acc[i] += (ok0 ? a0 : 0.f) + (ok1 ? a1 : 0.f) + (ok3 ? a3 : 0.f) + (ok4 ? a4 : 0.f);
+          }
+          if (valid) {
+            const long long vox = ((static_cast<long long>(n) * g.D + d) * g.H + gh) * g.W + w;
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] += p.bias[i];
+            }
+            if (p.res) {
+              const float4* rs = reinterpret_cast<const float4*>(p.res + vox * p.res_stride);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float4 f = src[i];
+                const float4 f = rs[i];
                 acc[4 * i] += f.x;
                 acc[4 * i + 1] += f.y;
                 acc[4 * i + 2] += f.z;
                 acc[4 * i + 3] += f.w;
               }
             }
-          }
-          named_bar_sync(1, 128);
-        }
-        if (valid) {
-          const long long vox = ((static_cast<long long>(n) * g.D + d) * g.H + gh) * g.W + w;
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] += p.bias[i];
-          }
-          if (p.res) {
-            const float4* rs = reinterpret_cast<const float4*>(p.res + vox * p.res_stride);
+            float4* o = reinterpret_cast<float4*>(p.out + vox * p.out_stride);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 f = rs[i];
-              acc[4 * i] += f.x;
-              acc[4 * i + 1] += f.y;
-              acc[4 * i + 2] += f.z;
-              acc[4 * i + 3] += f.w;
+              float4 f = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+              if (p.accumulate) {
+                const float4 old = o[i];
+                f.x += old.x;
+                f.y += old.y;
+                f.z += old.z;
+                f.w += old.w;
+              }
+              o[i] = f;
+              st1[4 * i] += f.x;
+              st1[4 * i + 1] += f.y;
+              st1[4 * i + 2] += f.z;
+              st1[4 * i + 3] += f.w;
+              st2[4 * i] += f.x * f.x;
+              st2[4 * i + 1] += f.y * f.y;
+              st2[4 * i + 2] += f.z * f.z;
+              st2[4 * i + 3] += f.w * f.w;
             }
-          }
-          float4* o = reinterpret_cast<float4*>(p.out + vox * p.out_stride);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float4 f = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
-            if (p.accumulate) {
-              const float4 old = o[i];
-              f.x += old.x;
-              f.y += old.y;
-              f.z += old.z;
-              f.w += old.w;
-            }
-            o[i] = f;
           }
         }
+      }
+    }
+    if (p.stats) {   // the CTA's row of the two-stage per-channel reduction: butterfly inside the warp, four warp sums in double
+      named_bar_sync(1, 128);          // the exchange buffers of the last tile are no longer read
+      float* red = epi;                // [4 warps][32 values]
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float a = st1[i], b = st2[i];
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, off);
+          b += __shfl_xor_sync(0xffffffffu, b, off);
+        }
+        if (lane == 0) {
+          red[q * 32 + i] = a;
+          red[q * 32 + 16 + i] = b;
+        }
+      }
+      named_bar_sync(1, 128);
+      if (r < 32) {
+        const double t = static_cast<double>(red[r]) + static_cast<double>(red[32 + r]) + static_cast<double>(red[64 + r]) +
+                         static_cast<double>(red[96 + r]);
+        const int qn = r >> 4, c = r & 15;
+        p.stats[(static_cast<size_t>(blockIdx.x) * 2 + qn) * p.stats_c + p.stats_c0 + c] = t;
       }
     }
   }
@@ -443,6 +526,11 @@ inline int col_launch(const TcKernelPlan& pl, const TcArgs& a, bool split3, int 
         acc = a.acc2;
       }
       c.accumulate = kc > 0 ? 1 : acc;   // later k-chunks add to what the first one stored
+      if (a.stats && kc == g.n_kc - 1) {   // the values this launch stores are the layer's output: fold the BN statistics in
+        c.stats = a.stats;
+        c.stats_c = ctot;
+        c.stats_c0 = co;
+      }
       c.dbg = a.dbg;
       const sm100::TmaDesc& ah = src1 ? pl.a1_hi : pl.a2_hi;
       const sm100::TmaDesc& al = src1 ? pl.a1_lo : pl.a2_lo;

@@ -115,6 +115,7 @@ struct TcArgs {
   float* out1;
   float* out2;
   int acc1, acc2;
+  double* stats = nullptr;    // column kernel only (conv_col.cuh): per-CTA batch-norm partial sums of the output
   long long* dbg = nullptr;   // development counters (tools/kbench.cu): per CTA {loop cycles, cycles waiting on TMA
                               // data, MMAs, wall ns, cycles waiting for a free accumulator}
 };

@@ -179,6 +179,12 @@ inline void Engine::tc_run_fprop(Unit& u, int N) {
   a.out1 = u.z;
   a.out2 = nullptr;
   a.acc1 = a.acc2 = 0;
+  // column kernel: the epilogue also produces the per-CTA (sum z, sum z^2) rows of the unit's batch norm
+  fused_stats_blocks_ = 0;
+  if (pl.col && !u.bn_inference && !getenv("VNB_NO_FUSED_STATS")) {
+    a.stats = partial_;
+    fused_stats_blocks_ = std::max(1, std::min(N * pl.cg.n_hb * pl.cg.n_seg, sm_count_));
+  }
   ProfScope ps(*this, 0, conv5_flops(u, N), 0, &u, "fprop");
   launches_ += tc_launch(pl, a, cfg_.precision == PREC_BF16X3, sm_count_, stream_);
 }

@@ -1192,8 +1192,11 @@ class Engine {
         VNB_LAUNCH(image_stats_kernel, nblk, 256, 0, stream_, (const float*)u.z, V, partial_);
         ++launches_;
       } else {
+        fused_stats_blocks_ = 0;
         run_conv_fprop(u, N);
-        if (v4_ok(u.Cout, V * u.Cout)) {
+        if (fused_stats_blocks_ > 0) {   // the convolution's epilogue wrote the partial sums (conv_col.cuh)
+          nblk = fused_stats_blocks_;
+        } else if (v4_ok(u.Cout, V * u.Cout)) {
           const unsigned total4 = static_cast<unsigned>(V * u.Cout / 4);
           nblk = v4_blocks(total4, u.Cout);
           VNB_LAUNCH(bn_stats_v4_kernel, nblk, 256, 0, stream_, (const float*)u.z, u.Cout, total4, partial_);
@@ -1659,6 +1662,7 @@ class Engine {
   void tc_run_dgrad(Unit& u, int N);
   void tc_run_wgrad(Unit& u, int N);
   int sm_count_ = 148;
+  int fused_stats_blocks_ = 0;   // > 0: the last tc_run_fprop produced the BN partial sums in partial_ (that many rows)
   int image_cpad_ = 0;
   PackJob* pack_jobs_dev_[2] = {nullptr, nullptr};   // [0] early forward packs (compute stream), [1] the rest (side stream)
   int pack_blocks_[2] = {0, 0}, pack_njobs_[2] = {0, 0};
