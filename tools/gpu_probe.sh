@@ -1,6 +1,2 @@
-mkdir -p gpurun_out; rm -f gpurun_out/parity_report.txt
-(time python -m pytest tests -m gpu -q -x --durations=5) > gpurun_out/pytest_gpu.log 2>&1
-tail -12 gpurun_out/pytest_gpu.log
-cat gpurun_out/parity_report.txt
-VNB_NO_FUSED_STATS=1 python tools/step_probe.py bf16x3
 python tools/step_probe.py bf16x3
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --per-layer gpurun_out/per_layer_bf16x3.json > gpurun_out/bench_bf16x3.json 2> gpurun_out/bench_bf16x3.err; cut -c1-260 gpurun_out/bench_bf16x3.json
