@@ -131,6 +131,56 @@ inline void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, in
   int c[5] = {c0, c1, c2, 0, 0};
   tma_load_nd(dst, static_cast<const TmaDesc*>(tmap), bar, c);
 }
+inline void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  int c[5] = {c0, c1, c2, c3, 0};
+  tma_load_nd(dst, static_cast<const TmaDesc*>(tmap), bar, c);
+}
+// TMA stores: the box is written (or added, fp32) element by element, out-of-range parts clipped; synchronous
+inline void tma_store_nd(const TmaDesc* t, uint32_t src, const int* c, bool add) {
+  const uint32_t e = t->elem;
+  uint64_t total = 1;
+  for (int i = 0; i < t->rank; ++i) total *= t->box[i];
+  for (uint64_t lin = 0; lin < total; ++lin) {
+    uint64_t r = lin;
+    bool inb = true;
+    uint64_t goff = 0;
+    for (int i = 0; i < t->rank; ++i) {
+      const uint32_t idx = static_cast<uint32_t>(r % t->box[i]);
+      r /= t->box[i];
+      const long long g = static_cast<long long>(c[i]) + idx;
+      if (g < 0 || g >= static_cast<long long>(t->dims[i])) inb = false;
+      goff += static_cast<uint64_t>(g < 0 ? 0 : g) * t->strides[i];
+    }
+    if (!inb) continue;
+    const uint32_t a = swz_addr(src + static_cast<uint32_t>(lin) * e, t->swizzle);
+    uint8_t* dst = const_cast<uint8_t*>(t->base) + goff;
+    if (add) {
+      if (e != 4) {
+        fprintf(stderr, "[emul_sm100] TMA reduce-add is modelled for fp32 only\n");
+        abort();
+      }
+      float x, y;
+      memcpy(&x, dst, 4);
+      memcpy(&y, smem_ptr(a), 4);
+      x += y;
+      memcpy(dst, &x, 4);
+    } else {
+      memcpy(dst, smem_ptr(a), e);
+    }
+  }
+}
+inline void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  int c[5] = {c0, c1, c2, c3, 0};
+  tma_store_nd(static_cast<const TmaDesc*>(tmap), src, c, false);
+}
+inline void tma_reduce_add_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  int c[5] = {c0, c1, c2, c3, 0};
+  tma_store_nd(static_cast<const TmaDesc*>(tmap), src, c, true);
+}
+inline void tma_store_commit() {}
+template <int N>
+inline void tma_store_wait_read() {}
+inline void tma_store_wait_all() {}
 inline void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   int c[5] = {c0, c1, c2, c3, c4};
   tma_load_nd(dst, static_cast<const TmaDesc*>(tmap), bar, c);

@@ -51,8 +51,29 @@ int main(int argc, char** argv) {
     p.fine_in = fine; p.coarse_in = coarse; p.fine_out = fine; p.coarse_out = coarse; p.w = wt; p.dw = dwt; p.bias = nullptr;
     p.CF = Cin; p.CC = Cout; p.cd = Dims{D, H, W}; p.N = N; p.accumulate = 0;
     const long long M = (long long)Vc;
+    // tcgen05 / TMA form (k2_tc.cuh) unless VNB_K2_NO_TC is set; `cin2` != 0 selects the accumulating (reduce-add) epilogue
+    K2TcPlan tcp;
+    if (op != "k2w" && k2tc_enabled() && k2tc_plan_geometry(tcp, op == "k2s", N, p.cd, Cin, Cout)) {
+      tcp.img = s.alloc<uint16_t>((size_t)16 * Cin * Cout);
+      CK(cudaMemset(tcp.img, 0, (size_t)32 * Cin * Cout));
+      k2tc_encode_plan(tcp, N, p.cd, Cin, Cout, fine, coarse);
+      tcp.valid = true;
+      printf("k2tc plan: tile %dx%dx%d items=%d n_kc=%d NB=%d n_nb=%d stages=%d stage=%d smem=%zu tmem=%d\n", tcp.g.ow_t, tcp.g.oh_t, tcp.g.od_t,
+             tcp.g.n_items, tcp.g.n_kc, tcp.g.NB, tcp.g.n_nb, tcp.g.stages, tcp.g.stage_bytes, tcp.smem, tcp.g.tmem_cols);
+    }
+    K2WgPlan wgp;
+    if (op == "k2w" && k2tc_enabled() && k2wg_plan_geometry(wgp, N, p.cd, Cin, Cout)) {
+      k2wg_encode_plan(wgp, N, p.cd, Cin, Cout, fine, coarse);
+      wgp.valid = true;
+      printf("k2wg plan: tile %dx%dx%d n_mb=%d sets=%d set=%d smem=%zu tmem=%d\n", wgp.g.ow_t, wgp.g.oh_t, wgp.g.od_t, wgp.g.n_mb, wgp.g.sets,
+             wgp.g.set_bytes, wgp.smem, wgp.g.tmem_cols);
+    }
     auto launch = [&]() {
-      if (op == "k2g") {
+      if (wgp.valid) {
+        k2wg_launch(wgp, N, dwt, sms, 0);
+      } else if (tcp.valid) {
+        k2tc_launch(tcp, N, nullptr, cin2 != 0, sms, 0);
+      } else if (op == "k2g") {
         dim3 grid((unsigned)((M + kK2_BM - 1) / kK2_BM), (p.CC + kK2_BN - 1) / kK2_BN);
         k2_gather_mma_kernel<<<grid, 256>>>(p, M);
       } else if (op == "k2s") {
@@ -76,8 +97,8 @@ int main(int argc, char** argv) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double us2 = ms * 1e3 / reps;
     const double bytes = (double)Vf * Cin * 4 + (double)Vc * Cout * 4;
-    printf("KBENCH %s N=%d coarse %dx%dx%d CF=%d CC=%d : %.1f us/launch  %.0f GB/s (fine + coarse tensor once)\n", op.c_str(), N, D, H, W, Cin, Cout,
-           us2, bytes / (us2 * 1e-6) / 1e9);
+    printf("KBENCH %s%s N=%d coarse %dx%dx%d CF=%d CC=%d : %.1f us/launch  %.0f GB/s (fine + coarse tensor once)\n", op.c_str(),
+           (tcp.valid || wgp.valid) ? (cin2 ? " [tcgen05, reduce-add]" : " [tcgen05]") : "", N, D, H, W, Cin, Cout, us2, bytes / (us2 * 1e-6) / 1e9);
     return 0;
   } else if (op == "wgrad") {
     WgPlan pl;

@@ -730,16 +730,16 @@ __device__ __forceinline__ void pack_w5_tile(const PackJob& j, int tile_idx, flo
 // host helpers: tensor maps and launch plans
 // ---------------------------------------------------------------------------------------------
 inline void tma_encode(TmaDesc* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box, uint32_t swizzle_bytes) {
+                       const uint32_t* box, uint32_t swizzle_bytes, uint32_t elem_bytes = 2) {
 #ifdef VNB_EMULATE
   TmaDesc d;
   d.base = static_cast<const uint8_t*>(base);
   d.rank = rank;
-  d.elem = 2;
+  d.elem = elem_bytes;
   d.swizzle = swizzle_bytes;
   for (int i = 0; i < rank; ++i) {
     d.dims[i] = dims[i];
-    d.strides[i] = i == 0 ? 2 : strides_bytes[i - 1];
+    d.strides[i] = i == 0 ? elem_bytes : strides_bytes[i - 1];
     d.box[i] = box[i];
   }
   *out = d;
@@ -767,7 +767,7 @@ inline void tma_encode(TmaDesc* out, const void* base, int rank, const uint64_t*
                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
                                                       : CU_TENSOR_MAP_SWIZZLE_NONE;
-  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
+  const CUresult r = fn(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gd, gs, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("CUDA: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));

@@ -75,6 +75,52 @@ inline void Engine::tc_setup() {
     }
   }
   if (wg_partial_floats) wg_partial_ = dev_alloc<float>(wg_partial_floats);
+  // 2^3 stride-2 units: tcgen05 / TMA gather and scatter plans (k2_tc.cuh) over the fp32 activations and gradients
+  if (k2tc_enabled()) {
+    std::vector<K2PackJob> jobs;
+    for (Unit& u : units_) {
+      if (u.kind != U_DOWN && u.kind != U_UP) continue;
+      const Act& x1 = acts_[u.in1];
+      const Act& o = acts_[u.out];
+      const bool down = u.kind == U_DOWN;
+      const int CF = down ? u.Cin1 : u.Cout, CC = down ? u.Cout : u.Cin1;
+      const Dims cd = down ? o.dims : x1.dims;
+      K2PackJob j{};
+      j.w = params_ + u.w_off;
+      j.CF = CF;
+      j.CC = CC;
+      const size_t img_elems = 2 * u.w_count;
+      // fprop: down = gather (fine x -> coarse z), up = scatter (coarse x -> fine z)
+      if (k2tc_plan_geometry(u.k2_fprop, !down, NB, cd, CF, CC)) {
+        u.k2_fprop.img = dev_alloc<uint16_t>(img_elems);
+        (down ? j.img_gather : j.img_scatter) = u.k2_fprop.img;
+        k2tc_encode_plan(u.k2_fprop, NB, cd, CF, CC, down ? x1.a : u.z, down ? u.z : x1.a);
+        u.k2_fprop.valid = true;
+      }
+      // dgrad: down = scatter (coarse dz -> fine dx), up = gather (fine dz -> coarse dx)
+      if (u.need_dgrad && k2tc_plan_geometry(u.k2_dgrad, down, NB, cd, CF, CC)) {
+        u.k2_dgrad.img = dev_alloc<uint16_t>(img_elems);
+        (down ? j.img_scatter : j.img_gather) = u.k2_dgrad.img;
+        k2tc_encode_plan(u.k2_dgrad, NB, cd, CF, CC, down ? x1.d : o.d, down ? o.d : x1.d);
+        u.k2_dgrad.valid = true;
+      }
+      // filter gradient: fine = x (down) or dz (up), coarse = dz (down) or x (up)
+      if (k2wg_plan_geometry(u.k2_wgrad, NB, cd, CF, CC)) {
+        k2wg_encode_plan(u.k2_wgrad, NB, cd, CF, CC, down ? x1.a : o.d, down ? o.d : x1.a);
+        u.k2_wgrad.valid = true;
+      }
+      if (!j.img_gather && !j.img_scatter) continue;
+      j.first_block = k2_pack_blocks_;
+      j.n_blocks = static_cast<int>(std::min<size_t>((u.w_count + 255) / 256, 64));
+      k2_pack_blocks_ += j.n_blocks;
+      jobs.push_back(j);
+    }
+    if (!jobs.empty()) {
+      k2_pack_njobs_ = static_cast<int>(jobs.size());
+      k2_pack_jobs_dev_ = dev_alloc<K2PackJob>(jobs.size());
+      VNB_CUDA_OK(cudaMemcpy(k2_pack_jobs_dev_, jobs.data(), jobs.size() * sizeof(K2PackJob), cudaMemcpyHostToDevice));
+    }
+  }
 }
 
 // Weight packing (fp32 master -> bf16 hi/lo GEMM-B tiles) after every optimiser step.  The packs of the first forward
@@ -133,6 +179,10 @@ inline void Engine::tc_prepare_weights() {
   }
   if (pack_njobs_[0]) {
     VNB_LAUNCH(pack_w5_multi_kernel, pack_blocks_[0], 256, 0, stream_, (const PackJob*)pack_jobs_dev_[0], pack_njobs_[0]);
+    ++launches_;
+  }
+  if (k2_pack_njobs_) {   // 2^3 filters (0.2 % of the parameters): one small launch on the compute stream
+    VNB_LAUNCH(k2tc_pack_multi_kernel, k2_pack_blocks_, 256, 0, stream_, (const K2PackJob*)k2_pack_jobs_dev_, k2_pack_njobs_);
     ++launches_;
   }
   if (pack_njobs_[1]) {
@@ -255,6 +305,43 @@ inline void tc_op_conv5(int precision, const float* x, const float* w, const flo
   tc_launch(pl, a, lo, tc_query_sms(), 0);
   if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
     throw std::runtime_error("CUDA: tensor-core convolution kernel failed");
+}
+
+// 2^3 stride-2 gather / scatter through the tcgen05 kernel; false when the shape is outside its domain
+inline bool tc_op_k2(bool scatter, float* fine, float* coarse, const float* w, const float* bias, int n, Dims cd, int cf, int cc,
+                     bool accumulate = false) {
+  K2TcPlan pl;
+  if (!k2tc_enabled() || !k2tc_plan_geometry(pl, scatter, n, cd, cf, cc)) return false;
+  TcScratch s;
+  const size_t wn = static_cast<size_t>(8) * cf * cc;
+  pl.img = s.alloc<uint16_t>(2 * wn);
+  K2PackJob j{};
+  j.w = w;
+  (scatter ? j.img_scatter : j.img_gather) = pl.img;
+  j.CF = cf;
+  j.CC = cc;
+  j.first_block = 0;
+  j.n_blocks = static_cast<int>(std::min<size_t>((wn + 255) / 256, 64));
+  K2PackJob* jd = s.alloc<K2PackJob>(1);
+  if (cudaMemcpy(jd, &j, sizeof(j), cudaMemcpyHostToDevice) != cudaSuccess) throw std::runtime_error("CUDA: copy failed in tc_op_k2");
+  VNB_LAUNCH(k2tc_pack_multi_kernel, j.n_blocks, 256, 0, 0, (const K2PackJob*)jd, 1);
+  k2tc_encode_plan(pl, n, cd, cf, cc, fine, coarse);
+  k2tc_launch(pl, n, bias, accumulate, tc_query_sms(), 0);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
+    throw std::runtime_error("CUDA: tensor-core 2x2x2 kernel failed");
+  return true;
+}
+
+// 2^3 filter gradient through the tcgen05 kernel (dw is overwritten); false when the shape is outside its domain
+inline bool tc_op_k2_wgrad(const float* fine, const float* coarse, float* dw, int n, Dims cd, int cf, int cc) {
+  K2WgPlan pl;
+  if (!k2tc_enabled() || !k2wg_plan_geometry(pl, n, cd, cf, cc)) return false;
+  if (cudaMemset(dw, 0, static_cast<size_t>(8) * cf * cc * 4) != cudaSuccess) throw std::runtime_error("CUDA: memset failed in tc_op_k2_wgrad");
+  k2wg_encode_plan(pl, n, cd, cf, cc, fine, coarse);
+  k2wg_launch(pl, n, dw, tc_query_sms(), 0);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
+    throw std::runtime_error("CUDA: tensor-core 2x2x2 filter-gradient kernel failed");
+  return true;
 }
 
 inline void tc_op_wgrad5(int precision, const float* x, const float* dy, float* dw, int n, Dims dims, int cin, int cout, int ks = 5) {

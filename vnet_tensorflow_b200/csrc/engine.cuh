@@ -23,6 +23,7 @@
 #include "conv_tc.cuh"
 #include "vnb_cuda.h"
 #include "wgrad_tc.cuh"
+#include "k2_tc.cuh"
 #ifndef VNB_EMULATE
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: no link dependency, a no-op unless a profiler injects itself
 #endif
@@ -127,6 +128,8 @@ struct Unit {
   // backward plan
   bool res_accumulate = false, in1_accumulate = false, in2_accumulate = false, need_dgrad = true;
   TcConvPlan tc;                      // tensor-core plan (precision != fp32)
+  K2TcPlan k2_fprop, k2_dgrad;        // tcgen05 / TMA plans of the 2^3 stride-2 units (precision != fp32)
+  K2WgPlan k2_wgrad;
 };
 
 // NVTX range around the launches of one unit and pass ("vnet/decoder/level_1/conv_1 fwd"), on with VNB_NVTX=1:
@@ -1083,14 +1086,14 @@ class Engine {
         p.CF = u.Cin1;
         p.CC = u.Cout;
         p.cd = o.dims;
-        launch_k2_gather(p);
+        launch_k2_gather(p, &u.k2_fprop);
       } else {
         p.coarse_in = x1.a;
         p.fine_out = u.z;
         p.CF = u.Cout;
         p.CC = u.Cin1;
         p.cd = x1.dims;
-        launch_k2_scatter(p);
+        launch_k2_scatter(p, &u.k2_fprop);
       }
     } else if (u.kind == U_ADD) {
       const long long n = voxels_of(o.dims, N) * u.Cout;
@@ -1528,7 +1531,7 @@ class Engine {
         if (u.need_dgrad) {
           p.fine_out = x1.d;
           p.accumulate = u.in1_accumulate ? 1 : 0;
-          launch_k2_scatter(p);
+          launch_k2_scatter(p, &u.k2_dgrad);
         }
       } else {  // z fine, x coarse
         p.CF = u.Cout;
@@ -1538,12 +1541,12 @@ class Engine {
         if (u.need_dgrad) {
           p.coarse_out = x1.d;
           p.accumulate = u.in1_accumulate ? 1 : 0;
-          launch_k2_gather(p);
+          launch_k2_gather(p, &u.k2_dgrad);
         }
         p.coarse_in = x1.a;
       }
       p.bias = nullptr;
-      launch_k2_wgrad(p);
+      launch_k2_wgrad(p, &u.k2_wgrad);
     } else if (u.kind == U_CONV1 && conv1_general(u)) {
       const long long V = voxels_of(o.dims, N);
       if (u.need_dgrad) {
@@ -1592,9 +1595,14 @@ class Engine {
     }
   }
   static bool k2_tiled_ok(const K2Args& p) { return p.CF % 16 == 0 && p.CC % 16 == 0; }
-  void launch_k2_gather(const K2Args& p) {
+  void launch_k2_gather(const K2Args& p, K2TcPlan* tcp = nullptr) {
     const long long M = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
     if (M > 0xFFFFFFFFLL) throw std::invalid_argument("2x2x2 convolution: more than 2^32 coarse voxels per batch");
+    if (tcp && tcp->valid && cfg_.precision != PREC_FP32) {   // tcgen05 + TMA gather (k2_tc.cuh)
+      k2tc_launch(*tcp, p.N, p.bias, p.accumulate != 0, sm_count_, stream_);
+      ++launches_;
+      return;
+    }
     if (k2_tiled_ok(p)) {
       dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (p.CC + kK2_BN - 1) / kK2_BN);
       if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_gather_mma_kernel, grid, 256, 0, stream_, p, M);
@@ -1604,9 +1612,14 @@ class Engine {
     }
     ++launches_;
   }
-  void launch_k2_scatter(const K2Args& p) {
+  void launch_k2_scatter(const K2Args& p, K2TcPlan* tcp = nullptr) {
     const long long M = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
     if (M > 0xFFFFFFFFLL) throw std::invalid_argument("2x2x2 convolution: more than 2^32 coarse voxels per batch");
+    if (tcp && tcp->valid && cfg_.precision != PREC_FP32) {   // tcgen05 + TMA depth-to-space scatter (k2_tc.cuh)
+      k2tc_launch(*tcp, p.N, p.bias, p.accumulate != 0, sm_count_, stream_);
+      ++launches_;
+      return;
+    }
     if (k2_tiled_ok(p)) {
       dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (8 * p.CF + kK2_BN - 1) / kK2_BN);
       if (cfg_.precision != PREC_FP32) VNB_LAUNCH(k2_scatter_mma_kernel, grid, 256, 0, stream_, p, M);
@@ -1616,9 +1629,14 @@ class Engine {
     }
     ++launches_;
   }
-  void launch_k2_wgrad(const K2Args& p) {
+  void launch_k2_wgrad(const K2Args& p, K2WgPlan* tcp = nullptr) {
     const long long M = static_cast<long long>(p.N) * p.cd.D * p.cd.H * p.cd.W;
     if (M > 0xFFFFFFFFLL) throw std::invalid_argument("2x2x2 convolution: more than 2^32 coarse voxels per batch");
+    if (tcp && tcp->valid && cfg_.precision != PREC_FP32) {   // tcgen05 filter gradient (k2_tc.cuh)
+      k2wg_launch(*tcp, p.N, p.dw, sm_count_, stream_);
+      ++launches_;
+      return;
+    }
     if (k2_tiled_ok(p)) {
       const int gx = (8 * p.CF + kK2_BM - 1) / kK2_BM, gy = (p.CC + kK2_BN - 1) / kK2_BN;
       long long splits = std::max<long long>(1, std::min<long long>((M + 255) / 256, (4 * 148 + gx * gy - 1) / (gx * gy)));
@@ -1664,6 +1682,8 @@ class Engine {
   int sm_count_ = 148;
   int fused_stats_blocks_ = 0;   // > 0: the last tc_run_fprop produced the BN partial sums in partial_ (that many rows)
   int image_cpad_ = 0;
+  K2PackJob* k2_pack_jobs_dev_ = nullptr;            // weight images of the tcgen05 2^3 kernels (one launch per step)
+  int k2_pack_blocks_ = 0, k2_pack_njobs_ = 0;
   PackJob* pack_jobs_dev_[2] = {nullptr, nullptr};   // [0] early forward packs (compute stream), [1] the rest (side stream)
   int pack_blocks_[2] = {0, 0}, pack_njobs_[2] = {0, 0};
   bool pack_built_ = false, late_packs_pending_ = false;

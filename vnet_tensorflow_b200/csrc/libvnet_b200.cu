@@ -752,7 +752,9 @@ int vnb_op_k2(int device, int precision, int op, const float* fine, const float*
     p.accumulate = 0;
     const bool tiled = cf % 16 == 0 && cc % 16 == 0, mma = precision != VNB_PREC_FP32;
     if (op == 0) {
-      if (tiled) {
+      if (mma && tc_op_k2(false, dfine.buf.as<float>(), dcoarse.buf.as<float>(), p.w, p.bias, n, p.cd, cf, cc)) {
+        // tcgen05 + TMA gather (k2_tc.cuh)
+      } else if (tiled) {
         dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (cc + kK2_BN - 1) / kK2_BN);
         if (mma) VNB_LAUNCH(k2_gather_mma_kernel, grid, 256, 0, 0, p, M);
         else VNB_LAUNCH(k2_gather_tiled_kernel<false>, grid, 256, 0, 0, p, M);
@@ -762,7 +764,9 @@ int vnb_op_k2(int device, int precision, int op, const float* fine, const float*
       op_sync_and_check();
       VNB_CUDA_OK(cudaMemcpy(out, dcoarse.buf.p, coarse_b, cudaMemcpyDeviceToHost));
     } else if (op == 1) {
-      if (tiled) {
+      if (mma && tc_op_k2(true, dfine.buf.as<float>(), dcoarse.buf.as<float>(), p.w, p.bias, n, p.cd, cf, cc)) {
+        // tcgen05 + TMA depth-to-space scatter (k2_tc.cuh)
+      } else if (tiled) {
         dim3 grid(static_cast<unsigned>((M + kK2_BM - 1) / kK2_BM), (8 * cf + kK2_BN - 1) / kK2_BN);
         if (mma) VNB_LAUNCH(k2_scatter_mma_kernel, grid, 256, 0, 0, p, M);
         else VNB_LAUNCH(k2_scatter_tiled_kernel<false>, grid, 256, 0, 0, p, M);
@@ -773,7 +777,9 @@ int vnb_op_k2(int device, int precision, int op, const float* fine, const float*
       VNB_CUDA_OK(cudaMemcpy(out, dfine.buf.p, fine_b, cudaMemcpyDeviceToHost));
     } else {
       VNB_CUDA_OK(cudaMemset(dw_.buf.p, 0, w_b));
-      if (tiled) {
+      if (mma && tc_op_k2_wgrad(p.fine_in, p.coarse_in, p.dw, n, p.cd, cf, cc)) {
+        // tcgen05 filter gradient (k2_tc.cuh)
+      } else if (tiled) {
         const int gx = (8 * cf + kK2_BM - 1) / kK2_BM, gy = (cc + kK2_BN - 1) / kK2_BN;
         long long splits = std::max<long long>(1, std::min<long long>((M + 255) / 256, (4 * 148 + gx * gy - 1) / (gx * gy)));
         const long long mps = ((M + splits - 1) / splits + kK2_BK - 1) / kK2_BK * kK2_BK;
