@@ -55,6 +55,14 @@ def test_sass_is_blackwell_native(product_lib):
                 assert c["UTCHMMA"] >= 7 and c["UTMALDG"] >= 8 and c["LDTM"] >= 1 and c["UTCBAR"] >= 6, (names[k], dict(c))
                 assert c["HMMA"] == 0, names[k]          # no legacy mma.sync in the tcgen05 kernels
     assert seen["conv5_tc_kernel"] >= 8 and seen["conv5_col_kernel"] == 2 and seen["wgrad5_tc_kernel"] == 8, seen
+    # the 2^3 stride-2 kernels (gather / depth-to-space scatter with TMA store and reduce-add, filter gradient) and the
+    # deep-level filter gradient are tcgen05 / TMA code too
+    short = {re.sub(r"\(.*", "", names[k]).replace("void ", "").replace("vnb::", ""): c for k, c in per.items()}
+    k2 = short["k2_tc_kernel"]
+    assert k2["UTCHMMA"] >= 6 and k2["UTMALDG"] >= 3 and k2["UTMASTG"] >= 1 and k2["UTMAREDG"] >= 1 and k2["LDTM"] >= 2 and k2["HMMA"] == 0
+    for kern in ("k2_wgrad_tc_kernel", "wgrad5_deep_kernel"):
+        c = short[kern]
+        assert c["UTCHMMA"] >= 3 and c["UTMALDG"] >= 2 and c["LDTM"] >= 1 and c["UTCBAR"] >= 2 and c["HMMA"] == 0, (kern, dict(c))
     total = sum(c["UTCHMMA"] for c in per.values())
     assert total >= 500, total
 

@@ -198,7 +198,8 @@ def test_three_training_steps_follow_the_oracle(gpu_lib, precision):
 @pytest.mark.parametrize("cin,cout,dims", [(16, 16, (8, 8, 16)), (32, 16, (4, 8, 32)), (64, 32, (8, 8, 8)),
                                            (4, 16, (6, 5, 9)), (128, 128, (4, 4, 4)),
                                            (16, 16, (4, 6, 24)), (32, 32, (2, 4, 48)), (64, 64, (2, 2, 96)),
-                                           (16, 32, (2, 3, 192)), (32, 16, (3, 4, 160)), (128, 128, (2, 12, 12))])
+                                           (16, 32, (2, 3, 192)), (32, 16, (3, 4, 160)), (128, 128, (2, 12, 12)),
+                                           (128, 128, (4, 8, 8)), (256, 128, (3, 8, 16)), (128, 256, (8, 8, 8))])
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 def test_conv5_ops_match_torch(gpu_lib, cin, cout, dims, precision):
     """Per-op hooks: 5^3 SAME convolution forward, input gradient and filter gradient."""

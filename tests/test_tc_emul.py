@@ -127,6 +127,8 @@ def test_engine_bf16x3_short_batch_after_a_full_one(emul_lib):
     (64, 16, (3, 6, 32), 2, 1),     # Cout = 16, Cin = 64: roles swapped (P = dZ, Q = two X chunks per CTA), mirrored taps
     (16, 64, (6, 5, 16), 1, 2),     # two Q chunk groups, odd H, D > plane-offset group size
     (32, 32, (2, 8, 8), 1, 1),      # W = 8 with two interleaved chunks: K rows 8..15 come from the next line
+    (128, 128, (3, 8, 8), 1, 1),    # deep-level kernel (wgrad_deep.cuh): per-tap GEMM, one K tile per plane, bf16x3
+    (128, 256, (2, 4, 16), 2, 2),   # deep-level kernel: N = 256 accumulators, four-line K tiles, bf16
 ])
 def test_wgrad5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
     """MN-major overlapping-atom tap folding (kw on M, kh on N, kd on five TMEM accumulators)."""
@@ -140,6 +142,21 @@ def test_wgrad5_tc_kernel_matches_torch(emul_lib, cin, cout, dims, n, prec):
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     emul_lib.check(emul_lib.vnb_op_conv5_wgrad(0, prec, ptr(x), ptr(dy), ptr(dw), n, *dims, cin, cout))
     assert rel_err(dw, wt.grad.numpy()) < (1e-6 if prec == 2 else 3e-5)
+
+
+def test_wgrad5_deep_kernel_split_k_matches_torch(emul_lib, monkeypatch):
+    """wgrad_deep.cuh with K splits (partials + fixed-order reduce) and a second ci block."""
+    monkeypatch.setenv("VNB_WD_KSPLIT", "2")
+    cin, cout, dims, n = 256, 128, (3, 8, 8), 1
+    rng = np.random.default_rng(4)
+    x = rng.normal(0, 1, (n,) + dims + (cin,)).astype(np.float32)
+    dy = rng.normal(0, 1, (n,) + dims + (cout,)).astype(np.float32)
+    wt = torch.zeros(5, 5, 5, cin, cout, dtype=torch.float64, requires_grad=True)
+    R.conv_same(torch.from_numpy(_bf16(x)).double(), wt, torch.zeros(cout).double()).backward(torch.from_numpy(_bf16(dy)).double())
+    dw = np.empty((5, 5, 5, cin, cout), np.float32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    emul_lib.check(emul_lib.vnb_op_conv5_wgrad(0, 2, ptr(x), ptr(dy), ptr(dw), n, *dims, cin, cout))
+    assert rel_err(dw, wt.grad.numpy()) < 1e-6
 
 
 def test_multimodal_input_runs_on_tensor_cores_with_padded_channels(emul_lib):

@@ -100,6 +100,24 @@ int main(int argc, char** argv) {
     printf("KBENCH %s%s N=%d coarse %dx%dx%d CF=%d CC=%d : %.1f us/launch  %.0f GB/s (fine + coarse tensor once)\n", op.c_str(),
            (tcp.valid || wgp.valid) ? (cin2 ? " [tcgen05, reduce-add]" : " [tcgen05]") : "", N, D, H, W, Cin, Cout, us2, bytes / (us2 * 1e-6) / 1e9);
     return 0;
+  } else if (op == "wgrad" && ks == 5 && [&] { WdPlan t; return wd_plan_geometry(t, N, D, H, W, Cin, cin2, Cout, lo, sms); }()) {
+    // deep levels: per-tap GEMM kernel (wgrad_deep.cuh); VNB_WG_NO_DEEP=1 times wgrad5_tc_kernel instead
+    WdPlan pl;
+    wd_plan_geometry(pl, N, D, H, W, Cin, cin2, Cout, lo, sms);
+    uint16_t *xh = mk(V * Cin, 1), *xl = lo ? mk(V * Cin, 2) : nullptr, *zh = mk(V * Cout, 3), *zl = lo ? mk(V * Cout, 4) : nullptr;
+    uint16_t *x2h = cin2 ? mk(V * cin2, 5) : nullptr, *x2l = (cin2 && lo) ? mk(V * cin2, 6) : nullptr;
+    float* partial = s.alloc<float>(pl.partial_floats);
+    float* dw = s.alloc<float>((size_t)125 * (Cin + cin2) * Cout);
+    wd_encode_plan(pl, N, xh, xl, x2h, x2l, zh, zl);
+    printf("wgrad deep plan: HT=%d n_hb=%d n_cib=%d n_cob=%d NB=%d ksplit=%d stages=%d stage=%d items=%d smem=%zu\n", pl.g.HT, pl.g.n_hb, pl.g.n_cib,
+           pl.g.n_cob, pl.g.NB, pl.g.ksplit, pl.g.stages, pl.g.stage_bytes, pl.g.n_items, pl.smem);
+    for (int i = 0; i < 3; ++i) wd_launch(pl, N, partial, dw, sms, 0);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) wd_launch(pl, N, partial, dw, sms, 0);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventElapsedTime(&ms, e0, e1));
   } else if (op == "wgrad") {
     WgPlan pl;
     if (!wg_plan_geometry(pl, N, D, H, W, Cin, cin2, Cout, lo, sms, ks)) { printf("unsupported shape\n"); return 1; }

@@ -1,5 +1,5 @@
 """Per-kernel count of the Blackwell-only SASS instructions in the shipped library:
-UTCHMMA (tcgen05.mma), UTMALDG (TMA tensor load), LDTM (tcgen05.ld), UTCBAR (tcgen05.commit), SYNCS (mbarrier).
+UTCHMMA (tcgen05.mma), UTMALDG (TMA tensor load), UTMASTG / UTMAREDG (TMA tensor store / reduce-add), LDTM (tcgen05.ld), UTCBAR (tcgen05.commit), SYNCS (mbarrier).
     python tools/sass_summary.py [libvnet_b200.so] > profiles/r02_sass_summary.txt"""
 import collections
 import os
@@ -7,7 +7,7 @@ import re
 import subprocess
 import sys
 
-MNEMONICS = ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "HMMA", "LDGSTS")
+MNEMONICS = ("UTCHMMA", "UTMALDG", "UTMASTG", "UTMAREDG", "LDTM", "UTCBAR", "UTCATOMSWS", "SYNCS", "HMMA", "LDGSTS")
 
 
 def summarise(lib):
@@ -49,6 +49,6 @@ if __name__ == "__main__":
     for k, c in per.items():
         total.update(c)
         if sum(c.values()):
-            short = re.sub(r"\(.*", "", names[k]).replace("void vnb::", "")
+            short = re.sub(r"\(.*", "", names[k]).replace("void ", "").replace("vnb::", "")
             print("%-72s %s" % (short[:72], " ".join("%8d" % c[m] for m in MNEMONICS)))
     print("%-72s %s" % ("TOTAL", " ".join("%8d" % total[m] for m in MNEMONICS)))

@@ -73,6 +73,13 @@ inline void Engine::tc_setup() {
       wg.valid = true;
       wg_partial_floats = std::max(wg_partial_floats, wg.partial_floats);
     }
+    WdPlan& wd = u.tc.wgrad_deep;
+    if (ks == 5 && !padded_in && wd_plan_geometry(wd, NB, d.D, d.H, d.W, c1, u.Cin2, u.Cout, lo, sm_count_)) {
+      wd_encode_plan(wd, NB, x1.a_hi, x1.a_lo, u.in2 >= 0 ? acts_[u.in2].a_hi : nullptr, u.in2 >= 0 ? acts_[u.in2].a_lo : nullptr,
+                     o.d_hi, o.d_lo);
+      wd.valid = true;
+      wg_partial_floats = std::max(wg_partial_floats, wd.partial_floats);
+    }
   }
   if (wg_partial_floats) wg_partial_ = dev_alloc<float>(wg_partial_floats);
   // 2^3 stride-2 units: tcgen05 / TMA gather and scatter plans (k2_tc.cuh) over the fp32 activations and gradients
@@ -258,6 +265,10 @@ inline void Engine::tc_run_dgrad(Unit& u, int N) {
 inline void Engine::tc_run_wgrad(Unit& u, int N) {
   cudaStream_t st = wgrad_stream_begin();
   ProfScope ps(*this, 1, conv5_flops(u, N), st, &u, "wgrad");
+  if (u.tc.wgrad_deep.valid) {
+    launches_ += wd_launch(u.tc.wgrad_deep, N, wg_partial_, grads_ + u.w_off, sm_count_, st);
+    return;
+  }
   wg_launch(u.tc.wgrad, N, cfg_.precision == PREC_BF16X3, wg_partial_, grads_ + u.w_off, st, u.Cin1 + u.Cin2);
   launches_ += 2;
 }
@@ -347,7 +358,9 @@ inline bool tc_op_k2_wgrad(const float* fine, const float* coarse, float* dw, in
 inline void tc_op_wgrad5(int precision, const float* x, const float* dy, float* dw, int n, Dims dims, int cin, int cout, int ks = 5) {
   const bool lo = precision == PREC_BF16X3;
   WgPlan pl;
-  if (!wg_plan_geometry(pl, n, dims.D, dims.H, dims.W, cin, 0, cout, lo, tc_query_sms(), ks))
+  WdPlan wd;
+  const bool deep = ks == 5 && wd_plan_geometry(wd, n, dims.D, dims.H, dims.W, cin, 0, cout, lo, tc_query_sms());
+  if (!deep && !wg_plan_geometry(pl, n, dims.D, dims.H, dims.W, cin, 0, cout, lo, tc_query_sms(), ks))
     throw std::invalid_argument("shape not supported by the tensor-core wgrad (channels % 16, W in {8..128})");
   TcScratch s;
   const size_t V = static_cast<size_t>(n) * dims.D * dims.H * dims.W;
@@ -357,6 +370,14 @@ inline void tc_op_wgrad5(int precision, const float* x, const float* dy, float* 
   uint16_t* zl = lo ? s.alloc<uint16_t>(V * cout) : nullptr;
   VNB_LAUNCH(split_bf16_kernel, 1024, 256, 0, 0, x, static_cast<long long>(V * cin), xh, xl);
   VNB_LAUNCH(split_bf16_kernel, 1024, 256, 0, 0, dy, static_cast<long long>(V * cout), zh, zl);
+  if (deep) {   // per-tap GEMM form of the deep levels (wgrad_deep.cuh)
+    float* partial = s.alloc<float>(wd.partial_floats);
+    wd_encode_plan(wd, n, xh, xl, nullptr, nullptr, zh, zl);
+    wd_launch(wd, n, partial, dw, tc_query_sms(), 0);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)
+      throw std::runtime_error("CUDA: tensor-core deep-level wgrad kernel failed");
+    return;
+  }
   float* partial = s.alloc<float>(pl.partial_floats);
   wg_encode_plan(pl, n, xh, xl, nullptr, nullptr, zh, zl);
   wg_launch(pl, n, lo, partial, dw, 0);

@@ -26,6 +26,7 @@
 // warp0 = TMA producer, warp1 = MMA issuer, warps 2-5 = final TMEM read-out.
 #pragma once
 #include "conv_tc.cuh"
+#include "wgrad_deep.cuh"
 
 namespace vnb {
 
@@ -464,6 +465,7 @@ inline bool wg_plan_geometry(WgPlan& pl, int N, int D, int H, int W, int C1, int
 struct TcConvPlan {
   TcKernelPlan fprop, dgrad;
   WgPlan wgrad;
+  WdPlan wgrad_deep;   // per-tap GEMM form for the deep levels (wgrad_deep.cuh); preferred when valid
 };
 
 // P tensors: box (16, Wr+8, HT, 1, 1) over (C, W, H, D, N); SWIZZLE_32B
