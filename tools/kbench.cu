@@ -65,7 +65,7 @@ int main(int argc, char** argv) {
     if (op == "k2w" && k2tc_enabled() && k2wg_plan_geometry(wgp, N, p.cd, Cin, Cout)) {
       k2wg_encode_plan(wgp, N, p.cd, Cin, Cout, fine, coarse);
       wgp.valid = true;
-      printf("k2wg plan: tile %dx%dx%d n_mb=%d sets=%d set=%d smem=%zu tmem=%d\n", wgp.g.ow_t, wgp.g.oh_t, wgp.g.od_t, wgp.g.n_mb, wgp.g.sets,
+      printf("k2wg plan: tile %dx%dx%d n_mb=%d sets=%d set=%d smem=%zu tmem=%d\n", wgp.g.ow_t, wgp.g.oh_t, wgp.g.od_t, wgp.g.n_mb * wgp.g.n_cb, wgp.g.sets,
              wgp.g.set_bytes, wgp.smem, wgp.g.tmem_cols);
     }
     auto launch = [&]() {

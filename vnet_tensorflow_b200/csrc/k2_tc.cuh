@@ -451,7 +451,7 @@ inline void k2tc_launch(K2TcPlan& pl, int N, const float* bias, bool accumulate,
 // column (32 MN elements x 128 K rows): the four A slots / the CC/32 B slots of a set are the atoms at LBO = 16 KB, a
 // K = 16 step advances the start address by two 8-row groups (1 KB).  A CTA owns one M block and a contiguous range of
 // voxel tiles, accumulates them all into one TMEM accumulator (24 MMAs per tile: 8 K steps x 3 split passes) and adds
-// the [128][CC] result to dw with fp32 atomics (dw is zeroed by the caller; like the mma.sync kernel it replaces this
+// the [128][min(CC, 64)] result to dw with fp32 atomics (wider layers: one CTA group per 64-column block) (dw is zeroed by the caller; like the mma.sync kernel it replaces this
 // is the step's only run-to-run non-determinism, last-bit level).
 // ---------------------------------------------------------------------------------------------
 constexpr int kK2WgSlot = 16384;
@@ -459,9 +459,9 @@ constexpr int kK2WgMaxSets = 3;
 
 struct K2WgGeom {
   int ow_t, oh_t, od_t, n_tw, n_th, n_td;
-  int n_tiles, n_mb, splits;     // voxel tiles, M blocks (8 CF / 128), tile ranges per M block
+  int n_tiles, n_mb, splits;     // voxel tiles, M blocks (8 CF / 128), tile ranges per (M block, column block)
   int in_cpm;                    // 32-row chunks per (kd,kh) map = CF / 16
-  int CC, n_bc;                  // GEMM N; B chunks = CC / 32
+  int CC, NBw, n_cb, n_bc;       // coarse channels; GEMM N per CTA = min(CC, 64); column blocks; B chunks per CTA = NBw / 32
   int sets, set_bytes, tmem_cols;
 };
 
@@ -503,7 +503,9 @@ k2_wgrad_tc_kernel(const __grid_constant__ sm100::TmaDesc f0, const __grid_const
   tc_fence_after_sync();
   const uint32_t tmem = warp_uniform(*slot_ptr);
 
-  const int mb = static_cast<int>(blockIdx.x) % g.n_mb, sp = static_cast<int>(blockIdx.x) / g.n_mb;
+  const int n_pairs = g.n_mb * g.n_cb;
+  const int mb = (static_cast<int>(blockIdx.x) % n_pairs) % g.n_mb, cb = (static_cast<int>(blockIdx.x) % n_pairs) / g.n_mb;
+  const int sp = static_cast<int>(blockIdx.x) / n_pairs;
   const int t_lo = static_cast<int>(static_cast<long long>(sp) * g.n_tiles / g.splits);
   const int t_hi = static_cast<int>(static_cast<long long>(sp + 1) * g.n_tiles / g.splits);
   const int n_slots = 4 + g.n_bc;
@@ -528,7 +530,7 @@ k2_wgrad_tc_kernel(const __grid_constant__ sm100::TmaDesc f0, const __grid_const
           const TmaDesc* fm = mi == 0 ? &f0 : mi == 1 ? &f1 : mi == 2 ? &f2 : &f3;
           tma_load_4d(st + c * kK2WgSlot, fm, full(s), c0, c1, c2, c3);
         }
-        for (int j = 0; j < g.n_bc; ++j) tma_load_4d(st + (4 + j) * kK2WgSlot, &cmap, full(s), j * 32, c1, c2, c3);
+        for (int j = 0; j < g.n_bc; ++j) tma_load_4d(st + (4 + j) * kK2WgSlot, &cmap, full(s), cb * g.NBw + j * 32, c1, c2, c3);
       }
       __syncwarp();
       if (++s == g.sets) {
@@ -539,7 +541,7 @@ k2_wgrad_tc_kernel(const __grid_constant__ sm100::TmaDesc f0, const __grid_const
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     const bool leader = elect_one();
-    const uint32_t idesc = make_instr_desc(128, static_cast<uint32_t>(g.CC), FMT_BF16, 1, 1);
+    const uint32_t idesc = make_instr_desc(128, static_cast<uint32_t>(g.NBw), FMT_BF16, 1, 1);
     const uint64_t desc0 = make_smem_desc(0, kK2WgSlot, 512, SWZ_64B);   // MN-major: atoms at LBO, 8-row K groups at SBO
     int s = 0;
     uint32_t ph = 0;
@@ -607,8 +609,8 @@ k2_wgrad_tc_kernel(const __grid_constant__ sm100::TmaDesc f0, const __grid_const
     const int row = mb * 128 + q * 32 + lane;
     mbar_wait(accf, 0);
     tc_fence_after_sync();
-    float* dst = dw + static_cast<size_t>(row) * g.CC;
-    for (int j = 0; j < g.CC / 16; ++j) {
+    float* dst = dw + static_cast<size_t>(row) * g.CC + cb * g.NBw;
+    for (int j = 0; j < g.NBw / 16; ++j) {
       uint32_t v[16];
       tmem_ld16(tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(j) * 16u, v);
       tmem_ld_wait();
@@ -634,7 +636,7 @@ struct K2WgPlan {
 };
 
 inline bool k2wg_plan_geometry(K2WgPlan& pl, int N, Dims cd, int CF, int CC) {
-  if (CF <= 0 || CC <= 0 || CF % 16 != 0 || CC % 32 != 0 || CC > 256) return false;
+  if (CF <= 0 || CC <= 0 || CF % 16 != 0 || CC % 32 != 0) return false;
   K2WgGeom& g = pl.g;
   g = K2WgGeom{};
   pl.Dc = cd.D;
@@ -644,13 +646,16 @@ inline bool k2wg_plan_geometry(K2WgPlan& pl, int N, Dims cd, int CF, int CC) {
   g.n_mb = CF / 16;
   g.in_cpm = CF / 16;
   g.CC = CC;
-  g.n_bc = CC / 32;
+  g.NBw = std::min(CC, 64);
+  if (CC % g.NBw != 0) return false;
+  g.n_cb = CC / g.NBw;
+  g.n_bc = g.NBw / 32;
   g.set_bytes = (4 + g.n_bc) * kK2WgSlot;
   g.sets = std::min(kK2WgMaxSets, (227 * 1024 - kK2TcBarBytes - 1024) / g.set_bytes);
   if (g.sets < 2) return false;
   pl.smem = static_cast<size_t>(g.sets) * g.set_bytes + kK2TcBarBytes + 1024;
   g.tmem_cols = 32;
-  while (g.tmem_cols < CC) g.tmem_cols *= 2;
+  while (g.tmem_cols < g.NBw) g.tmem_cols *= 2;
   return true;
 }
 
@@ -684,8 +689,9 @@ inline void k2wg_launch(K2WgPlan& pl, int N, float* dw, int sms, cudaStream_t st
   K2WgGeom g = pl.g;
   g.n_td = static_cast<int>((static_cast<long long>(N) * pl.Dc + g.od_t - 1) / g.od_t);
   g.n_tiles = g.n_tw * g.n_th * g.n_td;
-  g.splits = std::max(1, std::min(g.n_tiles, sms / g.n_mb));
-  VNB_LAUNCH(kfn, g.n_mb * g.splits, kK2TcThreads, pl.smem, stream, pl.f[0], pl.f[1], pl.f[2], pl.f[3], pl.c, g, dw);
+  const int n_pairs = g.n_mb * g.n_cb;
+  g.splits = std::max(1, std::min(g.n_tiles, sms / n_pairs));
+  VNB_LAUNCH(kfn, n_pairs * g.splits, kK2TcThreads, pl.smem, stream, pl.f[0], pl.f[1], pl.f[2], pl.f[3], pl.c, g, dw);
 }
 
 }  // namespace vnb
