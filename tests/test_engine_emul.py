@@ -557,7 +557,10 @@ def test_loss_parts_are_the_two_summaries_of_the_mixed_losses(emul_lib, loss, we
 def test_op_hooks_k2_bn_softmax_dice_adam(emul_lib):
     from tests import op_hook_cases as H
     H.check_k2_ops(emul_lib, "fp32", 16, 32, (3, 4, 5))
-    H.check_k2_ops(emul_lib, "bf16x3", 16, 32, (2, 4, 8))       # mma.sync 3xTF32 tiles (CPU model of the warp MMA)
+    H.check_k2_ops(emul_lib, "bf16x3", 16, 32, (2, 4, 8))       # tcgen05 / TMA kernels (k2_tc.cuh) on the CPU model of the async units
+    H.check_k2_ops(emul_lib, "bf16x3", 32, 64, (3, 5, 12))      # grid that no 128-voxel box tiles exactly: zero-filled loads, clipped stores
+    H.check_k2_ops(emul_lib, "bf16x3", 64, 128, (2, 2, 4), n=1)  # scatter in two 256-column blocks, filter gradient in 64-column blocks
+    H.check_k2_ops(emul_lib, "bf16x3", 16, 24, (2, 4, 8))       # CC % 32 != 0: the mma.sync 3xTF32 tiles (CPU model of the warp MMA)
     H.check_k2_ops(emul_lib, "fp32", 4, 6, (2, 3, 2), n=1)      # channels outside the tiled kernels' domain
     H.check_bn_ops(emul_lib, 4096, 16)
     H.check_bn_ops(emul_lib, 1000, 128, with_alpha=False)

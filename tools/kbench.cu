@@ -54,8 +54,8 @@ int main(int argc, char** argv) {
     // tcgen05 / TMA form (k2_tc.cuh) unless VNB_K2_NO_TC is set; `cin2` != 0 selects the accumulating (reduce-add) epilogue
     K2TcPlan tcp;
     if (op != "k2w" && k2tc_enabled() && k2tc_plan_geometry(tcp, op == "k2s", N, p.cd, Cin, Cout)) {
-      tcp.img = s.alloc<uint16_t>((size_t)16 * Cin * Cout);
-      CK(cudaMemset(tcp.img, 0, (size_t)32 * Cin * Cout));
+      tcp.img = s.alloc<uint16_t>((size_t)24 * Cin * Cout);
+      CK(cudaMemset(tcp.img, 0, (size_t)48 * Cin * Cout));
       k2tc_encode_plan(tcp, N, p.cd, Cin, Cout, fine, coarse);
       tcp.valid = true;
       printf("k2tc plan: tile %dx%dx%d items=%d n_kc=%d NB=%d n_nb=%d stages=%d stage=%d smem=%zu tmem=%d\n", tcp.g.ow_t, tcp.g.oh_t, tcp.g.od_t,

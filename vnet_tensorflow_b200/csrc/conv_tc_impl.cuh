@@ -96,7 +96,7 @@ inline void Engine::tc_setup() {
       j.w = params_ + u.w_off;
       j.CF = CF;
       j.CC = CC;
-      const size_t img_elems = 2 * u.w_count;
+      const size_t img_elems = 3 * u.w_count;
       // fprop: down = gather (fine x -> coarse z), up = scatter (coarse x -> fine z)
       if (k2tc_plan_geometry(u.k2_fprop, !down, NB, cd, CF, CC)) {
         u.k2_fprop.img = dev_alloc<uint16_t>(img_elems);
@@ -325,7 +325,7 @@ inline bool tc_op_k2(bool scatter, float* fine, float* coarse, const float* w, c
   if (!k2tc_enabled() || !k2tc_plan_geometry(pl, scatter, n, cd, cf, cc)) return false;
   TcScratch s;
   const size_t wn = static_cast<size_t>(8) * cf * cc;
-  pl.img = s.alloc<uint16_t>(2 * wn);
+  pl.img = s.alloc<uint16_t>(3 * wn);
   K2PackJob j{};
   j.w = w;
   (scatter ? j.img_scatter : j.img_gather) = pl.img;

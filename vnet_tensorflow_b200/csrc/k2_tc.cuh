@@ -14,10 +14,13 @@
 // depth-to-space interleave happens in the tensor map's strides).  The coarse tensor uses one map of the same shape.
 //
 // The activations stay fp32 in HBM (they are read exactly once here, 4 B/element, the kernels are HBM-bound), and
-// the products are fp32-grade like the bf16x3 convolutions: a converter warpgroup splits every fp32 chunk that TMA
-// landed in shared memory into bf16 (hi, lo) K-major SWIZZLE_64B tiles, and the MMA warp issues hi*hi + lo*hi + hi*lo
-// (kind::f16, fp32 accumulate in TMEM).  The weights are pre-split once per optimiser step (k2tc_pack_multi_kernel)
-// into the [K chunk][hi|lo][N][32] images the B loads fetch.
+// the products are fp32-exact to rounding: a converter warpgroup splits every fp32 chunk that TMA landed in shared
+// memory into THREE bf16 pieces (hi, mid, lo: 3 x 8 = the 24 significant bits of an fp32, an exact decomposition) as
+// K-major SWIZZLE_64B planes, and the MMA warp issues the six products down to 2^-16 relative weight (mid*mid, lo*hi,
+// hi*lo, mid*hi, hi*mid, hi*hi; kind::f16, fp32 accumulate in TMEM) -- the tensor pipe is < 20 % busy either way, so
+// the extra passes are free and the error (~1e-7 relative) is below the 3xTF32 mma.sync kernels these replace.  The
+// weights are pre-split once per optimiser step (k2tc_pack_multi_kernel) into the [K chunk][hi|mid|lo][N][32] images
+// the B loads fetch.  (The filter-gradient kernel below keeps the two-piece split: its slots are converted in place.)
 //
 // Roles of the 320 threads: warp 0 TMA producer, warp 1 MMA issuer (owns TMEM), warps 2-5 converters (thread = row),
 // warps 6-9 epilogue (TMEM -> registers -> swizzled staging -> TMA store, or TMA reduce-add when the destination
@@ -34,6 +37,7 @@ constexpr int kK2TcA16 = 128 * 64;       // one bf16 plane of it: 128 rows x 32 
 constexpr int kK2TcOutBuf = 128 * 128;   // epilogue staging: 128 rows x 32 floats, SWIZZLE_128B
 constexpr int kK2TcMaxStages = 4;
 constexpr int kK2TcBarBytes = 256;
+constexpr int kK2TcBiasBytes = 1024;   // bias table in shared memory (<= 256 distinct channels)
 
 struct K2TcGeom {
   int ow_t, oh_t, od_t;          // tile = ow_t x oh_t x od_t = 128 coarse voxels (od over the merged (n, od) axis)
@@ -57,6 +61,27 @@ __device__ __forceinline__ void k2tc_split2(float a, float b, uint32_t& hi, uint
 #endif
 }
 
+// (a, b) -> packed bf16 pairs of the exact three-piece split x = hi + mid + lo
+__device__ __forceinline__ void k2tc_split3(float a, float b, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(rb), "f"(ra));
+  const float sa = ra - __uint_as_float(mid << 16), sb = rb - __uint_as_float(mid & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(sb), "f"(sa));
+#else
+  auto piece = [](float& x) {
+    const uint16_t h = f32_to_bf16(x);
+    x -= bf16_to_f32(h);
+    return static_cast<uint32_t>(h);
+  };
+  const uint32_t ha = piece(a), hb = piece(b), ma = piece(a), mb = piece(b), la = piece(a), lb = piece(b);
+  hi = ha | (hb << 16);
+  mid = ma | (mb << 16);
+  lo = la | (lb << 16);
+#endif
+}
+
 __global__ void __launch_bounds__(kK2TcThreads, 1)
 k2_tc_kernel(const __grid_constant__ sm100::TmaDesc in0, const __grid_constant__ sm100::TmaDesc in1,
              const __grid_constant__ sm100::TmaDesc in2, const __grid_constant__ sm100::TmaDesc in3,
@@ -68,7 +93,7 @@ k2_tc_kernel(const __grid_constant__ sm100::TmaDesc in0, const __grid_constant__
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* sm = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const uint32_t sm_addr = smem_u32(sm);
-  // layout: stages x {A fp32 | A hi | A lo | B hi | B lo} | 2 staging buffers | barriers
+  // layout: stages x {A fp32 | A hi | A mid | A lo | B hi | B mid | B lo} | 2 staging buffers | barriers | bias table
   const uint32_t out_off = static_cast<uint32_t>(g.stages) * g.stage_bytes;
   const uint32_t bar_base = sm_addr + out_off + 2 * kK2TcOutBuf;
   auto full = [&](int s) { return bar_base + 8u * s; };            // TMA landed (A fp32 + B)
@@ -79,8 +104,13 @@ k2_tc_kernel(const __grid_constant__ sm100::TmaDesc in0, const __grid_constant__
   const uint32_t slot_addr = bar_base + 8u * 16;
   volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(sm + out_off + 2 * kK2TcOutBuf + 8 * 16);
 
+  // the bias sits in shared memory: a global load per column on the epilogue's critical path cost the up convolution
+  // 118 us instead of 62 (every chunk waited a round trip through the L2 the stream itself saturates)
+  float* bias_s = reinterpret_cast<float*>(sm + out_off + 2 * kK2TcOutBuf + kK2TcBarBytes);
+
   const int tid = threadIdx.x;
   const int warp = static_cast<int>(warp_uniform(static_cast<uint32_t>(tid >> 5)));
+  if (bias != nullptr && tid < g.bias_mod) bias_s[tid] = bias[tid];
   if (tid == 0) {
     for (int s = 0; s < kK2TcMaxStages; ++s) {
       mbar_init(full(s), 1);
@@ -127,11 +157,11 @@ k2_tc_kernel(const __grid_constant__ sm100::TmaDesc in0, const __grid_constant__
           const uint32_t st = sm_addr + static_cast<uint32_t>(s) * g.stage_bytes;
           const int mi = kc / g.in_cpm, c0 = (kc % g.in_cpm) * 32;
           const TmaDesc* im = mi == 0 ? &in0 : mi == 1 ? &in1 : mi == 2 ? &in2 : &in3;
-          mbar_expect_tx(full(s), kK2TcA32 + 2u * b_plane);
+          mbar_expect_tx(full(s), kK2TcA32 + 3u * b_plane);
           tma_load_4d(st, im, full(s), c0, c1, c2, c3);
-          const int brow = kc * 2 * g.Ntot + nb * g.NB;
-          tma_load_2d(st + kK2TcA32 + 2 * kK2TcA16, &bmap, full(s), 0, brow);
-          tma_load_2d(st + kK2TcA32 + 2 * kK2TcA16 + b_plane, &bmap, full(s), 0, brow + g.Ntot);
+          const int brow = kc * 3 * g.Ntot + nb * g.NB;
+          for (int pc = 0; pc < 3; ++pc)
+            tma_load_2d(st + kK2TcA32 + 3 * kK2TcA16 + pc * b_plane, &bmap, full(s), 0, brow + pc * g.Ntot);
         }
         __syncwarp();
         if (++s == g.stages) {
@@ -156,14 +186,18 @@ k2_tc_kernel(const __grid_constant__ sm100::TmaDesc in0, const __grid_constant__
         mbar_wait_warp(conv(s), ph);
         tc_fence_after_sync();
         const uint32_t a_hi = sm_addr + static_cast<uint32_t>(s) * g.stage_bytes + kK2TcA32;
-        const uint32_t b_hi = a_hi + 2 * kK2TcA16;
-        const uint64_t dah = desc0 + (a_hi >> 4), dal = dah + (kK2TcA16 >> 4);
-        const uint64_t dbh = desc0 + (b_hi >> 4), dbl = dbh + (b_plane >> 4);
+        const uint32_t b_hi = a_hi + 3 * kK2TcA16;
+        const uint64_t a16 = kK2TcA16 >> 4, b16 = b_plane >> 4;
+        const uint64_t dah = desc0 + (a_hi >> 4), dam = dah + a16, dal = dam + a16;
+        const uint64_t dbh = desc0 + (b_hi >> 4), dbm = dbh + b16, dbl = dbm + b16;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {   // two K = 16 steps per 32-element chunk: start address + 32 bytes
           const uint64_t o = static_cast<uint64_t>(ks * 2);
-          mma_f16_ss_if(leader, d_tmem, dal + o, dbh + o, idesc, (kc | ks) != 0 ? 1u : 0u);   // small terms first
+          mma_f16_ss_if(leader, d_tmem, dam + o, dbm + o, idesc, (kc | ks) != 0 ? 1u : 0u);   // smallest terms first
+          mma_f16_ss_if(leader, d_tmem, dal + o, dbh + o, idesc, 1u);
           mma_f16_ss_if(leader, d_tmem, dah + o, dbl + o, idesc, 1u);
+          mma_f16_ss_if(leader, d_tmem, dam + o, dbh + o, idesc, 1u);
+          mma_f16_ss_if(leader, d_tmem, dah + o, dbm + o, idesc, 1u);
           mma_f16_ss_if(leader, d_tmem, dah + o, dbh + o, idesc, 1u);
         }
         mma_commit_if(leader, empty(s));
@@ -194,14 +228,15 @@ k2_tc_kernel(const __grid_constant__ sm100::TmaDesc in0, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < 4; ++q) {   // eight K elements = one 16-byte unit of each plane
           const float4 a = x[2 * q], b = x[2 * q + 1];
-          uint4 h, l;
-          k2tc_split2(a.x, a.y, h.x, l.x);
-          k2tc_split2(a.z, a.w, h.y, l.y);
-          k2tc_split2(b.x, b.y, h.z, l.z);
-          k2tc_split2(b.z, b.w, h.w, l.w);
+          uint4 h, m, l;
+          k2tc_split3(a.x, a.y, h.x, m.x, l.x);
+          k2tc_split3(a.z, a.w, h.y, m.y, l.y);
+          k2tc_split3(b.x, b.y, h.z, m.z, l.z);
+          k2tc_split3(b.z, b.w, h.w, m.w, l.w);
           const uint32_t o = dst_off + ((static_cast<uint32_t>(q) ^ sw64) << 4);
           *reinterpret_cast<uint4*>(st + o) = h;
-          *reinterpret_cast<uint4*>(st + o + kK2TcA16) = l;
+          *reinterpret_cast<uint4*>(st + o + kK2TcA16) = m;
+          *reinterpret_cast<uint4*>(st + o + 2 * kK2TcA16) = l;
         }
         fence_proxy_async_smem();   // the planes are read by the tensor core through the async proxy
         mbar_arrive(conv(s));
@@ -239,14 +274,17 @@ k2_tc_kernel(const __grid_constant__ sm100::TmaDesc in0, const __grid_constant__
         float y[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i >> 4][i & 15]);
-        if (bias) {
-          const int b0 = n0 % g.bias_mod;
+        if (bias) {   // bias_mod % 16 == 0 and n0 % 32 == 0: a group of four columns never straddles the wrap
+          int bi = n0 % g.bias_mod;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            int bi = b0 + i;
-            bi -= bi >= g.bias_mod ? g.bias_mod : 0;
-            bi -= bi >= g.bias_mod ? g.bias_mod : 0;
-            y[i] += __ldg(bias + bi);
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + bi);
+            y[4 * jj] += b4.x;
+            y[4 * jj + 1] += b4.y;
+            y[4 * jj + 2] += b4.z;
+            y[4 * jj + 3] += b4.w;
+            bi += 4;
+            bi = bi >= g.bias_mod ? bi - g.bias_mod : bi;
           }
         }
         // staging buffer jc & 1: its previous TMA store (two chunks ago) must have finished reading
@@ -278,9 +316,9 @@ k2_tc_kernel(const __grid_constant__ sm100::TmaDesc in0, const __grid_constant__
 
 // ---------------------------------------------------------------------------------------------
 // weight images: w [8 CF][CC] fp32 (TF layout [2][2][2][CF][CC]; the transposed convolution's [2][2][2][out][in] is the
-// same array) -> bf16 (hi, lo) B operands, K-major rows of 32 elements:
-//   gather  image  [kc < 8CF/32][hi|lo][cc][kk]     = w[kc*32 + kk][cc]
-//   scatter image  [kc < CC/32][hi|lo][n < 8CF][kk] = w[n][kc*32 + kk]
+// same array) -> bf16 (hi, mid, lo) B operands, K-major rows of 32 elements:
+//   gather  image  [kc < 8CF/32][hi|mid|lo][cc][kk]     = w[kc*32 + kk][cc]
+//   scatter image  [kc < CC/32][hi|mid|lo][n < 8CF][kk] = w[n][kc*32 + kk]
 // ---------------------------------------------------------------------------------------------
 struct K2PackJob {
   const float* w;
@@ -296,17 +334,19 @@ __global__ void __launch_bounds__(256) k2tc_pack_multi_kernel(const K2PackJob* _
   const int rows = 8 * j.CF, total = rows * j.CC;
   for (int e = (static_cast<int>(blockIdx.x) - j.first_block) * 256 + static_cast<int>(threadIdx.x); e < total; e += j.n_blocks * 256) {
     const int row = e / j.CC, col = e % j.CC;
-    const float v = j.w[e];
-    const uint16_t hi = f32_to_bf16(v), lo = f32_to_bf16(v - bf16_to_f32(hi));
+    float v = j.w[e];
+    uint16_t pc[3];
+    for (int k = 0; k < 3; ++k) {   // exact three-piece split
+      pc[k] = f32_to_bf16(v);
+      v -= bf16_to_f32(pc[k]);
+    }
     if (j.img_gather) {
-      const size_t o = (static_cast<size_t>(row / 32) * 2 * j.CC + col) * 32 + row % 32;
-      j.img_gather[o] = hi;
-      j.img_gather[o + static_cast<size_t>(j.CC) * 32] = lo;
+      const size_t o = (static_cast<size_t>(row / 32) * 3 * j.CC + col) * 32 + row % 32;
+      for (int k = 0; k < 3; ++k) j.img_gather[o + static_cast<size_t>(k) * j.CC * 32] = pc[k];
     }
     if (j.img_scatter) {
-      const size_t o = (static_cast<size_t>(col / 32) * 2 * rows + row) * 32 + col % 32;
-      j.img_scatter[o] = hi;
-      j.img_scatter[o + static_cast<size_t>(rows) * 32] = lo;
+      const size_t o = (static_cast<size_t>(col / 32) * 3 * rows + row) * 32 + col % 32;
+      for (int k = 0; k < 3; ++k) j.img_scatter[o + static_cast<size_t>(k) * rows * 32] = pc[k];
     }
   }
 }
@@ -319,7 +359,7 @@ struct K2TcPlan {
   bool scatter = false;
   K2TcGeom g{};
   sm100::TmaDesc in[4], out[4], b;
-  uint16_t* img = nullptr;   // weight image of this direction (8 CF CC x 2 bf16)
+  uint16_t* img = nullptr;   // weight image of this direction (8 CF CC x 3 bf16)
   size_t smem = 0;
   int Dc = 0;
   // what the tensor maps were encoded for: a launch with another batch size re-encodes them, so that the (n, od) axis
@@ -366,6 +406,9 @@ inline bool k2tc_plan_geometry(K2TcPlan& pl, bool scatter, int N, Dims cd, int C
     g.in_cpm = CF / 16;     // 2 CF / 32 chunks per (kd, kh) map
     g.Ntot = CC;
     g.NB = CC;
+    // few tiles (the deepest level: 8 tiles of 1024 coarse voxels): narrower column blocks give more, shorter items
+    // (the A chunks are then loaded and split once per block; everything sits in L2 at that size)
+    while (g.NB > 64 && g.NB % 64 == 0 && static_cast<long long>(g.n_tw) * g.n_th * g.n_td * (CC / g.NB) * 4 <= 148) g.NB /= 2;
     g.out_cpm = CC / 32;    // every output chunk through map 0
     g.bias_mod = CC;
   } else {
@@ -377,8 +420,9 @@ inline bool k2tc_plan_geometry(K2TcPlan& pl, bool scatter, int N, Dims cd, int C
     g.bias_mod = CF;
   }
   g.n_nb = g.Ntot / g.NB;
-  g.stage_bytes = ((kK2TcA32 + 2 * kK2TcA16 + 2 * g.NB * 64 + 1023) / 1024) * 1024;
-  const int fixed = 2 * kK2TcOutBuf + kK2TcBarBytes + 1024;
+  g.stage_bytes = ((kK2TcA32 + 3 * kK2TcA16 + 3 * g.NB * 64 + 1023) / 1024) * 1024;
+  if (g.bias_mod > 256 || g.bias_mod % 16 != 0) return false;
+  const int fixed = 2 * kK2TcOutBuf + kK2TcBarBytes + kK2TcBiasBytes + 1024;
   g.stages = std::min(kK2TcMaxStages, (227 * 1024 - fixed) / g.stage_bytes);
   if (g.stages < 2) return false;
   pl.smem = static_cast<size_t>(fixed) + static_cast<size_t>(g.stages) * g.stage_bytes;
@@ -417,7 +461,7 @@ inline void k2tc_encode_plan(K2TcPlan& pl, int N, Dims cd, int CF, int CC, const
   for (int t = 0; t < 4; ++t) k2tc_encode_fine(&f[t], fine, N, cd, CF, t >> 1, t & 1, pl.g);
   k2tc_encode_coarse(&c[0], coarse, N, cd, CC, pl.g);
   c[1] = c[2] = c[3] = c[0];
-  tma_encode_w(&pl.b, pl.img, static_cast<long long>(pl.g.n_kc) * 2 * pl.g.Ntot, 32, pl.g.NB);
+  tma_encode_w(&pl.b, pl.img, static_cast<long long>(pl.g.n_kc) * 3 * pl.g.Ntot, 32, pl.g.NB);
 }
 
 // launch for a batch of N (<= the plan's); `accumulate`: add into the destination (TMA reduce-add)
