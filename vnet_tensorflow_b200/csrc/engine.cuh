@@ -1202,7 +1202,7 @@ class Engine {
         } else if (v4_ok(u.Cout, V * u.Cout)) {
           const unsigned total4 = static_cast<unsigned>(V * u.Cout / 4);
           nblk = v4_blocks(total4, u.Cout);
-          VNB_LAUNCH(bn_stats_v4_kernel, nblk, 256, 0, stream_, (const float*)u.z, u.Cout, total4, partial_);
+          VNB_LAUNCH_PDL(bn_stats_v4_kernel, nblk, 256, 0, stream_, (const float*)u.z, u.Cout, total4, partial_);
           ++launches_;
         } else {
           RedGeom g = red_geom(u.Cout, 0, V);
@@ -1225,7 +1225,7 @@ class Engine {
         nblk = 1;
         count *= stats_world_;
       }
-      VNB_LAUNCH(bn_finalize_fwd_kernel, u.Cout, 128, 0, stream_, fin_partial, nblk, nq_stride,
+      VNB_LAUNCH_PDL(bn_finalize_fwd_kernel, u.Cout, 128, 0, stream_, fin_partial, nblk, nq_stride,
                  u.Cout, count, u.chain, bn_params(u), u.kind == U_INPUT_TILE ? 1 : 0,
                  update_moving ? 1 : 0, u.mean, u.var, u.scale, u.shift, u.bn_inference ? 1 : 0);
       ++launches_;
@@ -1244,7 +1244,7 @@ class Engine {
       ap.seed = seed;
       ap.unit = static_cast<uint32_t>(ui);
       if (v4_ok(u.Cout, ap.total))
-        VNB_LAUNCH(bn_apply_v4_kernel, grid_for(ap.total / 4, 256), 256, 0, stream_, ap);
+        VNB_LAUNCH_PDL(bn_apply_v4_kernel, grid_for(ap.total / 4, 256), 256, 0, stream_, ap);
       else
         VNB_LAUNCH(bn_apply_kernel, grid_for(ap.total, 256), 256, 0, stream_, ap);
       ++launches_;
@@ -1327,7 +1327,7 @@ class Engine {
       if (v4) {
         const unsigned total4 = static_cast<unsigned>(V * u.Cout / 4);
         nblk = v4_blocks(total4, u.Cout);
-        VNB_LAUNCH(bn_bwd_reduce_v4_kernel, nblk, 256, 0, stream_, b, total4, partial_);
+        VNB_LAUNCH_PDL(bn_bwd_reduce_v4_kernel, nblk, 256, 0, stream_, b, total4, partial_);
         ++launches_;
       } else {
         RedGeom g = red_geom(u.Cout, 0, V);
@@ -1351,7 +1351,7 @@ class Engine {
         gsum = global;
         nblk = 1;
       }
-      VNB_LAUNCH(bn_finalize_bwd_kernel, u.Cout, 128, 0, stream_, fin_partial, nblk, u.Cout,
+      VNB_LAUNCH_PDL(bn_finalize_bwd_kernel, u.Cout, 128, 0, stream_, fin_partial, nblk, u.Cout,
                  static_cast<double>(V), u.chain, bn_params(u), (const double*)u.var, gp, u.P, u.Q, u.S,
                  u.bn_inference ? 1 : 0, gsum, static_cast<double>(V) * stats_world_);
       ++launches_;
@@ -1360,7 +1360,7 @@ class Engine {
         continue;
       }
       if (v4)
-        VNB_LAUNCH(bn_bwd_apply_v4_kernel, grid_for(V * u.Cout / 4, 256), 256, 0, stream_, b, V * u.Cout);
+        VNB_LAUNCH_PDL(bn_bwd_apply_v4_kernel, grid_for(V * u.Cout / 4, 256), 256, 0, stream_, b, V * u.Cout);
       else
         VNB_LAUNCH(bn_bwd_apply_kernel, grid_for(V * u.Cout, 256), 256, 0, stream_, b, V * u.Cout);
       ++launches_;

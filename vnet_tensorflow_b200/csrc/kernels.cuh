@@ -200,6 +200,8 @@ __global__ void bn_finalize_fwd_kernel(const double* __restrict__ partial, int n
                                        int update_moving, double* __restrict__ mean_out,
                                        double* __restrict__ var_out, float* __restrict__ scale_out,
                                        float* __restrict__ shift_out, int inference = 0) {
+  pdl_trigger();   // see vnb_cuda.h: the next short pass may become resident now ...
+  pdl_wait();      // ... and this one reads nothing of its predecessor before that grid has completed
   const int c = blockIdx.x;  // one block per channel; threads sum the per-block partials in a fixed order
   if (inference) {  // training=False: normalise with the moving statistics (attention.py:69 fed train_phase=False)
     if (threadIdx.x != 0) return;
@@ -371,6 +373,8 @@ __global__ void bn_finalize_bwd_kernel(const double* __restrict__ partial, int n
                                        BnGradPtrs gp, float* __restrict__ P, float* __restrict__ Q,
                                        float* __restrict__ S, int inference = 0,
                                        const double* __restrict__ gsum = nullptr, double gcount = 0.0) {
+  pdl_trigger();   // see vnb_cuda.h: the next short pass may become resident now ...
+  pdl_wait();      // ... and this one reads nothing of its predecessor before that grid has completed
   const int c = blockIdx.x;  // one block per channel
   __shared__ double fin_red[3][128];
   double p0 = 0, p1 = 0, p2 = 0;
@@ -861,6 +865,8 @@ __device__ __forceinline__ void store_hi_lo4(uint16_t* hi, uint16_t* lo, unsigne
 }
 
 __global__ void __launch_bounds__(256) bn_apply_v4_kernel(ApplyArgs p) {
+  pdl_trigger();   // see vnb_cuda.h: the next short pass may become resident now ...
+  pdl_wait();      // ... and this one reads nothing of its predecessor before that grid has completed
   const unsigned total4 = static_cast<unsigned>(p.total / 4), C4 = static_cast<unsigned>(p.C / 4);
   const float keep_scale = dropout_keep_scale(p.drop_rate);
   const uint32_t dkey = dropout_key(p.seed, p.unit), dthr = dropout_threshold(p.drop_rate);
@@ -928,6 +934,8 @@ __device__ __forceinline__ void bwd_g4(const BwdArgs& p, unsigned i, unsigned c,
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_v4_kernel(BwdArgs p, long long total) {
+  pdl_trigger();   // see vnb_cuda.h: the next short pass may become resident now ...
+  pdl_wait();      // ... and this one reads nothing of its predecessor before that grid has completed
   const unsigned total4 = static_cast<unsigned>(total / 4), C4 = static_cast<unsigned>(p.C / 4);
   const float4* __restrict__ z4 = reinterpret_cast<const float4*>(p.z);
 #pragma unroll 2
@@ -1032,6 +1040,8 @@ __device__ __forceinline__ void block_channel_combine_v4(float (&acc)[NQ][4], un
 
 __global__ void __launch_bounds__(256) bn_stats_v4_kernel(const float* __restrict__ z, int C, unsigned total4,
                                                           double* __restrict__ partial) {
+  pdl_trigger();   // see vnb_cuda.h: the next short pass may become resident now ...
+  pdl_wait();      // ... and this one reads nothing of its predecessor before that grid has completed
   const unsigned C4 = static_cast<unsigned>(C / 4);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   // thread t keeps channel quad t % C4 because the stride gridDim*256 is a multiple of C4
@@ -1045,6 +1055,8 @@ __global__ void __launch_bounds__(256) bn_stats_v4_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_v4_kernel(BwdArgs p, unsigned total4, double* __restrict__ partial) {
+  pdl_trigger();   // see vnb_cuda.h: the next short pass may become resident now ...
+  pdl_wait();      // ... and this one reads nothing of its predecessor before that grid has completed
   const unsigned C4 = static_cast<unsigned>(p.C / 4);
   const unsigned c = (threadIdx.x % C4) * 4;
   const float mu[4] = {static_cast<float>(p.mean[c]), static_cast<float>(p.mean[c + 1]), static_cast<float>(p.mean[c + 2]),

@@ -16,8 +16,47 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #define VNB_HD __host__ __device__ __forceinline__
+
+// Programmatic dependent launch for the chains of short HBM-bound passes (statistics -> finalize -> apply): a kernel
+// launched with VNB_LAUNCH_PDL may become resident while its predecessor in the stream is still running; it calls
+// pdl_wait() before it touches anything the predecessor wrote (the wait returns when that grid has completed and its
+// writes are visible) and pdl_trigger() to let its own successor do the same.  Saves the launch latency at every
+// boundary of such a chain; VNB_NO_PDL=1 launches them the ordinary way.
+#ifdef VNB_EMULATE
+#define VNB_LAUNCH_PDL VNB_LAUNCH
+namespace vnb {
+inline void pdl_wait() {}
+inline void pdl_trigger() {}
+}  // namespace vnb
+#else
+namespace vnb {
+inline bool pdl_enabled() {
+  static const bool on = getenv("VNB_NO_PDL") == nullptr;
+  return on;
+}
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+}  // namespace vnb
+#define VNB_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) \
+  vnb::launch_pdl(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__)
+#endif
 
 namespace vnb {
 
